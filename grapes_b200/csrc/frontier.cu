@@ -1,0 +1,564 @@
+// Frontier expansion, bitmap dedup, rank relabel, induced-block extraction and the
+// dst-sorted (deterministic) CSR build used by the aggregation kernels.
+//
+// Replaces, on the device, the scipy/torch CPU code of the reference:
+//   get_neighborhoods           /root/reference/modules/utils.py:74-82
+//   mask dedup + id lists       /root/reference/main.py:183-191
+//   TensorMap.update / .map     /root/reference/modules/utils.py:98-120
+//   slice_adjacency             /root/reference/modules/utils.py:85-95
+// All outputs are bit-exact with those (ordering contracts in DESIGN.md section 3).
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------
+// k_row_offsets: one block.  rows[P] -> row_off[P+1] (exclusive scan of CSR degrees), m.
+// Marks bm_rows (every row) and bm_batch (rows with degree > 0: a row with no neighbours never
+// shows up in `neighborhoods`, main.py:186, so it is not a batch node).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_row_offsets(const int64_t* __restrict__ indptr,
+                                                      const int* __restrict__ rows,
+                                                      const int* __restrict__ P_dev, int cap_P,
+                                                      int* __restrict__ row_off, int* __restrict__ m_out,
+                                                      int cap_m, uint32_t* bm_rows, uint32_t* bm_batch,
+                                                      int* overflow) {
+    __shared__ long long s_scan[34];
+    int P = *P_dev;
+    if (P > cap_P) { P = cap_P; if (threadIdx.x == 0) atomicOr(overflow, GRAPES_OVF_ROWS); }
+    long long carry = 0;
+    for (int base = 0; base < P; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        long long deg = 0;
+        if (i < P) {
+            const int r = rows[i];
+            deg = indptr[r + 1] - indptr[r];
+            if (bm_rows) bitmap_set(bm_rows, r);
+            if (bm_batch && deg > 0) bitmap_set(bm_batch, r);
+        }
+        long long total;
+        const long long excl = block_scan_excl<long long>(deg, s_scan, &total);
+        if (i < P) row_off[i] = (int)min(carry + excl, (long long)cap_m);
+        carry += total;
+    }
+    if (threadIdx.x == 0) {
+        if (carry > cap_m) { atomicOr(overflow, GRAPES_OVF_EDGES); carry = cap_m; }
+        row_off[P] = (int)carry;
+        *m_out = (int)carry;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_expand: edge-balanced CSR row gather.  Slot e of the concatenated neighbour lists belongs
+// to row i = upper_bound(row_off, e) - 1; adjacent threads read adjacent `indices` entries.
+// Emits (e_row = position in rows, e_col = neighbour global id) and marks bm_batch.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_expand(const int64_t* __restrict__ indptr,
+                                                const int* __restrict__ indices,
+                                                const int* __restrict__ rows, const int* __restrict__ P_dev,
+                                                int cap_P, const int* __restrict__ row_off,
+                                                const int* __restrict__ m_dev,
+                                                int* __restrict__ e_row, int* __restrict__ e_col,
+                                                uint32_t* bm_batch) {
+    const int P = min(*P_dev, cap_P);
+    const int m = *m_dev;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < m; e += gridDim.x * blockDim.x) {
+        int lo = 0, hi = P;                       // largest i with row_off[i] <= e
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(&row_off[mid]) <= e) lo = mid; else hi = mid;
+        }
+        const int r = rows[lo];
+        const int v = indices[indptr[r] + (e - row_off[lo])];
+        e_row[e] = lo;
+        e_col[e] = v;
+        if (bm_batch) bitmap_set(bm_batch, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_rank_scan: single-pass scan over the node bitmap.  For every word: exclusive popcount
+// prefix (pref_batch; pref_nb for batch & ~prev).  Enumerates the set bits in ascending id
+// order, which IS the reference's local numbering (mask -> nonzero, main.py:189-195):
+//   batch_nodes[j] = v, nb_nodes[q] = v, nb_local[q] = j, ind_bits[j] = indicator columns of v.
+// bm_ind row `hop` receives batch & ~prev (indicator[neighbor_nodes, hop] = 1, main.py:191).
+// ---------------------------------------------------------------------------------------
+#define RANK_THREADS 256
+#define RANK_WPT 4
+#define RANK_TILE (RANK_THREADS * RANK_WPT)
+
+__global__ void __launch_bounds__(RANK_THREADS) k_rank_scan(
+    const uint32_t* __restrict__ bm_batch, const uint32_t* __restrict__ bm_prev, int W,
+    int* __restrict__ pref_batch, int* __restrict__ pref_nb, int* __restrict__ batch_nodes,
+    int* __restrict__ nb_nodes, int* __restrict__ nb_local, uint32_t* __restrict__ ind_bits,
+    uint32_t* bm_ind, int ind_rows, int hop, int cap_n, int* __restrict__ n_out,
+    int* __restrict__ c_out, int* overflow, unsigned long long* status, unsigned int* counters) {
+    __shared__ unsigned long long s_scan[RANK_THREADS / 32 + 2];
+    __shared__ int s_tile;
+    __shared__ unsigned long long s_excl;
+    __shared__ int s_last;
+    if (threadIdx.x == 0) s_tile = lb_take_ticket(counters);
+    __syncthreads();
+    const int tile = s_tile;
+    const int w0 = tile * RANK_TILE + threadIdx.x * RANK_WPT;
+    uint32_t b[RANK_WPT], p[RANK_WPT];
+    unsigned long long mine = 0ull;
+#pragma unroll
+    for (int i = 0; i < RANK_WPT; ++i) {
+        const int w = w0 + i;
+        b[i] = (w < W) ? bm_batch[w] : 0u;
+        p[i] = (w < W && bm_prev) ? bm_prev[w] : 0u;
+        mine += ((unsigned long long)__popc(b[i]) << 31) | (unsigned long long)__popc(b[i] & ~p[i]);
+    }
+    unsigned long long total;
+    const unsigned long long excl_in_tile = block_scan_excl<unsigned long long>(mine, s_scan, &total);
+    const bool nonempty = tile * RANK_TILE < W;
+    if (threadIdx.x < 32) {
+        unsigned long long ex = 0ull;
+        if (nonempty) ex = lb_exclusive(status, tile, total);
+        if (threadIdx.x == 0) { s_excl = ex; s_last = lb_finish(counters) ? 1 : 0; }
+    }
+    __syncthreads();
+    if (nonempty) {
+        const unsigned long long pre = s_excl + excl_in_tile;
+        int rb = (int)(pre >> 31), rn = (int)(pre & 0x7fffffffull);
+#pragma unroll
+        for (int i = 0; i < RANK_WPT; ++i) {
+            const int w = w0 + i;
+            if (w >= W) break;
+            pref_batch[w] = rb;
+            if (pref_nb) pref_nb[w] = rn;
+            uint32_t bits = b[i];
+            const uint32_t nbits = bits & ~p[i];
+            if (bm_ind) bm_ind[(size_t)hop * W + w] = nbits;
+            uint32_t ind_w[8];
+            if (ind_bits && bits) {
+#pragma unroll
+                for (int h = 0; h < 8; ++h) {
+                    ind_w[h] = 0u;
+                    if (h < ind_rows - 1 && h < hop) ind_w[h] = bm_ind[(size_t)h * W + w];
+                    if (h == hop && h < ind_rows - 1) ind_w[h] = nbits;
+                    if (h == ind_rows - 1) ind_w[h] = bm_ind[(size_t)h * W + w];
+                }
+            }
+            while (bits) {
+                const int t = __ffs(bits) - 1;
+                bits &= bits - 1u;
+                const int v = (w << 5) + t;
+                const int j = rb++;
+                if (j < cap_n) {
+                    batch_nodes[j] = v;
+                    if (ind_bits) {
+                        uint32_t ib = 0u;
+#pragma unroll
+                        for (int h = 0; h < 8; ++h) ib |= ((ind_w[h] >> t) & 1u) << h;
+                        ind_bits[j] = ib;
+                    }
+                }
+                if ((nbits >> t) & 1u) {
+                    const int q = rn++;
+                    if (q < cap_n && nb_nodes) { nb_nodes[q] = v; nb_local[q] = j; }
+                }
+            }
+        }
+        if ((W - 1) / RANK_TILE == tile && threadIdx.x == RANK_THREADS - 1) {
+            // last thread of the last non-empty tile holds the grand totals
+            const unsigned long long tot = s_excl + total;
+            int n = (int)(tot >> 31), c = (int)(tot & 0x7fffffffull);
+            if (n > cap_n) { atomicOr(overflow, GRAPES_OVF_NODES); n = cap_n; if (c > cap_n) c = cap_n; }
+            *n_out = n;
+            if (c_out) *c_out = c;
+        }
+    }
+    if (s_last) lb_cleanup(status, counters);
+}
+
+// ---------------------------------------------------------------------------------------
+// k_edge_local: global (row position, neighbour id) -> local (src, dst) ids = TensorMap.map of
+// `neighborhoods` (main.py:195).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_edge_local(const int* __restrict__ rows,
+                                                    const int* __restrict__ e_row,
+                                                    const int* __restrict__ e_col,
+                                                    const int* __restrict__ m_dev,
+                                                    const uint32_t* __restrict__ bm,
+                                                    const int* __restrict__ pref,
+                                                    int* __restrict__ e_src, int* __restrict__ e_dst) {
+    const int m = *m_dev;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < m; e += gridDim.x * blockDim.x) {
+        e_src[e] = bitmap_rank(bm, pref, rows[e_row[e]]);
+        e_dst[e] = bitmap_rank(bm, pref, e_col[e]);
+    }
+}
+
+// k_relabel: out[i] = rank(ids[i])  (TensorMap.map on an arbitrary id list, main.py:213,253-254,259)
+__global__ void __launch_bounds__(256) k_relabel(const int* __restrict__ ids, const int* __restrict__ cnt_dev,
+                                                 int cap, const uint32_t* __restrict__ bm,
+                                                 const int* __restrict__ pref, int* __restrict__ out) {
+    const int n = min(*cnt_dev, cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        out[i] = bitmap_rank(bm, pref, ids[i]);
+}
+
+// ---------------------------------------------------------------------------------------
+// CSR build from a (key, val) edge list with self-loop edges (key == val) dropped -- what
+// add_remaining_self_loops does before it appends its own loops.
+//   k_hist: cnt[key]++           k_scan_i32: off = exclusive scan(cnt) (+ dinv = (cnt+1)^-1/2)
+//   k_fill: slot claim            k_sort_rows / k_sort_hub: ascending val inside each row, so
+// the summation order of every aggregation is fixed (run-to-run deterministic, no fp atomics).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_hist(const int* __restrict__ key, const int* __restrict__ val,
+                                              const int* __restrict__ E_dev, int cap_E, int* cnt) {
+    const int E = min(*E_dev, cap_E);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+        const int k = key[e];
+        if (k != val[e]) atomicAdd(&cnt[k], 1);
+    }
+}
+
+#define SCAN_THREADS 256
+#define SCAN_IPT 4
+#define SCAN_TILE (SCAN_THREADS * SCAN_IPT)
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_i32(const int* __restrict__ in,
+                                                           const int* __restrict__ n_dev, int cap_n,
+                                                           int* __restrict__ out, float* __restrict__ dinv,
+                                                           int* __restrict__ total_out,
+                                                           unsigned long long* status, unsigned int* counters) {
+    __shared__ unsigned long long s_scan[SCAN_THREADS / 32 + 2];
+    __shared__ int s_tile;
+    __shared__ unsigned long long s_excl;
+    __shared__ int s_last;
+    if (threadIdx.x == 0) s_tile = lb_take_ticket(counters);
+    __syncthreads();
+    const int tile = s_tile;
+    const int n = min(*n_dev, cap_n);
+    const int i0 = tile * SCAN_TILE + threadIdx.x * SCAN_IPT;
+    int v[SCAN_IPT];
+    unsigned long long mine = 0ull;
+#pragma unroll
+    for (int i = 0; i < SCAN_IPT; ++i) {
+        v[i] = (i0 + i < n) ? in[i0 + i] : 0;
+        mine += (unsigned long long)v[i];
+    }
+    unsigned long long total;
+    const unsigned long long excl_in_tile = block_scan_excl<unsigned long long>(mine, s_scan, &total);
+    const bool nonempty = (tile * SCAN_TILE < n) || (tile == 0);
+    if (threadIdx.x < 32) {
+        unsigned long long ex = 0ull;
+        if (nonempty) ex = lb_exclusive(status, tile, total);
+        if (threadIdx.x == 0) { s_excl = ex; s_last = lb_finish(counters) ? 1 : 0; }
+    }
+    __syncthreads();
+    if (nonempty) {
+        int run = (int)(s_excl + excl_in_tile);
+#pragma unroll
+        for (int i = 0; i < SCAN_IPT; ++i) {
+            const int idx = i0 + i;
+            if (idx < n) {
+                out[idx] = run;
+                if (dinv) dinv[idx] = 1.0f / sqrtf((float)(v[i] + 1));
+                run += v[i];
+            }
+        }
+        const int last_tile = (n == 0) ? 0 : (n - 1) / SCAN_TILE;
+        if (tile == last_tile && threadIdx.x == SCAN_THREADS - 1) {
+            const int tot = (int)(s_excl + total);
+            out[n] = tot;
+            if (total_out) *total_out = tot;
+        }
+    }
+    if (s_last) lb_cleanup(status, counters);
+}
+
+// claim slots from the back of each row; leaves cnt[] all-zero again
+__global__ void __launch_bounds__(256) k_fill(const int* __restrict__ key, const int* __restrict__ val,
+                                              const int* __restrict__ E_dev, int cap_E,
+                                              const int* __restrict__ off, int* cnt, int* __restrict__ out_val) {
+    const int E = min(*E_dev, cap_E);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+        const int k = key[e], v = val[e];
+        if (k != v) {
+            const int pos = off[k] + atomicSub(&cnt[k], 1) - 1;
+            out_val[pos] = v;
+        }
+    }
+}
+
+#define SORT_SMALL 32
+__global__ void __launch_bounds__(256) k_sort_rows(const int* __restrict__ off, const int* __restrict__ n_dev,
+                                                   int cap_n, int* vals, int* hub_rows, int* hub_count,
+                                                   int hub_cap, int* overflow) {
+    const int n = min(*n_dev, cap_n);
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const int beg = off[j], len = off[j + 1] - beg;
+        if (len < 2) continue;
+        if (len > SORT_SMALL) {
+            const int slot = atomicAdd(hub_count, 1);
+            if (slot < hub_cap) hub_rows[slot] = j; else atomicOr(overflow, GRAPES_OVF_HUB);
+            continue;
+        }
+        int* a = vals + beg;
+        for (int i = 1; i < len; ++i) {                      // insertion sort, rows are short
+            const int x = a[i];
+            int k = i - 1;
+            while (k >= 0 && a[k] > x) { a[k + 1] = a[k]; --k; }
+            a[k + 1] = x;
+        }
+    }
+}
+
+// one block per hub row: rank sort (values inside a row are distinct or ties are harmless)
+__global__ void __launch_bounds__(256) k_sort_hub(const int* __restrict__ off, int* vals, int* tmp,
+                                                  const int* __restrict__ hub_rows, int* hub_count, int hub_cap) {
+    const int nh = min(*hub_count, hub_cap);
+    for (int h = blockIdx.x; h < nh; h += gridDim.x) {
+        const int j = hub_rows[h];
+        const int beg = off[j], len = off[j + 1] - beg;
+        const int* a = vals + beg;
+        for (int i = threadIdx.x; i < len; i += blockDim.x) {
+            const int x = a[i];
+            int r = 0;
+            for (int t = 0; t < len; ++t) {
+                const int y = a[t];
+                r += (y < x) || (y == x && t < i);
+            }
+            tmp[beg + r] = x;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < len; i += blockDim.x) vals[beg + i] = tmp[beg + i];
+        __syncthreads();
+    }
+}
+__global__ void k_reset_counter(int* c) { *c = 0; }
+
+// ---------------------------------------------------------------------------------------
+// k_filter_compact: ordered stream compaction of the expanded edge list by membership of the
+// neighbour in a column bitmap == slice_adjacency(adjacency, rows, cols) (utils.py:85-95):
+// row-major by position in rows, ascending neighbour id inside a row, GLOBAL ids out.
+// ---------------------------------------------------------------------------------------
+#define FC_THREADS 256
+#define FC_IPT 4
+#define FC_TILE (FC_THREADS * FC_IPT)
+
+__global__ void __launch_bounds__(FC_THREADS) k_filter_compact(
+    const int* __restrict__ rows, const int* __restrict__ e_row, const int* __restrict__ e_col,
+    const int* __restrict__ m_dev, int cap_m, const uint32_t* __restrict__ bm_cols,
+    int* __restrict__ out_src, int* __restrict__ out_dst, int cap_out, int* __restrict__ count_out,
+    int* overflow, unsigned long long* status, unsigned int* counters) {
+    __shared__ unsigned long long s_scan[FC_THREADS / 32 + 2];
+    __shared__ int s_tile;
+    __shared__ unsigned long long s_excl;
+    __shared__ int s_last;
+    if (threadIdx.x == 0) s_tile = lb_take_ticket(counters);
+    __syncthreads();
+    const int tile = s_tile;
+    const int m = min(*m_dev, cap_m);
+    const int i0 = tile * FC_TILE + threadIdx.x * FC_IPT;
+    int col[FC_IPT];
+    bool keep[FC_IPT];
+    unsigned long long mine = 0ull;
+#pragma unroll
+    for (int i = 0; i < FC_IPT; ++i) {
+        const int e = i0 + i;
+        keep[i] = false;
+        col[i] = 0;
+        if (e < m) { col[i] = e_col[e]; keep[i] = bitmap_test(bm_cols, col[i]); }
+        mine += keep[i] ? 1ull : 0ull;
+    }
+    unsigned long long total;
+    const unsigned long long excl_in_tile = block_scan_excl<unsigned long long>(mine, s_scan, &total);
+    const bool nonempty = (tile * FC_TILE < m) || (tile == 0);
+    if (threadIdx.x < 32) {
+        unsigned long long ex = 0ull;
+        if (nonempty) ex = lb_exclusive(status, tile, total);
+        if (threadIdx.x == 0) { s_excl = ex; s_last = lb_finish(counters) ? 1 : 0; }
+    }
+    __syncthreads();
+    if (nonempty) {
+        int run = (int)(s_excl + excl_in_tile);
+#pragma unroll
+        for (int i = 0; i < FC_IPT; ++i) {
+            if (keep[i]) {
+                if (run < cap_out) { out_src[run] = rows[e_row[i0 + i]]; out_dst[run] = col[i]; }
+                ++run;
+            }
+        }
+        const int last_tile = (m == 0) ? 0 : (m - 1) / FC_TILE;
+        if (tile == last_tile && threadIdx.x == FC_THREADS - 1) {
+            int tot = (int)(s_excl + total);
+            if (tot > cap_out) { atomicOr(overflow, GRAPES_OVF_BLOCK); tot = cap_out; }
+            *count_out = tot;
+        }
+    }
+    if (s_last) lb_cleanup(status, counters);
+}
+
+// ---------------------------------------------------------------------------------------
+// small list <-> bitmap utilities
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bitmap_set_list(const int* __restrict__ ids, const int* __restrict__ cnt_dev,
+                                                         int cap, uint32_t* bm) {
+    const int n = min(*cnt_dev, cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) bitmap_set(bm, ids[i]);
+}
+__global__ void __launch_bounds__(256) k_bitmap_clear_list(const int* __restrict__ ids, const int* __restrict__ cnt_dev,
+                                                           int cap, uint32_t* bm) {
+    const int n = min(*cnt_dev, cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) bm[ids[i] >> 5] = 0u;
+}
+// dst[off .. off+n) = src[0..n); *total = off + n   (next-hop assembly, main.py:236-238)
+__global__ void __launch_bounds__(256) k_append_list(const int* __restrict__ src, const int* __restrict__ cnt_dev,
+                                                     int cap, int* __restrict__ dst, int off, int* total) {
+    const int n = min(*cnt_dev, cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[off + i] = src[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && total) *total = off + n;
+}
+__global__ void __launch_bounds__(256) k_i64_to_i32(const int64_t* __restrict__ in, int* __restrict__ out, int n,
+                                                    int* count_out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = (int)in[i];
+    if (count_out && blockIdx.x == 0 && threadIdx.x == 0) *count_out = n;
+}
+__global__ void __launch_bounds__(256) k_i32_to_i64(const int* __restrict__ in, const int* __restrict__ cnt_dev,
+                                                    int cap, int64_t* __restrict__ out) {
+    const int n = cnt_dev ? min(*cnt_dev, cap) : cap;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = (int64_t)in[i];
+}
+
+// =======================================================================================
+// C ABI
+// =======================================================================================
+static inline int grid_for(const grapes_ctx* ctx, long long work, int threads, int per_sm = 8) {
+    long long b = (work + threads - 1) / threads;
+    long long cap = (long long)ctx->sm_count * per_sm;
+    if (b < 1) b = 1;
+    return (int)(b < cap ? b : cap);
+}
+
+extern "C" {
+
+int grapes_row_offsets(grapes_ctx* ctx, const int64_t* indptr, const int* rows, const int* P_dev, int cap_P,
+                       int* row_off, int* m_dev, int cap_m, uint32_t* bm_rows, uint32_t* bm_batch,
+                       int* overflow, void* stream) {
+    GRAPES_REQUIRE(ctx && indptr && rows && P_dev && row_off && m_dev && overflow, "null argument");
+    k_row_offsets<<<1, 1024, 0, (cudaStream_t)stream>>>(indptr, rows, P_dev, cap_P, row_off, m_dev, cap_m,
+                                                          bm_rows, bm_batch, overflow);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+int grapes_expand_rows(grapes_ctx* ctx, const int64_t* indptr, const int* indices, const int* rows,
+                       const int* P_dev, int cap_P, const int* row_off, const int* m_dev, int cap_m,
+                       int* e_row, int* e_col, uint32_t* bm_batch, void* stream) {
+    GRAPES_REQUIRE(ctx && indptr && indices && rows && P_dev && row_off && m_dev && e_row && e_col, "null argument");
+    k_expand<<<grid_for(ctx, cap_m, 256), 256, 0, (cudaStream_t)stream>>>(indptr, indices, rows, P_dev, cap_P,
+                                                                          row_off, m_dev, e_row, e_col, bm_batch);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+int grapes_rank_nodes(grapes_ctx* ctx, const uint32_t* bm_batch, const uint32_t* bm_prev, int* pref_batch,
+                      int* pref_nb, int* batch_nodes, int* nb_nodes, int* nb_local, uint32_t* ind_bits,
+                      uint32_t* bm_ind, int ind_rows, int hop, int cap_n, int* n_dev, int* c_dev,
+                      int* overflow, void* stream) {
+    GRAPES_REQUIRE(ctx && bm_batch && pref_batch && batch_nodes && n_dev && overflow, "null argument");
+    GRAPES_REQUIRE(ind_rows >= 0 && ind_rows <= 8, "at most 8 indicator columns (sampling_hops <= 7)");
+    GRAPES_REQUIRE(!ind_bits || bm_ind, "ind_bits needs bm_ind");
+    GRAPES_REQUIRE(!nb_nodes || (nb_local && pref_nb && c_dev), "nb_nodes needs nb_local, pref_nb, c_dev");
+    const int tiles = grapes_div_up(ctx->num_words, RANK_TILE);
+    GRAPES_REQUIRE(tiles <= ctx->scan_cap_tiles, "scan scratch too small");
+    k_rank_scan<<<tiles, RANK_THREADS, 0, (cudaStream_t)stream>>>(
+        bm_batch, bm_prev, ctx->num_words, pref_batch, pref_nb, batch_nodes, nb_nodes, nb_local, ind_bits,
+        bm_ind, ind_rows, hop, cap_n, n_dev, c_dev, overflow, ctx->scan_status, ctx->scan_counters);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+int grapes_edges_to_local(grapes_ctx* ctx, const int* rows, const int* e_row, const int* e_col, const int* m_dev,
+                          int cap_m, const uint32_t* bm, const int* pref, int* e_src, int* e_dst, void* stream) {
+    GRAPES_REQUIRE(ctx && rows && e_row && e_col && m_dev && bm && pref && e_src && e_dst, "null argument");
+    k_edge_local<<<grid_for(ctx, cap_m, 256), 256, 0, (cudaStream_t)stream>>>(rows, e_row, e_col, m_dev, bm, pref,
+                                                                              e_src, e_dst);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+int grapes_relabel(grapes_ctx* ctx, const int* ids, const int* count_dev, int cap, const uint32_t* bm,
+                   const int* pref, int* out, void* stream) {
+    GRAPES_REQUIRE(ctx && ids && count_dev && bm && pref && out, "null argument");
+    k_relabel<<<grid_for(ctx, cap, 256), 256, 0, (cudaStream_t)stream>>>(ids, count_dev, cap, bm, pref, out);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+int grapes_build_csr(grapes_ctx* ctx, const int* key, const int* val, const int* E_dev, int cap_E,
+                     const int* n_dev, int cap_n, int* cnt_scratch, int* off, int* sorted_val, int* tmp_val,
+                     float* dinv, int* nnz_dev, int* overflow, void* stream) {
+    GRAPES_REQUIRE(ctx && key && val && E_dev && n_dev && cnt_scratch && off && sorted_val && tmp_val && overflow,
+                   "null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int tiles = grapes_div_up(cap_n, SCAN_TILE);
+    GRAPES_REQUIRE(tiles <= ctx->scan_cap_tiles, "scan scratch too small for cap_n");
+    GRAPES_CUDA_OK(cudaMemsetAsync(cnt_scratch, 0, sizeof(int) * (size_t)cap_n, s));
+    k_hist<<<grid_for(ctx, cap_E, 256), 256, 0, s>>>(key, val, E_dev, cap_E, cnt_scratch);
+    k_scan_i32<<<grapes_max_i(tiles, 1), SCAN_THREADS, 0, s>>>(cnt_scratch, n_dev, cap_n, off, dinv, nnz_dev,
+                                                              ctx->scan_status, ctx->scan_counters);
+    k_fill<<<grid_for(ctx, cap_E, 256), 256, 0, s>>>(key, val, E_dev, cap_E, off, cnt_scratch, sorted_val);
+    k_reset_counter<<<1, 1, 0, s>>>(ctx->hub_count);
+    k_sort_rows<<<grid_for(ctx, cap_n, 256), 256, 0, s>>>(off, n_dev, cap_n, sorted_val, ctx->hub_rows,
+                                                          ctx->hub_count, ctx->hub_cap, overflow);
+    k_sort_hub<<<ctx->sm_count, 256, 0, s>>>(off, sorted_val, tmp_val, ctx->hub_rows, ctx->hub_count, ctx->hub_cap);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+int grapes_slice_block(grapes_ctx* ctx, const int* rows, const int* e_row, const int* e_col, const int* m_dev,
+                       int cap_m, const uint32_t* bm_cols, int* out_src, int* out_dst, int cap_out,
+                       int* count_dev, int* overflow, void* stream) {
+    GRAPES_REQUIRE(ctx && rows && e_row && e_col && m_dev && bm_cols && out_src && out_dst && count_dev && overflow,
+                   "null argument");
+    const int tiles = grapes_max_i(grapes_div_up(cap_m, FC_TILE), 1);
+    GRAPES_REQUIRE(tiles <= ctx->scan_cap_tiles, "scan scratch too small for cap_m");
+    k_filter_compact<<<tiles, FC_THREADS, 0, (cudaStream_t)stream>>>(rows, e_row, e_col, m_dev, cap_m, bm_cols,
+                                                                     out_src, out_dst, cap_out, count_dev, overflow,
+                                                                     ctx->scan_status, ctx->scan_counters);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+int grapes_bitmap_set(grapes_ctx* ctx, const int* ids, const int* count_dev, int cap, uint32_t* bm, void* stream) {
+    GRAPES_REQUIRE(ctx && ids && count_dev && bm, "null argument");
+    k_bitmap_set_list<<<grid_for(ctx, cap, 256), 256, 0, (cudaStream_t)stream>>>(ids, count_dev, cap, bm);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+int grapes_bitmap_clear_words(grapes_ctx* ctx, const int* ids, const int* count_dev, int cap, uint32_t* bm,
+                              void* stream) {
+    GRAPES_REQUIRE(ctx && ids && count_dev && bm, "null argument");
+    k_bitmap_clear_list<<<grid_for(ctx, cap, 256), 256, 0, (cudaStream_t)stream>>>(ids, count_dev, cap, bm);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+int grapes_append_list(grapes_ctx* ctx, const int* src, const int* count_dev, int cap, int* dst, int dst_offset,
+                       int* total_dev, void* stream) {
+    GRAPES_REQUIRE(ctx && src && count_dev && dst, "null argument");
+    k_append_list<<<grid_for(ctx, cap, 256), 256, 0, (cudaStream_t)stream>>>(src, count_dev, cap, dst, dst_offset,
+                                                                             total_dev);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+int grapes_ids_i64_to_i32(grapes_ctx* ctx, const int64_t* in, int n, int* out, int* count_dev, void* stream) {
+    GRAPES_REQUIRE(ctx && out && (in || n == 0), "null argument");
+    k_i64_to_i32<<<grid_for(ctx, n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, n, count_dev);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+int grapes_ids_i32_to_i64(grapes_ctx* ctx, const int* in, const int* count_dev, int cap, int64_t* out, void* stream) {
+    GRAPES_REQUIRE(ctx && out && (in || cap == 0), "null argument");
+    k_i32_to_i64<<<grid_for(ctx, cap, 256), 256, 0, (cudaStream_t)stream>>>(in, count_dev, cap, out);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+}  // extern "C"

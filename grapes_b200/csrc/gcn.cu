@@ -1,0 +1,640 @@
+// gcn_norm + GCNConv aggregation (deterministic CSR SpMM, no fp atomics) and the fp32 SIMT GEMMs.
+//
+// Restates on the device what PyG 2.5.2 GCNConv does for the reference's call sites
+// (/root/reference/modules/gcn.py:18,21,32,36):
+//   out = D^-1/2 (A_noloop + I) D^-1/2 (X W^T) + b,  deg = in-degree incl. the added self-loop.
+// Aggregation commutes with the dense transform, so it is done at the NARROWER width
+// (features for layer 1, the scalar / class logits for layer 2) -- DESIGN.md section 4.
+#include "common.cuh"
+
+template <int VEC> struct VecT;
+template <> struct VecT<1> { typedef float T; };
+template <> struct VecT<2> { typedef float2 T; };
+template <> struct VecT<4> { typedef float4 T; };
+
+template <int VEC>
+__device__ __forceinline__ void vec_fma(float (&acc)[VEC], float w, const float* p) {
+    typename VecT<VEC>::T v = *reinterpret_cast<const typename VecT<VEC>::T*>(p);
+    const float* f = reinterpret_cast<const float*>(&v);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = fmaf(w, f[i], acc[i]);
+}
+
+// ---------------------------------------------------------------------------------------
+// k_agg: one warp per destination row j (local id).
+//   out[j, :F] = dinv[j]^2 * X[g(j), :F] + sum_{s in in(j)} dinv[s] dinv[j] * X[g(s), :F]   (+bias)(relu)
+//   g(j) = nodes[j] (feature gather fused: reads global feature rows directly, main.py:198-204)
+//          or j when nodes == nullptr (plain SpMM on a local matrix).
+//   out[j, F + t] (t < num_ind) = the same aggregation of indicator bit t (ind_bits), i.e. the
+//   indicator_features columns of main.py:199-202 without materialising the N x (hops+1) matrix.
+//   Columns [F + num_ind, ldo) are zero-filled (K padding for the GEMM).
+// Sources are preloaded 32 at a time and broadcast by shuffle so the dependent chain
+// in_src -> nodes -> X is paid once per 32 sources.
+// ---------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256) k_agg(const float* __restrict__ X, int F, int ldx,
+                                             const int* __restrict__ nodes, const int* __restrict__ n_dev, int cap_n,
+                                             const int* __restrict__ in_off, const int* __restrict__ in_src,
+                                             const float* __restrict__ dinv, const uint32_t* __restrict__ ind_bits,
+                                             int num_ind, const float* __restrict__ bias, int relu,
+                                             float* __restrict__ out, int ldo) {
+    const int n = min(*n_dev, cap_n);
+    const int lane = lane_id();
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n; j += warps) {
+        const float dj = dinv[j];
+        const int beg = in_off[j], end = in_off[j + 1];
+        const size_t gj = nodes ? (size_t)nodes[j] : (size_t)j;
+        const float* xj = X + gj * ldx;
+        float* oj = out + (size_t)j * ldo;
+        for (int cb = 0; cb < F; cb += 32 * VEC) {           // warp-uniform trip count
+            const int c0 = cb + lane * VEC;
+            const bool act = c0 < F;
+            float acc[VEC];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+            if (act) vec_fma<VEC>(acc, dj * dj, xj + c0);
+            for (int pb = beg; pb < end; pb += 32) {
+                const int p = pb + lane;
+                float w = 0.f; unsigned long long sg = 0ull;
+                if (p < end) {
+                    const int sl = in_src[p];
+                    w = dinv[sl] * dj;
+                    sg = nodes ? (unsigned long long)nodes[sl] : (unsigned long long)sl;
+                }
+                const int cnt = min(32, end - pb);
+                for (int t = 0; t < cnt; ++t) {
+                    const float wt = __shfl_sync(GRAPES_FULL_MASK, w, t);
+                    const unsigned long long st = __shfl_sync(GRAPES_FULL_MASK, sg, t);
+                    if (act) vec_fma<VEC>(acc, wt, X + (size_t)st * ldx + c0);
+                }
+            }
+            if (act) {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    float v = acc[i];
+                    if (bias) v += bias[c0 + i];
+                    if (relu) v = fmaxf(v, 0.f);
+                    acc[i] = v;
+                }
+                *reinterpret_cast<typename VecT<VEC>::T*>(oj + c0) = *reinterpret_cast<typename VecT<VEC>::T*>(acc);
+            }
+        }
+        if (ldo > F) {
+            float a = 0.f;
+            if (lane < num_ind) {
+                a = dj * dj * (float)((ind_bits[j] >> lane) & 1u);
+                for (int p = beg; p < end; ++p) {
+                    const int sl = in_src[p];
+                    a = fmaf(dinv[sl] * dj, (float)((ind_bits[sl] >> lane) & 1u), a);
+                }
+            }
+            for (int c = F + lane; c < ldo; c += 32) oj[c] = (c < F + num_ind) ? a : 0.f;
+        }
+    }
+}
+
+// scalar (width-1) aggregation, one thread per row:  out[j] = dinv[j]^2 z[j] + sum w z[src] + bias
+// optional `zero_out[j] = 0` clears a companion vector in the same pass.
+__global__ void __launch_bounds__(256) k_agg_scalar(const float* __restrict__ z, const int* __restrict__ n_dev,
+                                                    int cap_n, const int* __restrict__ in_off,
+                                                    const int* __restrict__ in_src, const float* __restrict__ dinv,
+                                                    const float* __restrict__ bias, float* __restrict__ out,
+                                                    float* __restrict__ zero_out) {
+    const int n = min(*n_dev, cap_n);
+    const float b = bias ? bias[0] : 0.f;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const float dj = dinv[j];
+        float a = dj * dj * z[j];
+        const int end = in_off[j + 1];
+        for (int p = in_off[j]; p < end; ++p) {
+            const int sl = in_src[p];
+            a = fmaf(dinv[sl] * dj, z[sl], a);
+        }
+        out[j] = a + b;
+        if (zero_out) zero_out[j] = 0.f;
+    }
+}
+
+// Transposed scalar aggregation for the hop graph, using the row-major edge list the expansion
+// already produced (row i of `row_off` = edges whose SOURCE is prev position i):
+//   dz[j]  = dinv[j]^2 dl[j]                                   for every row j          (k_dz_self)
+//   dz[s] += sum_{e in row i, dst != s} dinv[s] dinv[dst] dl[dst]   s = e_src of row i   (k_dz_rows)
+__global__ void __launch_bounds__(256) k_dz_self(const float* __restrict__ dl, const int* __restrict__ n_dev, int cap_n,
+                                                 const float* __restrict__ dinv, float* __restrict__ dz) {
+    const int n = min(*n_dev, cap_n);
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+        dz[j] = dinv[j] * dinv[j] * dl[j];
+}
+__global__ void __launch_bounds__(256) k_dz_rows(const float* __restrict__ dl, const int* __restrict__ P_dev, int cap_P,
+                                                 const int* __restrict__ row_off, const int* __restrict__ e_src,
+                                                 const int* __restrict__ e_dst, const float* __restrict__ dinv,
+                                                 float* __restrict__ dz) {
+    const int P = min(*P_dev, cap_P);
+    const int lane = lane_id();
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < P; i += warps) {
+        const int beg = row_off[i], end = row_off[i + 1];
+        if (beg >= end) continue;
+        const int s = e_src[beg];
+        float a = 0.f;
+        for (int e = beg + lane; e < end; e += 32) {
+            const int d = e_dst[e];
+            if (d != s) a = fmaf(dinv[d], dl[d], a);
+        }
+        a = warp_sum(a);
+        if (lane == 0) dz[s] += dinv[s] * a;
+    }
+}
+
+// v[j] = 1 / n for j < n  (d mean(logits) / d logits, main.py:228)
+__global__ void __launch_bounds__(256) k_fill_inv_count(float* __restrict__ v, const int* __restrict__ n_dev, int cap_n) {
+    const int n = min(*n_dev, cap_n);
+    const float inv = n > 0 ? 1.0f / (float)n : 0.f;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) v[j] = inv;
+}
+
+// ---------------------------------------------------------------------------------------
+// Deterministic reductions
+// ---------------------------------------------------------------------------------------
+// out[c] (+)= scale * sum_r part[r*ld + c], r < R (R from device or host)
+__global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ part, const int* __restrict__ R_dev, int R_cap,
+                                                int ld, int C, float scale, int accumulate, float* __restrict__ out) {
+    const int R = R_dev ? min(*R_dev, R_cap) : R_cap;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+        float a = 0.f;
+        for (int r = 0; r < R; ++r) a += part[(size_t)r * ld + c];
+        a *= scale;
+        out[c] = accumulate ? out[c] + a : a;
+    }
+}
+
+// column sums of a tall matrix M[R x C] in two deterministic stages: slab partials, then k_colsum
+__global__ void __launch_bounds__(256) k_colsum_slabs(const float* __restrict__ Mx, const int* __restrict__ R_dev,
+                                                      int R_cap, int ld, int C, float* __restrict__ part) {
+    const int R = min(*R_dev, R_cap);
+    const int slabs = gridDim.y;
+    const int rows_per = (R + slabs - 1) / slabs;
+    const int r0 = blockIdx.y * rows_per, r1 = min(R, r0 + rows_per);
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+        float a = 0.f;
+        for (int r = r0; r < r1; ++r) a += Mx[(size_t)r * ld + c];
+        part[(size_t)blockIdx.y * C + c] = a;
+    }
+}
+
+// block-wide deterministic sum of a vector with a device-side length:  *out (+)= scale * sum(v)/ (divide_by_n ? n : 1)
+__global__ void __launch_bounds__(1024) k_vec_sum(const float* __restrict__ v, const int* __restrict__ n_dev, int cap_n,
+                                                  float scale, int divide_by_n, int accumulate, float* out) {
+    __shared__ float s[32];
+    const int n = min(*n_dev, cap_n);
+    float a = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a += v[i];
+    a = warp_sum(a);
+    if (lane_id() == 0) s[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = (threadIdx.x < (blockDim.x >> 5)) ? s[threadIdx.x] : 0.f;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) {
+            t *= scale;
+            if (divide_by_n) t = (n > 0) ? t / (float)n : 0.f;
+            *out = accumulate ? *out + t : t;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// fp32 SIMT tile GEMM: 128x128x16 CTA tile, 256 threads, 8x8 per thread (two 4-wide groups 64 apart
+// so the float4 shared loads are bank-conflict free).  Operands may be K-contiguous ("KC":
+// T[m*ld + k]) or MN-contiguous (T[k*ld + m]).  The tcgen05 path (gemm_tc.cu) replaces this for the
+// sampler-layer shapes; this one stays as the generic / small-shape fallback ON THE DEVICE.
+// ---------------------------------------------------------------------------------------
+#define GB_M 128
+#define GB_N 128
+#define GB_K 16
+#define G_THREADS 256
+#define G_PAD 4
+
+template <bool KC>
+__device__ __forceinline__ void load_tile(const float* __restrict__ T, int ld, int mn0, int MN, int k0, int k1,
+                                          float (*S)[GB_M + G_PAD]) {
+    // fills S[kk][mm] = T(mn0 + mm, k0 + kk), zero outside [0,MN) x [k0,k1)
+    const int tid = threadIdx.x;
+    if (KC) {
+        const int mm = tid >> 1, kk0 = (tid & 1) * 8;
+        const int mrow = mn0 + mm;
+        const float* src = T + (size_t)mrow * ld + k0 + kk0;
+        const bool vec = ((ld & 3) == 0) && ((((size_t)T) & 15) == 0) && ((k0 & 3) == 0);
+        if (mrow < MN && vec && k0 + kk0 + 8 <= k1) {
+            const float4 a = *reinterpret_cast<const float4*>(src);
+            const float4 b = *reinterpret_cast<const float4*>(src + 4);
+            S[kk0 + 0][mm] = a.x; S[kk0 + 1][mm] = a.y; S[kk0 + 2][mm] = a.z; S[kk0 + 3][mm] = a.w;
+            S[kk0 + 4][mm] = b.x; S[kk0 + 5][mm] = b.y; S[kk0 + 6][mm] = b.z; S[kk0 + 7][mm] = b.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int k = k0 + kk0 + i;
+                S[kk0 + i][mm] = (mrow < MN && k < k1) ? src[i] : 0.f;
+            }
+        }
+    } else {
+        const int mm = (tid & 31) * 4;
+        const bool vec = ((ld & 3) == 0) && ((((size_t)T) & 15) == 0) && ((mn0 & 3) == 0);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int kk = (tid >> 5) + r * 8;
+            const int k = k0 + kk;
+            const float* src = T + (size_t)k * ld + mn0 + mm;
+            if (k < k1 && vec && mn0 + mm + 4 <= MN) {
+                const float4 a = *reinterpret_cast<const float4*>(src);
+                S[kk][mm] = a.x; S[kk][mm + 1] = a.y; S[kk][mm + 2] = a.z; S[kk][mm + 3] = a.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) S[kk][mm + i] = (k < k1 && mn0 + mm + i < MN) ? src[i] : 0.f;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ int g_row(int ty, int r) { return (r < 4) ? ty * 4 + r : 64 + ty * 4 + (r - 4); }
+__device__ __forceinline__ int g_col(int tx, int c) { return (c < 4) ? tx * 4 + c : 64 + tx * 4 + (c - 4); }
+
+// acc += A(m0.., k0..k1) * B(n0.., k0..k1)^T
+template <bool A_KC, bool B_KC>
+__device__ __forceinline__ void gemm_mainloop(const float* __restrict__ A, int lda, int m0, int M,
+                                              const float* __restrict__ B, int ldb, int n0, int N, int k0, int k1,
+                                              float (*As)[GB_M + G_PAD], float (*Bs)[GB_N + G_PAD],
+                                              float (&acc)[8][8]) {
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    for (int k = k0; k < k1; k += GB_K) {
+        load_tile<A_KC>(A, lda, m0, M, k, k1, As);
+        load_tile<B_KC>(B, ldb, n0, N, k, k1, Bs);
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GB_K; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(a[r], b[c], acc[r][c]);
+        }
+        __syncthreads();
+    }
+}
+
+// Generic C[M x N] = A * B^T-like product (+bias[n]) (relu) (* mask: C = (G > 0) ? C : 0).
+// M may come from the device (M_dev).  grid = (tiles_n, tiles_m_cap).
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(G_THREADS) k_gemm(const float* __restrict__ A, int lda, const float* __restrict__ B,
+                                                    int ldb, float* __restrict__ C, int ldc,
+                                                    const int* __restrict__ M_dev, int M_cap, int N, int K,
+                                                    const float* __restrict__ bias, int relu,
+                                                    const float* __restrict__ relu_gate, int ldg) {
+    __shared__ __align__(16) float As[GB_K][GB_M + G_PAD];
+    __shared__ __align__(16) float Bs[GB_K][GB_N + G_PAD];
+    const int M = M_dev ? min(*M_dev, M_cap) : M_cap;
+    const int n0 = blockIdx.x * GB_N;
+    for (int m0 = blockIdx.y * GB_M; m0 < M; m0 += gridDim.y * GB_M) {
+        float acc[8][8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+        gemm_mainloop<A_KC, B_KC>(A, lda, m0, M, B, ldb, n0, N, 0, K, As, Bs, acc);
+        const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int row = m0 + g_row(ty, r);
+            if (row >= M) continue;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int col = n0 + g_col(tx, c);
+                if (col >= N) continue;
+                float v = acc[r][c];
+                if (bias) v += bias[col];
+                if (relu) v = fmaxf(v, 0.f);
+                if (relu_gate) v = (relu_gate[(size_t)row * ldg + col] > 0.f) ? v : 0.f;
+                C[(size_t)row * ldc + col] = v;
+            }
+        }
+    }
+}
+
+// Split-K "TN" product for weight gradients:  P[slab][M x N] = sum_{r in slab} A[r, m] * B[r, n]
+// (A: R x M row-major, B: R x N row-major, R = rows from the device).  grid = (tiles_n, tiles_m, slabs).
+// Slab boundaries are multiples of GB_K so the summation order does not depend on the grid.
+__global__ void __launch_bounds__(G_THREADS) k_gemm_tn_splitk(const float* __restrict__ A, int lda,
+                                                              const float* __restrict__ B, int ldb,
+                                                              const int* __restrict__ R_dev, int R_cap, int M, int N,
+                                                              float* __restrict__ part) {
+    __shared__ __align__(16) float As[GB_K][GB_M + G_PAD];
+    __shared__ __align__(16) float Bs[GB_K][GB_N + G_PAD];
+    const int R = R_dev ? min(*R_dev, R_cap) : R_cap;
+    const int slabs = gridDim.z;
+    int rows_per = (R + slabs - 1) / slabs;
+    rows_per = ((rows_per + GB_K - 1) / GB_K) * GB_K;
+    const int r0 = min(R, (int)blockIdx.z * rows_per), r1 = min(R, r0 + rows_per);
+    const int m0 = blockIdx.y * GB_M, n0 = blockIdx.x * GB_N;
+    float acc[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+    gemm_mainloop<false, false>(A, lda, m0, M, B, ldb, n0, N, r0, r1, As, Bs, acc);
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    float* P = part + (size_t)blockIdx.z * M * N;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int row = m0 + g_row(ty, r);
+        if (row >= M) continue;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int col = n0 + g_col(tx, c);
+            if (col < N) P[(size_t)row * N + col] = acc[r][c];
+        }
+    }
+}
+
+// out[i] (+)= scale * sum_s part[s*size + i]
+__global__ void __launch_bounds__(256) k_reduce_slabs(const float* __restrict__ part, int slabs, int size, float scale,
+                                                      int accumulate, float* __restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < size; i += gridDim.x * blockDim.x) {
+        float a = 0.f;
+        for (int s = 0; s < slabs; ++s) a += part[(size_t)s * size + i];
+        a *= scale;
+        out[i] = accumulate ? out[i] + a : a;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Sampler-network layer 1+2 fused around the GEMM (out_dim == 1: gcn_gf and gcn_z, main.py:112-114).
+//   forward : z[j]   = sum_d relu(Y[j,:] . W1[d,:] + b1[d]) * w2[d]           (hidden never stored)
+//   backward: recompute pre = Y W1^T + b1;  dpre[j,d] = dz[j] * w2[d] * [pre > 0]      -> dpre (n x D)
+//             dw2_part[cta][d] = sum_j dz[j] relu(pre[j,d]);  db1_part[cta][d] = sum_j dpre[j,d]
+// One CTA owns 128 rows and walks the hidden dimension in chunks of 128.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(G_THREADS) k_l1_fwd(const float* __restrict__ Y, int ldy, const int* __restrict__ n_dev,
+                                                      int cap_n, int K, const float* __restrict__ W1, int ldw, int D,
+                                                      const float* __restrict__ b1, const float* __restrict__ w2,
+                                                      float* __restrict__ z) {
+    __shared__ __align__(16) float As[GB_K][GB_M + G_PAD];
+    __shared__ __align__(16) float Bs[GB_K][GB_N + G_PAD];
+    const int n = min(*n_dev, cap_n);
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    for (int m0 = blockIdx.x * GB_M; m0 < n; m0 += gridDim.x * GB_M) {
+        float zrow[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) zrow[r] = 0.f;
+        for (int n0 = 0; n0 < D; n0 += GB_N) {
+            float acc[8][8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+            gemm_mainloop<true, true>(Y, ldy, m0, n, W1, ldw, n0, D, 0, K, As, Bs, acc);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int col = n0 + g_col(tx, c);
+                const float bb = (col < D) ? b1[col] : 0.f;
+                const float ww = (col < D) ? w2[col] : 0.f;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) zrow[r] = fmaf(fmaxf(acc[r][c] + bb, 0.f), ww, zrow[r]);
+            }
+        }
+        // reduce over the 16 tx lanes that share a row (contiguous half-warp)
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            float v = zrow[r];
+            v += __shfl_xor_sync(GRAPES_FULL_MASK, v, 8);
+            v += __shfl_xor_sync(GRAPES_FULL_MASK, v, 4);
+            v += __shfl_xor_sync(GRAPES_FULL_MASK, v, 2);
+            v += __shfl_xor_sync(GRAPES_FULL_MASK, v, 1);
+            const int row = m0 + g_row(ty, r);
+            if (tx == 0 && row < n) z[row] = v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(G_THREADS) k_l1_bwd(const float* __restrict__ Y, int ldy, const int* __restrict__ n_dev,
+                                                      int cap_n, int K, const float* __restrict__ W1, int ldw, int D,
+                                                      const float* __restrict__ b1, const float* __restrict__ w2,
+                                                      const float* __restrict__ dz, float* __restrict__ dpre, int ldd,
+                                                      float* __restrict__ dw2_part, float* __restrict__ db1_part) {
+    __shared__ __align__(16) float As[GB_K][GB_M + G_PAD];
+    __shared__ __align__(16) float Bs[GB_K][GB_N + G_PAD];
+    __shared__ float red[16][GB_N];
+    const int n = min(*n_dev, cap_n);
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    // per-CTA partial sums over all the row tiles this CTA walks (fixed order -> deterministic)
+    for (int n0 = 0; n0 < D; n0 += GB_N) {
+        float pw2[8], pb1[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { pw2[c] = 0.f; pb1[c] = 0.f; }
+        for (int m0 = blockIdx.x * GB_M; m0 < n; m0 += gridDim.x * GB_M) {
+            float acc[8][8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+            gemm_mainloop<true, true>(Y, ldy, m0, n, W1, ldw, n0, D, 0, K, As, Bs, acc);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int row = m0 + g_row(ty, r);
+                const float g = (row < n) ? dz[row] : 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int col = n0 + g_col(tx, c);
+                    if (col >= D) continue;
+                    const float pre = acc[r][c] + b1[col];
+                    const float o = fmaxf(pre, 0.f);
+                    const float d = (pre > 0.f) ? g * w2[col] : 0.f;
+                    pw2[c] = fmaf(g, o, pw2[c]);
+                    pb1[c] += d;
+                    if (row < n) dpre[(size_t)row * ldd + col] = d;
+                }
+            }
+        }
+        // reduce the 16 ty groups column-wise through shared memory, in a fixed order
+        for (int which = 0; which < 2; ++which) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) red[ty][g_col(tx, c)] = which ? pb1[c] : pw2[c];
+            __syncthreads();
+            if (threadIdx.x < GB_N) {
+                float a = 0.f;
+#pragma unroll
+                for (int t = 0; t < 16; ++t) a += red[t][threadIdx.x];
+                const int col = n0 + threadIdx.x;
+                if (col < D) (which ? db1_part : dw2_part)[(size_t)blockIdx.x * D + col] = a;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// =======================================================================================
+// C ABI
+// =======================================================================================
+static inline int grid_for(const grapes_ctx* ctx, long long work, int threads, int per_sm = 8) {
+    long long b = (work + threads - 1) / threads;
+    long long cap = (long long)ctx->sm_count * per_sm;
+    if (b < 1) b = 1;
+    return (int)(b < cap ? b : cap);
+}
+
+extern "C" {
+
+int grapes_aggregate(grapes_ctx* ctx, const float* X, int F, int ldx, const int* nodes, const int* n_dev, int cap_n,
+                     const int* in_off, const int* in_src, const float* dinv, const uint32_t* ind_bits, int num_ind,
+                     const float* bias, int relu, float* out, int ldo, void* stream) {
+    GRAPES_REQUIRE(ctx && X && n_dev && in_off && in_src && dinv && out, "null argument");
+    GRAPES_REQUIRE(ldo >= F + num_ind, "ldo too small");
+    GRAPES_REQUIRE(num_ind == 0 || ind_bits, "indicator columns need ind_bits");
+    GRAPES_REQUIRE(num_ind <= 8, "at most 8 indicator columns");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int blocks = grid_for(ctx, (long long)cap_n * 32, 256, 8);
+    const bool a16 = ((((size_t)X) | ((size_t)out)) & 15) == 0;
+    const bool a8 = ((((size_t)X) | ((size_t)out)) & 7) == 0;
+    if (a16 && (F % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0))
+        k_agg<4><<<blocks, 256, 0, s>>>(X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias,
+                                        relu, out, ldo);
+    else if (a8 && (F % 2 == 0) && (ldx % 2 == 0) && (ldo % 2 == 0))
+        k_agg<2><<<blocks, 256, 0, s>>>(X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias,
+                                        relu, out, ldo);
+    else
+        k_agg<1><<<blocks, 256, 0, s>>>(X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias,
+                                        relu, out, ldo);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+int grapes_aggregate_scalar(grapes_ctx* ctx, const float* z, const int* n_dev, int cap_n, const int* in_off,
+                            const int* in_src, const float* dinv, const float* bias, float* out, float* zero_out,
+                            void* stream) {
+    GRAPES_REQUIRE(ctx && z && n_dev && in_off && in_src && dinv && out, "null argument");
+    k_agg_scalar<<<grid_for(ctx, cap_n, 256), 256, 0, (cudaStream_t)stream>>>(z, n_dev, cap_n, in_off, in_src, dinv,
+                                                                              bias, out, zero_out);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+int grapes_aggregate_scalar_T(grapes_ctx* ctx, const float* dl, const int* n_dev, int cap_n, const int* P_dev,
+                              int cap_P, const int* row_off, const int* e_src, const int* e_dst, const float* dinv,
+                              float* dz, void* stream) {
+    GRAPES_REQUIRE(ctx && dl && n_dev && P_dev && row_off && e_src && e_dst && dinv && dz, "null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    k_dz_self<<<grid_for(ctx, cap_n, 256), 256, 0, s>>>(dl, n_dev, cap_n, dinv, dz);
+    k_dz_rows<<<grid_for(ctx, (long long)cap_P * 32, 256), 256, 0, s>>>(dl, P_dev, cap_P, row_off, e_src, e_dst, dinv,
+                                                                         dz);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+int grapes_fill_inv_count(grapes_ctx* ctx, float* v, const int* n_dev, int cap_n, void* stream) {
+    GRAPES_REQUIRE(ctx && v && n_dev, "null argument");
+    k_fill_inv_count<<<grid_for(ctx, cap_n, 256), 256, 0, (cudaStream_t)stream>>>(v, n_dev, cap_n);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+int grapes_vec_sum(grapes_ctx* ctx, const float* v, const int* n_dev, int cap_n, float scale, int divide_by_n,
+                   int accumulate, float* out, void* stream) {
+    GRAPES_REQUIRE(ctx && v && n_dev && out, "null argument");
+    k_vec_sum<<<1, 1024, 0, (cudaStream_t)stream>>>(v, n_dev, cap_n, scale, divide_by_n, accumulate, out);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+// layout: bit0 = A is K-contiguous, bit1 = B is K-contiguous
+int grapes_gemm(grapes_ctx* ctx, int layout, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                const int* M_dev, int M_cap, int N, int K, const float* bias, int relu, const float* relu_gate,
+                int ldg, void* stream) {
+    GRAPES_REQUIRE(ctx && A && B && C, "null argument");
+    GRAPES_REQUIRE(M_cap >= 0 && N > 0 && K > 0, "bad shape");
+    if (M_cap == 0) return GRAPES_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int tiles_n = grapes_div_up(N, GB_N);
+    int tiles_m = grapes_div_up(M_cap, GB_M);
+    const int max_y = grapes_max_i(1, (ctx->sm_count * 4) / tiles_n);
+    tiles_m = grapes_min_i(tiles_m, max_y);
+    dim3 grid(tiles_n, tiles_m);
+    switch (layout & 3) {
+        case 3: k_gemm<true, true><<<grid, G_THREADS, 0, s>>>(A, lda, B, ldb, C, ldc, M_dev, M_cap, N, K, bias, relu, relu_gate, ldg); break;
+        case 1: k_gemm<true, false><<<grid, G_THREADS, 0, s>>>(A, lda, B, ldb, C, ldc, M_dev, M_cap, N, K, bias, relu, relu_gate, ldg); break;
+        case 2: k_gemm<false, true><<<grid, G_THREADS, 0, s>>>(A, lda, B, ldb, C, ldc, M_dev, M_cap, N, K, bias, relu, relu_gate, ldg); break;
+        default: k_gemm<false, false><<<grid, G_THREADS, 0, s>>>(A, lda, B, ldb, C, ldc, M_dev, M_cap, N, K, bias, relu, relu_gate, ldg); break;
+    }
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+// out[M x N] (+)= scale * A[R x M]^T B[R x N]   (weight gradients; deterministic split over rows)
+int grapes_gemm_tn(grapes_ctx* ctx, const float* A, int lda, const float* B, int ldb, const int* R_dev, int R_cap,
+                   int M, int N, float scale, int accumulate, float* out, void* stream) {
+    GRAPES_REQUIRE(ctx && A && B && out, "null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int tiles_n = grapes_div_up(N, GB_N), tiles_m = grapes_div_up(M, GB_M);
+    int slabs = grapes_max_i(1, ctx->sm_count / (tiles_n * tiles_m));
+    slabs = grapes_min_i(slabs, grapes_max_i(1, grapes_div_up(R_cap, 4 * GB_K)));
+    const size_t need = (size_t)slabs * M * N * sizeof(float);
+    GRAPES_REQUIRE(need <= ctx->partials_bytes, "split-K partial buffer too small");
+    dim3 grid(tiles_n, tiles_m, slabs);
+    k_gemm_tn_splitk<<<grid, G_THREADS, 0, s>>>(A, lda, B, ldb, R_dev, R_cap, M, N, ctx->partials);
+    k_reduce_slabs<<<grid_for(ctx, (long long)M * N, 256), 256, 0, s>>>(ctx->partials, slabs, M * N, scale, accumulate,
+                                                                       out);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+// out[c] (+)= scale * sum_r Mx[r, c]
+int grapes_colsum(grapes_ctx* ctx, const float* Mx, const int* R_dev, int R_cap, int ld, int C, float scale,
+                  int accumulate, float* out, void* stream) {
+    GRAPES_REQUIRE(ctx && Mx && out, "null argument");
+    GRAPES_REQUIRE(R_dev != nullptr, "R_dev required");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int slabs = grapes_max_i(1, grapes_min_i(ctx->sm_count, grapes_div_up(R_cap, 64)));
+    GRAPES_REQUIRE((size_t)slabs * C * sizeof(float) <= ctx->partials_bytes, "partial buffer too small");
+    dim3 grid(grapes_div_up(C, 256), slabs);
+    k_colsum_slabs<<<grid, 256, 0, s>>>(Mx, R_dev, R_cap, ld, C, ctx->partials);
+    k_colsum<<<grapes_div_up(C, 256), 256, 0, s>>>(ctx->partials, nullptr, slabs, C, C, scale, accumulate, out);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+int grapes_sampler_l1_fwd(grapes_ctx* ctx, const float* Y, int ldy, const int* n_dev, int cap_n, int K,
+                          const float* W1, int ldw, int D, const float* b1, const float* w2, float* z, void* stream) {
+    GRAPES_REQUIRE(ctx && Y && n_dev && W1 && b1 && w2 && z, "null argument");
+    const int blocks = grapes_max_i(1, grapes_min_i(grapes_div_up(cap_n, GB_M), ctx->sm_count * 2));
+    k_l1_fwd<<<blocks, G_THREADS, 0, (cudaStream_t)stream>>>(Y, ldy, n_dev, cap_n, K, W1, ldw, D, b1, w2, z);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+// Gradient DIRECTION of sum(dz . z) w.r.t. (W1, b1, w2): accumulated (+=, times `scale`) into gW1/gb1/gw2.
+int grapes_sampler_l1_bwd(grapes_ctx* ctx, const float* Y, int ldy, const int* n_dev, int cap_n, int K,
+                          const float* W1, int ldw, int D, const float* b1, const float* w2, const float* dz,
+                          float* dpre_scratch, float scale, int accumulate, float* gW1, int ldgw, float* gb1,
+                          float* gw2, void* stream) {
+    GRAPES_REQUIRE(ctx && Y && n_dev && W1 && b1 && w2 && dz && dpre_scratch && gW1 && gb1 && gw2, "null argument");
+    GRAPES_REQUIRE(ldgw == K, "gW1 must be dense [D x K]");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int blocks = grapes_max_i(1, grapes_min_i(grapes_div_up(cap_n, GB_M), ctx->sm_count));
+    GRAPES_REQUIRE((size_t)2 * blocks * D * sizeof(float) <= ctx->partials_bytes, "partial buffer too small");
+    float* dw2_part = ctx->partials;
+    float* db1_part = ctx->partials + (size_t)blocks * D;
+    k_l1_bwd<<<blocks, G_THREADS, 0, s>>>(Y, ldy, n_dev, cap_n, K, W1, ldw, D, b1, w2, dz, dpre_scratch, D, dw2_part,
+                                          db1_part);
+    // a CTA whose first tile is past n writes zeros (its loops do not run), so all `blocks` rows are valid
+    k_colsum<<<grapes_div_up(D, 256), 256, 0, s>>>(dw2_part, nullptr, blocks, D, D, scale, accumulate, gw2);
+    k_colsum<<<grapes_div_up(D, 256), 256, 0, s>>>(db1_part, nullptr, blocks, D, D, scale, accumulate, gb1);
+    GRAPES_LAUNCH_OK();
+    // gW1[D x K] += scale * dpre^T Y   (uses ctx->partials again, stream-ordered after the colsums)
+    return grapes_gemm_tn(ctx, dpre_scratch, D, Y, ldy, n_dev, cap_n, D, K, scale, accumulate, gW1, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,202 @@
+// Classifier loss (+ its gradient w.r.t. the logits), the GFlowNet / REINFORCE loss wiring and Adam,
+// as device-resident kernels so a whole GRAPES step can be replayed as one CUDA graph.
+//   CrossEntropyLoss / BCEWithLogitsLoss + reg_param * sum(var(logits, dim=1))   main.py:120-123,260-261
+//   trajectory-balance / REINFORCE loss                                          main.py:271-282
+//   torch.optim.Adam (defaults betas=(0.9,0.999), eps=1e-8, no weight decay)     main.py:117-118
+#include "common.cuh"
+
+#define LOSS_THREADS 1024
+
+__device__ __forceinline__ float block_sum_1024(float v, float* s) {
+    v = warp_sum(v);
+    if (lane_id() == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = (threadIdx.x < (blockDim.x >> 5)) ? s[threadIdx.x] : 0.f;
+    if (threadIdx.x < 32) { r = warp_sum(r); if (threadIdx.x == 0) s[0] = r; }
+    __syncthreads();
+    r = s[0];
+    __syncthreads();
+    return r;
+}
+
+// logits [A x C] (ld = ldl).  Target rows: row_ids[B] (local ids of the target nodes, main.py:259).
+// labels: int64 class ids per GLOBAL node (multiclass) or float [N x C] (multilabel), indexed by targets[B].
+// dlogits must be zeroed by the caller (grapes_classifier_loss does it).
+__global__ void __launch_bounds__(LOSS_THREADS) k_classifier_loss(
+    const float* __restrict__ logits, int ldl, int C, const int* __restrict__ A_dev, int A_cap,
+    const int* __restrict__ row_ids, const int* __restrict__ targets, int B, const int64_t* __restrict__ labels_i64,
+    const float* __restrict__ labels_f32, float reg_param, float* __restrict__ dlogits, float* loss_out) {
+    __shared__ float s[32];
+    const int A = min(*A_dev, A_cap);
+    const int lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    float part = 0.f;
+    if (labels_i64) {
+        const float invB = 1.0f / (float)B;
+        for (int r = warp; r < B; r += nwarps) {
+            const int row = row_ids[r];
+            const float* lr = logits + (size_t)row * ldl;
+            const int y = (int)labels_i64[targets[r]];
+            float mx = -INFINITY;
+            for (int c = lane; c < C; c += 32) mx = fmaxf(mx, lr[c]);
+            mx = warp_max(mx);
+            float se = 0.f;
+            for (int c = lane; c < C; c += 32) se += expf(lr[c] - mx);
+            se = warp_sum(se);
+            const float lse = mx + logf(se);
+            for (int c = lane; c < C; c += 32) {
+                const float pr = expf(lr[c] - lse);
+                dlogits[(size_t)row * ldl + c] = (pr - (c == y ? 1.f : 0.f)) * invB;
+            }
+            if (lane == 0) part += (lse - lr[y]) * invB;
+        }
+    } else {
+        const float inv = 1.0f / ((float)B * (float)C);
+        for (int r = warp; r < B; r += nwarps) {
+            const int row = row_ids[r];
+            const float* lr = logits + (size_t)row * ldl;
+            const float* yr = labels_f32 + (size_t)targets[r] * C;
+            float a = 0.f;
+            for (int c = lane; c < C; c += 32) {
+                const float l = lr[c], y = yr[c];
+                a += (1.0f - y) * l + fmaxf(-l, 0.f) + log1pf(expf(-fabsf(l)));
+                dlogits[(size_t)row * ldl + c] = (1.0f / (1.0f + expf(-l)) - y) * inv;
+            }
+            part += a * inv;          // lanes hold partial sums, reduced below
+        }
+    }
+    float loss = block_sum_1024(part, s);
+    if (reg_param != 0.f && C > 1) {                     // reg_param * sum_rows var(logits, dim=1), unbiased
+        float rp = 0.f;
+        const float invc1 = 1.0f / (float)(C - 1);
+        for (int row = warp; row < A; row += nwarps) {
+            const float* lr = logits + (size_t)row * ldl;
+            float sm = 0.f;
+            for (int c = lane; c < C; c += 32) sm += lr[c];
+            const float mean = warp_sum(sm) / (float)C;
+            float sq = 0.f;
+            for (int c = lane; c < C; c += 32) {
+                const float d = lr[c] - mean;
+                sq = fmaf(d, d, sq);
+                dlogits[(size_t)row * ldl + c] += reg_param * 2.0f * d * invc1;
+            }
+            sq = warp_sum(sq);
+            if (lane == 0) rp += sq * invc1;
+        }
+        loss += reg_param * block_sum_1024(rp, s);
+    }
+    if (threadIdx.x == 0) *loss_out = loss;
+}
+
+// scal layout (float): see GRAPES_SCAL_* in the header.
+//   TB       : loss_gfn = (log_z + tot + coef*loss_c)^2 ; d/dtheta = 2(...) * (dlog_z + dtot)      main.py:282
+//   REINFORCE: loss_gfn = -tot * loss_c                 ; d/dtheta = -loss_c * dtot               main.py:279
+__global__ void k_gfn_finalize(float* scal, float loss_coef, float log_z_init, int reinforce, int have_log_z) {
+    const float loss_c = scal[GRAPES_SCAL_LOSS_C];
+    const float tot = scal[GRAPES_SCAL_TOT_LOG_PROB];
+    const float log_z = have_log_z ? scal[GRAPES_SCAL_LOG_Z_MEAN] - log_z_init : 0.f;
+    scal[GRAPES_SCAL_LOG_Z] = log_z;
+    if (reinforce) {
+        scal[GRAPES_SCAL_LOSS_GFN] = -tot * loss_c;
+        scal[GRAPES_SCAL_G_GF] = -loss_c;
+        scal[GRAPES_SCAL_G_Z] = 0.f;
+    } else {
+        const float r = log_z + tot + loss_coef * loss_c;
+        scal[GRAPES_SCAL_LOSS_GFN] = r * r;
+        scal[GRAPES_SCAL_G_GF] = 2.0f * r;
+        scal[GRAPES_SCAL_G_Z] = 2.0f * r;
+    }
+}
+
+// grad[i] = (*g) * dir[i]
+__global__ void __launch_bounds__(256) k_scale_by_dev(const float* __restrict__ dir, const float* __restrict__ g, int n,
+                                                      float* __restrict__ grad) {
+    const float gg = *g;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) grad[i] = gg * dir[i];
+}
+
+// torch.optim.Adam single-tensor math on a flat buffer; `step` (device, float) is the count BEFORE this update.
+__global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                              float* __restrict__ v, int n, float lr, float beta1, float beta2,
+                                              float eps, const float* __restrict__ step) {
+    __shared__ float s_step_size, s_bc2_sqrt;
+    if (threadIdx.x == 0) {
+        const double t = (double)(*step) + 1.0;
+        const double bc1 = 1.0 - pow((double)beta1, t), bc2 = 1.0 - pow((double)beta2, t);
+        s_step_size = (float)((double)lr / bc1);
+        s_bc2_sqrt = (float)sqrt(bc2);
+    }
+    __syncthreads();
+    const float step_size = s_step_size, bc2s = s_bc2_sqrt;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float gi = g[i];
+        const float mi = m[i] + (gi - m[i]) * (1.0f - beta1);          // exp_avg.lerp_(grad, 1-beta1)
+        const float vi = v[i] * beta2 + (1.0f - beta2) * gi * gi;      // mul_(beta2).addcmul_(g, g, 1-beta2)
+        m[i] = mi; v[i] = vi;
+        const float denom = sqrtf(vi) / bc2s + eps;
+        p[i] = p[i] - step_size * (mi / denom);
+    }
+}
+__global__ void k_step_inc(float* step) { *step += 1.0f; }
+__global__ void __launch_bounds__(256) k_fill_f32(float* p, float v, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
+}
+
+static inline int grid_for(const grapes_ctx* ctx, long long work, int threads, int per_sm = 8) {
+    long long b = (work + threads - 1) / threads;
+    long long cap = (long long)ctx->sm_count * per_sm;
+    if (b < 1) b = 1;
+    return (int)(b < cap ? b : cap);
+}
+
+extern "C" {
+
+int grapes_classifier_loss(grapes_ctx* ctx, const float* logits, int ldl, int C, const int* A_dev, int A_cap,
+                           const int* row_ids, const int* targets, int B, const int64_t* labels_i64,
+                           const float* labels_f32, float reg_param, float* dlogits, float* loss_out, void* stream) {
+    GRAPES_REQUIRE(ctx && logits && A_dev && row_ids && targets && dlogits && loss_out, "null argument");
+    GRAPES_REQUIRE((labels_i64 != nullptr) != (labels_f32 != nullptr), "exactly one label array");
+    GRAPES_REQUIRE(B > 0 && C > 0, "bad shape");
+    cudaStream_t s = (cudaStream_t)stream;
+    GRAPES_CUDA_OK(cudaMemsetAsync(dlogits, 0, sizeof(float) * (size_t)A_cap * ldl, s));
+    k_classifier_loss<<<1, LOSS_THREADS, 0, s>>>(logits, ldl, C, A_dev, A_cap, row_ids, targets, B, labels_i64,
+                                                 labels_f32, reg_param, dlogits, loss_out);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+int grapes_gfn_finalize(grapes_ctx* ctx, float* scal, float loss_coef, float log_z_init, int reinforce, int have_log_z,
+                        void* stream) {
+    GRAPES_REQUIRE(ctx && scal, "null argument");
+    k_gfn_finalize<<<1, 1, 0, (cudaStream_t)stream>>>(scal, loss_coef, log_z_init, reinforce, have_log_z);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+int grapes_scale_by_device_scalar(grapes_ctx* ctx, const float* dir, const float* g_dev, int n, float* grad,
+                                  void* stream) {
+    GRAPES_REQUIRE(ctx && dir && g_dev && grad, "null argument");
+    k_scale_by_dev<<<grid_for(ctx, n, 256), 256, 0, (cudaStream_t)stream>>>(dir, g_dev, n, grad);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+int grapes_adam_step(grapes_ctx* ctx, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int n,
+                     float lr, float beta1, float beta2, float eps, float* step_dev, int increment_step,
+                     void* stream) {
+    GRAPES_REQUIRE(ctx && params && grads && exp_avg && exp_avg_sq && step_dev, "null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    k_adam<<<grid_for(ctx, n, 256), 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                 step_dev);
+    if (increment_step) k_step_inc<<<1, 1, 0, s>>>(step_dev);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+int grapes_fill_f32(grapes_ctx* ctx, float* p, float value, int n, void* stream) {
+    GRAPES_REQUIRE(ctx && p, "null argument");
+    k_fill_f32<<<grid_for(ctx, n, 256), 256, 0, (cudaStream_t)stream>>>(p, value, n);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,267 @@
+// Per-hop node selection: Gumbel-top-k over the candidate frontier + Bernoulli log-probability of
+// the chosen mask + sampler statistics.  Replaces sample_neighborhoods_from_probs
+// (/root/reference/modules/utils.py:13-71) and the deterministic top-k of the mini-batch evaluator
+// (/root/reference/eval.py:126-130), without the per-hop D2H of the mask (utils.py:60).
+//
+// One CTA (1024 threads = 32 warps).  The k-th largest key is found by an MSB-first radix select
+// on order-preserving uint32 keys; every warp builds a private 256-bin digit histogram with
+// match-any aggregation, warps are merged through shared memory.  Ties at the threshold go to the
+// LOWEST candidate index (torch.topk leaves ties unspecified; the oracle uses the same rule).
+#include "common.cuh"
+
+#define SEL_THREADS 1024
+#define SEL_WARPS (SEL_THREADS / 32)
+
+__device__ __forceinline__ uint32_t float_to_ordered(float f) {
+    if (f != f) return 0u;                                   // NaN ranks lowest
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// Philox4x32-10 (Salmon et al. 2011): counter-based, one call = 4 uniforms
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0; key.y += W1;
+    }
+    return ctr;
+}
+__device__ __forceinline__ float philox_uniform(unsigned long long seed, unsigned long long offset, int i) {
+    uint4 ctr = make_uint4((uint32_t)(i >> 2), 0u, (uint32_t)offset, (uint32_t)(offset >> 32));
+    const uint4 r = philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint32_t x = (i & 3) == 0 ? r.x : (i & 3) == 1 ? r.y : (i & 3) == 2 ? r.z : r.w;
+    return (float)(x & 0xffffffu) * (1.0f / 16777216.0f);   // 24-bit mantissa in [0,1), as torch.rand
+}
+
+__device__ __forceinline__ float sigmoidf_(float l) { return 1.0f / (1.0f + expf(-l)); }
+// Bernoulli(logits=l).log_prob(y) = -BCEWithLogits(l, y)  (utils.py:71)
+__device__ __forceinline__ float bern_log_prob(float l, float y) {
+    return -((1.0f - y) * l + fmaxf(-l, 0.f) + log1pf(expf(-fabsf(l))));
+}
+__device__ __forceinline__ float entropy_bits(float p) {
+    const float e = -(p * log2f(p) + (1.0f - p) * log2f(1.0f - p));
+    return (e != e) ? 0.f : e;                                // NaN entropy -> 0 (utils.py:52-54)
+}
+
+template <typename T, typename Op>
+__device__ __forceinline__ T block_reduce(T v, T* smem, Op op, T identity) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(GRAPES_FULL_MASK, v, o));
+    if (lane_id() == 0) smem[threadIdx.x >> 5] = v;
+    __syncthreads();
+    T r = (threadIdx.x < SEL_WARPS) ? smem[threadIdx.x] : identity;
+    if (threadIdx.x < 32) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r = op(r, __shfl_xor_sync(GRAPES_FULL_MASK, r, o));
+        if (threadIdx.x == 0) smem[0] = r;
+    }
+    __syncthreads();
+    r = smem[0];
+    __syncthreads();
+    return r;
+}
+struct OpAdd { __device__ float operator()(float a, float b) const { return a + b; } };
+struct OpMin { __device__ float operator()(float a, float b) const { return fminf(a, b); } };
+struct OpMax { __device__ float operator()(float a, float b) const { return fmaxf(a, b); } };
+
+// mode: GRAPES_NOISE_*
+__global__ void __launch_bounds__(SEL_THREADS) k_select(
+    const float* __restrict__ logits_all, const int* __restrict__ nb_local, const int* __restrict__ nb_nodes,
+    const int* __restrict__ c_dev, int cap_c, int k, int mode, const float* __restrict__ noise,
+    unsigned long long* rng_state, uint32_t* __restrict__ ukeys, float* __restrict__ keys_out,
+    int* __restrict__ sampled_out, int sampled_offset, int* __restrict__ s_dev, int* __restrict__ total_dev,
+    uint8_t* __restrict__ mask_out, float* __restrict__ log_prob, float* tot_log_prob, float* __restrict__ stats,
+    float* __restrict__ dl_all, float* sum_dl, uint32_t* bm_mark) {
+    __shared__ int s_hist[SEL_WARPS][256];
+    __shared__ float s_red[SEL_WARPS];
+    __shared__ long long s_scan[SEL_WARPS + 2];
+    __shared__ uint32_t s_prefix;
+    __shared__ int s_kr;
+    const int c = min(*c_dev, cap_c);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool take_all = (k >= c);                       // utils.py:31-33: no noise is drawn
+    unsigned long long seed = 0ull, offset = 0ull;
+    if (mode == GRAPES_NOISE_PHILOX) { seed = rng_state[0]; offset = rng_state[1]; }
+
+    // ---- pass 0: keys + probability statistics -------------------------------------------
+    float pmin = INFINITY, pmax = -INFINITY, esum = 0.f;
+    for (int i = tid; i < c; i += SEL_THREADS) {
+        const float l = logits_all[nb_local ? nb_local[i] : i];
+        const float p = sigmoidf_(l);
+        float key;
+        if (mode == GRAPES_NOISE_KEYS) key = noise[i];
+        else if (mode == GRAPES_NOISE_NONE_TOPK_PROBS) key = p;               // eval.py:126
+        else {
+            float g;
+            if (mode == GRAPES_NOISE_GUMBEL) g = noise[i];
+            else {
+                float u = (mode == GRAPES_NOISE_UNIFORM) ? noise[i] : philox_uniform(seed, offset, i);
+                if (mode == GRAPES_NOISE_PHILOX) u = u * ((1.0f - 1.1920929e-07f) - 1.17549435e-38f) + 1.17549435e-38f;
+                g = -logf(-logf(u));
+            }
+            key = logf(p) + g;                                                // utils.py:42
+        }
+        if (!take_all) ukeys[i] = float_to_ordered(key);
+        if (keys_out) keys_out[i] = key;
+        pmin = fminf(pmin, p); pmax = fmaxf(pmax, p);
+        esum += entropy_bits(p);
+    }
+    pmin = block_reduce(pmin, s_red, OpMin(), INFINITY);
+    pmax = block_reduce(pmax, s_red, OpMax(), -INFINITY);
+    esum = block_reduce(esum, s_red, OpAdd(), 0.f);
+    const float emean = (c > 0) ? esum / (float)c : 0.f;
+    float evar = 0.f;
+    for (int i = tid; i < c; i += SEL_THREADS) {
+        const float d = entropy_bits(sigmoidf_(logits_all[nb_local ? nb_local[i] : i])) - emean;
+        evar = fmaf(d, d, evar);
+    }
+    evar = block_reduce(evar, s_red, OpAdd(), 0.f);
+    if (tid == 0 && stats) {
+        stats[0] = pmin; stats[1] = pmax; stats[2] = emean;
+        stats[3] = (c > 1) ? sqrtf(evar / (float)(c - 1)) : 0.f;               // unbiased (utils.py:56)
+    }
+
+    // ---- radix select of the k-th largest key --------------------------------------------
+    uint32_t thr = 0u;      // threshold key
+    int kr = 0;             // how many of the keys == thr are taken (lowest index first)
+    if (!take_all) {
+        if (tid == 0) { s_prefix = 0u; s_kr = k; }
+        __syncthreads();
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            for (int b = lane; b < 256; b += 32) s_hist[warp][b] = 0;
+            __syncwarp();
+            const uint32_t prefix = s_prefix;
+            const uint32_t himask = (shift == 24) ? 0u : (0xffffffffu << (shift + 8));
+            for (int base = 0; base < c; base += SEL_THREADS) {
+                const int i = base + tid;
+                bool valid = false; uint32_t digit = 0u;
+                if (i < c) {
+                    const uint32_t u = ukeys[i];
+                    valid = (u & himask) == prefix;
+                    digit = (u >> shift) & 255u;
+                }
+                // warp-aggregated histogram update
+                const unsigned peers = __match_any_sync(GRAPES_FULL_MASK, valid ? digit : 0xffffffffu);
+                if (valid && lane == (__ffs(peers) - 1)) s_hist[warp][digit] += __popc(peers);
+                __syncwarp();
+            }
+            __syncthreads();
+            // merge warps: thread b < 256 sums bin b
+            if (tid < 256) {
+                int a = 0;
+#pragma unroll
+                for (int w = 0; w < SEL_WARPS; ++w) a += s_hist[w][tid];
+                s_hist[0][tid] = a;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                // walk bins from the top; lane l owns bins [255-8l-7 .. 255-8l] (descending order)
+                int mine[8], msum = 0;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) { mine[t] = s_hist[0][255 - (lane * 8 + t)]; msum += mine[t]; }
+                const int incl = warp_scan_incl(msum);
+                const int excl = incl - msum;
+                const int krem = s_kr;
+                const bool here = (excl < krem) && (incl >= krem);
+                if (here) {
+                    int cum = excl;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        if (cum + mine[t] >= krem) {
+                            s_prefix = prefix | ((uint32_t)(255 - (lane * 8 + t)) << shift);
+                            s_kr = krem - cum;
+                            break;
+                        }
+                        cum += mine[t];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        thr = s_prefix;
+        kr = s_kr;
+    }
+
+    // ---- ordered selection: each thread owns a contiguous index range --------------------
+    const int ipt = (c + SEL_THREADS - 1) / SEL_THREADS;
+    const int i0 = min(c, tid * ipt), i1 = min(c, i0 + ipt);
+    int n_eq = 0, n_gt = 0;
+    if (!take_all) {
+        for (int i = i0; i < i1; ++i) {
+            const uint32_t u = ukeys[i];
+            n_eq += (u == thr);
+            n_gt += (u > thr);
+        }
+    }
+    long long total;
+    const long long packed = ((long long)n_eq << 32) | (long long)n_gt;
+    const long long excl = block_scan_excl<long long>(packed, s_scan, &total);
+    int eq_before = (int)(excl >> 32), gt_before = (int)(excl & 0xffffffffll);
+    float lp_sum = 0.f, dl_sum = 0.f;
+    for (int i = i0; i < i1; ++i) {
+        bool sel;
+        int pos;
+        if (take_all) { sel = true; pos = i; }
+        else {
+            const uint32_t u = ukeys[i];
+            sel = false; pos = 0;
+            if (u > thr) { sel = true; pos = gt_before + min(eq_before, kr); ++gt_before; }
+            else if (u == thr) { if (eq_before < kr) { sel = true; pos = gt_before + eq_before; } ++eq_before; }
+        }
+        const int li = nb_local ? nb_local[i] : i;
+        const float l = logits_all[li];
+        const float y = sel ? 1.f : 0.f;
+        const float lp = bern_log_prob(l, y);
+        if (log_prob) log_prob[i] = lp;
+        lp_sum += lp;
+        const float d = y - sigmoidf_(l);
+        if (dl_all) dl_all[li] = d;
+        dl_sum += d;
+        if (mask_out) mask_out[i] = sel ? 1 : 0;
+        if (sel) {
+            const int g = nb_nodes ? nb_nodes[i] : i;
+            if (sampled_out) sampled_out[sampled_offset + pos] = g;
+            if (bm_mark && nb_nodes) bitmap_set(bm_mark, g);
+        }
+    }
+    // fixed-order block sums (thread ranges are contiguous, tree order is fixed)
+    lp_sum = block_reduce(lp_sum, s_red, OpAdd(), 0.f);
+    dl_sum = block_reduce(dl_sum, s_red, OpAdd(), 0.f);
+    if (tid == 0) {
+        const int s = take_all ? c : k;
+        if (s_dev) *s_dev = s;
+        if (total_dev) *total_dev = sampled_offset + s;
+        if (tot_log_prob) *tot_log_prob += lp_sum;
+        if (sum_dl) *sum_dl += dl_sum;
+        if (take_all && stats) { stats[0] = stats[1] = stats[2] = stats[3] = 0.f; }   // reference returns {}
+        if (mode == GRAPES_NOISE_PHILOX && !take_all) rng_state[1] = offset + 1ull;
+    }
+}
+
+extern "C" {
+
+int grapes_select_topk(grapes_ctx* ctx, const float* logits_all, const int* nb_local, const int* nb_nodes,
+                       const int* c_dev, int cap_c, int k, int noise_mode, const float* noise,
+                       unsigned long long* rng_state, uint32_t* ukeys_scratch, float* keys_out, int* sampled_out,
+                       int sampled_offset, int* s_dev, int* total_dev, uint8_t* mask_out, float* log_prob,
+                       float* tot_log_prob, float* stats, float* dl_all, float* sum_dl, uint32_t* bm_mark,
+                       void* stream) {
+    GRAPES_REQUIRE(ctx && logits_all && c_dev && ukeys_scratch, "null argument");
+    GRAPES_REQUIRE(k > 0, "num_samples must be positive (utils.py:35)");
+    GRAPES_REQUIRE(noise_mode >= 0 && noise_mode <= GRAPES_NOISE_NONE_TOPK_PROBS, "bad noise mode");
+    GRAPES_REQUIRE(!(noise_mode == GRAPES_NOISE_GUMBEL || noise_mode == GRAPES_NOISE_UNIFORM ||
+                     noise_mode == GRAPES_NOISE_KEYS) || noise, "noise array required");
+    GRAPES_REQUIRE(noise_mode != GRAPES_NOISE_PHILOX || rng_state, "rng_state required");
+    k_select<<<1, SEL_THREADS, 0, (cudaStream_t)stream>>>(logits_all, nb_local, nb_nodes, c_dev, cap_c, k, noise_mode,
+                                                          noise, rng_state, ukeys_scratch, keys_out, sampled_out,
+                                                          sampled_offset, s_dev, total_dev, mask_out, log_prob,
+                                                          tot_log_prob, stats, dl_all, sum_dl, bm_mark);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+}  // extern "C"

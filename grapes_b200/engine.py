@@ -1,0 +1,505 @@
+"""Device-resident GRAPES training step (the batch body of ``train()``,
+/root/reference/main.py:161-291) as ONE stream of hand-written sm_100a kernels behind the C ABI.
+
+Differences in *mechanism* (never in results) from the reference loop:
+  * the graph, features and labels stay in HBM; nothing is gathered on the host or shipped per hop
+    (the reference does 5 H2D copies + 1 D2H sync per hop);
+  * every data-dependent size (m, n, c, |sampled|, |block|, |all_nodes|) lives in device memory,
+    buffers are capacity-bounded, so the whole step enqueues without a host sync and can be
+    captured into a CUDA graph and replayed;
+  * GCNConv aggregation is done at the narrower width (A_hat (X W) == (A_hat X) W);
+  * the GFlowNet / REINFORCE gradient is linear in the scalar 2*(log_z + sum log_prob + coef*loss_c)
+    (resp. -loss_c), so each hop's gradient DIRECTION is accumulated right after that hop's
+    selection while its aggregated features are still hot in L2, and scaled once at the end;
+    no autograd graph is kept across hops.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from ._lib import lib, ptr, GrapesError
+from .graph import DeviceGraph
+
+SCAL = dict(loss_c=0, tot_log_prob=1, log_z_mean=2, log_z=3, loss_gfn=4, g_gf=5, g_z=6, sum_dl=7)
+NOISE_PHILOX, NOISE_GUMBEL, NOISE_UNIFORM, NOISE_KEYS, NOISE_TOPK_PROBS = 0, 1, 2, 3, 4
+OVF_NAMES = {1: "rows>cap_P", 2: "edges>cap_m", 4: "nodes>cap_n", 8: "block>cap_blk", 16: "hub worklist"}
+
+
+def _round_up(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+class _Net:
+    """Offsets of one 2-layer GCN (hidden D, in K, out O) inside the flat parameter buffer.
+    Parameter names/shapes follow PyG GCNConv: lin.weight [out, in], bias [out]."""
+
+    def __init__(self, base: int, K: int, D: int, O: int):
+        self.K, self.D, self.O = K, D, O
+        self.W1 = base
+        self.b1 = self.W1 + D * K
+        self.W2 = self.b1 + D
+        self.b2 = self.W2 + O * D
+        self.end = self.b2 + O
+        self.base = base
+
+    @property
+    def size(self):
+        return self.end - self.base
+
+    def views(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
+        return {
+            "gcn_layers.0.bias": flat[self.b1:self.b1 + self.D],
+            "gcn_layers.0.lin.weight": flat[self.W1:self.W1 + self.D * self.K].view(self.D, self.K),
+            "gcn_layers.1.bias": flat[self.b2:self.b2 + self.O],
+            "gcn_layers.1.lin.weight": flat[self.W2:self.W2 + self.O * self.D].view(self.O, self.D),
+        }
+
+
+def glorot_(w: torch.Tensor, generator=None):
+    """PyG Linear(weight_initializer='glorot'): U(-a, a), a = sqrt(6/(fan_in+fan_out)); bias zeros."""
+    a = math.sqrt(6.0 / (w.shape[0] + w.shape[1]))
+    cpu = (torch.rand(w.shape, generator=generator, dtype=torch.float32) * 2 - 1) * a
+    w.copy_(cpu.to(w.device))
+
+
+class GrapesEngine:
+    def __init__(self, graph: DeviceGraph, x: torch.Tensor, y: torch.Tensor, *, num_classes: int,
+                 batch_size: int, num_samples: int, sampling_hops: int, use_indicators: bool = True,
+                 hidden_dim: int = 256, lr_gc: float = 1e-3, lr_gf: float = 1e-4, loss_coef: float = 1e4,
+                 log_z_init: float = 0., reg_param: float = 0., random_sampling: bool = False,
+                 reinforce_baseline: bool = False, seed: int = 0, cap_edges: Optional[int] = None,
+                 cap_nodes: Optional[int] = None, cap_block: Optional[int] = None):
+        self.g = graph
+        self.L = lib()
+        dev = graph.device
+        self.device = dev
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        assert sampling_hops <= 7, "indicator bits are packed in 8 columns"
+        self.x, self.y = x, y.contiguous()
+        self.multilabel = (y.dim() == 2)
+        if self.multilabel:
+            self.y = self.y.to(torch.float32)
+        else:
+            self.y = self.y.to(torch.int64)
+        N, F = graph.num_nodes, x.shape[1]
+        self.N, self.F, self.C, self.D = N, F, int(num_classes), int(hidden_dim)
+        self.B, self.k, self.H = int(batch_size), int(num_samples), int(sampling_hops)
+        self.use_ind = bool(use_indicators)
+        self.num_ind = self.H + 1 if self.use_ind else 0
+        self.Fp = F + self.num_ind
+        self.ldY = _round_up(self.Fp, 4)
+        self.lr_gc, self.lr_gf = float(lr_gc), float(lr_gf)
+        self.loss_coef, self.log_z_init, self.reg_param = float(loss_coef), float(log_z_init), float(reg_param)
+        self.random_sampling, self.reinforce = bool(random_sampling), bool(reinforce_baseline)
+        W = graph.num_words
+        self.W = W
+
+        # ---- capacities -------------------------------------------------------------------
+        self.cap_P = self.B + self.k
+        deg = graph.indptr[1:] - graph.indptr[:-1]
+        max_deg = int(deg.max().item()) if graph.nnz > 0 else 0
+        if cap_edges is None:
+            cap_edges = min(graph.nnz, self.cap_P * max(max_deg, 1), 1 << 26)
+        self.cap_m = max(int(cap_edges), 1)
+        if cap_nodes is None:
+            cap_nodes = min(N, self.cap_m + self.cap_P)
+        self.cap_n = max(int(cap_nodes), 1)
+        self.cap_A = self.B + self.H * self.k
+        if cap_block is None:
+            cap_block = min(self.cap_m, self.cap_P * self.cap_P)
+        self.cap_blk = max(int(cap_block), 1)
+        if max(self.cap_m, self.cap_n) > graph.max_frontier:
+            raise GrapesError("frontier capacity exceeds the graph context's max_frontier")
+
+        i32 = dict(dtype=torch.int32, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        u32 = dict(dtype=torch.int32, device=dev)     # bitmaps are stored as int32 words
+        z = torch.zeros
+        e = torch.empty
+        # bitmaps
+        self.bm_prev = [z(W, **u32), z(W, **u32)]
+        self.bm_batch = z(W, **u32)
+        self.bm_all = z(W, **u32)
+        self.bm_ind = z((max(self.num_ind, 1), W), **u32)
+        self.pref_batch, self.pref_nb, self.pref_all = z(W + 1, **i32), z(W + 1, **i32), z(W + 1, **i32)
+        # lists
+        self.targets = z(self.B, **i32)
+        self.prev = [z(self.cap_P, **i32), z(self.cap_P, **i32)]
+        self.counts = z(64, **i32)          # device-side sizes, see _cnt()
+        self.row_off = z(self.cap_P + 1, **i32)
+        self.e_row, self.e_col = e(self.cap_m, **i32), e(self.cap_m, **i32)
+        self.e_src, self.e_dst = e(self.cap_m, **i32), e(self.cap_m, **i32)
+        self.batch_nodes, self.nb_nodes, self.nb_local = e(self.cap_n, **i32), e(self.cap_n, **i32), e(self.cap_n, **i32)
+        self.ind_bits = z(self.cap_n, **u32)
+        self.cnt_scratch = z(max(self.cap_n, self.cap_A), **i32)
+        self.in_off = z(self.cap_n + 1, **i32)
+        self.in_src, self.tmp_val = e(self.cap_m, **i32), e(self.cap_m, **i32)
+        self.dinv = e(self.cap_n, **f32)
+        self.Y = z((self.cap_n, self.ldY), **f32)
+        self.z_gf, self.z_z = e(self.cap_n, **f32), e(self.cap_n, **f32)
+        self.logits_all, self.zlogits = z(self.cap_n, **f32), e(self.cap_n, **f32)
+        self.dl_all, self.dz = z(self.cap_n, **f32), e(self.cap_n, **f32)
+        self.dpre = e((self.cap_n, self.D), **f32)
+        self.ukeys = e(self.cap_n, **i32)
+        self.log_prob = z((self.H, self.cap_n), **f32)
+        self.scal = z(16, **f32)
+        self.stats = z((self.H, 4), **f32)
+        self.overflow = z(1, **i32)
+        self.rng_state = torch.tensor([seed & 0x7fffffffffffffff, 0], dtype=torch.int64, device=dev)
+        # induced blocks (global ids), one per hop
+        self.blk_src = [e(self.cap_blk, **i32) for _ in range(self.H)]
+        self.blk_dst = [e(self.cap_blk, **i32) for _ in range(self.H)]
+        # classifier workspace
+        A = self.cap_A
+        self.all_nodes = e(A, **i32)
+        self.target_local = e(self.B, **i32)
+        self.cl_src = [e(self.cap_blk, **i32) for _ in range(2)]      # [0]: layer-1 block (last hop), [1]: layer-2 block (hop 0)
+        self.cl_dst = [e(self.cap_blk, **i32) for _ in range(2)]
+        self.cl_in_off = [z(A + 1, **i32) for _ in range(2)]
+        self.cl_in_src = [e(self.cap_blk, **i32) for _ in range(2)]
+        self.cl_dinv = [e(A, **f32) for _ in range(2)]
+        self.cl_out_off = z(A + 1, **i32)
+        self.cl_out_dst = e(self.cap_blk, **i32)
+        self.cl_tmp = e(self.cap_blk, **i32)
+        self.Yc = z((A, _round_up(F, 4)), **f32)
+        self.out1 = e((A, self.D), **f32)
+        self.Zc = e((A, self.C), **f32)
+        self.logits_c = z((A, self.C), **f32)
+        self.dlogits = z((A, self.C), **f32)
+        self.dZ = e((A, self.C), **f32)
+        self.dpre1 = e((A, self.D), **f32)
+
+        # ---- parameters (flat), gradients, Adam state -------------------------------------
+        D, C = self.D, self.C
+        self.net_c = _Net(0, F, D, C)
+        self.net_gf = _Net(self.net_c.end, self.Fp, D, 1)
+        self.net_z = _Net(self.net_gf.end, F, D, 1)
+        n_par = self.net_z.end
+        self.n_par = n_par
+        self.params = z(n_par, **f32)
+        self.grads = z(n_par, **f32)
+        self.gdir = z(n_par, **f32)         # gradient DIRECTION of (log_z, sum log_prob) w.r.t. gf / z params
+        self.exp_avg, self.exp_avg_sq = z(n_par, **f32), z(n_par, **f32)
+        self.adam_steps = z(2, **f32)        # [0] optimizer_c, [1] optimizer_gf
+        gen = torch.Generator().manual_seed(seed)
+        for net in (self.net_c, self.net_gf, self.net_z):
+            v = net.views(self.params)
+            glorot_(v["gcn_layers.0.lin.weight"], gen)
+            glorot_(v["gcn_layers.1.lin.weight"], gen)
+        self.const100 = torch.full((self.cap_n,), 100.0, **f32)
+        self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        self.record: Optional[dict] = None
+
+    # ------------------------------------------------------------------ helpers
+    _CNT = dict(P0=0, P1=1, m=2, n=3, c=4, nnz=5, A=6, B=7, blk=8, s=16, cl_nnz=24)
+
+    def _cnt(self, name: str, idx: int = 0) -> int:
+        return self.counts.data_ptr() + 4 * (self._CNT[name] + idx)
+
+    def _par(self, off: int) -> int:
+        return self.params.data_ptr() + 4 * off
+
+    def _dir(self, off: int) -> int:
+        return self.gdir.data_ptr() + 4 * off
+
+    def _grd(self, off: int) -> int:
+        return self.grads.data_ptr() + 4 * off
+
+    def _scal(self, name: str) -> int:
+        return self.scal.data_ptr() + 4 * SCAL[name]
+
+    def state_dicts(self) -> Dict[str, Dict[str, torch.Tensor]]:
+        return {"gcn_c": self.net_c.views(self.params), "gcn_gf": self.net_gf.views(self.params),
+                "gcn_z": self.net_z.views(self.params)}
+
+    def grad_dicts(self) -> Dict[str, Dict[str, torch.Tensor]]:
+        return {"gcn_c": self.net_c.views(self.grads), "gcn_gf": self.net_gf.views(self.grads),
+                "gcn_z": self.net_z.views(self.grads)}
+
+    def load_state_dicts(self, gcn_c=None, gcn_gf=None, gcn_z=None):
+        for net, sd in ((self.net_c, gcn_c), (self.net_gf, gcn_gf), (self.net_z, gcn_z)):
+            if sd is None:
+                continue
+            v = net.views(self.params)
+            for name, t in v.items():
+                t.copy_(sd[name].detach().to(self.device, torch.float32))
+
+    # ------------------------------------------------------------------ the step
+    def _enqueue(self, gumbel_noise: Optional[Sequence[Optional[torch.Tensor]]], apply_optim: bool,
+                 noise_mode: int = NOISE_GUMBEL):
+        L, g, ctx = self.L, self.g, self.g.ctx
+        st = torch.cuda.current_stream().cuda_stream
+        B, k, H, F, Fp, D, C, W = self.B, self.k, self.H, self.F, self.Fp, self.D, self.C, self.W
+        ovf = ptr(self.overflow)
+        rec = self.record
+        indptr, indices, X = ptr(g.indptr), ptr(g.indices), ptr(self.x)
+
+        # ---- per-batch reset (main.py:161-176) ----
+        L.grapes_zero(ctx, ptr(self.bm_all), 4 * W, st)
+        if self.use_ind:
+            L.grapes_zero(ctx, ptr(self.bm_ind), 4 * W * self.num_ind, st)
+        L.grapes_zero(ctx, ptr(self.scal), 4 * 16, st)
+        L.grapes_zero(ctx, ptr(self.gdir), 4 * self.n_par, st)
+        L.grapes_zero(ctx, ptr(self.stats), 4 * 4 * H, st)
+        # counts[B] = B ; prev[0][:B] = prev[1][:B] = targets ; P0 = B
+        L.grapes_append_list(ctx, ptr(self.targets), self._cnt("B"), B, ptr(self.prev[0]), 0, self._cnt("P0"), st)
+        L.grapes_append_list(ctx, ptr(self.targets), self._cnt("B"), B, ptr(self.prev[1]), 0, self._cnt("P1"), st)
+        L.grapes_bitmap_set(ctx, ptr(self.targets), self._cnt("B"), B, ptr(self.bm_all), st)
+        if self.use_ind:
+            L.grapes_bitmap_set(ctx, ptr(self.targets), self._cnt("B"), B,
+                                self.bm_ind.data_ptr() + 4 * W * (self.num_ind - 1), st)
+
+        for h in range(H):
+            cur, nxt = h % 2, (h + 1) % 2
+            P_dev = self._cnt("P0") if cur == 0 else self._cnt("P1")
+            Pn_dev = self._cnt("P0") if nxt == 0 else self._cnt("P1")
+            rows = ptr(self.prev[cur])
+            L.grapes_zero(ctx, ptr(self.bm_prev[cur]), 4 * W, st)
+            L.grapes_zero(ctx, ptr(self.bm_batch), 4 * W, st)
+            # get_neighborhoods + mask dedup (main.py:180-190)
+            L.grapes_row_offsets(ctx, indptr, rows, P_dev, self.cap_P, ptr(self.row_off), self._cnt("m"), self.cap_m,
+                                 ptr(self.bm_prev[cur]), ptr(self.bm_batch), ovf, st)
+            L.grapes_expand_rows(ctx, indptr, indices, rows, P_dev, self.cap_P, ptr(self.row_off), self._cnt("m"),
+                                 self.cap_m, ptr(self.e_row), ptr(self.e_col), ptr(self.bm_batch), st)
+            if h > 0:
+                # slice_adjacency(rows = T u S_{h-1}, cols = prev_{h-1}) (main.py:241-244): same row expansion
+                L.grapes_slice_block(ctx, rows, ptr(self.e_row), ptr(self.e_col), self._cnt("m"), self.cap_m,
+                                     ptr(self.bm_prev[nxt]), ptr(self.blk_src[h - 1]), ptr(self.blk_dst[h - 1]),
+                                     self.cap_blk, self._cnt("blk", h - 1), ovf, st)
+            L.grapes_rank_nodes(ctx, ptr(self.bm_batch), ptr(self.bm_prev[cur]), ptr(self.pref_batch),
+                                ptr(self.pref_nb), ptr(self.batch_nodes), ptr(self.nb_nodes), ptr(self.nb_local),
+                                ptr(self.ind_bits) if self.use_ind else None,
+                                ptr(self.bm_ind) if self.use_ind else None, self.num_ind, h, self.cap_n,
+                                self._cnt("n"), self._cnt("c"), ovf, st)
+            L.grapes_edges_to_local(ctx, rows, ptr(self.e_row), ptr(self.e_col), self._cnt("m"), self.cap_m,
+                                    ptr(self.bm_batch), ptr(self.pref_batch), ptr(self.e_src), ptr(self.e_dst), st)
+            # gcn_norm structure of the hop graph (dst-sorted CSR, deg^-1/2)
+            L.grapes_build_csr(ctx, ptr(self.e_dst), ptr(self.e_src), self._cnt("m"), self.cap_m, self._cnt("n"),
+                               self.cap_n, ptr(self.cnt_scratch), ptr(self.in_off), ptr(self.in_src),
+                               ptr(self.tmp_val), ptr(self.dinv), self._cnt("nnz"), ovf, st)
+            need_Y = not self.random_sampling
+            if need_Y:
+                # Y = A_hat [x | indicators]   (feature gather fused, main.py:198-204 + GCNConv aggregation)
+                L.grapes_aggregate(ctx, X, F, F, ptr(self.batch_nodes), self._cnt("n"), self.cap_n, ptr(self.in_off),
+                                   ptr(self.in_src), ptr(self.dinv), ptr(self.ind_bits) if self.use_ind else None,
+                                   self.num_ind, None, 0, ptr(self.Y), self.ldY, st)
+                gf = self.net_gf
+                L.grapes_sampler_l1_fwd(ctx, ptr(self.Y), self.ldY, self._cnt("n"), self.cap_n, Fp, self._par(gf.W1),
+                                        Fp, D, self._par(gf.b1), self._par(gf.W2), ptr(self.z_gf), st)
+                L.grapes_aggregate_scalar(ctx, ptr(self.z_gf), self._cnt("n"), self.cap_n, ptr(self.in_off),
+                                          ptr(self.in_src), ptr(self.dinv), self._par(gf.b2), ptr(self.logits_all),
+                                          ptr(self.dl_all), st)
+                logits_ptr = ptr(self.logits_all)
+            else:
+                logits_ptr = ptr(self.const100)                                   # main.py:207
+            noise = None if gumbel_noise is None else gumbel_noise[h]
+            mode = noise_mode if noise is not None else NOISE_PHILOX
+            lp = self.log_prob.data_ptr() + 4 * self.cap_n * h
+            L.grapes_select_topk(ctx, logits_ptr, ptr(self.nb_local), ptr(self.nb_nodes), self._cnt("c"), self.cap_n,
+                                 k, mode, ptr(noise), ptr(self.rng_state), ptr(self.ukeys),
+                                 ptr(rec["keys_buf"]) if rec is not None else None,
+                                 ptr(self.prev[nxt]), B, self._cnt("s", h), Pn_dev, None, lp,
+                                 self._scal("tot_log_prob"), self.stats.data_ptr() + 16 * h,
+                                 ptr(self.dl_all) if need_Y else None,
+                                 self._dir(self.net_gf.b2) if need_Y else None, ptr(self.bm_all), st)
+            if need_Y:
+                # d(sum log_prob)/d(theta_gf): direction accumulated now, scaled by g at the end
+                L.grapes_aggregate_scalar_T(ctx, ptr(self.dl_all), self._cnt("n"), self.cap_n, P_dev, self.cap_P,
+                                            ptr(self.row_off), ptr(self.e_src), ptr(self.e_dst), ptr(self.dinv),
+                                            ptr(self.dz), st)
+                gf = self.net_gf
+                L.grapes_sampler_l1_bwd(ctx, ptr(self.Y), self.ldY, self._cnt("n"), self.cap_n, Fp, self._par(gf.W1),
+                                        Fp, D, self._par(gf.b1), self._par(gf.W2), ptr(self.dz), ptr(self.dpre), 1.0,
+                                        1, self._dir(gf.W1), Fp, self._dir(gf.b1), self._dir(gf.W2), st)
+                if h == 0:
+                    # log_z = mean(gcn_z(x[batch_nodes], edges)) - log_z_init   (main.py:223-228)
+                    nz = self.net_z
+                    L.grapes_sampler_l1_fwd(ctx, ptr(self.Y), self.ldY, self._cnt("n"), self.cap_n, F,
+                                            self._par(nz.W1), F, D, self._par(nz.b1), self._par(nz.W2),
+                                            ptr(self.z_z), st)
+                    L.grapes_aggregate_scalar(ctx, ptr(self.z_z), self._cnt("n"), self.cap_n, ptr(self.in_off),
+                                              ptr(self.in_src), ptr(self.dinv), self._par(nz.b2), ptr(self.zlogits),
+                                              None, st)
+                    L.grapes_vec_sum(ctx, ptr(self.zlogits), self._cnt("n"), self.cap_n, 1.0, 1, 0,
+                                     self._scal("log_z_mean"), st)
+                    if not self.reinforce:
+                        L.grapes_fill_inv_count(ctx, ptr(self.zlogits), self._cnt("n"), self.cap_n, st)
+                        L.grapes_aggregate_scalar_T(ctx, ptr(self.zlogits), self._cnt("n"), self.cap_n, P_dev,
+                                                    self.cap_P, ptr(self.row_off), ptr(self.e_src), ptr(self.e_dst),
+                                                    ptr(self.dinv), ptr(self.dz), st)
+                        L.grapes_sampler_l1_bwd(ctx, ptr(self.Y), self.ldY, self._cnt("n"), self.cap_n, F,
+                                                self._par(nz.W1), F, D, self._par(nz.b1), self._par(nz.W2),
+                                                ptr(self.dz), ptr(self.dpre), 1.0, 1, self._dir(nz.W1), F,
+                                                self._dir(nz.b1), self._dir(nz.W2), st)
+                        L.grapes_fill_f32(ctx, self._dir(nz.b2), 1.0, 1, st)
+            if rec is not None:
+                self._record_hop(h, cur)
+
+        # ---- last block: slice_adjacency(rows = T u S_{H-1}, cols = prev_{H-1}) ----
+        cur, nxt = H % 2, (H + 1) % 2
+        P_dev = self._cnt("P0") if cur == 0 else self._cnt("P1")
+        rows = ptr(self.prev[cur])
+        L.grapes_row_offsets(ctx, indptr, rows, P_dev, self.cap_P, ptr(self.row_off), self._cnt("m"), self.cap_m,
+                             None, None, ovf, st)
+        L.grapes_expand_rows(ctx, indptr, indices, rows, P_dev, self.cap_P, ptr(self.row_off), self._cnt("m"),
+                             self.cap_m, ptr(self.e_row), ptr(self.e_col), None, st)
+        L.grapes_slice_block(ctx, rows, ptr(self.e_row), ptr(self.e_col), self._cnt("m"), self.cap_m,
+                             ptr(self.bm_prev[nxt]), ptr(self.blk_src[H - 1]), ptr(self.blk_dst[H - 1]), self.cap_blk,
+                             self._cnt("blk", H - 1), ovf, st)
+
+        # ---- classifier on the sampled subgraph (main.py:252-269) ----
+        L.grapes_rank_nodes(ctx, ptr(self.bm_all), None, ptr(self.pref_all), None, ptr(self.all_nodes), None, None,
+                            None, None, 0, 0, self.cap_A, self._cnt("A"), None, ovf, st)
+        L.grapes_relabel(ctx, ptr(self.targets), self._cnt("B"), B, ptr(self.bm_all), ptr(self.pref_all),
+                         ptr(self.target_local), st)
+        # GCN.forward with a per-layer list: hidden layer <- edge_indices[-1], last layer <- edge_indices[0] (gcn.py:30-36)
+        for slot, hop in ((0, H - 1), (1, 0)):
+            L.grapes_relabel(ctx, ptr(self.blk_src[hop]), self._cnt("blk", hop), self.cap_blk, ptr(self.bm_all),
+                             ptr(self.pref_all), ptr(self.cl_src[slot]), st)
+            L.grapes_relabel(ctx, ptr(self.blk_dst[hop]), self._cnt("blk", hop), self.cap_blk, ptr(self.bm_all),
+                             ptr(self.pref_all), ptr(self.cl_dst[slot]), st)
+            L.grapes_build_csr(ctx, ptr(self.cl_dst[slot]), ptr(self.cl_src[slot]), self._cnt("blk", hop),
+                               self.cap_blk, self._cnt("A"), self.cap_A, ptr(self.cnt_scratch),
+                               ptr(self.cl_in_off[slot]), ptr(self.cl_in_src[slot]), ptr(self.cl_tmp),
+                               ptr(self.cl_dinv[slot]), self._cnt("cl_nnz", slot), ovf, st)
+        L.grapes_build_csr(ctx, ptr(self.cl_src[1]), ptr(self.cl_dst[1]), self._cnt("blk", 0), self.cap_blk,
+                           self._cnt("A"), self.cap_A, ptr(self.cnt_scratch), ptr(self.cl_out_off),
+                           ptr(self.cl_out_dst), ptr(self.cl_tmp), None, self._cnt("cl_nnz", 2), ovf, st)
+        nc = self.net_c
+        ldYc = self.Yc.shape[1]
+        A_dev, cap_A = self._cnt("A"), self.cap_A
+        L.grapes_aggregate(ctx, X, F, F, ptr(self.all_nodes), A_dev, cap_A, ptr(self.cl_in_off[0]),
+                           ptr(self.cl_in_src[0]), ptr(self.cl_dinv[0]), None, 0, None, 0, ptr(self.Yc), ldYc, st)
+        L.grapes_gemm(ctx, 3, ptr(self.Yc), ldYc, self._par(nc.W1), F, ptr(self.out1), D, A_dev, cap_A, D, F,
+                      self._par(nc.b1), 1, None, 0, st)
+        L.grapes_gemm(ctx, 3, ptr(self.out1), D, self._par(nc.W2), D, ptr(self.Zc), C, A_dev, cap_A, C, D, None, 0,
+                      None, 0, st)
+        L.grapes_aggregate(ctx, ptr(self.Zc), C, C, None, A_dev, cap_A, ptr(self.cl_in_off[1]),
+                           ptr(self.cl_in_src[1]), ptr(self.cl_dinv[1]), None, 0, self._par(nc.b2), 0,
+                           ptr(self.logits_c), C, st)
+        L.grapes_classifier_loss(ctx, ptr(self.logits_c), C, C, A_dev, cap_A, ptr(self.target_local),
+                                 ptr(self.targets), B, None if self.multilabel else ptr(self.y),
+                                 ptr(self.y) if self.multilabel else None, self.reg_param, ptr(self.dlogits),
+                                 self._scal("loss_c"), st)
+        # backward of the classifier (loss_c.backward(), main.py:267)
+        L.grapes_colsum(ctx, ptr(self.dlogits), A_dev, cap_A, C, C, 1.0, 0, self._grd(nc.b2), st)
+        L.grapes_aggregate(ctx, ptr(self.dlogits), C, C, None, A_dev, cap_A, ptr(self.cl_out_off),
+                           ptr(self.cl_out_dst), ptr(self.cl_dinv[1]), None, 0, None, 0, ptr(self.dZ), C, st)
+        L.grapes_gemm_tn(ctx, ptr(self.dZ), C, ptr(self.out1), D, A_dev, cap_A, C, D, 1.0, 0, self._grd(nc.W2), st)
+        L.grapes_gemm(ctx, 1, ptr(self.dZ), C, self._par(nc.W2), D, ptr(self.dpre1), D, A_dev, cap_A, D, C, None, 0,
+                      ptr(self.out1), D, st)
+        L.grapes_colsum(ctx, ptr(self.dpre1), A_dev, cap_A, D, D, 1.0, 0, self._grd(nc.b1), st)
+        L.grapes_gemm_tn(ctx, ptr(self.dpre1), D, ptr(self.Yc), ldYc, A_dev, cap_A, D, F, 1.0, 0, self._grd(nc.W1),
+                         st)
+        # ---- GFlowNet / REINFORCE loss (main.py:271-291) ----
+        if not self.random_sampling:
+            L.grapes_gfn_finalize(ctx, ptr(self.scal), self.loss_coef, self.log_z_init, int(self.reinforce), 1, st)
+            gf, nz = self.net_gf, self.net_z
+            L.grapes_scale_by_device_scalar(ctx, self._dir(gf.base), self._scal("g_gf"), gf.size,
+                                            self._grd(gf.base), st)
+            L.grapes_scale_by_device_scalar(ctx, self._dir(nz.base), self._scal("g_z"), nz.size,
+                                            self._grd(nz.base), st)
+        if apply_optim:
+            self._enqueue_optim()
+
+    def _enqueue_optim(self):
+        L, ctx = self.L, self.g.ctx
+        st = torch.cuda.current_stream().cuda_stream
+        nc, gf, nz = self.net_c, self.net_gf, self.net_z
+        ea, es = self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
+        L.grapes_adam_step(ctx, self._par(nc.base), self._grd(nc.base), ea + 4 * nc.base, es + 4 * nc.base, nc.size,
+                           self.lr_gc, 0.9, 0.999, 1e-8, self.adam_steps.data_ptr(), 1, st)
+        if not self.random_sampling:
+            n = (nz.end - gf.base) if not self.reinforce else gf.size   # gcn_z has no grad under REINFORCE (main.py:279)
+            L.grapes_adam_step(ctx, self._par(gf.base), self._grd(gf.base), ea + 4 * gf.base, es + 4 * gf.base, n,
+                               self.lr_gf, 0.9, 0.999, 1e-8, self.adam_steps.data_ptr() + 4, 1, st)
+
+    # ------------------------------------------------------------------ public API
+    def set_targets(self, target_nodes: torch.Tensor):
+        t = target_nodes
+        if t.numel() != self.B:
+            raise GrapesError(f"engine built for batch_size={self.B}, got {t.numel()} targets")
+        self.targets.copy_(t.to(torch.int32), non_blocking=True)
+        self.counts[self._CNT["B"]] = self.B
+
+    def step(self, target_nodes: Optional[torch.Tensor] = None, gumbel_noise=None, apply_optim: bool = True,
+             use_graph: bool = False, record: bool = False, noise_mode: int = NOISE_GUMBEL):
+        if target_nodes is not None:
+            self.set_targets(target_nodes)
+        if use_graph:
+            assert gumbel_noise is None and not record
+            key = (apply_optim,)
+            gr = self._graphs.get(key)
+            if gr is None:
+                self.step(None, apply_optim=False)        # warm the allocator / lazy init outside capture
+                torch.cuda.synchronize()
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    self._enqueue(None, apply_optim)
+                self._graphs[key] = gr
+            gr.replay()
+            return None
+        if record:
+            self.record = {"hops": [], "keys_buf": torch.zeros(self.cap_n, dtype=torch.float32, device=self.device)}
+        try:
+            self._enqueue(gumbel_noise, apply_optim, noise_mode)
+        finally:
+            rec, self.record = self.record, None
+        if record:
+            self._record_final(rec)
+        return rec
+
+    def check_overflow(self):
+        v = int(self.overflow.item())
+        if v:
+            names = [n for b, n in OVF_NAMES.items() if v & b]
+            raise GrapesError("frontier capacity exceeded (" + ", ".join(names) + "): raise cap_edges / cap_nodes")
+
+    def scalars(self) -> Dict[str, float]:
+        s = self.scal.cpu()
+        return {k: float(s[i]) for k, i in SCAL.items()}
+
+    def count(self, name: str, idx: int = 0) -> int:
+        return int(self.counts[self._CNT[name] + idx].item())
+
+    # ------------------------------------------------------------------ recording (tests only; syncs)
+    def _record_hop(self, h: int, cur: int):
+        torch.cuda.synchronize()
+        P = self.count("P0" if cur == 0 else "P1")
+        m, n, c, s = self.count("m"), self.count("n"), self.count("c"), self.count("s", h)
+        nxt = (h + 1) % 2
+        r = dict(P=P, m=m, n=n, c=c, s=s,
+                 prev=self.prev[cur][:P].clone(), e_row=self.e_row[:m].clone(), e_col=self.e_col[:m].clone(),
+                 e_src=self.e_src[:m].clone(), e_dst=self.e_dst[:m].clone(),
+                 batch_nodes=self.batch_nodes[:n].clone(), neighbor_nodes=self.nb_nodes[:c].clone(),
+                 nb_local=self.nb_local[:c].clone(), ind_bits=self.ind_bits[:n].clone(),
+                 in_off=self.in_off[:n + 1].clone(), in_src=self.in_src[:self.count("nnz")].clone(),
+                 dinv=self.dinv[:n].clone(), Y=self.Y[:n].clone(), logits_all=self.logits_all[:n].clone(),
+                 sampled=self.prev[nxt][self.B:self.B + s].clone(), log_prob=self.log_prob[h, :c].clone(),
+                 keys=self.record["keys_buf"][:c].clone(), stats=self.stats[h].clone(),
+                 dl_all=self.dl_all[:n].clone(), dz=self.dz[:n].clone(), zlogits=self.zlogits[:n].clone())
+        if h > 0:
+            e = self.count("blk", h - 1)
+            self.record["hops"][h - 1]["block_edges"] = torch.stack([self.blk_src[h - 1][:e], self.blk_dst[h - 1][:e]]).clone()
+        self.record["hops"].append(r)
+
+    def _record_final(self, rec: dict):
+        torch.cuda.synchronize()
+        H = self.H
+        e = self.count("blk", H - 1)
+        rec["hops"][H - 1]["block_edges"] = torch.stack([self.blk_src[H - 1][:e], self.blk_dst[H - 1][:e]]).clone()
+        A = self.count("A")
+        rec["all_nodes"] = self.all_nodes[:A].clone()
+        rec["target_local"] = self.target_local.clone()
+        rec["logits_c"] = self.logits_c[:A].clone()
+        rec["scalars"] = self.scalars()
+        rec["grads"] = {k: {n: t.clone() for n, t in v.items()} for k, v in self.grad_dicts().items()}
+        rec["cl_edges"] = []
+        for slot, hop in ((0, H - 1), (1, 0)):
+            e = self.count("blk", hop)
+            rec["cl_edges"].append(torch.stack([self.cl_src[slot][:e], self.cl_dst[slot][:e]]).clone())
+        rec.pop("keys_buf", None)

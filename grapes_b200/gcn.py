@@ -1,0 +1,173 @@
+"""Drop-in mirror of the reference's ``modules/gcn.py`` ``GCN`` (/root/reference/modules/gcn.py:9-42)
+with ``torch_geometric.nn.GCNConv`` (PyG 2.5.2 defaults) replaced by the C-ABI CUDA kernels.
+
+Parameter names follow PyG (``gcn_layers.{i}.lin.weight`` [out, in], ``gcn_layers.{i}.bias`` [out]) so a
+reference ``state_dict`` loads unchanged.  ``forward`` returns ``(logits, memory_alloc_MB)`` like the
+reference (gcn.py:40-42).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Union
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ._lib import lib, ptr, GrapesError
+from .utils import _any_ctx, _stream
+
+
+class NormAdj:
+    """gcn_norm structure of one edge_index on n nodes: dst-sorted CSR (forward), src-sorted CSR
+    (backward), deg^-1/2 with the added self-loops."""
+
+    def __init__(self, edge_index: torch.Tensor, n: int):
+        if not edge_index.is_cuda:
+            raise GrapesError("grapes_b200 has no CPU fallback: edge_index must live on a CUDA device")
+        dev = edge_index.device
+        self.holder = _any_ctx(dev)
+        L, ctx = lib(), self.holder.ctx
+        E = int(edge_index.shape[1])
+        self.n, self.E = int(n), E
+        src = edge_index[0].to(torch.int32).contiguous()
+        dst = edge_index[1].to(torch.int32).contiguous()
+        capE, capn = max(E, 1), max(self.n, 1)
+        if max(capE, capn) > self.holder.max_frontier:
+            raise GrapesError("edge list larger than the library context's max_frontier")
+        self.cnt = torch.tensor([E, self.n, 0, 0, 0, 0], dtype=torch.int32, device=dev)
+        scratch = torch.zeros(capn, dtype=torch.int32, device=dev)
+        tmp = torch.empty(capE, dtype=torch.int32, device=dev)
+        ovf = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.in_off = torch.zeros(capn + 1, dtype=torch.int32, device=dev)
+        self.in_src = torch.empty(capE, dtype=torch.int32, device=dev)
+        self.out_off = torch.zeros(capn + 1, dtype=torch.int32, device=dev)
+        self.out_dst = torch.empty(capE, dtype=torch.int32, device=dev)
+        self.dinv = torch.empty(capn, dtype=torch.float32, device=dev)
+        c = self.cnt.data_ptr()
+        L.grapes_build_csr(ctx, ptr(dst), ptr(src), c, capE, c + 4, capn, ptr(scratch), ptr(self.in_off),
+                           ptr(self.in_src), ptr(tmp), ptr(self.dinv), c + 8, ptr(ovf), _stream())
+        L.grapes_build_csr(ctx, ptr(src), ptr(dst), c, capE, c + 4, capn, ptr(scratch), ptr(self.out_off),
+                           ptr(self.out_dst), ptr(tmp), None, c + 12, ptr(ovf), _stream())
+
+    def aggregate(self, x: torch.Tensor, transpose: bool = False, bias=None) -> torch.Tensor:
+        L, ctx = lib(), self.holder.ctx
+        x = x.contiguous()
+        Fdim = x.shape[1]
+        out = torch.empty_like(x)
+        off, idx = (self.out_off, self.out_dst) if transpose else (self.in_off, self.in_src)
+        L.grapes_aggregate(ctx, ptr(x), Fdim, Fdim, None, self.cnt.data_ptr() + 4, max(self.n, 1), ptr(off), ptr(idx),
+                           ptr(self.dinv), None, 0, ptr(bias), 0, ptr(out), Fdim, _stream())
+        return out
+
+
+def _gemm(layout, A, lda, B, ldb, M, N, K, bias=None, relu=0):
+    holder = _any_ctx(A.device)
+    C = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    if M > 0:
+        lib().grapes_gemm(holder.ctx, layout, ptr(A), lda, ptr(B), ldb, ptr(C), N, None, M, N, K, ptr(bias), relu,
+                          None, 0, _stream())
+    return C
+
+
+def _gemm_tn(A, B, R, M, N):
+    holder = _any_ctx(A.device)
+    out = torch.zeros((M, N), dtype=torch.float32, device=A.device)
+    if R > 0:
+        lib().grapes_gemm_tn(holder.ctx, ptr(A), M, ptr(B), N, None, R, M, N, 1.0, 0, ptr(out), _stream())
+    return out
+
+
+class _GCNConvFn(torch.autograd.Function):
+    """out = A_hat (x W^T) + b, computed at the narrower width: (A_hat x) W^T when in <= out."""
+
+    @staticmethod
+    def forward(ctx_, x, weight, bias, adj: NormAdj):
+        x = x.contiguous().float()
+        w = weight.contiguous().float()
+        n, I = x.shape
+        O = w.shape[0]
+        ctx_.adj, ctx_.agg_first = adj, I <= O
+        if ctx_.agg_first:
+            y = adj.aggregate(x)
+            out = _gemm(3, y, I, w, I, n, O, I, bias=bias)
+            ctx_.save_for_backward(y, w)
+        else:
+            h = _gemm(3, x, I, w, I, n, O, I)
+            out = adj.aggregate(h, bias=bias)
+            ctx_.save_for_backward(x, w)
+        return out
+
+    @staticmethod
+    def backward(ctx_, dout):
+        saved, w = ctx_.saved_tensors
+        adj = ctx_.adj
+        dout = dout.contiguous().float()
+        n, O = dout.shape
+        I = w.shape[1]
+        need_dx = ctx_.needs_input_grad[0]
+        db = dout.sum(0) if ctx_.needs_input_grad[2] else None
+        dx = None
+        if ctx_.agg_first:
+            dW = _gemm_tn(dout, saved, n, O, I)                       # dout^T (A_hat x)
+            if need_dx:
+                dy = _gemm(1, dout, O, w, I, n, I, O)                # dout W
+                dx = adj.aggregate(dy, transpose=True)
+        else:
+            dh = adj.aggregate(dout, transpose=True)                  # A_hat^T dout
+            dW = _gemm_tn(dh, saved, n, O, I)
+            if need_dx:
+                dx = _gemm(1, dh, O, w, I, n, I, O)
+        return dx, dW, db, None
+
+
+class _Lin(nn.Module):
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels))
+
+
+class GCNConv(nn.Module):
+    """PyG 2.5.2 ``GCNConv(in, out)`` with default arguments (improved=False, cached=False,
+    add_self_loops=True, normalize=True, bias=True); glorot weight, zero bias."""
+
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin = _Lin(in_channels, out_channels)
+        self.bias = nn.Parameter(torch.zeros(out_channels))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        a = math.sqrt(6.0 / (self.in_channels + self.out_channels))
+        with torch.no_grad():
+            self.lin.weight.uniform_(-a, a)
+            self.bias.zero_()
+
+    def forward(self, x, edge_index):
+        adj = edge_index if isinstance(edge_index, NormAdj) else NormAdj(edge_index, x.shape[0])
+        return _GCNConvFn.apply(x, self.lin.weight, self.bias, adj)
+
+
+class GCN(nn.Module):
+    def __init__(self, in_features: int, hidden_dims: List[int], dropout: float = 0.):
+        super(GCN, self).__init__()
+        self.dropout = dropout
+        dims = [in_features] + hidden_dims
+        gcn_layers = []
+        for i in range(len(hidden_dims) - 1):
+            gcn_layers.append(GCNConv(in_channels=dims[i], out_channels=dims[i + 1]))
+        gcn_layers.append(GCNConv(in_channels=dims[-2], out_channels=dims[-1]))
+        self.gcn_layers = nn.ModuleList(gcn_layers)
+
+    def forward(self, x: torch.Tensor, edge_index: Union[torch.Tensor, List[torch.Tensor]]):
+        layerwise_adjacency = type(edge_index) == list
+        for i, layer in enumerate(self.gcn_layers[:-1], start=1):
+            edges = edge_index[-i] if layerwise_adjacency else edge_index
+            x = torch.relu(layer(x, edges))
+            x = F.dropout(x, p=self.dropout, training=self.training)
+        edges = edge_index[0] if layerwise_adjacency else edge_index
+        logits = self.gcn_layers[-1](x, edges)
+        logits = F.dropout(logits, p=self.dropout, training=self.training)
+        memory_alloc = torch.cuda.memory_allocated() / (1024 * 1024)
+        return logits, memory_alloc

@@ -1,0 +1,102 @@
+"""Device-resident CSR graph: what ``adjacency`` is in the reference
+(/root/reference/main.py:134-136, a scipy ``csr_matrix`` on the host) becomes a pair of HBM arrays.
+
+Layout in HBM: ``indptr`` int64 [N+1] (papers100M-shape has nnz = 3.2e9), ``indices`` int32 [nnz],
+rows sorted, duplicates collapsed, self-loops kept -- exactly scipy's canonical CSR of the bool matrix.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from ._lib import lib, ptr, GrapesError
+import ctypes
+
+
+def _require_cuda(device) -> torch.device:
+    device = torch.device(device)
+    if device.type != "cuda" or not torch.cuda.is_available():
+        raise GrapesError("grapes_b200 has no CPU fallback: a CUDA (sm_100a) device is required")
+    return device
+
+
+class DeviceGraph:
+    """CSR adjacency + the per-device library context.
+
+    Accepted wherever the reference passes its scipy ``adjacency`` (get_neighborhoods,
+    slice_adjacency).  Built from the same ``(edge_index, num_nodes)`` the reference feeds scipy.
+    """
+
+    def __init__(self, indptr: torch.Tensor, indices: torch.Tensor, num_nodes: int,
+                 max_frontier: Optional[int] = None, partials_bytes: int = 64 << 20):
+        device = _require_cuda(indptr.device)
+        assert indptr.dtype == torch.int64 and indices.dtype == torch.int32
+        assert indptr.numel() == num_nodes + 1
+        self.device = device
+        self.num_nodes = int(num_nodes)
+        self.indptr = indptr.contiguous()
+        self.indices = indices.contiguous()
+        self.nnz = int(indices.numel())
+        self.num_words = (self.num_nodes + 31) // 32
+        if max_frontier is None:
+            max_frontier = max(self.num_nodes, 1 << 22)
+        self.max_frontier = int(min(max_frontier, (1 << 31) - 1))
+        self._ctx = ctypes.c_void_p()
+        L = lib()
+        rc = L.cdll.grapes_ctx_create(device.index or 0, self.num_nodes, self.max_frontier, partials_bytes,
+                                      ctypes.byref(self._ctx))
+        if rc != 0:
+            raise GrapesError(f"grapes_ctx_create failed ({rc}): {L.last_error()}")
+
+    @property
+    def ctx(self):
+        return self._ctx
+
+    def __del__(self):
+        try:
+            if getattr(self, "_ctx", None):
+                lib().cdll.grapes_ctx_destroy(self._ctx)
+                self._ctx = None
+        except Exception:
+            pass
+
+    @property
+    def shape(self):
+        return (self.num_nodes, self.num_nodes)
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def from_edge_index(cls, edge_index: torch.Tensor, num_nodes: int, device="cuda", **kw) -> "DeviceGraph":
+        """main.py:134-136: ``csr_matrix((ones bool, edge_index), (N, N))`` -- duplicates collapse,
+        columns sorted.  Done with sort/unique on the device (one-off, outside the step)."""
+        device = _require_cuda(device)
+        ei = edge_index.to(device=device, dtype=torch.int64)
+        key = ei[0] * int(num_nodes) + ei[1]
+        del ei
+        key = torch.unique(key, sorted=True)
+        rows = torch.div(key, int(num_nodes), rounding_mode="floor")
+        indices = (key - rows * int(num_nodes)).to(torch.int32)
+        del key
+        counts = torch.bincount(rows, minlength=int(num_nodes))
+        del rows
+        indptr = torch.zeros(int(num_nodes) + 1, dtype=torch.int64, device=device)
+        torch.cumsum(counts, 0, out=indptr[1:])
+        return cls(indptr, indices, num_nodes, **kw)
+
+    @classmethod
+    def from_scipy(cls, adjacency, device="cuda", **kw) -> "DeviceGraph":
+        adjacency = adjacency.tocsr()
+        adjacency.sum_duplicates()
+        adjacency.sort_indices()
+        device = _require_cuda(device)
+        indptr = torch.from_numpy(adjacency.indptr.astype("int64")).to(device)
+        indices = torch.from_numpy(adjacency.indices.astype("int32")).to(device)
+        return cls(indptr, indices, adjacency.shape[0], **kw)
+
+    def to_scipy(self):
+        import numpy as np
+        import scipy.sparse as sp
+        indptr = self.indptr.cpu().numpy()
+        indices = self.indices.cpu().numpy()
+        return sp.csr_matrix((np.ones(indices.shape[0], dtype=bool), indices, indptr), shape=self.shape)

@@ -1,0 +1,177 @@
+/*
+ * grapes_b200 -- C ABI of the B200-native GRAPES sampling-and-aggregation hot path.
+ *
+ * The reference (dfdazac/grapes) has no FFI of its own: its hot path is a set of Python callables
+ * (main.py:15-17 imports GCN, TensorMap, get_neighborhoods, sample_neighborhoods_from_probs,
+ * slice_adjacency).  Every entry point below cites the reference code it replaces
+ * (file:line under /root/reference); INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - every function returns GRAPES_OK (0) or a GRAPES_ERR_* code; grapes_last_error() has the text.
+ *     No C++ exceptions cross the ABI.
+ *   - all pointers except `ctx`, `overflow`-style outputs documented otherwise are DEVICE pointers
+ *     owned by the caller (torch's caching allocator in the Python host).  The library retains
+ *     nothing past a call; its only own state is the ctx workspace.
+ *   - node ids are int32 on the device, CSR `indptr` is int64 (papers100M-shape: nnz = 3.2e9).
+ *   - sizes that depend on the data (`*_dev`) live in device memory so a whole training step can be
+ *     enqueued -- and CUDA-graph captured -- without a host round-trip.  `cap_*` are the host-side
+ *     capacities of the caller's buffers; when data outgrows a capacity the kernel clamps, stays
+ *     memory-safe and ORs a GRAPES_OVF_* bit into `*overflow` (device int).
+ *   - `stream` is a cudaStream_t; kernels are enqueued there, never synchronised, and are safe to
+ *     capture.  One ctx per (process, device), not re-entrant.
+ */
+#ifndef GRAPES_B200_H
+#define GRAPES_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRAPES_OK 0
+#define GRAPES_ERR_ARG 1
+#define GRAPES_ERR_CUDA 2
+#define GRAPES_ERR_NOMEM 3
+
+#define GRAPES_OVF_ROWS 1   /* more rows than cap_P            */
+#define GRAPES_OVF_EDGES 2  /* frontier edges exceed cap_m     */
+#define GRAPES_OVF_NODES 4  /* frontier nodes exceed cap_n     */
+#define GRAPES_OVF_BLOCK 8  /* induced block exceeds cap_out   */
+#define GRAPES_OVF_HUB 16   /* hub-row worklist exceeded       */
+
+/* noise modes of grapes_select_topk */
+#define GRAPES_NOISE_PHILOX 0          /* draw u on the device (Philox4x32-10), g = -log(-log u)          */
+#define GRAPES_NOISE_GUMBEL 1          /* noise[i] = Gumbel(0,1) sample (what utils.py:40-41 draws)       */
+#define GRAPES_NOISE_UNIFORM 2         /* noise[i] = u in (tiny, 1-eps)                                   */
+#define GRAPES_NOISE_KEYS 3            /* noise[i] = perturbed log-prob itself (utils.py:42)              */
+#define GRAPES_NOISE_NONE_TOPK_PROBS 4 /* key = sigmoid(logit): deterministic top-k (eval.py:126-127)     */
+
+/* layout of the float `scal` block of grapes_gfn_finalize */
+#define GRAPES_SCAL_LOSS_C 0
+#define GRAPES_SCAL_TOT_LOG_PROB 1
+#define GRAPES_SCAL_LOG_Z_MEAN 2
+#define GRAPES_SCAL_LOG_Z 3
+#define GRAPES_SCAL_LOSS_GFN 4
+#define GRAPES_SCAL_G_GF 5
+#define GRAPES_SCAL_G_Z 6
+#define GRAPES_SCAL_SUM_DL 7
+#define GRAPES_SCAL_COUNT 16
+
+typedef struct grapes_ctx grapes_ctx;
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* Workspace for one graph of `num_nodes` nodes on CUDA device `device`; `max_frontier` bounds the
+ * number of frontier nodes/edges any later call is given (sizes the scan scratch);
+ * `partials_bytes` sizes the split-K partial buffer of the weight-gradient GEMMs.                 */
+int grapes_ctx_create(int device, int64_t num_nodes, int64_t max_frontier, int64_t partials_bytes, grapes_ctx** out);
+int grapes_ctx_destroy(grapes_ctx* ctx);
+const char* grapes_last_error(void);
+int grapes_abi_version(void);
+int grapes_zero(grapes_ctx* ctx, void* ptr, int64_t bytes, void* stream);
+
+/* ---- frontier expansion / dedup / relabel  (utils.py:74-82, main.py:183-195, utils.py:98-120) */
+/* rows[P] -> row_off[P+1] = exclusive scan of CSR degrees, *m_dev = total.  Sets the bit of every
+ * row in bm_rows (prev_nodes_mask, main.py:185) and of rows with degree > 0 in bm_batch.          */
+int grapes_row_offsets(grapes_ctx* ctx, const int64_t* indptr, const int* rows, const int* P_dev, int cap_P,
+                       int* row_off, int* m_dev, int cap_m, uint32_t* bm_rows, uint32_t* bm_batch, int* overflow,
+                       void* stream);
+/* get_neighborhoods (utils.py:74-82): e_row[e] = position in rows, e_col[e] = neighbour id, row-major
+ * by position, ascending neighbour inside a row.  Marks the neighbours in bm_batch (main.py:186).   */
+int grapes_expand_rows(grapes_ctx* ctx, const int64_t* indptr, const int* indices, const int* rows,
+                       const int* P_dev, int cap_P, const int* row_off, const int* m_dev, int cap_m, int* e_row,
+                       int* e_col, uint32_t* bm_batch, void* stream);
+/* mask -> ascending id lists + local numbering (main.py:187-195).  pref_* = per-word exclusive
+ * popcount prefix (local id of v = pref[v>>5] + popc(bm[v>>5] & ((1<<(v&31))-1)) = TensorMap.map).
+ * nb_* describe batch & ~prev (neighbor_nodes); bm_ind[hop] receives that mask and ind_bits[j]
+ * the indicator columns of batch node j (indicator_features, main.py:167-168,191,199-202).        */
+int grapes_rank_nodes(grapes_ctx* ctx, const uint32_t* bm_batch, const uint32_t* bm_prev, int* pref_batch,
+                      int* pref_nb, int* batch_nodes, int* nb_nodes, int* nb_local, uint32_t* ind_bits,
+                      uint32_t* bm_ind, int ind_rows, int hop, int cap_n, int* n_dev, int* c_dev, int* overflow,
+                      void* stream);
+/* node_map.map(neighborhoods) (main.py:195): local (src, dst) of every expanded edge.             */
+int grapes_edges_to_local(grapes_ctx* ctx, const int* rows, const int* e_row, const int* e_col, const int* m_dev,
+                          int cap_m, const uint32_t* bm, const int* pref, int* e_src, int* e_dst, void* stream);
+/* TensorMap.map on an id list (main.py:213,253-254,259).                                          */
+int grapes_relabel(grapes_ctx* ctx, const int* ids, const int* count_dev, int cap, const uint32_t* bm,
+                   const int* pref, int* out, void* stream);
+/* slice_adjacency (utils.py:85-95) on an already expanded row set: keeps edges whose neighbour is
+ * in bm_cols; GLOBAL ids out, [src = row id, dst = col id], reference ordering.                    */
+int grapes_slice_block(grapes_ctx* ctx, const int* rows, const int* e_row, const int* e_col, const int* m_dev,
+                       int cap_m, const uint32_t* bm_cols, int* out_src, int* out_dst, int cap_out, int* count_dev,
+                       int* overflow, void* stream);
+int grapes_bitmap_set(grapes_ctx* ctx, const int* ids, const int* count_dev, int cap, uint32_t* bm, void* stream);
+int grapes_bitmap_clear_words(grapes_ctx* ctx, const int* ids, const int* count_dev, int cap, uint32_t* bm,
+                              void* stream);
+/* dst[off..off+n) = src; *total_dev = off + n   (batch_nodes = cat([targets, sampled]), main.py:236) */
+int grapes_append_list(grapes_ctx* ctx, const int* src, const int* count_dev, int cap, int* dst, int dst_offset,
+                       int* total_dev, void* stream);
+int grapes_ids_i64_to_i32(grapes_ctx* ctx, const int64_t* in, int n, int* out, int* count_dev, void* stream);
+int grapes_ids_i32_to_i64(grapes_ctx* ctx, const int* in, const int* count_dev, int cap, int64_t* out, void* stream);
+
+/* ---- gcn_norm + aggregation (PyG 2.5.2 GCNConv / gcn_norm; call sites gcn.py:18,21,32,36) ----- */
+/* Edge list (key, val) -> CSR keyed by `key` with key==val edges dropped (add_remaining_self_loops),
+ * values ascending inside a row.  dinv (optional) = (count + 1)^-1/2 = deg^-1/2 incl. the self-loop. */
+int grapes_build_csr(grapes_ctx* ctx, const int* key, const int* val, const int* E_dev, int cap_E, const int* n_dev,
+                     int cap_n, int* cnt_scratch, int* off, int* sorted_val, int* tmp_val, float* dinv, int* nnz_dev,
+                     int* overflow, void* stream);
+/* out[j,:F] = dinv[j]^2 X[g(j)] + sum_s dinv[s] dinv[j] X[g(s)] (+bias)(relu); g = nodes[] or identity.
+ * Indicator columns [F, F+num_ind) from ind_bits; [F+num_ind, ldo) zero-filled.                       */
+int grapes_aggregate(grapes_ctx* ctx, const float* X, int F, int ldx, const int* nodes, const int* n_dev, int cap_n,
+                     const int* in_off, const int* in_src, const float* dinv, const uint32_t* ind_bits, int num_ind,
+                     const float* bias, int relu, float* out, int ldo, void* stream);
+int grapes_aggregate_scalar(grapes_ctx* ctx, const float* z, const int* n_dev, int cap_n, const int* in_off,
+                            const int* in_src, const float* dinv, const float* bias, float* out, float* zero_out,
+                            void* stream);
+/* transposed scalar aggregation on the hop graph (backward of the above), row-major edge list.       */
+int grapes_aggregate_scalar_T(grapes_ctx* ctx, const float* dl, const int* n_dev, int cap_n, const int* P_dev,
+                              int cap_P, const int* row_off, const int* e_src, const int* e_dst, const float* dinv,
+                              float* dz, void* stream);
+/* v[j] = 1/n: gradient of log_z = mean(gcn_z logits) w.r.t. those logits (main.py:227-228)          */
+int grapes_fill_inv_count(grapes_ctx* ctx, float* v, const int* n_dev, int cap_n, void* stream);
+int grapes_vec_sum(grapes_ctx* ctx, const float* v, const int* n_dev, int cap_n, float scale, int divide_by_n,
+                   int accumulate, float* out, void* stream);
+
+/* ---- dense transforms (GCNConv.lin; fp32) ---------------------------------------------------- */
+/* C[M x N] = A . B (+bias)(relu)(gated by relu_gate > 0).  layout bit0: A is [M x K] K-contiguous
+ * (else [K x M]); bit1: B is [N x K] K-contiguous (else [K x N]).  M may be a device count.          */
+int grapes_gemm(grapes_ctx* ctx, int layout, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                const int* M_dev, int M_cap, int N, int K, const float* bias, int relu, const float* relu_gate,
+                int ldg, void* stream);
+/* out[M x N] (+)= scale * A[R x M]^T B[R x N]  (weight gradients; deterministic split over rows)     */
+int grapes_gemm_tn(grapes_ctx* ctx, const float* A, int lda, const float* B, int ldb, const int* R_dev, int R_cap,
+                   int M, int N, float scale, int accumulate, float* out, void* stream);
+int grapes_colsum(grapes_ctx* ctx, const float* Mx, const int* R_dev, int R_cap, int ld, int C, float scale,
+                  int accumulate, float* out, void* stream);
+/* sampler nets (hidden D, out_dim 1; main.py:112-114): z = relu(Y W1^T + b1) . w2, hidden never stored */
+int grapes_sampler_l1_fwd(grapes_ctx* ctx, const float* Y, int ldy, const int* n_dev, int cap_n, int K,
+                          const float* W1, int ldw, int D, const float* b1, const float* w2, float* z, void* stream);
+int grapes_sampler_l1_bwd(grapes_ctx* ctx, const float* Y, int ldy, const int* n_dev, int cap_n, int K,
+                          const float* W1, int ldw, int D, const float* b1, const float* w2, const float* dz,
+                          float* dpre_scratch, float scale, int accumulate, float* gW1, int ldgw, float* gb1,
+                          float* gw2, void* stream);
+
+/* ---- selection (utils.py:13-71; eval.py:126-130) --------------------------------------------- */
+int grapes_select_topk(grapes_ctx* ctx, const float* logits_all, const int* nb_local, const int* nb_nodes,
+                       const int* c_dev, int cap_c, int k, int noise_mode, const float* noise,
+                       unsigned long long* rng_state, uint32_t* ukeys_scratch, float* keys_out, int* sampled_out,
+                       int sampled_offset, int* s_dev, int* total_dev, uint8_t* mask_out, float* log_prob,
+                       float* tot_log_prob, float* stats, float* dl_all, float* sum_dl, uint32_t* bm_mark,
+                       void* stream);
+
+/* ---- losses + optimiser (main.py:117-123,260-291) -------------------------------------------- */
+int grapes_classifier_loss(grapes_ctx* ctx, const float* logits, int ldl, int C, const int* A_dev, int A_cap,
+                           const int* row_ids, const int* targets, int B, const int64_t* labels_i64,
+                           const float* labels_f32, float reg_param, float* dlogits, float* loss_out, void* stream);
+int grapes_gfn_finalize(grapes_ctx* ctx, float* scal, float loss_coef, float log_z_init, int reinforce,
+                        int have_log_z, void* stream);
+int grapes_scale_by_device_scalar(grapes_ctx* ctx, const float* dir, const float* g_dev, int n, float* grad,
+                                  void* stream);
+int grapes_adam_step(grapes_ctx* ctx, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int n,
+                     float lr, float beta1, float beta2, float eps, float* step_dev, int increment_step, void* stream);
+int grapes_fill_f32(grapes_ctx* ctx, float* p, float value, int n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAPES_B200_H */

@@ -1,0 +1,89 @@
+"""Selection parity: the sampled SET is bit-exact when the kernel is fed
+the reference's keys or its logits + Gumbel noise; log-probs / stats within fp32 tolerance."""
+import pytest
+import torch
+
+from oracle import reference_port as rp
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def _run(logits, nb, k, dev, **kw):
+    from grapes_b200.utils import sample_neighborhoods_from_probs
+    return sample_neighborhoods_from_probs(logits.to(dev), nb, k, **kw)
+
+
+@pytest.mark.parametrize("n,k,seed", [(1000, 16, 0), (1135, 16, 1), (63407, 256, 2), (300, 299, 3), (40000, 1, 4)])
+def test_sampled_set_bit_exact_given_gumbel_noise(cuda_device, n, k, seed):
+    g = torch.Generator().manual_seed(seed)
+    logits = torch.randn(n, 1, generator=g) * 2
+    nb = torch.sort(torch.randperm(5 * n, generator=g)[:n]).values
+    noise = rp.draw_gumbel_like_reference(n, g)
+    ref_nodes, ref_lp, ref_stats = rp.sample_neighborhoods_from_probs(logits, nb, k, gumbel_noise=noise)
+    # the k-th / (k+1)-th key gap must exceed fp32 evaluation noise for the set to be well defined
+    keys = rp.perturbed_keys(logits.squeeze(-1), noise)
+    srt = torch.sort(keys, descending=True).values
+    assert (srt[k - 1] - srt[k]) > 1e-5 * srt.abs().max()
+    nodes, lp, stats = _run(logits, nb, k, cuda_device, gumbel_noise=noise)
+    assert torch.equal(nodes.cpu(), ref_nodes)
+    torch.testing.assert_close(lp.cpu(), ref_lp, rtol=RTOL, atol=1e-6)
+    for key in ("min_prob", "max_prob", "mean_entropy", "std_entropy"):
+        torch.testing.assert_close(stats[key].cpu(), ref_stats[key], rtol=1e-4, atol=1e-6)
+
+
+def test_exact_given_keys_with_ties_lowest_index(cuda_device):
+    from grapes_b200.utils import NOISE_KEYS
+    n, k = 5000, 100
+    g = torch.Generator().manual_seed(7)
+    keys = torch.randint(0, 50, (n,), generator=g).float()            # massive ties
+    keys[::97] = float("-inf")
+    logits = torch.zeros(n, 1)
+    nb = torch.arange(n) * 3
+    nodes, _, _ = _run(logits, nb, k, cuda_device, gumbel_noise=keys, noise_mode=NOISE_KEYS)
+    want = nb[torch.sort(rp.stable_topk_indices(keys, k)).values]
+    assert torch.equal(nodes.cpu(), want)
+
+
+def test_take_all_branch(cuda_device):
+    """k >= n: every neighbour kept, log_prob = logsigmoid(logits), empty stats (utils.py:31-33)."""
+    n = 37
+    logits = torch.randn(n, 1, generator=torch.Generator().manual_seed(0))
+    nb = torch.arange(n) * 2 + 1
+    for k in (n, n + 5):
+        nodes, lp, stats = _run(logits, nb, k, cuda_device)
+        assert torch.equal(nodes.cpu(), nb) and stats == {}
+        torch.testing.assert_close(lp.cpu(), torch.nn.functional.logsigmoid(logits.squeeze(-1)), rtol=RTOL, atol=1e-6)
+
+
+def test_log_prob_gradient(cuda_device):
+    n, k = 2000, 64
+    g = torch.Generator().manual_seed(5)
+    logits = (torch.randn(n, 1, generator=g) * 3).requires_grad_(True)
+    nb = torch.arange(n)
+    noise = rp.draw_gumbel_like_reference(n, g)
+    _, ref_lp, _ = rp.sample_neighborhoods_from_probs(logits, nb, k, gumbel_noise=noise)
+    ref_lp.sum().backward()
+    lg = logits.detach().to(cuda_device).requires_grad_(True)
+    from grapes_b200.utils import sample_neighborhoods_from_probs
+    _, lp, _ = sample_neighborhoods_from_probs(lg, nb, k, gumbel_noise=noise)
+    lp.sum().backward()
+    torch.testing.assert_close(lg.grad.cpu(), logits.grad, rtol=RTOL, atol=1e-6)
+
+
+def test_philox_sampler_is_uniform_when_logits_constant(cuda_device):
+    """random_sampling=True: constant logits 100 -> uniform k-subsets (main.py:207).  Property test at
+    a size no oracle loop is needed for: each node's inclusion frequency ~ k/n."""
+    from grapes_b200.utils import sample_neighborhoods_from_probs
+    n, k, trials = 512, 64, 400
+    logits = torch.full((n, 1), 100.0, device=cuda_device)
+    nb = torch.arange(n)
+    hits = torch.zeros(n)
+    rng = torch.tensor([1234, 0], dtype=torch.int64, device=cuda_device)
+    for _ in range(trials):
+        nodes, _, _ = sample_neighborhoods_from_probs(logits, nb, k, rng_state=rng)
+        assert nodes.numel() == k and torch.all(nodes[1:] > nodes[:-1])
+        hits[nodes.cpu()] += 1
+    freq = hits / trials
+    assert abs(freq.mean().item() - k / n) < 1e-6
+    assert freq.min() > 0.04 and freq.max() < 0.25          # k/n = 0.125, sd ~ 0.0165
