@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""Benchmark of the GRAPES sample+train step (BASELINE.json metric: target nodes/sec).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
+
+A "step" is one batch of the reference's training loop (main.py:161-291): 3-hop frontier expansion +
+sampler GCN + Gumbel-top-k per hop, gcn_z, classifier forward/backward, GFlowNet loss backward, both
+Adam updates.  Workload (N=1): the ogbn-products-shaped synthetic graph BASELINE.json's metric is quoted
+on (2,449,029 nodes, 61.9M undirected pairs -> ~123.7M nnz, 100 features, 47 classes, batch 1024,
+k=256/hop, 3 hops, hidden 256).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from grapes_b200.synth import SHAPES  # noqa: E402
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="grapes_b200", choices=["grapes_b200", "reference"])
+    ap.add_argument("--workload", default="products", choices=list(SHAPES))
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--cpu-budget-s", type=float, default=20.0)
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------
+def build_workload(name: str, seed: int, device):
+    """SURVEY.md section 8(d) generator, run with torch ops on `device` (one-off, untimed)."""
+    cfg = dict(SHAPES[name])
+    N, E_dir, F, C, n_train = cfg["N"], cfg["E_dir"], cfg["F"], cfg["C"], cfg["n_train"]
+    g = torch.Generator(device=device).manual_seed(seed)
+    half = E_dir // 2
+    src = torch.randint(0, N, (half,), generator=g, device=device, dtype=torch.int64)
+    dst = torch.randint(0, N, (half,), generator=g, device=device, dtype=torch.int64)
+    key = torch.cat([src * N + dst, dst * N + src])
+    del src, dst
+    key = torch.unique(key, sorted=True)                 # csr_matrix(bool) collapses duplicates (main.py:134)
+    rows = torch.div(key, N, rounding_mode="floor")
+    indices = (key - rows * N).to(torch.int32)
+    del key
+    counts = torch.bincount(rows, minlength=N)
+    del rows
+    indptr = torch.zeros(N + 1, dtype=torch.int64, device=device)
+    torch.cumsum(counts, 0, out=indptr[1:])
+    x = torch.randn(N, F, generator=g, device=device, dtype=torch.float32)
+    y = torch.randint(0, C, (N,), generator=g, device=device, dtype=torch.int64)
+    train_idx = torch.sort(torch.randperm(N, generator=g, device=device)[:n_train]).values
+    return cfg, indptr, indices, x, y, train_idx
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [q.strip() for q in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------
+def cpu_reference_run(cfg, indptr, indices, x, y, train_idx, steps, warmup, budget_s, rank_offset=0):
+    """Times the reference's CPU path (oracle port of main.py:161-291 + restated PyG GCNConv, torch CPU
+    fp32, Adam) on the host cores.  Bounded: stops early once `budget_s` of timed work is spent."""
+    import numpy as np
+    import scipy.sparse as sp
+    from oracle import reference_port as rp
+    from grapes_b200.synth import SynthData
+    torch.set_num_threads(os.cpu_count() or 1)
+    N = cfg["N"]
+    ip, ix = indptr.cpu().numpy(), indices.cpu().numpy()
+    adj = sp.csr_matrix((np.ones(ix.shape[0], dtype=bool), ix, ip), shape=(N, N))
+    data = SynthData(x=x.cpu(), y=y.cpu(), edge_index=torch.zeros(2, 0, dtype=torch.long), train_mask=None,
+                     val_mask=None, test_mask=None, num_nodes=N, num_features=cfg["F"], num_classes=cfg["C"])
+    st = rp.OracleState(data, sampling_hops=cfg["sampling_hops"], num_samples=cfg["num_samples"], hidden_dim=256,
+                        seed=0, adjacency=adj)
+    tr = train_idx.cpu()
+    B = cfg["batch_size"]
+    nb = tr.numel() // B
+    done, t_total = 0, 0.0
+    for j in range(warmup + steps):
+        b = (rank_offset + j) % nb
+        t0 = time.perf_counter()
+        rp.reference_step(st, tr[b * B:(b + 1) * B])
+        dt = time.perf_counter() - t0
+        if j >= warmup:
+            done += 1
+            t_total += dt
+            if t_total > budget_s:
+                break
+    return done, t_total, torch.get_num_threads()
+
+
+def main():
+    args = parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfgname = args.workload
+    have_cuda = torch.cuda.is_available()
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        dev = torch.device("cuda", local_rank) if have_cuda else torch.device("cpu")
+        cfg, indptr, indices, x, y, train_idx = build_workload(cfgname, args.seed, dev)
+        warm = min(args.warmup, 2)
+        done, t_total, threads = cpu_reference_run(cfg, indptr, indices, x, y, train_idx, args.steps, warm,
+                                                   budget_s=150.0)
+        B = cfg["batch_size"]
+        val = done * B / t_total
+        sample = f"{done} of the requested {args.steps} steps of batch {B} (stops after 150 s of timed work), {warm} warm-up"
+        line = {"impl": "reference", "metric": "target nodes/sec (sample+train)", "value": val, "unit": "nodes/s",
+                "n_gpus": args.gpus, "steps": done, "warmup": warm, "ms_per_step": 1e3 * t_total / done,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(cfgname, cfg, 1),
+                "cpu_baseline": {"value": val, "unit": "nodes/s", "cores": threads, "kind": "port", "sample": sample},
+                "e2e": {"value": val, "unit": "nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ this repo's CUDA path
+    if not have_cuda:
+        print("bench.py: no CUDA device -- grapes_b200 has no CPU fallback", file=sys.stderr)
+        return 2
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from grapes_b200._lib import lib
+    from grapes_b200.engine import GrapesEngine
+    from grapes_b200.graph import DeviceGraph
+
+    cfg, indptr, indices, x, y, train_idx = build_workload(cfgname, args.seed, dev)
+    N, F, C, B = cfg["N"], cfg["F"], cfg["C"], cfg["batch_size"]
+    graph = DeviceGraph(indptr, indices, N)
+    eng = GrapesEngine(graph, x, y, num_classes=C, batch_size=B, num_samples=cfg["num_samples"],
+                       sampling_hops=cfg["sampling_hops"], hidden_dim=256, seed=args.seed)
+    L = lib()
+    K, W = args.steps, max(args.warmup, 3)
+    nb = train_idx.numel() // B
+    order = [(rank + j * world) % nb for j in range(W + K)]          # target nodes sharded across ranks
+    batches = torch.stack([train_idx[b * B:(b + 1) * B] for b in order]).to(torch.int32)
+    eng.counts[eng._CNT["B"]] = B
+    use_graph = not args.no_graph
+
+    def one_step(j):
+        eng.targets.copy_(batches[j])
+        if world > 1:
+            eng.step(None, apply_optim=False, use_graph=use_graph)
+            dist.all_reduce(eng.grads, op=dist.ReduceOp.AVG)        # the only collective: gradient allreduce
+            eng._enqueue_optim()
+        else:
+            eng.step(None, apply_optim=True, use_graph=use_graph)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for j in range(W):
+        one_step(j)
+    sync_all()
+    eng.check_overflow()
+    launches0 = L.grapes_kernel_launches()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for j in range(W, W + K):
+        one_step(j)
+    e1.record()
+    sync_all()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    eng.check_overflow()
+    if use_graph:
+        # kernels recorded into the graph once, replayed K times
+        per_step = eng.launches_per_graph + (0 if world == 1 else 4)
+        launches = per_step * K
+    else:
+        launches = L.grapes_kernel_launches() - launches0
+        per_step = launches // K
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * K / (ms / 1e3)
+
+    # ------------------------------------------------------------------ e2e: host buffers in, loss out, every step
+    host_targets = torch.stack([train_idx[b * B:(b + 1) * B] for b in order]).to(torch.int64).cpu().pin_memory()
+    host_scal = torch.zeros(16, dtype=torch.float32).pin_memory()
+    dev_t64 = torch.zeros(B, dtype=torch.int64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def e2e_step(j):
+        dev_t64.copy_(host_targets[j], non_blocking=True)                                # H2D: B int64 ids
+        L.grapes_ids_i64_to_i32(graph.ctx, dev_t64.data_ptr(), B, eng.targets.data_ptr(), eng._cnt("B"), st)
+        if world > 1:
+            eng.step(None, apply_optim=False, use_graph=use_graph)
+            dist.all_reduce(eng.grads, op=dist.ReduceOp.AVG)
+            eng._enqueue_optim()
+        else:
+            eng.step(None, apply_optim=True, use_graph=use_graph)
+        host_scal.copy_(eng.scal, non_blocking=True)                                     # D2H: losses
+        torch.cuda.current_stream().synchronize()                                        # loss_c.item() (main.py:269,291)
+        return float(host_scal[0])
+
+    for j in range(3):
+        e2e_step(j)
+    sync_all()
+    e0.record()
+    for j in range(W, W + K):
+        e2e_step(j)
+    e1.record()
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e = {"value": world * B * K / (e2e_ms / 1e3), "unit": "nodes/s", "h2d_bytes_per_step": B * 8,
+           "d2h_bytes_per_step": 64, "ms_per_step": e2e_ms / K}
+
+    # ------------------------------------------------------------------ per-kernel breakdown + roofline (rank 0)
+    line = None
+    if rank == 0:
+        hbm_peak, tf_peak, peak_src = load_peaks()
+        P_STEPS = 5
+        eng.trace_counts = []
+        L.profiling = True
+        for j in range(P_STEPS):
+            eng.targets.copy_(batches[j])
+            eng.step(None, apply_optim=True, use_graph=False)
+        prof = L.profile_summary()
+        L.profiling = False
+        sizes = [c.cpu() for c in eng.trace_counts]
+        eng.trace_counts = None
+        H = cfg["sampling_hops"]
+        per_hop = []
+        for i in range(H):
+            cs = sizes[i::H][:P_STEPS]
+            per_hop.append({k: sum(int(c[eng._CNT[k]]) for c in cs) / len(cs) for k in ("m", "n", "c", "nnz")})
+        breakdown = {k: round(v[0] / P_STEPS, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+        Fp, ldY, D = eng.Fp, eng.ldY, eng.D
+        n_sum = sum(h["n"] for h in per_hop)
+        nnz_sum = sum(h["nnz"] for h in per_hop)
+        # algorithmic bytes / flops per STEP of each hot entry point
+        alg = {
+            "grapes_aggregate": ("hbm", sum(4 * h["n"] * (F + ldY) + 12 * h["n"] + 4 * h["nnz"] for h in per_hop)),
+            "grapes_sampler_l1_fwd": ("tensor", 2.0 * (n_sum * Fp * D + per_hop[0]["n"] * F * D)),
+            "grapes_sampler_l1_bwd": ("tensor", 4.0 * (n_sum * Fp * D + per_hop[0]["n"] * F * D)),
+        }
+        rooflines = {}
+        for name, (bound, work) in alg.items():
+            if name not in prof:
+                continue
+            sec = prof[name][0] / P_STEPS / 1e3
+            if bound == "hbm":
+                ach = work / sec / 1e9
+                rooflines[name] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                                   "frac": ach / hbm_peak, "traffic": None, "ms_per_step": sec * 1e3}
+            else:
+                ach = work / sec / 1e12
+                rooflines[name] = {"bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
+                                   "frac": ach / tf_peak, "traffic": None, "ms_per_step": sec * 1e3}
+        dominant = max(rooflines, key=lambda k: rooflines[k]["ms_per_step"]) if rooflines else None
+        roof = dict(rooflines[dominant], kernel=dominant, peak_source=peak_src) if dominant else None
+
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            done, t_total, threads = cpu_reference_run(cfg, indptr, indices, x, y, train_idx, 10, 1, args.cpu_budget_s)
+            cpu = {"value": done * B / t_total, "unit": "nodes/s", "cores": threads, "kind": "port",
+                   "sample": f"{done} steps of batch {B} on the same graph (oracle port of main.py:161-291, torch CPU fp32)",
+                   "ms_per_step": 1e3 * t_total / done}
+        line = {"metric": "target nodes/sec (sample+train)", "value": value, "unit": "nodes/s", "n_gpus": world,
+                "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(cfgname, cfg, world),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": int(per_step),
+                "roofline": roof, "rooflines": rooflines, "cpu_baseline": cpu, "breakdown_ms_per_step": breakdown,
+                "frontier": per_hop, "cuda_graph": use_graph}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def workload_config(name, cfg, world):
+    return {"workload": f"{name}-shaped synthetic graph: N={cfg['N']}, directed pairs={cfg['E_dir']} (symmetrised, "
+                        f"duplicates collapsed), F={cfg['F']}, C={cfg['C']}, batch={cfg['batch_size']}, "
+                        f"k={cfg['num_samples']}/hop, hops={cfg['sampling_hops']}, hidden=256, TB loss, Adam",
+            "global_batch": cfg["batch_size"] * world, "parallelism": f"dp{world} (targets sharded, graph+features replicated)",
+            "l2_policy": "inputs larger than L2: 1.5 GB graph+features resident in HBM, every step gathers a different "
+                         "frontier (~180k rows); no explicit flush"}
+
+
+if __name__ == "__main__":
+    sys.exit(main())

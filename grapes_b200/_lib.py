@@ -25,7 +25,7 @@ def parse_header(path: str = HEADER) -> Dict[str, Tuple[str, List[Tuple[str, str
     text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
     text = re.sub(r"//[^\n]*", " ", text)
     out = {}
-    for m in re.finditer(r"(const\s+char\s*\*|int)\s+(grapes_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+    for m in re.finditer(r"(const\s+char\s*\*|int64_t|int)\s+(grapes_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
         ret, name, params = m.group(1), m.group(2), m.group(3)
         plist = []
         params = " ".join(params.split())
@@ -34,7 +34,7 @@ def parse_header(path: str = HEADER) -> Dict[str, Tuple[str, List[Tuple[str, str
                 p = p.strip()
                 mm = re.match(r"(.*?)(\w+)$", p)
                 plist.append((mm.group(1).strip(), mm.group(2)))
-        out[name] = ("char*" if "char" in ret else "int", plist)
+        out[name] = ("char*" if "char" in ret else ("int64" if "64" in ret else "int"), plist)
     return out
 
 
@@ -59,9 +59,11 @@ class _Lib:
         self.protos = parse_header()
         for name, (ret, params) in self.protos.items():
             fn = getattr(self.cdll, name)
-            fn.restype = ctypes.c_char_p if ret == "char*" else ctypes.c_int
+            fn.restype = {"char*": ctypes.c_char_p, "int64": ctypes.c_int64}.get(ret, ctypes.c_int)
             fn.argtypes = [_ctype(t) for t, _ in params]
-        self.launches = 0          # number of C-ABI compute calls issued (bench.py's gpu_launches)
+        self.launches = 0          # number of C-ABI compute calls issued
+        self.profiling = False     # when True every call is bracketed by CUDA events (bench.py breakdown)
+        self._events = []
 
     def last_error(self) -> str:
         return self.cdll.grapes_last_error().decode()
@@ -74,13 +76,34 @@ class _Lib:
             return fn
 
         def call(*args):
-            rc = fn(*args)
+            if self.profiling:
+                import torch
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                rc = fn(*args)
+                e1.record()
+                self._events.append((name, e0, e1))
+            else:
+                rc = fn(*args)
             if rc != 0:
                 raise GrapesError(f"{name} failed ({rc}): {self.last_error()}")
             self.launches += 1
         call.__name__ = name
         setattr(self, name, call)
         return call
+
+
+    def profile_summary(self, reset: bool = True):
+        """name -> (total ms, calls) of the event-bracketed calls since the last reset (syncs)."""
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in self._events:
+            ms, n = out.get(name, (0.0, 0))
+            out[name] = (ms + e0.elapsed_time(e1), n + 1)
+        if reset:
+            self._events = []
+        return out
 
 
 _LIB = None

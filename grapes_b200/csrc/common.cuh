@@ -28,6 +28,7 @@ struct grapes_ctx {
 };
 
 void grapes_set_error(const char* fmt, ...);
+void grapes_count_launches(int n);   // bookkeeping for bench.py's gpu_launches
 
 #define GRAPES_CUDA_OK(expr)                                                              \
     do {                                                                                  \

@@ -4,6 +4,8 @@
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
+static long long g_launches = 0;
+void grapes_count_launches(int n) { g_launches += n; }
 
 void grapes_set_error(const char* fmt, ...) {
     va_list ap;
@@ -16,6 +18,7 @@ extern "C" {
 
 const char* grapes_last_error(void) { return g_err; }
 int grapes_abi_version(void) { return 1; }
+int64_t grapes_kernel_launches(void) { return (int64_t)g_launches; }
 
 int grapes_ctx_create(int device, int64_t num_nodes, int64_t max_frontier, int64_t partials_bytes, grapes_ctx** out) {
     GRAPES_REQUIRE(out != nullptr, "null out");

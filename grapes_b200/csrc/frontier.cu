@@ -440,6 +440,7 @@ int grapes_row_offsets(grapes_ctx* ctx, const int64_t* indptr, const int* rows, 
     GRAPES_REQUIRE(ctx && indptr && rows && P_dev && row_off && m_dev && overflow, "null argument");
     k_row_offsets<<<1, 1024, 0, (cudaStream_t)stream>>>(indptr, rows, P_dev, cap_P, row_off, m_dev, cap_m,
                                                           bm_rows, bm_batch, overflow);
+    grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
 }
@@ -450,6 +451,7 @@ int grapes_expand_rows(grapes_ctx* ctx, const int64_t* indptr, const int* indice
     GRAPES_REQUIRE(ctx && indptr && indices && rows && P_dev && row_off && m_dev && e_row && e_col, "null argument");
     k_expand<<<grid_for(ctx, cap_m, 256), 256, 0, (cudaStream_t)stream>>>(indptr, indices, rows, P_dev, cap_P,
                                                                           row_off, m_dev, e_row, e_col, bm_batch);
+    grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
 }
@@ -467,6 +469,7 @@ int grapes_rank_nodes(grapes_ctx* ctx, const uint32_t* bm_batch, const uint32_t*
     k_rank_scan<<<tiles, RANK_THREADS, 0, (cudaStream_t)stream>>>(
         bm_batch, bm_prev, ctx->num_words, pref_batch, pref_nb, batch_nodes, nb_nodes, nb_local, ind_bits,
         bm_ind, ind_rows, hop, cap_n, n_dev, c_dev, overflow, ctx->scan_status, ctx->scan_counters);
+        grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
 }
@@ -476,6 +479,7 @@ int grapes_edges_to_local(grapes_ctx* ctx, const int* rows, const int* e_row, co
     GRAPES_REQUIRE(ctx && rows && e_row && e_col && m_dev && bm && pref && e_src && e_dst, "null argument");
     k_edge_local<<<grid_for(ctx, cap_m, 256), 256, 0, (cudaStream_t)stream>>>(rows, e_row, e_col, m_dev, bm, pref,
                                                                               e_src, e_dst);
+    grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
 }
@@ -484,6 +488,7 @@ int grapes_relabel(grapes_ctx* ctx, const int* ids, const int* count_dev, int ca
                    const int* pref, int* out, void* stream) {
     GRAPES_REQUIRE(ctx && ids && count_dev && bm && pref && out, "null argument");
     k_relabel<<<grid_for(ctx, cap, 256), 256, 0, (cudaStream_t)stream>>>(ids, count_dev, cap, bm, pref, out);
+    grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
 }
@@ -498,13 +503,19 @@ int grapes_build_csr(grapes_ctx* ctx, const int* key, const int* val, const int*
     GRAPES_REQUIRE(tiles <= ctx->scan_cap_tiles, "scan scratch too small for cap_n");
     GRAPES_CUDA_OK(cudaMemsetAsync(cnt_scratch, 0, sizeof(int) * (size_t)cap_n, s));
     k_hist<<<grid_for(ctx, cap_E, 256), 256, 0, s>>>(key, val, E_dev, cap_E, cnt_scratch);
+    grapes_count_launches(1);
     k_scan_i32<<<grapes_max_i(tiles, 1), SCAN_THREADS, 0, s>>>(cnt_scratch, n_dev, cap_n, off, dinv, nnz_dev,
                                                               ctx->scan_status, ctx->scan_counters);
+    grapes_count_launches(1);
     k_fill<<<grid_for(ctx, cap_E, 256), 256, 0, s>>>(key, val, E_dev, cap_E, off, cnt_scratch, sorted_val);
+    grapes_count_launches(1);
     k_reset_counter<<<1, 1, 0, s>>>(ctx->hub_count);
+    grapes_count_launches(1);
     k_sort_rows<<<grid_for(ctx, cap_n, 256), 256, 0, s>>>(off, n_dev, cap_n, sorted_val, ctx->hub_rows,
                                                           ctx->hub_count, ctx->hub_cap, overflow);
+    grapes_count_launches(1);
     k_sort_hub<<<ctx->sm_count, 256, 0, s>>>(off, sorted_val, tmp_val, ctx->hub_rows, ctx->hub_count, ctx->hub_cap);
+    grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
 }
@@ -519,6 +530,7 @@ int grapes_slice_block(grapes_ctx* ctx, const int* rows, const int* e_row, const
     k_filter_compact<<<tiles, FC_THREADS, 0, (cudaStream_t)stream>>>(rows, e_row, e_col, m_dev, cap_m, bm_cols,
                                                                      out_src, out_dst, cap_out, count_dev, overflow,
                                                                      ctx->scan_status, ctx->scan_counters);
+    grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
 }
@@ -526,6 +538,7 @@ int grapes_slice_block(grapes_ctx* ctx, const int* rows, const int* e_row, const
 int grapes_bitmap_set(grapes_ctx* ctx, const int* ids, const int* count_dev, int cap, uint32_t* bm, void* stream) {
     GRAPES_REQUIRE(ctx && ids && count_dev && bm, "null argument");
     k_bitmap_set_list<<<grid_for(ctx, cap, 256), 256, 0, (cudaStream_t)stream>>>(ids, count_dev, cap, bm);
+    grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
 }
@@ -534,6 +547,7 @@ int grapes_bitmap_clear_words(grapes_ctx* ctx, const int* ids, const int* count_
                               void* stream) {
     GRAPES_REQUIRE(ctx && ids && count_dev && bm, "null argument");
     k_bitmap_clear_list<<<grid_for(ctx, cap, 256), 256, 0, (cudaStream_t)stream>>>(ids, count_dev, cap, bm);
+    grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
 }
@@ -543,6 +557,7 @@ int grapes_append_list(grapes_ctx* ctx, const int* src, const int* count_dev, in
     GRAPES_REQUIRE(ctx && src && count_dev && dst, "null argument");
     k_append_list<<<grid_for(ctx, cap, 256), 256, 0, (cudaStream_t)stream>>>(src, count_dev, cap, dst, dst_offset,
                                                                              total_dev);
+    grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
 }
@@ -550,6 +565,7 @@ int grapes_append_list(grapes_ctx* ctx, const int* src, const int* count_dev, in
 int grapes_ids_i64_to_i32(grapes_ctx* ctx, const int64_t* in, int n, int* out, int* count_dev, void* stream) {
     GRAPES_REQUIRE(ctx && out && (in || n == 0), "null argument");
     k_i64_to_i32<<<grid_for(ctx, n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, n, count_dev);
+    grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
 }
@@ -557,6 +573,7 @@ int grapes_ids_i64_to_i32(grapes_ctx* ctx, const int64_t* in, int n, int* out, i
 int grapes_ids_i32_to_i64(grapes_ctx* ctx, const int* in, const int* count_dev, int cap, int64_t* out, void* stream) {
     GRAPES_REQUIRE(ctx && out && (in || cap == 0), "null argument");
     k_i32_to_i64<<<grid_for(ctx, cap, 256), 256, 0, (cudaStream_t)stream>>>(in, count_dev, cap, out);
+    grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
 }

@@ -509,6 +509,7 @@ int grapes_aggregate(grapes_ctx* ctx, const float* X, int F, int ldx, const int*
     else
         k_agg<1><<<blocks, 256, 0, s>>>(X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias,
                                         relu, out, ldo);
+    grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
 }
@@ -519,6 +520,7 @@ int grapes_aggregate_scalar(grapes_ctx* ctx, const float* z, const int* n_dev, i
     GRAPES_REQUIRE(ctx && z && n_dev && in_off && in_src && dinv && out, "null argument");
     k_agg_scalar<<<grid_for(ctx, cap_n, 256), 256, 0, (cudaStream_t)stream>>>(z, n_dev, cap_n, in_off, in_src, dinv,
                                                                               bias, out, zero_out);
+    grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
 }
@@ -529,8 +531,10 @@ int grapes_aggregate_scalar_T(grapes_ctx* ctx, const float* dl, const int* n_dev
     GRAPES_REQUIRE(ctx && dl && n_dev && P_dev && row_off && e_src && e_dst && dinv && dz, "null argument");
     cudaStream_t s = (cudaStream_t)stream;
     k_dz_self<<<grid_for(ctx, cap_n, 256), 256, 0, s>>>(dl, n_dev, cap_n, dinv, dz);
+    grapes_count_launches(1);
     k_dz_rows<<<grid_for(ctx, (long long)cap_P * 32, 256), 256, 0, s>>>(dl, P_dev, cap_P, row_off, e_src, e_dst, dinv,
                                                                          dz);
+    grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
 }
@@ -538,6 +542,7 @@ int grapes_aggregate_scalar_T(grapes_ctx* ctx, const float* dl, const int* n_dev
 int grapes_fill_inv_count(grapes_ctx* ctx, float* v, const int* n_dev, int cap_n, void* stream) {
     GRAPES_REQUIRE(ctx && v && n_dev, "null argument");
     k_fill_inv_count<<<grid_for(ctx, cap_n, 256), 256, 0, (cudaStream_t)stream>>>(v, n_dev, cap_n);
+    grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
 }
@@ -546,6 +551,7 @@ int grapes_vec_sum(grapes_ctx* ctx, const float* v, const int* n_dev, int cap_n,
                    int accumulate, float* out, void* stream) {
     GRAPES_REQUIRE(ctx && v && n_dev && out, "null argument");
     k_vec_sum<<<1, 1024, 0, (cudaStream_t)stream>>>(v, n_dev, cap_n, scale, divide_by_n, accumulate, out);
+    grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
 }
@@ -563,6 +569,7 @@ int grapes_gemm(grapes_ctx* ctx, int layout, const float* A, int lda, const floa
     const int max_y = grapes_max_i(1, (ctx->sm_count * 4) / tiles_n);
     tiles_m = grapes_min_i(tiles_m, max_y);
     dim3 grid(tiles_n, tiles_m);
+    grapes_count_launches(1);
     switch (layout & 3) {
         case 3: k_gemm<true, true><<<grid, G_THREADS, 0, s>>>(A, lda, B, ldb, C, ldc, M_dev, M_cap, N, K, bias, relu, relu_gate, ldg); break;
         case 1: k_gemm<true, false><<<grid, G_THREADS, 0, s>>>(A, lda, B, ldb, C, ldc, M_dev, M_cap, N, K, bias, relu, relu_gate, ldg); break;
@@ -585,8 +592,10 @@ int grapes_gemm_tn(grapes_ctx* ctx, const float* A, int lda, const float* B, int
     GRAPES_REQUIRE(need <= ctx->partials_bytes, "split-K partial buffer too small");
     dim3 grid(tiles_n, tiles_m, slabs);
     k_gemm_tn_splitk<<<grid, G_THREADS, 0, s>>>(A, lda, B, ldb, R_dev, R_cap, M, N, ctx->partials);
+    grapes_count_launches(1);
     k_reduce_slabs<<<grid_for(ctx, (long long)M * N, 256), 256, 0, s>>>(ctx->partials, slabs, M * N, scale, accumulate,
                                                                        out);
+    grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
 }
@@ -601,7 +610,9 @@ int grapes_colsum(grapes_ctx* ctx, const float* Mx, const int* R_dev, int R_cap,
     GRAPES_REQUIRE((size_t)slabs * C * sizeof(float) <= ctx->partials_bytes, "partial buffer too small");
     dim3 grid(grapes_div_up(C, 256), slabs);
     k_colsum_slabs<<<grid, 256, 0, s>>>(Mx, R_dev, R_cap, ld, C, ctx->partials);
+    grapes_count_launches(1);
     k_colsum<<<grapes_div_up(C, 256), 256, 0, s>>>(ctx->partials, nullptr, slabs, C, C, scale, accumulate, out);
+    grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
 }
@@ -611,6 +622,7 @@ int grapes_sampler_l1_fwd(grapes_ctx* ctx, const float* Y, int ldy, const int* n
     GRAPES_REQUIRE(ctx && Y && n_dev && W1 && b1 && w2 && z, "null argument");
     const int blocks = grapes_max_i(1, grapes_min_i(grapes_div_up(cap_n, GB_M), ctx->sm_count * 2));
     k_l1_fwd<<<blocks, G_THREADS, 0, (cudaStream_t)stream>>>(Y, ldy, n_dev, cap_n, K, W1, ldw, D, b1, w2, z);
+    grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
 }
@@ -629,9 +641,12 @@ int grapes_sampler_l1_bwd(grapes_ctx* ctx, const float* Y, int ldy, const int* n
     float* db1_part = ctx->partials + (size_t)blocks * D;
     k_l1_bwd<<<blocks, G_THREADS, 0, s>>>(Y, ldy, n_dev, cap_n, K, W1, ldw, D, b1, w2, dz, dpre_scratch, D, dw2_part,
                                           db1_part);
+    grapes_count_launches(1);
     // a CTA whose first tile is past n writes zeros (its loops do not run), so all `blocks` rows are valid
     k_colsum<<<grapes_div_up(D, 256), 256, 0, s>>>(dw2_part, nullptr, blocks, D, D, scale, accumulate, gw2);
+    grapes_count_launches(1);
     k_colsum<<<grapes_div_up(D, 256), 256, 0, s>>>(db1_part, nullptr, blocks, D, D, scale, accumulate, gb1);
+    grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     // gW1[D x K] += scale * dpre^T Y   (uses ctx->partials again, stream-ordered after the colsums)
     return grapes_gemm_tn(ctx, dpre_scratch, D, Y, ldy, n_dev, cap_n, D, K, scale, accumulate, gW1, stream);

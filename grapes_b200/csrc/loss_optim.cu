@@ -160,6 +160,7 @@ int grapes_classifier_loss(grapes_ctx* ctx, const float* logits, int ldl, int C,
     GRAPES_CUDA_OK(cudaMemsetAsync(dlogits, 0, sizeof(float) * (size_t)A_cap * ldl, s));
     k_classifier_loss<<<1, LOSS_THREADS, 0, s>>>(logits, ldl, C, A_dev, A_cap, row_ids, targets, B, labels_i64,
                                                  labels_f32, reg_param, dlogits, loss_out);
+    grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
 }
@@ -168,6 +169,7 @@ int grapes_gfn_finalize(grapes_ctx* ctx, float* scal, float loss_coef, float log
                         void* stream) {
     GRAPES_REQUIRE(ctx && scal, "null argument");
     k_gfn_finalize<<<1, 1, 0, (cudaStream_t)stream>>>(scal, loss_coef, log_z_init, reinforce, have_log_z);
+    grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
 }
@@ -176,6 +178,7 @@ int grapes_scale_by_device_scalar(grapes_ctx* ctx, const float* dir, const float
                                   void* stream) {
     GRAPES_REQUIRE(ctx && dir && g_dev && grad, "null argument");
     k_scale_by_dev<<<grid_for(ctx, n, 256), 256, 0, (cudaStream_t)stream>>>(dir, g_dev, n, grad);
+    grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
 }
@@ -187,7 +190,9 @@ int grapes_adam_step(grapes_ctx* ctx, float* params, const float* grads, float* 
     cudaStream_t s = (cudaStream_t)stream;
     k_adam<<<grid_for(ctx, n, 256), 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                  step_dev);
+    grapes_count_launches(1);
     if (increment_step) k_step_inc<<<1, 1, 0, s>>>(step_dev);
+    grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
 }
@@ -195,6 +200,7 @@ int grapes_adam_step(grapes_ctx* ctx, float* params, const float* grads, float* 
 int grapes_fill_f32(grapes_ctx* ctx, float* p, float value, int n, void* stream) {
     GRAPES_REQUIRE(ctx && p, "null argument");
     k_fill_f32<<<grid_for(ctx, n, 256), 256, 0, (cudaStream_t)stream>>>(p, value, n);
+    grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
 }

@@ -260,6 +260,7 @@ int grapes_select_topk(grapes_ctx* ctx, const float* logits_all, const int* nb_l
                                                           noise, rng_state, ukeys_scratch, keys_out, sampled_out,
                                                           sampled_offset, s_dev, total_dev, mask_out, log_prob,
                                                           tot_log_prob, stats, dl_all, sum_dl, bm_mark);
+    grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
 }

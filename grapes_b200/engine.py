@@ -192,7 +192,9 @@ class GrapesEngine:
             glorot_(v["gcn_layers.1.lin.weight"], gen)
         self.const100 = torch.full((self.cap_n,), 100.0, **f32)
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        self.launches_per_graph = 0
         self.record: Optional[dict] = None
+        self.trace_counts: Optional[list] = None     # bench.py: per-hop clones of the device-side sizes
 
     # ------------------------------------------------------------------ helpers
     _CNT = dict(P0=0, P1=1, m=2, n=3, c=4, nnz=5, A=6, B=7, blk=8, s=16, cl_nnz=24)
@@ -338,6 +340,8 @@ class GrapesEngine:
                         L.grapes_fill_f32(ctx, self._dir(nz.b2), 1.0, 1, st)
             if rec is not None:
                 self._record_hop(h, cur)
+            if self.trace_counts is not None:
+                self.trace_counts.append(self.counts.clone())
 
         # ---- last block: slice_adjacency(rows = T u S_{H-1}, cols = prev_{H-1}) ----
         cur, nxt = H % 2, (H + 1) % 2
@@ -438,8 +442,10 @@ class GrapesEngine:
                 self.step(None, apply_optim=False)        # warm the allocator / lazy init outside capture
                 torch.cuda.synchronize()
                 gr = torch.cuda.CUDAGraph()
+                n0 = self.L.grapes_kernel_launches()
                 with torch.cuda.graph(gr):
                     self._enqueue(None, apply_optim)
+                self.launches_per_graph = int(self.L.grapes_kernel_launches() - n0)
                 self._graphs[key] = gr
             gr.replay()
             return None

@@ -34,6 +34,9 @@ def _expand(adjacency: DeviceGraph, rows32: Tensor):
     L, ctx, dev = lib(), adjacency.ctx, adjacency.device
     P = rows32.numel()
     cnt = torch.zeros(4, dtype=torch.int32, device=dev)
+    if P == 0:
+        empty = torch.empty(0, dtype=torch.int32, device=dev)
+        return empty, empty, 0, cnt, torch.zeros(1, dtype=torch.int32, device=dev)
     cnt[0] = P
     row_off = torch.empty(P + 1, dtype=torch.int32, device=dev)
     cap_m = (1 << 31) - 1
@@ -65,6 +68,8 @@ def slice_adjacency(adjacency: DeviceGraph, rows: Tensor, cols: Tensor) -> Tenso
     L, ctx, dev = lib(), adjacency.ctx, adjacency.device
     rows32, cols32 = _i32(rows, dev), _i32(cols, dev)
     e_row, e_col, m, cnt, _ = _expand(adjacency, rows32)
+    if m == 0 or cols32.numel() == 0:
+        return torch.empty((2, 0), dtype=torch.int64, device=dev)
     bm = torch.zeros(adjacency.num_words, dtype=torch.int32, device=dev)
     cnt[2] = cols32.numel()
     L.grapes_bitmap_set(ctx, ptr(cols32), cnt.data_ptr() + 8, max(cols32.numel(), 1), ptr(bm), _stream())
@@ -125,7 +130,7 @@ def _any_ctx(device):
         dev = torch.device(device)
         _CTX_CACHE[key] = DeviceGraph(torch.zeros(2, dtype=torch.int64, device=dev),
                                       torch.zeros(0, dtype=torch.int32, device=dev), 1, max_frontier=1 << 20,
-                                      partials_bytes=1 << 20)
+                                      partials_bytes=64 << 20)
     return _CTX_CACHE[key]
 
 

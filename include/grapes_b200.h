@@ -68,6 +68,8 @@ int grapes_ctx_create(int device, int64_t num_nodes, int64_t max_frontier, int64
 int grapes_ctx_destroy(grapes_ctx* ctx);
 const char* grapes_last_error(void);
 int grapes_abi_version(void);
+/* number of kernels this library has launched (or recorded into a capturing stream) so far      */
+int64_t grapes_kernel_launches(void);
 int grapes_zero(grapes_ctx* ctx, void* ptr, int64_t bytes, void* stream);
 
 /* ---- frontier expansion / dedup / relabel  (utils.py:74-82, main.py:183-195, utils.py:98-120) */

@@ -249,7 +249,7 @@ class OracleState:
     def __init__(self, data, *, sampling_hops=2, num_samples=16, use_indicators=True,
                  hidden_dim=256, lr_gc=1e-3, lr_gf=1e-4, loss_coef=1e4, log_z_init=0.,
                  reg_param=0., dropout=0., random_sampling=False, reinforce_baseline=False,
-                 seed: int = 0, dtype=torch.float32):
+                 seed: int = 0, dtype=torch.float32, adjacency: Optional[sp.csr_matrix] = None):
         self.data = data
         self.hops, self.k = sampling_hops, num_samples
         self.use_indicators = use_indicators
@@ -265,7 +265,7 @@ class OracleState:
         self.opt_c = torch.optim.Adam(self.gcn_c.parameters(), lr=lr_gc)
         self.opt_gf = torch.optim.Adam(list(self.gcn_gf.parameters()) + list(self.gcn_z.parameters()), lr=lr_gf)
         self.loss_fn = nn.CrossEntropyLoss() if data.y.dim() == 1 else nn.BCEWithLogitsLoss()
-        self.adjacency = build_adjacency(data.edge_index, N)
+        self.adjacency = adjacency if adjacency is not None else build_adjacency(data.edge_index, N)
         self.node_map = TensorMap(N)
         self.prev_nodes_mask = torch.zeros(N, dtype=torch.bool)
         self.batch_nodes_mask = torch.zeros(N, dtype=torch.bool)

@@ -1,0 +1,90 @@
+"""Generates the golden fixtures in this directory FROM THE REFERENCE ITSELF: imports
+/root/reference/modules/utils.py (through the scipy tensor-index shim of oracle/ref_import.py) and runs
+its own get_neighborhoods / slice_adjacency / TensorMap / sample_neighborhoods_from_probs and the mask
+dedup statements of main.py:183-195 on seeded synthetic graphs.  Run in the build container only
+(the GPU box has no /root/reference); the .npz outputs are committed.
+
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from grapes_b200.synth import make_synth            # noqa: E402
+from oracle import ref_import                       # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CASES = [("tiny", 0, 32, 8, 2), ("tiny", 1, 50, 4, 3), ("cora", 0, 512, 16, 2)]
+
+
+def main():
+    ru = ref_import.load_reference_utils()
+    for name, seed, B, k, hops in CASES:
+        d = make_synth(name, seed=seed)
+        N = d.num_nodes
+        adj = ref_import.reference_adjacency(d.edge_index, N)
+        train_idx = d.train_mask.nonzero().squeeze(1)
+        target_nodes = train_idx[:B]
+        out = {"N": N, "edge_index": d.edge_index.numpy(), "target_nodes": target_nodes.numpy(), "k": k, "hops": hops,
+               "csr_indptr": adj.m.indptr.astype(np.int64), "csr_indices": adj.m.indices.astype(np.int64)}
+        # ---- the hop loop's integer statements, verbatim from main.py:161-247 with random-but-seeded logits
+        node_map = ru.TensorMap(size=N)
+        prev_nodes_mask = torch.zeros(N, dtype=torch.bool)
+        batch_nodes_mask = torch.zeros(N, dtype=torch.bool)
+        previous_nodes = target_nodes.clone()
+        all_nodes_mask = torch.zeros_like(prev_nodes_mask)
+        all_nodes_mask[target_nodes] = True
+        g = torch.Generator().manual_seed(seed + 77)
+        for hop in range(hops):
+            neighborhoods = ru.get_neighborhoods(previous_nodes, adj)
+            prev_nodes_mask.zero_(); batch_nodes_mask.zero_()
+            prev_nodes_mask[previous_nodes] = True
+            batch_nodes_mask[neighborhoods.view(-1)] = True
+            neighbor_nodes_mask = batch_nodes_mask & ~prev_nodes_mask
+            batch_nodes = node_map.values[batch_nodes_mask]
+            neighbor_nodes = node_map.values[neighbor_nodes_mask]
+            node_map.update(batch_nodes)
+            local_neighborhoods = node_map.map(neighborhoods)
+            logits = torch.randn(neighbor_nodes.shape[0], 1, generator=g) * 2
+            torch.manual_seed(1000 * seed + hop)                  # seeds the Gumbel draw at utils.py:40-41
+            sampled, log_prob, stats = ru.sample_neighborhoods_from_probs(logits, neighbor_nodes, k)
+            torch.manual_seed(1000 * seed + hop)                  # re-draw the identical noise to store it
+            fi = torch.finfo(torch.float32)
+            n = neighbor_nodes.shape[0]
+            noise = np.zeros(0, np.float32)
+            if k < n:
+                from torch.distributions import Gumbel
+                noise = Gumbel(torch.tensor(0.), torch.tensor(1.)).sample((n,)).numpy()
+            all_nodes_mask[sampled] = True
+            batch_next = torch.cat([target_nodes, sampled], dim=0)
+            k_hop_edges = ru.slice_adjacency(adj, rows=batch_next, cols=previous_nodes)
+            p = f"hop{hop}_"
+            out.update({p + "prev": previous_nodes.numpy(), p + "neighborhoods": neighborhoods.numpy(),
+                        p + "batch_nodes": batch_nodes.numpy(), p + "neighbor_nodes": neighbor_nodes.numpy(),
+                        p + "local_neighborhoods": local_neighborhoods.numpy(), p + "logits": logits.numpy(),
+                        p + "gumbel": noise, p + "sampled": sampled.numpy(), p + "log_prob": log_prob.numpy(),
+                        p + "stats": np.array([float(stats[s]) for s in ("min_prob", "max_prob", "mean_entropy", "std_entropy")]
+                                              if stats else [], np.float64),
+                        p + "block_edges": k_hop_edges.numpy()})
+            previous_nodes = batch_next.clone()
+        all_nodes = node_map.values[all_nodes_mask]
+        node_map.update(all_nodes)
+        out["all_nodes"] = all_nodes.numpy()
+        out["local_target_ids"] = node_map.map(target_nodes).numpy()
+        path = os.path.join(HERE, f"hoploop_{name}_s{seed}.npz")
+        np.savez_compressed(path, **out)
+        print("wrote", path, os.path.getsize(path), "bytes")
+    # TensorMap docstring vector (utils.py:104-108)
+    nodes = torch.tensor([22, 32, 42, 52])
+    tm = ru.TensorMap(size=nodes.max() + 1)
+    tm.update(nodes)
+    np.savez(os.path.join(HERE, "tensormap_docstring.npz"), keys=np.array([52, 42, 32, 22, 22]),
+             mapped=tm.map(torch.tensor([52, 42, 32, 22, 22])).numpy())
+
+
+if __name__ == "__main__":
+    main()

@@ -29,7 +29,10 @@ def _setup(name, seed, dev, **kw):
     d = make_synth(name, seed=seed, multilabel=kw.pop("multilabel", False))
     hp = dict(sampling_hops=cfg["sampling_hops"], num_samples=cfg["num_samples"])
     hp.update(kw)
-    st = rp.OracleState(d, seed=seed + 100, dtype=torch.float64, hidden_dim=hp.pop("hidden_dim", 256), **hp)
+    hidden = hp.pop("hidden_dim", 256)
+    st = rp.OracleState(d, seed=seed + 100, dtype=torch.float64, hidden_dim=hidden, **hp)
+    # the same reference path in its own precision (fp32): measures how far fp32 itself sits from fp64
+    st.fp32 = rp.OracleState(d, seed=seed + 100, dtype=torch.float32, hidden_dim=hidden, **hp)
     g = DeviceGraph.from_edge_index(d.edge_index, d.num_nodes, device=dev)
     eng = GrapesEngine(g, d.x.to(dev), d.y.to(dev), num_classes=d.num_classes, batch_size=cfg["batch_size"],
                        hidden_dim=st.gcn_c.gcn_layers[0].lin.weight.shape[0],
@@ -39,8 +42,18 @@ def _setup(name, seed, dev, **kw):
     return d, st, eng, train_idx, cfg["batch_size"]
 
 
+def _grad_tol(got32, ref64):
+    """Gradients are sums of O(frontier) signed terms; their fp32 conditioning is a property of the
+    problem, not of the kernel.  Bar: 1e-5 relative, or -- when the reference's own fp32 evaluation
+    (same path, CPU torch) is already further than that from float64 -- no worse than 2x the reference."""
+    return max(TOL, 2.0 * _rel(got32, ref64))
+
+
 def _check_step(st, eng, targets, dev, apply_optim=True):
     ref = rp.reference_step(st, targets, apply_optim=apply_optim)
+    ref32 = rp.reference_step(st.fp32, targets, gumbel_noise=[h["noise"] for h in ref["hops"]], apply_optim=apply_optim)
+    for a, b in zip(ref32["hops"], ref["hops"]):
+        assert torch.equal(a["sampled"], b["sampled"]), "fp32 / fp64 oracle disagree on the sampled set: pick another seed"
     for h in ref["hops"]:                     # the selection must be well separated for a bit-exact set claim
         if h["keys"] is not None:
             srt = torch.sort(h["keys"], descending=True).values
@@ -80,7 +93,7 @@ def _check_step(st, eng, targets, dev, apply_optim=True):
     assert abs(s["loss_c"] - ref["loss_c"].item()) < TOL * abs(ref["loss_c"].item())
     assert abs(s["tot_log_prob"] - ref["tot_log_prob"].item()) < TOL * abs(ref["tot_log_prob"].item())
     for name, gref in ref["grads_c"].items():
-        assert _rel(rec["grads"]["gcn_c"][name], gref) < TOL, f"grad gcn_c {name}"
+        assert _rel(rec["grads"]["gcn_c"][name], gref) < _grad_tol(ref32["grads_c"][name], gref), f"grad gcn_c {name}"
     if not st.random_sampling:
         assert abs(s["log_z"] - ref["log_z"].item()) < TOL * max(1.0, abs(ref["log_z"].item()))
         assert abs(s["loss_gfn"] - ref["loss_gfn"].item()) < 4 * TOL * abs(ref["loss_gfn"].item())
@@ -99,14 +112,42 @@ def test_step_parity_trajectory_balance(cuda_device, name, seed):
 
 
 def test_three_steps_with_adam(cuda_device):
-    """weights after 3 optimiser steps stay within 1e-4 of the float64 oracle's."""
+    """Weights after optimiser steps track the float64 oracle.  Adam divides by sqrt(v): elements whose
+    gradient is small relative to the tensor's scale amplify fp32 noise, so the bar is 1e-4 of the
+    weight scale or 2x the deviation of the reference's own fp32 run, whichever is larger."""
     d, st, eng, train_idx, B = _setup("cora", 2, cuda_device)
     for i in range(2):
         _check_step(st, eng, train_idx[i * B:(i + 1) * B], cuda_device, apply_optim=True)
-    for key, net in (("gcn_c", st.gcn_c), ("gcn_gf", st.gcn_gf), ("gcn_z", st.gcn_z)):
-        for name, p in net.named_parameters():
+    for key, net, net32 in (("gcn_c", st.gcn_c, st.fp32.gcn_c), ("gcn_gf", st.gcn_gf, st.fp32.gcn_gf),
+                            ("gcn_z", st.gcn_z, st.fp32.gcn_z)):
+        for (name, p), (_, p32) in zip(net.named_parameters(), net32.named_parameters()):
             got = eng.state_dicts()[key][name]
-            assert _rel(got, p.detach()) < 1e-4, f"{key} {name} after Adam"
+            tol = max(1e-4, 2.0 * _rel(p32.detach(), p.detach()))
+            assert _rel(got, p.detach()) < tol, f"{key} {name} after Adam"
+
+
+def test_adam_kernel_matches_torch_adam(cuda_device):
+    """Same gradients in -> same weights out as torch.optim.Adam (main.py:117-118), 6 steps."""
+    from grapes_b200._lib import lib, ptr
+    from grapes_b200.utils import _any_ctx
+    gen = torch.Generator().manual_seed(0)
+    n = 10_007
+    p0 = torch.randn(n, generator=gen)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=3e-3)
+    p = p0.clone().to(cuda_device)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    step = torch.zeros(1, device=cuda_device)
+    ctx = _any_ctx(cuda_device).ctx
+    for i in range(6):
+        g = torch.randn(n, generator=gen) * (10.0 ** (i - 3))
+        ref.grad = g.clone()
+        opt.step()
+        gd = g.to(cuda_device)
+        lib().grapes_adam_step(ctx, ptr(p), ptr(gd), ptr(m), ptr(v), n, 3e-3, 0.9, 0.999, 1e-8, ptr(step), 1,
+                               torch.cuda.current_stream().cuda_stream)
+    torch.testing.assert_close(p.cpu(), ref.detach(), rtol=1e-6, atol=1e-7)
+    assert step.item() == 6.0
 
 
 def test_step_parity_reinforce(cuda_device):

@@ -1,0 +1,148 @@
+"""CPU tests (no GPU): the oracle against the golden vectors generated from the reference's own code
+(tests/golden/make_golden.py), against the reference imported live when /root/reference is present,
+and against closed forms for the un-vendored PyG GCNConv arithmetic."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from grapes_b200.synth import make_synth
+from oracle import ref_import
+from oracle import reference_port as rp
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def test_tensormap_docstring_golden():
+    """utils.py:104-108 -- the only known-answer vector the reference holds."""
+    z = np.load(os.path.join(GOLDEN, "tensormap_docstring.npz"))
+    nodes = torch.tensor([22, 32, 42, 52])
+    tm = rp.TensorMap(size=nodes.max() + 1)
+    tm.update(nodes)
+    got = tm.map(_t(z["keys"]))
+    assert got.tolist() == z["mapped"].tolist() == [3, 2, 1, 0, 0]
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "hoploop_*.npz"))))
+def test_oracle_matches_reference_golden(path):
+    z = np.load(path)
+    N, k, hops = int(z["N"]), int(z["k"]), int(z["hops"])
+    adj = rp.build_adjacency(_t(z["edge_index"]), N)
+    assert np.array_equal(adj.indptr, z["csr_indptr"]) and np.array_equal(adj.indices, z["csr_indices"])
+    target = _t(z["target_nodes"])
+    node_map = rp.TensorMap(N)
+    prev = target.clone()
+    all_mask = torch.zeros(N, dtype=torch.bool)
+    all_mask[target] = True
+    for hop in range(hops):
+        p = f"hop{hop}_"
+        assert torch.equal(prev, _t(z[p + "prev"]))
+        nb = rp.get_neighborhoods(prev, adj)
+        assert torch.equal(nb, _t(z[p + "neighborhoods"]))
+        pm = torch.zeros(N, dtype=torch.bool); bm = torch.zeros(N, dtype=torch.bool)
+        pm[prev] = True; bm[nb.view(-1)] = True
+        batch_nodes = node_map.values[bm]
+        neighbor_nodes = node_map.values[bm & ~pm]
+        assert torch.equal(batch_nodes, _t(z[p + "batch_nodes"]))
+        assert torch.equal(neighbor_nodes, _t(z[p + "neighbor_nodes"]))
+        node_map.update(batch_nodes)
+        assert torch.equal(node_map.map(nb), _t(z[p + "local_neighborhoods"]))
+        logits = _t(z[p + "logits"])
+        noise = _t(z[p + "gumbel"]) if z[p + "gumbel"].size else None
+        for stable in (False, True):
+            sampled, lp, stats = rp.sample_neighborhoods_from_probs(logits, neighbor_nodes, k, gumbel_noise=noise,
+                                                                    stable_ties=stable)
+            assert torch.equal(sampled, _t(z[p + "sampled"]))
+            assert torch.equal(lp, _t(z[p + "log_prob"]))
+            if stats:
+                got = [float(stats[s]) for s in ("min_prob", "max_prob", "mean_entropy", "std_entropy")]
+                assert np.allclose(got, z[p + "stats"], rtol=0, atol=0)
+        all_mask[sampled] = True
+        nxt = torch.cat([target, sampled])
+        assert torch.equal(rp.slice_adjacency(adj, nxt, prev), _t(z[p + "block_edges"]))
+        prev = nxt
+    all_nodes = node_map.values[all_mask]
+    node_map.update(all_nodes)
+    assert torch.equal(all_nodes, _t(z["all_nodes"]))
+    assert torch.equal(node_map.map(target), _t(z["local_target_ids"]))
+
+
+@pytest.mark.skipif(not ref_import.reference_available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("name,seed", [("tiny", 3), ("cora", 1), ("small", 0)])
+def test_oracle_matches_live_reference(name, seed):
+    ru = ref_import.load_reference_utils()
+    d = make_synth(name, seed=seed)
+    adj_ref = ref_import.reference_adjacency(d.edge_index, d.num_nodes)
+    adj = rp.build_adjacency(d.edge_index, d.num_nodes)
+    g = torch.Generator().manual_seed(seed)
+    for P in (1, 7, 200):
+        nodes = torch.randperm(d.num_nodes, generator=g)[:P]
+        assert torch.equal(ru.get_neighborhoods(nodes, adj_ref), rp.get_neighborhoods(nodes, adj))
+        cols = torch.randperm(d.num_nodes, generator=g)[:P + 3]
+        assert torch.equal(ru.slice_adjacency(adj_ref, nodes, cols), rp.slice_adjacency(adj, nodes, cols))
+    for n, k in ((500, 16), (40, 64), (2000, 256)):
+        logits = torch.randn(n, 1, generator=g)
+        nb = torch.arange(n) * 2
+        torch.manual_seed(seed)
+        a = ru.sample_neighborhoods_from_probs(logits, nb, k)
+        torch.manual_seed(seed)
+        b = rp.sample_neighborhoods_from_probs(logits, nb, k, stable_ties=False)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and a[2].keys() == b[2].keys()
+        for key in a[2]:
+            assert torch.equal(a[2][key], b[2][key])
+
+
+def test_gcn_conv_dense_closed_form():
+    """PyG GCNConv == D^-1/2 (A_noloop + I) D^-1/2 X W^T + b with deg = in-degree incl. the loop."""
+    g = torch.Generator().manual_seed(0)
+    n = 40
+    ei = torch.randint(0, n, (2, 150), generator=g)
+    ei[:, :4] = ei[0, :4]                                   # explicit self-loops are replaced, not doubled
+    ei = torch.cat([ei, ei[:, 10:14]], dim=1)               # duplicate edges are KEPT by PyG
+    x = torch.randn(n, 9, dtype=torch.float64, generator=g)
+    W = torch.randn(5, 9, dtype=torch.float64, generator=g)
+    b = torch.randn(5, dtype=torch.float64, generator=g)
+    A = torch.zeros(n, n, dtype=torch.float64)
+    for s, t in ei.t().tolist():
+        if s != t:
+            A[t, s] += 1
+    A += torch.eye(n, dtype=torch.float64)
+    Dm = torch.diag(A.sum(1).pow(-0.5))
+    ref = Dm @ A @ Dm @ x @ W.t() + b
+    assert torch.allclose(rp.gcn_conv(x, ei, W, b), ref, atol=1e-12)
+
+
+def test_gcn_conv_hand_computed_4_nodes():
+    """edges 0->1, 0->2, 3->2 (+ a self-loop 1->1 that is dropped).  deg = [1, 2, 3, 1]."""
+    ei = torch.tensor([[0, 0, 3, 1], [1, 2, 2, 1]])
+    x = torch.tensor([[1.0], [2.0], [3.0], [4.0]], dtype=torch.float64)
+    W = torch.tensor([[2.0]], dtype=torch.float64)
+    out = rp.gcn_conv(x, ei, W, torch.tensor([0.5], dtype=torch.float64))
+    h = 2 * x.squeeze(1)
+    want = torch.tensor([h[0] / 1,
+                         h[1] / 2 + h[0] / (1 * 2) ** 0.5,
+                         h[2] / 3 + h[0] / (1 * 3) ** 0.5 + h[3] / (1 * 3) ** 0.5,
+                         h[3] / 1]) + 0.5
+    assert torch.allclose(out.squeeze(1), want, atol=1e-12)
+
+
+def test_reference_step_runs_and_is_deterministic_given_noise():
+    d = make_synth("tiny", seed=0)
+    tr = d.train_mask.nonzero().squeeze(1)[:32]
+    st = rp.OracleState(d, sampling_hops=2, num_samples=8, seed=1)
+    rec = rp.reference_step(st, tr, apply_optim=False)
+    noise = [h["noise"] for h in rec["hops"]]
+    st2 = rp.OracleState(d, sampling_hops=2, num_samples=8, seed=1)
+    rec2 = rp.reference_step(st2, tr, gumbel_noise=noise, apply_optim=False)
+    assert torch.equal(rec["loss_gfn"], rec2["loss_gfn"])
+    for a, b in zip(rec["hops"], rec2["hops"]):
+        assert torch.equal(a["sampled"], b["sampled"])
+    # trajectory-balance closed form used by the CUDA path: d loss / d logit_i = 2 r (mask_i - p_i)
+    r = rec["log_z"] + rec["tot_log_prob"] + st.loss_coef * rec["loss_c"]
+    assert torch.allclose(rec["loss_gfn"], r * r, rtol=1e-6)
