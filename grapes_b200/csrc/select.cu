@@ -3,9 +3,8 @@
 // (/root/reference/modules/utils.py:13-71) and the deterministic top-k of the mini-batch evaluator
 // (/root/reference/eval.py:126-130), without the per-hop D2H of the mask (utils.py:60).
 //
-// One CTA (1024 threads = 32 warps).  The k-th largest key is found by an MSB-first radix select
-// on order-preserving uint32 keys; every warp builds a private 256-bin digit histogram with
-// match-any aggregation, warps are merged through shared memory.  Ties at the threshold go to the
+// The k-th largest key is found by an MSB-first radix select on order-preserving uint32 keys;
+// warps build digit histograms with match-any aggregation.  Ties at the threshold go to the
 // LOWEST candidate index (torch.topk leaves ties unspecified; the oracle uses the same rule).
 #include "common.cuh"
 
@@ -69,27 +68,54 @@ struct OpMin { __device__ float operator()(float a, float b) const { return fmin
 struct OpMax { __device__ float operator()(float a, float b) const { return fmaxf(a, b); } };
 
 // mode: GRAPES_NOISE_*
-__global__ void __launch_bounds__(SEL_THREADS) k_select(
+//
+// One thread-block CLUSTER of SEL_CTAS CTAs x 1024 threads (distributed shared memory): every CTA
+// scans a strided share of the candidates, digit histograms are merged into CTA 0's shared memory
+// with DSMEM atomics, CTA 0 picks the digit and every CTA reads the running prefix back through
+// DSMEM.  Integer atomics only -> the result does not depend on scheduling.
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+#define SEL_CTAS 8
+
+struct SelShared {
+    int hist[256];                 // CTA 0: cluster-wide digit histogram of the current pass
+    uint32_t prefix;               // CTA 0: bits of the threshold key fixed so far
+    int kr;                        // CTA 0: rank still to be resolved inside the current prefix
+    float part[SEL_CTAS][8];       // CTA 0: per-CTA partial reductions (min, max, esum, evar, lp, dl)
+    long long counts[SEL_CTAS];    // CTA 0: per-CTA (n_eq << 32 | n_gt) of the final pass
+};
+
+__global__ void __cluster_dims__(SEL_CTAS, 1, 1) __launch_bounds__(SEL_THREADS) k_select(
     const float* __restrict__ logits_all, const int* __restrict__ nb_local, const int* __restrict__ nb_nodes,
     const int* __restrict__ c_dev, int cap_c, int k, int mode, const float* __restrict__ noise,
     unsigned long long* rng_state, uint32_t* __restrict__ ukeys, float* __restrict__ keys_out,
     int* __restrict__ sampled_out, int sampled_offset, int* __restrict__ s_dev, int* __restrict__ total_dev,
     uint8_t* __restrict__ mask_out, float* __restrict__ log_prob, float* tot_log_prob, float* __restrict__ stats,
     float* __restrict__ dl_all, float* sum_dl, uint32_t* bm_mark) {
-    __shared__ int s_hist[SEL_WARPS][256];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    __shared__ SelShared sh;
+    __shared__ int s_whist[SEL_WARPS / 4][256];      // 8 sub-histograms per CTA (4 warps share one)
     __shared__ float s_red[SEL_WARPS];
     __shared__ long long s_scan[SEL_WARPS + 2];
-    __shared__ uint32_t s_prefix;
-    __shared__ int s_kr;
+    SelShared* sh0 = cluster.map_shared_rank(&sh, 0);
     const int c = min(*c_dev, cap_c);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gtid = rank * SEL_THREADS + tid, gthreads = SEL_CTAS * SEL_THREADS;
     const bool take_all = (k >= c);                       // utils.py:31-33: no noise is drawn
     unsigned long long seed = 0ull, offset = 0ull;
     if (mode == GRAPES_NOISE_PHILOX) { seed = rng_state[0]; offset = rng_state[1]; }
+    __shared__ float s_bcast_f;
+    __shared__ uint32_t s_bcast_u;
+    __shared__ long long s_bcast_ll;
+    if (tid < 256) sh.hist[tid] = 0;
+    if (tid == 0) { sh.prefix = 0u; sh.kr = k; }
+    cluster.sync();                                        // every CTA of the cluster is running: DSMEM is safe
 
-    // ---- pass 0: keys + probability statistics -------------------------------------------
+    // ---- pass 0: keys + probability statistics (coalesced, strided over the whole cluster) ----
     float pmin = INFINITY, pmax = -INFINITY, esum = 0.f;
-    for (int i = tid; i < c; i += SEL_THREADS) {
+    for (int i = gtid; i < c; i += gthreads) {
         const float l = logits_all[nb_local ? nb_local[i] : i];
         const float p = sigmoidf_(l);
         float key;
@@ -113,82 +139,89 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(
     pmin = block_reduce(pmin, s_red, OpMin(), INFINITY);
     pmax = block_reduce(pmax, s_red, OpMax(), -INFINITY);
     esum = block_reduce(esum, s_red, OpAdd(), 0.f);
-    const float emean = (c > 0) ? esum / (float)c : 0.f;
+    if (tid == 0) { sh0->part[rank][0] = pmin; sh0->part[rank][1] = pmax; sh0->part[rank][2] = esum; }
+    cluster.sync();                                        // also publishes ukeys[] to the other CTAs
+    if (tid == 0) {
+        float t = 0.f;
+        for (int r = 0; r < SEL_CTAS; ++r) t += sh0->part[r][2];              // fixed order
+        s_bcast_f = (c > 0) ? t / (float)c : 0.f;
+    }
+    __syncthreads();
+    const float emean = s_bcast_f;
     float evar = 0.f;
-    for (int i = tid; i < c; i += SEL_THREADS) {
+    for (int i = gtid; i < c; i += gthreads) {
         const float d = entropy_bits(sigmoidf_(logits_all[nb_local ? nb_local[i] : i])) - emean;
         evar = fmaf(d, d, evar);
     }
     evar = block_reduce(evar, s_red, OpAdd(), 0.f);
-    if (tid == 0 && stats) {
-        stats[0] = pmin; stats[1] = pmax; stats[2] = emean;
-        stats[3] = (c > 1) ? sqrtf(evar / (float)(c - 1)) : 0.f;               // unbiased (utils.py:56)
-    }
+    if (tid == 0) sh0->part[rank][3] = evar;
 
-    // ---- radix select of the k-th largest key --------------------------------------------
-    uint32_t thr = 0u;      // threshold key
-    int kr = 0;             // how many of the keys == thr are taken (lowest index first)
+    // ---- radix select of the k-th largest key (MSB first, 8 bits per pass) -------------------
+    uint32_t thr = 0u;
+    int kr = 0;
     if (!take_all) {
-        if (tid == 0) { s_prefix = 0u; s_kr = k; }
-        __syncthreads();
         for (int shift = 24; shift >= 0; shift -= 8) {
-            for (int b = lane; b < 256; b += 32) s_hist[warp][b] = 0;
-            __syncwarp();
-            const uint32_t prefix = s_prefix;
+            for (int b = tid; b < (SEL_WARPS / 4) * 256; b += SEL_THREADS) (&s_whist[0][0])[b] = 0;
+            if (tid == 0) s_bcast_u = sh0->prefix;
+            __syncthreads();
+            const uint32_t prefix = s_bcast_u;
             const uint32_t himask = (shift == 24) ? 0u : (0xffffffffu << (shift + 8));
-            for (int base = 0; base < c; base += SEL_THREADS) {
-                const int i = base + tid;
+            for (int base = 0; base < c; base += gthreads) {
+                const int i = base + gtid;
                 bool valid = false; uint32_t digit = 0u;
                 if (i < c) {
                     const uint32_t u = ukeys[i];
                     valid = (u & himask) == prefix;
                     digit = (u >> shift) & 255u;
                 }
-                // warp-aggregated histogram update
                 const unsigned peers = __match_any_sync(GRAPES_FULL_MASK, valid ? digit : 0xffffffffu);
-                if (valid && lane == (__ffs(peers) - 1)) s_hist[warp][digit] += __popc(peers);
-                __syncwarp();
+                if (valid && lane == (__ffs(peers) - 1)) atomicAdd(&s_whist[warp >> 2][digit], __popc(peers));
             }
             __syncthreads();
-            // merge warps: thread b < 256 sums bin b
             if (tid < 256) {
                 int a = 0;
 #pragma unroll
-                for (int w = 0; w < SEL_WARPS; ++w) a += s_hist[w][tid];
-                s_hist[0][tid] = a;
+                for (int w = 0; w < SEL_WARPS / 4; ++w) a += s_whist[w][tid];
+                if (a) atomicAdd(&sh0->hist[tid], a);                          // DSMEM atomic into CTA 0
             }
-            __syncthreads();
-            if (warp == 0) {
+            cluster.sync();
+            if (rank == 0 && warp == 0) {
                 // walk bins from the top; lane l owns bins [255-8l-7 .. 255-8l] (descending order)
                 int mine[8], msum = 0;
 #pragma unroll
-                for (int t = 0; t < 8; ++t) { mine[t] = s_hist[0][255 - (lane * 8 + t)]; msum += mine[t]; }
+                for (int t = 0; t < 8; ++t) { mine[t] = sh.hist[255 - (lane * 8 + t)]; msum += mine[t]; }
                 const int incl = warp_scan_incl(msum);
                 const int excl = incl - msum;
-                const int krem = s_kr;
+                const int krem = sh.kr;
                 const bool here = (excl < krem) && (incl >= krem);
+                __syncwarp();
                 if (here) {
                     int cum = excl;
 #pragma unroll
                     for (int t = 0; t < 8; ++t) {
                         if (cum + mine[t] >= krem) {
-                            s_prefix = prefix | ((uint32_t)(255 - (lane * 8 + t)) << shift);
-                            s_kr = krem - cum;
+                            sh.prefix = prefix | ((uint32_t)(255 - (lane * 8 + t)) << shift);
+                            sh.kr = krem - cum;
                             break;
                         }
                         cum += mine[t];
                     }
                 }
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < 8; ++t) sh.hist[lane * 8 + t] = 0;        // clean for the next pass
             }
-            __syncthreads();
+            cluster.sync();
         }
-        thr = s_prefix;
-        kr = s_kr;
+        thr = sh0->prefix;
+        kr = sh0->kr;
     }
 
-    // ---- ordered selection: each thread owns a contiguous index range --------------------
-    const int ipt = (c + SEL_THREADS - 1) / SEL_THREADS;
-    const int i0 = min(c, tid * ipt), i1 = min(c, i0 + ipt);
+    // ---- ordered selection: CTA r owns a contiguous chunk, each thread a contiguous sub-range ----
+    const int chunk = (c + SEL_CTAS - 1) / SEL_CTAS;
+    const int cb = min(c, rank * chunk), ce = min(c, cb + chunk);
+    const int ipt = (ce - cb + SEL_THREADS - 1) / SEL_THREADS;
+    const int i0 = min(ce, cb + tid * ipt), i1 = min(ce, i0 + ipt);
     int n_eq = 0, n_gt = 0;
     if (!take_all) {
         for (int i = i0; i < i1; ++i) {
@@ -200,7 +233,16 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(
     long long total;
     const long long packed = ((long long)n_eq << 32) | (long long)n_gt;
     const long long excl = block_scan_excl<long long>(packed, s_scan, &total);
-    int eq_before = (int)(excl >> 32), gt_before = (int)(excl & 0xffffffffll);
+    if (tid == 0) sh0->counts[rank] = total;
+    cluster.sync();
+    if (tid == 0) {
+        long long b = 0;
+        for (int r = 0; r < rank; ++r) b += sh0->counts[r];
+        s_bcast_ll = b;
+    }
+    __syncthreads();
+    const long long before = s_bcast_ll;
+    int eq_before = (int)((before + excl) >> 32), gt_before = (int)((before + excl) & 0xffffffffll);
     float lp_sum = 0.f, dl_sum = 0.f;
     for (int i = i0; i < i1; ++i) {
         bool sel;
@@ -228,18 +270,31 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(
             if (bm_mark && nb_nodes) bitmap_set(bm_mark, g);
         }
     }
-    // fixed-order block sums (thread ranges are contiguous, tree order is fixed)
     lp_sum = block_reduce(lp_sum, s_red, OpAdd(), 0.f);
     dl_sum = block_reduce(dl_sum, s_red, OpAdd(), 0.f);
-    if (tid == 0) {
+    if (tid == 0) { sh0->part[rank][4] = lp_sum; sh0->part[rank][5] = dl_sum; }
+    cluster.sync();
+    if (rank == 0 && tid == 0) {
+        float mn = INFINITY, mx = -INFINITY, ev = 0.f, lp = 0.f, dl = 0.f;
+        for (int r = 0; r < SEL_CTAS; ++r) {                                   // fixed order -> deterministic
+            mn = fminf(mn, sh.part[r][0]); mx = fmaxf(mx, sh.part[r][1]);
+            ev += sh.part[r][3]; lp += sh.part[r][4]; dl += sh.part[r][5];
+        }
         const int s = take_all ? c : k;
         if (s_dev) *s_dev = s;
         if (total_dev) *total_dev = sampled_offset + s;
-        if (tot_log_prob) *tot_log_prob += lp_sum;
-        if (sum_dl) *sum_dl += dl_sum;
-        if (take_all && stats) { stats[0] = stats[1] = stats[2] = stats[3] = 0.f; }   // reference returns {}
+        if (tot_log_prob) *tot_log_prob += lp;
+        if (sum_dl) *sum_dl += dl;
+        if (stats) {
+            if (take_all) { stats[0] = stats[1] = stats[2] = stats[3] = 0.f; }   // reference returns {}
+            else {
+                stats[0] = mn; stats[1] = mx; stats[2] = emean;
+                stats[3] = (c > 1) ? sqrtf(ev / (float)(c - 1)) : 0.f;         // unbiased (utils.py:56)
+            }
+        }
         if (mode == GRAPES_NOISE_PHILOX && !take_all) rng_state[1] = offset + 1ull;
     }
+    cluster.sync();                                        // keep CTA 0's shared memory alive until all are done
 }
 
 extern "C" {
@@ -256,7 +311,7 @@ int grapes_select_topk(grapes_ctx* ctx, const float* logits_all, const int* nb_l
     GRAPES_REQUIRE(!(noise_mode == GRAPES_NOISE_GUMBEL || noise_mode == GRAPES_NOISE_UNIFORM ||
                      noise_mode == GRAPES_NOISE_KEYS) || noise, "noise array required");
     GRAPES_REQUIRE(noise_mode != GRAPES_NOISE_PHILOX || rng_state, "rng_state required");
-    k_select<<<1, SEL_THREADS, 0, (cudaStream_t)stream>>>(logits_all, nb_local, nb_nodes, c_dev, cap_c, k, noise_mode,
+    k_select<<<SEL_CTAS, SEL_THREADS, 0, (cudaStream_t)stream>>>(logits_all, nb_local, nb_nodes, c_dev, cap_c, k, noise_mode,
                                                           noise, rng_state, ukeys_scratch, keys_out, sampled_out,
                                                           sampled_offset, s_dev, total_dev, mask_out, log_prob,
                                                           tot_log_prob, stats, dl_all, sum_dl, bm_mark);

