@@ -191,6 +191,7 @@ class GrapesEngine:
             glorot_(v["gcn_layers.0.lin.weight"], gen)
             glorot_(v["gcn_layers.1.lin.weight"], gen)
         self.const100 = torch.full((self.cap_n,), 100.0, **f32)
+        self.bsz = self.B                   # current batch size (<= capacity B); the last batch of an epoch is partial
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self.launches_per_graph = 0
         self.record: Optional[dict] = None
@@ -235,7 +236,7 @@ class GrapesEngine:
                  noise_mode: int = NOISE_GUMBEL):
         L, g, ctx = self.L, self.g, self.g.ctx
         st = torch.cuda.current_stream().cuda_stream
-        B, k, H, F, Fp, D, C, W = self.B, self.k, self.H, self.F, self.Fp, self.D, self.C, self.W
+        B, k, H, F, Fp, D, C, W = self.bsz, self.k, self.H, self.F, self.Fp, self.D, self.C, self.W
         ovf = ptr(self.overflow)
         rec = self.record
         indptr, indices, X = ptr(g.indptr), ptr(g.indices), ptr(self.x)
@@ -425,10 +426,12 @@ class GrapesEngine:
     # ------------------------------------------------------------------ public API
     def set_targets(self, target_nodes: torch.Tensor):
         t = target_nodes
-        if t.numel() != self.B:
-            raise GrapesError(f"engine built for batch_size={self.B}, got {t.numel()} targets")
-        self.targets.copy_(t.to(torch.int32), non_blocking=True)
-        self.counts[self._CNT["B"]] = self.B
+        b = int(t.numel())
+        if b > self.B or b < 1:
+            raise GrapesError(f"engine built for batch_size<={self.B}, got {b} targets")
+        self.bsz = b
+        self.targets[:b].copy_(t.to(torch.int32), non_blocking=True)
+        self.counts[self._CNT["B"]] = b
 
     def step(self, target_nodes: Optional[torch.Tensor] = None, gumbel_noise=None, apply_optim: bool = True,
              use_graph: bool = False, record: bool = False, noise_mode: int = NOISE_GUMBEL):
@@ -436,7 +439,7 @@ class GrapesEngine:
             self.set_targets(target_nodes)
         if use_graph:
             assert gumbel_noise is None and not record
-            key = (apply_optim,)
+            key = (apply_optim, self.bsz)
             gr = self._graphs.get(key)
             if gr is None:
                 self.step(None, apply_optim=False)        # warm the allocator / lazy init outside capture
@@ -485,7 +488,7 @@ class GrapesEngine:
                  nb_local=self.nb_local[:c].clone(), ind_bits=self.ind_bits[:n].clone(),
                  in_off=self.in_off[:n + 1].clone(), in_src=self.in_src[:self.count("nnz")].clone(),
                  dinv=self.dinv[:n].clone(), Y=self.Y[:n].clone(), logits_all=self.logits_all[:n].clone(),
-                 sampled=self.prev[nxt][self.B:self.B + s].clone(), log_prob=self.log_prob[h, :c].clone(),
+                 sampled=self.prev[nxt][self.bsz:self.bsz + s].clone(), log_prob=self.log_prob[h, :c].clone(),
                  keys=self.record["keys_buf"][:c].clone(), stats=self.stats[h].clone(),
                  dl_all=self.dl_all[:n].clone(), dz=self.dz[:n].clone(), zlogits=self.zlogits[:n].clone())
         if h > 0:
@@ -500,7 +503,7 @@ class GrapesEngine:
         rec["hops"][H - 1]["block_edges"] = torch.stack([self.blk_src[H - 1][:e], self.blk_dst[H - 1][:e]]).clone()
         A = self.count("A")
         rec["all_nodes"] = self.all_nodes[:A].clone()
-        rec["target_local"] = self.target_local.clone()
+        rec["target_local"] = self.target_local[:self.bsz].clone()
         rec["logits_c"] = self.logits_c[:A].clone()
         rec["scalars"] = self.scalars()
         rec["grads"] = {k: {n: t.clone() for n, t in v.items()} for k, v in self.grad_dicts().items()}

@@ -1,0 +1,103 @@
+"""``train(args)`` with the reference's contract (/root/reference/main.py:57-364): same ``Arguments``,
+same epoch / batch order (sequential, un-shuffled batches of ``train_idx``, last batch partial,
+main.py:125-126), same return tuple ``(test_f1, mem_point1, mem_point2, mem_point3)``; the batch body runs
+on :class:`grapes_b200.engine.GrapesEngine` instead of scipy + PyG.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+
+from ._lib import GrapesError
+from .args import Arguments
+from .data import get_data
+from .engine import GrapesEngine
+from .gcn import GCN
+from .graph import DeviceGraph
+from .utils import get_logger
+
+
+@torch.inference_mode()
+def evaluate(engine: GrapesEngine, data, mask: torch.Tensor, full_batch: bool = True):
+    """Full-batch evaluation (/root/reference/eval.py:47-70) on the device: one full-graph forward of the
+    classifier through the same CUDA GCNConv kernels, accuracy and micro-F1 (multi-label: TP/FP/FN F1)."""
+    if not full_batch:
+        raise NotImplementedError("mini-batch evaluation (eval.py:71-163) is a 'next' row (DESIGN.md section 7)")
+    dev = engine.device
+    gcn_c = GCN(engine.F, [engine.D, engine.C]).to(dev)
+    gcn_c.load_state_dict(engine.state_dicts()["gcn_c"])
+    gcn_c.eval()
+    logits, _ = gcn_c(engine.x, data.edge_index.to(dev))
+    mask = mask.to(dev)
+    y = engine.y
+    if y.dim() == 1:
+        pred = torch.argmax(logits, dim=1)[mask]
+        acc = (pred == y[mask]).float().mean().item()
+        return acc, acc                                   # micro-F1 == accuracy for single-label multi-class
+    y_pred = logits[mask] > 0
+    y_true = y[mask] > 0.5
+    tp = int((y_true & y_pred).sum()); fp = int((~y_true & y_pred).sum()); fn = int((y_true & ~y_pred).sum())
+    try:
+        precision, recall = tp / (tp + fp), tp / (tp + fn)
+        f1 = 2 * precision * recall / (precision + recall)
+    except ZeroDivisionError:
+        f1 = 0.
+    return f1, f1
+
+
+def train(args: Arguments, data=None, device: Optional[torch.device] = None, use_cuda_graph: bool = True,
+          max_batches: Optional[int] = None):
+    logger = get_logger()
+    if not torch.cuda.is_available():
+        raise GrapesError("grapes_b200 has no CPU fallback: a CUDA (sm_100a) device is required")
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    if data is None:
+        path = os.path.join(os.getcwd(), 'data', args.dataset)
+        data, num_features, num_classes = get_data(root=path, name=args.dataset, seed=args.seed, split_id=args.split_id)
+    else:
+        num_features, num_classes = data.num_features, data.num_classes
+    if args.embed_nodes or data.x is None:
+        if not args.embed_nodes:
+            raise ValueError('Dataset does not contain node features, and embed_nodes is False. '
+                             'Did you mean to run with --embed_nodes=True?')          # main.py:91-94
+        raise NotImplementedError("embed_nodes (learned node features) is a 'next' row (DESIGN.md section 7)")
+    if args.model_type != 'gcn':
+        raise ValueError("only model_type='gcn' is wired in the reference's train() (main.py:109)")
+    if args.dropout != 0.:
+        raise NotImplementedError("dropout > 0 is not used by any reference config; use grapes_b200.gcn.GCN directly")
+
+    graph = DeviceGraph.from_edge_index(data.edge_index, data.num_nodes, device=device)
+    engine = GrapesEngine(graph, data.x.to(device).contiguous(), data.y.to(device), num_classes=num_classes,
+                          batch_size=args.batch_size, num_samples=args.num_samples, sampling_hops=args.sampling_hops,
+                          use_indicators=args.use_indicators, hidden_dim=args.hidden_dim, lr_gc=args.lr_gc,
+                          lr_gf=args.lr_gf, loss_coef=args.loss_coef, log_z_init=args.log_z_init,
+                          reg_param=args.reg_param, random_sampling=args.random_sampling,
+                          reinforce_baseline=args.reinforce_baseline, seed=0 if args.seed is None else args.seed)
+    train_idx = data.train_mask.nonzero().squeeze(1).to(device)
+    batches = list(torch.split(train_idx, args.batch_size))      # DataLoader(TensorDataset(train_idx), batch_size)
+    if max_batches is not None:
+        batches = batches[:max_batches]
+
+    mem1, mem2, mem3 = [], [], []
+    logger.info('Training')
+    test_f1 = 0.0
+    for epoch in range(1, args.max_epochs + 1):
+        acc_c = torch.zeros((), device=device)
+        acc_gfn = torch.zeros((), device=device)
+        for batch in batches:
+            engine.step(batch, use_graph=use_cuda_graph)
+            acc_c += engine.scal[0] / len(batches)               # deferred: no .item() inside the loop
+            acc_gfn += engine.scal[4] / len(batches)
+            mb = torch.cuda.memory_allocated() / (1024 * 1024)
+            mem1.append(torch.cuda.max_memory_allocated() / (1024 * 1024)); mem2.append(mb); mem3.append(mb)
+        engine.check_overflow()
+        if (epoch + 1) % args.eval_frequency == 0:                # main.py:319
+            accuracy, f1 = evaluate(engine, data, data.val_mask, full_batch=args.eval_full_batch)
+            logger.info(f'loss_gfn={acc_gfn.item():.6f}, loss_c={acc_c.item():.6f}, '
+                        f'valid_accuracy={accuracy:.3f}, valid_f1={f1:.3f}')
+    test_accuracy, test_f1 = evaluate(engine, data, data.test_mask, full_batch=args.eval_full_batch)
+    logger.info(f'test_accuracy={test_accuracy:.3f}, test_f1={test_f1:.3f}')
+    train.last_engine = engine
+    return test_f1, mem1, mem2, mem3
