@@ -12,6 +12,12 @@ template <> struct VecT<1> { typedef float T; };
 template <> struct VecT<2> { typedef float2 T; };
 template <> struct VecT<4> { typedef float4 T; };
 
+__device__ __forceinline__ float f32_to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
 template <int VEC>
 __device__ __forceinline__ void vec_fma(float (&acc)[VEC], float w, const float* p) {
     typename VecT<VEC>::T v = *reinterpret_cast<const typename VecT<VEC>::T*>(p);
@@ -37,7 +43,8 @@ __global__ void __launch_bounds__(256) k_agg(const float* __restrict__ X, int F,
                                              const int* __restrict__ in_off, const int* __restrict__ in_src,
                                              const float* __restrict__ dinv, const uint32_t* __restrict__ ind_bits,
                                              int num_ind, const float* __restrict__ bias, int relu,
-                                             float* __restrict__ out, int ldo) {
+                                             float* __restrict__ out, int ldo, float* __restrict__ out_hi,
+                                             float* __restrict__ out_lo) {
     const int n = min(*n_dev, cap_n);
     const int lane = lane_id();
     const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -46,7 +53,9 @@ __global__ void __launch_bounds__(256) k_agg(const float* __restrict__ X, int F,
         const int beg = in_off[j], end = in_off[j + 1];
         const size_t gj = nodes ? (size_t)nodes[j] : (size_t)j;
         const float* xj = X + gj * ldx;
-        float* oj = out + (size_t)j * ldo;
+        float* oj = out ? out + (size_t)j * ldo : nullptr;
+        float* ohj = out_hi ? out_hi + (size_t)j * ldo : nullptr;
+        float* olj = out_hi ? out_lo + (size_t)j * ldo : nullptr;
         for (int cb = 0; cb < F; cb += 32 * VEC) {           // warp-uniform trip count
             const int c0 = cb + lane * VEC;
             const bool act = c0 < F;
@@ -77,7 +86,14 @@ __global__ void __launch_bounds__(256) k_agg(const float* __restrict__ X, int F,
                     if (relu) v = fmaxf(v, 0.f);
                     acc[i] = v;
                 }
-                *reinterpret_cast<typename VecT<VEC>::T*>(oj + c0) = *reinterpret_cast<typename VecT<VEC>::T*>(acc);
+                if (oj) *reinterpret_cast<typename VecT<VEC>::T*>(oj + c0) = *reinterpret_cast<typename VecT<VEC>::T*>(acc);
+                if (ohj) {                                   // 3xTF32 operand split for the tcgen05 GEMM
+                    float h[VEC], l[VEC];
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) { h[i] = f32_to_tf32(acc[i]); l[i] = f32_to_tf32(acc[i] - h[i]); }
+                    *reinterpret_cast<typename VecT<VEC>::T*>(ohj + c0) = *reinterpret_cast<typename VecT<VEC>::T*>(h);
+                    *reinterpret_cast<typename VecT<VEC>::T*>(olj + c0) = *reinterpret_cast<typename VecT<VEC>::T*>(l);
+                }
             }
         }
         if (ldo > F) {
@@ -89,14 +105,19 @@ __global__ void __launch_bounds__(256) k_agg(const float* __restrict__ X, int F,
                     a = fmaf(dinv[sl] * dj, (float)((ind_bits[sl] >> lane) & 1u), a);
                 }
             }
-            for (int c = F + lane; c < ldo; c += 32) oj[c] = (c < F + num_ind) ? a : 0.f;
+            for (int c = F + lane; c < ldo; c += 32) {
+                const float v = (c < F + num_ind) ? a : 0.f;
+                if (oj) oj[c] = v;
+                if (ohj) { const float h = f32_to_tf32(v); ohj[c] = h; olj[c] = f32_to_tf32(v - h); }
+            }
         }
     }
 }
 
 // scalar (width-1) aggregation, one thread per row:  out[j] = dinv[j]^2 z[j] + sum w z[src] + bias
 // optional `zero_out[j] = 0` clears a companion vector in the same pass.
-__global__ void __launch_bounds__(256) k_agg_scalar(const float* __restrict__ z, const int* __restrict__ n_dev,
+__global__ void __launch_bounds__(256) k_agg_scalar(const float* __restrict__ z, int nparts, int part_stride,
+                                                    const int* __restrict__ n_dev,
                                                     int cap_n, const int* __restrict__ in_off,
                                                     const int* __restrict__ in_src, const float* __restrict__ dinv,
                                                     const float* __restrict__ bias, float* __restrict__ out,
@@ -105,11 +126,15 @@ __global__ void __launch_bounds__(256) k_agg_scalar(const float* __restrict__ z,
     const float b = bias ? bias[0] : 0.f;
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
         const float dj = dinv[j];
-        float a = dj * dj * z[j];
+        float zj = z[j];
+        for (int t = 1; t < nparts; ++t) zj += z[(size_t)t * part_stride + j];
+        float a = dj * dj * zj;
         const int end = in_off[j + 1];
         for (int p = in_off[j]; p < end; ++p) {
             const int sl = in_src[p];
-            a = fmaf(dinv[sl] * dj, z[sl], a);
+            float zs = z[sl];
+            for (int t = 1; t < nparts; ++t) zs += z[(size_t)t * part_stride + sl];
+            a = fmaf(dinv[sl] * dj, zs, a);
         }
         out[j] = a + b;
         if (zero_out) zero_out[j] = 0.f;
@@ -491,34 +516,37 @@ extern "C" {
 
 int grapes_aggregate(grapes_ctx* ctx, const float* X, int F, int ldx, const int* nodes, const int* n_dev, int cap_n,
                      const int* in_off, const int* in_src, const float* dinv, const uint32_t* ind_bits, int num_ind,
-                     const float* bias, int relu, float* out, int ldo, void* stream) {
-    GRAPES_REQUIRE(ctx && X && n_dev && in_off && in_src && dinv && out, "null argument");
+                     const float* bias, int relu, float* out, int ldo, float* out_hi, float* out_lo, void* stream) {
+    GRAPES_REQUIRE(ctx && X && n_dev && in_off && in_src && dinv && (out || out_hi), "null argument");
+    GRAPES_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), "out_hi and out_lo go together");
     GRAPES_REQUIRE(ldo >= F + num_ind, "ldo too small");
     GRAPES_REQUIRE(num_ind == 0 || ind_bits, "indicator columns need ind_bits");
     GRAPES_REQUIRE(num_ind <= 8, "at most 8 indicator columns");
     cudaStream_t s = (cudaStream_t)stream;
     const int blocks = grid_for(ctx, (long long)cap_n * 32, 256, 8);
-    const bool a16 = ((((size_t)X) | ((size_t)out)) & 15) == 0;
-    const bool a8 = ((((size_t)X) | ((size_t)out)) & 7) == 0;
+    const size_t al = ((size_t)X) | ((size_t)out) | ((size_t)out_hi) | ((size_t)out_lo);
+    const bool a16 = (al & 15) == 0;
+    const bool a8 = (al & 7) == 0;
     if (a16 && (F % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0))
         k_agg<4><<<blocks, 256, 0, s>>>(X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias,
-                                        relu, out, ldo);
+                                        relu, out, ldo, out_hi, out_lo);
     else if (a8 && (F % 2 == 0) && (ldx % 2 == 0) && (ldo % 2 == 0))
         k_agg<2><<<blocks, 256, 0, s>>>(X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias,
-                                        relu, out, ldo);
+                                        relu, out, ldo, out_hi, out_lo);
     else
         k_agg<1><<<blocks, 256, 0, s>>>(X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias,
-                                        relu, out, ldo);
+                                        relu, out, ldo, out_hi, out_lo);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
 }
 
-int grapes_aggregate_scalar(grapes_ctx* ctx, const float* z, const int* n_dev, int cap_n, const int* in_off,
+int grapes_aggregate_scalar(grapes_ctx* ctx, const float* z, int nparts, int part_stride, const int* n_dev, int cap_n, const int* in_off,
                             const int* in_src, const float* dinv, const float* bias, float* out, float* zero_out,
                             void* stream) {
     GRAPES_REQUIRE(ctx && z && n_dev && in_off && in_src && dinv && out, "null argument");
-    k_agg_scalar<<<grid_for(ctx, cap_n, 256), 256, 0, (cudaStream_t)stream>>>(z, n_dev, cap_n, in_off, in_src, dinv,
+    GRAPES_REQUIRE(nparts >= 1, "nparts >= 1");
+    k_agg_scalar<<<grid_for(ctx, cap_n, 256), 256, 0, (cudaStream_t)stream>>>(z, nparts, part_stride, n_dev, cap_n, in_off, in_src, dinv,
                                                                               bias, out, zero_out);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();

@@ -1,0 +1,354 @@
+// tcgen05 (5th-gen tensor core) path for the sampler networks' dense transform -- the only true
+// contraction on the GRAPES hot path (gcn_gf / gcn_z layer 1: [n x K] . [K x 256], main.py:112-114,210,227).
+//
+//   z[j] = sum_d relu(Y[j,:] . W1[d,:] + b1[d]) * w2[d]          (hidden activations never leave the SM)
+//
+// fp32-accurate on TF32 tensor cores by operand splitting (3xTF32): Y = Yh + Yl, W = Wh + Wl with
+// Xh = tf32(X), Xl = tf32(X - Xh);  Y.W ~= Yh.Wh + Yh.Wl + Yl.Wh  (error ~2^-21, inside the 1e-5 bar).
+//
+// Kernel shape (one CTA per SM, persistent over 128-row x 128-col output tiles):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D, SWIZZLE_128B boxes of 32 fp32 x 128 rows, 3-stage ring
+//   warp 1      MMA issuer:   one elected lane, tcgen05.mma.cta_group::1.kind::tf32 M128 N128 K8,
+//               accumulators in TMEM (2 x 128 columns, double buffered), tcgen05.commit -> mbarriers
+//   warps 2..5  epilogue:     tcgen05.ld 32x32b (TMEM lane == output row), bias + relu + dot(w2) per row,
+//               relu mask emitted as bits (warp ballot) for the backward
+#include <cuda.h>
+
+#include "common.cuh"
+
+#define TC_BM 128
+#define TC_BN 128
+#define TC_BK 32                       // fp32 elements per 128-byte swizzle row
+#define TC_STAGES 3
+#define TC_TILE_BYTES (TC_BM * TC_BK * 4)          // 16 KB: one operand tile of one k-block
+#define TC_STAGE_BYTES (4 * TC_TILE_BYTES)         // A_hi, A_lo, B_hi, B_lo
+#define TC_THREADS 192
+#define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/)
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni WAIT_DONE;\n\t"
+        "bra.uni WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]^T, kind::tf32, issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier once every MMA issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, K-major operand tile stored as [rows][32 fp32] with SWIZZLE_128B
+// (what TMA writes): start address >> 4, LBO (unused for swizzled K-major) = 1, SBO = 8 rows * 128 B = 1024 B,
+// descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.   (cute/arch/mma_sm100_desc.hpp SmemDescriptor)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)1u << 16;
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1u << 46;
+    d |= (uint64_t)2u << 61;
+    return d;
+}
+// Instruction descriptor (InstrDescriptor): c_format F32 (1) @4, a/b_format TF32 (2) @7/@10, K-major A and B,
+// N >> 3 @17, M >> 4 @24.
+__device__ __forceinline__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward kernel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1) k_l1_fwd_tc(
+    const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+    const int* __restrict__ n_dev, int cap_n, int K, int D, const float* __restrict__ b1,
+    const float* __restrict__ w2, float* __restrict__ zpart, uint32_t* __restrict__ maskT) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // SWIZZLE_128B tiles: 1024 B aligned
+    uint64_t* bars = (uint64_t*)(smem + TC_STAGES * TC_STAGE_BYTES);
+    uint64_t* full_bar = bars;                       // [TC_STAGES]  TMA -> MMA
+    uint64_t* empty_bar = bars + TC_STAGES;          // [TC_STAGES]  MMA -> TMA
+    uint64_t* tfull_bar = bars + 2 * TC_STAGES;      // [2]          MMA -> epilogue
+    uint64_t* tempty_bar = bars + 2 * TC_STAGES + 2; // [2]          epilogue -> MMA
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = min(*n_dev, cap_n);
+    const int NH = D / TC_BN;
+    const int m_tiles = (n + TC_BM - 1) / TC_BM;
+    const int total_tiles = m_tiles * NH;
+    const int nkb = (K + TC_BK - 1) / TC_BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int m0 = (t / NH) * TC_BM, n0 = (t % NH) * TC_BN;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* st = smem + stage * TC_STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
+                    tma_load_2d(st + 0 * TC_TILE_BYTES, &tmA_hi, &full_bar[stage], kb * TC_BK, m0);
+                    tma_load_2d(st + 1 * TC_TILE_BYTES, &tmA_lo, &full_bar[stage], kb * TC_BK, m0);
+                    tma_load_2d(st + 2 * TC_TILE_BYTES, &tmB_hi, &full_bar[stage], kb * TC_BK, n0);
+                    tma_load_2d(st + 3 * TC_TILE_BYTES, &tmB_lo, &full_bar[stage], kb * TC_BK, n0);
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_tf32(TC_BM, TC_BN);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_BN);
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * TC_STAGE_BYTES);
+                    const uint64_t a_hi = make_kmajor_sw128_desc(sa + 0 * TC_TILE_BYTES);
+                    const uint64_t a_lo = make_kmajor_sw128_desc(sa + 1 * TC_TILE_BYTES);
+                    const uint64_t b_hi = make_kmajor_sw128_desc(sa + 2 * TC_TILE_BYTES);
+                    const uint64_t b_lo = make_kmajor_sw128_desc(sa + 3 * TC_TILE_BYTES);
+#pragma unroll
+                    for (int ks = 0; ks < TC_BK / 8; ++ks) {
+                        const uint64_t adv = (uint64_t)((ks * 32) >> 4);      // +32 bytes per K=8 slice inside the swizzle row
+                        umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | ks) ? 1u : 0u);   // small terms first
+                        umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                        umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+                    }
+                    umma_commit(&empty_bar[stage]);                   // smem slot free once these MMAs retire
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);                         // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4 =====
+        const int q = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int mt = t / NH, nh = t % NH;
+            const int row = mt * TC_BM + q * 32 + lane;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            float zsum = 0.f;
+            uint32_t mbits[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int ch = 0; ch < TC_BN / 32; ++ch) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_BN + ch * 32), v);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const int col = nh * TC_BN + ch * 32 + c;
+                    const float pre = __uint_as_float(v[c]) + __ldg(&b1[col]);
+                    zsum = fmaf(fmaxf(pre, 0.f), __ldg(&w2[col]), zsum);
+                    if (maskT) {
+                        const uint32_t word = __ballot_sync(GRAPES_FULL_MASK, pre > 0.f && row < n);
+                        if (lane == c) mbits[ch] = word;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (row < n) zpart[(size_t)nh * cap_n + row] = zsum;
+            if (maskT) {
+                // maskT[(row group of 32)][D]: bit r of word (g, d) = relu'(pre[32 g + r, d])
+                uint32_t* dst = maskT + (size_t)(mt * 4 + q) * D + nh * TC_BN;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) dst[ch * 32 + lane] = mbits[ch];
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+// operand split: hi = tf32(x), lo = tf32(x - hi); zero padded to ld_dst columns
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__global__ void __launch_bounds__(256) k_split_tf32(const float* __restrict__ src, int ld_src, int R, int K,
+                                                    float* __restrict__ hi, float* __restrict__ lo, int ld_dst) {
+    const long long total = (long long)R * ld_dst;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / ld_dst), c = (int)(i % ld_dst);
+        const float x = (c < K) ? src[(size_t)r * ld_src + c] : 0.f;
+        const float h = to_tf32(x);
+        hi[i] = h;
+        lo[i] = to_tf32(x - h);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host: tensor maps
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+// row-major fp32 matrix [rows x cols] with row stride ld (elements); box = 32 cols x 128 rows, SWIZZLE_128B
+static int make_map(CUtensorMap* m, const float* base, int rows, int cols, int ld) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) { grapes_set_error("cuTensorMapEncodeTiled not available from the driver"); return GRAPES_ERR_CUDA; }
+    if ((((uintptr_t)base) & 15) || (ld % 4)) { grapes_set_error("TMA operand must be 16 B aligned with ld %% 4 == 0"); return GRAPES_ERR_ARG; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {TC_BK, TC_BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { grapes_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return GRAPES_ERR_CUDA; }
+    return GRAPES_OK;
+}
+
+extern "C" {
+
+int grapes_split_tf32(grapes_ctx* ctx, const float* src, int ld_src, int R, int K, float* hi, float* lo, int ld_dst,
+                      void* stream) {
+    GRAPES_REQUIRE(ctx && src && hi && lo, "null argument");
+    GRAPES_REQUIRE(ld_dst >= K && ld_src >= K, "bad leading dimension");
+    long long total = (long long)R * ld_dst;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    if (blocks < 1) blocks = 1;
+    k_split_tf32<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, ld_src, R, K, hi, lo, ld_dst);
+    grapes_count_launches(1);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+// zpart[D/128][cap_n]: per 128-column half partial row dots (summed by grapes_aggregate_scalar_parts)
+int grapes_sampler_l1_fwd_tc(grapes_ctx* ctx, const float* Y_hi, const float* Y_lo, int ldy, const int* n_dev,
+                             int cap_n, int K, const float* W_hi, const float* W_lo, int ldw, int D, const float* b1,
+                             const float* w2, float* zpart, uint32_t* maskT, void* stream) {
+    GRAPES_REQUIRE(ctx && Y_hi && Y_lo && n_dev && W_hi && W_lo && b1 && w2 && zpart, "null argument");
+    GRAPES_REQUIRE(D % TC_BN == 0 && D >= TC_BN, "hidden dim must be a multiple of 128 for the tcgen05 path");
+    GRAPES_REQUIRE(K > 0 && K <= ldy && K <= ldw, "bad K");
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    int rc;
+    if ((rc = make_map(&ma_hi, Y_hi, cap_n, K, ldy)) != GRAPES_OK) return rc;
+    if ((rc = make_map(&ma_lo, Y_lo, cap_n, K, ldy)) != GRAPES_OK) return rc;
+    if ((rc = make_map(&mb_hi, W_hi, D, K, ldw)) != GRAPES_OK) return rc;
+    if ((rc = make_map(&mb_lo, W_lo, D, K, ldw)) != GRAPES_OK) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GRAPES_CUDA_OK(cudaFuncSetAttribute(k_l1_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        attr_set = true;
+    }
+    const int max_tiles = ((cap_n + TC_BM - 1) / TC_BM) * (D / TC_BN);
+    int blocks = max_tiles < ctx->sm_count ? max_tiles : ctx->sm_count;
+    if (blocks < 1) blocks = 1;
+    k_l1_fwd_tc<<<blocks, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, n_dev, cap_n, K,
+                                                                             D, b1, w2, zpart, maskT);
+    grapes_count_launches(1);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+}  // extern "C"

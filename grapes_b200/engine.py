@@ -72,7 +72,8 @@ class GrapesEngine:
                  hidden_dim: int = 256, lr_gc: float = 1e-3, lr_gf: float = 1e-4, loss_coef: float = 1e4,
                  log_z_init: float = 0., reg_param: float = 0., random_sampling: bool = False,
                  reinforce_baseline: bool = False, seed: int = 0, cap_edges: Optional[int] = None,
-                 cap_nodes: Optional[int] = None, cap_block: Optional[int] = None):
+                 cap_nodes: Optional[int] = None, cap_block: Optional[int] = None,
+                 use_tensor_cores: bool = True):
         self.g = graph
         self.L = lib()
         dev = graph.device
@@ -140,6 +141,13 @@ class GrapesEngine:
         self.in_src, self.tmp_val = e(self.cap_m, **i32), e(self.cap_m, **i32)
         self.dinv = e(self.cap_n, **f32)
         self.Y = z((self.cap_n, self.ldY), **f32)
+        self.use_tc = bool(use_tensor_cores) and (self.D % 128 == 0)
+        self.ldW = _round_up(self.Fp, 4)
+        if self.use_tc:
+            self.Y_hi, self.Y_lo = z((self.cap_n, self.ldY), **f32), z((self.cap_n, self.ldY), **f32)
+            self.Wgf_hi, self.Wgf_lo = z((self.D, self.ldW), **f32), z((self.D, self.ldW), **f32)
+            self.Wz_hi, self.Wz_lo = z((self.D, self.ldW), **f32), z((self.D, self.ldW), **f32)
+            self.zpart = z((self.D // 128, self.cap_n), **f32)
         self.z_gf, self.z_z = e(self.cap_n, **f32), e(self.cap_n, **f32)
         self.logits_all, self.zlogits = z(self.cap_n, **f32), e(self.cap_n, **f32)
         self.dl_all, self.dz = z(self.cap_n, **f32), e(self.cap_n, **f32)
@@ -287,15 +295,28 @@ class GrapesEngine:
             need_Y = not self.random_sampling
             if need_Y:
                 # Y = A_hat [x | indicators]   (feature gather fused, main.py:198-204 + GCNConv aggregation)
+                tc = self.use_tc
                 L.grapes_aggregate(ctx, X, F, F, ptr(self.batch_nodes), self._cnt("n"), self.cap_n, ptr(self.in_off),
                                    ptr(self.in_src), ptr(self.dinv), ptr(self.ind_bits) if self.use_ind else None,
-                                   self.num_ind, None, 0, ptr(self.Y), self.ldY, st)
+                                   self.num_ind, None, 0, ptr(self.Y), self.ldY,
+                                   ptr(self.Y_hi) if tc else None, ptr(self.Y_lo) if tc else None, st)
                 gf = self.net_gf
-                L.grapes_sampler_l1_fwd(ctx, ptr(self.Y), self.ldY, self._cnt("n"), self.cap_n, Fp, self._par(gf.W1),
-                                        Fp, D, self._par(gf.b1), self._par(gf.W2), ptr(self.z_gf), st)
-                L.grapes_aggregate_scalar(ctx, ptr(self.z_gf), self._cnt("n"), self.cap_n, ptr(self.in_off),
-                                          ptr(self.in_src), ptr(self.dinv), self._par(gf.b2), ptr(self.logits_all),
-                                          ptr(self.dl_all), st)
+                if tc:
+                    if h == 0:
+                        self._split_weights(st)
+                    L.grapes_sampler_l1_fwd_tc(ctx, ptr(self.Y_hi), ptr(self.Y_lo), self.ldY, self._cnt("n"),
+                                               self.cap_n, Fp, ptr(self.Wgf_hi), ptr(self.Wgf_lo), self.ldW, D,
+                                               self._par(gf.b1), self._par(gf.W2), ptr(self.zpart), None, st)
+                    L.grapes_aggregate_scalar(ctx, ptr(self.zpart), D // 128, self.cap_n, self._cnt("n"), self.cap_n,
+                                              ptr(self.in_off), ptr(self.in_src), ptr(self.dinv), self._par(gf.b2),
+                                              ptr(self.logits_all), ptr(self.dl_all), st)
+                else:
+                    L.grapes_sampler_l1_fwd(ctx, ptr(self.Y), self.ldY, self._cnt("n"), self.cap_n, Fp,
+                                            self._par(gf.W1), Fp, D, self._par(gf.b1), self._par(gf.W2),
+                                            ptr(self.z_gf), st)
+                    L.grapes_aggregate_scalar(ctx, ptr(self.z_gf), 1, 0, self._cnt("n"), self.cap_n, ptr(self.in_off),
+                                              ptr(self.in_src), ptr(self.dinv), self._par(gf.b2),
+                                              ptr(self.logits_all), ptr(self.dl_all), st)
                 logits_ptr = ptr(self.logits_all)
             else:
                 logits_ptr = ptr(self.const100)                                   # main.py:207
@@ -321,12 +342,20 @@ class GrapesEngine:
                 if h == 0:
                     # log_z = mean(gcn_z(x[batch_nodes], edges)) - log_z_init   (main.py:223-228)
                     nz = self.net_z
-                    L.grapes_sampler_l1_fwd(ctx, ptr(self.Y), self.ldY, self._cnt("n"), self.cap_n, F,
-                                            self._par(nz.W1), F, D, self._par(nz.b1), self._par(nz.W2),
-                                            ptr(self.z_z), st)
-                    L.grapes_aggregate_scalar(ctx, ptr(self.z_z), self._cnt("n"), self.cap_n, ptr(self.in_off),
-                                              ptr(self.in_src), ptr(self.dinv), self._par(nz.b2), ptr(self.zlogits),
-                                              None, st)
+                    if self.use_tc:
+                        L.grapes_sampler_l1_fwd_tc(ctx, ptr(self.Y_hi), ptr(self.Y_lo), self.ldY, self._cnt("n"),
+                                                   self.cap_n, F, ptr(self.Wz_hi), ptr(self.Wz_lo), self.ldW, D,
+                                                   self._par(nz.b1), self._par(nz.W2), ptr(self.zpart), None, st)
+                        L.grapes_aggregate_scalar(ctx, ptr(self.zpart), D // 128, self.cap_n, self._cnt("n"),
+                                                  self.cap_n, ptr(self.in_off), ptr(self.in_src), ptr(self.dinv),
+                                                  self._par(nz.b2), ptr(self.zlogits), None, st)
+                    else:
+                        L.grapes_sampler_l1_fwd(ctx, ptr(self.Y), self.ldY, self._cnt("n"), self.cap_n, F,
+                                                self._par(nz.W1), F, D, self._par(nz.b1), self._par(nz.W2),
+                                                ptr(self.z_z), st)
+                        L.grapes_aggregate_scalar(ctx, ptr(self.z_z), 1, 0, self._cnt("n"), self.cap_n,
+                                                  ptr(self.in_off), ptr(self.in_src), ptr(self.dinv),
+                                                  self._par(nz.b2), ptr(self.zlogits), None, st)
                     L.grapes_vec_sum(ctx, ptr(self.zlogits), self._cnt("n"), self.cap_n, 1.0, 1, 0,
                                      self._scal("log_z_mean"), st)
                     if not self.reinforce:
@@ -378,14 +407,14 @@ class GrapesEngine:
         ldYc = self.Yc.shape[1]
         A_dev, cap_A = self._cnt("A"), self.cap_A
         L.grapes_aggregate(ctx, X, F, F, ptr(self.all_nodes), A_dev, cap_A, ptr(self.cl_in_off[0]),
-                           ptr(self.cl_in_src[0]), ptr(self.cl_dinv[0]), None, 0, None, 0, ptr(self.Yc), ldYc, st)
+                           ptr(self.cl_in_src[0]), ptr(self.cl_dinv[0]), None, 0, None, 0, ptr(self.Yc), ldYc, None, None, st)
         L.grapes_gemm(ctx, 3, ptr(self.Yc), ldYc, self._par(nc.W1), F, ptr(self.out1), D, A_dev, cap_A, D, F,
                       self._par(nc.b1), 1, None, 0, st)
         L.grapes_gemm(ctx, 3, ptr(self.out1), D, self._par(nc.W2), D, ptr(self.Zc), C, A_dev, cap_A, C, D, None, 0,
                       None, 0, st)
         L.grapes_aggregate(ctx, ptr(self.Zc), C, C, None, A_dev, cap_A, ptr(self.cl_in_off[1]),
                            ptr(self.cl_in_src[1]), ptr(self.cl_dinv[1]), None, 0, self._par(nc.b2), 0,
-                           ptr(self.logits_c), C, st)
+                           ptr(self.logits_c), C, None, None, st)
         L.grapes_classifier_loss(ctx, ptr(self.logits_c), C, C, A_dev, cap_A, ptr(self.target_local),
                                  ptr(self.targets), B, None if self.multilabel else ptr(self.y),
                                  ptr(self.y) if self.multilabel else None, self.reg_param, ptr(self.dlogits),
@@ -393,7 +422,7 @@ class GrapesEngine:
         # backward of the classifier (loss_c.backward(), main.py:267)
         L.grapes_colsum(ctx, ptr(self.dlogits), A_dev, cap_A, C, C, 1.0, 0, self._grd(nc.b2), st)
         L.grapes_aggregate(ctx, ptr(self.dlogits), C, C, None, A_dev, cap_A, ptr(self.cl_out_off),
-                           ptr(self.cl_out_dst), ptr(self.cl_dinv[1]), None, 0, None, 0, ptr(self.dZ), C, st)
+                           ptr(self.cl_out_dst), ptr(self.cl_dinv[1]), None, 0, None, 0, ptr(self.dZ), C, None, None, st)
         L.grapes_gemm_tn(ctx, ptr(self.dZ), C, ptr(self.out1), D, A_dev, cap_A, C, D, 1.0, 0, self._grd(nc.W2), st)
         L.grapes_gemm(ctx, 1, ptr(self.dZ), C, self._par(nc.W2), D, ptr(self.dpre1), D, A_dev, cap_A, D, C, None, 0,
                       ptr(self.out1), D, st)
@@ -410,6 +439,15 @@ class GrapesEngine:
                                             self._grd(nz.base), st)
         if apply_optim:
             self._enqueue_optim()
+
+    def _split_weights(self, st):
+        """3xTF32 operand split of the (per-step changing) layer-1 weights of gcn_gf / gcn_z."""
+        L, ctx = self.L, self.g.ctx
+        gf, nz = self.net_gf, self.net_z
+        L.grapes_split_tf32(ctx, self._par(gf.W1), self.Fp, self.D, self.Fp, ptr(self.Wgf_hi), ptr(self.Wgf_lo),
+                            self.ldW, st)
+        L.grapes_split_tf32(ctx, self._par(nz.W1), self.F, self.D, self.F, ptr(self.Wz_hi), ptr(self.Wz_lo),
+                            self.ldW, st)
 
     def _enqueue_optim(self):
         L, ctx = self.L, self.g.ctx

@@ -118,11 +118,13 @@ int grapes_build_csr(grapes_ctx* ctx, const int* key, const int* val, const int*
                      int cap_n, int* cnt_scratch, int* off, int* sorted_val, int* tmp_val, float* dinv, int* nnz_dev,
                      int* overflow, void* stream);
 /* out[j,:F] = dinv[j]^2 X[g(j)] + sum_s dinv[s] dinv[j] X[g(s)] (+bias)(relu); g = nodes[] or identity.
- * Indicator columns [F, F+num_ind) from ind_bits; [F+num_ind, ldo) zero-filled.                       */
+ * Indicator columns [F, F+num_ind) from ind_bits; [F+num_ind, ldo) zero-filled.  out_hi/out_lo
+ * (optional, same ldo) receive the 3xTF32 operand split tf32(v), tf32(v - tf32(v)) for the tcgen05 GEMM. */
 int grapes_aggregate(grapes_ctx* ctx, const float* X, int F, int ldx, const int* nodes, const int* n_dev, int cap_n,
                      const int* in_off, const int* in_src, const float* dinv, const uint32_t* ind_bits, int num_ind,
-                     const float* bias, int relu, float* out, int ldo, void* stream);
-int grapes_aggregate_scalar(grapes_ctx* ctx, const float* z, const int* n_dev, int cap_n, const int* in_off,
+                     const float* bias, int relu, float* out, int ldo, float* out_hi, float* out_lo, void* stream);
+/* z may be given as `nparts` partial vectors `part_stride` floats apart (summed on the fly)           */
+int grapes_aggregate_scalar(grapes_ctx* ctx, const float* z, int nparts, int part_stride, const int* n_dev, int cap_n, const int* in_off,
                             const int* in_src, const float* dinv, const float* bias, float* out, float* zero_out,
                             void* stream);
 /* transposed scalar aggregation on the hop graph (backward of the above), row-major edge list.       */
@@ -152,6 +154,15 @@ int grapes_sampler_l1_bwd(grapes_ctx* ctx, const float* Y, int ldy, const int* n
                           const float* W1, int ldw, int D, const float* b1, const float* w2, const float* dz,
                           float* dpre_scratch, float scale, int accumulate, float* gW1, int ldgw, float* gb1,
                           float* gw2, void* stream);
+
+/* tcgen05 path of the same layer (sm_100a tensor cores, 3xTF32 split operands, TMA + TMEM):
+ * operands pre-split into hi/lo fp32 arrays (grapes_aggregate's out_hi/out_lo, grapes_split_tf32 for the
+ * weights); zpart[D/128][cap_n] partial row dots; maskT[(rows/32)][D] relu mask bits (optional).         */
+int grapes_split_tf32(grapes_ctx* ctx, const float* src, int ld_src, int R, int K, float* hi, float* lo, int ld_dst,
+                      void* stream);
+int grapes_sampler_l1_fwd_tc(grapes_ctx* ctx, const float* Y_hi, const float* Y_lo, int ldy, const int* n_dev,
+                             int cap_n, int K, const float* W_hi, const float* W_lo, int ldw, int D, const float* b1,
+                             const float* w2, float* zpart, uint32_t* maskT, void* stream);
 
 /* ---- selection (utils.py:13-71; eval.py:126-130) --------------------------------------------- */
 int grapes_select_topk(grapes_ctx* ctx, const float* logits_all, const int* nb_local, const int* nb_nodes,

@@ -1,0 +1,62 @@
+"""tcgen05 (3xTF32) sampler-layer kernel against a float64 torch reference of the same op:
+z = relu(Y W1^T + b1) . w2, tolerance 1e-5 relative (the fp32 bar of BASELINE.json)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_tc(Y, W1, b1, w2, n, dev, with_mask=False):
+    from grapes_b200._lib import lib, ptr
+    from grapes_b200.utils import _any_ctx
+    L, ctx = lib(), _any_ctx(dev).ctx
+    st = torch.cuda.current_stream().cuda_stream
+    cap_n, ldy = Y.shape
+    D, K = W1.shape
+    ldw = (K + 3) // 4 * 4
+    Yh, Yl = torch.empty_like(Y), torch.empty_like(Y)
+    Wh = torch.empty((D, ldw), device=dev); Wl = torch.empty((D, ldw), device=dev)
+    L.grapes_split_tf32(ctx, ptr(Y), ldy, cap_n, ldy, ptr(Yh), ptr(Yl), ldy, st)
+    L.grapes_split_tf32(ctx, ptr(W1), K, D, K, ptr(Wh), ptr(Wl), ldw, st)
+    zpart = torch.zeros((D // 128, cap_n), device=dev)
+    cnt = torch.tensor([n], dtype=torch.int32, device=dev)
+    maskT = torch.zeros(((cap_n + 127) // 128 * 4, D), dtype=torch.int32, device=dev) if with_mask else None
+    L.grapes_sampler_l1_fwd_tc(ctx, ptr(Yh), ptr(Yl), ldy, ptr(cnt), cap_n, K, ptr(Wh), ptr(Wl), ldw, D, ptr(b1),
+                               ptr(w2), ptr(zpart), ptr(maskT), st)
+    torch.cuda.synchronize()
+    return zpart.sum(0)[:n], maskT
+
+
+@pytest.mark.parametrize("n,cap_n,K,D", [(1000, 1500, 104, 256), (64943, 66000, 104, 256), (130, 256, 15, 128),
+                                         (5000, 5000, 605, 256), (1, 128, 100, 256), (777, 900, 1436, 384)])
+def test_l1_fwd_tc_matches_fp64(cuda_device, n, cap_n, K, D):
+    g = torch.Generator().manual_seed(n + K)
+    ldy = (K + 3) // 4 * 4
+    Y = torch.zeros(cap_n, ldy)
+    Y[:, :K] = torch.randn(cap_n, K, generator=g)
+    W1 = (torch.rand(D, K, generator=g) * 2 - 1) * (6.0 / (D + K)) ** 0.5
+    b1 = torch.randn(D, generator=g) * 0.1
+    w2 = torch.randn(D, generator=g) * 0.1
+    ref = (torch.relu(Y[:n, :K].double() @ W1.double().t() + b1.double()) * w2.double()).sum(1)
+    got, _ = _run_tc(Y.to(cuda_device), W1.to(cuda_device), b1.to(cuda_device), w2.to(cuda_device), n, cuda_device)
+    err = (got.double().cpu() - ref).abs().max() / ref.abs().max()
+    assert err < 1e-5, f"relative error {err:.3e}"
+
+
+def test_l1_fwd_tc_relu_mask_bits(cuda_device):
+    n, cap_n, K, D = 3000, 3072, 104, 256
+    g = torch.Generator().manual_seed(1)
+    Y = torch.randn(cap_n, K, generator=g)
+    W1 = torch.randn(D, K, generator=g) * 0.1
+    b1 = torch.randn(D, generator=g)
+    w2 = torch.randn(D, generator=g)
+    pre = Y[:n].double() @ W1.double().t() + b1.double()
+    _, maskT = _run_tc(Y.to(cuda_device), W1.to(cuda_device), b1.to(cuda_device), w2.to(cuda_device), n, cuda_device,
+                       with_mask=True)
+    m = maskT.cpu()
+    rows = torch.arange(n)
+    bits = (m[rows // 32] >> (rows % 32).unsqueeze(1)) & 1          # [n, D]
+    want = (pre > 0)
+    clear = pre.abs() > 1e-4                                        # away from the relu kink the mask is exact
+    assert torch.equal(bits.bool()[clear], want[clear])
+    assert (bits.bool() != want).float().mean() < 1e-4
