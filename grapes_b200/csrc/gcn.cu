@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) k_agg(const float* __restrict__ X, int F,
                                              const float* __restrict__ dinv, const uint32_t* __restrict__ ind_bits,
                                              int num_ind, const float* __restrict__ bias, int relu,
                                              float* __restrict__ out, int ldo, float* __restrict__ out_hi,
-                                             float* __restrict__ out_lo) {
+                                             float* __restrict__ out_lo, int ones_col) {
     const int n = min(*n_dev, cap_n);
     const int lane = lane_id();
     const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) k_agg(const float* __restrict__ X, int F,
                 }
             }
             for (int c = F + lane; c < ldo; c += 32) {
-                const float v = (c < F + num_ind) ? a : 0.f;
+                const float v = (c < F + num_ind) ? a : (c == ones_col ? 1.f : 0.f);
                 if (oj) oj[c] = v;
                 if (ohj) { const float h = f32_to_tf32(v); ohj[c] = h; olj[c] = f32_to_tf32(v - h); }
             }
@@ -516,9 +516,11 @@ extern "C" {
 
 int grapes_aggregate(grapes_ctx* ctx, const float* X, int F, int ldx, const int* nodes, const int* n_dev, int cap_n,
                      const int* in_off, const int* in_src, const float* dinv, const uint32_t* ind_bits, int num_ind,
-                     const float* bias, int relu, float* out, int ldo, float* out_hi, float* out_lo, void* stream) {
+                     const float* bias, int relu, float* out, int ldo, float* out_hi, float* out_lo, int ones_col,
+                     void* stream) {
     GRAPES_REQUIRE(ctx && X && n_dev && in_off && in_src && dinv && (out || out_hi), "null argument");
     GRAPES_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), "out_hi and out_lo go together");
+    GRAPES_REQUIRE(ones_col < 0 || (ones_col >= F + num_ind && ones_col < ldo), "ones_col must lie in the pad columns");
     GRAPES_REQUIRE(ldo >= F + num_ind, "ldo too small");
     GRAPES_REQUIRE(num_ind == 0 || ind_bits, "indicator columns need ind_bits");
     GRAPES_REQUIRE(num_ind <= 8, "at most 8 indicator columns");
@@ -529,13 +531,13 @@ int grapes_aggregate(grapes_ctx* ctx, const float* X, int F, int ldx, const int*
     const bool a8 = (al & 7) == 0;
     if (a16 && (F % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0))
         k_agg<4><<<blocks, 256, 0, s>>>(X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias,
-                                        relu, out, ldo, out_hi, out_lo);
+                                        relu, out, ldo, out_hi, out_lo, ones_col);
     else if (a8 && (F % 2 == 0) && (ldx % 2 == 0) && (ldo % 2 == 0))
         k_agg<2><<<blocks, 256, 0, s>>>(X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias,
-                                        relu, out, ldo, out_hi, out_lo);
+                                        relu, out, ldo, out_hi, out_lo, ones_col);
     else
         k_agg<1><<<blocks, 256, 0, s>>>(X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias,
-                                        relu, out, ldo, out_hi, out_lo);
+                                        relu, out, ldo, out_hi, out_lo, ones_col);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;

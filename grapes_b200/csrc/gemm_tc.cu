@@ -253,6 +253,209 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_l1_fwd_tc(
 }
 
 // ------------------------------------------------------------------------------------------------
+// backward kernel:  S[d, k] = sum_r relu'(pre[r, d]) * dz[r] * Y[r, k]        (k < N; Y[:, K] == 1)
+//
+// from which   dW1[d,k] = w2[d] S[d,k],   db1[d] = w2[d] S[d,K],   dw2[d] = sum_k W1[d,k] S[d,k] + b1[d] S[d,K]
+// (relu(pre) = pre * relu'(pre), so no hidden activation and no dpre matrix is ever stored).
+//
+// The reduction runs over rows r, split across the persistent CTAs in blocks of 32 rows:
+//   A' (M = d, K-major)   built IN the kernel by 4 expander warps from the relu mask BITS the forward emitted
+//                         and the 3xTF32 split of dz:  A'_hi[d,r] = bit ? tf32(dz[r]) : 0,  A'_lo likewise
+//                         (generic-proxy st.shared in the SWIZZLE_128B pattern + fence.proxy.async)
+//   B' (N = k, MN-major)  the aggregated features Y_hi / Y_lo, TMA boxes of 32 rows x 32 columns
+//   D                     [D x N] fp32 in TMEM (NH halves x N columns), accumulated over all the CTA's rows
+// ------------------------------------------------------------------------------------------------
+#define TCB_ROWS 32                                  // rows per k-block (one 128-byte swizzle row of A')
+#define TCB_A_TILE (128 * 128)                       // 128 d x 32 r fp32 = 16 KB
+#define TCB_B_TILE (TCB_ROWS * 128)                  // 32 r x 32 k fp32 = 4 KB
+
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;     // stride between 32-column blocks of the MN dimension
+    d |= (uint64_t)(1024u >> 4) << 32;                     // stride between 8-row groups of the K dimension
+    d |= (uint64_t)1u << 46;
+    d |= (uint64_t)2u << 61;
+    return d;
+}
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_l1_bwd_tc(
+    const __grid_constant__ CUtensorMap tmY_hi, const __grid_constant__ CUtensorMap tmY_lo,
+    const int* __restrict__ n_dev, int cap_n, int NH, int NB, int stages, const uint32_t* __restrict__ maskT, int D,
+    const float* __restrict__ dz, float* __restrict__ part) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int a_bytes = NH * TCB_A_TILE;             // one of (hi | lo)
+    const int b_bytes = NB * TCB_B_TILE;
+    const int stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    uint64_t* bars = (uint64_t*)(smem + stages * stage_bytes);
+    uint64_t* full_bar = bars;                       // [stages] TMA (1 + tx) + 4 expander warps -> MMA
+    uint64_t* empty_bar = bars + 4;                  // [stages] MMA -> TMA + expanders
+    uint64_t* done_bar = bars + 8;                   // all MMAs retired -> epilogue
+    uint32_t* tmem_slot = (uint32_t*)(bars + 9);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = min(*n_dev, cap_n);
+    const int groups = (n + TCB_ROWS - 1) / TCB_ROWS;
+    const int N = NB * 32;                           // accumulator columns per half
+    const int my_groups = (groups > (int)blockIdx.x) ? (groups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmY_hi); tma_prefetch_desc(&tmY_lo);
+        for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 5); mbar_init(&empty_bar[s], 1); }
+        mbar_init(done_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* st = smem + stage * stage_bytes + 2 * a_bytes;
+                mbar_arrive_expect_tx(&full_bar[stage], 2 * b_bytes);
+                for (int nb = 0; nb < NB; ++nb) {
+                    tma_load_2d(st + nb * TCB_B_TILE, &tmY_hi, &full_bar[stage], nb * 32, g * TCB_ROWS);
+                    tma_load_2d(st + b_bytes + nb * TCB_B_TILE, &tmY_lo, &full_bar[stage], nb * 32, g * TCB_ROWS);
+                }
+                if (++stage == stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            // A: K-major, B: MN-major (bit 16), M = 128, N = NB*32
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
+                                   ((uint32_t)(128 >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            bool first = true;
+            for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+                const uint64_t b_hi = make_mnmajor_sw128_desc(sa + 2 * a_bytes, TCB_B_TILE);
+                const uint64_t b_lo = make_mnmajor_sw128_desc(sa + 2 * a_bytes + b_bytes, TCB_B_TILE);
+                for (int h = 0; h < NH; ++h) {
+                    const uint64_t a_hi = make_kmajor_sw128_desc(sa + h * TCB_A_TILE);
+                    const uint64_t a_lo = make_kmajor_sw128_desc(sa + a_bytes + h * TCB_A_TILE);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(h * N);
+#pragma unroll
+                    for (int ks = 0; ks < TCB_ROWS / 8; ++ks) {
+                        const uint64_t adv_a = (uint64_t)((ks * 32) >> 4);       // 8 r = 32 bytes along the swizzle row
+                        const uint64_t adv_b = (uint64_t)((ks * 1024) >> 4);     // 8 rows of 128 bytes
+                        umma_tf32(d_tmem, a_lo + adv_a, b_hi + adv_b, idesc, (first && ks == 0) ? 0u : 1u);
+                        umma_tf32(d_tmem, a_hi + adv_a, b_lo + adv_b, idesc, 1u);
+                        umma_tf32(d_tmem, a_hi + adv_a, b_hi + adv_b, idesc, 1u);
+                    }
+                }
+                first = false;
+                umma_commit(&empty_bar[stage]);
+                if (++stage == stages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(done_bar);
+        }
+    } else {
+        // ===== expanders (warps 2..5), then epilogue =====
+        const int e = (warp - 2) * 32 + lane;            // d index inside a half
+        int stage = 0; uint32_t phase = 0;
+        for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+            const int r = g * TCB_ROWS + lane;
+            const float dzr = (r < n) ? dz[r] : 0.f;
+            const float dzh = tf32_rna(dzr), dzl = tf32_rna(dzr - dzh);
+            uint32_t words[4];
+            for (int h = 0; h < NH && h < 4; ++h) words[h] = maskT[(size_t)g * D + h * 128 + e];
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* st = smem + stage * stage_bytes;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float vh[4], vl[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    vh[i] = __shfl_sync(GRAPES_FULL_MASK, dzh, c * 4 + i);
+                    vl[i] = __shfl_sync(GRAPES_FULL_MASK, dzl, c * 4 + i);
+                }
+                const int off = e * 128 + ((c ^ (e & 7)) << 4);          // SWIZZLE_128B: 16-byte chunk index ^ (row % 8)
+                for (int h = 0; h < NH && h < 4; ++h) {
+                    const uint32_t w = words[h] >> (c * 4);
+                    float4 ah, al;
+                    ah.x = (w & 1u) ? vh[0] : 0.f; ah.y = (w & 2u) ? vh[1] : 0.f; ah.z = (w & 4u) ? vh[2] : 0.f; ah.w = (w & 8u) ? vh[3] : 0.f;
+                    al.x = (w & 1u) ? vl[0] : 0.f; al.y = (w & 2u) ? vl[1] : 0.f; al.z = (w & 4u) ? vl[2] : 0.f; al.w = (w & 8u) ? vl[3] : 0.f;
+                    *reinterpret_cast<float4*>(st + h * TCB_A_TILE + off) = ah;
+                    *reinterpret_cast<float4*>(st + a_bytes + h * TCB_A_TILE + off) = al;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[stage]);
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        // epilogue: this CTA's partial S -> part[cta][NH*128][N]
+        const int q = warp & 3;
+        float* dst = part + (size_t)blockIdx.x * NH * 128 * N;
+        if (my_groups > 0) {
+            mbar_wait(done_bar, 0);
+            tc_fence_after();
+            for (int h = 0; h < NH; ++h) {
+                float* row = dst + (size_t)(h * 128 + q * 32 + lane) * N;
+                for (int ch = 0; ch < NB; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * N + ch * 32), v);
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4)
+                        *reinterpret_cast<float4*>(row + ch * 32 + c) =
+                            make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]), __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
+                }
+            }
+        } else {
+            for (int h = 0; h < NH; ++h) {
+                float* row = dst + (size_t)(h * 128 + q * 32 + lane) * N;
+                for (int c = 0; c < N; c += 4) *reinterpret_cast<float4*>(row + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// Sum the per-CTA partials (fixed order) and turn S into the three gradients, accumulated (+=, times scale).
+// One block per hidden unit d.
+__global__ void __launch_bounds__(128) k_l1_bwd_finalize(const float* __restrict__ part, int nparts, int D, int N, int K,
+                                                         const float* __restrict__ W1, int ldw,
+                                                         const float* __restrict__ b1, const float* __restrict__ w2,
+                                                         int ones_col, float scale, float* __restrict__ gW1,
+                                                         float* __restrict__ gb1, float* __restrict__ gw2) {
+    __shared__ float red[4];
+    const int d = blockIdx.x;
+    const float w2d = w2[d];
+    float acc_w2 = 0.f;
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+        float s = 0.f;
+        for (int p = 0; p < nparts; ++p) s += part[((size_t)p * D + d) * N + k];
+        if (k < K) {
+            gW1[(size_t)d * K + k] += scale * w2d * s;
+            acc_w2 = fmaf(W1[(size_t)d * ldw + k], s, acc_w2);
+        } else if (k == ones_col) {
+            gb1[d] += scale * w2d * s;
+            acc_w2 = fmaf(b1[d], s, acc_w2);
+        }
+    }
+    acc_w2 = warp_sum(acc_w2);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc_w2;
+    __syncthreads();
+    if (threadIdx.x == 0) gw2[d] += scale * (red[0] + red[1] + red[2] + red[3]);
+}
+
+// ------------------------------------------------------------------------------------------------
 // operand split: hi = tf32(x), lo = tf32(x - hi); zero padded to ld_dst columns
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float to_tf32(float x) {
@@ -292,13 +495,13 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 // row-major fp32 matrix [rows x cols] with row stride ld (elements); box = 32 cols x 128 rows, SWIZZLE_128B
-static int make_map(CUtensorMap* m, const float* base, int rows, int cols, int ld) {
+static int make_map(CUtensorMap* m, const float* base, int rows, int cols, int ld, int box_rows = TC_BM) {
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) { grapes_set_error("cuTensorMapEncodeTiled not available from the driver"); return GRAPES_ERR_CUDA; }
     if ((((uintptr_t)base) & 15) || (ld % 4)) { grapes_set_error("TMA operand must be 16 B aligned with ld %% 4 == 0"); return GRAPES_ERR_ARG; }
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {TC_BK, TC_BM};
+    cuuint32_t box[2] = {TC_BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -346,6 +549,47 @@ int grapes_sampler_l1_fwd_tc(grapes_ctx* ctx, const float* Y_hi, const float* Y_
     if (blocks < 1) blocks = 1;
     k_l1_fwd_tc<<<blocks, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, n_dev, cap_n, K,
                                                                              D, b1, w2, zpart, maskT);
+    grapes_count_launches(1);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+
+// Gradient DIRECTION of sum_r dz[r] z[r] w.r.t. (W1, b1, w2), accumulated (+=, times `scale`).
+// Y_hi/Y_lo must carry a column of ones at index `ones_col` (>= K); maskT from grapes_sampler_l1_fwd_tc.
+int grapes_sampler_l1_bwd_tc(grapes_ctx* ctx, const float* Y_hi, const float* Y_lo, int ldy, int ncols,
+                             const int* n_dev, int cap_n, int K, int ones_col, const uint32_t* maskT,
+                             const float* W1, int ldw, int D, const float* b1, const float* w2, const float* dz,
+                             float scale, float* gW1, float* gb1, float* gw2, void* stream) {
+    GRAPES_REQUIRE(ctx && Y_hi && Y_lo && n_dev && maskT && W1 && b1 && w2 && dz && gW1 && gb1 && gw2, "null argument");
+    GRAPES_REQUIRE(D % 128 == 0 && D >= 128 && D <= 512, "hidden dim must be a multiple of 128 (<= 512)");
+    GRAPES_REQUIRE(K <= ones_col && ones_col < ncols && ncols <= ldy, "bad column layout");
+    const int NH = D / 128, NB = (ncols + 31) / 32;
+    GRAPES_REQUIRE(NH * NB * 32 <= 512 && NB * 32 <= 256, "accumulator does not fit TMEM (use the SIMT path)");
+    const int stage_bytes = NH * 2 * TCB_A_TILE + NB * 2 * TCB_B_TILE;
+    int stages = (220 * 1024) / stage_bytes;
+    if (stages > 4) stages = 4;
+    GRAPES_REQUIRE(stages >= 2, "stage does not fit shared memory");
+    const int smem_bytes = stages * stage_bytes + 1024 + 256;
+    CUtensorMap my_hi, my_lo;
+    int rc;
+    if ((rc = make_map(&my_hi, Y_hi, cap_n, ncols, ldy, TCB_ROWS)) != GRAPES_OK) return rc;
+    if ((rc = make_map(&my_lo, Y_lo, cap_n, ncols, ldy, TCB_ROWS)) != GRAPES_OK) return rc;
+    static int attr_bytes = 0;
+    if (smem_bytes > attr_bytes) {
+        GRAPES_CUDA_OK(cudaFuncSetAttribute(k_l1_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        attr_bytes = smem_bytes;
+    }
+    const int max_groups = (cap_n + TCB_ROWS - 1) / TCB_ROWS;
+    int blocks = max_groups < ctx->sm_count ? max_groups : ctx->sm_count;
+    if (blocks < 1) blocks = 1;
+    const int N = NB * 32;
+    GRAPES_REQUIRE((size_t)blocks * D * N * sizeof(float) <= ctx->partials_bytes, "split partial buffer too small");
+    cudaStream_t s = (cudaStream_t)stream;
+    k_l1_bwd_tc<<<blocks, TC_THREADS, smem_bytes, s>>>(my_hi, my_lo, n_dev, cap_n, NH, NB, stages, maskT, D, dz,
+                                                       ctx->partials);
+    grapes_count_launches(1);
+    k_l1_bwd_finalize<<<D, 128, 0, s>>>(ctx->partials, blocks, D, N, K, W1, ldw, b1, w2, ones_col, scale, gW1, gb1, gw2);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;

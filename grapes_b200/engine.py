@@ -93,6 +93,12 @@ class GrapesEngine:
         self.num_ind = self.H + 1 if self.use_ind else 0
         self.Fp = F + self.num_ind
         self.ldY = _round_up(self.Fp, 4)
+        self.use_tc = bool(use_tensor_cores) and (self.D % 128 == 0)
+        nb = (self.Fp + 1 + 31) // 32                      # 32-column accumulator blocks of the tensor-core backward
+        self.use_tc_bwd = self.use_tc and (self.D // 128) * nb * 32 <= 512 and nb * 32 <= 256
+        if self.use_tc_bwd:
+            self.ldY = _round_up(self.Fp + 1, 4)           # room for the column of ones (bias column)
+        self.ldW = _round_up(self.Fp, 4)
         self.lr_gc, self.lr_gf = float(lr_gc), float(lr_gf)
         self.loss_coef, self.log_z_init, self.reg_param = float(loss_coef), float(log_z_init), float(reg_param)
         self.random_sampling, self.reinforce = bool(random_sampling), bool(reinforce_baseline)
@@ -141,8 +147,10 @@ class GrapesEngine:
         self.in_src, self.tmp_val = e(self.cap_m, **i32), e(self.cap_m, **i32)
         self.dinv = e(self.cap_n, **f32)
         self.Y = z((self.cap_n, self.ldY), **f32)
-        self.use_tc = bool(use_tensor_cores) and (self.D % 128 == 0)
-        self.ldW = _round_up(self.Fp, 4)
+        if self.use_tc_bwd:
+            ng = (self.cap_n + 127) // 128 * 4
+            self.mask_gf = z((ng, self.D), **i32)
+            self.mask_z = z((ng, self.D), **i32)
         if self.use_tc:
             self.Y_hi, self.Y_lo = z((self.cap_n, self.ldY), **f32), z((self.cap_n, self.ldY), **f32)
             self.Wgf_hi, self.Wgf_lo = z((self.D, self.ldW), **f32), z((self.D, self.ldW), **f32)
@@ -151,7 +159,7 @@ class GrapesEngine:
         self.z_gf, self.z_z = e(self.cap_n, **f32), e(self.cap_n, **f32)
         self.logits_all, self.zlogits = z(self.cap_n, **f32), e(self.cap_n, **f32)
         self.dl_all, self.dz = z(self.cap_n, **f32), e(self.cap_n, **f32)
-        self.dpre = e((self.cap_n, self.D), **f32)
+        self.dpre = e((1 if self.use_tc_bwd else self.cap_n, self.D), **f32)
         self.ukeys = e(self.cap_n, **i32)
         self.log_prob = z((self.H, self.cap_n), **f32)
         self.scal = z(16, **f32)
@@ -298,15 +306,17 @@ class GrapesEngine:
                 tc = self.use_tc
                 L.grapes_aggregate(ctx, X, F, F, ptr(self.batch_nodes), self._cnt("n"), self.cap_n, ptr(self.in_off),
                                    ptr(self.in_src), ptr(self.dinv), ptr(self.ind_bits) if self.use_ind else None,
-                                   self.num_ind, None, 0, ptr(self.Y), self.ldY,
-                                   ptr(self.Y_hi) if tc else None, ptr(self.Y_lo) if tc else None, st)
+                                   self.num_ind, None, 0, None if self.use_tc_bwd else ptr(self.Y), self.ldY,
+                                   ptr(self.Y_hi) if tc else None, ptr(self.Y_lo) if tc else None,
+                                   Fp if self.use_tc_bwd else -1, st)
                 gf = self.net_gf
                 if tc:
                     if h == 0:
                         self._split_weights(st)
                     L.grapes_sampler_l1_fwd_tc(ctx, ptr(self.Y_hi), ptr(self.Y_lo), self.ldY, self._cnt("n"),
                                                self.cap_n, Fp, ptr(self.Wgf_hi), ptr(self.Wgf_lo), self.ldW, D,
-                                               self._par(gf.b1), self._par(gf.W2), ptr(self.zpart), None, st)
+                                               self._par(gf.b1), self._par(gf.W2), ptr(self.zpart),
+                                               ptr(self.mask_gf) if self.use_tc_bwd else None, st)
                     L.grapes_aggregate_scalar(ctx, ptr(self.zpart), D // 128, self.cap_n, self._cnt("n"), self.cap_n,
                                               ptr(self.in_off), ptr(self.in_src), ptr(self.dinv), self._par(gf.b2),
                                               ptr(self.logits_all), ptr(self.dl_all), st)
@@ -336,16 +346,24 @@ class GrapesEngine:
                                             ptr(self.row_off), ptr(self.e_src), ptr(self.e_dst), ptr(self.dinv),
                                             ptr(self.dz), st)
                 gf = self.net_gf
-                L.grapes_sampler_l1_bwd(ctx, ptr(self.Y), self.ldY, self._cnt("n"), self.cap_n, Fp, self._par(gf.W1),
-                                        Fp, D, self._par(gf.b1), self._par(gf.W2), ptr(self.dz), ptr(self.dpre), 1.0,
-                                        1, self._dir(gf.W1), Fp, self._dir(gf.b1), self._dir(gf.W2), st)
+                if self.use_tc_bwd:
+                    L.grapes_sampler_l1_bwd_tc(ctx, ptr(self.Y_hi), ptr(self.Y_lo), self.ldY, Fp + 1, self._cnt("n"),
+                                               self.cap_n, Fp, Fp, ptr(self.mask_gf), self._par(gf.W1), Fp, D,
+                                               self._par(gf.b1), self._par(gf.W2), ptr(self.dz), 1.0,
+                                               self._dir(gf.W1), self._dir(gf.b1), self._dir(gf.W2), st)
+                else:
+                    L.grapes_sampler_l1_bwd(ctx, ptr(self.Y), self.ldY, self._cnt("n"), self.cap_n, Fp,
+                                            self._par(gf.W1), Fp, D, self._par(gf.b1), self._par(gf.W2), ptr(self.dz),
+                                            ptr(self.dpre), 1.0, 1, self._dir(gf.W1), Fp, self._dir(gf.b1),
+                                            self._dir(gf.W2), st)
                 if h == 0:
                     # log_z = mean(gcn_z(x[batch_nodes], edges)) - log_z_init   (main.py:223-228)
                     nz = self.net_z
                     if self.use_tc:
                         L.grapes_sampler_l1_fwd_tc(ctx, ptr(self.Y_hi), ptr(self.Y_lo), self.ldY, self._cnt("n"),
                                                    self.cap_n, F, ptr(self.Wz_hi), ptr(self.Wz_lo), self.ldW, D,
-                                                   self._par(nz.b1), self._par(nz.W2), ptr(self.zpart), None, st)
+                                                   self._par(nz.b1), self._par(nz.W2), ptr(self.zpart),
+                                                   ptr(self.mask_z) if self.use_tc_bwd else None, st)
                         L.grapes_aggregate_scalar(ctx, ptr(self.zpart), D // 128, self.cap_n, self._cnt("n"),
                                                   self.cap_n, ptr(self.in_off), ptr(self.in_src), ptr(self.dinv),
                                                   self._par(nz.b2), ptr(self.zlogits), None, st)
@@ -363,10 +381,17 @@ class GrapesEngine:
                         L.grapes_aggregate_scalar_T(ctx, ptr(self.zlogits), self._cnt("n"), self.cap_n, P_dev,
                                                     self.cap_P, ptr(self.row_off), ptr(self.e_src), ptr(self.e_dst),
                                                     ptr(self.dinv), ptr(self.dz), st)
-                        L.grapes_sampler_l1_bwd(ctx, ptr(self.Y), self.ldY, self._cnt("n"), self.cap_n, F,
-                                                self._par(nz.W1), F, D, self._par(nz.b1), self._par(nz.W2),
-                                                ptr(self.dz), ptr(self.dpre), 1.0, 1, self._dir(nz.W1), F,
-                                                self._dir(nz.b1), self._dir(nz.W2), st)
+                        if self.use_tc_bwd:
+                            L.grapes_sampler_l1_bwd_tc(ctx, ptr(self.Y_hi), ptr(self.Y_lo), self.ldY, Fp + 1,
+                                                       self._cnt("n"), self.cap_n, F, Fp, ptr(self.mask_z),
+                                                       self._par(nz.W1), F, D, self._par(nz.b1), self._par(nz.W2),
+                                                       ptr(self.dz), 1.0, self._dir(nz.W1), self._dir(nz.b1),
+                                                       self._dir(nz.W2), st)
+                        else:
+                            L.grapes_sampler_l1_bwd(ctx, ptr(self.Y), self.ldY, self._cnt("n"), self.cap_n, F,
+                                                    self._par(nz.W1), F, D, self._par(nz.b1), self._par(nz.W2),
+                                                    ptr(self.dz), ptr(self.dpre), 1.0, 1, self._dir(nz.W1), F,
+                                                    self._dir(nz.b1), self._dir(nz.W2), st)
                         L.grapes_fill_f32(ctx, self._dir(nz.b2), 1.0, 1, st)
             if rec is not None:
                 self._record_hop(h, cur)
@@ -407,14 +432,14 @@ class GrapesEngine:
         ldYc = self.Yc.shape[1]
         A_dev, cap_A = self._cnt("A"), self.cap_A
         L.grapes_aggregate(ctx, X, F, F, ptr(self.all_nodes), A_dev, cap_A, ptr(self.cl_in_off[0]),
-                           ptr(self.cl_in_src[0]), ptr(self.cl_dinv[0]), None, 0, None, 0, ptr(self.Yc), ldYc, None, None, st)
+                           ptr(self.cl_in_src[0]), ptr(self.cl_dinv[0]), None, 0, None, 0, ptr(self.Yc), ldYc, None, None, -1, st)
         L.grapes_gemm(ctx, 3, ptr(self.Yc), ldYc, self._par(nc.W1), F, ptr(self.out1), D, A_dev, cap_A, D, F,
                       self._par(nc.b1), 1, None, 0, st)
         L.grapes_gemm(ctx, 3, ptr(self.out1), D, self._par(nc.W2), D, ptr(self.Zc), C, A_dev, cap_A, C, D, None, 0,
                       None, 0, st)
         L.grapes_aggregate(ctx, ptr(self.Zc), C, C, None, A_dev, cap_A, ptr(self.cl_in_off[1]),
                            ptr(self.cl_in_src[1]), ptr(self.cl_dinv[1]), None, 0, self._par(nc.b2), 0,
-                           ptr(self.logits_c), C, None, None, st)
+                           ptr(self.logits_c), C, None, None, -1, st)
         L.grapes_classifier_loss(ctx, ptr(self.logits_c), C, C, A_dev, cap_A, ptr(self.target_local),
                                  ptr(self.targets), B, None if self.multilabel else ptr(self.y),
                                  ptr(self.y) if self.multilabel else None, self.reg_param, ptr(self.dlogits),
@@ -422,7 +447,7 @@ class GrapesEngine:
         # backward of the classifier (loss_c.backward(), main.py:267)
         L.grapes_colsum(ctx, ptr(self.dlogits), A_dev, cap_A, C, C, 1.0, 0, self._grd(nc.b2), st)
         L.grapes_aggregate(ctx, ptr(self.dlogits), C, C, None, A_dev, cap_A, ptr(self.cl_out_off),
-                           ptr(self.cl_out_dst), ptr(self.cl_dinv[1]), None, 0, None, 0, ptr(self.dZ), C, None, None, st)
+                           ptr(self.cl_out_dst), ptr(self.cl_dinv[1]), None, 0, None, 0, ptr(self.dZ), C, None, None, -1, st)
         L.grapes_gemm_tn(ctx, ptr(self.dZ), C, ptr(self.out1), D, A_dev, cap_A, C, D, 1.0, 0, self._grd(nc.W2), st)
         L.grapes_gemm(ctx, 1, ptr(self.dZ), C, self._par(nc.W2), D, ptr(self.dpre1), D, A_dev, cap_A, D, C, None, 0,
                       ptr(self.out1), D, st)
@@ -525,7 +550,7 @@ class GrapesEngine:
                  batch_nodes=self.batch_nodes[:n].clone(), neighbor_nodes=self.nb_nodes[:c].clone(),
                  nb_local=self.nb_local[:c].clone(), ind_bits=self.ind_bits[:n].clone(),
                  in_off=self.in_off[:n + 1].clone(), in_src=self.in_src[:self.count("nnz")].clone(),
-                 dinv=self.dinv[:n].clone(), Y=self.Y[:n].clone(), logits_all=self.logits_all[:n].clone(),
+                 dinv=self.dinv[:n].clone(), Y=((self.Y_hi[:n] + self.Y_lo[:n]) if self.use_tc_bwd else self.Y[:n].clone()), logits_all=self.logits_all[:n].clone(),
                  sampled=self.prev[nxt][self.bsz:self.bsz + s].clone(), log_prob=self.log_prob[h, :c].clone(),
                  keys=self.record["keys_buf"][:c].clone(), stats=self.stats[h].clone(),
                  dl_all=self.dl_all[:n].clone(), dz=self.dz[:n].clone(), zlogits=self.zlogits[:n].clone())

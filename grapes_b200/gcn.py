@@ -57,7 +57,7 @@ class NormAdj:
         out = torch.empty_like(x)
         off, idx = (self.out_off, self.out_dst) if transpose else (self.in_off, self.in_src)
         L.grapes_aggregate(ctx, ptr(x), Fdim, Fdim, None, self.cnt.data_ptr() + 4, max(self.n, 1), ptr(off), ptr(idx),
-                           ptr(self.dinv), None, 0, ptr(bias), 0, ptr(out), Fdim, None, None, _stream())
+                           ptr(self.dinv), None, 0, ptr(bias), 0, ptr(out), Fdim, None, None, -1, _stream())
         return out
 
 

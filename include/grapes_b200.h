@@ -119,10 +119,12 @@ int grapes_build_csr(grapes_ctx* ctx, const int* key, const int* val, const int*
                      int* overflow, void* stream);
 /* out[j,:F] = dinv[j]^2 X[g(j)] + sum_s dinv[s] dinv[j] X[g(s)] (+bias)(relu); g = nodes[] or identity.
  * Indicator columns [F, F+num_ind) from ind_bits; [F+num_ind, ldo) zero-filled.  out_hi/out_lo
- * (optional, same ldo) receive the 3xTF32 operand split tf32(v), tf32(v - tf32(v)) for the tcgen05 GEMM. */
+ * (optional, same ldo) receive the 3xTF32 operand split tf32(v), tf32(v - tf32(v)) for the tcgen05 GEMM;
+ * ones_col >= 0 puts a column of ones there (bias column of the tensor-core backward), -1 = none.       */
 int grapes_aggregate(grapes_ctx* ctx, const float* X, int F, int ldx, const int* nodes, const int* n_dev, int cap_n,
                      const int* in_off, const int* in_src, const float* dinv, const uint32_t* ind_bits, int num_ind,
-                     const float* bias, int relu, float* out, int ldo, float* out_hi, float* out_lo, void* stream);
+                     const float* bias, int relu, float* out, int ldo, float* out_hi, float* out_lo, int ones_col,
+                     void* stream);
 /* z may be given as `nparts` partial vectors `part_stride` floats apart (summed on the fly)           */
 int grapes_aggregate_scalar(grapes_ctx* ctx, const float* z, int nparts, int part_stride, const int* n_dev, int cap_n, const int* in_off,
                             const int* in_src, const float* dinv, const float* bias, float* out, float* zero_out,
@@ -163,6 +165,13 @@ int grapes_split_tf32(grapes_ctx* ctx, const float* src, int ld_src, int R, int 
 int grapes_sampler_l1_fwd_tc(grapes_ctx* ctx, const float* Y_hi, const float* Y_lo, int ldy, const int* n_dev,
                              int cap_n, int K, const float* W_hi, const float* W_lo, int ldw, int D, const float* b1,
                              const float* w2, float* zpart, uint32_t* maskT, void* stream);
+
+/* backward on tensor cores: S = mask^T (dz * Y) from the relu mask bits; Y must hold a column of ones at
+ * `ones_col` (K <= ones_col < ncols <= ldy).  Accumulates scale * d(sum dz.z)/d(W1,b1,w2).               */
+int grapes_sampler_l1_bwd_tc(grapes_ctx* ctx, const float* Y_hi, const float* Y_lo, int ldy, int ncols,
+                             const int* n_dev, int cap_n, int K, int ones_col, const uint32_t* maskT,
+                             const float* W1, int ldw, int D, const float* b1, const float* w2, const float* dz,
+                             float scale, float* gW1, float* gb1, float* gw2, void* stream);
 
 /* ---- selection (utils.py:13-71; eval.py:126-130) --------------------------------------------- */
 int grapes_select_topk(grapes_ctx* ctx, const float* logits_all, const int* nb_local, const int* nb_nodes,

@@ -60,3 +60,48 @@ def test_l1_fwd_tc_relu_mask_bits(cuda_device):
     clear = pre.abs() > 1e-4                                        # away from the relu kink the mask is exact
     assert torch.equal(bits.bool()[clear], want[clear])
     assert (bits.bool() != want).float().mean() < 1e-4
+
+
+@pytest.mark.parametrize("n,cap_n,K,D,extra", [(3000, 3072, 104, 256, 0), (64943, 66000, 104, 256, 0), (100, 128, 15, 128, 0),
+                                               (2000, 2048, 100, 256, 4), (5000, 5100, 131, 256, 0)])
+def test_l1_bwd_tc_matches_fp64_autograd(cuda_device, n, cap_n, K, D, extra):
+    """d(sum_r dz[r] z[r]) / d(W1, b1, w2) from the relu-mask bits: S = mask^T (dz * [Y | 1]).
+    `extra` indicator-like columns sit between K and the ones column (the gcn_z case, K = F < F')."""
+    from grapes_b200._lib import lib, ptr
+    from grapes_b200.utils import _any_ctx
+    dev = cuda_device
+    L, ctx = lib(), _any_ctx(dev).ctx
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(n + K + extra)
+    ones_col = K + extra
+    ncols = ones_col + 1
+    ldy = (ncols + 3) // 4 * 4
+    Y = torch.zeros(cap_n, ldy)
+    Y[:, :ones_col] = torch.randn(cap_n, ones_col, generator=g)
+    Y[:, ones_col] = 1.0
+    W1 = (torch.rand(D, K, generator=g) * 2 - 1) * (6.0 / (D + K)) ** 0.5
+    b1 = torch.randn(D, generator=g) * 0.1
+    w2 = torch.randn(D, generator=g) * 0.1
+    dz = torch.randn(cap_n, generator=g)
+    # float64 autograd reference
+    W1r, b1r, w2r = (t.double().requires_grad_(True) for t in (W1, b1, w2))
+    z = (torch.relu(Y[:n, :K].double() @ W1r.t() + b1r) * w2r).sum(1)
+    (z * dz[:n].double()).sum().backward()
+    Yd, W1d, b1d, w2d, dzd = (t.to(dev) for t in (Y, W1, b1, w2, dz))
+    ldw = (K + 3) // 4 * 4
+    Yh, Yl = torch.empty_like(Yd), torch.empty_like(Yd)
+    Wh, Wl = torch.empty((D, ldw), device=dev), torch.empty((D, ldw), device=dev)
+    L.grapes_split_tf32(ctx, ptr(Yd), ldy, cap_n, ldy, ptr(Yh), ptr(Yl), ldy, st)
+    L.grapes_split_tf32(ctx, ptr(W1d), K, D, K, ptr(Wh), ptr(Wl), ldw, st)
+    zpart = torch.zeros((D // 128, cap_n), device=dev)
+    cnt = torch.tensor([n], dtype=torch.int32, device=dev)
+    maskT = torch.zeros(((cap_n + 127) // 128 * 4, D), dtype=torch.int32, device=dev)
+    L.grapes_sampler_l1_fwd_tc(ctx, ptr(Yh), ptr(Yl), ldy, ptr(cnt), cap_n, K, ptr(Wh), ptr(Wl), ldw, D, ptr(b1d),
+                               ptr(w2d), ptr(zpart), ptr(maskT), st)
+    gW1, gb1, gw2 = torch.zeros(D, K, device=dev), torch.zeros(D, device=dev), torch.zeros(D, device=dev)
+    L.grapes_sampler_l1_bwd_tc(ctx, ptr(Yh), ptr(Yl), ldy, ncols, ptr(cnt), cap_n, K, ones_col, ptr(maskT), ptr(W1d), K,
+                               D, ptr(b1d), ptr(w2d), ptr(dzd), 1.0, ptr(gW1), ptr(gb1), ptr(gw2), st)
+    torch.cuda.synchronize()
+    for got, ref, name in ((gW1, W1r.grad, "W1"), (gb1, b1r.grad, "b1"), (gw2, w2r.grad, "w2")):
+        err = (got.double().cpu() - ref).abs().max() / ref.abs().max()
+        assert err < 1e-5, f"{name}: relative error {err:.3e}"
