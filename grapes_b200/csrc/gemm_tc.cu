@@ -263,19 +263,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_l1_fwd_tc(
 //                         and the 3xTF32 split of dz:  A'_hi[d,r] = bit ? tf32(dz[r]) : 0,  A'_lo likewise
 //                         (generic-proxy st.shared in the SWIZZLE_128B pattern + fence.proxy.async)
 //   B' (N = k, MN-major)  the aggregated features Y_hi / Y_lo, TMA boxes of 32 rows x 32 columns
+//                         (SWIZZLE_128B_ATOM_32B: the only legal MN-major layout for 32-bit operands)
 //   D                     [D x N] fp32 in TMEM (NH halves x N columns), accumulated over all the CTA's rows
 // ------------------------------------------------------------------------------------------------
 #define TCB_ROWS 32                                  // rows per k-block (one 128-byte swizzle row of A')
 #define TCB_A_TILE (128 * 128)                       // 128 d x 32 r fp32 = 16 KB
 #define TCB_B_TILE (TCB_ROWS * 128)                  // 32 r x 32 k fp32 = 4 KB
 
-__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+// MN-major 32-bit (tf32) operands have exactly one legal shared-memory layout on sm_100: SWIZZLE_128B with a
+// 32-byte swizzle atom (layout type 1 = SWIZZLE_128B_BASE32B; TMA mode CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B):
+// rows of 128 bytes (32 MN elements), the 32-byte chunk index XORed with (row % 4), K atom = 4 rows (512 B).
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_32b_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;     // stride between 32-column blocks of the MN dimension
-    d |= (uint64_t)(1024u >> 4) << 32;                     // stride between 8-row groups of the K dimension
+    d |= (uint64_t)(512u >> 4) << 32;                      // stride between 4-row atoms of the K dimension
     d |= (uint64_t)1u << 46;
-    d |= (uint64_t)2u << 61;
+    d |= (uint64_t)1u << 61;
     return d;
 }
 __device__ __forceinline__ float tf32_rna(float x) {
@@ -287,7 +291,7 @@ __device__ __forceinline__ float tf32_rna(float x) {
 __global__ void __launch_bounds__(TC_THREADS, 1) k_l1_bwd_tc(
     const __grid_constant__ CUtensorMap tmY_hi, const __grid_constant__ CUtensorMap tmY_lo,
     const int* __restrict__ n_dev, int cap_n, int NH, int NB, int stages, const uint32_t* __restrict__ maskT, int D,
-    const float* __restrict__ dz, float* __restrict__ part) {
+    const float* __restrict__ dz, float* __restrict__ part, int debug) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int a_bytes = NH * TCB_A_TILE;             // one of (hi | lo)
@@ -342,8 +346,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_l1_bwd_tc(
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-                const uint64_t b_hi = make_mnmajor_sw128_desc(sa + 2 * a_bytes, TCB_B_TILE);
-                const uint64_t b_lo = make_mnmajor_sw128_desc(sa + 2 * a_bytes + b_bytes, TCB_B_TILE);
+                const uint64_t b_hi = make_mnmajor_sw128_32b_desc(sa + 2 * a_bytes, TCB_B_TILE);
+                const uint64_t b_lo = make_mnmajor_sw128_32b_desc(sa + 2 * a_bytes + b_bytes, TCB_B_TILE);
                 for (int h = 0; h < NH; ++h) {
                     const uint64_t a_hi = make_kmajor_sw128_desc(sa + h * TCB_A_TILE);
                     const uint64_t a_lo = make_kmajor_sw128_desc(sa + a_bytes + h * TCB_A_TILE);
@@ -389,6 +393,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_l1_bwd_tc(
                     float4 ah, al;
                     ah.x = (w & 1u) ? vh[0] : 0.f; ah.y = (w & 2u) ? vh[1] : 0.f; ah.z = (w & 4u) ? vh[2] : 0.f; ah.w = (w & 8u) ? vh[3] : 0.f;
                     al.x = (w & 1u) ? vl[0] : 0.f; al.y = (w & 2u) ? vl[1] : 0.f; al.z = (w & 4u) ? vl[2] : 0.f; al.w = (w & 8u) ? vl[3] : 0.f;
+                    if (debug & 1) { ah = make_float4(1.f, 1.f, 1.f, 1.f); al = make_float4(0.f, 0.f, 0.f, 0.f); }
                     *reinterpret_cast<float4*>(st + h * TCB_A_TILE + off) = ah;
                     *reinterpret_cast<float4*>(st + a_bytes + h * TCB_A_TILE + off) = al;
                 }
@@ -495,7 +500,8 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 // row-major fp32 matrix [rows x cols] with row stride ld (elements); box = 32 cols x 128 rows, SWIZZLE_128B
-static int make_map(CUtensorMap* m, const float* base, int rows, int cols, int ld, int box_rows = TC_BM) {
+static int make_map(CUtensorMap* m, const float* base, int rows, int cols, int ld, int box_rows = TC_BM,
+                    CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) { grapes_set_error("cuTensorMapEncodeTiled not available from the driver"); return GRAPES_ERR_CUDA; }
     if ((((uintptr_t)base) & 15) || (ld % 4)) { grapes_set_error("TMA operand must be 16 B aligned with ld %% 4 == 0"); return GRAPES_ERR_ARG; }
@@ -504,13 +510,18 @@ static int make_map(CUtensorMap* m, const float* base, int rows, int cols, int l
     cuuint32_t box[2] = {TC_BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { grapes_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return GRAPES_ERR_CUDA; }
     return GRAPES_OK;
 }
 
+static int g_tc_debug = 0;
+
 extern "C" {
+
+int grapes_tc_debug(int flags) { g_tc_debug = flags; return 0; }
+const float* grapes_ctx_partials(grapes_ctx* ctx) { return ctx->partials; }
 
 int grapes_split_tf32(grapes_ctx* ctx, const float* src, int ld_src, int R, int K, float* hi, float* lo, int ld_dst,
                       void* stream) {
@@ -573,8 +584,8 @@ int grapes_sampler_l1_bwd_tc(grapes_ctx* ctx, const float* Y_hi, const float* Y_
     const int smem_bytes = stages * stage_bytes + 1024 + 256;
     CUtensorMap my_hi, my_lo;
     int rc;
-    if ((rc = make_map(&my_hi, Y_hi, cap_n, ncols, ldy, TCB_ROWS)) != GRAPES_OK) return rc;
-    if ((rc = make_map(&my_lo, Y_lo, cap_n, ncols, ldy, TCB_ROWS)) != GRAPES_OK) return rc;
+    if ((rc = make_map(&my_hi, Y_hi, cap_n, ncols, ldy, TCB_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != GRAPES_OK) return rc;
+    if ((rc = make_map(&my_lo, Y_lo, cap_n, ncols, ldy, TCB_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != GRAPES_OK) return rc;
     static int attr_bytes = 0;
     if (smem_bytes > attr_bytes) {
         GRAPES_CUDA_OK(cudaFuncSetAttribute(k_l1_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -587,7 +598,7 @@ int grapes_sampler_l1_bwd_tc(grapes_ctx* ctx, const float* Y_hi, const float* Y_
     GRAPES_REQUIRE((size_t)blocks * D * N * sizeof(float) <= ctx->partials_bytes, "split partial buffer too small");
     cudaStream_t s = (cudaStream_t)stream;
     k_l1_bwd_tc<<<blocks, TC_THREADS, smem_bytes, s>>>(my_hi, my_lo, n_dev, cap_n, NH, NB, stages, maskT, D, dz,
-                                                       ctx->partials);
+                                                       ctx->partials, g_tc_debug);
     grapes_count_launches(1);
     k_l1_bwd_finalize<<<D, 128, 0, s>>>(ctx->partials, blocks, D, N, K, W1, ldw, b1, w2, ones_col, scale, gW1, gb1, gw2);
     grapes_count_launches(1);
