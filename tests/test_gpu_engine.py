@@ -21,7 +21,9 @@ def _rel(got, ref):
     return ((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30)).item()
 
 
-def _setup(name, seed, dev, **kw):
+def _setup(name, seed, dev, use_tensor_cores=False, **kw):
+    """use_tensor_cores=False: the fp32 SIMT kernels, whose rounding is at the reference's own level, so the strict
+    1e-5 bars apply elementwise.  The tcgen05 (3xTF32) path is covered by test_tensor_core_engine_* below."""
     from grapes_b200.engine import GrapesEngine
     from grapes_b200.graph import DeviceGraph
     from grapes_b200.synth import SHAPES
@@ -36,7 +38,7 @@ def _setup(name, seed, dev, **kw):
     g = DeviceGraph.from_edge_index(d.edge_index, d.num_nodes, device=dev)
     eng = GrapesEngine(g, d.x.to(dev), d.y.to(dev), num_classes=d.num_classes, batch_size=cfg["batch_size"],
                        hidden_dim=st.gcn_c.gcn_layers[0].lin.weight.shape[0],
-                       lr_gc=1e-3, lr_gf=1e-4, seed=seed, **hp)
+                       lr_gc=1e-3, lr_gf=1e-4, seed=seed, use_tensor_cores=use_tensor_cores, **hp)
     eng.load_state_dicts(gcn_c=st.gcn_c.state_dict(), gcn_gf=st.gcn_gf.state_dict(), gcn_z=st.gcn_z.state_dict())
     train_idx = d.train_mask.nonzero().squeeze(1)
     return d, st, eng, train_idx, cfg["batch_size"]
@@ -49,7 +51,21 @@ def _grad_tol(got32, ref64):
     return max(TOL, 2.0 * _rel(got32, ref64))
 
 
-def _check_step(st, eng, targets, dev, apply_optim=True):
+def _grad_ok(got, ref64, ref32, relaxed):
+    """strict: elementwise bar.  relaxed (tensor-core path): a hidden unit whose pre-activation sits within fp32
+    noise of the relu kink may take the other branch than float64 did (so can the reference's own fp32 run); such
+    a flip moves ONE row of the weight gradient.  Allow <= 3 outlier rows, bounded, and hold all others to the bar."""
+    tol = _grad_tol(ref32, ref64)
+    ref = torch.as_tensor(ref64).double()
+    err = (torch.as_tensor(got).double().cpu() - ref).abs() / ref.abs().max().clamp_min(1e-30)
+    if not relaxed:
+        return bool(err.max() < tol)
+    rows = err.reshape(err.shape[0], -1).max(1).values if err.dim() > 1 else err
+    bad = rows > 3 * tol
+    return bool(bad.sum() <= 3 and err.max() < 2e-2)
+
+
+def _check_step(st, eng, targets, dev, apply_optim=True, relaxed=False):
     ref = rp.reference_step(st, targets, apply_optim=apply_optim)
     ref32 = rp.reference_step(st.fp32, targets, gumbel_noise=[h["noise"] for h in ref["hops"]], apply_optim=apply_optim)
     for a, b in zip(ref32["hops"], ref["hops"]):
@@ -93,7 +109,7 @@ def _check_step(st, eng, targets, dev, apply_optim=True):
     assert abs(s["loss_c"] - ref["loss_c"].item()) < TOL * abs(ref["loss_c"].item())
     assert abs(s["tot_log_prob"] - ref["tot_log_prob"].item()) < TOL * abs(ref["tot_log_prob"].item())
     for name, gref in ref["grads_c"].items():
-        assert _rel(rec["grads"]["gcn_c"][name], gref) < _grad_tol(ref32["grads_c"][name], gref), f"grad gcn_c {name}"
+        assert _grad_ok(rec["grads"]["gcn_c"][name], gref, ref32["grads_c"][name], False), f"grad gcn_c {name}"
     if not st.random_sampling:
         assert abs(s["log_z"] - ref["log_z"].item()) < TOL * max(1.0, abs(ref["log_z"].item()))
         assert abs(s["loss_gfn"] - ref["loss_gfn"].item()) < 4 * TOL * abs(ref["loss_gfn"].item())
@@ -109,6 +125,44 @@ def _check_step(st, eng, targets, dev, apply_optim=True):
 def test_step_parity_trajectory_balance(cuda_device, name, seed):
     d, st, eng, train_idx, B = _setup(name, seed, cuda_device)
     _check_step(st, eng, train_idx[:B], cuda_device, apply_optim=False)
+
+
+@pytest.mark.parametrize("name,seed", [("tiny", 0), ("small", 1), ("small", 2)])
+def test_tensor_core_engine_step_parity(cuda_device, name, seed):
+    """The same whole-step parity with the tcgen05 3xTF32 kernels in the loop: integer outputs and sampled sets stay
+    bit-exact, logits / losses hold the 1e-5 bar, gradients hold it up to relu-kink flips (see _grad_ok)."""
+    d, st, eng, train_idx, B = _setup(name, seed, cuda_device, use_tensor_cores=True)
+    assert eng.use_tc and eng.use_tc_bwd
+    _check_step(st, eng, train_idx[:B], cuda_device, apply_optim=False, relaxed=True)
+
+
+def test_tensor_core_engine_matches_simt_engine(cuda_device):
+    """Mid-size frontier (several 128-row tiles per CTA, several 32-row blocks per CTA in the backward)."""
+    from grapes_b200.synth import SHAPES
+    kw = dict(N=40_000, E_dir=1_200_000, F=100, C=10, n_train=10_000, batch_size=256, num_samples=64, sampling_hops=2)
+    SHAPES["mid"] = kw
+    try:
+        d, st, e_tc, train_idx, B = _setup("mid", 3, cuda_device, use_tensor_cores=True)
+        _, _, e_simt, _, _ = _setup("mid", 3, cuda_device, use_tensor_cores=False)
+    finally:
+        SHAPES.pop("mid")
+    assert e_tc.use_tc_bwd and not e_simt.use_tc
+    t = train_idx[:B].to(cuda_device)
+    noise = [torch.randn(e_tc.cap_n, device=cuda_device).abs().log().neg() for _ in range(2)]    # any fixed noise
+    r1 = e_tc.step(t, gumbel_noise=noise, apply_optim=False, record=True)
+    r2 = e_simt.step(t, gumbel_noise=noise, apply_optim=False, record=True)
+    e_tc.check_overflow(); e_simt.check_overflow()
+    for a, b in zip(r1["hops"], r2["hops"]):
+        assert a["n"] > 5000
+        assert torch.equal(a["sampled"], b["sampled"]) and torch.equal(a["batch_nodes"], b["batch_nodes"])
+        assert _rel(a["logits_all"], b["logits_all"].cpu()) < TOL
+    for k in ("loss_c", "tot_log_prob", "log_z", "loss_gfn"):
+        assert abs(r1["scalars"][k] - r2["scalars"][k]) <= 4 * TOL * abs(r2["scalars"][k])
+    for net in ("gcn_gf", "gcn_z"):
+        for name, g2 in r2["grads"][net].items():
+            g1 = r1["grads"][net][name]
+            num = (g1.double() - g2.double()).norm() / g2.double().norm()
+            assert num < 1e-4, f"{net}.{name}: relative L2 difference {num:.2e}"
 
 
 def test_three_steps_with_adam(cuda_device):
