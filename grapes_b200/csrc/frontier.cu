@@ -271,8 +271,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_i32(const int* __restrict
 // claim slots from the back of each row; leaves cnt[] all-zero again
 __global__ void __launch_bounds__(256) k_fill(const int* __restrict__ key, const int* __restrict__ val,
                                               const int* __restrict__ E_dev, int cap_E,
-                                              const int* __restrict__ off, int* cnt, int* __restrict__ out_val) {
+                                              const int* __restrict__ off, int* cnt, int* __restrict__ out_val,
+                                              int* hub_count) {
     const int E = min(*E_dev, cap_E);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *hub_count = 0;      // the previous build's k_sort_hub is done (stream order)
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
         const int k = key[e], v = val[e];
         if (k != v) {
@@ -327,7 +329,87 @@ __global__ void __launch_bounds__(256) k_sort_hub(const int* __restrict__ off, i
         __syncthreads();
     }
 }
-__global__ void k_reset_counter(int* c) { *c = 0; }
+
+
+// ---------------------------------------------------------------------------------------
+// k_build_csr_small: the whole build (hist -> scan -> fill -> per-row sort -> deg^-1/2) in ONE 1024-thread CTA for
+// graphs with at most SMALL_N nodes (the classifier's sampled blocks: <= B + hops*k nodes, main.py:252-257).
+// ---------------------------------------------------------------------------------------
+#define SMALL_N 4096
+__global__ void __launch_bounds__(1024) k_build_csr_small(const int* __restrict__ key, const int* __restrict__ val,
+                                                          const int* __restrict__ E_dev, int cap_E,
+                                                          const int* __restrict__ n_dev, int cap_n,
+                                                          int* __restrict__ off, int* __restrict__ out_val,
+                                                          int* __restrict__ tmp, float* __restrict__ dinv,
+                                                          int* __restrict__ nnz_out) {
+    __shared__ int s_cnt[SMALL_N];
+    __shared__ int s_off[SMALL_N + 1];
+    __shared__ int s_scan[34];
+    __shared__ int s_hub[64];
+    __shared__ int s_nhub;
+    const int E = min(*E_dev, cap_E);
+    const int n = min(min(*n_dev, cap_n), SMALL_N);
+    const int tid = threadIdx.x;
+    for (int i = tid; i < n; i += 1024) s_cnt[i] = 0;
+    if (tid == 0) s_nhub = 0;
+    __syncthreads();
+    for (int e = tid; e < E; e += 1024) {
+        const int k = key[e];
+        if (k != val[e]) atomicAdd(&s_cnt[k], 1);
+    }
+    __syncthreads();
+    int carry = 0;
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + tid;
+        const int c = (i < n) ? s_cnt[i] : 0;
+        int total;
+        const int ex = block_scan_excl<int>(c, s_scan, &total);
+        if (i < n) {
+            s_off[i] = carry + ex;
+            off[i] = carry + ex;
+            if (dinv) dinv[i] = 1.0f / sqrtf((float)(c + 1));
+        }
+        carry += total;
+    }
+    if (tid == 0) { s_off[n] = carry; off[n] = carry; if (nnz_out) *nnz_out = carry; }
+    __syncthreads();
+    for (int e = tid; e < E; e += 1024) {
+        const int k = key[e], v = val[e];
+        if (k != v) out_val[s_off[k] + atomicSub(&s_cnt[k], 1) - 1] = v;
+    }
+    __syncthreads();
+    for (int j = tid; j < n; j += 1024) {
+        const int beg = s_off[j], len = s_off[j + 1] - beg;
+        if (len < 2) continue;
+        if (len > 64) {
+            const int slot = atomicAdd(&s_nhub, 1);
+            if (slot < 64) { s_hub[slot] = j; continue; }         // > 64 hub rows: fall through to the slow exact path
+        }
+        int* a = out_val + beg;
+        for (int i = 1; i < len; ++i) {
+            const int x = a[i];
+            int k = i - 1;
+            while (k >= 0 && a[k] > x) { a[k + 1] = a[k]; --k; }
+            a[k + 1] = x;
+        }
+    }
+    __syncthreads();
+    const int nh = min(s_nhub, 64);
+    for (int h = 0; h < nh; ++h) {                                // whole-block rank sort of each hub row
+        const int j = s_hub[h];
+        const int beg = s_off[j], len = s_off[j + 1] - beg;
+        const int* a = out_val + beg;
+        for (int i = tid; i < len; i += 1024) {
+            const int x = a[i];
+            int r = 0;
+            for (int t = 0; t < len; ++t) { const int y = a[t]; r += (y < x) || (y == x && t < i); }
+            tmp[beg + r] = x;
+        }
+        __syncthreads();
+        for (int i = tid; i < len; i += 1024) out_val[beg + i] = tmp[beg + i];
+        __syncthreads();
+    }
+}
 
 // ---------------------------------------------------------------------------------------
 // k_filter_compact: ordered stream compaction of the expanded edge list by membership of the
@@ -499,6 +581,13 @@ int grapes_build_csr(grapes_ctx* ctx, const int* key, const int* val, const int*
     GRAPES_REQUIRE(ctx && key && val && E_dev && n_dev && cnt_scratch && off && sorted_val && tmp_val && overflow,
                    "null argument");
     cudaStream_t s = (cudaStream_t)stream;
+    if (cap_n <= SMALL_N && cap_E <= 8 * SMALL_N) {
+        k_build_csr_small<<<1, 1024, 0, s>>>(key, val, E_dev, cap_E, n_dev, cap_n, off, sorted_val, tmp_val, dinv,
+                                             nnz_dev);
+        grapes_count_launches(1);
+        GRAPES_LAUNCH_OK();
+        return GRAPES_OK;
+    }
     const int tiles = grapes_div_up(cap_n, SCAN_TILE);
     GRAPES_REQUIRE(tiles <= ctx->scan_cap_tiles, "scan scratch too small for cap_n");
     GRAPES_CUDA_OK(cudaMemsetAsync(cnt_scratch, 0, sizeof(int) * (size_t)cap_n, s));
@@ -507,9 +596,8 @@ int grapes_build_csr(grapes_ctx* ctx, const int* key, const int* val, const int*
     k_scan_i32<<<grapes_max_i(tiles, 1), SCAN_THREADS, 0, s>>>(cnt_scratch, n_dev, cap_n, off, dinv, nnz_dev,
                                                               ctx->scan_status, ctx->scan_counters);
     grapes_count_launches(1);
-    k_fill<<<grid_for(ctx, cap_E, 256), 256, 0, s>>>(key, val, E_dev, cap_E, off, cnt_scratch, sorted_val);
-    grapes_count_launches(1);
-    k_reset_counter<<<1, 1, 0, s>>>(ctx->hub_count);
+    k_fill<<<grid_for(ctx, cap_E, 256), 256, 0, s>>>(key, val, E_dev, cap_E, off, cnt_scratch, sorted_val,
+                                                     ctx->hub_count);
     grapes_count_launches(1);
     k_sort_rows<<<grid_for(ctx, cap_n, 256), 256, 0, s>>>(off, n_dev, cap_n, sorted_val, ctx->hub_rows,
                                                           ctx->hub_count, ctx->hub_cap, overflow);

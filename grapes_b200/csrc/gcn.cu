@@ -208,13 +208,29 @@ __global__ void __launch_bounds__(256) k_colsum_slabs(const float* __restrict__ 
     }
 }
 
-// block-wide deterministic sum of a vector with a device-side length:  *out (+)= scale * sum(v)/ (divide_by_n ? n : 1)
-__global__ void __launch_bounds__(1024) k_vec_sum(const float* __restrict__ v, const int* __restrict__ n_dev, int cap_n,
-                                                  float scale, int divide_by_n, int accumulate, float* out) {
-    __shared__ float s[32];
+// deterministic sum of a vector with a device-side length, two stages:
+//   k_vec_sum_part: block b sums its fixed 4096-element chunk -> part[b]
+//   k_vec_sum_final: one block adds the partials in index order;  *out (+)= scale * sum / (divide_by_n ? n : 1)
+#define VS_CHUNK 4096
+__global__ void __launch_bounds__(256) k_vec_sum_part(const float* __restrict__ v, const int* __restrict__ n_dev,
+                                                      int cap_n, float* __restrict__ part) {
+    __shared__ float s[8];
     const int n = min(*n_dev, cap_n);
+    const int base = blockIdx.x * VS_CHUNK;
     float a = 0.f;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) a += v[i];
+    for (int i = base + threadIdx.x; i < min(n, base + VS_CHUNK); i += 256) a += v[i];
+    a = warp_sum(a);
+    if (lane_id() == 0) s[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) part[blockIdx.x] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+}
+__global__ void __launch_bounds__(1024) k_vec_sum_final(const float* __restrict__ part, int nparts,
+                                                        const int* __restrict__ n_dev, int cap_n, float scale,
+                                                        int divide_by_n, int accumulate, float* out) {
+    __shared__ float s[32];
+    const int n = n_dev ? min(*n_dev, cap_n) : cap_n;
+    float a = 0.f;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) a += part[i];
     a = warp_sum(a);
     if (lane_id() == 0) s[threadIdx.x >> 5] = a;
     __syncthreads();
@@ -580,7 +596,12 @@ int grapes_fill_inv_count(grapes_ctx* ctx, float* v, const int* n_dev, int cap_n
 int grapes_vec_sum(grapes_ctx* ctx, const float* v, const int* n_dev, int cap_n, float scale, int divide_by_n,
                    int accumulate, float* out, void* stream) {
     GRAPES_REQUIRE(ctx && v && n_dev && out, "null argument");
-    k_vec_sum<<<1, 1024, 0, (cudaStream_t)stream>>>(v, n_dev, cap_n, scale, divide_by_n, accumulate, out);
+    const int nparts = grapes_max_i(1, grapes_div_up(cap_n, VS_CHUNK));
+    GRAPES_REQUIRE((size_t)nparts * sizeof(float) <= ctx->partials_bytes, "partial buffer too small");
+    k_vec_sum_part<<<nparts, 256, 0, (cudaStream_t)stream>>>(v, n_dev, cap_n, ctx->partials);
+    grapes_count_launches(1);
+    k_vec_sum_final<<<1, 1024, 0, (cudaStream_t)stream>>>(ctx->partials, nparts, n_dev, cap_n, scale, divide_by_n,
+                                                          accumulate, out);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;

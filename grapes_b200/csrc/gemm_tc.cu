@@ -433,29 +433,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_l1_bwd_tc(
 }
 
 // Sum the per-CTA partials (fixed order) and turn S into the three gradients, accumulated (+=, times scale).
-// One block per hidden unit d.
-__global__ void __launch_bounds__(128) k_l1_bwd_finalize(const float* __restrict__ part, int nparts, int D, int N, int K,
-                                                         const float* __restrict__ W1, int ldw,
-                                                         const float* __restrict__ b1, const float* __restrict__ w2,
-                                                         int ones_col, float scale, float* __restrict__ gW1,
-                                                         float* __restrict__ gb1, float* __restrict__ gw2) {
+// One block per hidden unit d; 8 groups of 128 threads split the partials, then a fixed-order combine.
+#define FIN_GROUPS 8
+__global__ void __launch_bounds__(128 * FIN_GROUPS) k_l1_bwd_finalize(
+    const float* __restrict__ part, int nparts, int D, int N, int K, const float* __restrict__ W1, int ldw,
+    const float* __restrict__ b1, const float* __restrict__ w2, int ones_col, float scale, float* __restrict__ gW1,
+    float* __restrict__ gb1, float* __restrict__ gw2) {
+    __shared__ float sums[FIN_GROUPS][256];
     __shared__ float red[4];
     const int d = blockIdx.x;
-    const float w2d = w2[d];
-    float acc_w2 = 0.f;
-    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+    const int kl = threadIdx.x & 127, pg = threadIdx.x >> 7;
+    for (int k0 = 0; k0 < N; k0 += 128) {            // N <= 256
+        const int k = k0 + kl;
         float s = 0.f;
-        for (int p = 0; p < nparts; ++p) s += part[((size_t)p * D + d) * N + k];
-        if (k < K) {
-            gW1[(size_t)d * K + k] += scale * w2d * s;
-            acc_w2 = fmaf(W1[(size_t)d * ldw + k], s, acc_w2);
-        } else if (k == ones_col) {
-            gb1[d] += scale * w2d * s;
-            acc_w2 = fmaf(b1[d], s, acc_w2);
-        }
+        if (k < N)
+            for (int p = pg; p < nparts; p += FIN_GROUPS) s += part[((size_t)p * D + d) * N + k];
+        sums[pg][k0 + kl] = s;
     }
-    acc_w2 = warp_sum(acc_w2);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc_w2;
+    __syncthreads();
+    if (pg == 0) {
+        const float w2d = w2[d];
+        float acc_w2 = 0.f;
+        for (int k = kl; k < N; k += 128) {
+            float s = 0.f;
+#pragma unroll
+            for (int g = 0; g < FIN_GROUPS; ++g) s += sums[g][k];
+            if (k < K) {
+                gW1[(size_t)d * K + k] += scale * w2d * s;
+                acc_w2 = fmaf(W1[(size_t)d * ldw + k], s, acc_w2);
+            } else if (k == ones_col) {
+                gb1[d] += scale * w2d * s;
+                acc_w2 = fmaf(b1[d], s, acc_w2);
+            }
+        }
+        acc_w2 = warp_sum(acc_w2);
+        if ((kl & 31) == 0) red[kl >> 5] = acc_w2;
+    }
     __syncthreads();
     if (threadIdx.x == 0) gw2[d] += scale * (red[0] + red[1] + red[2] + red[3]);
 }
@@ -600,7 +613,7 @@ int grapes_sampler_l1_bwd_tc(grapes_ctx* ctx, const float* Y_hi, const float* Y_
     k_l1_bwd_tc<<<blocks, TC_THREADS, smem_bytes, s>>>(my_hi, my_lo, n_dev, cap_n, NH, NB, stages, maskT, D, dz,
                                                        ctx->partials, g_tc_debug);
     grapes_count_launches(1);
-    k_l1_bwd_finalize<<<D, 128, 0, s>>>(ctx->partials, blocks, D, N, K, W1, ldw, b1, w2, ones_col, scale, gW1, gb1, gw2);
+    k_l1_bwd_finalize<<<D, 128 * FIN_GROUPS, 0, s>>>(ctx->partials, blocks, D, N, K, W1, ldw, b1, w2, ones_col, scale, gW1, gb1, gw2);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;

@@ -22,48 +22,56 @@ __device__ __forceinline__ float block_sum_1024(float v, float* s) {
 // logits [A x C] (ld = ldl).  Target rows: row_ids[B] (local ids of the target nodes, main.py:259).
 // labels: int64 class ids per GLOBAL node (multiclass) or float [N x C] (multilabel), indexed by targets[B].
 // dlogits must be zeroed by the caller (grapes_classifier_loss does it).
-__global__ void __launch_bounds__(LOSS_THREADS) k_classifier_loss(
-    const float* __restrict__ logits, int ldl, int C, const int* __restrict__ A_dev, int A_cap,
-    const int* __restrict__ row_ids, const int* __restrict__ targets, int B, const int64_t* __restrict__ labels_i64,
-    const float* __restrict__ labels_f32, float reg_param, float* __restrict__ dlogits, float* loss_out) {
+// Stage 1 (one warp per target row): per-row loss term -> row_loss[r], gradient rows.  Stage 2 (one block): fixed-order
+// sum of the B terms (+ the reg_param * sum_rows var(logits) term and its gradient) -> *loss_out.
+__global__ void __launch_bounds__(256) k_loss_rows(const float* __restrict__ logits, int ldl, int C,
+                                                   const int* __restrict__ row_ids, const int* __restrict__ targets,
+                                                   int B, const int64_t* __restrict__ labels_i64,
+                                                   const float* __restrict__ labels_f32, float* __restrict__ dlogits,
+                                                   float* __restrict__ row_loss) {
+    const int lane = lane_id();
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= B) return;
+    const int row = row_ids[r];
+    const float* lr = logits + (size_t)row * ldl;
+    if (labels_i64) {
+        const float invB = 1.0f / (float)B;
+        const int y = (int)labels_i64[targets[r]];
+        float mx = -INFINITY;
+        for (int c = lane; c < C; c += 32) mx = fmaxf(mx, lr[c]);
+        mx = warp_max(mx);
+        float se = 0.f;
+        for (int c = lane; c < C; c += 32) se += expf(lr[c] - mx);
+        se = warp_sum(se);
+        const float lse = mx + logf(se);
+        for (int c = lane; c < C; c += 32) {
+            const float pr = expf(lr[c] - lse);
+            dlogits[(size_t)row * ldl + c] = (pr - (c == y ? 1.f : 0.f)) * invB;
+        }
+        if (lane == 0) row_loss[r] = (lse - lr[y]) * invB;
+    } else {
+        const float inv = 1.0f / ((float)B * (float)C);
+        const float* yr = labels_f32 + (size_t)targets[r] * C;
+        float a = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float l = lr[c], y = yr[c];
+            a += (1.0f - y) * l + fmaxf(-l, 0.f) + log1pf(expf(-fabsf(l)));
+            dlogits[(size_t)row * ldl + c] = (1.0f / (1.0f + expf(-l)) - y) * inv;
+        }
+        a = warp_sum(a);
+        if (lane == 0) row_loss[r] = a * inv;
+    }
+}
+
+__global__ void __launch_bounds__(LOSS_THREADS) k_loss_final(const float* __restrict__ logits, int ldl, int C,
+                                                             const int* __restrict__ A_dev, int A_cap, int B,
+                                                             const float* __restrict__ row_loss, float reg_param,
+                                                             float* __restrict__ dlogits, float* loss_out) {
     __shared__ float s[32];
     const int A = min(*A_dev, A_cap);
     const int lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     float part = 0.f;
-    if (labels_i64) {
-        const float invB = 1.0f / (float)B;
-        for (int r = warp; r < B; r += nwarps) {
-            const int row = row_ids[r];
-            const float* lr = logits + (size_t)row * ldl;
-            const int y = (int)labels_i64[targets[r]];
-            float mx = -INFINITY;
-            for (int c = lane; c < C; c += 32) mx = fmaxf(mx, lr[c]);
-            mx = warp_max(mx);
-            float se = 0.f;
-            for (int c = lane; c < C; c += 32) se += expf(lr[c] - mx);
-            se = warp_sum(se);
-            const float lse = mx + logf(se);
-            for (int c = lane; c < C; c += 32) {
-                const float pr = expf(lr[c] - lse);
-                dlogits[(size_t)row * ldl + c] = (pr - (c == y ? 1.f : 0.f)) * invB;
-            }
-            if (lane == 0) part += (lse - lr[y]) * invB;
-        }
-    } else {
-        const float inv = 1.0f / ((float)B * (float)C);
-        for (int r = warp; r < B; r += nwarps) {
-            const int row = row_ids[r];
-            const float* lr = logits + (size_t)row * ldl;
-            const float* yr = labels_f32 + (size_t)targets[r] * C;
-            float a = 0.f;
-            for (int c = lane; c < C; c += 32) {
-                const float l = lr[c], y = yr[c];
-                a += (1.0f - y) * l + fmaxf(-l, 0.f) + log1pf(expf(-fabsf(l)));
-                dlogits[(size_t)row * ldl + c] = (1.0f / (1.0f + expf(-l)) - y) * inv;
-            }
-            part += a * inv;          // lanes hold partial sums, reduced below
-        }
-    }
+    for (int r = threadIdx.x; r < B; r += blockDim.x) part += row_loss[r];
     float loss = block_sum_1024(part, s);
     if (reg_param != 0.f && C > 1) {                     // reg_param * sum_rows var(logits, dim=1), unbiased
         float rp = 0.f;
@@ -158,8 +166,12 @@ int grapes_classifier_loss(grapes_ctx* ctx, const float* logits, int ldl, int C,
     GRAPES_REQUIRE(B > 0 && C > 0, "bad shape");
     cudaStream_t s = (cudaStream_t)stream;
     GRAPES_CUDA_OK(cudaMemsetAsync(dlogits, 0, sizeof(float) * (size_t)A_cap * ldl, s));
-    k_classifier_loss<<<1, LOSS_THREADS, 0, s>>>(logits, ldl, C, A_dev, A_cap, row_ids, targets, B, labels_i64,
-                                                 labels_f32, reg_param, dlogits, loss_out);
+    GRAPES_REQUIRE((size_t)B * sizeof(float) <= ctx->partials_bytes, "partial buffer too small");
+    k_loss_rows<<<grapes_div_up((long long)B * 32, 256), 256, 0, s>>>(logits, ldl, C, row_ids, targets, B, labels_i64,
+                                                                      labels_f32, dlogits, ctx->partials);
+    grapes_count_launches(1);
+    k_loss_final<<<1, LOSS_THREADS, 0, s>>>(logits, ldl, C, A_dev, A_cap, B, ctx->partials, reg_param, dlogits,
+                                            loss_out);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;

@@ -131,10 +131,12 @@ class GrapesEngine:
         z = torch.zeros
         e = torch.empty
         # bitmaps
-        self.bm_prev = [z(W, **u32), z(W, **u32)]
-        self.bm_batch = z(W, **u32)
-        self.bm_all = z(W, **u32)
-        self.bm_ind = z((max(self.num_ind, 1), W), **u32)
+        # one pool so a hop needs ONE memset (prev[cur] is adjacent to batch) and the step start ONE (all | ind rows)
+        self.bm_pool = z((4 + max(self.num_ind, 1)) * W, **u32)
+        self.bm_prev = [self.bm_pool[0:W], self.bm_pool[2 * W:3 * W]]
+        self.bm_batch = self.bm_pool[W:2 * W]
+        self.bm_all = self.bm_pool[3 * W:4 * W]
+        self.bm_ind = self.bm_pool[4 * W:].view(max(self.num_ind, 1), W)
         self.pref_batch, self.pref_nb, self.pref_all = z(W + 1, **i32), z(W + 1, **i32), z(W + 1, **i32)
         # lists
         self.targets = z(self.B, **i32)
@@ -165,8 +167,8 @@ class GrapesEngine:
         self.dpre = e((1 if self.use_tc_bwd else self.cap_n, self.D), **f32)
         self.ukeys = e(self.cap_n, **i32)
         self.log_prob = z((self.H, self.cap_n), **f32)
-        self.scal = z(16, **f32)
-        self.stats = z((self.H, 4), **f32)
+        self.scal = None   # views into zero_pool, set below (scal | stats | gdir share one memset per step)
+        self.stats = None
         self.overflow = z(1, **i32)
         self.rng_state = torch.tensor([seed & 0x7fffffffffffffff, 0], dtype=torch.int64, device=dev)
         # induced blocks (global ids), one per hop
@@ -201,7 +203,10 @@ class GrapesEngine:
         self.n_par = n_par
         self.params = z(n_par, **f32)
         self.grads = z(n_par, **f32)
-        self.gdir = z(n_par, **f32)         # gradient DIRECTION of (log_z, sum log_prob) w.r.t. gf / z params
+        self.zero_pool = z(16 + 4 * self.H + n_par, **f32)
+        self.scal = self.zero_pool[:16]
+        self.stats = self.zero_pool[16:16 + 4 * self.H].view(self.H, 4)
+        self.gdir = self.zero_pool[16 + 4 * self.H:]   # gradient DIRECTION of (log_z, sum log_prob) w.r.t. gf / z params
         self.exp_avg, self.exp_avg_sq = z(n_par, **f32), z(n_par, **f32)
         self.adam_steps = z(2, **f32)        # [0] optimizer_c, [1] optimizer_gf
         gen = torch.Generator().manual_seed(seed)
@@ -261,12 +266,8 @@ class GrapesEngine:
         indptr, indices, X = ptr(g.indptr), ptr(g.indices), ptr(self.x)
 
         # ---- per-batch reset (main.py:161-176) ----
-        L.grapes_zero(ctx, ptr(self.bm_all), 4 * W, st)
-        if self.use_ind:
-            L.grapes_zero(ctx, ptr(self.bm_ind), 4 * W * self.num_ind, st)
-        L.grapes_zero(ctx, ptr(self.scal), 4 * 16, st)
-        L.grapes_zero(ctx, ptr(self.gdir), 4 * self.n_par, st)
-        L.grapes_zero(ctx, ptr(self.stats), 4 * 4 * H, st)
+        L.grapes_zero(ctx, ptr(self.bm_all), 4 * W * (1 + self.num_ind), st)          # all_nodes mask | indicator rows
+        L.grapes_zero(ctx, ptr(self.zero_pool), 4 * self.zero_pool.numel(), st)       # scalars | stats | gradient direction
         # counts[B] = B ; prev[0][:B] = prev[1][:B] = targets ; P0 = B
         L.grapes_append_list(ctx, ptr(self.targets), self._cnt("B"), B, ptr(self.prev[0]), 0, self._cnt("P0"), st)
         L.grapes_append_list(ctx, ptr(self.targets), self._cnt("B"), B, ptr(self.prev[1]), 0, self._cnt("P1"), st)
@@ -280,8 +281,7 @@ class GrapesEngine:
             P_dev = self._cnt("P0") if cur == 0 else self._cnt("P1")
             Pn_dev = self._cnt("P0") if nxt == 0 else self._cnt("P1")
             rows = ptr(self.prev[cur])
-            L.grapes_zero(ctx, ptr(self.bm_prev[cur]), 4 * W, st)
-            L.grapes_zero(ctx, ptr(self.bm_batch), 4 * W, st)
+            L.grapes_zero(ctx, ptr(self.bm_prev[0]) if cur == 0 else ptr(self.bm_batch), 8 * W, st)   # prev[cur] + batch
             # get_neighborhoods + mask dedup (main.py:180-190)
             L.grapes_row_offsets(ctx, indptr, rows, P_dev, self.cap_P, ptr(self.row_off), self._cnt("m"), self.cap_m,
                                  ptr(self.bm_prev[cur]), ptr(self.bm_batch), ovf, st)
