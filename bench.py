@@ -206,7 +206,9 @@ def main():
     L = lib()
     K, W = args.steps, max(args.warmup, 3)
     nb = train_idx.numel() // B
-    order = [(rank + j * world) % nb for j in range(W + K)]          # target nodes sharded across ranks
+    from grapes_b200.dist import allreduce_mean_, shard_batches
+    mine = shard_batches(nb, rank, world)                             # batch i -> rank i mod W
+    order = [mine[j % len(mine)] for j in range(W + K)]
     batches = torch.stack([train_idx[b * B:(b + 1) * B] for b in order]).to(torch.int32)
     eng.counts[eng._CNT["B"]] = B
     use_graph = not args.no_graph
@@ -215,7 +217,7 @@ def main():
         eng.targets.copy_(batches[j])
         if world > 1:
             eng.step(None, apply_optim=False, use_graph=use_graph)
-            dist.all_reduce(eng.grads, op=dist.ReduceOp.AVG)        # the only collective: gradient allreduce
+            allreduce_mean_(eng.grads)                              # the only collective: gradient allreduce
             eng._enqueue_optim()
         else:
             eng.step(None, apply_optim=True, use_graph=use_graph)
@@ -267,7 +269,7 @@ def main():
         L.grapes_ids_i64_to_i32(graph.ctx, dev_t64.data_ptr(), B, eng.targets.data_ptr(), eng._cnt("B"), st)
         if world > 1:
             eng.step(None, apply_optim=False, use_graph=use_graph)
-            dist.all_reduce(eng.grads, op=dist.ReduceOp.AVG)
+            allreduce_mean_(eng.grads)
             eng._enqueue_optim()
         else:
             eng.step(None, apply_optim=True, use_graph=use_graph)

@@ -180,11 +180,14 @@ __global__ void __launch_bounds__(256) k_edge_local(const int* __restrict__ rows
                                                     const int* __restrict__ m_dev,
                                                     const uint32_t* __restrict__ bm,
                                                     const int* __restrict__ pref,
-                                                    int* __restrict__ e_src, int* __restrict__ e_dst) {
+                                                    int* __restrict__ e_src, int* __restrict__ e_dst, int* cnt_hist) {
     const int m = *m_dev;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < m; e += gridDim.x * blockDim.x) {
-        e_src[e] = bitmap_rank(bm, pref, rows[e_row[e]]);
-        e_dst[e] = bitmap_rank(bm, pref, e_col[e]);
+        const int s = bitmap_rank(bm, pref, rows[e_row[e]]);
+        const int d = bitmap_rank(bm, pref, e_col[e]);
+        e_src[e] = s;
+        e_dst[e] = d;
+        if (cnt_hist && s != d) atomicAdd(&cnt_hist[d], 1);       // in-degree histogram of the CSR build, fused
     }
 }
 
@@ -271,10 +274,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_i32(const int* __restrict
 // claim slots from the back of each row; leaves cnt[] all-zero again
 __global__ void __launch_bounds__(256) k_fill(const int* __restrict__ key, const int* __restrict__ val,
                                               const int* __restrict__ E_dev, int cap_E,
-                                              const int* __restrict__ off, int* cnt, int* __restrict__ out_val,
-                                              int* hub_count) {
+                                              const int* __restrict__ off, int* cnt, int* __restrict__ out_val) {
     const int E = min(*E_dev, cap_E);
-    if (blockIdx.x == 0 && threadIdx.x == 0) *hub_count = 0;      // the previous build's k_sort_hub is done (stream order)
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
         const int k = key[e], v = val[e];
         if (k != v) {
@@ -284,52 +285,46 @@ __global__ void __launch_bounds__(256) k_fill(const int* __restrict__ key, const
     }
 }
 
-#define SORT_SMALL 32
+// One warp per row: rows of <= 32 values are rank-sorted in registers (shuffles), longer rows by a rank sort
+// through `tmp` (O(len^2 / 32) per warp; in-degrees are bounded by the number of expanded rows).
 __global__ void __launch_bounds__(256) k_sort_rows(const int* __restrict__ off, const int* __restrict__ n_dev,
-                                                   int cap_n, int* vals, int* hub_rows, int* hub_count,
-                                                   int hub_cap, int* overflow) {
+                                                   int cap_n, int* vals, int* tmp) {
     const int n = min(*n_dev, cap_n);
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-        const int beg = off[j], len = off[j + 1] - beg;
-        if (len < 2) continue;
-        if (len > SORT_SMALL) {
-            const int slot = atomicAdd(hub_count, 1);
-            if (slot < hub_cap) hub_rows[slot] = j; else atomicOr(overflow, GRAPES_OVF_HUB);
-            continue;
-        }
-        int* a = vals + beg;
-        for (int i = 1; i < len; ++i) {                      // insertion sort, rows are short
-            const int x = a[i];
-            int k = i - 1;
-            while (k >= 0 && a[k] > x) { a[k + 1] = a[k]; --k; }
-            a[k + 1] = x;
-        }
-    }
-}
-
-// one block per hub row: rank sort (values inside a row are distinct or ties are harmless)
-__global__ void __launch_bounds__(256) k_sort_hub(const int* __restrict__ off, int* vals, int* tmp,
-                                                  const int* __restrict__ hub_rows, int* hub_count, int hub_cap) {
-    const int nh = min(*hub_count, hub_cap);
-    for (int h = blockIdx.x; h < nh; h += gridDim.x) {
-        const int j = hub_rows[h];
-        const int beg = off[j], len = off[j + 1] - beg;
-        const int* a = vals + beg;
-        for (int i = threadIdx.x; i < len; i += blockDim.x) {
-            const int x = a[i];
-            int r = 0;
-            for (int t = 0; t < len; ++t) {
-                const int y = a[t];
-                r += (y < x) || (y == x && t < i);
+    const int lane = lane_id();
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int j0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; j0 < n; j0 += warps * 32) {
+        // each lane inspects one row of a 32-row group; rows needing work are then handled by the whole warp
+        const int jr = j0 + lane;
+        const int len_l = (jr < n) ? off[jr + 1] - off[jr] : 0;
+        unsigned todo = __ballot_sync(GRAPES_FULL_MASK, len_l >= 2);
+        while (todo) {
+            const int t = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const int j = j0 + t;
+            const int beg = off[j], len = off[j + 1] - beg;
+            if (len <= 32) {
+                const int x = (lane < len) ? vals[beg + lane] : 0x7fffffff;
+                int r = 0;
+                for (int u = 0; u < len; ++u) {
+                    const int y = __shfl_sync(GRAPES_FULL_MASK, x, u);
+                    r += (y < x) || (y == x && u < lane);
+                }
+                __syncwarp();
+                if (lane < len) vals[beg + r] = x;
+            } else {
+                for (int i = lane; i < len; i += 32) {
+                    const int x = vals[beg + i];
+                    int r = 0;
+                    for (int u = 0; u < len; ++u) { const int y = vals[beg + u]; r += (y < x) || (y == x && u < i); }
+                    tmp[beg + r] = x;
+                }
+                __syncwarp();
+                for (int i = lane; i < len; i += 32) vals[beg + i] = tmp[beg + i];
             }
-            tmp[beg + r] = x;
+            __syncwarp();
         }
-        __syncthreads();
-        for (int i = threadIdx.x; i < len; i += blockDim.x) vals[beg + i] = tmp[beg + i];
-        __syncthreads();
     }
 }
-
 
 // ---------------------------------------------------------------------------------------
 // k_build_csr_small: the whole build (hist -> scan -> fill -> per-row sort -> deg^-1/2) in ONE 1024-thread CTA for
@@ -557,10 +552,11 @@ int grapes_rank_nodes(grapes_ctx* ctx, const uint32_t* bm_batch, const uint32_t*
 }
 
 int grapes_edges_to_local(grapes_ctx* ctx, const int* rows, const int* e_row, const int* e_col, const int* m_dev,
-                          int cap_m, const uint32_t* bm, const int* pref, int* e_src, int* e_dst, void* stream) {
+                          int cap_m, const uint32_t* bm, const int* pref, int* e_src, int* e_dst, int* cnt_hist,
+                          void* stream) {
     GRAPES_REQUIRE(ctx && rows && e_row && e_col && m_dev && bm && pref && e_src && e_dst, "null argument");
     k_edge_local<<<grid_for(ctx, cap_m, 256), 256, 0, (cudaStream_t)stream>>>(rows, e_row, e_col, m_dev, bm, pref,
-                                                                              e_src, e_dst);
+                                                                              e_src, e_dst, cnt_hist);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
@@ -576,12 +572,12 @@ int grapes_relabel(grapes_ctx* ctx, const int* ids, const int* count_dev, int ca
 }
 
 int grapes_build_csr(grapes_ctx* ctx, const int* key, const int* val, const int* E_dev, int cap_E,
-                     const int* n_dev, int cap_n, int* cnt_scratch, int* off, int* sorted_val, int* tmp_val,
-                     float* dinv, int* nnz_dev, int* overflow, void* stream) {
+                     const int* n_dev, int cap_n, int* cnt_scratch, int hist_done, int* off, int* sorted_val,
+                     int* tmp_val, float* dinv, int* nnz_dev, int* overflow, void* stream) {
     GRAPES_REQUIRE(ctx && key && val && E_dev && n_dev && cnt_scratch && off && sorted_val && tmp_val && overflow,
                    "null argument");
     cudaStream_t s = (cudaStream_t)stream;
-    if (cap_n <= SMALL_N && cap_E <= 8 * SMALL_N) {
+    if (!hist_done && cap_n <= SMALL_N) {
         k_build_csr_small<<<1, 1024, 0, s>>>(key, val, E_dev, cap_E, n_dev, cap_n, off, sorted_val, tmp_val, dinv,
                                              nnz_dev);
         grapes_count_launches(1);
@@ -590,19 +586,17 @@ int grapes_build_csr(grapes_ctx* ctx, const int* key, const int* val, const int*
     }
     const int tiles = grapes_div_up(cap_n, SCAN_TILE);
     GRAPES_REQUIRE(tiles <= ctx->scan_cap_tiles, "scan scratch too small for cap_n");
-    GRAPES_CUDA_OK(cudaMemsetAsync(cnt_scratch, 0, sizeof(int) * (size_t)cap_n, s));
-    k_hist<<<grid_for(ctx, cap_E, 256), 256, 0, s>>>(key, val, E_dev, cap_E, cnt_scratch);
-    grapes_count_launches(1);
+    if (!hist_done) {
+        // cnt_scratch is all-zero on entry by contract (zero-initialised by the caller; k_fill returns it to zero)
+        k_hist<<<grid_for(ctx, cap_E, 256), 256, 0, s>>>(key, val, E_dev, cap_E, cnt_scratch);
+        grapes_count_launches(1);
+    }
     k_scan_i32<<<grapes_max_i(tiles, 1), SCAN_THREADS, 0, s>>>(cnt_scratch, n_dev, cap_n, off, dinv, nnz_dev,
                                                               ctx->scan_status, ctx->scan_counters);
     grapes_count_launches(1);
-    k_fill<<<grid_for(ctx, cap_E, 256), 256, 0, s>>>(key, val, E_dev, cap_E, off, cnt_scratch, sorted_val,
-                                                     ctx->hub_count);
+    k_fill<<<grid_for(ctx, cap_E, 256), 256, 0, s>>>(key, val, E_dev, cap_E, off, cnt_scratch, sorted_val);
     grapes_count_launches(1);
-    k_sort_rows<<<grid_for(ctx, cap_n, 256), 256, 0, s>>>(off, n_dev, cap_n, sorted_val, ctx->hub_rows,
-                                                          ctx->hub_count, ctx->hub_cap, overflow);
-    grapes_count_launches(1);
-    k_sort_hub<<<ctx->sm_count, 256, 0, s>>>(off, sorted_val, tmp_val, ctx->hub_rows, ctx->hub_count, ctx->hub_cap);
+    k_sort_rows<<<grid_for(ctx, cap_n, 256), 256, 0, s>>>(off, n_dev, cap_n, sorted_val, tmp_val);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;

@@ -179,6 +179,39 @@ __global__ void __launch_bounds__(256) k_fill_inv_count(float* __restrict__ v, c
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) v[j] = inv;
 }
 
+// both parts in one launch: blocks [0, nbA) do the self term for rows that are NOT expanded rows (tested in the
+// prev bitmap), blocks [nbA, ..) own the expanded rows completely (self term + their out-edges) -> no write race.
+__global__ void __launch_bounds__(256) k_dz_fused(const float* __restrict__ dl, const int* __restrict__ n_dev, int cap_n,
+                                                  const int* __restrict__ P_dev, int cap_P,
+                                                  const int* __restrict__ row_off, const int* __restrict__ e_src,
+                                                  const int* __restrict__ e_dst, const float* __restrict__ dinv,
+                                                  const uint32_t* __restrict__ bm_prev,
+                                                  const int* __restrict__ batch_nodes, int nbA,
+                                                  float* __restrict__ dz) {
+    if ((int)blockIdx.x < nbA) {
+        const int n = min(*n_dev, cap_n);
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += nbA * blockDim.x)
+            if (!bitmap_test(bm_prev, batch_nodes[j])) dz[j] = dinv[j] * dinv[j] * dl[j];
+        return;
+    }
+    const int P = min(*P_dev, cap_P);
+    const int lane = lane_id();
+    const int nbB = gridDim.x - nbA;
+    const int warps = (nbB * blockDim.x) >> 5;
+    for (int i = (((int)blockIdx.x - nbA) * blockDim.x + threadIdx.x) >> 5; i < P; i += warps) {
+        const int beg = row_off[i], end = row_off[i + 1];
+        if (beg >= end) continue;
+        const int s = e_src[beg];
+        float a = 0.f;
+        for (int e = beg + lane; e < end; e += 32) {
+            const int d = e_dst[e];
+            if (d != s) a = fmaf(dinv[d], dl[d], a);
+        }
+        a = warp_sum(a);
+        if (lane == 0) dz[s] = dinv[s] * dinv[s] * dl[s] + dinv[s] * a;
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // Deterministic reductions
 // ---------------------------------------------------------------------------------------
@@ -573,9 +606,17 @@ int grapes_aggregate_scalar(grapes_ctx* ctx, const float* z, int nparts, int par
 
 int grapes_aggregate_scalar_T(grapes_ctx* ctx, const float* dl, const int* n_dev, int cap_n, const int* P_dev,
                               int cap_P, const int* row_off, const int* e_src, const int* e_dst, const float* dinv,
-                              float* dz, void* stream) {
+                              const uint32_t* bm_prev, const int* batch_nodes, float* dz, void* stream) {
     GRAPES_REQUIRE(ctx && dl && n_dev && P_dev && row_off && e_src && e_dst && dinv && dz, "null argument");
     cudaStream_t s = (cudaStream_t)stream;
+    if (bm_prev && batch_nodes) {
+        const int nbA = grid_for(ctx, cap_n, 256), nbB = grid_for(ctx, (long long)cap_P * 32, 256);
+        k_dz_fused<<<nbA + nbB, 256, 0, s>>>(dl, n_dev, cap_n, P_dev, cap_P, row_off, e_src, e_dst, dinv, bm_prev,
+                                             batch_nodes, nbA, dz);
+        grapes_count_launches(1);
+        GRAPES_LAUNCH_OK();
+        return GRAPES_OK;
+    }
     k_dz_self<<<grid_for(ctx, cap_n, 256), 256, 0, s>>>(dl, n_dev, cap_n, dinv, dz);
     grapes_count_launches(1);
     k_dz_rows<<<grid_for(ctx, (long long)cap_P * 32, 256), 256, 0, s>>>(dl, P_dev, cap_P, row_off, e_src, e_dst, dinv,

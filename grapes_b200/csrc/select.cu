@@ -297,6 +297,214 @@ __global__ void __cluster_dims__(SEL_CTAS, 1, 1) __launch_bounds__(SEL_THREADS) 
     cluster.sync();                                        // keep CTA 0's shared memory alive until all are done
 }
 
+// ---------------------------------------------------------------------------------------
+// k_select_reg: the same selection with every candidate key held ON CHIP (shared memory, blocked layout: CTA r owns
+// a contiguous chunk, thread t a contiguous sub-range of <= SEL_MAX_IPT items, stored column-wise so accesses are
+// conflict free), so keys are computed and read from global memory exactly once; 3 radix passes of 11 / 11 / 10
+// bits.  Used when c <= 8 * 1024 * SEL_MAX_IPT, else k_select (keys in global memory).
+// ---------------------------------------------------------------------------------------
+#define SEL_MAX_IPT 40
+#define SEL_BINS 2048
+
+struct SelSharedR {
+    int hist[SEL_BINS];
+    uint32_t prefix;
+    int kr;
+    float part[SEL_CTAS][8];
+    long long counts[SEL_CTAS];
+};
+
+__global__ void __cluster_dims__(SEL_CTAS, 1, 1) __launch_bounds__(SEL_THREADS, 1) k_select_reg(
+    const float* __restrict__ logits_all, const int* __restrict__ nb_local, const int* __restrict__ nb_nodes,
+    const int* __restrict__ c_dev, int cap_c, int k, int mode, const float* __restrict__ noise,
+    unsigned long long* rng_state, float* __restrict__ keys_out, int* __restrict__ sampled_out, int sampled_offset,
+    int* __restrict__ s_dev, int* __restrict__ total_dev, uint8_t* __restrict__ mask_out, float* __restrict__ log_prob,
+    float* tot_log_prob, float* __restrict__ stats, float* __restrict__ dl_all, float* sum_dl, uint32_t* bm_mark) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    __shared__ SelSharedR sh;
+    __shared__ int s_lhist[SEL_BINS];
+    __shared__ float s_red[SEL_WARPS];
+    __shared__ long long s_scan[SEL_WARPS + 2];
+    __shared__ uint32_t s_bcast_u;
+    __shared__ long long s_bcast_ll;
+    SelSharedR* sh0 = cluster.map_shared_rank(&sh, 0);
+    const int c = min(*c_dev, cap_c);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool take_all = (k >= c);
+    unsigned long long seed = 0ull, offset = 0ull;
+    if (mode == GRAPES_NOISE_PHILOX) { seed = rng_state[0]; offset = rng_state[1]; }
+    for (int b = tid; b < SEL_BINS; b += SEL_THREADS) sh.hist[b] = 0;
+    if (tid == 0) { sh.prefix = 0u; sh.kr = k; }
+    cluster.sync();
+
+    const int chunk = (c + SEL_CTAS - 1) / SEL_CTAS;
+    const int cb = min(c, rank * chunk), ce = min(c, cb + chunk);
+    const int ipt = (chunk + SEL_THREADS - 1) / SEL_THREADS;       // <= SEL_MAX_IPT (checked by the launcher)
+    const int i0 = min(ce, cb + tid * ipt);
+    const int cnt = max(0, min(ce, i0 + ipt) - i0);
+
+    // ---- pass 0: load once, keys + statistics ----
+    extern __shared__ uint32_t s_uk[];                             // [ipt][1024]
+#define UK(j) s_uk[(j) * SEL_THREADS + tid]
+    float pmin = INFINITY, pmax = -INFINITY, esum = 0.f, esq = 0.f;
+    for (int j = 0; j < cnt; ++j) {
+        {
+            const int i = i0 + j;
+            const float l = logits_all[nb_local ? nb_local[i] : i];
+            const float p = sigmoidf_(l);
+            float key;
+            if (mode == GRAPES_NOISE_KEYS) key = noise[i];
+            else if (mode == GRAPES_NOISE_NONE_TOPK_PROBS) key = p;
+            else {
+                float g;
+                if (mode == GRAPES_NOISE_GUMBEL) g = noise[i];
+                else {
+                    float u = (mode == GRAPES_NOISE_UNIFORM) ? noise[i] : philox_uniform(seed, offset, i);
+                    if (mode == GRAPES_NOISE_PHILOX) u = u * ((1.0f - 1.1920929e-07f) - 1.17549435e-38f) + 1.17549435e-38f;
+                    g = -logf(-logf(u));
+                }
+                key = logf(p) + g;
+            }
+            UK(j) = float_to_ordered(key);
+            if (keys_out) keys_out[i] = key;
+            pmin = fminf(pmin, p); pmax = fmaxf(pmax, p);
+            const float e = entropy_bits(p);
+            esum += e; esq = fmaf(e, e, esq);
+        }
+    }
+    pmin = block_reduce(pmin, s_red, OpMin(), INFINITY);
+    pmax = block_reduce(pmax, s_red, OpMax(), -INFINITY);
+    esum = block_reduce(esum, s_red, OpAdd(), 0.f);
+    esq = block_reduce(esq, s_red, OpAdd(), 0.f);
+    if (tid == 0) { sh0->part[rank][0] = pmin; sh0->part[rank][1] = pmax; sh0->part[rank][2] = esum; sh0->part[rank][3] = esq; }
+
+    // ---- radix select: 11 + 11 + 10 bits ----
+    uint32_t thr = 0u;
+    int kr = 0;
+    if (!take_all) {
+        const int shifts[3] = {21, 10, 0};
+        const int nbits[3] = {11, 11, 10};
+#pragma unroll
+        for (int ps = 0; ps < 3; ++ps) {
+            const int shift = shifts[ps];
+            const uint32_t dmask = (1u << nbits[ps]) - 1u;
+            for (int b = tid; b < SEL_BINS; b += SEL_THREADS) s_lhist[b] = 0;
+            if (tid == 0) s_bcast_u = sh0->prefix;
+            __syncthreads();
+            const uint32_t prefix = s_bcast_u;
+            const uint32_t himask = (ps == 0) ? 0u : (0xffffffffu << (shift + nbits[ps]));
+            for (int j = 0; j < cnt; ++j) {
+                const uint32_t u = UK(j);
+                if ((u & himask) == prefix) atomicAdd(&s_lhist[(u >> shift) & dmask], 1);
+            }
+            __syncthreads();
+            for (int b = tid; b < SEL_BINS; b += SEL_THREADS) {
+                const int a = s_lhist[b];
+                if (a) atomicAdd(&sh0->hist[b], a);
+            }
+            cluster.sync();
+            if (rank == 0 && warp == 0) {
+                // lane l owns bins [2047-64l-63 .. 2047-64l] in descending order
+                int msum = 0;
+                for (int t = 0; t < 64; ++t) msum += sh.hist[SEL_BINS - 1 - (lane * 64 + t)];
+                const int incl = warp_scan_incl(msum);
+                const int excl = incl - msum;
+                const int krem = sh.kr;
+                if (excl < krem && incl >= krem) {
+                    int cum = excl;
+                    for (int t = 0; t < 64; ++t) {
+                        const int bin = SEL_BINS - 1 - (lane * 64 + t);
+                        const int h = sh.hist[bin];
+                        if (cum + h >= krem) { sh.prefix = prefix | ((uint32_t)bin << shift); sh.kr = krem - cum; break; }
+                        cum += h;
+                    }
+                }
+                __syncwarp();
+                for (int t = 0; t < 64; ++t) sh.hist[lane * 64 + t] = 0;
+            }
+            cluster.sync();
+        }
+        thr = sh0->prefix;
+        kr = sh0->kr;
+    }
+
+    // ---- ordered selection straight from registers ----
+    int n_eq = 0, n_gt = 0;
+    if (!take_all) {
+        for (int j = 0; j < cnt; ++j) { const uint32_t u = UK(j); n_eq += (u == thr); n_gt += (u > thr); }
+    }
+    long long total;
+    const long long packed = ((long long)n_eq << 32) | (long long)n_gt;
+    const long long excl = block_scan_excl<long long>(packed, s_scan, &total);
+    if (tid == 0) sh0->counts[rank] = total;
+    cluster.sync();
+    if (tid == 0) {
+        long long b = 0;
+        for (int r = 0; r < rank; ++r) b += sh0->counts[r];
+        s_bcast_ll = b;
+    }
+    __syncthreads();
+    const long long before = s_bcast_ll;
+    int eq_before = (int)((before + excl) >> 32), gt_before = (int)((before + excl) & 0xffffffffll);
+    float lp_sum = 0.f, dl_sum = 0.f;
+    for (int j = 0; j < cnt; ++j) {
+        {
+            const int i = i0 + j;
+            bool sel; int pos;
+            if (take_all) { sel = true; pos = i; }
+            else {
+                const uint32_t u = UK(j);
+                sel = false; pos = 0;
+                if (u > thr) { sel = true; pos = gt_before + min(eq_before, kr); ++gt_before; }
+                else if (u == thr) { if (eq_before < kr) { sel = true; pos = gt_before + eq_before; } ++eq_before; }
+            }
+            const int li = nb_local ? nb_local[i] : i;
+            const float l = logits_all[li];
+            const float y = sel ? 1.f : 0.f;
+            const float lp = bern_log_prob(l, y);
+            if (log_prob) log_prob[i] = lp;
+            lp_sum += lp;
+            const float d = y - sigmoidf_(l);
+            if (dl_all) dl_all[li] = d;
+            dl_sum += d;
+            if (mask_out) mask_out[i] = sel ? 1 : 0;
+            if (sel) {
+                const int g = nb_nodes ? nb_nodes[i] : i;
+                if (sampled_out) sampled_out[sampled_offset + pos] = g;
+                if (bm_mark && nb_nodes) bitmap_set(bm_mark, g);
+            }
+        }
+    }
+    lp_sum = block_reduce(lp_sum, s_red, OpAdd(), 0.f);
+    dl_sum = block_reduce(dl_sum, s_red, OpAdd(), 0.f);
+    if (tid == 0) { sh0->part[rank][4] = lp_sum; sh0->part[rank][5] = dl_sum; }
+    cluster.sync();
+    if (rank == 0 && tid == 0) {
+        float mn = INFINITY, mx = -INFINITY, lp = 0.f, dl = 0.f;
+        double es = 0.0, eq = 0.0;
+        for (int r = 0; r < SEL_CTAS; ++r) {
+            mn = fminf(mn, sh.part[r][0]); mx = fmaxf(mx, sh.part[r][1]);
+            es += (double)sh.part[r][2]; eq += (double)sh.part[r][3]; lp += sh.part[r][4]; dl += sh.part[r][5];
+        }
+        const int s = take_all ? c : k;
+        if (s_dev) *s_dev = s;
+        if (total_dev) *total_dev = sampled_offset + s;
+        if (tot_log_prob) *tot_log_prob += lp;
+        if (sum_dl) *sum_dl += dl;
+        if (stats) {
+            if (take_all) { stats[0] = stats[1] = stats[2] = stats[3] = 0.f; }
+            else {
+                const double mean = (c > 0) ? es / (double)c : 0.0;
+                const double var = (c > 1) ? fmax(0.0, (eq - (double)c * mean * mean) / (double)(c - 1)) : 0.0;
+                stats[0] = mn; stats[1] = mx; stats[2] = (float)mean; stats[3] = (float)sqrt(var);
+            }
+        }
+        if (mode == GRAPES_NOISE_PHILOX && !take_all) rng_state[1] = offset + 1ull;
+    }
+    cluster.sync();
+}
+
 extern "C" {
 
 int grapes_select_topk(grapes_ctx* ctx, const float* logits_all, const int* nb_local, const int* nb_nodes,
@@ -311,6 +519,22 @@ int grapes_select_topk(grapes_ctx* ctx, const float* logits_all, const int* nb_l
     GRAPES_REQUIRE(!(noise_mode == GRAPES_NOISE_GUMBEL || noise_mode == GRAPES_NOISE_UNIFORM ||
                      noise_mode == GRAPES_NOISE_KEYS) || noise, "noise array required");
     GRAPES_REQUIRE(noise_mode != GRAPES_NOISE_PHILOX || rng_state, "rng_state required");
+    if (cap_c <= SEL_CTAS * SEL_THREADS * SEL_MAX_IPT) {
+        const int chunk = (cap_c + SEL_CTAS - 1) / SEL_CTAS;
+        const int ipt = (chunk + SEL_THREADS - 1) / SEL_THREADS;
+        const int smem = ipt * SEL_THREADS * 4;
+        static int attr = 0;
+        if (smem > attr) {
+            GRAPES_CUDA_OK(cudaFuncSetAttribute(k_select_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr = smem;
+        }
+        k_select_reg<<<SEL_CTAS, SEL_THREADS, smem, (cudaStream_t)stream>>>(
+            logits_all, nb_local, nb_nodes, c_dev, cap_c, k, noise_mode, noise, rng_state, keys_out, sampled_out,
+            sampled_offset, s_dev, total_dev, mask_out, log_prob, tot_log_prob, stats, dl_all, sum_dl, bm_mark);
+        grapes_count_launches(1);
+        GRAPES_LAUNCH_OK();
+        return GRAPES_OK;
+    }
     k_select<<<SEL_CTAS, SEL_THREADS, 0, (cudaStream_t)stream>>>(logits_all, nb_local, nb_nodes, c_dev, cap_c, k, noise_mode,
                                                           noise, rng_state, ukeys_scratch, keys_out, sampled_out,
                                                           sampled_offset, s_dev, total_dev, mask_out, log_prob,

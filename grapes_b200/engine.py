@@ -298,10 +298,11 @@ class GrapesEngine:
                                 ptr(self.bm_ind) if self.use_ind else None, self.num_ind, h, self.cap_n,
                                 self._cnt("n"), self._cnt("c"), ovf, st)
             L.grapes_edges_to_local(ctx, rows, ptr(self.e_row), ptr(self.e_col), self._cnt("m"), self.cap_m,
-                                    ptr(self.bm_batch), ptr(self.pref_batch), ptr(self.e_src), ptr(self.e_dst), st)
+                                    ptr(self.bm_batch), ptr(self.pref_batch), ptr(self.e_src), ptr(self.e_dst),
+                                    ptr(self.cnt_scratch), st)
             # gcn_norm structure of the hop graph (dst-sorted CSR, deg^-1/2)
             L.grapes_build_csr(ctx, ptr(self.e_dst), ptr(self.e_src), self._cnt("m"), self.cap_m, self._cnt("n"),
-                               self.cap_n, ptr(self.cnt_scratch), ptr(self.in_off), ptr(self.in_src),
+                               self.cap_n, ptr(self.cnt_scratch), 1, ptr(self.in_off), ptr(self.in_src),
                                ptr(self.tmp_val), ptr(self.dinv), self._cnt("nnz"), ovf, st)
             need_Y = not self.random_sampling
             if need_Y:
@@ -347,7 +348,7 @@ class GrapesEngine:
                 # d(sum log_prob)/d(theta_gf): direction accumulated now, scaled by g at the end
                 L.grapes_aggregate_scalar_T(ctx, ptr(self.dl_all), self._cnt("n"), self.cap_n, P_dev, self.cap_P,
                                             ptr(self.row_off), ptr(self.e_src), ptr(self.e_dst), ptr(self.dinv),
-                                            ptr(self.dz), st)
+                                            ptr(self.bm_prev[cur]), ptr(self.batch_nodes), ptr(self.dz), st)
                 gf = self.net_gf
                 if self.use_tc_bwd:
                     L.grapes_sampler_l1_bwd_tc(ctx, ptr(self.Y_hi), ptr(self.Y_lo), self.ldY, Fp + 1, self._cnt("n"),
@@ -383,7 +384,8 @@ class GrapesEngine:
                         L.grapes_fill_inv_count(ctx, ptr(self.zlogits), self._cnt("n"), self.cap_n, st)
                         L.grapes_aggregate_scalar_T(ctx, ptr(self.zlogits), self._cnt("n"), self.cap_n, P_dev,
                                                     self.cap_P, ptr(self.row_off), ptr(self.e_src), ptr(self.e_dst),
-                                                    ptr(self.dinv), ptr(self.dz), st)
+                                                    ptr(self.dinv), ptr(self.bm_prev[cur]), ptr(self.batch_nodes),
+                                                    ptr(self.dz), st)
                         if self.use_tc_bwd:
                             L.grapes_sampler_l1_bwd_tc(ctx, ptr(self.Y_hi), ptr(self.Y_lo), self.ldY, Fp + 1,
                                                        self._cnt("n"), self.cap_n, F, Fp, ptr(self.mask_z),
@@ -425,11 +427,11 @@ class GrapesEngine:
             L.grapes_relabel(ctx, ptr(self.blk_dst[hop]), self._cnt("blk", hop), self.cap_blk, ptr(self.bm_all),
                              ptr(self.pref_all), ptr(self.cl_dst[slot]), st)
             L.grapes_build_csr(ctx, ptr(self.cl_dst[slot]), ptr(self.cl_src[slot]), self._cnt("blk", hop),
-                               self.cap_blk, self._cnt("A"), self.cap_A, ptr(self.cnt_scratch),
+                               self.cap_blk, self._cnt("A"), self.cap_A, ptr(self.cnt_scratch), 0,
                                ptr(self.cl_in_off[slot]), ptr(self.cl_in_src[slot]), ptr(self.cl_tmp),
                                ptr(self.cl_dinv[slot]), self._cnt("cl_nnz", slot), ovf, st)
         L.grapes_build_csr(ctx, ptr(self.cl_src[1]), ptr(self.cl_dst[1]), self._cnt("blk", 0), self.cap_blk,
-                           self._cnt("A"), self.cap_A, ptr(self.cnt_scratch), ptr(self.cl_out_off),
+                           self._cnt("A"), self.cap_A, ptr(self.cnt_scratch), 0, ptr(self.cl_out_off),
                            ptr(self.cl_out_dst), ptr(self.cl_tmp), None, self._cnt("cl_nnz", 2), ovf, st)
         nc = self.net_c
         ldYc = self.Yc.shape[1]

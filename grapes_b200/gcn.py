@@ -45,9 +45,9 @@ class NormAdj:
         self.out_dst = torch.empty(capE, dtype=torch.int32, device=dev)
         self.dinv = torch.empty(capn, dtype=torch.float32, device=dev)
         c = self.cnt.data_ptr()
-        L.grapes_build_csr(ctx, ptr(dst), ptr(src), c, capE, c + 4, capn, ptr(scratch), ptr(self.in_off),
+        L.grapes_build_csr(ctx, ptr(dst), ptr(src), c, capE, c + 4, capn, ptr(scratch), 0, ptr(self.in_off),
                            ptr(self.in_src), ptr(tmp), ptr(self.dinv), c + 8, ptr(ovf), _stream())
-        L.grapes_build_csr(ctx, ptr(src), ptr(dst), c, capE, c + 4, capn, ptr(scratch), ptr(self.out_off),
+        L.grapes_build_csr(ctx, ptr(src), ptr(dst), c, capE, c + 4, capn, ptr(scratch), 0, ptr(self.out_off),
                            ptr(self.out_dst), ptr(tmp), None, c + 12, ptr(ovf), _stream())
 
     def aggregate(self, x: torch.Tensor, transpose: bool = False, bias=None) -> torch.Tensor:

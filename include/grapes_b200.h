@@ -91,9 +91,11 @@ int grapes_rank_nodes(grapes_ctx* ctx, const uint32_t* bm_batch, const uint32_t*
                       int* pref_nb, int* batch_nodes, int* nb_nodes, int* nb_local, uint32_t* ind_bits,
                       uint32_t* bm_ind, int ind_rows, int hop, int cap_n, int* n_dev, int* c_dev, int* overflow,
                       void* stream);
-/* node_map.map(neighborhoods) (main.py:195): local (src, dst) of every expanded edge.             */
+/* node_map.map(neighborhoods) (main.py:195): local (src, dst) of every expanded edge.  cnt_hist
+ * (optional, all-zero on entry) receives the in-degree histogram grapes_build_csr(hist_done=1) needs. */
 int grapes_edges_to_local(grapes_ctx* ctx, const int* rows, const int* e_row, const int* e_col, const int* m_dev,
-                          int cap_m, const uint32_t* bm, const int* pref, int* e_src, int* e_dst, void* stream);
+                          int cap_m, const uint32_t* bm, const int* pref, int* e_src, int* e_dst, int* cnt_hist,
+                          void* stream);
 /* TensorMap.map on an id list (main.py:213,253-254,259).                                          */
 int grapes_relabel(grapes_ctx* ctx, const int* ids, const int* count_dev, int cap, const uint32_t* bm,
                    const int* pref, int* out, void* stream);
@@ -113,10 +115,12 @@ int grapes_ids_i32_to_i64(grapes_ctx* ctx, const int* in, const int* count_dev, 
 
 /* ---- gcn_norm + aggregation (PyG 2.5.2 GCNConv / gcn_norm; call sites gcn.py:18,21,32,36) ----- */
 /* Edge list (key, val) -> CSR keyed by `key` with key==val edges dropped (add_remaining_self_loops),
- * values ascending inside a row.  dinv (optional) = (count + 1)^-1/2 = deg^-1/2 incl. the self-loop. */
+ * values ascending inside a row.  dinv (optional) = (count + 1)^-1/2 = deg^-1/2 incl. the self-loop.
+ * cnt_scratch[cap_n] must be all-zero on entry and is all-zero again on exit; hist_done=1 means it already
+ * holds the per-key counts (grapes_edges_to_local's cnt_hist).                                          */
 int grapes_build_csr(grapes_ctx* ctx, const int* key, const int* val, const int* E_dev, int cap_E, const int* n_dev,
-                     int cap_n, int* cnt_scratch, int* off, int* sorted_val, int* tmp_val, float* dinv, int* nnz_dev,
-                     int* overflow, void* stream);
+                     int cap_n, int* cnt_scratch, int hist_done, int* off, int* sorted_val, int* tmp_val, float* dinv,
+                     int* nnz_dev, int* overflow, void* stream);
 /* out[j,:F] = dinv[j]^2 X[g(j)] + sum_s dinv[s] dinv[j] X[g(s)] (+bias)(relu); g = nodes[] or identity.
  * Indicator columns [F, F+num_ind) from ind_bits; [F+num_ind, ldo) zero-filled.  out_hi/out_lo
  * (optional, same ldo) receive the 3xTF32 operand split tf32(v), tf32(v - tf32(v)) for the tcgen05 GEMM;
@@ -132,7 +136,7 @@ int grapes_aggregate_scalar(grapes_ctx* ctx, const float* z, int nparts, int par
 /* transposed scalar aggregation on the hop graph (backward of the above), row-major edge list.       */
 int grapes_aggregate_scalar_T(grapes_ctx* ctx, const float* dl, const int* n_dev, int cap_n, const int* P_dev,
                               int cap_P, const int* row_off, const int* e_src, const int* e_dst, const float* dinv,
-                              float* dz, void* stream);
+                              const uint32_t* bm_prev, const int* batch_nodes, float* dz, void* stream);
 /* v[j] = 1/n: gradient of log_z = mean(gcn_z logits) w.r.t. those logits (main.py:227-228)          */
 int grapes_fill_inv_count(grapes_ctx* ctx, float* v, const int* n_dev, int cap_n, void* stream);
 int grapes_vec_sum(grapes_ctx* ctx, const float* v, const int* n_dev, int cap_n, float scale, int divide_by_n,
