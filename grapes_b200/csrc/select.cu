@@ -303,7 +303,7 @@ __global__ void __cluster_dims__(SEL_CTAS, 1, 1) __launch_bounds__(SEL_THREADS) 
 // conflict free), so keys are computed and read from global memory exactly once; 3 radix passes of 11 / 11 / 10
 // bits.  Used when c <= 8 * 1024 * SEL_MAX_IPT, else k_select (keys in global memory).
 // ---------------------------------------------------------------------------------------
-#define SEL_MAX_IPT 40
+#define SEL_MAX_IPT 24
 #define SEL_BINS 2048
 
 struct SelSharedR {
@@ -345,13 +345,26 @@ __global__ void __cluster_dims__(SEL_CTAS, 1, 1) __launch_bounds__(SEL_THREADS, 
     const int cnt = max(0, min(ce, i0 + ipt) - i0);
 
     // ---- pass 0: load once, keys + statistics ----
-    extern __shared__ uint32_t s_uk[];                             // [ipt][1024]
+    extern __shared__ uint32_t s_uk[];                             // [ipt][1024] keys, then [ipt][1024] logits
 #define UK(j) s_uk[(j) * SEL_THREADS + tid]
+    float* s_lg = reinterpret_cast<float*>(s_uk + ipt * SEL_THREADS);
+#define LG(j) s_lg[(j) * SEL_THREADS + tid]
+    // gather the logits first, 8 independent loads in flight per thread (the index -> logit chain is latency bound)
+    for (int j0 = 0; j0 < cnt; j0 += 8) {
+        int li[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) li[u] = (j0 + u < cnt) ? (nb_local ? nb_local[i0 + j0 + u] : i0 + j0 + u) : 0;
+        float lv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) lv[u] = (j0 + u < cnt) ? logits_all[li[u]] : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (j0 + u < cnt) LG(j0 + u) = lv[u];
+    }
     float pmin = INFINITY, pmax = -INFINITY, esum = 0.f, esq = 0.f;
     for (int j = 0; j < cnt; ++j) {
         {
             const int i = i0 + j;
-            const float l = logits_all[nb_local ? nb_local[i] : i];
+            const float l = LG(j);
             const float p = sigmoidf_(l);
             float key;
             if (mode == GRAPES_NOISE_KEYS) key = noise[i];
@@ -459,14 +472,13 @@ __global__ void __cluster_dims__(SEL_CTAS, 1, 1) __launch_bounds__(SEL_THREADS, 
                 if (u > thr) { sel = true; pos = gt_before + min(eq_before, kr); ++gt_before; }
                 else if (u == thr) { if (eq_before < kr) { sel = true; pos = gt_before + eq_before; } ++eq_before; }
             }
-            const int li = nb_local ? nb_local[i] : i;
-            const float l = logits_all[li];
+            const float l = LG(j);
             const float y = sel ? 1.f : 0.f;
             const float lp = bern_log_prob(l, y);
             if (log_prob) log_prob[i] = lp;
             lp_sum += lp;
             const float d = y - sigmoidf_(l);
-            if (dl_all) dl_all[li] = d;
+            if (dl_all) dl_all[nb_local ? nb_local[i] : i] = d;
             dl_sum += d;
             if (mask_out) mask_out[i] = sel ? 1 : 0;
             if (sel) {
@@ -522,7 +534,7 @@ int grapes_select_topk(grapes_ctx* ctx, const float* logits_all, const int* nb_l
     if (cap_c <= SEL_CTAS * SEL_THREADS * SEL_MAX_IPT) {
         const int chunk = (cap_c + SEL_CTAS - 1) / SEL_CTAS;
         const int ipt = (chunk + SEL_THREADS - 1) / SEL_THREADS;
-        const int smem = ipt * SEL_THREADS * 4;
+        const int smem = 2 * ipt * SEL_THREADS * 4;
         static int attr = 0;
         if (smem > attr) {
             GRAPES_CUDA_OK(cudaFuncSetAttribute(k_select_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
