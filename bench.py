@@ -316,10 +316,14 @@ def main():
         n_sum = sum(h["n"] for h in per_hop)
         nnz_sum = sum(h["nnz"] for h in per_hop)
         # algorithmic bytes / flops per STEP of each hot entry point
+        fwd_flops = 2.0 * (n_sum * Fp * D + per_hop[0]["n"] * F * D)
         alg = {
             "grapes_aggregate": ("hbm", sum(4 * h["n"] * (F + ldY) + 12 * h["n"] + 4 * h["nnz"] for h in per_hop)),
-            "grapes_sampler_l1_fwd": ("tensor", 2.0 * (n_sum * Fp * D + per_hop[0]["n"] * F * D)),
-            "grapes_sampler_l1_bwd": ("tensor", 4.0 * (n_sum * Fp * D + per_hop[0]["n"] * F * D)),
+            "grapes_sampler_l1_fwd": ("tensor", fwd_flops),
+            "grapes_sampler_l1_bwd": ("tensor", 2.0 * fwd_flops),
+            # tcgen05 path: the backward is ONE contraction S = mask^T (dz * Y) (no recompute), same flops as the forward
+            "grapes_sampler_l1_fwd_tc": ("tensor", fwd_flops),
+            "grapes_sampler_l1_bwd_tc": ("tensor", fwd_flops),
         }
         rooflines = {}
         for name, (bound, work) in alg.items():
