@@ -64,6 +64,7 @@ class _Lib:
         self.launches = 0          # number of C-ABI compute calls issued
         self.profiling = False     # when True every call is bracketed by CUDA events (bench.py breakdown)
         self._events = []
+        self.tag = ""              # appended to the profiled name (the engine tags its classifier-sized launches)
 
     def last_error(self) -> str:
         return self.cdll.grapes_last_error().decode()
@@ -82,7 +83,7 @@ class _Lib:
                 e0.record()
                 rc = fn(*args)
                 e1.record()
-                self._events.append((name, e0, e1))
+                self._events.append((name + self.tag, e0, e1))
             else:
                 rc = fn(*args)
             if rc != 0:

@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(256) k_expand(const int64_t* __restrict__ indp
 // k_rank_scan: single-pass scan over the node bitmap.  For every word: exclusive popcount
 // prefix (pref_batch; pref_nb for batch & ~prev).  Enumerates the set bits in ascending id
 // order, which IS the reference's local numbering (mask -> nonzero, main.py:189-195):
-//   batch_nodes[j] = v, nb_nodes[q] = v, nb_local[q] = j, ind_bits[j] = indicator columns of v.
+//   batch_nodes[j] = v, nb_nodes[q] = v, nb_local[q] = j, nb_index[j] = q (-1 if v is not a neighbour),
+//   ind_bits[j] = indicator columns of v.
 // bm_ind row `hop` receives batch & ~prev (indicator[neighbor_nodes, hop] = 1, main.py:191).
 // ---------------------------------------------------------------------------------------
 #define RANK_THREADS 256
@@ -87,8 +88,8 @@ __global__ void __launch_bounds__(256) k_expand(const int64_t* __restrict__ indp
 __global__ void __launch_bounds__(RANK_THREADS) k_rank_scan(
     const uint32_t* __restrict__ bm_batch, const uint32_t* __restrict__ bm_prev, int W,
     int* __restrict__ pref_batch, int* __restrict__ pref_nb, int* __restrict__ batch_nodes,
-    int* __restrict__ nb_nodes, int* __restrict__ nb_local, uint32_t* __restrict__ ind_bits,
-    uint32_t* bm_ind, int ind_rows, int hop, int cap_n, int* __restrict__ n_out,
+    int* __restrict__ nb_nodes, int* __restrict__ nb_local, int* __restrict__ nb_index,
+    uint32_t* __restrict__ ind_bits, uint32_t* bm_ind, int ind_rows, int hop, int cap_n, int* __restrict__ n_out,
     int* __restrict__ c_out, int* overflow, unsigned long long* status, unsigned int* counters) {
     __shared__ unsigned long long s_scan[RANK_THREADS / 32 + 2];
     __shared__ int s_tile;
@@ -155,7 +156,8 @@ __global__ void __launch_bounds__(RANK_THREADS) k_rank_scan(
                 if ((nbits >> t) & 1u) {
                     const int q = rn++;
                     if (q < cap_n && nb_nodes) { nb_nodes[q] = v; nb_local[q] = j; }
-                }
+                    if (nb_index && j < cap_n) nb_index[j] = q < cap_n ? q : -1;
+                } else if (nb_index && j < cap_n) nb_index[j] = -1;
             }
         }
         if ((W - 1) / RANK_TILE == tile && threadIdx.x == RANK_THREADS - 1) {
@@ -488,6 +490,21 @@ __global__ void __launch_bounds__(256) k_append_list(const int* __restrict__ src
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[off + i] = src[i];
     if (blockIdx.x == 0 && threadIdx.x == 0 && total) *total = off + n;
 }
+// k_step_reset: per-batch reset of the id lists (main.py:161-168): copies the targets to the head of every hop's
+// row list (batch_nodes = cat([targets, sampled]), main.py:236), marks them in up to two bitmaps and publishes P0.
+__global__ void __launch_bounds__(256) k_step_reset(const int* __restrict__ targets, const int* __restrict__ B_dev,
+                                                    int cap_B, int* __restrict__ lists, long long list_stride,
+                                                    int nlists, int* __restrict__ P0_dev, uint32_t* bm_a,
+                                                    uint32_t* bm_b) {
+    const int n = min(*B_dev, cap_B);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int t = targets[i];
+        for (int l = 0; l < nlists; ++l) lists[(long long)l * list_stride + i] = t;
+        if (bm_a) bitmap_set(bm_a, t);
+        if (bm_b) bitmap_set(bm_b, t);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && P0_dev) *P0_dev = n;
+}
 __global__ void __launch_bounds__(256) k_i64_to_i32(const int64_t* __restrict__ in, int* __restrict__ out, int n,
                                                     int* count_out) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = (int)in[i];
@@ -534,8 +551,8 @@ int grapes_expand_rows(grapes_ctx* ctx, const int64_t* indptr, const int* indice
 }
 
 int grapes_rank_nodes(grapes_ctx* ctx, const uint32_t* bm_batch, const uint32_t* bm_prev, int* pref_batch,
-                      int* pref_nb, int* batch_nodes, int* nb_nodes, int* nb_local, uint32_t* ind_bits,
-                      uint32_t* bm_ind, int ind_rows, int hop, int cap_n, int* n_dev, int* c_dev,
+                      int* pref_nb, int* batch_nodes, int* nb_nodes, int* nb_local, int* nb_index,
+                      uint32_t* ind_bits, uint32_t* bm_ind, int ind_rows, int hop, int cap_n, int* n_dev, int* c_dev,
                       int* overflow, void* stream) {
     GRAPES_REQUIRE(ctx && bm_batch && pref_batch && batch_nodes && n_dev && overflow, "null argument");
     GRAPES_REQUIRE(ind_rows >= 0 && ind_rows <= 8, "at most 8 indicator columns (sampling_hops <= 7)");
@@ -544,7 +561,7 @@ int grapes_rank_nodes(grapes_ctx* ctx, const uint32_t* bm_batch, const uint32_t*
     const int tiles = grapes_div_up(ctx->num_words, RANK_TILE);
     GRAPES_REQUIRE(tiles <= ctx->scan_cap_tiles, "scan scratch too small");
     k_rank_scan<<<tiles, RANK_THREADS, 0, (cudaStream_t)stream>>>(
-        bm_batch, bm_prev, ctx->num_words, pref_batch, pref_nb, batch_nodes, nb_nodes, nb_local, ind_bits,
+        bm_batch, bm_prev, ctx->num_words, pref_batch, pref_nb, batch_nodes, nb_nodes, nb_local, nb_index, ind_bits,
         bm_ind, ind_rows, hop, cap_n, n_dev, c_dev, overflow, ctx->scan_status, ctx->scan_counters);
         grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
@@ -639,6 +656,17 @@ int grapes_append_list(grapes_ctx* ctx, const int* src, const int* count_dev, in
     GRAPES_REQUIRE(ctx && src && count_dev && dst, "null argument");
     k_append_list<<<grid_for(ctx, cap, 256), 256, 0, (cudaStream_t)stream>>>(src, count_dev, cap, dst, dst_offset,
                                                                              total_dev);
+    grapes_count_launches(1);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+int grapes_step_reset(grapes_ctx* ctx, const int* targets, const int* B_dev, int cap_B, int* lists,
+                      int64_t list_stride, int nlists, int* P0_dev, uint32_t* bm_a, uint32_t* bm_b, void* stream) {
+    GRAPES_REQUIRE(ctx && targets && B_dev && lists && nlists >= 1, "null argument");
+    k_step_reset<<<grid_for(ctx, cap_B, 256), 256, 0, (cudaStream_t)stream>>>(targets, B_dev, cap_B, lists,
+                                                                              (long long)list_stride, nlists, P0_dev,
+                                                                              bm_a, bm_b);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;

@@ -221,6 +221,7 @@ __global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ part, 
     const int R = R_dev ? min(*R_dev, R_cap) : R_cap;
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
         float a = 0.f;
+#pragma unroll 8
         for (int r = 0; r < R; ++r) a += part[(size_t)r * ld + c];
         a *= scale;
         out[c] = accumulate ? out[c] + a : a;
@@ -236,6 +237,7 @@ __global__ void __launch_bounds__(256) k_colsum_slabs(const float* __restrict__ 
     const int r0 = blockIdx.y * rows_per, r1 = min(R, r0 + rows_per);
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
         float a = 0.f;
+#pragma unroll 8
         for (int r = r0; r < r1; ++r) a += Mx[(size_t)r * ld + c];
         part[(size_t)blockIdx.y * C + c] = a;
     }
@@ -435,11 +437,148 @@ __global__ void __launch_bounds__(G_THREADS) k_gemm_tn_splitk(const float* __res
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Small-tile variant (64x64x16 CTA tile, 256 threads, 4x4 per thread) for the classifier-sized products
+// (A = B + hops*k <= a few thousand rows): the 128x128 tiling would leave most of the 148 SMs idle.
+// Same summation order over k as the large-tile kernel (k ascending, one fmaf per k).
+// ---------------------------------------------------------------------------------------
+#define GS_M 64
+#define GS_N 64
+#define GS_PAD 4
+
+template <bool KC>
+__device__ __forceinline__ void load_tile_s(const float* __restrict__ T, int ld, int mn0, int MN, int k0, int k1,
+                                            float (*S)[GS_M + GS_PAD]) {
+    const int tid = threadIdx.x;
+    if (KC) {
+        const int mm = tid >> 2, kk0 = (tid & 3) * 4;
+        const int mrow = mn0 + mm;
+        const float* src = T + (size_t)mrow * ld + k0 + kk0;
+        const bool vec = ((ld & 3) == 0) && ((((size_t)T) & 15) == 0) && ((k0 & 3) == 0);
+        if (mrow < MN && vec && k0 + kk0 + 4 <= k1) {
+            const float4 a = *reinterpret_cast<const float4*>(src);
+            S[kk0 + 0][mm] = a.x; S[kk0 + 1][mm] = a.y; S[kk0 + 2][mm] = a.z; S[kk0 + 3][mm] = a.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int k = k0 + kk0 + i;
+                S[kk0 + i][mm] = (mrow < MN && k < k1) ? src[i] : 0.f;
+            }
+        }
+    } else {
+        const int mm = (tid & 15) * 4, kk = tid >> 4;
+        const int k = k0 + kk;
+        const float* src = T + (size_t)k * ld + mn0 + mm;
+        const bool vec = ((ld & 3) == 0) && ((((size_t)T) & 15) == 0) && ((mn0 & 3) == 0);
+        if (k < k1 && vec && mn0 + mm + 4 <= MN) {
+            const float4 a = *reinterpret_cast<const float4*>(src);
+            S[kk][mm] = a.x; S[kk][mm + 1] = a.y; S[kk][mm + 2] = a.z; S[kk][mm + 3] = a.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) S[kk][mm + i] = (k < k1 && mn0 + mm + i < MN) ? src[i] : 0.f;
+        }
+    }
+}
+
+template <bool A_KC, bool B_KC>
+__device__ __forceinline__ void gemm_mainloop_s(const float* __restrict__ A, int lda, int m0, int M,
+                                                const float* __restrict__ B, int ldb, int n0, int N, int k0, int k1,
+                                                float (*As)[GS_M + GS_PAD], float (*Bs)[GS_N + GS_PAD],
+                                                float (&acc)[4][4]) {
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    for (int k = k0; k < k1; k += GB_K) {
+        load_tile_s<A_KC>(A, lda, m0, M, k, k1, As);
+        load_tile_s<B_KC>(B, ldb, n0, N, k, k1, Bs);
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GB_K; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float a[4] = {a0.x, a0.y, a0.z, a0.w};
+            const float b[4] = {b0.x, b0.y, b0.z, b0.w};
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(a[r], b[c], acc[r][c]);
+        }
+        __syncthreads();
+    }
+}
+
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(G_THREADS) k_gemm_s(const float* __restrict__ A, int lda, const float* __restrict__ B,
+                                                      int ldb, float* __restrict__ C, int ldc,
+                                                      const int* __restrict__ M_dev, int M_cap, int N, int K,
+                                                      const float* __restrict__ bias, int relu,
+                                                      const float* __restrict__ relu_gate, int ldg) {
+    __shared__ __align__(16) float As[GB_K][GS_M + GS_PAD];
+    __shared__ __align__(16) float Bs[GB_K][GS_N + GS_PAD];
+    const int M = M_dev ? min(*M_dev, M_cap) : M_cap;
+    const int n0 = blockIdx.x * GS_N;
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    for (int m0 = blockIdx.y * GS_M; m0 < M; m0 += gridDim.y * GS_M) {
+        float acc[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+        gemm_mainloop_s<A_KC, B_KC>(A, lda, m0, M, B, ldb, n0, N, 0, K, As, Bs, acc);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int row = m0 + ty * 4 + r;
+            if (row >= M) continue;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int col = n0 + tx * 4 + c;
+                if (col >= N) continue;
+                float v = acc[r][c];
+                if (bias) v += bias[col];
+                if (relu) v = fmaxf(v, 0.f);
+                if (relu_gate) v = (relu_gate[(size_t)row * ldg + col] > 0.f) ? v : 0.f;
+                C[(size_t)row * ldc + col] = v;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(G_THREADS) k_gemm_tn_splitk_s(const float* __restrict__ A, int lda,
+                                                                const float* __restrict__ B, int ldb,
+                                                                const int* __restrict__ R_dev, int R_cap, int M, int N,
+                                                                float* __restrict__ part) {
+    __shared__ __align__(16) float As[GB_K][GS_M + GS_PAD];
+    __shared__ __align__(16) float Bs[GB_K][GS_N + GS_PAD];
+    const int R = R_dev ? min(*R_dev, R_cap) : R_cap;
+    const int slabs = gridDim.z;
+    int rows_per = (R + slabs - 1) / slabs;
+    rows_per = ((rows_per + GB_K - 1) / GB_K) * GB_K;
+    const int r0 = min(R, (int)blockIdx.z * rows_per), r1 = min(R, r0 + rows_per);
+    const int m0 = blockIdx.y * GS_M, n0 = blockIdx.x * GS_N;
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+    gemm_mainloop_s<false, false>(A, lda, m0, M, B, ldb, n0, N, r0, r1, As, Bs, acc);
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    float* P = part + (size_t)blockIdx.z * M * N;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int row = m0 + ty * 4 + r;
+        if (row >= M) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int col = n0 + tx * 4 + c;
+            if (col < N) P[(size_t)row * N + col] = acc[r][c];
+        }
+    }
+}
+
 // out[i] (+)= scale * sum_s part[s*size + i]
 __global__ void __launch_bounds__(256) k_reduce_slabs(const float* __restrict__ part, int slabs, int size, float scale,
                                                       int accumulate, float* __restrict__ out) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < size; i += gridDim.x * blockDim.x) {
         float a = 0.f;
+#pragma unroll 8
         for (int s = 0; s < slabs; ++s) a += part[(size_t)s * size + i];
         a *= scale;
         out[i] = accumulate ? out[i] + a : a;
@@ -656,12 +795,24 @@ int grapes_gemm(grapes_ctx* ctx, int layout, const float* A, int lda, const floa
     GRAPES_REQUIRE(M_cap >= 0 && N > 0 && K > 0, "bad shape");
     if (M_cap == 0) return GRAPES_OK;
     cudaStream_t s = (cudaStream_t)stream;
+    grapes_count_launches(1);
+    if ((long long)grapes_div_up(N, GB_N) * grapes_div_up(M_cap, GB_M) < ctx->sm_count) {
+        // classifier-sized product: 64x64 tiles so the grid covers the GPU
+        dim3 grid(grapes_div_up(N, GS_N), grapes_min_i(grapes_div_up(M_cap, GS_M), 65535));
+        switch (layout & 3) {
+            case 3: k_gemm_s<true, true><<<grid, G_THREADS, 0, s>>>(A, lda, B, ldb, C, ldc, M_dev, M_cap, N, K, bias, relu, relu_gate, ldg); break;
+            case 1: k_gemm_s<true, false><<<grid, G_THREADS, 0, s>>>(A, lda, B, ldb, C, ldc, M_dev, M_cap, N, K, bias, relu, relu_gate, ldg); break;
+            case 2: k_gemm_s<false, true><<<grid, G_THREADS, 0, s>>>(A, lda, B, ldb, C, ldc, M_dev, M_cap, N, K, bias, relu, relu_gate, ldg); break;
+            default: k_gemm_s<false, false><<<grid, G_THREADS, 0, s>>>(A, lda, B, ldb, C, ldc, M_dev, M_cap, N, K, bias, relu, relu_gate, ldg); break;
+        }
+        GRAPES_LAUNCH_OK();
+        return GRAPES_OK;
+    }
     const int tiles_n = grapes_div_up(N, GB_N);
     int tiles_m = grapes_div_up(M_cap, GB_M);
     const int max_y = grapes_max_i(1, (ctx->sm_count * 4) / tiles_n);
     tiles_m = grapes_min_i(tiles_m, max_y);
     dim3 grid(tiles_n, tiles_m);
-    grapes_count_launches(1);
     switch (layout & 3) {
         case 3: k_gemm<true, true><<<grid, G_THREADS, 0, s>>>(A, lda, B, ldb, C, ldc, M_dev, M_cap, N, K, bias, relu, relu_gate, ldg); break;
         case 1: k_gemm<true, false><<<grid, G_THREADS, 0, s>>>(A, lda, B, ldb, C, ldc, M_dev, M_cap, N, K, bias, relu, relu_gate, ldg); break;
@@ -677,13 +828,15 @@ int grapes_gemm_tn(grapes_ctx* ctx, const float* A, int lda, const float* B, int
                    int M, int N, float scale, int accumulate, float* out, void* stream) {
     GRAPES_REQUIRE(ctx && A && B && out, "null argument");
     cudaStream_t s = (cudaStream_t)stream;
-    const int tiles_n = grapes_div_up(N, GB_N), tiles_m = grapes_div_up(M, GB_M);
-    int slabs = grapes_max_i(1, ctx->sm_count / (tiles_n * tiles_m));
+    const bool small = R_cap <= 16384;                 // classifier-sized: 64x64 tiles, fewer / shorter slabs
+    const int tiles_n = grapes_div_up(N, small ? GS_N : GB_N), tiles_m = grapes_div_up(M, small ? GS_M : GB_M);
+    int slabs = grapes_max_i(1, (small ? 2 * ctx->sm_count : ctx->sm_count) / (tiles_n * tiles_m));
     slabs = grapes_min_i(slabs, grapes_max_i(1, grapes_div_up(R_cap, 4 * GB_K)));
     const size_t need = (size_t)slabs * M * N * sizeof(float);
     GRAPES_REQUIRE(need <= ctx->partials_bytes, "split-K partial buffer too small");
     dim3 grid(tiles_n, tiles_m, slabs);
-    k_gemm_tn_splitk<<<grid, G_THREADS, 0, s>>>(A, lda, B, ldb, R_dev, R_cap, M, N, ctx->partials);
+    if (small) k_gemm_tn_splitk_s<<<grid, G_THREADS, 0, s>>>(A, lda, B, ldb, R_dev, R_cap, M, N, ctx->partials);
+    else k_gemm_tn_splitk<<<grid, G_THREADS, 0, s>>>(A, lda, B, ldb, R_dev, R_cap, M, N, ctx->partials);
     grapes_count_launches(1);
     k_reduce_slabs<<<grid_for(ctx, (long long)M * N, 256), 256, 0, s>>>(ctx->partials, slabs, M * N, scale, accumulate,
                                                                        out);

@@ -371,12 +371,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_l1_bwd_tc(
         // ===== expanders (warps 2..5), then epilogue =====
         const int e = (warp - 2) * 32 + lane;            // d index inside a half
         int stage = 0; uint32_t phase = 0;
+        // software pipeline: the dz / mask words of the NEXT group are loaded while this group is expanded, so the
+        // global-load latency is off the expander's critical path
+        float dz_nx = 0.f;
+        uint32_t words_nx[4] = {0u, 0u, 0u, 0u};
+        if ((int)blockIdx.x < groups) {
+            const int r0 = blockIdx.x * TCB_ROWS + lane;
+            dz_nx = (r0 < n) ? dz[r0] : 0.f;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) if (h < NH) words_nx[h] = maskT[(size_t)blockIdx.x * D + h * 128 + e];
+        }
         for (int g = blockIdx.x; g < groups; g += gridDim.x) {
-            const int r = g * TCB_ROWS + lane;
-            const float dzr = (r < n) ? dz[r] : 0.f;
-            const float dzh = tf32_rna(dzr), dzl = tf32_rna(dzr - dzh);
+            const float dzr = dz_nx;
             uint32_t words[4];
-            for (int h = 0; h < NH && h < 4; ++h) words[h] = maskT[(size_t)g * D + h * 128 + e];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) words[h] = words_nx[h];
+            const int gn = g + gridDim.x;
+            if (gn < groups) {
+                const int rn = gn * TCB_ROWS + lane;
+                dz_nx = (rn < n) ? dz[rn] : 0.f;
+#pragma unroll
+                for (int h = 0; h < 4; ++h) if (h < NH) words_nx[h] = maskT[(size_t)gn * D + h * 128 + e];
+            }
+            const float dzh = tf32_rna(dzr), dzl = tf32_rna(dzr - dzh);
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* st = smem + stage * stage_bytes;
 #pragma unroll
@@ -388,7 +405,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_l1_bwd_tc(
                     vl[i] = __shfl_sync(GRAPES_FULL_MASK, dzl, c * 4 + i);
                 }
                 const int off = e * 128 + ((c ^ (e & 7)) << 4);          // SWIZZLE_128B: 16-byte chunk index ^ (row % 8)
-                for (int h = 0; h < NH && h < 4; ++h) {
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    if (h >= NH) break;
                     const uint32_t w = words[h] >> (c * 4);
                     float4 ah, al;
                     ah.x = (w & 1u) ? vh[0] : 0.f; ah.y = (w & 2u) ? vh[1] : 0.f; ah.z = (w & 4u) ? vh[2] : 0.f; ah.w = (w & 8u) ? vh[3] : 0.f;
@@ -433,44 +452,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_l1_bwd_tc(
 }
 
 // Sum the per-CTA partials (fixed order) and turn S into the three gradients, accumulated (+=, times scale).
-// One block per hidden unit d; 8 groups of 128 threads split the partials, then a fixed-order combine.
-#define FIN_GROUPS 8
-__global__ void __launch_bounds__(128 * FIN_GROUPS) k_l1_bwd_finalize(
+// One 1024-thread block per hidden unit d.  N/4 threads cover one partial row with float4 loads; the 1024/(N/4)
+// thread groups split the partials, each thread keeping 5 independent 16-byte loads in flight, then a fixed-order
+// combine through shared memory.
+#define FIN_THREADS 1024
+__global__ void __launch_bounds__(FIN_THREADS) k_l1_bwd_finalize(
     const float* __restrict__ part, int nparts, int D, int N, int K, const float* __restrict__ W1, int ldw,
     const float* __restrict__ b1, const float* __restrict__ w2, int ones_col, float scale, float* __restrict__ gW1,
     float* __restrict__ gb1, float* __restrict__ gw2) {
-    __shared__ float sums[FIN_GROUPS][256];
-    __shared__ float red[4];
+    __shared__ __align__(16) float sums[4 * FIN_THREADS];        // [groups][N], groups * N == 4096
+    __shared__ float red[8];
     const int d = blockIdx.x;
-    const int kl = threadIdx.x & 127, pg = threadIdx.x >> 7;
-    for (int k0 = 0; k0 < N; k0 += 128) {            // N <= 256
-        const int k = k0 + kl;
-        float s = 0.f;
-        if (k < N)
-            for (int p = pg; p < nparts; p += FIN_GROUPS) s += part[((size_t)p * D + d) * N + k];
-        sums[pg][k0 + kl] = s;
-    }
-    __syncthreads();
-    if (pg == 0) {
-        const float w2d = w2[d];
-        float acc_w2 = 0.f;
-        for (int k = kl; k < N; k += 128) {
-            float s = 0.f;
+    const int nq = N >> 2;                                       // threads per partial row (N is a multiple of 32, <= 256)
+    const int groups = FIN_THREADS / nq;
+    const int pg = threadIdx.x / nq, kq = threadIdx.x % nq;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = pg; p < nparts; p += 5 * groups) {
+        float4 v[5];
 #pragma unroll
-            for (int g = 0; g < FIN_GROUPS; ++g) s += sums[g][k];
-            if (k < K) {
-                gW1[(size_t)d * K + k] += scale * w2d * s;
-                acc_w2 = fmaf(W1[(size_t)d * ldw + k], s, acc_w2);
-            } else if (k == ones_col) {
-                gb1[d] += scale * w2d * s;
-                acc_w2 = fmaf(b1[d], s, acc_w2);
-            }
+        for (int u = 0; u < 5; ++u) {
+            const int pp = p + u * groups;
+            v[u] = (pp < nparts) ? __ldg(reinterpret_cast<const float4*>(part + ((size_t)pp * D + d) * N) + kq)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+#pragma unroll
+        for (int u = 0; u < 5; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+    }
+    reinterpret_cast<float4*>(sums)[pg * nq + kq] = acc;
+    __syncthreads();
+    float acc_w2 = 0.f;
+    if (threadIdx.x < N) {
+        const int k = threadIdx.x;
+        float s = 0.f;
+        for (int g = 0; g < groups; ++g) s += sums[g * N + k];   // fixed order
+        const float w2d = w2[d];
+        if (k < K) {
+            gW1[(size_t)d * K + k] += scale * w2d * s;
+            acc_w2 = W1[(size_t)d * ldw + k] * s;
+        } else if (k == ones_col) {
+            gb1[d] += scale * w2d * s;
+            acc_w2 = b1[d] * s;
+        }
+    }
+    if (threadIdx.x < 256) {
         acc_w2 = warp_sum(acc_w2);
-        if ((kl & 31) == 0) red[kl >> 5] = acc_w2;
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc_w2;
     }
     __syncthreads();
-    if (threadIdx.x == 0) gw2[d] += scale * (red[0] + red[1] + red[2] + red[3]);
+    if (threadIdx.x == 0)
+        gw2[d] += scale * (((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7])));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -613,7 +643,7 @@ int grapes_sampler_l1_bwd_tc(grapes_ctx* ctx, const float* Y_hi, const float* Y_
     k_l1_bwd_tc<<<blocks, TC_THREADS, smem_bytes, s>>>(my_hi, my_lo, n_dev, cap_n, NH, NB, stages, maskT, D, dz,
                                                        ctx->partials, g_tc_debug);
     grapes_count_launches(1);
-    k_l1_bwd_finalize<<<D, 128 * FIN_GROUPS, 0, s>>>(ctx->partials, blocks, D, N, K, W1, ldw, b1, w2, ones_col, scale, gW1, gb1, gw2);
+    k_l1_bwd_finalize<<<D, FIN_THREADS, 0, s>>>(ctx->partials, blocks, D, N, K, W1, ldw, b1, w2, ones_col, scale, gW1, gb1, gw2);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;

@@ -3,18 +3,47 @@
 // (/root/reference/modules/utils.py:13-71) and the deterministic top-k of the mini-batch evaluator
 // (/root/reference/eval.py:126-130), without the per-hop D2H of the mask (utils.py:60).
 //
-// The k-th largest key is found by an MSB-first radix select on order-preserving uint32 keys;
-// warps build digit histograms with match-any aggregation.  Ties at the threshold go to the
-// LOWEST candidate index (torch.topk leaves ties unspecified; the oracle uses the same rule).
+// Two kernels:
+//   k_logits_keys (GPU-wide)   layer-2 aggregation of the sampler net -> logits (main.py:210-213); for every
+//                 candidate the probability, Gumbel noise and perturbed key (utils.py:37-42) as an
+//                 order-preserving uint32, the log-probability / gradient of the UNSELECTED outcome, entropy
+//                 statistics (per-block partials, combined later in a fixed order), and a 2048-bucket histogram
+//                 of a monotone coarse image of the key (uniform 1/32-wide buckets on [-32, 32)).
+//   k_select      (one 8-CTA cluster)  exact k-th largest key: the bucket holding the threshold comes from the
+//                 histogram, its (few) members are gathered into CTA 0's shared memory through DSMEM and ranked
+//                 exactly on the composite (key, lowest index first); every CTA then marks its selected items,
+//                 fixes their log-probability / gradient, and writes them in ascending order.  If the bucket is too
+//                 crowded (massive ties) an MSB-first radix select on the 64-bit composite finds the same threshold.
+// Ties at the threshold go to the LOWEST candidate index (torch.topk leaves ties unspecified; the oracle uses
+// the same rule).  Integer counting only -> the selected set does not depend on scheduling.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+namespace cg = cooperative_groups;
 
 #define SEL_THREADS 1024
 #define SEL_WARPS (SEL_THREADS / 32)
+#define SEL_CTAS 8
+#define SEL_BUCKETS 2048
+#define SEL_MEMBER_CAP 2048
+#define SEL_STAT_FLOATS 8            // per-block partials of k_logits_keys: min p, max p, sum e, sum e^2, sum lp, sum dl
 
 __device__ __forceinline__ uint32_t float_to_ordered(float f) {
     if (f != f) return 0u;                                   // NaN ranks lowest
     const uint32_t u = __float_as_uint(f);
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+// monotone non-decreasing coarse image of a key: uniform buckets of width 1/32 on [-32, 32), clamped
+__device__ __forceinline__ int key_bucket(uint32_t ukey) {
+    if (ukey == 0u) return 0;                                // NaN
+    const float x = (ordered_to_float(ukey) + 32.0f) * 32.0f;
+    return (int)fminf(fmaxf(x, 0.f), (float)(SEL_BUCKETS - 1));
+}
+__device__ __forceinline__ unsigned long long composite(uint32_t ukey, int idx) {
+    return ((unsigned long long)ukey << 32) | (unsigned long long)(0xffffffffu - (uint32_t)idx);
 }
 
 // Philox4x32-10 (Salmon et al. 2011): counter-based, one call = 4 uniforms
@@ -46,13 +75,13 @@ __device__ __forceinline__ float entropy_bits(float p) {
     return (e != e) ? 0.f : e;                                // NaN entropy -> 0 (utils.py:52-54)
 }
 
-template <typename T, typename Op>
+template <typename T, typename Op, int WARPS>
 __device__ __forceinline__ T block_reduce(T v, T* smem, Op op, T identity) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(GRAPES_FULL_MASK, v, o));
     if (lane_id() == 0) smem[threadIdx.x >> 5] = v;
     __syncthreads();
-    T r = (threadIdx.x < SEL_WARPS) ? smem[threadIdx.x] : identity;
+    T r = (threadIdx.x < WARPS) ? smem[threadIdx.x] : identity;
     if (threadIdx.x < 32) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) r = op(r, __shfl_xor_sync(GRAPES_FULL_MASK, r, o));
@@ -67,57 +96,66 @@ struct OpAdd { __device__ float operator()(float a, float b) const { return a + 
 struct OpMin { __device__ float operator()(float a, float b) const { return fminf(a, b); } };
 struct OpMax { __device__ float operator()(float a, float b) const { return fmaxf(a, b); } };
 
-// mode: GRAPES_NOISE_*
-//
-// One thread-block CLUSTER of SEL_CTAS CTAs x 1024 threads (distributed shared memory): every CTA
-// scans a strided share of the candidates, digit histograms are merged into CTA 0's shared memory
-// with DSMEM atomics, CTA 0 picks the digit and every CTA reads the running prefix back through
-// DSMEM.  Integer atomics only -> the result does not depend on scheduling.
-#include <cooperative_groups.h>
-namespace cg = cooperative_groups;
-
-#define SEL_CTAS 8
-
-struct SelShared {
-    int hist[256];                 // CTA 0: cluster-wide digit histogram of the current pass
-    uint32_t prefix;               // CTA 0: bits of the threshold key fixed so far
-    int kr;                        // CTA 0: rank still to be resolved inside the current prefix
-    float part[SEL_CTAS][8];       // CTA 0: per-CTA partial reductions (min, max, esum, evar, lp, dl)
-    long long counts[SEL_CTAS];    // CTA 0: per-CTA (n_eq << 32 | n_gt) of the final pass
-};
-
-__global__ void __cluster_dims__(SEL_CTAS, 1, 1) __launch_bounds__(SEL_THREADS) k_select(
-    const float* __restrict__ logits_all, const int* __restrict__ nb_local, const int* __restrict__ nb_nodes,
-    const int* __restrict__ c_dev, int cap_c, int k, int mode, const float* __restrict__ noise,
-    unsigned long long* rng_state, uint32_t* __restrict__ ukeys, float* __restrict__ keys_out,
-    int* __restrict__ sampled_out, int sampled_offset, int* __restrict__ s_dev, int* __restrict__ total_dev,
-    uint8_t* __restrict__ mask_out, float* __restrict__ log_prob, float* tot_log_prob, float* __restrict__ stats,
-    float* __restrict__ dl_all, float* sum_dl, uint32_t* bm_mark) {
-    cg::cluster_group cluster = cg::this_cluster();
-    const int rank = (int)cluster.block_rank();
-    __shared__ SelShared sh;
-    __shared__ int s_whist[SEL_WARPS / 4][256];      // 8 sub-histograms per CTA (4 warps share one)
-    __shared__ float s_red[SEL_WARPS];
-    __shared__ long long s_scan[SEL_WARPS + 2];
-    SelShared* sh0 = cluster.map_shared_rank(&sh, 0);
-    const int c = min(*c_dev, cap_c);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int gtid = rank * SEL_THREADS + tid, gthreads = SEL_CTAS * SEL_THREADS;
-    const bool take_all = (k >= c);                       // utils.py:31-33: no noise is drawn
+// ---------------------------------------------------------------------------------------
+// k_logits_keys: one thread per frontier row j.
+//   aggregated mode (in_off != nullptr):  logit[j] = dinv[j]^2 z[j] + sum_s dinv[s] dinv[j] z[s] + bias
+//                                         (layer 2 of the sampler GCN at width 1; z may come as `nparts` partials)
+//   direct mode     (in_off == nullptr):  logit[j] = z[j]
+//   i = nb_index[j] (candidate index, -1 = not a candidate; nullptr = identity).  For candidates:
+//   lg_c[i] = logit, ukeys[i] = ordered(key), keys_out[i] = key, bucket histogram, statistics of p = sigmoid(logit),
+//   log_prob[i] / dl_all[j] / mask_out[i] of the UNSELECTED outcome (selected outcome when k >= c: everything is kept).
+// stat_part[block][8] = (min p, max p, sum entropy, sum entropy^2, sum log_prob, sum dl) of the block's candidates.
+// ---------------------------------------------------------------------------------------
+#define KEYS_THREADS 256
+__global__ void __launch_bounds__(KEYS_THREADS) k_logits_keys(
+    const float* __restrict__ z, int nparts, int part_stride, const int* __restrict__ n_dev, int cap_n,
+    const int* __restrict__ in_off, const int* __restrict__ in_src, const float* __restrict__ dinv,
+    const float* __restrict__ bias, const int* __restrict__ nb_index, const int* __restrict__ c_dev, int k, int mode,
+    const float* __restrict__ noise, const unsigned long long* __restrict__ rng_state,
+    float* __restrict__ logits_all, float* __restrict__ lg_c, uint32_t* __restrict__ ukeys,
+    float* __restrict__ keys_out, float* __restrict__ log_prob, float* __restrict__ dl_all,
+    uint8_t* __restrict__ mask_out, float* __restrict__ stat_part, int* bucket_hist) {
+    __shared__ float s_red[KEYS_THREADS / 32];
+    const int n = min(*n_dev, cap_n);
+    const bool take_all = (k >= min(*c_dev, cap_n));          // utils.py:31-33: no noise is drawn
     unsigned long long seed = 0ull, offset = 0ull;
     if (mode == GRAPES_NOISE_PHILOX) { seed = rng_state[0]; offset = rng_state[1]; }
-    __shared__ float s_bcast_f;
-    __shared__ uint32_t s_bcast_u;
-    __shared__ long long s_bcast_ll;
-    if (tid < 256) sh.hist[tid] = 0;
-    if (tid == 0) { sh.prefix = 0u; sh.kr = k; }
-    cluster.sync();                                        // every CTA of the cluster is running: DSMEM is safe
-
-    // ---- pass 0: keys + probability statistics (coalesced, strided over the whole cluster) ----
-    float pmin = INFINITY, pmax = -INFINITY, esum = 0.f;
-    for (int i = gtid; i < c; i += gthreads) {
-        const float l = logits_all[nb_local ? nb_local[i] : i];
-        const float p = sigmoidf_(l);
+    const float b = bias ? bias[0] : 0.f;
+    float pmin = INFINITY, pmax = -INFINITY, esum = 0.f, esq = 0.f, lpsum = 0.f, dlsum = 0.f;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        float logit;
+        if (in_off) {
+            const float dj = dinv[j];
+            float zj = z[j];
+            for (int t = 1; t < nparts; ++t) zj += z[(size_t)t * part_stride + j];
+            float a = dj * dj * zj;
+            const int end = in_off[j + 1];
+            for (int p = in_off[j]; p < end; ++p) {
+                const int sl = in_src[p];
+                float zs = z[sl];
+                for (int t = 1; t < nparts; ++t) zs += z[(size_t)t * part_stride + sl];
+                a = fmaf(dinv[sl] * dj, zs, a);
+            }
+            logit = a + b;
+        } else {
+            logit = z[j];
+        }
+        if (logits_all) logits_all[j] = logit;
+        const int i = nb_index ? nb_index[j] : j;
+        if (i < 0) {
+            if (dl_all) dl_all[j] = 0.f;
+            continue;
+        }
+        lg_c[i] = logit;
+        const float p = sigmoidf_(logit);
+        const float y = take_all ? 1.f : 0.f;
+        const float lp = bern_log_prob(logit, y);
+        const float d = y - p;
+        if (log_prob) log_prob[i] = lp;
+        if (dl_all) dl_all[j] = d;
+        if (mask_out) mask_out[i] = take_all ? 1 : 0;
+        lpsum += lp; dlsum += d;
+        if (take_all) continue;
         float key;
         if (mode == GRAPES_NOISE_KEYS) key = noise[i];
         else if (mode == GRAPES_NOISE_NONE_TOPK_PROBS) key = p;               // eval.py:126
@@ -131,429 +169,364 @@ __global__ void __cluster_dims__(SEL_CTAS, 1, 1) __launch_bounds__(SEL_THREADS) 
             }
             key = logf(p) + g;                                                // utils.py:42
         }
-        if (!take_all) ukeys[i] = float_to_ordered(key);
+        const uint32_t uk = float_to_ordered(key);
+        ukeys[i] = uk;
         if (keys_out) keys_out[i] = key;
+        atomicAdd(&bucket_hist[key_bucket(uk)], 1);           // integer counts: order independent
         pmin = fminf(pmin, p); pmax = fmaxf(pmax, p);
-        esum += entropy_bits(p);
+        const float e = entropy_bits(p);
+        esum += e; esq = fmaf(e, e, esq);
     }
-    pmin = block_reduce(pmin, s_red, OpMin(), INFINITY);
-    pmax = block_reduce(pmax, s_red, OpMax(), -INFINITY);
-    esum = block_reduce(esum, s_red, OpAdd(), 0.f);
-    if (tid == 0) { sh0->part[rank][0] = pmin; sh0->part[rank][1] = pmax; sh0->part[rank][2] = esum; }
-    cluster.sync();                                        // also publishes ukeys[] to the other CTAs
-    if (tid == 0) {
-        float t = 0.f;
-        for (int r = 0; r < SEL_CTAS; ++r) t += sh0->part[r][2];              // fixed order
-        s_bcast_f = (c > 0) ? t / (float)c : 0.f;
+    pmin = block_reduce<float, OpMin, KEYS_THREADS / 32>(pmin, s_red, OpMin(), INFINITY);
+    pmax = block_reduce<float, OpMax, KEYS_THREADS / 32>(pmax, s_red, OpMax(), -INFINITY);
+    esum = block_reduce<float, OpAdd, KEYS_THREADS / 32>(esum, s_red, OpAdd(), 0.f);
+    esq = block_reduce<float, OpAdd, KEYS_THREADS / 32>(esq, s_red, OpAdd(), 0.f);
+    lpsum = block_reduce<float, OpAdd, KEYS_THREADS / 32>(lpsum, s_red, OpAdd(), 0.f);
+    dlsum = block_reduce<float, OpAdd, KEYS_THREADS / 32>(dlsum, s_red, OpAdd(), 0.f);
+    if (threadIdx.x == 0) {
+        float* sp = stat_part + (size_t)blockIdx.x * SEL_STAT_FLOATS;
+        sp[0] = pmin; sp[1] = pmax; sp[2] = esum; sp[3] = esq; sp[4] = lpsum; sp[5] = dlsum; sp[6] = 0.f; sp[7] = 0.f;
     }
-    __syncthreads();
-    const float emean = s_bcast_f;
-    float evar = 0.f;
-    for (int i = gtid; i < c; i += gthreads) {
-        const float d = entropy_bits(sigmoidf_(logits_all[nb_local ? nb_local[i] : i])) - emean;
-        evar = fmaf(d, d, evar);
-    }
-    evar = block_reduce(evar, s_red, OpAdd(), 0.f);
-    if (tid == 0) sh0->part[rank][3] = evar;
-
-    // ---- radix select of the k-th largest key (MSB first, 8 bits per pass) -------------------
-    uint32_t thr = 0u;
-    int kr = 0;
-    if (!take_all) {
-        for (int shift = 24; shift >= 0; shift -= 8) {
-            for (int b = tid; b < (SEL_WARPS / 4) * 256; b += SEL_THREADS) (&s_whist[0][0])[b] = 0;
-            if (tid == 0) s_bcast_u = sh0->prefix;
-            __syncthreads();
-            const uint32_t prefix = s_bcast_u;
-            const uint32_t himask = (shift == 24) ? 0u : (0xffffffffu << (shift + 8));
-            for (int base = 0; base < c; base += gthreads) {
-                const int i = base + gtid;
-                bool valid = false; uint32_t digit = 0u;
-                if (i < c) {
-                    const uint32_t u = ukeys[i];
-                    valid = (u & himask) == prefix;
-                    digit = (u >> shift) & 255u;
-                }
-                const unsigned peers = __match_any_sync(GRAPES_FULL_MASK, valid ? digit : 0xffffffffu);
-                if (valid && lane == (__ffs(peers) - 1)) atomicAdd(&s_whist[warp >> 2][digit], __popc(peers));
-            }
-            __syncthreads();
-            if (tid < 256) {
-                int a = 0;
-#pragma unroll
-                for (int w = 0; w < SEL_WARPS / 4; ++w) a += s_whist[w][tid];
-                if (a) atomicAdd(&sh0->hist[tid], a);                          // DSMEM atomic into CTA 0
-            }
-            cluster.sync();
-            if (rank == 0 && warp == 0) {
-                // walk bins from the top; lane l owns bins [255-8l-7 .. 255-8l] (descending order)
-                int mine[8], msum = 0;
-#pragma unroll
-                for (int t = 0; t < 8; ++t) { mine[t] = sh.hist[255 - (lane * 8 + t)]; msum += mine[t]; }
-                const int incl = warp_scan_incl(msum);
-                const int excl = incl - msum;
-                const int krem = sh.kr;
-                const bool here = (excl < krem) && (incl >= krem);
-                __syncwarp();
-                if (here) {
-                    int cum = excl;
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        if (cum + mine[t] >= krem) {
-                            sh.prefix = prefix | ((uint32_t)(255 - (lane * 8 + t)) << shift);
-                            sh.kr = krem - cum;
-                            break;
-                        }
-                        cum += mine[t];
-                    }
-                }
-                __syncwarp();
-#pragma unroll
-                for (int t = 0; t < 8; ++t) sh.hist[lane * 8 + t] = 0;        // clean for the next pass
-            }
-            cluster.sync();
-        }
-        thr = sh0->prefix;
-        kr = sh0->kr;
-    }
-
-    // ---- ordered selection: CTA r owns a contiguous chunk, each thread a contiguous sub-range ----
-    const int chunk = (c + SEL_CTAS - 1) / SEL_CTAS;
-    const int cb = min(c, rank * chunk), ce = min(c, cb + chunk);
-    const int ipt = (ce - cb + SEL_THREADS - 1) / SEL_THREADS;
-    const int i0 = min(ce, cb + tid * ipt), i1 = min(ce, i0 + ipt);
-    int n_eq = 0, n_gt = 0;
-    if (!take_all) {
-        for (int i = i0; i < i1; ++i) {
-            const uint32_t u = ukeys[i];
-            n_eq += (u == thr);
-            n_gt += (u > thr);
-        }
-    }
-    long long total;
-    const long long packed = ((long long)n_eq << 32) | (long long)n_gt;
-    const long long excl = block_scan_excl<long long>(packed, s_scan, &total);
-    if (tid == 0) sh0->counts[rank] = total;
-    cluster.sync();
-    if (tid == 0) {
-        long long b = 0;
-        for (int r = 0; r < rank; ++r) b += sh0->counts[r];
-        s_bcast_ll = b;
-    }
-    __syncthreads();
-    const long long before = s_bcast_ll;
-    int eq_before = (int)((before + excl) >> 32), gt_before = (int)((before + excl) & 0xffffffffll);
-    float lp_sum = 0.f, dl_sum = 0.f;
-    for (int i = i0; i < i1; ++i) {
-        bool sel;
-        int pos;
-        if (take_all) { sel = true; pos = i; }
-        else {
-            const uint32_t u = ukeys[i];
-            sel = false; pos = 0;
-            if (u > thr) { sel = true; pos = gt_before + min(eq_before, kr); ++gt_before; }
-            else if (u == thr) { if (eq_before < kr) { sel = true; pos = gt_before + eq_before; } ++eq_before; }
-        }
-        const int li = nb_local ? nb_local[i] : i;
-        const float l = logits_all[li];
-        const float y = sel ? 1.f : 0.f;
-        const float lp = bern_log_prob(l, y);
-        if (log_prob) log_prob[i] = lp;
-        lp_sum += lp;
-        const float d = y - sigmoidf_(l);
-        if (dl_all) dl_all[li] = d;
-        dl_sum += d;
-        if (mask_out) mask_out[i] = sel ? 1 : 0;
-        if (sel) {
-            const int g = nb_nodes ? nb_nodes[i] : i;
-            if (sampled_out) sampled_out[sampled_offset + pos] = g;
-            if (bm_mark && nb_nodes) bitmap_set(bm_mark, g);
-        }
-    }
-    lp_sum = block_reduce(lp_sum, s_red, OpAdd(), 0.f);
-    dl_sum = block_reduce(dl_sum, s_red, OpAdd(), 0.f);
-    if (tid == 0) { sh0->part[rank][4] = lp_sum; sh0->part[rank][5] = dl_sum; }
-    cluster.sync();
-    if (rank == 0 && tid == 0) {
-        float mn = INFINITY, mx = -INFINITY, ev = 0.f, lp = 0.f, dl = 0.f;
-        for (int r = 0; r < SEL_CTAS; ++r) {                                   // fixed order -> deterministic
-            mn = fminf(mn, sh.part[r][0]); mx = fmaxf(mx, sh.part[r][1]);
-            ev += sh.part[r][3]; lp += sh.part[r][4]; dl += sh.part[r][5];
-        }
-        const int s = take_all ? c : k;
-        if (s_dev) *s_dev = s;
-        if (total_dev) *total_dev = sampled_offset + s;
-        if (tot_log_prob) *tot_log_prob += lp;
-        if (sum_dl) *sum_dl += dl;
-        if (stats) {
-            if (take_all) { stats[0] = stats[1] = stats[2] = stats[3] = 0.f; }   // reference returns {}
-            else {
-                stats[0] = mn; stats[1] = mx; stats[2] = emean;
-                stats[3] = (c > 1) ? sqrtf(ev / (float)(c - 1)) : 0.f;         // unbiased (utils.py:56)
-            }
-        }
-        if (mode == GRAPES_NOISE_PHILOX && !take_all) rng_state[1] = offset + 1ull;
-    }
-    cluster.sync();                                        // keep CTA 0's shared memory alive until all are done
 }
 
 // ---------------------------------------------------------------------------------------
-// k_select_reg: the same selection with every candidate key held ON CHIP (shared memory, blocked layout: CTA r owns
-// a contiguous chunk, thread t a contiguous sub-range of <= SEL_MAX_IPT items, stored column-wise so accesses are
-// conflict free), so keys are computed and read from global memory exactly once; 3 radix passes of 11 / 11 / 10
-// bits.  Used when c <= 8 * 1024 * SEL_MAX_IPT, else k_select (keys in global memory).
+// k_select
 // ---------------------------------------------------------------------------------------
-#define SEL_MAX_IPT 24
-#define SEL_BINS 2048
+// phase time stamps of the last k_select launch (globaltimer ns, CTA 0 thread 0) -- scripts/bench_select.py
+__device__ unsigned long long g_sel_stamps[16];
+__device__ __forceinline__ void sel_stamp(int slot, int rank) {
+    if (threadIdx.x == 0 && rank == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_sel_stamps[slot] = t;
+    }
+}
 
-struct SelSharedR {
-    int hist[SEL_BINS];
-    uint32_t prefix;
-    int kr;
-    float part[SEL_CTAS][8];
-    long long counts[SEL_CTAS];
+struct SelShared {
+    // CTA 0 (written by every CTA through DSMEM)
+    unsigned long long member[SEL_MEMBER_CAP];   // composites of the threshold bucket's members
+    int m_count;
+    unsigned long long thr_comp;                 // selected <=> composite >= thr_comp
+    int fallback;
+    int hist[256];                               // fallback radix pass: cluster-wide digit histogram
+    unsigned long long prefix;                   // fallback: composite bits fixed so far
+    int kr;                                      // fallback: rank left inside the prefix
+    // every CTA (each CTA publishes its totals to all)
+    int sel_count[SEL_CTAS];
+    float lp_delta[SEL_CTAS], dl_delta[SEL_CTAS];
 };
 
-__global__ void __cluster_dims__(SEL_CTAS, 1, 1) __launch_bounds__(SEL_THREADS, 1) k_select_reg(
-    const float* __restrict__ logits_all, const int* __restrict__ nb_local, const int* __restrict__ nb_nodes,
-    const int* __restrict__ c_dev, int cap_c, int k, int mode, const float* __restrict__ noise,
-    unsigned long long* rng_state, float* __restrict__ keys_out, int* __restrict__ sampled_out, int sampled_offset,
-    int* __restrict__ s_dev, int* __restrict__ total_dev, uint8_t* __restrict__ mask_out, float* __restrict__ log_prob,
-    float* tot_log_prob, float* __restrict__ stats, float* __restrict__ dl_all, float* sum_dl, uint32_t* bm_mark) {
+__global__ void __cluster_dims__(SEL_CTAS, 1, 1) __launch_bounds__(SEL_THREADS, 1) k_select(
+    const uint32_t* __restrict__ ukeys, const float* __restrict__ lg_c, const int* __restrict__ nb_local,
+    const int* __restrict__ nb_nodes, const int* __restrict__ c_dev, int cap_c, int k, int mode,
+    unsigned long long* rng_state, const float* __restrict__ stat_part, int nstat, int* bucket_hist,
+    int* __restrict__ sampled_out, int sampled_offset, int* __restrict__ s_dev, int* __restrict__ total_dev,
+    uint8_t* __restrict__ mask_out, float* __restrict__ log_prob, float* tot_log_prob, float* __restrict__ stats,
+    float* __restrict__ dl_all, float* sum_dl, uint32_t* bm_mark) {
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
-    __shared__ SelSharedR sh;
-    __shared__ int s_lhist[SEL_BINS];
+    __shared__ SelShared sh;
     __shared__ float s_red[SEL_WARPS];
     __shared__ long long s_scan[SEL_WARPS + 2];
-    __shared__ uint32_t s_bcast_u;
-    __shared__ long long s_bcast_ll;
-    SelSharedR* sh0 = cluster.map_shared_rank(&sh, 0);
+    __shared__ int s_wcnt[SEL_THREADS];              // per (round, warp) selected counts of one super-round
+    __shared__ int s_lhist[256];                     // fallback: this CTA's digit histogram
+    __shared__ int s_bucket, s_above;
+    __shared__ unsigned long long s_thr;
+    __shared__ int s_fb;
+    SelShared* sh0 = cluster.map_shared_rank(&sh, 0);
     const int c = min(*c_dev, cap_c);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool take_all = (k >= c);
-    unsigned long long seed = 0ull, offset = 0ull;
-    if (mode == GRAPES_NOISE_PHILOX) { seed = rng_state[0]; offset = rng_state[1]; }
-    for (int b = tid; b < SEL_BINS; b += SEL_THREADS) sh.hist[b] = 0;
-    if (tid == 0) { sh.prefix = 0u; sh.kr = k; }
-    cluster.sync();
-
     const int chunk = (c + SEL_CTAS - 1) / SEL_CTAS;
     const int cb = min(c, rank * chunk), ce = min(c, cb + chunk);
-    const int ipt = (chunk + SEL_THREADS - 1) / SEL_THREADS;       // <= SEL_MAX_IPT (checked by the launcher)
-    const int i0 = min(ce, cb + tid * ipt);
-    const int cnt = max(0, min(ce, i0 + ipt) - i0);
+    const int len = ce - cb;                         // CTA r owns the contiguous candidates [cb, ce)
+    sel_stamp(0, rank);
+    if (tid == 0) { sh.m_count = 0; sh.fallback = 0; sh.kr = k; sh.prefix = 0ull; sh.thr_comp = 0ull; }
+    if (tid < 256) sh.hist[tid] = 0;
 
-    // ---- pass 0: load once, keys + statistics ----
-    extern __shared__ uint32_t s_uk[];                             // [ipt][1024] keys, then [ipt][1024] logits
-#define UK(j) s_uk[(j) * SEL_THREADS + tid]
-    float* s_lg = reinterpret_cast<float*>(s_uk + ipt * SEL_THREADS);
-#define LG(j) s_lg[(j) * SEL_THREADS + tid]
-    // gather the logits first, 8 independent loads in flight per thread (the index -> logit chain is latency bound)
-    for (int j0 = 0; j0 < cnt; j0 += 8) {
-        int li[8];
+    unsigned long long thr_comp = 0ull;              // take_all: everything is selected
+    if (!take_all) {
+        // ---- 1. threshold bucket from the global histogram (every CTA, redundantly) ----
+        const int b0 = SEL_BUCKETS - 1 - 2 * tid;    // thread t owns buckets b0, b0-1 (descending order)
+        const int h0 = bucket_hist[b0], h1 = bucket_hist[b0 - 1];
+        long long total;
+        const int e0 = (int)block_scan_excl<long long>((long long)(h0 + h1), s_scan, &total);
+        const int e1 = e0 + h0, e2 = e1 + h1;
+        if (e0 < k && e1 >= k) { s_bucket = b0; s_above = e0; }
+        else if (e1 < k && e2 >= k) { s_bucket = b0 - 1; s_above = e1; }
+        cluster.sync();                              // all CTAs run (DSMEM is safe) and have read the histogram
+        sel_stamp(1, rank);
+        if (rank == 0) { bucket_hist[b0] = 0; bucket_hist[b0 - 1] = 0; }      // clean for the next launch
+        const int bucket = s_bucket, above = s_above;
+        // ---- 2. gather the bucket's members into CTA 0 ----
+        for (int q0 = 0; q0 < len; q0 += 8 * SEL_THREADS) {
+            uint32_t v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) li[u] = (j0 + u < cnt) ? (nb_local ? nb_local[i0 + j0 + u] : i0 + j0 + u) : 0;
-        float lv[8];
+            for (int u = 0; u < 8; ++u) { const int q = q0 + u * SEL_THREADS + tid; v[u] = (q < len) ? ukeys[cb + q] : 0u; }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) lv[u] = (j0 + u < cnt) ? logits_all[li[u]] : 0.f;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) if (j0 + u < cnt) LG(j0 + u) = lv[u];
-    }
-    float pmin = INFINITY, pmax = -INFINITY, esum = 0.f, esq = 0.f;
-    for (int j = 0; j < cnt; ++j) {
-        {
-            const int i = i0 + j;
-            const float l = LG(j);
-            const float p = sigmoidf_(l);
-            float key;
-            if (mode == GRAPES_NOISE_KEYS) key = noise[i];
-            else if (mode == GRAPES_NOISE_NONE_TOPK_PROBS) key = p;
+            for (int u = 0; u < 8; ++u) {
+                const int q = q0 + u * SEL_THREADS + tid;
+                if (q < len && key_bucket(v[u]) == bucket) {
+                    const int pos = atomicAdd(&sh0->m_count, 1);
+                    if (pos < SEL_MEMBER_CAP) sh0->member[pos] = composite(v[u], cb + q);
+                }
+            }
+        }
+        cluster.sync();
+        sel_stamp(2, rank);
+        // ---- 3. CTA 0: exact rank inside the bucket on the composite (key desc, index asc) ----
+        if (rank == 0) {
+            const int M = sh.m_count;
+            const int want = k - above - 1;          // number of members that must rank above the threshold member
+            if (M > SEL_MEMBER_CAP) { if (tid == 0) sh.fallback = 1; }
             else {
-                float g;
-                if (mode == GRAPES_NOISE_GUMBEL) g = noise[i];
-                else {
-                    float u = (mode == GRAPES_NOISE_UNIFORM) ? noise[i] : philox_uniform(seed, offset, i);
-                    if (mode == GRAPES_NOISE_PHILOX) u = u * ((1.0f - 1.1920929e-07f) - 1.17549435e-38f) + 1.17549435e-38f;
-                    g = -logf(-logf(u));
+                for (int t = tid; t < M; t += SEL_THREADS) {
+                    const unsigned long long mine = sh.member[t];
+                    int r = 0;
+                    for (int o = 0; o < M; ++o) r += (sh.member[o] > mine);
+                    if (r == want) sh.thr_comp = mine;
                 }
-                key = logf(p) + g;
             }
-            UK(j) = float_to_ordered(key);
-            if (keys_out) keys_out[i] = key;
-            pmin = fminf(pmin, p); pmax = fmaxf(pmax, p);
-            const float e = entropy_bits(p);
-            esum += e; esq = fmaf(e, e, esq);
         }
-    }
-    pmin = block_reduce(pmin, s_red, OpMin(), INFINITY);
-    pmax = block_reduce(pmax, s_red, OpMax(), -INFINITY);
-    esum = block_reduce(esum, s_red, OpAdd(), 0.f);
-    esq = block_reduce(esq, s_red, OpAdd(), 0.f);
-    if (tid == 0) { sh0->part[rank][0] = pmin; sh0->part[rank][1] = pmax; sh0->part[rank][2] = esum; sh0->part[rank][3] = esq; }
-
-    // ---- radix select: 11 + 11 + 10 bits ----
-    uint32_t thr = 0u;
-    int kr = 0;
-    if (!take_all) {
-        const int shifts[3] = {21, 10, 0};
-        const int nbits[3] = {11, 11, 10};
-#pragma unroll
-        for (int ps = 0; ps < 3; ++ps) {
-            const int shift = shifts[ps];
-            const uint32_t dmask = (1u << nbits[ps]) - 1u;
-            for (int b = tid; b < SEL_BINS; b += SEL_THREADS) s_lhist[b] = 0;
-            if (tid == 0) s_bcast_u = sh0->prefix;
-            __syncthreads();
-            const uint32_t prefix = s_bcast_u;
-            const uint32_t himask = (ps == 0) ? 0u : (0xffffffffu << (shift + nbits[ps]));
-            for (int j = 0; j < cnt; ++j) {
-                const uint32_t u = UK(j);
-                if ((u & himask) == prefix) atomicAdd(&s_lhist[(u >> shift) & dmask], 1);
-            }
-            __syncthreads();
-            for (int b = tid; b < SEL_BINS; b += SEL_THREADS) {
-                const int a = s_lhist[b];
-                if (a) atomicAdd(&sh0->hist[b], a);
-            }
-            cluster.sync();
-            if (rank == 0 && warp == 0) {
-                // lane l owns bins [2047-64l-63 .. 2047-64l] in descending order
-                int msum = 0;
-                for (int t = 0; t < 64; ++t) msum += sh.hist[SEL_BINS - 1 - (lane * 64 + t)];
-                const int incl = warp_scan_incl(msum);
-                const int excl = incl - msum;
-                const int krem = sh.kr;
-                if (excl < krem && incl >= krem) {
-                    int cum = excl;
-                    for (int t = 0; t < 64; ++t) {
-                        const int bin = SEL_BINS - 1 - (lane * 64 + t);
-                        const int h = sh.hist[bin];
-                        if (cum + h >= krem) { sh.prefix = prefix | ((uint32_t)bin << shift); sh.kr = krem - cum; break; }
-                        cum += h;
+        cluster.sync();
+        sel_stamp(3, rank);
+        if (tid == 0) { s_thr = sh0->thr_comp; s_fb = sh0->fallback; }
+        __syncthreads();
+        thr_comp = s_thr;
+        if (s_fb) {
+            // ---- fallback (crowded bucket, e.g. massive ties): MSB-first radix select on the 64-bit composite,
+            //      8 passes of 8 bits over all candidates, histograms merged into CTA 0 with DSMEM atomics ----
+            for (int shift = 56; shift >= 0; shift -= 8) {
+                __syncthreads();
+                if (tid < 256) s_lhist[tid] = 0;
+                if (tid == 0) s_thr = sh0->prefix;
+                __syncthreads();
+                const unsigned long long prefix = s_thr;
+                const unsigned long long himask = (shift == 56) ? 0ull : (~0ull << (shift + 8));
+                for (int q = tid; q < len; q += SEL_THREADS) {
+                    const unsigned long long cm = composite(ukeys[cb + q], cb + q);
+                    if ((cm & himask) == prefix) atomicAdd(&s_lhist[(int)((cm >> shift) & 255ull)], 1);
+                }
+                __syncthreads();
+                if (tid < 256 && s_lhist[tid]) atomicAdd(&sh0->hist[tid], s_lhist[tid]);
+                cluster.sync();
+                if (rank == 0 && tid == 0) {
+                    int cum = 0;
+                    const int krem = sh.kr;
+                    for (int bin = 255; bin >= 0; --bin) {
+                        const int hcount = sh.hist[bin];
+                        if (cum + hcount >= krem) {
+                            sh.prefix = prefix | ((unsigned long long)bin << shift);
+                            sh.kr = krem - cum;
+                            break;
+                        }
+                        cum += hcount;
                     }
+                    for (int bin = 0; bin < 256; ++bin) sh.hist[bin] = 0;
                 }
-                __syncwarp();
-                for (int t = 0; t < 64; ++t) sh.hist[lane * 64 + t] = 0;
+                cluster.sync();
             }
-            cluster.sync();
+            if (tid == 0) s_thr = sh0->prefix;
+            __syncthreads();
+            thr_comp = s_thr;                        // the k-th largest composite itself (composites are distinct)
         }
-        thr = sh0->prefix;
-        kr = sh0->kr;
+    } else {
+        cluster.sync();                              // every CTA runs before the first remote access below
     }
 
-    // ---- ordered selection straight from registers ----
-    int n_eq = 0, n_gt = 0;
+    // ---- 4. count the selected items of this CTA; fix their log-prob / gradient (k_logits_keys wrote the
+    //         unselected outcome) ----
+    int my_cnt = 0;
+    float lp_delta = 0.f, dl_delta = 0.f;
     if (!take_all) {
-        for (int j = 0; j < cnt; ++j) { const uint32_t u = UK(j); n_eq += (u == thr); n_gt += (u > thr); }
+        for (int q0 = 0; q0 < len; q0 += 8 * SEL_THREADS) {
+            uint32_t v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int q = q0 + u * SEL_THREADS + tid; v[u] = (q < len) ? ukeys[cb + q] : 0u; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int q = q0 + u * SEL_THREADS + tid;
+                if (q < len && composite(v[u], cb + q) >= thr_comp) {
+                    const int i = cb + q;
+                    ++my_cnt;
+                    const float l = lg_c[i];
+                    const float lp1 = bern_log_prob(l, 1.f), lp0 = bern_log_prob(l, 0.f);
+                    if (log_prob) log_prob[i] = lp1;
+                    if (dl_all) dl_all[nb_local ? nb_local[i] : i] = 1.f - sigmoidf_(l);
+                    if (mask_out) mask_out[i] = 1;
+                    lp_delta += lp1 - lp0;
+                    dl_delta += 1.f;
+                }
+            }
+        }
     }
     long long total;
-    const long long packed = ((long long)n_eq << 32) | (long long)n_gt;
-    const long long excl = block_scan_excl<long long>(packed, s_scan, &total);
-    if (tid == 0) sh0->counts[rank] = total;
-    cluster.sync();
-    if (tid == 0) {
-        long long b = 0;
-        for (int r = 0; r < rank; ++r) b += sh0->counts[r];
-        s_bcast_ll = b;
+    block_scan_excl<long long>((long long)my_cnt, s_scan, &total);
+    lp_delta = block_reduce<float, OpAdd, SEL_WARPS>(lp_delta, s_red, OpAdd(), 0.f);
+    dl_delta = block_reduce<float, OpAdd, SEL_WARPS>(dl_delta, s_red, OpAdd(), 0.f);
+    if (tid < SEL_CTAS) {                            // publish to every CTA: after the barrier each reads only its own copy
+        SelShared* dst = cluster.map_shared_rank(&sh, tid);
+        dst->sel_count[rank] = take_all ? len : (int)total;
+        dst->lp_delta[rank] = lp_delta;
+        dst->dl_delta[rank] = dl_delta;
     }
-    __syncthreads();
-    const long long before = s_bcast_ll;
-    int eq_before = (int)((before + excl) >> 32), gt_before = (int)((before + excl) & 0xffffffffll);
-    float lp_sum = 0.f, dl_sum = 0.f;
-    for (int j = 0; j < cnt; ++j) {
-        {
-            const int i = i0 + j;
-            bool sel; int pos;
-            if (take_all) { sel = true; pos = i; }
-            else {
-                const uint32_t u = UK(j);
-                sel = false; pos = 0;
-                if (u > thr) { sel = true; pos = gt_before + min(eq_before, kr); ++gt_before; }
-                else if (u == thr) { if (eq_before < kr) { sel = true; pos = gt_before + eq_before; } ++eq_before; }
-            }
-            const float l = LG(j);
-            const float y = sel ? 1.f : 0.f;
-            const float lp = bern_log_prob(l, y);
-            if (log_prob) log_prob[i] = lp;
-            lp_sum += lp;
-            const float d = y - sigmoidf_(l);
-            if (dl_all) dl_all[nb_local ? nb_local[i] : i] = d;
-            dl_sum += d;
-            if (mask_out) mask_out[i] = sel ? 1 : 0;
+    cluster.sync();                                  // after this nobody touches remote shared memory
+    sel_stamp(4, rank);
+    int carry = 0;                                   // selected items in lower-ranked CTAs
+    for (int r = 0; r < rank; ++r) carry += sh.sel_count[r];
+
+    // ---- 5. ordered output: position = #selected with a smaller index (ballot per 32 items + one scan per
+    //         super-round of 32 x 1024 items) ----
+    for (int sr = 0; sr < len; sr += 32 * SEL_THREADS) {
+        const int rounds = min(32, (len - sr + SEL_THREADS - 1) / SEL_THREADS);
+        for (int u = 0; u < rounds; ++u) {           // pass a: flags -> per (round, warp) counts
+            const int q = sr + u * SEL_THREADS + tid;
+            bool sel = false;
+            if (q < len) sel = take_all || composite(ukeys[cb + q], cb + q) >= thr_comp;
+            const uint32_t bal = __ballot_sync(GRAPES_FULL_MASK, sel);
+            if (lane == 0) s_wcnt[u * 32 + warp] = __popc(bal);
+        }
+        if (tid >= rounds * 32) s_wcnt[tid] = 0;
+        __syncthreads();
+        long long tot2;
+        const int base = (int)block_scan_excl<long long>((long long)s_wcnt[tid], s_scan, &tot2);
+        s_wcnt[tid] = base;                          // exclusive prefix of (round, warp) in index order
+        __syncthreads();
+        for (int u = 0; u < rounds; ++u) {           // pass b: positions
+            const int q = sr + u * SEL_THREADS + tid;
+            bool sel = false;
+            if (q < len) sel = take_all || composite(ukeys[cb + q], cb + q) >= thr_comp;
+            const uint32_t bal = __ballot_sync(GRAPES_FULL_MASK, sel);
             if (sel) {
+                const int i = cb + q;
+                const int pos = carry + s_wcnt[u * 32 + warp] + __popc(bal & ((1u << lane) - 1u));
                 const int g = nb_nodes ? nb_nodes[i] : i;
                 if (sampled_out) sampled_out[sampled_offset + pos] = g;
                 if (bm_mark && nb_nodes) bitmap_set(bm_mark, g);
             }
         }
+        carry += (int)tot2;
+        __syncthreads();
     }
-    lp_sum = block_reduce(lp_sum, s_red, OpAdd(), 0.f);
-    dl_sum = block_reduce(dl_sum, s_red, OpAdd(), 0.f);
-    if (tid == 0) { sh0->part[rank][4] = lp_sum; sh0->part[rank][5] = dl_sum; }
-    cluster.sync();
-    if (rank == 0 && tid == 0) {
-        float mn = INFINITY, mx = -INFINITY, lp = 0.f, dl = 0.f;
-        double es = 0.0, eq = 0.0;
-        for (int r = 0; r < SEL_CTAS; ++r) {
-            mn = fminf(mn, sh.part[r][0]); mx = fmaxf(mx, sh.part[r][1]);
-            es += (double)sh.part[r][2]; eq += (double)sh.part[r][3]; lp += sh.part[r][4]; dl += sh.part[r][5];
+    sel_stamp(5, rank);
+    if (rank != 0) return;
+    if (tid < 32) {
+        // statistics / sums: per-block partials of k_logits_keys combined in a fixed order
+        float mn = INFINITY, mx = -INFINITY;
+        double es = 0.0, eq = 0.0, lp = 0.0, dl = 0.0;
+        for (int bq = tid; bq < nstat; bq += 32) {
+            const float* p = stat_part + (size_t)bq * SEL_STAT_FLOATS;
+            mn = fminf(mn, p[0]); mx = fmaxf(mx, p[1]); es += (double)p[2]; eq += (double)p[3];
+            lp += (double)p[4]; dl += (double)p[5];
         }
-        const int s = take_all ? c : k;
-        if (s_dev) *s_dev = s;
-        if (total_dev) *total_dev = sampled_offset + s;
-        if (tot_log_prob) *tot_log_prob += lp;
-        if (sum_dl) *sum_dl += dl;
-        if (stats) {
-            if (take_all) { stats[0] = stats[1] = stats[2] = stats[3] = 0.f; }
-            else {
-                const double mean = (c > 0) ? es / (double)c : 0.0;
-                const double var = (c > 1) ? fmax(0.0, (eq - (double)c * mean * mean) / (double)(c - 1)) : 0.0;
-                stats[0] = mn; stats[1] = mx; stats[2] = (float)mean; stats[3] = (float)sqrt(var);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(GRAPES_FULL_MASK, mn, o));
+            mx = fmaxf(mx, __shfl_xor_sync(GRAPES_FULL_MASK, mx, o));
+            es += __shfl_xor_sync(GRAPES_FULL_MASK, es, o);
+            eq += __shfl_xor_sync(GRAPES_FULL_MASK, eq, o);
+            lp += __shfl_xor_sync(GRAPES_FULL_MASK, lp, o);
+            dl += __shfl_xor_sync(GRAPES_FULL_MASK, dl, o);
+        }
+        if (tid == 0) {
+            for (int r = 0; r < SEL_CTAS; ++r) { lp += (double)sh.lp_delta[r]; dl += (double)sh.dl_delta[r]; }   // fixed order
+            const int s = take_all ? c : k;
+            if (s_dev) *s_dev = s;
+            if (total_dev) *total_dev = sampled_offset + s;
+            if (tot_log_prob) *tot_log_prob += (float)lp;
+            if (sum_dl) *sum_dl += (float)dl;
+            if (stats) {
+                if (take_all) { stats[0] = stats[1] = stats[2] = stats[3] = 0.f; }   // reference returns {}
+                else {
+                    const double mean = (c > 0) ? es / (double)c : 0.0;
+                    const double var = (c > 1) ? fmax(0.0, (eq - (double)c * mean * mean) / (double)(c - 1)) : 0.0;
+                    stats[0] = mn; stats[1] = mx; stats[2] = (float)mean; stats[3] = (float)sqrt(var);   // unbiased (utils.py:56)
+                }
             }
+            if (mode == GRAPES_NOISE_PHILOX && !take_all) rng_state[1] += 1ull;
+            sel_stamp(6, 0);
         }
-        if (mode == GRAPES_NOISE_PHILOX && !take_all) rng_state[1] = offset + 1ull;
     }
-    cluster.sync();
+}
+
+static inline int keys_grid(const grapes_ctx* ctx, int cap_n) {
+    long long b = ((long long)cap_n + KEYS_THREADS - 1) / KEYS_THREADS;
+    const long long cap = (long long)ctx->sm_count * 8;
+    if (b < 1) b = 1;
+    return (int)(b < cap ? b : cap);
 }
 
 extern "C" {
 
-int grapes_select_topk(grapes_ctx* ctx, const float* logits_all, const int* nb_local, const int* nb_nodes,
-                       const int* c_dev, int cap_c, int k, int noise_mode, const float* noise,
-                       unsigned long long* rng_state, uint32_t* ukeys_scratch, float* keys_out, int* sampled_out,
-                       int sampled_offset, int* s_dev, int* total_dev, uint8_t* mask_out, float* log_prob,
-                       float* tot_log_prob, float* stats, float* dl_all, float* sum_dl, uint32_t* bm_mark,
-                       void* stream) {
-    GRAPES_REQUIRE(ctx && logits_all && c_dev && ukeys_scratch, "null argument");
+// debugging aid: copies the 16 phase time stamps (ns) of the last selection launch to the host (synchronises)
+int grapes_debug_select_stamps(int64_t* out16) {
+    unsigned long long h[16];
+    if (cudaMemcpyFromSymbol(h, g_sel_stamps, sizeof(h)) != cudaSuccess) return GRAPES_ERR_CUDA;
+    for (int i = 0; i < 16; ++i) out16[i] = (int64_t)h[i];
+    return GRAPES_OK;
+}
+
+// floats of scratch grapes_select_* needs in `work`: bucket histogram (must be ZERO before the first call; the
+// library leaves it zero again after every call) | per-block statistics | candidate logits
+int64_t grapes_select_work_floats(grapes_ctx* ctx, int cap_c) {
+    if (!ctx) return 0;
+    return (int64_t)SEL_BUCKETS + (int64_t)SEL_STAT_FLOATS * keys_grid(ctx, cap_c) + (int64_t)cap_c + 16;
+}
+
+// Sampler-net layer 2 + keys for one hop (main.py:210-213 + utils.py:37-42), then the selection (utils.py:43-71).
+//   z / nparts / part_stride, in_off / in_src / dinv / bias: as grapes_aggregate_scalar; in_off == NULL means
+//   `z` already holds the per-row logits.  nb_index[j] = candidate index of frontier row j or -1 (NULL: every row is
+//   candidate j).  work: grapes_select_work_floats(cap_n) floats, 16-byte aligned, zero-initialised once.
+int grapes_select_hop(grapes_ctx* ctx, const float* z, int nparts, int part_stride, const int* n_dev, int cap_n,
+                      const int* in_off, const int* in_src, const float* dinv, const float* bias,
+                      const int* nb_index, const int* nb_local, const int* nb_nodes, const int* c_dev, int k,
+                      int noise_mode, const float* noise, unsigned long long* rng_state, float* work,
+                      uint32_t* ukeys_scratch, float* logits_all, float* keys_out, int* sampled_out,
+                      int sampled_offset, int* s_dev, int* total_dev, uint8_t* mask_out, float* log_prob,
+                      float* tot_log_prob, float* stats, float* dl_all, float* sum_dl, uint32_t* bm_mark,
+                      void* stream) {
+    GRAPES_REQUIRE(ctx && z && n_dev && c_dev && work && ukeys_scratch, "null argument");
+    GRAPES_REQUIRE(!in_off || (in_src && dinv), "aggregated mode needs in_src and dinv");
+    GRAPES_REQUIRE(nparts >= 1, "nparts >= 1");
     GRAPES_REQUIRE(k > 0, "num_samples must be positive (utils.py:35)");
     GRAPES_REQUIRE(noise_mode >= 0 && noise_mode <= GRAPES_NOISE_NONE_TOPK_PROBS, "bad noise mode");
     GRAPES_REQUIRE(!(noise_mode == GRAPES_NOISE_GUMBEL || noise_mode == GRAPES_NOISE_UNIFORM ||
                      noise_mode == GRAPES_NOISE_KEYS) || noise, "noise array required");
     GRAPES_REQUIRE(noise_mode != GRAPES_NOISE_PHILOX || rng_state, "rng_state required");
-    if (cap_c <= SEL_CTAS * SEL_THREADS * SEL_MAX_IPT) {
-        const int chunk = (cap_c + SEL_CTAS - 1) / SEL_CTAS;
-        const int ipt = (chunk + SEL_THREADS - 1) / SEL_THREADS;
-        const int smem = 2 * ipt * SEL_THREADS * 4;
-        static int attr = 0;
-        if (smem > attr) {
-            GRAPES_CUDA_OK(cudaFuncSetAttribute(k_select_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            attr = smem;
-        }
-        k_select_reg<<<SEL_CTAS, SEL_THREADS, smem, (cudaStream_t)stream>>>(
-            logits_all, nb_local, nb_nodes, c_dev, cap_c, k, noise_mode, noise, rng_state, keys_out, sampled_out,
-            sampled_offset, s_dev, total_dev, mask_out, log_prob, tot_log_prob, stats, dl_all, sum_dl, bm_mark);
-        grapes_count_launches(1);
-        GRAPES_LAUNCH_OK();
-        return GRAPES_OK;
-    }
-    k_select<<<SEL_CTAS, SEL_THREADS, 0, (cudaStream_t)stream>>>(logits_all, nb_local, nb_nodes, c_dev, cap_c, k, noise_mode,
-                                                          noise, rng_state, ukeys_scratch, keys_out, sampled_out,
-                                                          sampled_offset, s_dev, total_dev, mask_out, log_prob,
-                                                          tot_log_prob, stats, dl_all, sum_dl, bm_mark);
+    GRAPES_REQUIRE((((size_t)work) & 15) == 0, "work must be 16-byte aligned");
+    GRAPES_REQUIRE(!(nb_index && dl_all) || nb_local, "a frontier (nb_index) needs nb_local for the gradient scatter");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nblk = keys_grid(ctx, cap_n);
+    int* bucket_hist = reinterpret_cast<int*>(work);
+    float* stat_part = work + SEL_BUCKETS;
+    float* lg_c = stat_part + (size_t)SEL_STAT_FLOATS * nblk;
+    k_logits_keys<<<nblk, KEYS_THREADS, 0, s>>>(z, nparts, part_stride, n_dev, cap_n, in_off, in_src, dinv, bias,
+                                                nb_index, c_dev, k, noise_mode, noise, rng_state, logits_all, lg_c,
+                                                ukeys_scratch, keys_out, log_prob, dl_all, mask_out, stat_part,
+                                                bucket_hist);
+    grapes_count_launches(1);
+    k_select<<<SEL_CTAS, SEL_THREADS, 0, s>>>(ukeys_scratch, lg_c, nb_local, nb_nodes, c_dev, cap_n, k, noise_mode,
+                                              rng_state, stat_part, nblk, bucket_hist, sampled_out, sampled_offset,
+                                              s_dev, total_dev, mask_out, log_prob, tot_log_prob, stats, dl_all,
+                                              sum_dl, bm_mark);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
+}
+
+// sample_neighborhoods_from_probs on given logits (utils.py:13-71): logits_all[i] is candidate i's logit.
+// Thin form of grapes_select_hop for callers that already hold the logits.
+int grapes_select_topk(grapes_ctx* ctx, const float* logits_all, const int* nb_local, const int* nb_nodes,
+                       const int* c_dev, int cap_c, int k, int noise_mode, const float* noise,
+                       unsigned long long* rng_state, uint32_t* ukeys_scratch, float* work, float* keys_out,
+                       int* sampled_out, int sampled_offset, int* s_dev, int* total_dev, uint8_t* mask_out,
+                       float* log_prob, float* tot_log_prob, float* stats, float* dl_all, float* sum_dl,
+                       uint32_t* bm_mark, void* stream) {
+    GRAPES_REQUIRE(nb_local == nullptr, "grapes_select_topk takes per-candidate logits; use grapes_select_hop for a frontier");
+    return grapes_select_hop(ctx, logits_all, 1, 0, c_dev, cap_c, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                             nb_nodes, c_dev, k, noise_mode, noise, rng_state, work, ukeys_scratch, nullptr, keys_out,
+                             sampled_out, sampled_offset, s_dev, total_dev, mask_out, log_prob, tot_log_prob, stats,
+                             dl_all, sum_dl, bm_mark, stream);
 }
 
 }  // extern "C"

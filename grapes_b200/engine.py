@@ -15,8 +15,10 @@ Differences in *mechanism* (never in results) from the reference loop:
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import math
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -66,6 +68,13 @@ def glorot_(w: torch.Tensor, generator=None):
     w.copy_(cpu.to(w.device))
 
 
+class _Hop:
+    """Workspace of ONE hop.  Every array a later consumer reads (the hop's backward on the side stream, the
+    induced-block slice, the recorder of the tests) is per hop, so nothing is overwritten inside a step and the
+    branches of the step graph only synchronise where data really flows."""
+    CNT = dict(P=0, m=1, n=2, c=3, nnz=4, s=5, blk=6)
+
+
 class GrapesEngine:
     def __init__(self, graph: DeviceGraph, x: torch.Tensor, y: torch.Tensor, *, num_classes: int,
                  batch_size: int, num_samples: int, sampling_hops: int, use_indicators: bool = True,
@@ -73,7 +82,7 @@ class GrapesEngine:
                  log_z_init: float = 0., reg_param: float = 0., random_sampling: bool = False,
                  reinforce_baseline: bool = False, seed: int = 0, cap_edges: Optional[int] = None,
                  cap_nodes: Optional[int] = None, cap_block: Optional[int] = None,
-                 use_tensor_cores: bool = True):
+                 use_tensor_cores: bool = True, multi_stream: bool = True):
         self.g = graph
         self.L = lib()
         dev = graph.device
@@ -107,6 +116,17 @@ class GrapesEngine:
         self.random_sampling, self.reinforce = bool(random_sampling), bool(reinforce_baseline)
         W = graph.num_words
         self.W = W
+        H = self.H
+
+        # ---- streams: main = the caller's current stream; side A carries every hop's backward and the gcn_z
+        # chain, side B the induced-block slices.  Each stream has its own library context (scan / split-K scratch).
+        self.multi_stream = bool(multi_stream)
+        if self.multi_stream:
+            self.side_a, self.side_b = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+            self.ctx_a, self.ctx_b = graph.new_ctx(), graph.new_ctx(1 << 20)
+        else:
+            self.side_a = self.side_b = None
+            self.ctx_a = self.ctx_b = graph.ctx
 
         # ---- capacities -------------------------------------------------------------------
         self.cap_P = self.B + self.k
@@ -127,53 +147,88 @@ class GrapesEngine:
 
         i32 = dict(dtype=torch.int32, device=dev)
         f32 = dict(dtype=torch.float32, device=dev)
-        u32 = dict(dtype=torch.int32, device=dev)     # bitmaps are stored as int32 words
         z = torch.zeros
         e = torch.empty
-        # bitmaps
-        # one pool so a hop needs ONE memset (prev[cur] is adjacent to batch) and the step start ONE (all | ind rows)
-        self.bm_pool = z((4 + max(self.num_ind, 1)) * W, **u32)
-        self.bm_prev = [self.bm_pool[0:W], self.bm_pool[2 * W:3 * W]]
-        self.bm_batch = self.bm_pool[W:2 * W]
-        self.bm_all = self.bm_pool[3 * W:4 * W]
-        self.bm_ind = self.bm_pool[4 * W:].view(max(self.num_ind, 1), W)
+        cap_m, cap_n, cap_P = self.cap_m, self.cap_n, self.cap_P
+        D, C = self.D, self.C
+
+        # ---- parameters (flat), gradients, Adam state -------------------------------------
+        self.net_c = _Net(0, F, D, C)
+        self.net_gf = _Net(self.net_c.end, self.Fp, D, 1)
+        self.net_z = _Net(self.net_gf.end, F, D, 1)
+        n_par = self.net_z.end
+        self.n_par = n_par
+
+        # ---- ONE pool that is cleared by ONE memset at the start of every step:
+        #   bitmaps (int32 words): all_nodes | indicator rows | prev rows of hop 0..H-1 | batch rows of hop 0..H-1
+        #   floats: scalars | per-hop stats | gradient direction of the sampler nets
+        n_bm = 1 + max(self.num_ind, 1) + 2 * H
+        n_fl = 16 + 4 * H + n_par
+        self.step_pool = z(n_bm * W + n_fl, **i32)
+        bm = self.step_pool[:n_bm * W].view(n_bm, W)
+        self.bm_all = bm[0]
+        self.bm_ind = bm[1:1 + max(self.num_ind, 1)]
+        self.bm_prev = [bm[1 + max(self.num_ind, 1) + h] for h in range(H)]
+        self.bm_batch = [bm[1 + max(self.num_ind, 1) + H + h] for h in range(H)]
+        fl = self.step_pool[n_bm * W:].view(torch.float32)
+        self.zero_pool = fl
+        self.scal = fl[:16]
+        self.stats = fl[16:16 + 4 * H].view(H, 4)
+        self.gdir = fl[16 + 4 * H:]          # gradient DIRECTION of (log_z, sum log_prob) w.r.t. gf / z params
         self.pref_batch, self.pref_nb, self.pref_all = z(W + 1, **i32), z(W + 1, **i32), z(W + 1, **i32)
-        # lists
+
+        # ---- id lists and device-side sizes ------------------------------------------------
         self.targets = z(self.B, **i32)
-        self.prev = [z(self.cap_P, **i32), z(self.cap_P, **i32)]
-        self.counts = z(64, **i32)          # device-side sizes, see _cnt()
-        self.row_off = z(self.cap_P + 1, **i32)
-        self.e_row, self.e_col = e(self.cap_m, **i32), e(self.cap_m, **i32)
-        self.e_src, self.e_dst = e(self.cap_m, **i32), e(self.cap_m, **i32)
-        self.batch_nodes, self.nb_nodes, self.nb_local = e(self.cap_n, **i32), e(self.cap_n, **i32), e(self.cap_n, **i32)
-        self.ind_bits = z(self.cap_n, **u32)
-        self.cnt_scratch = z(max(self.cap_n, self.cap_A), **i32)
-        self.in_off = z(self.cap_n + 1, **i32)
-        self.in_src, self.tmp_val = e(self.cap_m, **i32), e(self.cap_m, **i32)
-        self.dinv = e(self.cap_n, **f32)
-        self.Y = z((self.cap_n, self.ldY), **f32)
-        if self.use_tc_bwd:
-            ng = (self.cap_n + 127) // 128 * 4
-            self.mask_gf = z((ng, self.D), **i32)
-            self.mask_z = z((ng, self.D), **i32)
-        if self.use_tc:
-            self.Y_hi, self.Y_lo = z((self.cap_n, self.ldY), **f32), z((self.cap_n, self.ldY), **f32)
-            self.Wgf_hi, self.Wgf_lo = z((self.D, self.ldW), **f32), z((self.D, self.ldW), **f32)
-            self.Wz_hi, self.Wz_lo = z((self.D, self.ldW), **f32), z((self.D, self.ldW), **f32)
-            self.zpart = z((self.D // 128, self.cap_n), **f32)
-        self.z_gf, self.z_z = e(self.cap_n, **f32), e(self.cap_n, **f32)
-        self.logits_all, self.zlogits = z(self.cap_n, **f32), e(self.cap_n, **f32)
-        self.dl_all, self.dz = z(self.cap_n, **f32), e(self.cap_n, **f32)
-        self.dpre = e((1 if self.use_tc_bwd else self.cap_n, self.D), **f32)
-        self.ukeys = e(self.cap_n, **i32)
-        self.log_prob = z((self.H, self.cap_n), **f32)
-        self.scal = None   # views into zero_pool, set below (scal | stats | gdir share one memset per step)
-        self.stats = None
+        self.prev_pool = z((H + 1, cap_P), **i32)            # prev[h] = rows expanded at hop h; prev[H] = last block's rows
+        self.prev = [self.prev_pool[h] for h in range(H + 1)]
+        self.counts = z(16 * (H + 2), **i32)                 # [0:16] globals, then one 16-int block per hop (+ final)
+        self.cnt_scratch = z(max(cap_n, self.cap_A), **i32)
+        self.tmp_val = e(cap_m, **i32)
+        self.ukeys = e(cap_n, **i32)
+        self.sel_work = z(int(self.L.cdll.grapes_select_work_floats(graph.ctx, cap_n)), **f32)   # zero once: the library keeps its histogram clean
+        self.log_prob = z((H, cap_n), **f32)
         self.overflow = z(1, **i32)
         self.rng_state = torch.tensor([seed & 0x7fffffffffffffff, 0], dtype=torch.int64, device=dev)
-        # induced blocks (global ids), one per hop
-        self.blk_src = [e(self.cap_blk, **i32) for _ in range(self.H)]
-        self.blk_dst = [e(self.cap_blk, **i32) for _ in range(self.H)]
+
+        # ---- per-hop workspaces ------------------------------------------------------------
+        need_Y = not self.random_sampling
+        self.hops: List[_Hop] = []
+        for h in range(H):
+            hw = _Hop()
+            hw.row_off = z(cap_P + 1, **i32)
+            hw.e_row, hw.e_col = e(cap_m, **i32), e(cap_m, **i32)
+            hw.e_src, hw.e_dst = e(cap_m, **i32), e(cap_m, **i32)
+            hw.batch_nodes, hw.nb_nodes, hw.nb_local = e(cap_n, **i32), e(cap_n, **i32), e(cap_n, **i32)
+            hw.nb_index = e(cap_n, **i32)
+            hw.ind_bits = z(cap_n, **i32)
+            hw.in_off, hw.in_src, hw.dinv = z(cap_n + 1, **i32), e(cap_m, **i32), e(cap_n, **f32)
+            hw.logits_all, hw.dl_all, hw.dz = z(cap_n, **f32), z(cap_n, **f32), e(cap_n, **f32)
+            hw.Y = hw.Y_hi = hw.Y_lo = hw.mask_gf = None
+            if need_Y:
+                if self.use_tc:
+                    hw.Y_hi, hw.Y_lo = z((cap_n, self.ldY), **f32), z((cap_n, self.ldY), **f32)
+                if not self.use_tc_bwd:
+                    hw.Y = z((cap_n, self.ldY), **f32)
+                if self.use_tc_bwd:
+                    hw.mask_gf = z(((cap_n + 127) // 128 * 4, D), **i32)
+            hw.blk_src, hw.blk_dst = e(self.cap_blk, **i32), e(self.cap_blk, **i32)
+            self.hops.append(hw)
+        # expansion of the last block's rows (T u S_{H-1})
+        self.fin_row_off = z(cap_P + 1, **i32)
+        self.fin_e_row, self.fin_e_col = e(cap_m, **i32), e(cap_m, **i32)
+        # sampler-net scratch
+        if need_Y:
+            if self.use_tc:
+                self.Wgf_hi, self.Wgf_lo = z((D, self.ldW), **f32), z((D, self.ldW), **f32)
+                self.Wz_hi, self.Wz_lo = z((D, self.ldW), **f32), z((D, self.ldW), **f32)
+                self.zpart, self.zpart_z = z((D // 128, cap_n), **f32), z((D // 128, cap_n), **f32)
+                if self.use_tc_bwd:
+                    self.mask_z = z(((cap_n + 127) // 128 * 4, D), **i32)
+            else:
+                self.z_gf, self.z_z = e(cap_n, **f32), e(cap_n, **f32)
+            self.zlogits, self.dz_z = e(cap_n, **f32), e(cap_n, **f32)
+            self.dpre = e((1 if self.use_tc_bwd else cap_n, D), **f32)
+        self.const100 = torch.full((cap_n,), 100.0, **f32)
         # classifier workspace
         A = self.cap_A
         self.all_nodes = e(A, **i32)
@@ -187,26 +242,15 @@ class GrapesEngine:
         self.cl_out_dst = e(self.cap_blk, **i32)
         self.cl_tmp = e(self.cap_blk, **i32)
         self.Yc = z((A, _round_up(F, 4)), **f32)
-        self.out1 = e((A, self.D), **f32)
-        self.Zc = e((A, self.C), **f32)
-        self.logits_c = z((A, self.C), **f32)
-        self.dlogits = z((A, self.C), **f32)
-        self.dZ = e((A, self.C), **f32)
-        self.dpre1 = e((A, self.D), **f32)
+        self.out1 = e((A, D), **f32)
+        self.Zc = e((A, C), **f32)
+        self.logits_c = z((A, C), **f32)
+        self.dlogits = z((A, C), **f32)
+        self.dZ = e((A, C), **f32)
+        self.dpre1 = e((A, D), **f32)
 
-        # ---- parameters (flat), gradients, Adam state -------------------------------------
-        D, C = self.D, self.C
-        self.net_c = _Net(0, F, D, C)
-        self.net_gf = _Net(self.net_c.end, self.Fp, D, 1)
-        self.net_z = _Net(self.net_gf.end, F, D, 1)
-        n_par = self.net_z.end
-        self.n_par = n_par
         self.params = z(n_par, **f32)
         self.grads = z(n_par, **f32)
-        self.zero_pool = z(16 + 4 * self.H + n_par, **f32)
-        self.scal = self.zero_pool[:16]
-        self.stats = self.zero_pool[16:16 + 4 * self.H].view(self.H, 4)
-        self.gdir = self.zero_pool[16 + 4 * self.H:]   # gradient DIRECTION of (log_z, sum log_prob) w.r.t. gf / z params
         self.exp_avg, self.exp_avg_sq = z(n_par, **f32), z(n_par, **f32)
         self.adam_steps = z(2, **f32)        # [0] optimizer_c, [1] optimizer_gf
         gen = torch.Generator().manual_seed(seed)
@@ -214,18 +258,23 @@ class GrapesEngine:
             v = net.views(self.params)
             glorot_(v["gcn_layers.0.lin.weight"], gen)
             glorot_(v["gcn_layers.1.lin.weight"], gen)
-        self.const100 = torch.full((self.cap_n,), 100.0, **f32)
         self.bsz = self.B                   # current batch size (<= capacity B); the last batch of an epoch is partial
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self.launches_per_graph = 0
         self.record: Optional[dict] = None
-        self.trace_counts: Optional[list] = None     # bench.py: per-hop clones of the device-side sizes
+        # timing experiments only (scripts/ablate.py): leave out parts of the step to see what the rest costs
+        self.ablate = set(filter(None, os.environ.get("GRAPES_ABLATE", "").split(",")))
 
     # ------------------------------------------------------------------ helpers
-    _CNT = dict(P0=0, P1=1, m=2, n=3, c=4, nnz=5, A=6, B=7, blk=8, s=16, cl_nnz=24)
+    _CNT = dict(B=0, A=1, cl_nnz=2)
 
     def _cnt(self, name: str, idx: int = 0) -> int:
+        """device address of a global size (B, A, cl_nnz[0..2])"""
         return self.counts.data_ptr() + 4 * (self._CNT[name] + idx)
+
+    def _hc(self, h: int, name: str) -> int:
+        """device address of a per-hop size (P, m, n, c, nnz, s, blk); h == H is the last block's row list"""
+        return self.counts.data_ptr() + 4 * (16 * (h + 1) + _Hop.CNT[name])
 
     def _par(self, off: int) -> int:
         return self.params.data_ptr() + 4 * off
@@ -258,179 +307,143 @@ class GrapesEngine:
     # ------------------------------------------------------------------ the step
     def _enqueue(self, gumbel_noise: Optional[Sequence[Optional[torch.Tensor]]], apply_optim: bool,
                  noise_mode: int = NOISE_GUMBEL):
-        L, g, ctx = self.L, self.g, self.g.ctx
-        st = torch.cuda.current_stream().cuda_stream
+        L, g = self.L, self.g
+        main = torch.cuda.current_stream()
+        multi = self.multi_stream and self.side_a is not None
+        ctx, st = g.ctx, main.cuda_stream
+        ctx_a, ctx_b = self.ctx_a, self.ctx_b
+        sA, sB = (self.side_a, self.side_b) if multi else (main, main)
+        stA, stB = sA.cuda_stream, sB.cuda_stream
+        on = (lambda s: torch.cuda.stream(s)) if multi else (lambda s: contextlib.nullcontext())
+
+        forked = set()
+
+        def fork(side):                     # `side` continues from everything enqueued on main so far
+            if multi:
+                side.wait_stream(main)
+                forked.add(side)
+
+        def join(side):                     # only streams that took part in this step (graph capture forbids others)
+            if multi and side in forked:
+                main.wait_stream(side)
+                forked.discard(side)
+
         B, k, H, F, Fp, D, C, W = self.bsz, self.k, self.H, self.F, self.Fp, self.D, self.C, self.W
+        cap_P, cap_m, cap_n = self.cap_P, self.cap_m, self.cap_n
         ovf = ptr(self.overflow)
         rec = self.record
         indptr, indices, X = ptr(g.indptr), ptr(g.indices), ptr(self.x)
+        need_Y = not self.random_sampling
+        tc = self.use_tc
+        gf, nz = self.net_gf, self.net_z
 
-        # ---- per-batch reset (main.py:161-176) ----
-        L.grapes_zero(ctx, ptr(self.bm_all), 4 * W * (1 + self.num_ind), st)          # all_nodes mask | indicator rows
-        L.grapes_zero(ctx, ptr(self.zero_pool), 4 * self.zero_pool.numel(), st)       # scalars | stats | gradient direction
-        # counts[B] = B ; prev[0][:B] = prev[1][:B] = targets ; P0 = B
-        L.grapes_append_list(ctx, ptr(self.targets), self._cnt("B"), B, ptr(self.prev[0]), 0, self._cnt("P0"), st)
-        L.grapes_append_list(ctx, ptr(self.targets), self._cnt("B"), B, ptr(self.prev[1]), 0, self._cnt("P1"), st)
-        L.grapes_bitmap_set(ctx, ptr(self.targets), self._cnt("B"), B, ptr(self.bm_all), st)
-        if self.use_ind:
-            L.grapes_bitmap_set(ctx, ptr(self.targets), self._cnt("B"), B,
-                                self.bm_ind.data_ptr() + 4 * W * (self.num_ind - 1), st)
+        # ---- per-batch reset (main.py:161-176): one memset + one kernel ----
+        L.grapes_zero(ctx, ptr(self.step_pool), 4 * self.step_pool.numel(), st)
+        L.grapes_step_reset(ctx, ptr(self.targets), self._cnt("B"), B, ptr(self.prev_pool), cap_P, H + 1,
+                            self._hc(0, "P"), ptr(self.bm_all),
+                            self.bm_ind.data_ptr() + 4 * W * (self.num_ind - 1) if self.use_ind else None, st)
 
         for h in range(H):
-            cur, nxt = h % 2, (h + 1) % 2
-            P_dev = self._cnt("P0") if cur == 0 else self._cnt("P1")
-            Pn_dev = self._cnt("P0") if nxt == 0 else self._cnt("P1")
-            rows = ptr(self.prev[cur])
-            L.grapes_zero(ctx, ptr(self.bm_prev[0]) if cur == 0 else ptr(self.bm_batch), 8 * W, st)   # prev[cur] + batch
+            hw = self.hops[h]
+            rows, P_dev = ptr(self.prev[h]), self._hc(h, "P")
+            m_dev, n_dev, c_dev = self._hc(h, "m"), self._hc(h, "n"), self._hc(h, "c")
             # get_neighborhoods + mask dedup (main.py:180-190)
-            L.grapes_row_offsets(ctx, indptr, rows, P_dev, self.cap_P, ptr(self.row_off), self._cnt("m"), self.cap_m,
-                                 ptr(self.bm_prev[cur]), ptr(self.bm_batch), ovf, st)
-            L.grapes_expand_rows(ctx, indptr, indices, rows, P_dev, self.cap_P, ptr(self.row_off), self._cnt("m"),
-                                 self.cap_m, ptr(self.e_row), ptr(self.e_col), ptr(self.bm_batch), st)
+            L.grapes_row_offsets(ctx, indptr, rows, P_dev, cap_P, ptr(hw.row_off), m_dev, cap_m,
+                                 ptr(self.bm_prev[h]), ptr(self.bm_batch[h]), ovf, st)
+            L.grapes_expand_rows(ctx, indptr, indices, rows, P_dev, cap_P, ptr(hw.row_off), m_dev, cap_m,
+                                 ptr(hw.e_row), ptr(hw.e_col), ptr(self.bm_batch[h]), st)
             if h > 0:
-                # slice_adjacency(rows = T u S_{h-1}, cols = prev_{h-1}) (main.py:241-244): same row expansion
-                L.grapes_slice_block(ctx, rows, ptr(self.e_row), ptr(self.e_col), self._cnt("m"), self.cap_m,
-                                     ptr(self.bm_prev[nxt]), ptr(self.blk_src[h - 1]), ptr(self.blk_dst[h - 1]),
-                                     self.cap_blk, self._cnt("blk", h - 1), ovf, st)
-            L.grapes_rank_nodes(ctx, ptr(self.bm_batch), ptr(self.bm_prev[cur]), ptr(self.pref_batch),
-                                ptr(self.pref_nb), ptr(self.batch_nodes), ptr(self.nb_nodes), ptr(self.nb_local),
-                                ptr(self.ind_bits) if self.use_ind else None,
-                                ptr(self.bm_ind) if self.use_ind else None, self.num_ind, h, self.cap_n,
-                                self._cnt("n"), self._cnt("c"), ovf, st)
-            L.grapes_edges_to_local(ctx, rows, ptr(self.e_row), ptr(self.e_col), self._cnt("m"), self.cap_m,
-                                    ptr(self.bm_batch), ptr(self.pref_batch), ptr(self.e_src), ptr(self.e_dst),
-                                    ptr(self.cnt_scratch), st)
+                # slice_adjacency(rows = T u S_{h-1}, cols = prev_{h-1}) (main.py:241-244): same row expansion; side B
+                pw = self.hops[h - 1]
+                fork(sB)
+                with on(sB):
+                    L.grapes_slice_block(ctx_b, rows, ptr(hw.e_row), ptr(hw.e_col), m_dev, cap_m,
+                                         ptr(self.bm_prev[h - 1]), ptr(pw.blk_src), ptr(pw.blk_dst), self.cap_blk,
+                                         self._hc(h - 1, "blk"), ovf, stB)
+            L.grapes_rank_nodes(ctx, ptr(self.bm_batch[h]), ptr(self.bm_prev[h]), ptr(self.pref_batch),
+                                ptr(self.pref_nb), ptr(hw.batch_nodes), ptr(hw.nb_nodes), ptr(hw.nb_local),
+                                ptr(hw.nb_index), ptr(hw.ind_bits) if self.use_ind else None,
+                                ptr(self.bm_ind) if self.use_ind else None, self.num_ind, h, cap_n,
+                                n_dev, c_dev, ovf, st)
+            L.grapes_edges_to_local(ctx, rows, ptr(hw.e_row), ptr(hw.e_col), m_dev, cap_m, ptr(self.bm_batch[h]),
+                                    ptr(self.pref_batch), ptr(hw.e_src), ptr(hw.e_dst), ptr(self.cnt_scratch), st)
             # gcn_norm structure of the hop graph (dst-sorted CSR, deg^-1/2)
-            L.grapes_build_csr(ctx, ptr(self.e_dst), ptr(self.e_src), self._cnt("m"), self.cap_m, self._cnt("n"),
-                               self.cap_n, ptr(self.cnt_scratch), 1, ptr(self.in_off), ptr(self.in_src),
-                               ptr(self.tmp_val), ptr(self.dinv), self._cnt("nnz"), ovf, st)
-            need_Y = not self.random_sampling
+            L.grapes_build_csr(ctx, ptr(hw.e_dst), ptr(hw.e_src), m_dev, cap_m, n_dev, cap_n, ptr(self.cnt_scratch),
+                               1, ptr(hw.in_off), ptr(hw.in_src), ptr(self.tmp_val), ptr(hw.dinv),
+                               self._hc(h, "nnz"), ovf, st)
             if need_Y:
                 # Y = A_hat [x | indicators]   (feature gather fused, main.py:198-204 + GCNConv aggregation)
-                tc = self.use_tc
-                L.grapes_aggregate(ctx, X, F, F, ptr(self.batch_nodes), self._cnt("n"), self.cap_n, ptr(self.in_off),
-                                   ptr(self.in_src), ptr(self.dinv), ptr(self.ind_bits) if self.use_ind else None,
-                                   self.num_ind, None, 0, None if self.use_tc_bwd else ptr(self.Y), self.ldY,
-                                   ptr(self.Y_hi) if tc else None, ptr(self.Y_lo) if tc else None,
+                L.grapes_aggregate(ctx, X, F, F, ptr(hw.batch_nodes), n_dev, cap_n, ptr(hw.in_off), ptr(hw.in_src),
+                                   ptr(hw.dinv), ptr(hw.ind_bits) if self.use_ind else None, self.num_ind, None, 0,
+                                   ptr(hw.Y), self.ldY, ptr(hw.Y_hi), ptr(hw.Y_lo),
                                    Fp if self.use_tc_bwd else -1, st)
-                gf = self.net_gf
                 if tc:
                     if h == 0:
-                        self._split_weights(st)
-                    L.grapes_sampler_l1_fwd_tc(ctx, ptr(self.Y_hi), ptr(self.Y_lo), self.ldY, self._cnt("n"),
-                                               self.cap_n, Fp, ptr(self.Wgf_hi), ptr(self.Wgf_lo), self.ldW, D,
-                                               self._par(gf.b1), self._par(gf.W2), ptr(self.zpart),
-                                               ptr(self.mask_gf) if self.use_tc_bwd else None, st)
-                    L.grapes_aggregate_scalar(ctx, ptr(self.zpart), D // 128, self.cap_n, self._cnt("n"), self.cap_n,
-                                              ptr(self.in_off), ptr(self.in_src), ptr(self.dinv), self._par(gf.b2),
-                                              ptr(self.logits_all), ptr(self.dl_all), st)
+                        self._split_weights(ctx, st)
+                    L.grapes_sampler_l1_fwd_tc(ctx, ptr(hw.Y_hi), ptr(hw.Y_lo), self.ldY, n_dev, cap_n, Fp,
+                                               ptr(self.Wgf_hi), ptr(self.Wgf_lo), self.ldW, D, self._par(gf.b1),
+                                               self._par(gf.W2), ptr(self.zpart), ptr(hw.mask_gf), st)
+                    z_ptr, z_parts, z_stride = ptr(self.zpart), D // 128, cap_n
                 else:
-                    L.grapes_sampler_l1_fwd(ctx, ptr(self.Y), self.ldY, self._cnt("n"), self.cap_n, Fp,
-                                            self._par(gf.W1), Fp, D, self._par(gf.b1), self._par(gf.W2),
-                                            ptr(self.z_gf), st)
-                    L.grapes_aggregate_scalar(ctx, ptr(self.z_gf), 1, 0, self._cnt("n"), self.cap_n, ptr(self.in_off),
-                                              ptr(self.in_src), ptr(self.dinv), self._par(gf.b2),
-                                              ptr(self.logits_all), ptr(self.dl_all), st)
-                logits_ptr = ptr(self.logits_all)
-            else:
-                logits_ptr = ptr(self.const100)                                   # main.py:207
+                    L.grapes_sampler_l1_fwd(ctx, ptr(hw.Y), self.ldY, n_dev, cap_n, Fp, self._par(gf.W1), Fp, D,
+                                            self._par(gf.b1), self._par(gf.W2), ptr(self.z_gf), st)
+                    z_ptr, z_parts, z_stride = ptr(self.z_gf), 1, 0
             noise = None if gumbel_noise is None else gumbel_noise[h]
             mode = noise_mode if noise is not None else NOISE_PHILOX
-            lp = self.log_prob.data_ptr() + 4 * self.cap_n * h
-            L.grapes_select_topk(ctx, logits_ptr, ptr(self.nb_local), ptr(self.nb_nodes), self._cnt("c"), self.cap_n,
-                                 k, mode, ptr(noise), ptr(self.rng_state), ptr(self.ukeys),
-                                 ptr(rec["keys_buf"]) if rec is not None else None,
-                                 ptr(self.prev[nxt]), B, self._cnt("s", h), Pn_dev, None, lp,
-                                 self._scal("tot_log_prob"), self.stats.data_ptr() + 16 * h,
-                                 ptr(self.dl_all) if need_Y else None,
-                                 self._dir(self.net_gf.b2) if need_Y else None, ptr(self.bm_all), st)
+            lp = self.log_prob.data_ptr() + 4 * cap_n * h
+            # layer 2 of gcn_gf at width 1 -> logits (main.py:210-213), then sample_neighborhoods_from_probs
+            # (utils.py:13-71): keys, Gumbel-top-k, log-probs, stats, d(sum log_prob)/d logits
             if need_Y:
-                # d(sum log_prob)/d(theta_gf): direction accumulated now, scaled by g at the end
-                L.grapes_aggregate_scalar_T(ctx, ptr(self.dl_all), self._cnt("n"), self.cap_n, P_dev, self.cap_P,
-                                            ptr(self.row_off), ptr(self.e_src), ptr(self.e_dst), ptr(self.dinv),
-                                            ptr(self.bm_prev[cur]), ptr(self.batch_nodes), ptr(self.dz), st)
-                gf = self.net_gf
-                if self.use_tc_bwd:
-                    L.grapes_sampler_l1_bwd_tc(ctx, ptr(self.Y_hi), ptr(self.Y_lo), self.ldY, Fp + 1, self._cnt("n"),
-                                               self.cap_n, Fp, Fp, ptr(self.mask_gf), self._par(gf.W1), Fp, D,
-                                               self._par(gf.b1), self._par(gf.W2), ptr(self.dz), 1.0,
-                                               self._dir(gf.W1), self._dir(gf.b1), self._dir(gf.W2), st)
-                else:
-                    L.grapes_sampler_l1_bwd(ctx, ptr(self.Y), self.ldY, self._cnt("n"), self.cap_n, Fp,
-                                            self._par(gf.W1), Fp, D, self._par(gf.b1), self._par(gf.W2), ptr(self.dz),
-                                            ptr(self.dpre), 1.0, 1, self._dir(gf.W1), Fp, self._dir(gf.b1),
-                                            self._dir(gf.W2), st)
-                if h == 0:
-                    # log_z = mean(gcn_z(x[batch_nodes], edges)) - log_z_init   (main.py:223-228)
-                    nz = self.net_z
-                    if self.use_tc:
-                        L.grapes_sampler_l1_fwd_tc(ctx, ptr(self.Y_hi), ptr(self.Y_lo), self.ldY, self._cnt("n"),
-                                                   self.cap_n, F, ptr(self.Wz_hi), ptr(self.Wz_lo), self.ldW, D,
-                                                   self._par(nz.b1), self._par(nz.W2), ptr(self.zpart),
-                                                   ptr(self.mask_z) if self.use_tc_bwd else None, st)
-                        L.grapes_aggregate_scalar(ctx, ptr(self.zpart), D // 128, self.cap_n, self._cnt("n"),
-                                                  self.cap_n, ptr(self.in_off), ptr(self.in_src), ptr(self.dinv),
-                                                  self._par(nz.b2), ptr(self.zlogits), None, st)
-                    else:
-                        L.grapes_sampler_l1_fwd(ctx, ptr(self.Y), self.ldY, self._cnt("n"), self.cap_n, F,
-                                                self._par(nz.W1), F, D, self._par(nz.b1), self._par(nz.W2),
-                                                ptr(self.z_z), st)
-                        L.grapes_aggregate_scalar(ctx, ptr(self.z_z), 1, 0, self._cnt("n"), self.cap_n,
-                                                  ptr(self.in_off), ptr(self.in_src), ptr(self.dinv),
-                                                  self._par(nz.b2), ptr(self.zlogits), None, st)
-                    L.grapes_vec_sum(ctx, ptr(self.zlogits), self._cnt("n"), self.cap_n, 1.0, 1, 0,
-                                     self._scal("log_z_mean"), st)
-                    if not self.reinforce:
-                        L.grapes_fill_inv_count(ctx, ptr(self.zlogits), self._cnt("n"), self.cap_n, st)
-                        L.grapes_aggregate_scalar_T(ctx, ptr(self.zlogits), self._cnt("n"), self.cap_n, P_dev,
-                                                    self.cap_P, ptr(self.row_off), ptr(self.e_src), ptr(self.e_dst),
-                                                    ptr(self.dinv), ptr(self.bm_prev[cur]), ptr(self.batch_nodes),
-                                                    ptr(self.dz), st)
-                        if self.use_tc_bwd:
-                            L.grapes_sampler_l1_bwd_tc(ctx, ptr(self.Y_hi), ptr(self.Y_lo), self.ldY, Fp + 1,
-                                                       self._cnt("n"), self.cap_n, F, Fp, ptr(self.mask_z),
-                                                       self._par(nz.W1), F, D, self._par(nz.b1), self._par(nz.W2),
-                                                       ptr(self.dz), 1.0, self._dir(nz.W1), self._dir(nz.b1),
-                                                       self._dir(nz.W2), st)
-                        else:
-                            L.grapes_sampler_l1_bwd(ctx, ptr(self.Y), self.ldY, self._cnt("n"), self.cap_n, F,
-                                                    self._par(nz.W1), F, D, self._par(nz.b1), self._par(nz.W2),
-                                                    ptr(self.dz), ptr(self.dpre), 1.0, 1, self._dir(nz.W1), F,
-                                                    self._dir(nz.b1), self._dir(nz.W2), st)
-                        L.grapes_fill_f32(ctx, self._dir(nz.b2), 1.0, 1, st)
-            if rec is not None:
-                self._record_hop(h, cur)
-            if self.trace_counts is not None:
-                self.trace_counts.append(self.counts.clone())
+                agg = (z_ptr, z_parts, z_stride, n_dev, cap_n, ptr(hw.in_off), ptr(hw.in_src), ptr(hw.dinv),
+                       self._par(gf.b2))
+            else:
+                agg = (ptr(self.const100), 1, 0, n_dev, cap_n, None, None, None, None)        # main.py:207
+            L.grapes_select_hop(ctx, *agg, ptr(hw.nb_index), ptr(hw.nb_local), ptr(hw.nb_nodes), c_dev, k, mode,
+                                ptr(noise), ptr(self.rng_state), ptr(self.sel_work), ptr(self.ukeys),
+                                ptr(hw.logits_all) if need_Y else None,
+                                ptr(rec["keys"][h]) if rec is not None else None,
+                                ptr(self.prev[h + 1]), B, self._hc(h, "s"), self._hc(h + 1, "P"), None, lp,
+                                self._scal("tot_log_prob"), self.stats.data_ptr() + 16 * h,
+                                ptr(hw.dl_all) if need_Y else None,
+                                self._dir(gf.b2) if need_Y else None, ptr(self.bm_all), st)
+            if need_Y and "nobwd" not in self.ablate:
+                # ---- side A: d(sum log_prob)/d(theta_gf), direction accumulated now, scaled by g at the end ----
+                fork(sA)
+                with on(sA):
+                    self._enqueue_hop_backward(h, ctx_a, stA)
 
         # ---- last block: slice_adjacency(rows = T u S_{H-1}, cols = prev_{H-1}) ----
-        cur, nxt = H % 2, (H + 1) % 2
-        P_dev = self._cnt("P0") if cur == 0 else self._cnt("P1")
-        rows = ptr(self.prev[cur])
-        L.grapes_row_offsets(ctx, indptr, rows, P_dev, self.cap_P, ptr(self.row_off), self._cnt("m"), self.cap_m,
-                             None, None, ovf, st)
-        L.grapes_expand_rows(ctx, indptr, indices, rows, P_dev, self.cap_P, ptr(self.row_off), self._cnt("m"),
-                             self.cap_m, ptr(self.e_row), ptr(self.e_col), None, st)
-        L.grapes_slice_block(ctx, rows, ptr(self.e_row), ptr(self.e_col), self._cnt("m"), self.cap_m,
-                             ptr(self.bm_prev[nxt]), ptr(self.blk_src[H - 1]), ptr(self.blk_dst[H - 1]), self.cap_blk,
-                             self._cnt("blk", H - 1), ovf, st)
+        rows, P_dev, m_dev = ptr(self.prev[H]), self._hc(H, "P"), self._hc(H, "m")
+        L.grapes_row_offsets(ctx, indptr, rows, P_dev, cap_P, ptr(self.fin_row_off), m_dev, cap_m, None, None, ovf, st)
+        L.grapes_expand_rows(ctx, indptr, indices, rows, P_dev, cap_P, ptr(self.fin_row_off), m_dev, cap_m,
+                             ptr(self.fin_e_row), ptr(self.fin_e_col), None, st)
+        lw = self.hops[H - 1]
+        join(sB)                                                                  # earlier blocks + frees ctx_b's scratch order
+        L.grapes_slice_block(ctx, rows, ptr(self.fin_e_row), ptr(self.fin_e_col), m_dev, cap_m,
+                             ptr(self.bm_prev[H - 1]), ptr(lw.blk_src), ptr(lw.blk_dst), self.cap_blk,
+                             self._hc(H - 1, "blk"), ovf, st)
 
+        if "nocls" in self.ablate:
+            join(sA)
+            return
         # ---- classifier on the sampled subgraph (main.py:252-269) ----
+        L.tag = "[cls]"
         L.grapes_rank_nodes(ctx, ptr(self.bm_all), None, ptr(self.pref_all), None, ptr(self.all_nodes), None, None,
-                            None, None, 0, 0, self.cap_A, self._cnt("A"), None, ovf, st)
+                            None, None, None, 0, 0, self.cap_A, self._cnt("A"), None, ovf, st)
         L.grapes_relabel(ctx, ptr(self.targets), self._cnt("B"), B, ptr(self.bm_all), ptr(self.pref_all),
                          ptr(self.target_local), st)
         # GCN.forward with a per-layer list: hidden layer <- edge_indices[-1], last layer <- edge_indices[0] (gcn.py:30-36)
         for slot, hop in ((0, H - 1), (1, 0)):
-            L.grapes_relabel(ctx, ptr(self.blk_src[hop]), self._cnt("blk", hop), self.cap_blk, ptr(self.bm_all),
+            bw = self.hops[hop]
+            L.grapes_relabel(ctx, ptr(bw.blk_src), self._hc(hop, "blk"), self.cap_blk, ptr(self.bm_all),
                              ptr(self.pref_all), ptr(self.cl_src[slot]), st)
-            L.grapes_relabel(ctx, ptr(self.blk_dst[hop]), self._cnt("blk", hop), self.cap_blk, ptr(self.bm_all),
+            L.grapes_relabel(ctx, ptr(bw.blk_dst), self._hc(hop, "blk"), self.cap_blk, ptr(self.bm_all),
                              ptr(self.pref_all), ptr(self.cl_dst[slot]), st)
-            L.grapes_build_csr(ctx, ptr(self.cl_dst[slot]), ptr(self.cl_src[slot]), self._cnt("blk", hop),
+            L.grapes_build_csr(ctx, ptr(self.cl_dst[slot]), ptr(self.cl_src[slot]), self._hc(hop, "blk"),
                                self.cap_blk, self._cnt("A"), self.cap_A, ptr(self.cnt_scratch), 0,
                                ptr(self.cl_in_off[slot]), ptr(self.cl_in_src[slot]), ptr(self.cl_tmp),
                                ptr(self.cl_dinv[slot]), self._cnt("cl_nnz", slot), ovf, st)
-        L.grapes_build_csr(ctx, ptr(self.cl_src[1]), ptr(self.cl_dst[1]), self._cnt("blk", 0), self.cap_blk,
+        L.grapes_build_csr(ctx, ptr(self.cl_src[1]), ptr(self.cl_dst[1]), self._hc(0, "blk"), self.cap_blk,
                            self._cnt("A"), self.cap_A, ptr(self.cnt_scratch), 0, ptr(self.cl_out_off),
                            ptr(self.cl_out_dst), ptr(self.cl_tmp), None, self._cnt("cl_nnz", 2), ovf, st)
         nc = self.net_c
@@ -459,10 +472,11 @@ class GrapesEngine:
         L.grapes_colsum(ctx, ptr(self.dpre1), A_dev, cap_A, D, D, 1.0, 0, self._grd(nc.b1), st)
         L.grapes_gemm_tn(ctx, ptr(self.dpre1), D, ptr(self.Yc), ldYc, A_dev, cap_A, D, F, 1.0, 0, self._grd(nc.W1),
                          st)
+        L.tag = ""
         # ---- GFlowNet / REINFORCE loss (main.py:271-291) ----
+        join(sA)
         if not self.random_sampling:
             L.grapes_gfn_finalize(ctx, ptr(self.scal), self.loss_coef, self.log_z_init, int(self.reinforce), 1, st)
-            gf, nz = self.net_gf, self.net_z
             L.grapes_scale_by_device_scalar(ctx, self._dir(gf.base), self._scal("g_gf"), gf.size,
                                             self._grd(gf.base), st)
             L.grapes_scale_by_device_scalar(ctx, self._dir(nz.base), self._scal("g_z"), nz.size,
@@ -470,9 +484,60 @@ class GrapesEngine:
         if apply_optim:
             self._enqueue_optim()
 
-    def _split_weights(self, st):
+    def _enqueue_hop_backward(self, h: int, ctx, st):
+        """Side stream A.  Gradient direction of sum(log_prob_h) w.r.t. gcn_gf (main.py:271-287 via
+        d log_prob_i / d logit_i = mask_i - sigmoid(logit_i)); at hop 0 also gcn_z forward (log_z,
+        main.py:223-228) and its gradient direction.  Reads only this hop's workspace."""
+        L = self.L
+        hw = self.hops[h]
+        F, Fp, D, cap_n, cap_P = self.F, self.Fp, self.D, self.cap_n, self.cap_P
+        gf, nz = self.net_gf, self.net_z
+        n_dev, P_dev = self._hc(h, "n"), self._hc(h, "P")
+        L.grapes_aggregate_scalar_T(ctx, ptr(hw.dl_all), n_dev, cap_n, P_dev, cap_P, ptr(hw.row_off), ptr(hw.e_src),
+                                    ptr(hw.e_dst), ptr(hw.dinv), ptr(self.bm_prev[h]), ptr(hw.batch_nodes),
+                                    ptr(hw.dz), st)
+        if self.use_tc_bwd:
+            L.grapes_sampler_l1_bwd_tc(ctx, ptr(hw.Y_hi), ptr(hw.Y_lo), self.ldY, Fp + 1, n_dev, cap_n, Fp, Fp,
+                                       ptr(hw.mask_gf), self._par(gf.W1), Fp, D, self._par(gf.b1), self._par(gf.W2),
+                                       ptr(hw.dz), 1.0, self._dir(gf.W1), self._dir(gf.b1), self._dir(gf.W2), st)
+        else:
+            L.grapes_sampler_l1_bwd(ctx, ptr(hw.Y), self.ldY, n_dev, cap_n, Fp, self._par(gf.W1), Fp, D,
+                                    self._par(gf.b1), self._par(gf.W2), ptr(hw.dz), ptr(self.dpre), 1.0, 1,
+                                    self._dir(gf.W1), Fp, self._dir(gf.b1), self._dir(gf.W2), st)
+        if h != 0:
+            return
+        # log_z = mean(gcn_z(x[batch_nodes], edges)) - log_z_init   (main.py:223-228)
+        if self.use_tc:
+            L.grapes_sampler_l1_fwd_tc(ctx, ptr(hw.Y_hi), ptr(hw.Y_lo), self.ldY, n_dev, cap_n, F, ptr(self.Wz_hi),
+                                       ptr(self.Wz_lo), self.ldW, D, self._par(nz.b1), self._par(nz.W2),
+                                       ptr(self.zpart_z), ptr(self.mask_z) if self.use_tc_bwd else None, st)
+            L.grapes_aggregate_scalar(ctx, ptr(self.zpart_z), D // 128, cap_n, n_dev, cap_n, ptr(hw.in_off),
+                                      ptr(hw.in_src), ptr(hw.dinv), self._par(nz.b2), ptr(self.zlogits), None, st)
+        else:
+            L.grapes_sampler_l1_fwd(ctx, ptr(hw.Y), self.ldY, n_dev, cap_n, F, self._par(nz.W1), F, D,
+                                    self._par(nz.b1), self._par(nz.W2), ptr(self.z_z), st)
+            L.grapes_aggregate_scalar(ctx, ptr(self.z_z), 1, 0, n_dev, cap_n, ptr(hw.in_off), ptr(hw.in_src),
+                                      ptr(hw.dinv), self._par(nz.b2), ptr(self.zlogits), None, st)
+        L.grapes_vec_sum(ctx, ptr(self.zlogits), n_dev, cap_n, 1.0, 1, 0, self._scal("log_z_mean"), st)
+        if self.reinforce:
+            return                                             # gcn_z has no gradient under REINFORCE (main.py:279)
+        L.grapes_fill_inv_count(ctx, ptr(self.zlogits), n_dev, cap_n, st)
+        L.grapes_aggregate_scalar_T(ctx, ptr(self.zlogits), n_dev, cap_n, P_dev, cap_P, ptr(hw.row_off),
+                                    ptr(hw.e_src), ptr(hw.e_dst), ptr(hw.dinv), ptr(self.bm_prev[h]),
+                                    ptr(hw.batch_nodes), ptr(self.dz_z), st)
+        if self.use_tc_bwd:
+            L.grapes_sampler_l1_bwd_tc(ctx, ptr(hw.Y_hi), ptr(hw.Y_lo), self.ldY, Fp + 1, n_dev, cap_n, F, Fp,
+                                       ptr(self.mask_z), self._par(nz.W1), F, D, self._par(nz.b1), self._par(nz.W2),
+                                       ptr(self.dz_z), 1.0, self._dir(nz.W1), self._dir(nz.b1), self._dir(nz.W2), st)
+        else:
+            L.grapes_sampler_l1_bwd(ctx, ptr(hw.Y), self.ldY, n_dev, cap_n, F, self._par(nz.W1), F, D,
+                                    self._par(nz.b1), self._par(nz.W2), ptr(self.dz_z), ptr(self.dpre), 1.0, 1,
+                                    self._dir(nz.W1), F, self._dir(nz.b1), self._dir(nz.W2), st)
+        L.grapes_fill_f32(ctx, self._dir(nz.b2), 1.0, 1, st)
+
+    def _split_weights(self, ctx, st):
         """3xTF32 operand split of the (per-step changing) layer-1 weights of gcn_gf / gcn_z."""
-        L, ctx = self.L, self.g.ctx
+        L = self.L
         gf, nz = self.net_gf, self.net_z
         L.grapes_split_tf32(ctx, self._par(gf.W1), self.Fp, self.D, self.Fp, ptr(self.Wgf_hi), ptr(self.Wgf_lo),
                             self.ldW, st)
@@ -521,14 +586,15 @@ class GrapesEngine:
             gr.replay()
             return None
         if record:
-            self.record = {"hops": [], "keys_buf": torch.zeros(self.cap_n, dtype=torch.float32, device=self.device)}
+            self.record = {"keys": [torch.zeros(self.cap_n, dtype=torch.float32, device=self.device)
+                                    for _ in range(self.H)]}
         try:
             self._enqueue(gumbel_noise, apply_optim, noise_mode)
         finally:
             rec, self.record = self.record, None
         if record:
-            self._record_final(rec)
-        return rec
+            return self._record_all(rec)
+        return None
 
     def check_overflow(self):
         v = int(self.overflow.item())
@@ -543,40 +609,46 @@ class GrapesEngine:
     def count(self, name: str, idx: int = 0) -> int:
         return int(self.counts[self._CNT[name] + idx].item())
 
-    # ------------------------------------------------------------------ recording (tests only; syncs)
-    def _record_hop(self, h: int, cur: int):
-        torch.cuda.synchronize()
-        P = self.count("P0" if cur == 0 else "P1")
-        m, n, c, s = self.count("m"), self.count("n"), self.count("c"), self.count("s", h)
-        nxt = (h + 1) % 2
-        r = dict(P=P, m=m, n=n, c=c, s=s,
-                 prev=self.prev[cur][:P].clone(), e_row=self.e_row[:m].clone(), e_col=self.e_col[:m].clone(),
-                 e_src=self.e_src[:m].clone(), e_dst=self.e_dst[:m].clone(),
-                 batch_nodes=self.batch_nodes[:n].clone(), neighbor_nodes=self.nb_nodes[:c].clone(),
-                 nb_local=self.nb_local[:c].clone(), ind_bits=self.ind_bits[:n].clone(),
-                 in_off=self.in_off[:n + 1].clone(), in_src=self.in_src[:self.count("nnz")].clone(),
-                 dinv=self.dinv[:n].clone(), Y=((self.Y_hi[:n] + self.Y_lo[:n]) if self.use_tc_bwd else self.Y[:n].clone()), logits_all=self.logits_all[:n].clone(),
-                 sampled=self.prev[nxt][self.bsz:self.bsz + s].clone(), log_prob=self.log_prob[h, :c].clone(),
-                 keys=self.record["keys_buf"][:c].clone(), stats=self.stats[h].clone(),
-                 dl_all=self.dl_all[:n].clone(), dz=self.dz[:n].clone(), zlogits=self.zlogits[:n].clone())
-        if h > 0:
-            e = self.count("blk", h - 1)
-            self.record["hops"][h - 1]["block_edges"] = torch.stack([self.blk_src[h - 1][:e], self.blk_dst[h - 1][:e]]).clone()
-        self.record["hops"].append(r)
+    def hop_sizes(self) -> List[Dict[str, int]]:
+        """device-side sizes of the last step, one dict per hop (syncs)"""
+        c = self.counts.cpu().tolist()
+        return [{k: c[16 * (h + 1) + i] for k, i in _Hop.CNT.items()} for h in range(self.H)]
 
-    def _record_final(self, rec: dict):
+    # ------------------------------------------------------------------ recording (tests only; syncs)
+    def _record_all(self, rec: dict) -> dict:
         torch.cuda.synchronize()
         H = self.H
-        e = self.count("blk", H - 1)
-        rec["hops"][H - 1]["block_edges"] = torch.stack([self.blk_src[H - 1][:e], self.blk_dst[H - 1][:e]]).clone()
+        sizes = self.hop_sizes()
+        out = {"hops": []}
+        for h in range(H):
+            hw, sz = self.hops[h], sizes[h]
+            P, m, n, c, s, e = sz["P"], sz["m"], sz["n"], sz["c"], sz["s"], sz["blk"]
+            if self.random_sampling:
+                Y = None
+            elif self.use_tc_bwd:
+                Y = hw.Y_hi[:n] + hw.Y_lo[:n]
+            else:
+                Y = hw.Y[:n].clone()
+            r = dict(P=P, m=m, n=n, c=c, s=s,
+                     prev=self.prev[h][:P].clone(), e_row=hw.e_row[:m].clone(), e_col=hw.e_col[:m].clone(),
+                     e_src=hw.e_src[:m].clone(), e_dst=hw.e_dst[:m].clone(),
+                     batch_nodes=hw.batch_nodes[:n].clone(), neighbor_nodes=hw.nb_nodes[:c].clone(),
+                     nb_local=hw.nb_local[:c].clone(), ind_bits=hw.ind_bits[:n].clone(),
+                     in_off=hw.in_off[:n + 1].clone(), in_src=hw.in_src[:sz["nnz"]].clone(),
+                     dinv=hw.dinv[:n].clone(), Y=Y, logits_all=hw.logits_all[:n].clone(),
+                     sampled=self.prev[h + 1][self.bsz:self.bsz + s].clone(), log_prob=self.log_prob[h, :c].clone(),
+                     keys=rec["keys"][h][:c].clone(), stats=self.stats[h].clone(),
+                     dl_all=hw.dl_all[:n].clone(), dz=hw.dz[:n].clone(),
+                     block_edges=torch.stack([hw.blk_src[:e], hw.blk_dst[:e]]).clone())
+            out["hops"].append(r)
         A = self.count("A")
-        rec["all_nodes"] = self.all_nodes[:A].clone()
-        rec["target_local"] = self.target_local[:self.bsz].clone()
-        rec["logits_c"] = self.logits_c[:A].clone()
-        rec["scalars"] = self.scalars()
-        rec["grads"] = {k: {n: t.clone() for n, t in v.items()} for k, v in self.grad_dicts().items()}
-        rec["cl_edges"] = []
+        out["all_nodes"] = self.all_nodes[:A].clone()
+        out["target_local"] = self.target_local[:self.bsz].clone()
+        out["logits_c"] = self.logits_c[:A].clone()
+        out["scalars"] = self.scalars()
+        out["grads"] = {k: {n: t.clone() for n, t in v.items()} for k, v in self.grad_dicts().items()}
+        out["cl_edges"] = []
         for slot, hop in ((0, H - 1), (1, 0)):
-            e = self.count("blk", hop)
-            rec["cl_edges"].append(torch.stack([self.cl_src[slot][:e], self.cl_dst[slot][:e]]).clone())
-        rec.pop("keys_buf", None)
+            e = sizes[hop]["blk"]
+            out["cl_edges"].append(torch.stack([self.cl_src[slot][:e], self.cl_dst[slot][:e]]).clone())
+        return out

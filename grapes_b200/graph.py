@@ -43,6 +43,7 @@ class DeviceGraph:
             max_frontier = max(self.num_nodes, 1 << 22)
         self.max_frontier = int(min(max_frontier, (1 << 31) - 1))
         self._ctx = ctypes.c_void_p()
+        self._extra = []
         L = lib()
         rc = L.cdll.grapes_ctx_create(device.index or 0, self.num_nodes, self.max_frontier, partials_bytes,
                                       ctypes.byref(self._ctx))
@@ -53,8 +54,23 @@ class DeviceGraph:
     def ctx(self):
         return self._ctx
 
+    def new_ctx(self, partials_bytes: int = 64 << 20):
+        """Another library context for the same graph: one per CUDA stream that issues calls concurrently
+        (a ctx owns the scan / split-K scratch and is not re-entrant)."""
+        c = ctypes.c_void_p()
+        L = lib()
+        rc = L.cdll.grapes_ctx_create(self.device.index or 0, self.num_nodes, self.max_frontier, partials_bytes,
+                                      ctypes.byref(c))
+        if rc != 0:
+            raise GrapesError(f"grapes_ctx_create failed ({rc}): {L.last_error()}")
+        self._extra.append(c)
+        return c
+
     def __del__(self):
         try:
+            for c in getattr(self, "_extra", []):
+                lib().cdll.grapes_ctx_destroy(c)
+            self._extra = []
             if getattr(self, "_ctx", None):
                 lib().cdll.grapes_ctx_destroy(self._ctx)
                 self._ctx = None

@@ -160,6 +160,7 @@ def sample_neighborhoods_from_probs(logits: Tensor, neighbor_nodes: Tensor, num_
     cnt[0] = n
     cap = max(n, 1)
     ukeys = torch.empty(cap, dtype=torch.int32, device=dev)
+    work = torch.zeros(int(L.cdll.grapes_select_work_floats(ctx, cap)), dtype=torch.float32, device=dev)
     sampled = torch.empty(cap, dtype=torch.int32, device=dev)
     log_prob = torch.empty(cap, dtype=torch.float32, device=dev)
     dl = torch.empty(cap, dtype=torch.float32, device=dev)
@@ -175,7 +176,7 @@ def sample_neighborhoods_from_probs(logits: Tensor, neighbor_nodes: Tensor, num_
         rng_state = torch.tensor([int(torch.initial_seed()) & 0x7fffffffffffffff,
                                   int(torch.randint(0, 1 << 62, (1,)).item())], dtype=torch.int64, device=dev)
     L.grapes_select_topk(ctx, ptr(lf), None, ptr(nb32), cnt.data_ptr(), cap, k, mode, ptr(noise), ptr(rng_state),
-                         ptr(ukeys), None, ptr(sampled), 0, cnt.data_ptr() + 4, None, None, ptr(log_prob),
+                         ptr(ukeys), ptr(work), None, ptr(sampled), 0, cnt.data_ptr() + 4, None, None, ptr(log_prob),
                          acc.data_ptr(), ptr(stats), ptr(dl), acc.data_ptr() + 4, None, _stream())
     s = int(cnt[1].item())
     out_nodes = sampled[:s].to(torch.int64).to(neighbor_nodes.device)

@@ -85,10 +85,11 @@ int grapes_expand_rows(grapes_ctx* ctx, const int64_t* indptr, const int* indice
                        int* e_col, uint32_t* bm_batch, void* stream);
 /* mask -> ascending id lists + local numbering (main.py:187-195).  pref_* = per-word exclusive
  * popcount prefix (local id of v = pref[v>>5] + popc(bm[v>>5] & ((1<<(v&31))-1)) = TensorMap.map).
- * nb_* describe batch & ~prev (neighbor_nodes); bm_ind[hop] receives that mask and ind_bits[j]
+ * nb_* describe batch & ~prev (neighbor_nodes; nb_index[j] = position of batch node j in it or -1, optional);
+ * bm_ind[hop] receives that mask and ind_bits[j]
  * the indicator columns of batch node j (indicator_features, main.py:167-168,191,199-202).        */
 int grapes_rank_nodes(grapes_ctx* ctx, const uint32_t* bm_batch, const uint32_t* bm_prev, int* pref_batch,
-                      int* pref_nb, int* batch_nodes, int* nb_nodes, int* nb_local, uint32_t* ind_bits,
+                      int* pref_nb, int* batch_nodes, int* nb_nodes, int* nb_local, int* nb_index, uint32_t* ind_bits,
                       uint32_t* bm_ind, int ind_rows, int hop, int cap_n, int* n_dev, int* c_dev, int* overflow,
                       void* stream);
 /* node_map.map(neighborhoods) (main.py:195): local (src, dst) of every expanded edge.  cnt_hist
@@ -110,6 +111,10 @@ int grapes_bitmap_clear_words(grapes_ctx* ctx, const int* ids, const int* count_
 /* dst[off..off+n) = src; *total_dev = off + n   (batch_nodes = cat([targets, sampled]), main.py:236) */
 int grapes_append_list(grapes_ctx* ctx, const int* src, const int* count_dev, int cap, int* dst, int dst_offset,
                        int* total_dev, void* stream);
+/* per-batch reset (main.py:161-168): targets -> head of `nlists` row lists `list_stride` ints apart, their bits
+ * set in bm_a / bm_b (all_nodes_mask, last indicator row; either may be NULL), *P0_dev = batch size.       */
+int grapes_step_reset(grapes_ctx* ctx, const int* targets, const int* B_dev, int cap_B, int* lists,
+                      int64_t list_stride, int nlists, int* P0_dev, uint32_t* bm_a, uint32_t* bm_b, void* stream);
 int grapes_ids_i64_to_i32(grapes_ctx* ctx, const int64_t* in, int n, int* out, int* count_dev, void* stream);
 int grapes_ids_i32_to_i64(grapes_ctx* ctx, const int* in, const int* count_dev, int cap, int64_t* out, void* stream);
 
@@ -178,12 +183,29 @@ int grapes_sampler_l1_bwd_tc(grapes_ctx* ctx, const float* Y_hi, const float* Y_
                              float scale, float* gW1, float* gb1, float* gw2, void* stream);
 
 /* ---- selection (utils.py:13-71; eval.py:126-130) --------------------------------------------- */
+/* debugging aid: phase time stamps (globaltimer ns) of the last on-chip selection launch, HOST array of 16 */
+int grapes_debug_select_stamps(int64_t* out16);
+/* floats of scratch (`work`, 16-byte aligned) the two calls below need for cap_c candidates              */
+int64_t grapes_select_work_floats(grapes_ctx* ctx, int cap_c);
+/* One hop of the sampler head: layer-2 aggregation of the sampler GCN at width 1 -> logits (main.py:210-213;
+ * arguments as grapes_aggregate_scalar, in_off == NULL: z already holds the logits), then
+ * sample_neighborhoods_from_probs (utils.py:13-71) on the candidate rows: Gumbel-top-k, Bernoulli log-prob of the
+ * mask, statistics, d(sum log_prob)/d logit.  nb_index[j] = candidate index of frontier row j or -1.       */
+int grapes_select_hop(grapes_ctx* ctx, const float* z, int nparts, int part_stride, const int* n_dev, int cap_n,
+                      const int* in_off, const int* in_src, const float* dinv, const float* bias,
+                      const int* nb_index, const int* nb_local, const int* nb_nodes, const int* c_dev, int k,
+                      int noise_mode, const float* noise, unsigned long long* rng_state, float* work,
+                      uint32_t* ukeys_scratch, float* logits_all, float* keys_out, int* sampled_out,
+                      int sampled_offset, int* s_dev, int* total_dev, uint8_t* mask_out, float* log_prob,
+                      float* tot_log_prob, float* stats, float* dl_all, float* sum_dl, uint32_t* bm_mark,
+                      void* stream);
+/* the same on per-candidate logits (logits_all[i] = logit of candidate i; nb_local must be NULL)          */
 int grapes_select_topk(grapes_ctx* ctx, const float* logits_all, const int* nb_local, const int* nb_nodes,
                        const int* c_dev, int cap_c, int k, int noise_mode, const float* noise,
-                       unsigned long long* rng_state, uint32_t* ukeys_scratch, float* keys_out, int* sampled_out,
-                       int sampled_offset, int* s_dev, int* total_dev, uint8_t* mask_out, float* log_prob,
-                       float* tot_log_prob, float* stats, float* dl_all, float* sum_dl, uint32_t* bm_mark,
-                       void* stream);
+                       unsigned long long* rng_state, uint32_t* ukeys_scratch, float* work, float* keys_out,
+                       int* sampled_out, int sampled_offset, int* s_dev, int* total_dev, uint8_t* mask_out,
+                       float* log_prob, float* tot_log_prob, float* stats, float* dl_all, float* sum_dl,
+                       uint32_t* bm_mark, void* stream);
 
 /* ---- losses + optimiser (main.py:117-123,260-291) -------------------------------------------- */
 int grapes_classifier_loss(grapes_ctx* ctx, const float* logits, int ldl, int C, const int* A_dev, int A_cap,

