@@ -333,54 +333,53 @@ __global__ void __launch_bounds__(256) k_sort_rows(const int* __restrict__ off, 
 // graphs with at most SMALL_N nodes (the classifier's sampled blocks: <= B + hops*k nodes, main.py:252-257).
 // ---------------------------------------------------------------------------------------
 #define SMALL_N 4096
-__global__ void __launch_bounds__(1024) k_build_csr_small(const int* __restrict__ key, const int* __restrict__ val,
-                                                          const int* __restrict__ E_dev, int cap_E,
-                                                          const int* __restrict__ n_dev, int cap_n,
-                                                          int* __restrict__ off, int* __restrict__ out_val,
-                                                          int* __restrict__ tmp, float* __restrict__ dinv,
-                                                          int* __restrict__ nnz_out) {
-    __shared__ int s_cnt[SMALL_N];
-    __shared__ int s_off[SMALL_N + 1];
-    __shared__ int s_scan[34];
-    __shared__ int s_hub[64];
-    __shared__ int s_nhub;
-    const int E = min(*E_dev, cap_E);
-    const int n = min(min(*n_dev, cap_n), SMALL_N);
+struct CsrSmallSmem {
+    int cnt[SMALL_N];
+    int off[SMALL_N + 1];
+    int scan[34];
+    int hub[64];
+    int nhub;
+};
+
+// whole-CTA (1024 threads) CSR build of <= SMALL_N rows; key/val may have been written earlier by this CTA (no
+// read-only-cache loads).  Ends with all threads past the last shared-memory use except `sm` contents.
+__device__ void csr_small_build(const int* key, const int* val, int E, int n, int* off, int* out_val, int* tmp,
+                                float* dinv, int* nnz_out, CsrSmallSmem& sm) {
     const int tid = threadIdx.x;
-    for (int i = tid; i < n; i += 1024) s_cnt[i] = 0;
-    if (tid == 0) s_nhub = 0;
+    for (int i = tid; i < n; i += 1024) sm.cnt[i] = 0;
+    if (tid == 0) sm.nhub = 0;
     __syncthreads();
     for (int e = tid; e < E; e += 1024) {
         const int k = key[e];
-        if (k != val[e]) atomicAdd(&s_cnt[k], 1);
+        if (k != val[e]) atomicAdd(&sm.cnt[k], 1);
     }
     __syncthreads();
     int carry = 0;
     for (int base = 0; base < n; base += 1024) {
         const int i = base + tid;
-        const int c = (i < n) ? s_cnt[i] : 0;
+        const int c = (i < n) ? sm.cnt[i] : 0;
         int total;
-        const int ex = block_scan_excl<int>(c, s_scan, &total);
+        const int ex = block_scan_excl<int>(c, sm.scan, &total);
         if (i < n) {
-            s_off[i] = carry + ex;
+            sm.off[i] = carry + ex;
             off[i] = carry + ex;
             if (dinv) dinv[i] = 1.0f / sqrtf((float)(c + 1));
         }
         carry += total;
     }
-    if (tid == 0) { s_off[n] = carry; off[n] = carry; if (nnz_out) *nnz_out = carry; }
+    if (tid == 0) { sm.off[n] = carry; off[n] = carry; if (nnz_out) *nnz_out = carry; }
     __syncthreads();
     for (int e = tid; e < E; e += 1024) {
         const int k = key[e], v = val[e];
-        if (k != v) out_val[s_off[k] + atomicSub(&s_cnt[k], 1) - 1] = v;
+        if (k != v) out_val[sm.off[k] + atomicSub(&sm.cnt[k], 1) - 1] = v;
     }
     __syncthreads();
     for (int j = tid; j < n; j += 1024) {
-        const int beg = s_off[j], len = s_off[j + 1] - beg;
+        const int beg = sm.off[j], len = sm.off[j + 1] - beg;
         if (len < 2) continue;
         if (len > 64) {
-            const int slot = atomicAdd(&s_nhub, 1);
-            if (slot < 64) { s_hub[slot] = j; continue; }         // > 64 hub rows: fall through to the slow exact path
+            const int slot = atomicAdd(&sm.nhub, 1);
+            if (slot < 64) { sm.hub[slot] = j; continue; }        // > 64 hub rows: fall through to the slow exact path
         }
         int* a = out_val + beg;
         for (int i = 1; i < len; ++i) {
@@ -391,10 +390,10 @@ __global__ void __launch_bounds__(1024) k_build_csr_small(const int* __restrict_
         }
     }
     __syncthreads();
-    const int nh = min(s_nhub, 64);
+    const int nh = min(sm.nhub, 64);
     for (int h = 0; h < nh; ++h) {                                // whole-block rank sort of each hub row
-        const int j = s_hub[h];
-        const int beg = s_off[j], len = s_off[j + 1] - beg;
+        const int j = sm.hub[h];
+        const int beg = sm.off[j], len = sm.off[j + 1] - beg;
         const int* a = out_val + beg;
         for (int i = tid; i < len; i += 1024) {
             const int x = a[i];
@@ -406,6 +405,58 @@ __global__ void __launch_bounds__(1024) k_build_csr_small(const int* __restrict_
         for (int i = tid; i < len; i += 1024) out_val[beg + i] = tmp[beg + i];
         __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(1024) k_build_csr_small(const int* key, const int* val, const int* __restrict__ E_dev,
+                                                          int cap_E, const int* __restrict__ n_dev, int cap_n, int* off,
+                                                          int* out_val, int* tmp, float* dinv, int* nnz_out) {
+    __shared__ CsrSmallSmem sm;
+    const int E = min(*E_dev, cap_E);
+    const int n = min(min(*n_dev, cap_n), SMALL_N);
+    csr_small_build(key, val, E, n, off, out_val, tmp, dinv, nnz_out, sm);
+}
+
+// ---------------------------------------------------------------------------------------
+// k_cls_prep: everything between "all_nodes is ranked" and "the classifier can run" in ONE CTA (main.py:252-257):
+// local ids of the targets (main.py:259), relabel of the two induced blocks GCN.forward consumes (layer 1 <-
+// edge_indices[-1], layer 2 <- edge_indices[0]; gcn.py:30-36), their dst-sorted CSRs + deg^-1/2 (gcn_norm) and the
+// src-sorted CSR of the layer-2 block for the backward.  The sampled subgraph has <= SMALL_N nodes.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_cls_prep(
+    const uint32_t* __restrict__ bm, const int* __restrict__ pref, const int* __restrict__ A_dev, int cap_A,
+    const int* __restrict__ targets, const int* __restrict__ B_dev, int cap_B, int* target_local,
+    const int* __restrict__ blk0_src, const int* __restrict__ blk0_dst, const int* __restrict__ E0_dev,
+    const int* __restrict__ blk1_src, const int* __restrict__ blk1_dst, const int* __restrict__ E1_dev, int cap_blk,
+    int* cl_src0, int* cl_dst0, int* cl_src1, int* cl_dst1, int* in_off0, int* in_src0, float* dinv0, int* in_off1,
+    int* in_src1, float* dinv1, int* out_off1, int* out_dst1, int* tmp, int* nnz_out3, int* tgt_of_row) {
+    __shared__ CsrSmallSmem sm;
+    const int tid = threadIdx.x;
+    const int A = min(min(*A_dev, cap_A), SMALL_N);
+    const int B = min(*B_dev, cap_B);
+    const int E0 = min(*E0_dev, cap_blk), E1 = min(*E1_dev, cap_blk);
+    if (tgt_of_row) {
+        for (int i = tid; i < A; i += 1024) tgt_of_row[i] = -1;
+        __syncthreads();
+    }
+    for (int i = tid; i < B; i += 1024) {
+        const int loc = bitmap_rank(bm, pref, targets[i]);
+        target_local[i] = loc;
+        if (tgt_of_row) tgt_of_row[loc] = i;
+    }
+    for (int e = tid; e < E0; e += 1024) {
+        cl_src0[e] = bitmap_rank(bm, pref, blk0_src[e]);
+        cl_dst0[e] = bitmap_rank(bm, pref, blk0_dst[e]);
+    }
+    for (int e = tid; e < E1; e += 1024) {
+        cl_src1[e] = bitmap_rank(bm, pref, blk1_src[e]);
+        cl_dst1[e] = bitmap_rank(bm, pref, blk1_dst[e]);
+    }
+    __syncthreads();                                              // this CTA's global writes are visible to itself
+    csr_small_build(cl_dst0, cl_src0, E0, A, in_off0, in_src0, tmp, dinv0, nnz_out3 + 0, sm);
+    __syncthreads();
+    csr_small_build(cl_dst1, cl_src1, E1, A, in_off1, in_src1, tmp, dinv1, nnz_out3 + 1, sm);
+    __syncthreads();
+    csr_small_build(cl_src1, cl_dst1, E1, A, out_off1, out_dst1, tmp, nullptr, nnz_out3 + 2, sm);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -614,6 +665,27 @@ int grapes_build_csr(grapes_ctx* ctx, const int* key, const int* val, const int*
     k_fill<<<grid_for(ctx, cap_E, 256), 256, 0, s>>>(key, val, E_dev, cap_E, off, cnt_scratch, sorted_val);
     grapes_count_launches(1);
     k_sort_rows<<<grid_for(ctx, cap_n, 256), 256, 0, s>>>(off, n_dev, cap_n, sorted_val, tmp_val);
+    grapes_count_launches(1);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+int grapes_classifier_prep(grapes_ctx* ctx, const uint32_t* bm_all, const int* pref_all, const int* A_dev, int cap_A,
+                           const int* targets, const int* B_dev, int cap_B, int* target_local, const int* blk0_src,
+                           const int* blk0_dst, const int* E0_dev, const int* blk1_src, const int* blk1_dst,
+                           const int* E1_dev, int cap_blk, int* cl_src0, int* cl_dst0, int* cl_src1, int* cl_dst1,
+                           int* in_off0, int* in_src0, float* dinv0, int* in_off1, int* in_src1, float* dinv1,
+                           int* out_off1, int* out_dst1, int* tmp, int* nnz_dev3, int* tgt_of_row, void* stream) {
+    GRAPES_REQUIRE(ctx && bm_all && pref_all && A_dev && targets && B_dev && target_local && blk0_src && blk0_dst &&
+                       E0_dev && blk1_src && blk1_dst && E1_dev && cl_src0 && cl_dst0 && cl_src1 && cl_dst1 && in_off0 &&
+                       in_src0 && dinv0 && in_off1 && in_src1 && dinv1 && out_off1 && out_dst1 && tmp && nnz_dev3,
+                   "null argument");
+    GRAPES_REQUIRE(cap_A <= SMALL_N, "sampled subgraph too large for the single-CTA preparation");
+    k_cls_prep<<<1, 1024, 0, (cudaStream_t)stream>>>(bm_all, pref_all, A_dev, cap_A, targets, B_dev, cap_B, target_local,
+                                                      blk0_src, blk0_dst, E0_dev, blk1_src, blk1_dst, E1_dev, cap_blk,
+                                                      cl_src0, cl_dst0, cl_src1, cl_dst1, in_off0, in_src0, dinv0,
+                                                      in_off1, in_src1, dinv1, out_off1, out_dst1, tmp, nnz_dev3,
+                                                      tgt_of_row);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;

@@ -95,6 +95,113 @@ __global__ void __launch_bounds__(LOSS_THREADS) k_loss_final(const float* __rest
     if (threadIdx.x == 0) *loss_out = loss;
 }
 
+// ---------------------------------------------------------------------------------------
+// Row-parallel classifier loss (main.py:260-261).  k_loss_rows2: one warp per row of the sampled subgraph; a target
+// row (tgt_of_row[row] = r >= 0) gets its CrossEntropy / BCE term and gradient, every row the
+// reg_param * var(logits) term, other rows zeros -- so dlogits needs no memset.  Each block also leaves the column
+// sums of its rows in colpart[block][C].  k_loss_final2 (one CTA) adds the A row terms and the per-block column
+// sums (= gradient of the last layer's bias) in a fixed order.
+// ---------------------------------------------------------------------------------------
+#define LR2_WARPS 8
+__global__ void __launch_bounds__(LR2_WARPS * 32) k_loss_rows2(
+    const float* __restrict__ logits, int ldl, int C, const int* __restrict__ A_dev, int A_cap,
+    const int* __restrict__ tgt_of_row, const int* __restrict__ targets, int B,
+    const int64_t* __restrict__ labels_i64, const float* __restrict__ labels_f32, float reg_param,
+    float* __restrict__ dlogits, float* __restrict__ row_loss, float* __restrict__ colpart) {
+    extern __shared__ float s_cols[];                    // [LR2_WARPS][C]
+    const int A = min(*A_dev, A_cap);
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const int row = blockIdx.x * LR2_WARPS + warp;
+    float* mycols = s_cols + warp * C;
+    for (int c = lane; c < C; c += 32) mycols[c] = 0.f;
+    if (row < A) {
+        const float* lr = logits + (size_t)row * ldl;
+        float* dr = dlogits + (size_t)row * ldl;
+        const int r = tgt_of_row[row];
+        float loss = 0.f;
+        if (r >= 0 && labels_i64) {
+            const float invB = 1.0f / (float)B;
+            const int y = (int)labels_i64[targets[r]];
+            float mx = -INFINITY;
+            for (int c = lane; c < C; c += 32) mx = fmaxf(mx, lr[c]);
+            mx = warp_max(mx);
+            float se = 0.f;
+            for (int c = lane; c < C; c += 32) se += expf(lr[c] - mx);
+            se = warp_sum(se);
+            const float lse = mx + logf(se);
+            for (int c = lane; c < C; c += 32) mycols[c] = (expf(lr[c] - lse) - (c == y ? 1.f : 0.f)) * invB;
+            loss = (lse - lr[y]) * invB;
+        } else if (r >= 0) {
+            const float inv = 1.0f / ((float)B * (float)C);
+            const float* yr = labels_f32 + (size_t)targets[r] * C;
+            float a = 0.f;
+            for (int c = lane; c < C; c += 32) {
+                const float l = lr[c], y = yr[c];
+                a += (1.0f - y) * l + fmaxf(-l, 0.f) + log1pf(expf(-fabsf(l)));
+                mycols[c] = (1.0f / (1.0f + expf(-l)) - y) * inv;
+            }
+            loss = warp_sum(a) * inv;
+        }
+        if (reg_param != 0.f && C > 1) {                 // reg_param * var(logits[row], unbiased)
+            const float invc1 = 1.0f / (float)(C - 1);
+            float sm = 0.f;
+            for (int c = lane; c < C; c += 32) sm += lr[c];
+            const float mean = warp_sum(sm) / (float)C;
+            float sq = 0.f;
+            for (int c = lane; c < C; c += 32) {
+                const float d = lr[c] - mean;
+                sq = fmaf(d, d, sq);
+                mycols[c] += reg_param * 2.0f * d * invc1;
+            }
+            loss += reg_param * warp_sum(sq) * invc1;
+        }
+        __syncwarp();
+        for (int c = lane; c < C; c += 32) dr[c] = mycols[c];
+        if (lane == 0) row_loss[row] = loss;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < LR2_WARPS; ++w) a += s_cols[w * C + c];
+        colpart[(size_t)blockIdx.x * C + c] = a;
+    }
+}
+
+__global__ void __launch_bounds__(LOSS_THREADS) k_loss_final2(const int* __restrict__ A_dev, int A_cap, int C,
+                                                              const float* __restrict__ row_loss,
+                                                              const float* __restrict__ colpart, int nblocks,
+                                                              float* loss_out, float* __restrict__ colsum_out) {
+    __shared__ float s[32];
+    __shared__ float s_col[LOSS_THREADS];
+    const int A = min(*A_dev, A_cap);
+    float part = 0.f;
+    for (int r = threadIdx.x; r < A; r += LOSS_THREADS) part += row_loss[r];
+    const float loss = block_sum_1024(part, s);
+    if (threadIdx.x == 0) *loss_out = loss;
+    if (!colsum_out) return;
+    const int used = (A + LR2_WARPS - 1) / LR2_WARPS;    // blocks that own rows; the rest wrote zeros
+    const int nb = min(nblocks, used);
+    const int groups = max(1, LOSS_THREADS / C);
+    const int g = threadIdx.x / C, c = threadIdx.x % C;
+    float a = 0.f;
+    if (g < groups)
+        for (int b0 = g; b0 < nb; b0 += 8 * groups) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int b = b0 + u * groups; v[u] = (b < nb) ? colpart[(size_t)b * C + c] : 0.f; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a += v[u];
+        }
+    s_col[threadIdx.x] = a;
+    __syncthreads();
+    if ((int)threadIdx.x < C) {
+        float t = 0.f;
+        for (int gg = 0; gg < groups; ++gg) t += s_col[gg * C + threadIdx.x];
+        colsum_out[threadIdx.x] = t;
+    }
+}
+
 // scal layout (float): see GRAPES_SCAL_* in the header.
 //   TB       : loss_gfn = (log_z + tot + coef*loss_c)^2 ; d/dtheta = 2(...) * (dlog_z + dtot)      main.py:282
 //   REINFORCE: loss_gfn = -tot * loss_c                 ; d/dtheta = -loss_c * dtot               main.py:279
@@ -145,6 +252,71 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float
     }
 }
 __global__ void k_step_inc(float* step) { *step += 1.0f; }
+// finalize + scale in one launch: every block recomputes the scalar from the (read-only) inputs of `scal`, block 0
+// publishes the derived scalars; grad = g * direction for the gcn_gf and gcn_z parameter ranges.
+__global__ void __launch_bounds__(256) k_gfn_finalize_scale(float* scal, float loss_coef, float log_z_init, int reinforce,
+                                                            int have_log_z, const float* __restrict__ dir_gf, int n_gf,
+                                                            float* __restrict__ grad_gf,
+                                                            const float* __restrict__ dir_z, int n_z,
+                                                            float* __restrict__ grad_z) {
+    const float loss_c = scal[GRAPES_SCAL_LOSS_C];
+    const float tot = scal[GRAPES_SCAL_TOT_LOG_PROB];
+    const float log_z = have_log_z ? scal[GRAPES_SCAL_LOG_Z_MEAN] - log_z_init : 0.f;
+    float loss_gfn, g_gf, g_z;
+    if (reinforce) { loss_gfn = -tot * loss_c; g_gf = -loss_c; g_z = 0.f; }
+    else { const float r = log_z + tot + loss_coef * loss_c; loss_gfn = r * r; g_gf = 2.0f * r; g_z = 2.0f * r; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        scal[GRAPES_SCAL_LOG_Z] = log_z;
+        scal[GRAPES_SCAL_LOSS_GFN] = loss_gfn;
+        scal[GRAPES_SCAL_G_GF] = g_gf;
+        scal[GRAPES_SCAL_G_Z] = g_z;
+    }
+    const int tot_n = n_gf + n_z;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tot_n; i += gridDim.x * blockDim.x) {
+        if (i < n_gf) grad_gf[i] = g_gf * dir_gf[i];
+        else grad_z[i - n_gf] = g_z * dir_z[i - n_gf];
+    }
+}
+
+// Two Adam parameter groups (optimizer_c, optimizer_gf: main.py:117-118) in one launch.  Every block reads the step
+// counts before anyone changes them; the last block to finish increments both (threadfence + ticket), so no
+// separate increment launch is needed.
+__global__ void __launch_bounds__(256) k_adam2(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                               float* __restrict__ v, int off0, int n0, float lr0, int off1, int n1,
+                                               float lr1, float beta1, float beta2, float eps, float* steps,
+                                               unsigned int* ticket) {
+    __shared__ float s_step_size[2], s_bc2_sqrt[2];
+    __shared__ int s_last;
+    if (threadIdx.x < 2) {
+        const double t = (double)steps[threadIdx.x] + 1.0;
+        const double bc1 = 1.0 - pow((double)beta1, t), bc2 = 1.0 - pow((double)beta2, t);
+        s_step_size[threadIdx.x] = (float)((double)(threadIdx.x ? lr1 : lr0) / bc1);
+        s_bc2_sqrt[threadIdx.x] = (float)sqrt(bc2);
+    }
+    __syncthreads();
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n0 + n1; t += gridDim.x * blockDim.x) {
+        const int grp = t < n0 ? 0 : 1;
+        const int i = grp ? off1 + (t - n0) : off0 + t;
+        const float gi = g[i];
+        const float mi = m[i] + (gi - m[i]) * (1.0f - beta1);          // exp_avg.lerp_(grad, 1-beta1)
+        const float vi = v[i] * beta2 + (1.0f - beta2) * gi * gi;      // mul_(beta2).addcmul_(g, g, 1-beta2)
+        m[i] = mi; v[i] = vi;
+        const float denom = sqrtf(vi) / s_bc2_sqrt[grp] + eps;
+        p[i] = p[i] - s_step_size[grp] * (mi / denom);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        if (n0 > 0) steps[0] += 1.0f;
+        if (n1 > 0) steps[1] += 1.0f;
+        *ticket = 0u;
+    }
+}
+
 __global__ void __launch_bounds__(256) k_fill_f32(float* p, float v, int n) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
 }
@@ -159,12 +331,27 @@ static inline int grid_for(const grapes_ctx* ctx, long long work, int threads, i
 extern "C" {
 
 int grapes_classifier_loss(grapes_ctx* ctx, const float* logits, int ldl, int C, const int* A_dev, int A_cap,
-                           const int* row_ids, const int* targets, int B, const int64_t* labels_i64,
-                           const float* labels_f32, float reg_param, float* dlogits, float* loss_out, void* stream) {
+                           const int* row_ids, const int* tgt_of_row, const int* targets, int B, const int64_t* labels_i64,
+                           const float* labels_f32, float reg_param, float* dlogits, float* loss_out,
+                           float* colsum_out, void* stream) {
     GRAPES_REQUIRE(ctx && logits && A_dev && row_ids && targets && dlogits && loss_out, "null argument");
     GRAPES_REQUIRE((labels_i64 != nullptr) != (labels_f32 != nullptr), "exactly one label array");
     GRAPES_REQUIRE(B > 0 && C > 0, "bad shape");
     cudaStream_t s = (cudaStream_t)stream;
+    if (tgt_of_row && C <= LOSS_THREADS) {
+        const int nblocks = grapes_div_up(A_cap, LR2_WARPS);
+        GRAPES_REQUIRE(((size_t)A_cap + (size_t)nblocks * C) * sizeof(float) <= ctx->partials_bytes, "partial buffer too small");
+        float* row_loss = ctx->partials;
+        float* colpart = ctx->partials + A_cap;
+        k_loss_rows2<<<nblocks, LR2_WARPS * 32, LR2_WARPS * C * sizeof(float), s>>>(
+            logits, ldl, C, A_dev, A_cap, tgt_of_row, targets, B, labels_i64, labels_f32, reg_param, dlogits, row_loss,
+            colpart);
+        grapes_count_launches(1);
+        k_loss_final2<<<1, LOSS_THREADS, 0, s>>>(A_dev, A_cap, C, row_loss, colpart, nblocks, loss_out, colsum_out);
+        grapes_count_launches(1);
+        GRAPES_LAUNCH_OK();
+        return GRAPES_OK;
+    }
     GRAPES_CUDA_OK(cudaMemsetAsync(dlogits, 0, sizeof(float) * (size_t)A_cap * ldl, s));
     GRAPES_REQUIRE((size_t)B * sizeof(float) <= ctx->partials_bytes, "partial buffer too small");
     k_loss_rows<<<grapes_div_up((long long)B * 32, 256), 256, 0, s>>>(logits, ldl, C, row_ids, targets, B, labels_i64,
@@ -174,6 +361,7 @@ int grapes_classifier_loss(grapes_ctx* ctx, const float* logits, int ldl, int C,
                                             loss_out);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
+    if (colsum_out) return grapes_colsum(ctx, dlogits, A_dev, A_cap, ldl, C, 1.0f, 0, colsum_out, stream);
     return GRAPES_OK;
 }
 
@@ -204,6 +392,30 @@ int grapes_adam_step(grapes_ctx* ctx, float* params, const float* grads, float* 
                                                  step_dev);
     grapes_count_launches(1);
     if (increment_step) k_step_inc<<<1, 1, 0, s>>>(step_dev);
+    grapes_count_launches(1);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+int grapes_gfn_finalize_scale(grapes_ctx* ctx, float* scal, float loss_coef, float log_z_init, int reinforce,
+                              int have_log_z, const float* dir_gf, int n_gf, float* grad_gf, const float* dir_z,
+                              int n_z, float* grad_z, void* stream) {
+    GRAPES_REQUIRE(ctx && scal && dir_gf && grad_gf && (n_z == 0 || (dir_z && grad_z)), "null argument");
+    k_gfn_finalize_scale<<<grid_for(ctx, n_gf + n_z, 256), 256, 0, (cudaStream_t)stream>>>(
+        scal, loss_coef, log_z_init, reinforce, have_log_z, dir_gf, n_gf, grad_gf, dir_z, n_z, grad_z);
+    grapes_count_launches(1);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+int grapes_adam_step2(grapes_ctx* ctx, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                      int off0, int n0, float lr0, int off1, int n1, float lr1, float beta1, float beta2, float eps,
+                      float* steps_dev, void* stream) {
+    GRAPES_REQUIRE(ctx && params && grads && exp_avg && exp_avg_sq && steps_dev, "null argument");
+    GRAPES_REQUIRE(n0 >= 0 && n1 >= 0 && n0 + n1 > 0, "empty parameter groups");
+    k_adam2<<<grid_for(ctx, n0 + n1, 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, off0, n0,
+                                                                           lr0, off1, n1, lr1, beta1, beta2, eps,
+                                                                           steps_dev, ctx->scan_counters + 2);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;

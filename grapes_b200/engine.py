@@ -123,7 +123,7 @@ class GrapesEngine:
         self.multi_stream = bool(multi_stream)
         if self.multi_stream:
             self.side_a, self.side_b = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-            self.ctx_a, self.ctx_b = graph.new_ctx(), graph.new_ctx(1 << 20)
+            self.ctx_a, self.ctx_b = graph.new_ctx(), graph.new_ctx(16 << 20)
         else:
             self.side_a = self.side_b = None
             self.ctx_a = self.ctx_b = graph.ctx
@@ -233,6 +233,7 @@ class GrapesEngine:
         A = self.cap_A
         self.all_nodes = e(A, **i32)
         self.target_local = e(self.B, **i32)
+        self.tgt_of_row = e(A, **i32)
         self.cl_src = [e(self.cap_blk, **i32) for _ in range(2)]      # [0]: layer-1 block (last hop), [1]: layer-2 block (hop 0)
         self.cl_dst = [e(self.cap_blk, **i32) for _ in range(2)]
         self.cl_in_off = [z(A + 1, **i32) for _ in range(2)]
@@ -430,22 +431,34 @@ class GrapesEngine:
         L.tag = "[cls]"
         L.grapes_rank_nodes(ctx, ptr(self.bm_all), None, ptr(self.pref_all), None, ptr(self.all_nodes), None, None,
                             None, None, None, 0, 0, self.cap_A, self._cnt("A"), None, ovf, st)
-        L.grapes_relabel(ctx, ptr(self.targets), self._cnt("B"), B, ptr(self.bm_all), ptr(self.pref_all),
-                         ptr(self.target_local), st)
         # GCN.forward with a per-layer list: hidden layer <- edge_indices[-1], last layer <- edge_indices[0] (gcn.py:30-36)
-        for slot, hop in ((0, H - 1), (1, 0)):
-            bw = self.hops[hop]
-            L.grapes_relabel(ctx, ptr(bw.blk_src), self._hc(hop, "blk"), self.cap_blk, ptr(self.bm_all),
-                             ptr(self.pref_all), ptr(self.cl_src[slot]), st)
-            L.grapes_relabel(ctx, ptr(bw.blk_dst), self._hc(hop, "blk"), self.cap_blk, ptr(self.bm_all),
-                             ptr(self.pref_all), ptr(self.cl_dst[slot]), st)
-            L.grapes_build_csr(ctx, ptr(self.cl_dst[slot]), ptr(self.cl_src[slot]), self._hc(hop, "blk"),
-                               self.cap_blk, self._cnt("A"), self.cap_A, ptr(self.cnt_scratch), 0,
-                               ptr(self.cl_in_off[slot]), ptr(self.cl_in_src[slot]), ptr(self.cl_tmp),
-                               ptr(self.cl_dinv[slot]), self._cnt("cl_nnz", slot), ovf, st)
-        L.grapes_build_csr(ctx, ptr(self.cl_src[1]), ptr(self.cl_dst[1]), self._hc(0, "blk"), self.cap_blk,
-                           self._cnt("A"), self.cap_A, ptr(self.cnt_scratch), 0, ptr(self.cl_out_off),
-                           ptr(self.cl_out_dst), ptr(self.cl_tmp), None, self._cnt("cl_nnz", 2), ovf, st)
+        b0, b1 = self.hops[H - 1], self.hops[0]
+        if self.cap_A <= 4096:
+            L.grapes_classifier_prep(ctx, ptr(self.bm_all), ptr(self.pref_all), self._cnt("A"), self.cap_A,
+                                     ptr(self.targets), self._cnt("B"), B, ptr(self.target_local),
+                                     ptr(b0.blk_src), ptr(b0.blk_dst), self._hc(H - 1, "blk"),
+                                     ptr(b1.blk_src), ptr(b1.blk_dst), self._hc(0, "blk"), self.cap_blk,
+                                     ptr(self.cl_src[0]), ptr(self.cl_dst[0]), ptr(self.cl_src[1]), ptr(self.cl_dst[1]),
+                                     ptr(self.cl_in_off[0]), ptr(self.cl_in_src[0]), ptr(self.cl_dinv[0]),
+                                     ptr(self.cl_in_off[1]), ptr(self.cl_in_src[1]), ptr(self.cl_dinv[1]),
+                                     ptr(self.cl_out_off), ptr(self.cl_out_dst), ptr(self.cl_tmp),
+                                     self._cnt("cl_nnz"), ptr(self.tgt_of_row), st)
+        else:
+            L.grapes_relabel(ctx, ptr(self.targets), self._cnt("B"), B, ptr(self.bm_all), ptr(self.pref_all),
+                             ptr(self.target_local), st)
+            for slot, hop in ((0, H - 1), (1, 0)):
+                bw = self.hops[hop]
+                L.grapes_relabel(ctx, ptr(bw.blk_src), self._hc(hop, "blk"), self.cap_blk, ptr(self.bm_all),
+                                 ptr(self.pref_all), ptr(self.cl_src[slot]), st)
+                L.grapes_relabel(ctx, ptr(bw.blk_dst), self._hc(hop, "blk"), self.cap_blk, ptr(self.bm_all),
+                                 ptr(self.pref_all), ptr(self.cl_dst[slot]), st)
+                L.grapes_build_csr(ctx, ptr(self.cl_dst[slot]), ptr(self.cl_src[slot]), self._hc(hop, "blk"),
+                                   self.cap_blk, self._cnt("A"), self.cap_A, ptr(self.cnt_scratch), 0,
+                                   ptr(self.cl_in_off[slot]), ptr(self.cl_in_src[slot]), ptr(self.cl_tmp),
+                                   ptr(self.cl_dinv[slot]), self._cnt("cl_nnz", slot), ovf, st)
+            L.grapes_build_csr(ctx, ptr(self.cl_src[1]), ptr(self.cl_dst[1]), self._hc(0, "blk"), self.cap_blk,
+                               self._cnt("A"), self.cap_A, ptr(self.cnt_scratch), 0, ptr(self.cl_out_off),
+                               ptr(self.cl_out_dst), ptr(self.cl_tmp), None, self._cnt("cl_nnz", 2), ovf, st)
         nc = self.net_c
         ldYc = self.Yc.shape[1]
         A_dev, cap_A = self._cnt("A"), self.cap_A
@@ -458,29 +471,34 @@ class GrapesEngine:
         L.grapes_aggregate(ctx, ptr(self.Zc), C, C, None, A_dev, cap_A, ptr(self.cl_in_off[1]),
                            ptr(self.cl_in_src[1]), ptr(self.cl_dinv[1]), None, 0, self._par(nc.b2), 0,
                            ptr(self.logits_c), C, None, None, -1, st)
+        # loss + d loss / d logits + d loss / d b2 (column sums) in one launch (main.py:260-261)
         L.grapes_classifier_loss(ctx, ptr(self.logits_c), C, C, A_dev, cap_A, ptr(self.target_local),
-                                 ptr(self.targets), B, None if self.multilabel else ptr(self.y),
+                                 ptr(self.tgt_of_row) if self.cap_A <= 4096 else None, ptr(self.targets), B, None if self.multilabel else ptr(self.y),
                                  ptr(self.y) if self.multilabel else None, self.reg_param, ptr(self.dlogits),
-                                 self._scal("loss_c"), st)
-        # backward of the classifier (loss_c.backward(), main.py:267)
-        L.grapes_colsum(ctx, ptr(self.dlogits), A_dev, cap_A, C, C, 1.0, 0, self._grd(nc.b2), st)
+                                 self._scal("loss_c"), self._grd(nc.b2), st)
+        # backward of the classifier (loss_c.backward(), main.py:267); the two weight-gradient products that nothing
+        # else waits for run on side B next to the chain dZ -> dpre1 -> dW1
         L.grapes_aggregate(ctx, ptr(self.dlogits), C, C, None, A_dev, cap_A, ptr(self.cl_out_off),
                            ptr(self.cl_out_dst), ptr(self.cl_dinv[1]), None, 0, None, 0, ptr(self.dZ), C, None, None, -1, st)
-        L.grapes_gemm_tn(ctx, ptr(self.dZ), C, ptr(self.out1), D, A_dev, cap_A, C, D, 1.0, 0, self._grd(nc.W2), st)
+        fork(sB)
+        with on(sB):
+            L.grapes_gemm_tn(ctx_b, ptr(self.dZ), C, ptr(self.out1), D, A_dev, cap_A, C, D, 1.0, 0, self._grd(nc.W2), stB)
         L.grapes_gemm(ctx, 1, ptr(self.dZ), C, self._par(nc.W2), D, ptr(self.dpre1), D, A_dev, cap_A, D, C, None, 0,
                       ptr(self.out1), D, st)
-        L.grapes_colsum(ctx, ptr(self.dpre1), A_dev, cap_A, D, D, 1.0, 0, self._grd(nc.b1), st)
+        fork(sB)
+        with on(sB):
+            L.grapes_colsum(ctx_b, ptr(self.dpre1), A_dev, cap_A, D, D, 1.0, 0, self._grd(nc.b1), stB)
         L.grapes_gemm_tn(ctx, ptr(self.dpre1), D, ptr(self.Yc), ldYc, A_dev, cap_A, D, F, 1.0, 0, self._grd(nc.W1),
                          st)
         L.tag = ""
-        # ---- GFlowNet / REINFORCE loss (main.py:271-291) ----
+        # ---- GFlowNet / REINFORCE loss (main.py:271-291): loss, gradient scale, scaled directions in one launch ----
+        join(sB)
         join(sA)
         if not self.random_sampling:
-            L.grapes_gfn_finalize(ctx, ptr(self.scal), self.loss_coef, self.log_z_init, int(self.reinforce), 1, st)
-            L.grapes_scale_by_device_scalar(ctx, self._dir(gf.base), self._scal("g_gf"), gf.size,
-                                            self._grd(gf.base), st)
-            L.grapes_scale_by_device_scalar(ctx, self._dir(nz.base), self._scal("g_z"), nz.size,
-                                            self._grd(nz.base), st)
+            n_z = 0 if self.reinforce else nz.size
+            L.grapes_gfn_finalize_scale(ctx, ptr(self.scal), self.loss_coef, self.log_z_init, int(self.reinforce), 1,
+                                        self._dir(gf.base), gf.size, self._grd(gf.base),
+                                        self._dir(nz.base), n_z, self._grd(nz.base), st)
         if apply_optim:
             self._enqueue_optim()
 
@@ -545,16 +563,17 @@ class GrapesEngine:
                             self.ldW, st)
 
     def _enqueue_optim(self):
+        """optimizer_c.step() and optimizer_gf.step() (main.py:268,289) as one launch over the flat buffers."""
         L, ctx = self.L, self.g.ctx
         st = torch.cuda.current_stream().cuda_stream
         nc, gf, nz = self.net_c, self.net_gf, self.net_z
-        ea, es = self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
-        L.grapes_adam_step(ctx, self._par(nc.base), self._grd(nc.base), ea + 4 * nc.base, es + 4 * nc.base, nc.size,
-                           self.lr_gc, 0.9, 0.999, 1e-8, self.adam_steps.data_ptr(), 1, st)
-        if not self.random_sampling:
-            n = (nz.end - gf.base) if not self.reinforce else gf.size   # gcn_z has no grad under REINFORCE (main.py:279)
-            L.grapes_adam_step(ctx, self._par(gf.base), self._grd(gf.base), ea + 4 * gf.base, es + 4 * gf.base, n,
-                               self.lr_gf, 0.9, 0.999, 1e-8, self.adam_steps.data_ptr() + 4, 1, st)
+        if self.random_sampling:
+            n1 = 0
+        else:
+            n1 = (nz.end - gf.base) if not self.reinforce else gf.size   # gcn_z has no grad under REINFORCE (main.py:279)
+        L.grapes_adam_step2(ctx, ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                            nc.base, nc.size, self.lr_gc, gf.base, n1, self.lr_gf, 0.9, 0.999, 1e-8,
+                            ptr(self.adam_steps), st)
 
     # ------------------------------------------------------------------ public API
     def set_targets(self, target_nodes: torch.Tensor):

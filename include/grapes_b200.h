@@ -105,6 +105,16 @@ int grapes_relabel(grapes_ctx* ctx, const int* ids, const int* count_dev, int ca
 int grapes_slice_block(grapes_ctx* ctx, const int* rows, const int* e_row, const int* e_col, const int* m_dev,
                        int cap_m, const uint32_t* bm_cols, int* out_src, int* out_dst, int cap_out, int* count_dev,
                        int* overflow, void* stream);
+/* main.py:252-259 + gcn.py:30-36 for a sampled subgraph of <= 4096 nodes, in one launch: local ids of the targets,
+ * relabel of the layer-1 block (blk0 = edge_indices[-1]) and the layer-2 block (blk1 = edge_indices[0]), their
+ * dst-sorted CSRs with deg^-1/2, and the src-sorted CSR of blk1 (classifier backward).  nnz_dev3[3] counts.
+ * tgt_of_row[cap_A] (optional) = index of the target sitting at that local row, or -1.                        */
+int grapes_classifier_prep(grapes_ctx* ctx, const uint32_t* bm_all, const int* pref_all, const int* A_dev, int cap_A,
+                           const int* targets, const int* B_dev, int cap_B, int* target_local, const int* blk0_src,
+                           const int* blk0_dst, const int* E0_dev, const int* blk1_src, const int* blk1_dst,
+                           const int* E1_dev, int cap_blk, int* cl_src0, int* cl_dst0, int* cl_src1, int* cl_dst1,
+                           int* in_off0, int* in_src0, float* dinv0, int* in_off1, int* in_src1, float* dinv1,
+                           int* out_off1, int* out_dst1, int* tmp, int* nnz_dev3, int* tgt_of_row, void* stream);
 int grapes_bitmap_set(grapes_ctx* ctx, const int* ids, const int* count_dev, int cap, uint32_t* bm, void* stream);
 int grapes_bitmap_clear_words(grapes_ctx* ctx, const int* ids, const int* count_dev, int cap, uint32_t* bm,
                               void* stream);
@@ -209,14 +219,26 @@ int grapes_select_topk(grapes_ctx* ctx, const float* logits_all, const int* nb_l
 
 /* ---- losses + optimiser (main.py:117-123,260-291) -------------------------------------------- */
 int grapes_classifier_loss(grapes_ctx* ctx, const float* logits, int ldl, int C, const int* A_dev, int A_cap,
-                           const int* row_ids, const int* targets, int B, const int64_t* labels_i64,
-                           const float* labels_f32, float reg_param, float* dlogits, float* loss_out, void* stream);
+                           const int* row_ids, const int* tgt_of_row /* optional inverse of row_ids (-1: not a target):
+                           enables the row-parallel 2-launch form */, const int* targets, int B, const int64_t* labels_i64,
+                           const float* labels_f32, float reg_param, float* dlogits, float* loss_out,
+                           float* colsum_out /* optional: column sums of dlogits = d loss / d last bias */,
+                           void* stream);
 int grapes_gfn_finalize(grapes_ctx* ctx, float* scal, float loss_coef, float log_z_init, int reinforce,
                         int have_log_z, void* stream);
+/* grapes_gfn_finalize + both grapes_scale_by_device_scalar calls (gcn_gf, gcn_z ranges) in one launch            */
+int grapes_gfn_finalize_scale(grapes_ctx* ctx, float* scal, float loss_coef, float log_z_init, int reinforce,
+                              int have_log_z, const float* dir_gf, int n_gf, float* grad_gf, const float* dir_z,
+                              int n_z, float* grad_z, void* stream);
 int grapes_scale_by_device_scalar(grapes_ctx* ctx, const float* dir, const float* g_dev, int n, float* grad,
                                   void* stream);
 int grapes_adam_step(grapes_ctx* ctx, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int n,
                      float lr, float beta1, float beta2, float eps, float* step_dev, int increment_step, void* stream);
+/* two Adam parameter groups (optimizer_c at off0, optimizer_gf at off1 of the flat buffers; main.py:117-118) in one
+ * launch; steps_dev[2] are the per-group step counts, incremented by the kernel itself                        */
+int grapes_adam_step2(grapes_ctx* ctx, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                      int off0, int n0, float lr0, int off1, int n1, float lr1, float beta1, float beta2, float eps,
+                      float* steps_dev, void* stream);
 int grapes_fill_f32(grapes_ctx* ctx, float* p, float value, int n, void* stream);
 
 #ifdef __cplusplus
