@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(KEYS_THREADS) k_logits_keys(
     const float* __restrict__ noise, const unsigned long long* __restrict__ rng_state,
     float* __restrict__ logits_all, float* __restrict__ lg_c, uint32_t* __restrict__ ukeys,
     float* __restrict__ keys_out, float* __restrict__ log_prob, float* __restrict__ dl_all,
-    uint8_t* __restrict__ mask_out, float* __restrict__ stat_part, int* bucket_hist) {
+    uint8_t* __restrict__ mask_out, float* __restrict__ stat_part) {
     __shared__ float s_red[KEYS_THREADS / 32];
     const int n = min(*n_dev, cap_n);
     const bool take_all = (k >= min(*c_dev, cap_n));          // utils.py:31-33: no noise is drawn
@@ -172,7 +172,6 @@ __global__ void __launch_bounds__(KEYS_THREADS) k_logits_keys(
         const uint32_t uk = float_to_ordered(key);
         ukeys[i] = uk;
         if (keys_out) keys_out[i] = key;
-        atomicAdd(&bucket_hist[key_bucket(uk)], 1);           // integer counts: order independent
         pmin = fminf(pmin, p); pmax = fmaxf(pmax, p);
         const float e = entropy_bits(p);
         esum += e; esq = fmaf(e, e, esq);
@@ -202,24 +201,26 @@ __device__ __forceinline__ void sel_stamp(int slot, int rank) {
     }
 }
 
+#define SEL_LOCAL_CAP 256            // members of the threshold bucket one CTA may hold before the radix fallback
+
 struct SelShared {
-    // CTA 0 (written by every CTA through DSMEM)
-    unsigned long long member[SEL_MEMBER_CAP];   // composites of the threshold bucket's members
+    int hist[SEL_BUCKETS];                       // this CTA's bucket histogram
+    int coarse[64];                              // sums of 32 consecutive buckets
+    unsigned long long member[SEL_LOCAL_CAP];    // this CTA's members of the threshold bucket (composites)
     int m_count;
-    unsigned long long thr_comp;                 // selected <=> composite >= thr_comp
-    int fallback;
-    int hist[256];                               // fallback radix pass: cluster-wide digit histogram
-    unsigned long long prefix;                   // fallback: composite bits fixed so far
-    int kr;                                      // fallback: rank left inside the prefix
-    // every CTA (each CTA publishes its totals to all)
+    // every CTA publishes its totals to all
     int sel_count[SEL_CTAS];
     float lp_delta[SEL_CTAS], dl_delta[SEL_CTAS];
+    // fallback radix select (CTA 0 holds the cluster-wide state)
+    int rhist[256];
+    unsigned long long prefix;
+    int kr;
 };
 
 __global__ void __cluster_dims__(SEL_CTAS, 1, 1) __launch_bounds__(SEL_THREADS, 1) k_select(
     const uint32_t* __restrict__ ukeys, const float* __restrict__ lg_c, const int* __restrict__ nb_local,
     const int* __restrict__ nb_nodes, const int* __restrict__ c_dev, int cap_c, int k, int mode,
-    unsigned long long* rng_state, const float* __restrict__ stat_part, int nstat, int* bucket_hist,
+    unsigned long long* rng_state, const float* __restrict__ stat_part, int nstat, int staged,
     int* __restrict__ sampled_out, int sampled_offset, int* __restrict__ s_dev, int* __restrict__ total_dev,
     uint8_t* __restrict__ mask_out, float* __restrict__ log_prob, float* tot_log_prob, float* __restrict__ stats,
     float* __restrict__ dl_all, float* sum_dl, uint32_t* bm_mark) {
@@ -229,10 +230,12 @@ __global__ void __cluster_dims__(SEL_CTAS, 1, 1) __launch_bounds__(SEL_THREADS, 
     __shared__ float s_red[SEL_WARPS];
     __shared__ long long s_scan[SEL_WARPS + 2];
     __shared__ int s_wcnt[SEL_THREADS];              // per (round, warp) selected counts of one super-round
-    __shared__ int s_lhist[256];                     // fallback: this CTA's digit histogram
-    __shared__ int s_bucket, s_above;
+    __shared__ int s_x[SEL_CTAS][64];                // exchanged coarse / fine counts
+    __shared__ unsigned long long s_all[SEL_CTAS * SEL_LOCAL_CAP];   // every CTA's members, gathered locally
+    __shared__ int s_lhist[256];
+    __shared__ int s_cb, s_above_c, s_bucket, s_above, s_fb;
     __shared__ unsigned long long s_thr;
-    __shared__ int s_fb;
+    extern __shared__ uint32_t s_keys[];             // staged: this CTA's keys
     SelShared* sh0 = cluster.map_shared_rank(&sh, 0);
     const int c = min(*c_dev, cap_c);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -240,25 +243,16 @@ __global__ void __cluster_dims__(SEL_CTAS, 1, 1) __launch_bounds__(SEL_THREADS, 
     const int chunk = (c + SEL_CTAS - 1) / SEL_CTAS;
     const int cb = min(c, rank * chunk), ce = min(c, cb + chunk);
     const int len = ce - cb;                         // CTA r owns the contiguous candidates [cb, ce)
+#define KEY(q) (staged ? s_keys[q] : ukeys[cb + (q)])
     sel_stamp(0, rank);
-    if (tid == 0) { sh.m_count = 0; sh.fallback = 0; sh.kr = k; sh.prefix = 0ull; sh.thr_comp = 0ull; }
-    if (tid < 256) sh.hist[tid] = 0;
+    if (tid == 0) { sh.m_count = 0; sh.kr = k; sh.prefix = 0ull; s_fb = 0; }
+    if (tid < 256) sh.rhist[tid] = 0;
 
     unsigned long long thr_comp = 0ull;              // take_all: everything is selected
     if (!take_all) {
-        // ---- 1. threshold bucket from the global histogram (every CTA, redundantly) ----
-        const int b0 = SEL_BUCKETS - 1 - 2 * tid;    // thread t owns buckets b0, b0-1 (descending order)
-        const int h0 = bucket_hist[b0], h1 = bucket_hist[b0 - 1];
-        long long total;
-        const int e0 = (int)block_scan_excl<long long>((long long)(h0 + h1), s_scan, &total);
-        const int e1 = e0 + h0, e2 = e1 + h1;
-        if (e0 < k && e1 >= k) { s_bucket = b0; s_above = e0; }
-        else if (e1 < k && e2 >= k) { s_bucket = b0 - 1; s_above = e1; }
-        cluster.sync();                              // all CTAs run (DSMEM is safe) and have read the histogram
-        sel_stamp(1, rank);
-        if (rank == 0) { bucket_hist[b0] = 0; bucket_hist[b0 - 1] = 0; }      // clean for the next launch
-        const int bucket = s_bucket, above = s_above;
-        // ---- 2. gather the bucket's members into CTA 0 ----
+        // ---- 1. this CTA's bucket histogram (keys staged in shared memory on the way) ----
+        for (int b = tid; b < SEL_BUCKETS; b += SEL_THREADS) sh.hist[b] = 0;
+        __syncthreads();
         for (int q0 = 0; q0 < len; q0 += 8 * SEL_THREADS) {
             uint32_t v[8];
 #pragma unroll
@@ -266,34 +260,81 @@ __global__ void __cluster_dims__(SEL_CTAS, 1, 1) __launch_bounds__(SEL_THREADS, 
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int q = q0 + u * SEL_THREADS + tid;
-                if (q < len && key_bucket(v[u]) == bucket) {
-                    const int pos = atomicAdd(&sh0->m_count, 1);
-                    if (pos < SEL_MEMBER_CAP) sh0->member[pos] = composite(v[u], cb + q);
-                }
+                if (q < len) { if (staged) s_keys[q] = v[u]; atomicAdd(&sh.hist[key_bucket(v[u])], 1); }
+            }
+        }
+        __syncthreads();
+        for (int cbn = warp; cbn < 64; cbn += SEL_WARPS) {
+            const int t = warp_sum(sh.hist[cbn * 32 + lane]);
+            if (lane == 0) sh.coarse[cbn] = t;
+        }
+        cluster.sync();                              // all 8 histograms complete and visible
+        sel_stamp(1, rank);
+        // ---- 2. threshold bucket: coarse level, then the 32 buckets inside it (every CTA, redundantly) ----
+        if (tid < SEL_CTAS * 64) s_x[tid >> 6][tid & 63] = cluster.map_shared_rank(sh.coarse, tid >> 6)[tid & 63];
+        __syncthreads();
+        if (warp == 0) {                             // lane l owns coarse bins 63-2l, 62-2l (descending)
+            int t0 = 0, t1 = 0;
+#pragma unroll
+            for (int r = 0; r < SEL_CTAS; ++r) { t0 += s_x[r][63 - 2 * lane]; t1 += s_x[r][62 - 2 * lane]; }
+            const int incl = warp_scan_incl(t0 + t1), excl = incl - (t0 + t1);
+            if (excl < k && excl + t0 >= k) { s_cb = 63 - 2 * lane; s_above_c = excl; }
+            else if (excl + t0 < k && incl >= k) { s_cb = 62 - 2 * lane; s_above_c = excl + t0; }
+        }
+        __syncthreads();
+        const int cbin = s_cb;
+        if (tid < SEL_CTAS * 32) s_x[tid >> 5][tid & 31] = cluster.map_shared_rank(sh.hist, tid >> 5)[cbin * 32 + (tid & 31)];
+        __syncthreads();
+        if (warp == 0) {                             // lane l owns bucket 31-l of the coarse bin (descending)
+            int t = 0;
+#pragma unroll
+            for (int r = 0; r < SEL_CTAS; ++r) t += s_x[r][31 - lane];
+            const int incl = warp_scan_incl(t), excl = incl - t;
+            const int krem = k - s_above_c;
+            if (excl < krem && incl >= krem) { s_bucket = cbin * 32 + 31 - lane; s_above = s_above_c + excl; }
+        }
+        __syncthreads();
+        const int bucket = s_bucket, above = s_above;
+        // ---- 3. members of the threshold bucket: local list, then every CTA gathers all 8 lists and ranks exactly
+        //         on the composite (key desc, index asc) ----
+        for (int q = tid; q < len; q += SEL_THREADS) {
+            const uint32_t u = KEY(q);
+            if (key_bucket(u) == bucket) {
+                const int pos = atomicAdd(&sh.m_count, 1);
+                if (pos < SEL_LOCAL_CAP) sh.member[pos] = composite(u, cb + q);
             }
         }
         cluster.sync();
         sel_stamp(2, rank);
-        // ---- 3. CTA 0: exact rank inside the bucket on the composite (key desc, index asc) ----
-        if (rank == 0) {
-            const int M = sh.m_count;
-            const int want = k - above - 1;          // number of members that must rank above the threshold member
-            if (M > SEL_MEMBER_CAP) { if (tid == 0) sh.fallback = 1; }
-            else {
-                for (int t = tid; t < M; t += SEL_THREADS) {
-                    const unsigned long long mine = sh.member[t];
-                    int r = 0;
-                    for (int o = 0; o < M; ++o) r += (sh.member[o] > mine);
-                    if (r == want) sh.thr_comp = mine;
-                }
-            }
+        int M = 0;
+        bool crowded = false;
+        int mbase[SEL_CTAS + 1];
+        mbase[0] = 0;
+#pragma unroll
+        for (int r = 0; r < SEL_CTAS; ++r) {
+            const int mr = cluster.map_shared_rank(&sh, r)->m_count;
+            crowded |= (mr > SEL_LOCAL_CAP);
+            mbase[r + 1] = mbase[r] + min(mr, SEL_LOCAL_CAP);
         }
-        cluster.sync();
-        sel_stamp(3, rank);
-        if (tid == 0) { s_thr = sh0->thr_comp; s_fb = sh0->fallback; }
-        __syncthreads();
-        thr_comp = s_thr;
-        if (s_fb) {
+        M = mbase[SEL_CTAS];
+        if (!crowded) {
+            for (int t = tid; t < M; t += SEL_THREADS) {
+                int r = 0;
+#pragma unroll
+                for (int rr = 1; rr < SEL_CTAS; ++rr) r += (t >= mbase[rr]);
+                s_all[t] = cluster.map_shared_rank(&sh, r)->member[t - mbase[r]];
+            }
+            __syncthreads();
+            const int want = k - above - 1;          // members that must rank above the threshold member
+            for (int t = tid; t < M; t += SEL_THREADS) {
+                const unsigned long long mine = s_all[t];
+                int r = 0;
+                for (int o = 0; o < M; ++o) r += (s_all[o] > mine);
+                if (r == want) s_thr = mine;
+            }
+            __syncthreads();
+            thr_comp = s_thr;
+        } else {
             // ---- fallback (crowded bucket, e.g. massive ties): MSB-first radix select on the 64-bit composite,
             //      8 passes of 8 bits over all candidates, histograms merged into CTA 0 with DSMEM atomics ----
             for (int shift = 56; shift >= 0; shift -= 8) {
@@ -304,17 +345,17 @@ __global__ void __cluster_dims__(SEL_CTAS, 1, 1) __launch_bounds__(SEL_THREADS, 
                 const unsigned long long prefix = s_thr;
                 const unsigned long long himask = (shift == 56) ? 0ull : (~0ull << (shift + 8));
                 for (int q = tid; q < len; q += SEL_THREADS) {
-                    const unsigned long long cm = composite(ukeys[cb + q], cb + q);
+                    const unsigned long long cm = composite(KEY(q), cb + q);
                     if ((cm & himask) == prefix) atomicAdd(&s_lhist[(int)((cm >> shift) & 255ull)], 1);
                 }
                 __syncthreads();
-                if (tid < 256 && s_lhist[tid]) atomicAdd(&sh0->hist[tid], s_lhist[tid]);
+                if (tid < 256 && s_lhist[tid]) atomicAdd(&sh0->rhist[tid], s_lhist[tid]);
                 cluster.sync();
                 if (rank == 0 && tid == 0) {
                     int cum = 0;
                     const int krem = sh.kr;
                     for (int bin = 255; bin >= 0; --bin) {
-                        const int hcount = sh.hist[bin];
+                        const int hcount = sh.rhist[bin];
                         if (cum + hcount >= krem) {
                             sh.prefix = prefix | ((unsigned long long)bin << shift);
                             sh.kr = krem - cum;
@@ -322,7 +363,7 @@ __global__ void __cluster_dims__(SEL_CTAS, 1, 1) __launch_bounds__(SEL_THREADS, 
                         }
                         cum += hcount;
                     }
-                    for (int bin = 0; bin < 256; ++bin) sh.hist[bin] = 0;
+                    for (int bin = 0; bin < 256; ++bin) sh.rhist[bin] = 0;
                 }
                 cluster.sync();
             }
@@ -333,30 +374,24 @@ __global__ void __cluster_dims__(SEL_CTAS, 1, 1) __launch_bounds__(SEL_THREADS, 
     } else {
         cluster.sync();                              // every CTA runs before the first remote access below
     }
+    sel_stamp(3, rank);
 
     // ---- 4. count the selected items of this CTA; fix their log-prob / gradient (k_logits_keys wrote the
     //         unselected outcome) ----
     int my_cnt = 0;
     float lp_delta = 0.f, dl_delta = 0.f;
     if (!take_all) {
-        for (int q0 = 0; q0 < len; q0 += 8 * SEL_THREADS) {
-            uint32_t v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) { const int q = q0 + u * SEL_THREADS + tid; v[u] = (q < len) ? ukeys[cb + q] : 0u; }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int q = q0 + u * SEL_THREADS + tid;
-                if (q < len && composite(v[u], cb + q) >= thr_comp) {
-                    const int i = cb + q;
-                    ++my_cnt;
-                    const float l = lg_c[i];
-                    const float lp1 = bern_log_prob(l, 1.f), lp0 = bern_log_prob(l, 0.f);
-                    if (log_prob) log_prob[i] = lp1;
-                    if (dl_all) dl_all[nb_local ? nb_local[i] : i] = 1.f - sigmoidf_(l);
-                    if (mask_out) mask_out[i] = 1;
-                    lp_delta += lp1 - lp0;
-                    dl_delta += 1.f;
-                }
+        for (int q = tid; q < len; q += SEL_THREADS) {
+            if (composite(KEY(q), cb + q) >= thr_comp) {
+                const int i = cb + q;
+                ++my_cnt;
+                const float l = lg_c[i];
+                const float lp1 = bern_log_prob(l, 1.f), lp0 = bern_log_prob(l, 0.f);
+                if (log_prob) log_prob[i] = lp1;
+                if (dl_all) dl_all[nb_local ? nb_local[i] : i] = 1.f - sigmoidf_(l);
+                if (mask_out) mask_out[i] = 1;
+                lp_delta += lp1 - lp0;
+                dl_delta += 1.f;
             }
         }
     }
@@ -382,7 +417,7 @@ __global__ void __cluster_dims__(SEL_CTAS, 1, 1) __launch_bounds__(SEL_THREADS, 
         for (int u = 0; u < rounds; ++u) {           // pass a: flags -> per (round, warp) counts
             const int q = sr + u * SEL_THREADS + tid;
             bool sel = false;
-            if (q < len) sel = take_all || composite(ukeys[cb + q], cb + q) >= thr_comp;
+            if (q < len) sel = take_all || composite(KEY(q), cb + q) >= thr_comp;
             const uint32_t bal = __ballot_sync(GRAPES_FULL_MASK, sel);
             if (lane == 0) s_wcnt[u * 32 + warp] = __popc(bal);
         }
@@ -395,7 +430,7 @@ __global__ void __cluster_dims__(SEL_CTAS, 1, 1) __launch_bounds__(SEL_THREADS, 
         for (int u = 0; u < rounds; ++u) {           // pass b: positions
             const int q = sr + u * SEL_THREADS + tid;
             bool sel = false;
-            if (q < len) sel = take_all || composite(ukeys[cb + q], cb + q) >= thr_comp;
+            if (q < len) sel = take_all || composite(KEY(q), cb + q) >= thr_comp;
             const uint32_t bal = __ballot_sync(GRAPES_FULL_MASK, sel);
             if (sel) {
                 const int i = cb + q;
@@ -466,17 +501,16 @@ int grapes_debug_select_stamps(int64_t* out16) {
     return GRAPES_OK;
 }
 
-// floats of scratch grapes_select_* needs in `work`: bucket histogram (must be ZERO before the first call; the
-// library leaves it zero again after every call) | per-block statistics | candidate logits
+// floats of scratch grapes_select_* needs in `work`: per-block statistics | candidate logits
 int64_t grapes_select_work_floats(grapes_ctx* ctx, int cap_c) {
     if (!ctx) return 0;
-    return (int64_t)SEL_BUCKETS + (int64_t)SEL_STAT_FLOATS * keys_grid(ctx, cap_c) + (int64_t)cap_c + 16;
+    return (int64_t)SEL_STAT_FLOATS * keys_grid(ctx, cap_c) + (int64_t)cap_c + 16;
 }
 
 // Sampler-net layer 2 + keys for one hop (main.py:210-213 + utils.py:37-42), then the selection (utils.py:43-71).
 //   z / nparts / part_stride, in_off / in_src / dinv / bias: as grapes_aggregate_scalar; in_off == NULL means
 //   `z` already holds the per-row logits.  nb_index[j] = candidate index of frontier row j or -1 (NULL: every row is
-//   candidate j).  work: grapes_select_work_floats(cap_n) floats, 16-byte aligned, zero-initialised once.
+//   candidate j).  work: grapes_select_work_floats(cap_n) floats, 16-byte aligned.
 int grapes_select_hop(grapes_ctx* ctx, const float* z, int nparts, int part_stride, const int* n_dev, int cap_n,
                       const int* in_off, const int* in_src, const float* dinv, const float* bias,
                       const int* nb_index, const int* nb_local, const int* nb_nodes, const int* c_dev, int k,
@@ -497,18 +531,25 @@ int grapes_select_hop(grapes_ctx* ctx, const float* z, int nparts, int part_stri
     GRAPES_REQUIRE(!(nb_index && dl_all) || nb_local, "a frontier (nb_index) needs nb_local for the gradient scatter");
     cudaStream_t s = (cudaStream_t)stream;
     const int nblk = keys_grid(ctx, cap_n);
-    int* bucket_hist = reinterpret_cast<int*>(work);
-    float* stat_part = work + SEL_BUCKETS;
+    float* stat_part = work;
     float* lg_c = stat_part + (size_t)SEL_STAT_FLOATS * nblk;
     k_logits_keys<<<nblk, KEYS_THREADS, 0, s>>>(z, nparts, part_stride, n_dev, cap_n, in_off, in_src, dinv, bias,
                                                 nb_index, c_dev, k, noise_mode, noise, rng_state, logits_all, lg_c,
-                                                ukeys_scratch, keys_out, log_prob, dl_all, mask_out, stat_part,
-                                                bucket_hist);
+                                                ukeys_scratch, keys_out, log_prob, dl_all, mask_out, stat_part);
     grapes_count_launches(1);
-    k_select<<<SEL_CTAS, SEL_THREADS, 0, s>>>(ukeys_scratch, lg_c, nb_local, nb_nodes, c_dev, cap_n, k, noise_mode,
-                                              rng_state, stat_part, nblk, bucket_hist, sampled_out, sampled_offset,
-                                              s_dev, total_dev, mask_out, log_prob, tot_log_prob, stats, dl_all,
-                                              sum_dl, bm_mark);
+    // keys of one CTA's chunk staged in shared memory when they fit next to the ~57 KB of static state
+    const size_t chunk_bytes = ((size_t)(cap_n + SEL_CTAS - 1) / SEL_CTAS) * sizeof(uint32_t);
+    const int staged = chunk_bytes <= 160 * 1024 ? 1 : 0;
+    const int smem = staged ? (int)chunk_bytes : 0;
+    static int attr = 0;
+    if (smem > attr) {
+        GRAPES_CUDA_OK(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = smem;
+    }
+    k_select<<<SEL_CTAS, SEL_THREADS, smem, s>>>(ukeys_scratch, lg_c, nb_local, nb_nodes, c_dev, cap_n, k, noise_mode,
+                                                 rng_state, stat_part, nblk, staged, sampled_out, sampled_offset,
+                                                 s_dev, total_dev, mask_out, log_prob, tot_log_prob, stats, dl_all,
+                                                 sum_dl, bm_mark);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
