@@ -25,6 +25,8 @@
 #define TC_THREADS 192
 #define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/)
 
+static int g_tc_debug = 0;      // bit 0: backward operand debug fill; bit 1: force the streaming (non W-resident) forward
+
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
 // ------------------------------------------------------------------------------------------------
@@ -104,6 +106,12 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ float tf32_rna_f(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
 // Shared-memory matrix descriptor, K-major operand tile stored as [rows][32 fp32] with SWIZZLE_128B
 // (what TMA writes): start address >> 4, LBO (unused for swizzled K-major) = 1, SBO = 8 rows * 128 B = 1024 B,
 // descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.   (cute/arch/mma_sm100_desc.hpp SmemDescriptor)
@@ -123,33 +131,61 @@ __device__ __forceinline__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward kernel
+// forward kernel.  One CTA per SM, persistent over 128-row x 128-column output tiles; 320 threads:
+//   warp 0      TMA producer: raw fp32 Y tiles (32 columns x 128 rows, SWIZZLE_128B) into a ring
+//   warp 1      MMA issuer (one elected lane), accumulators in TMEM (2 x 128 columns, double buffered)
+//   warps 2..5  epilogue: tcgen05.ld, bias + relu + dot(w2) per row, relu mask bits
+//   warps 6..9  converters (only when Y arrives as plain fp32, presplit == 0): 3xTF32 operand split of the Y tile IN
+//               shared memory (hi in place, lo beside it; elementwise, so the swizzle pattern is irrelevant), then
+//               fence.proxy.async -> the tensor core.  Saves the hi/lo copies in HBM at the price of one more
+//               pipeline step; with presplit == 1 the aggregation already wrote Y_hi / Y_lo and both are TMA-loaded.
+// Two modes:
+//   W-resident (K <= 160): the CTA owns ONE 128-column half of the hidden layer and keeps that half of W (hi | lo,
+//               all k-blocks) in shared memory for its whole life; only Y streams: 16 KB of L2 traffic per k-block
+//               and tile instead of 64 KB (the kernel is L2-feed bound when everything is re-fetched per tile).
+//   streaming:  W tiles travel with the Y tile in every stage (any K).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 1) k_l1_fwd_tc(
-    const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+#define TCF_THREADS 320
+__global__ void __launch_bounds__(TCF_THREADS, 1) k_l1_fwd_tc(
+    const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA_lo,
     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-    const int* __restrict__ n_dev, int cap_n, int K, int D, const float* __restrict__ b1,
-    const float* __restrict__ w2, float* __restrict__ zpart, uint32_t* __restrict__ maskT) {
+    const int* __restrict__ n_dev, int cap_n, int K, int D, int stages, int wres, int presplit,
+    const float* __restrict__ b1, const float* __restrict__ w2, float* __restrict__ zpart,
+    uint32_t* __restrict__ maskT) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // SWIZZLE_128B tiles: 1024 B aligned
-    uint64_t* bars = (uint64_t*)(smem + TC_STAGES * TC_STAGE_BYTES);
-    uint64_t* full_bar = bars;                       // [TC_STAGES]  TMA -> MMA
-    uint64_t* empty_bar = bars + TC_STAGES;          // [TC_STAGES]  MMA -> TMA
-    uint64_t* tfull_bar = bars + 2 * TC_STAGES;      // [2]          MMA -> epilogue
-    uint64_t* tempty_bar = bars + 2 * TC_STAGES + 2; // [2]          epilogue -> MMA
-    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 4);
+    const int nkb = (K + TC_BK - 1) / TC_BK;
+    const int stage_bytes = wres ? 2 * TC_TILE_BYTES : 4 * TC_TILE_BYTES;            // Y hi | Y lo (| W hi | W lo)
+    uint8_t* w_smem = smem;                                                          // W-resident: [nkb][hi | lo]
+    uint8_t* ring = smem + (wres ? nkb * 2 * TC_TILE_BYTES : 0);
+    uint64_t* bars = (uint64_t*)(ring + stages * stage_bytes);
+    uint64_t* raw_bar = bars;                        // [4]  TMA -> converters
+    uint64_t* conv_bar = bars + 4;                   // [4]  converters -> MMA
+    uint64_t* empty_bar = bars + 8;                  // [4]  MMA -> TMA
+    uint64_t* tfull_bar = bars + 12;                 // [2]  MMA -> epilogue
+    uint64_t* tempty_bar = bars + 14;                // [2]  epilogue -> MMA
+    uint64_t* w_bar = bars + 16;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 17);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = min(*n_dev, cap_n);
     const int NH = D / TC_BN;
     const int m_tiles = (n + TC_BM - 1) / TC_BM;
-    const int total_tiles = m_tiles * NH;
-    const int nkb = (K + TC_BK - 1) / TC_BK;
+    // tile walk: W-resident -> fixed column half, row tiles strided over the CTAs of that half;
+    //            streaming  -> all (row tile, half) pairs strided over the grid
+    const int t_first = wres ? (int)blockIdx.x / NH : (int)blockIdx.x;
+    const int t_step = wres ? (int)gridDim.x / NH : (int)gridDim.x;
+    const int t_count = wres ? m_tiles : m_tiles * NH;
+    const int nh_fixed = (int)blockIdx.x % NH;
+#define TILE_MT(t) (wres ? (t) : (t) / NH)
+#define TILE_NH(t) (wres ? nh_fixed : (t) % NH)
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
+        if (presplit) tma_prefetch_desc(&tmA_lo);
+        for (int s = 0; s < stages; ++s) { mbar_init(&raw_bar[s], 1); mbar_init(&conv_bar[s], 4); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        mbar_init(w_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, 256);
@@ -161,18 +197,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_l1_fwd_tc(
     if (warp == 0) {
         // ===== TMA producer =====
         if (elect_one()) {
+            if (wres && t_first < t_count) {
+                mbar_arrive_expect_tx(w_bar, (uint32_t)(nkb * 2 * TC_TILE_BYTES));
+                for (int kb = 0; kb < nkb; ++kb) {
+                    tma_load_2d(w_smem + kb * 2 * TC_TILE_BYTES, &tmB_hi, w_bar, kb * TC_BK, nh_fixed * TC_BN);
+                    tma_load_2d(w_smem + kb * 2 * TC_TILE_BYTES + TC_TILE_BYTES, &tmB_lo, w_bar, kb * TC_BK, nh_fixed * TC_BN);
+                }
+            }
             int stage = 0; uint32_t phase = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int m0 = (t / NH) * TC_BM, n0 = (t % NH) * TC_BN;
+            for (int t = t_first; t < t_count; t += t_step) {
+                const int m0 = TILE_MT(t) * TC_BM, n0 = TILE_NH(t) * TC_BN;
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* st = smem + stage * TC_STAGE_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
-                    tma_load_2d(st + 0 * TC_TILE_BYTES, &tmA_hi, &full_bar[stage], kb * TC_BK, m0);
-                    tma_load_2d(st + 1 * TC_TILE_BYTES, &tmA_lo, &full_bar[stage], kb * TC_BK, m0);
-                    tma_load_2d(st + 2 * TC_TILE_BYTES, &tmB_hi, &full_bar[stage], kb * TC_BK, n0);
-                    tma_load_2d(st + 3 * TC_TILE_BYTES, &tmB_lo, &full_bar[stage], kb * TC_BK, n0);
-                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                    uint8_t* st = ring + stage * stage_bytes;
+                    mbar_arrive_expect_tx(&raw_bar[stage], (uint32_t)(((presplit ? 2 : 1) + (wres ? 0 : 2)) * TC_TILE_BYTES));
+                    tma_load_2d(st, &tmA, &raw_bar[stage], kb * TC_BK, m0);
+                    if (presplit) tma_load_2d(st + TC_TILE_BYTES, &tmA_lo, &raw_bar[stage], kb * TC_BK, m0);
+                    if (!wres) {
+                        tma_load_2d(st + 2 * TC_TILE_BYTES, &tmB_hi, &raw_bar[stage], kb * TC_BK, n0);
+                        tma_load_2d(st + 3 * TC_TILE_BYTES, &tmB_lo, &raw_bar[stage], kb * TC_BK, n0);
+                    }
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -182,38 +227,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_l1_fwd_tc(
             const uint32_t idesc = make_idesc_tf32(TC_BM, TC_BN);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            if (wres && t_first < t_count) { mbar_wait(w_bar, 0); tc_fence_after(); }
+            const uint32_t wa = smem_u32(w_smem);
+            for (int t = t_first; t < t_count; t += t_step) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_BN);
                 for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
+                    mbar_wait(presplit ? &raw_bar[stage] : &conv_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * TC_STAGE_BYTES);
-                    const uint64_t a_hi = make_kmajor_sw128_desc(sa + 0 * TC_TILE_BYTES);
-                    const uint64_t a_lo = make_kmajor_sw128_desc(sa + 1 * TC_TILE_BYTES);
-                    const uint64_t b_hi = make_kmajor_sw128_desc(sa + 2 * TC_TILE_BYTES);
-                    const uint64_t b_lo = make_kmajor_sw128_desc(sa + 3 * TC_TILE_BYTES);
+                    const uint32_t sa = smem_u32(ring + stage * stage_bytes);
+                    const uint32_t sb = wres ? wa + kb * 2 * TC_TILE_BYTES : sa + 2 * TC_TILE_BYTES;
+                    const uint64_t a_hi = make_kmajor_sw128_desc(sa);
+                    const uint64_t a_lo = make_kmajor_sw128_desc(sa + TC_TILE_BYTES);
+                    const uint64_t b_hi = make_kmajor_sw128_desc(sb);
+                    const uint64_t b_lo = make_kmajor_sw128_desc(sb + TC_TILE_BYTES);
+                    const int nks = min(TC_BK / 8, (K - kb * TC_BK + 7) / 8);     // the last k-block may be partly padding
 #pragma unroll
                     for (int ks = 0; ks < TC_BK / 8; ++ks) {
+                        if (ks >= nks) break;
                         const uint64_t adv = (uint64_t)((ks * 32) >> 4);      // +32 bytes per K=8 slice inside the swizzle row
                         umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | ks) ? 1u : 0u);   // small terms first
                         umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
                         umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
                     }
                     umma_commit(&empty_bar[stage]);                   // smem slot free once these MMAs retire
-                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tfull_bar[acc]);                         // accumulator complete -> epilogue
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else {
+    } else if (warp < 6) {
         // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4 =====
         const int q = warp & 3;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            const int mt = t / NH, nh = t % NH;
+        for (int t = t_first; t < t_count; t += t_step) {
+            const int mt = TILE_MT(t), nh = TILE_NH(t);
             const int row = mt * TC_BM + q * 32 + lane;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
@@ -225,6 +275,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_l1_fwd_tc(
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_BN + ch * 32), v);
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
+                    // (read-only-cache loads: the shared-memory pipe is what feeds the tensor core, keep it free)
                     const int col = nh * TC_BN + ch * 32 + c;
                     const float pre = __uint_as_float(v[c]) + __ldg(&b1[col]);
                     zsum = fmaf(fmaxf(pre, 0.f), __ldg(&w2[col]), zsum);
@@ -245,6 +296,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_l1_fwd_tc(
                 for (int ch = 0; ch < 4; ++ch) dst[ch * 32 + lane] = mbits[ch];
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (!presplit) {
+        // ===== converters (warps 6..9): Y tile -> (hi, lo) in shared memory =====
+        const int ct = threadIdx.x - 6 * 32;                          // 0..127
+        int stage = 0; uint32_t phase = 0;
+        for (int t = t_first; t < t_count; t += t_step) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&raw_bar[stage], phase);
+                uint8_t* st = ring + stage * stage_bytes;
+                float4 v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(st + (size_t)(ct + i * 128) * 16);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float4 h, l;
+                    h.x = tf32_rna_f(v[i].x); h.y = tf32_rna_f(v[i].y); h.z = tf32_rna_f(v[i].z); h.w = tf32_rna_f(v[i].w);
+                    l.x = tf32_rna_f(v[i].x - h.x); l.y = tf32_rna_f(v[i].y - h.y);
+                    l.z = tf32_rna_f(v[i].z - h.z); l.w = tf32_rna_f(v[i].w - h.w);
+                    *reinterpret_cast<float4*>(st + (size_t)(ct + i * 128) * 16) = h;
+                    *reinterpret_cast<float4*>(st + TC_TILE_BYTES + (size_t)(ct + i * 128) * 16) = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&conv_bar[stage]);
+                if (++stage == stages) { stage = 0; phase ^= 1; }
+            }
         }
     }
     tc_fence_before();
@@ -289,7 +366,7 @@ __device__ __forceinline__ float tf32_rna(float x) {
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) k_l1_bwd_tc(
-    const __grid_constant__ CUtensorMap tmY_hi, const __grid_constant__ CUtensorMap tmY_lo,
+    const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmY_lo, int presplit,
     const int* __restrict__ n_dev, int cap_n, int NH, int NB, int stages, const uint32_t* __restrict__ maskT, int D,
     const float* __restrict__ dz, float* __restrict__ part, int debug) {
     extern __shared__ uint8_t smem_raw[];
@@ -298,10 +375,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_l1_bwd_tc(
     const int b_bytes = NB * TCB_B_TILE;
     const int stage_bytes = 2 * a_bytes + 2 * b_bytes;
     uint64_t* bars = (uint64_t*)(smem + stages * stage_bytes);
-    uint64_t* full_bar = bars;                       // [stages] TMA (1 + tx) + 4 expander warps -> MMA
+    uint64_t* full_bar = bars;                       // [stages] 4 expander warps -> MMA
     uint64_t* empty_bar = bars + 4;                  // [stages] MMA -> TMA + expanders
-    uint64_t* done_bar = bars + 8;                   // all MMAs retired -> epilogue
-    uint32_t* tmem_slot = (uint32_t*)(bars + 9);
+    uint64_t* tma_bar = bars + 8;                    // [stages] TMA (raw Y tile) -> expanders
+    uint64_t* done_bar = bars + 12;                  // all MMAs retired -> epilogue
+    uint32_t* tmem_slot = (uint32_t*)(bars + 13);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = min(*n_dev, cap_n);
@@ -310,8 +388,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_l1_bwd_tc(
     const int my_groups = (groups > (int)blockIdx.x) ? (groups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmY_hi); tma_prefetch_desc(&tmY_lo);
-        for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 5); mbar_init(&empty_bar[s], 1); }
+        tma_prefetch_desc(&tmY);
+        for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 4); mbar_init(&empty_bar[s], 1); mbar_init(&tma_bar[s], 1); }
         mbar_init(done_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -327,10 +405,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_l1_bwd_tc(
             for (int g = blockIdx.x; g < groups; g += gridDim.x) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* st = smem + stage * stage_bytes + 2 * a_bytes;
-                mbar_arrive_expect_tx(&full_bar[stage], 2 * b_bytes);
+                mbar_arrive_expect_tx(&tma_bar[stage], (uint32_t)((presplit ? 2 : 1) * b_bytes));
                 for (int nb = 0; nb < NB; ++nb) {
-                    tma_load_2d(st + nb * TCB_B_TILE, &tmY_hi, &full_bar[stage], nb * 32, g * TCB_ROWS);
-                    tma_load_2d(st + b_bytes + nb * TCB_B_TILE, &tmY_lo, &full_bar[stage], nb * 32, g * TCB_ROWS);
+                    tma_load_2d(st + nb * TCB_B_TILE, &tmY, &tma_bar[stage], nb * 32, g * TCB_ROWS);
+                    if (presplit) tma_load_2d(st + b_bytes + nb * TCB_B_TILE, &tmY_lo, &tma_bar[stage], nb * 32, g * TCB_ROWS);
                 }
                 if (++stage == stages) { stage = 0; phase ^= 1; }
             }
@@ -415,6 +493,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_l1_bwd_tc(
                     if (debug & 1) { ah = make_float4(1.f, 1.f, 1.f, 1.f); al = make_float4(0.f, 0.f, 0.f, 0.f); }
                     *reinterpret_cast<float4*>(st + h * TCB_A_TILE + off) = ah;
                     *reinterpret_cast<float4*>(st + a_bytes + h * TCB_A_TILE + off) = al;
+                }
+            }
+            // B' = the raw Y tile the TMA delivered: 3xTF32 split in place (hi) and beside it (lo); elementwise, so the
+            // 32-byte-atom swizzle the TMA wrote is preserved
+            mbar_wait(&tma_bar[stage], phase);
+            if (!presplit) {
+                uint8_t* braw = st + 2 * a_bytes;
+                const int n16 = b_bytes >> 4;                             // 16-byte chunks
+                for (int q = e; q < n16; q += 128) {
+                    const float4 v = *reinterpret_cast<const float4*>(braw + (size_t)q * 16);
+                    float4 h, l;
+                    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+                    l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+                    *reinterpret_cast<float4*>(braw + (size_t)q * 16) = h;
+                    *reinterpret_cast<float4*>(braw + b_bytes + (size_t)q * 16) = l;
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
@@ -559,8 +652,6 @@ static int make_map(CUtensorMap* m, const float* base, int rows, int cols, int l
     return GRAPES_OK;
 }
 
-static int g_tc_debug = 0;
-
 extern "C" {
 
 int grapes_tc_debug(int flags) { g_tc_debug = flags; return 0; }
@@ -580,29 +671,53 @@ int grapes_split_tf32(grapes_ctx* ctx, const float* src, int ld_src, int R, int 
     return GRAPES_OK;
 }
 
-// zpart[D/128][cap_n]: per 128-column half partial row dots (summed by grapes_aggregate_scalar_parts)
-int grapes_sampler_l1_fwd_tc(grapes_ctx* ctx, const float* Y_hi, const float* Y_lo, int ldy, const int* n_dev,
-                             int cap_n, int K, const float* W_hi, const float* W_lo, int ldw, int D, const float* b1,
+// zpart[D/128][cap_n]: per 128-column half partial row dots (summed by the caller, e.g. grapes_select_hop).
+// Y_lo == NULL: Y is plain fp32 and is split into the 3xTF32 (hi, lo) pair inside the kernel; otherwise (Y, Y_lo) is
+// the pair grapes_aggregate wrote (faster: one pipeline step less per k-block).
+int grapes_sampler_l1_fwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo, int ldy, const int* n_dev, int cap_n,
+                             int K, const float* W_hi, const float* W_lo, int ldw, int D, const float* b1,
                              const float* w2, float* zpart, uint32_t* maskT, void* stream) {
-    GRAPES_REQUIRE(ctx && Y_hi && Y_lo && n_dev && W_hi && W_lo && b1 && w2 && zpart, "null argument");
-    GRAPES_REQUIRE(D % TC_BN == 0 && D >= TC_BN, "hidden dim must be a multiple of 128 for the tcgen05 path");
+    GRAPES_REQUIRE(ctx && Y && n_dev && W_hi && W_lo && b1 && w2 && zpart, "null argument");
+    GRAPES_REQUIRE(D % TC_BN == 0 && D >= TC_BN && D <= 512, "hidden dim must be a multiple of 128 (<= 512) for the tcgen05 path");
     GRAPES_REQUIRE(K > 0 && K <= ldy && K <= ldw, "bad K");
-    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    const int presplit = Y_lo ? 1 : 0;
+    CUtensorMap ma, ma_lo, mb_hi, mb_lo;
     int rc;
-    if ((rc = make_map(&ma_hi, Y_hi, cap_n, K, ldy)) != GRAPES_OK) return rc;
-    if ((rc = make_map(&ma_lo, Y_lo, cap_n, K, ldy)) != GRAPES_OK) return rc;
+    if ((rc = make_map(&ma, Y, cap_n, K, ldy)) != GRAPES_OK) return rc;
+    if ((rc = make_map(&ma_lo, presplit ? Y_lo : Y, cap_n, K, ldy)) != GRAPES_OK) return rc;
     if ((rc = make_map(&mb_hi, W_hi, D, K, ldw)) != GRAPES_OK) return rc;
     if ((rc = make_map(&mb_lo, W_lo, D, K, ldw)) != GRAPES_OK) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        GRAPES_CUDA_OK(cudaFuncSetAttribute(k_l1_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-        attr_set = true;
+    const int nkb = (K + TC_BK - 1) / TC_BK, NH = D / TC_BN;
+    const int m_tiles_cap = (cap_n + TC_BM - 1) / TC_BM;
+    const int tail_w = 1024 /*align slack*/ + 256 /*barriers*/;
+    const int tail = tail_w;
+    // W-resident when one column half of W (hi | lo, all k-blocks) plus >= 3 ring stages of Y fit in shared memory
+    int stages = (227 * 1024 - tail_w - nkb * 2 * TC_TILE_BYTES) / (2 * TC_TILE_BYTES);
+    if (stages > 4) stages = 4;
+    // (measured on B200, K = 104: 26.7 us resident vs 29 us streaming; the 128x128x8 tf32 MMA is fed at the
+    //  shared-memory read limit either way.  grapes_tc_debug bit 1 forces streaming.)
+    int wres = (stages >= 3 && ctx->sm_count >= NH && !(g_tc_debug & 2)) ? 1 : 0;
+    int smem_bytes, blocks;
+    if (wres) {
+        smem_bytes = (nkb + stages) * 2 * TC_TILE_BYTES + tail_w;
+        int per_half = ctx->sm_count / NH;
+        if (per_half > m_tiles_cap) per_half = m_tiles_cap;
+        if (per_half < 1) per_half = 1;
+        blocks = per_half * NH;
+    } else {
+        stages = 3;
+        smem_bytes = stages * 4 * TC_TILE_BYTES + tail;
+        const int max_tiles = m_tiles_cap * NH;
+        blocks = max_tiles < ctx->sm_count ? max_tiles : ctx->sm_count;
+        if (blocks < 1) blocks = 1;
     }
-    const int max_tiles = ((cap_n + TC_BM - 1) / TC_BM) * (D / TC_BN);
-    int blocks = max_tiles < ctx->sm_count ? max_tiles : ctx->sm_count;
-    if (blocks < 1) blocks = 1;
-    k_l1_fwd_tc<<<blocks, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, n_dev, cap_n, K,
-                                                                             D, b1, w2, zpart, maskT);
+    static int attr = 0;
+    if (smem_bytes > attr) {
+        GRAPES_CUDA_OK(cudaFuncSetAttribute(k_l1_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        attr = smem_bytes;
+    }
+    k_l1_fwd_tc<<<blocks, TCF_THREADS, smem_bytes, (cudaStream_t)stream>>>(ma, ma_lo, mb_hi, mb_lo, n_dev, cap_n, K, D,
+                                                                           stages, wres, presplit, b1, w2, zpart, maskT);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
@@ -610,12 +725,12 @@ int grapes_sampler_l1_fwd_tc(grapes_ctx* ctx, const float* Y_hi, const float* Y_
 
 
 // Gradient DIRECTION of sum_r dz[r] z[r] w.r.t. (W1, b1, w2), accumulated (+=, times `scale`).
-// Y_hi/Y_lo must carry a column of ones at index `ones_col` (>= K); maskT from grapes_sampler_l1_fwd_tc.
-int grapes_sampler_l1_bwd_tc(grapes_ctx* ctx, const float* Y_hi, const float* Y_lo, int ldy, int ncols,
+// Y must carry a column of ones at index `ones_col` (>= K); maskT from grapes_sampler_l1_fwd_tc.  Y_lo as in the forward.
+int grapes_sampler_l1_bwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo, int ldy, int ncols,
                              const int* n_dev, int cap_n, int K, int ones_col, const uint32_t* maskT,
                              const float* W1, int ldw, int D, const float* b1, const float* w2, const float* dz,
                              float scale, float* gW1, float* gb1, float* gw2, void* stream) {
-    GRAPES_REQUIRE(ctx && Y_hi && Y_lo && n_dev && maskT && W1 && b1 && w2 && dz && gW1 && gb1 && gw2, "null argument");
+    GRAPES_REQUIRE(ctx && Y && n_dev && maskT && W1 && b1 && w2 && dz && gW1 && gb1 && gw2, "null argument");
     GRAPES_REQUIRE(D % 128 == 0 && D >= 128 && D <= 512, "hidden dim must be a multiple of 128 (<= 512)");
     GRAPES_REQUIRE(K <= ones_col && ones_col < ncols && ncols <= ldy, "bad column layout");
     const int NH = D / 128, NB = (ncols + 31) / 32;
@@ -625,10 +740,10 @@ int grapes_sampler_l1_bwd_tc(grapes_ctx* ctx, const float* Y_hi, const float* Y_
     if (stages > 4) stages = 4;
     GRAPES_REQUIRE(stages >= 2, "stage does not fit shared memory");
     const int smem_bytes = stages * stage_bytes + 1024 + 256;
-    CUtensorMap my_hi, my_lo;
+    CUtensorMap my, my_lo;
     int rc;
-    if ((rc = make_map(&my_hi, Y_hi, cap_n, ncols, ldy, TCB_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != GRAPES_OK) return rc;
-    if ((rc = make_map(&my_lo, Y_lo, cap_n, ncols, ldy, TCB_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != GRAPES_OK) return rc;
+    if ((rc = make_map(&my, Y, cap_n, ncols, ldy, TCB_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != GRAPES_OK) return rc;
+    if ((rc = make_map(&my_lo, Y_lo ? Y_lo : Y, cap_n, ncols, ldy, TCB_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != GRAPES_OK) return rc;
     static int attr_bytes = 0;
     if (smem_bytes > attr_bytes) {
         GRAPES_CUDA_OK(cudaFuncSetAttribute(k_l1_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -640,7 +755,7 @@ int grapes_sampler_l1_bwd_tc(grapes_ctx* ctx, const float* Y_hi, const float* Y_
     const int N = NB * 32;
     GRAPES_REQUIRE((size_t)blocks * D * N * sizeof(float) <= ctx->partials_bytes, "split partial buffer too small");
     cudaStream_t s = (cudaStream_t)stream;
-    k_l1_bwd_tc<<<blocks, TC_THREADS, smem_bytes, s>>>(my_hi, my_lo, n_dev, cap_n, NH, NB, stages, maskT, D, dz,
+    k_l1_bwd_tc<<<blocks, TC_THREADS, smem_bytes, s>>>(my, my_lo, Y_lo ? 1 : 0, n_dev, cap_n, NH, NB, stages, maskT, D, dz,
                                                        ctx->partials, g_tc_debug);
     grapes_count_launches(1);
     k_l1_bwd_finalize<<<D, FIN_THREADS, 0, s>>>(ctx->partials, blocks, D, N, K, W1, ldw, b1, w2, ones_col, scale, gW1, gb1, gw2);

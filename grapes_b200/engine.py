@@ -203,12 +203,12 @@ class GrapesEngine:
             hw.ind_bits = z(cap_n, **i32)
             hw.in_off, hw.in_src, hw.dinv = z(cap_n + 1, **i32), e(cap_m, **i32), e(cap_n, **f32)
             hw.logits_all, hw.dl_all, hw.dz = z(cap_n, **f32), z(cap_n, **f32), e(cap_n, **f32)
-            hw.Y = hw.Y_hi = hw.Y_lo = hw.mask_gf = None
+            hw.Y = hw.Y_lo = hw.mask_gf = None
             if need_Y:
+                # tensor-core path: (Y, Y_lo) is the 3xTF32 (hi, lo) pair written by the aggregation; else plain fp32 Y
+                hw.Y = z((cap_n, self.ldY), **f32)
                 if self.use_tc:
-                    hw.Y_hi, hw.Y_lo = z((cap_n, self.ldY), **f32), z((cap_n, self.ldY), **f32)
-                if not self.use_tc_bwd:
-                    hw.Y = z((cap_n, self.ldY), **f32)
+                    hw.Y_lo = z((cap_n, self.ldY), **f32)
                 if self.use_tc_bwd:
                     hw.mask_gf = z(((cap_n + 127) // 128 * 4, D), **i32)
             hw.blk_src, hw.blk_dst = e(self.cap_blk, **i32), e(self.cap_blk, **i32)
@@ -265,6 +265,8 @@ class GrapesEngine:
         self.record: Optional[dict] = None
         # timing experiments only (scripts/ablate.py): leave out parts of the step to see what the rest costs
         self.ablate = set(filter(None, os.environ.get("GRAPES_ABLATE", "").split(",")))
+        if os.environ.get("GRAPES_TC_DEBUG"):
+            self.L.cdll.grapes_tc_debug(int(os.environ["GRAPES_TC_DEBUG"]))
 
     # ------------------------------------------------------------------ helpers
     _CNT = dict(B=0, A=1, cl_nnz=2)
@@ -376,12 +378,12 @@ class GrapesEngine:
                 # Y = A_hat [x | indicators]   (feature gather fused, main.py:198-204 + GCNConv aggregation)
                 L.grapes_aggregate(ctx, X, F, F, ptr(hw.batch_nodes), n_dev, cap_n, ptr(hw.in_off), ptr(hw.in_src),
                                    ptr(hw.dinv), ptr(hw.ind_bits) if self.use_ind else None, self.num_ind, None, 0,
-                                   ptr(hw.Y), self.ldY, ptr(hw.Y_hi), ptr(hw.Y_lo),
+                                   None if tc else ptr(hw.Y), self.ldY, ptr(hw.Y) if tc else None, ptr(hw.Y_lo),
                                    Fp if self.use_tc_bwd else -1, st)
                 if tc:
                     if h == 0:
                         self._split_weights(ctx, st)
-                    L.grapes_sampler_l1_fwd_tc(ctx, ptr(hw.Y_hi), ptr(hw.Y_lo), self.ldY, n_dev, cap_n, Fp,
+                    L.grapes_sampler_l1_fwd_tc(ctx, ptr(hw.Y), ptr(hw.Y_lo), self.ldY, n_dev, cap_n, Fp,
                                                ptr(self.Wgf_hi), ptr(self.Wgf_lo), self.ldW, D, self._par(gf.b1),
                                                self._par(gf.W2), ptr(self.zpart), ptr(hw.mask_gf), st)
                     z_ptr, z_parts, z_stride = ptr(self.zpart), D // 128, cap_n
@@ -515,7 +517,7 @@ class GrapesEngine:
                                     ptr(hw.e_dst), ptr(hw.dinv), ptr(self.bm_prev[h]), ptr(hw.batch_nodes),
                                     ptr(hw.dz), st)
         if self.use_tc_bwd:
-            L.grapes_sampler_l1_bwd_tc(ctx, ptr(hw.Y_hi), ptr(hw.Y_lo), self.ldY, Fp + 1, n_dev, cap_n, Fp, Fp,
+            L.grapes_sampler_l1_bwd_tc(ctx, ptr(hw.Y), ptr(hw.Y_lo), self.ldY, Fp + 1, n_dev, cap_n, Fp, Fp,
                                        ptr(hw.mask_gf), self._par(gf.W1), Fp, D, self._par(gf.b1), self._par(gf.W2),
                                        ptr(hw.dz), 1.0, self._dir(gf.W1), self._dir(gf.b1), self._dir(gf.W2), st)
         else:
@@ -526,7 +528,7 @@ class GrapesEngine:
             return
         # log_z = mean(gcn_z(x[batch_nodes], edges)) - log_z_init   (main.py:223-228)
         if self.use_tc:
-            L.grapes_sampler_l1_fwd_tc(ctx, ptr(hw.Y_hi), ptr(hw.Y_lo), self.ldY, n_dev, cap_n, F, ptr(self.Wz_hi),
+            L.grapes_sampler_l1_fwd_tc(ctx, ptr(hw.Y), ptr(hw.Y_lo), self.ldY, n_dev, cap_n, F, ptr(self.Wz_hi),
                                        ptr(self.Wz_lo), self.ldW, D, self._par(nz.b1), self._par(nz.W2),
                                        ptr(self.zpart_z), ptr(self.mask_z) if self.use_tc_bwd else None, st)
             L.grapes_aggregate_scalar(ctx, ptr(self.zpart_z), D // 128, cap_n, n_dev, cap_n, ptr(hw.in_off),
@@ -544,7 +546,7 @@ class GrapesEngine:
                                     ptr(hw.e_src), ptr(hw.e_dst), ptr(hw.dinv), ptr(self.bm_prev[h]),
                                     ptr(hw.batch_nodes), ptr(self.dz_z), st)
         if self.use_tc_bwd:
-            L.grapes_sampler_l1_bwd_tc(ctx, ptr(hw.Y_hi), ptr(hw.Y_lo), self.ldY, Fp + 1, n_dev, cap_n, F, Fp,
+            L.grapes_sampler_l1_bwd_tc(ctx, ptr(hw.Y), ptr(hw.Y_lo), self.ldY, Fp + 1, n_dev, cap_n, F, Fp,
                                        ptr(self.mask_z), self._par(nz.W1), F, D, self._par(nz.b1), self._par(nz.W2),
                                        ptr(self.dz_z), 1.0, self._dir(nz.W1), self._dir(nz.b1), self._dir(nz.W2), st)
         else:
@@ -642,12 +644,7 @@ class GrapesEngine:
         for h in range(H):
             hw, sz = self.hops[h], sizes[h]
             P, m, n, c, s, e = sz["P"], sz["m"], sz["n"], sz["c"], sz["s"], sz["blk"]
-            if self.random_sampling:
-                Y = None
-            elif self.use_tc_bwd:
-                Y = hw.Y_hi[:n] + hw.Y_lo[:n]
-            else:
-                Y = hw.Y[:n].clone()
+            Y = None if self.random_sampling else (hw.Y[:n] + hw.Y_lo[:n] if self.use_tc else hw.Y[:n].clone())
             r = dict(P=P, m=m, n=n, c=c, s=s,
                      prev=self.prev[h][:P].clone(), e_row=hw.e_row[:m].clone(), e_col=hw.e_col[:m].clone(),
                      e_src=hw.e_src[:m].clone(), e_dst=hw.e_dst[:m].clone(),

@@ -176,21 +176,22 @@ int grapes_sampler_l1_bwd(grapes_ctx* ctx, const float* Y, int ldy, const int* n
                           float* dpre_scratch, float scale, int accumulate, float* gW1, int ldgw, float* gb1,
                           float* gw2, void* stream);
 
-/* tcgen05 path of the same layer (sm_100a tensor cores, 3xTF32 split operands, TMA + TMEM):
- * operands pre-split into hi/lo fp32 arrays (grapes_aggregate's out_hi/out_lo, grapes_split_tf32 for the
- * weights); zpart[D/128][cap_n] partial row dots; maskT[(rows/32)][D] relu mask bits (optional).         */
+/* tcgen05 path of the same layer (sm_100a tensor cores, 3xTF32 split operands, TMA + TMEM).  (Y, Y_lo) is the
+ * (hi, lo) pair grapes_aggregate's out_hi/out_lo wrote; Y_lo == NULL means Y is plain fp32 and is split inside the
+ * kernels (no hi/lo copies in HBM, one more pipeline step).  Weights are pre-split with grapes_split_tf32;
+ * zpart[D/128][cap_n] partial row dots; maskT[(rows/32)][D] relu mask bits (optional).                            */
 int grapes_split_tf32(grapes_ctx* ctx, const float* src, int ld_src, int R, int K, float* hi, float* lo, int ld_dst,
                       void* stream);
-int grapes_sampler_l1_fwd_tc(grapes_ctx* ctx, const float* Y_hi, const float* Y_lo, int ldy, const int* n_dev,
-                             int cap_n, int K, const float* W_hi, const float* W_lo, int ldw, int D, const float* b1,
+int grapes_sampler_l1_fwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo, int ldy, const int* n_dev, int cap_n,
+                             int K, const float* W_hi, const float* W_lo, int ldw, int D, const float* b1,
                              const float* w2, float* zpart, uint32_t* maskT, void* stream);
 
 /* backward on tensor cores: S = mask^T (dz * Y) from the relu mask bits; Y must hold a column of ones at
  * `ones_col` (K <= ones_col < ncols <= ldy).  Accumulates scale * d(sum dz.z)/d(W1,b1,w2).               */
-int grapes_sampler_l1_bwd_tc(grapes_ctx* ctx, const float* Y_hi, const float* Y_lo, int ldy, int ncols,
-                             const int* n_dev, int cap_n, int K, int ones_col, const uint32_t* maskT,
-                             const float* W1, int ldw, int D, const float* b1, const float* w2, const float* dz,
-                             float scale, float* gW1, float* gb1, float* gw2, void* stream);
+int grapes_sampler_l1_bwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo, int ldy, int ncols, const int* n_dev,
+                             int cap_n, int K, int ones_col, const uint32_t* maskT, const float* W1, int ldw, int D,
+                             const float* b1, const float* w2, const float* dz, float scale, float* gW1, float* gb1,
+                             float* gw2, void* stream);
 
 /* ---- selection (utils.py:13-71; eval.py:126-130) --------------------------------------------- */
 /* debugging aid: phase time stamps (globaltimer ns) of the last on-chip selection launch, HOST array of 16 */

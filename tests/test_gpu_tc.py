@@ -6,7 +6,19 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _run_tc(Y, W1, b1, w2, n, dev, with_mask=False):
+def _split(Y, presplit, dev):
+    """(Y, None): split inside the kernels; (Y_hi, Y_lo): the pair the aggregation writes."""
+    if not presplit:
+        return Y, None
+    from grapes_b200._lib import lib, ptr
+    from grapes_b200.utils import _any_ctx
+    Yh, Yl = torch.empty_like(Y), torch.empty_like(Y)
+    lib().grapes_split_tf32(_any_ctx(dev).ctx, ptr(Y), Y.shape[1], Y.shape[0], Y.shape[1], ptr(Yh), ptr(Yl), Y.shape[1],
+                            torch.cuda.current_stream().cuda_stream)
+    return Yh, Yl
+
+
+def _run_tc(Y, W1, b1, w2, n, dev, with_mask=False, presplit=True):
     from grapes_b200._lib import lib, ptr
     from grapes_b200.utils import _any_ctx
     L, ctx = lib(), _any_ctx(dev).ctx
@@ -14,22 +26,23 @@ def _run_tc(Y, W1, b1, w2, n, dev, with_mask=False):
     cap_n, ldy = Y.shape
     D, K = W1.shape
     ldw = (K + 3) // 4 * 4
-    Yh, Yl = torch.empty_like(Y), torch.empty_like(Y)
     Wh = torch.empty((D, ldw), device=dev); Wl = torch.empty((D, ldw), device=dev)
-    L.grapes_split_tf32(ctx, ptr(Y), ldy, cap_n, ldy, ptr(Yh), ptr(Yl), ldy, st)
     L.grapes_split_tf32(ctx, ptr(W1), K, D, K, ptr(Wh), ptr(Wl), ldw, st)
     zpart = torch.zeros((D // 128, cap_n), device=dev)
     cnt = torch.tensor([n], dtype=torch.int32, device=dev)
     maskT = torch.zeros(((cap_n + 127) // 128 * 4, D), dtype=torch.int32, device=dev) if with_mask else None
-    L.grapes_sampler_l1_fwd_tc(ctx, ptr(Yh), ptr(Yl), ldy, ptr(cnt), cap_n, K, ptr(Wh), ptr(Wl), ldw, D, ptr(b1),
+    Ya, Yb = _split(Y, presplit, dev)
+    L.grapes_sampler_l1_fwd_tc(ctx, ptr(Ya), ptr(Yb), ldy, ptr(cnt), cap_n, K, ptr(Wh), ptr(Wl), ldw, D, ptr(b1),
                                ptr(w2), ptr(zpart), ptr(maskT), st)
     torch.cuda.synchronize()
     return zpart.sum(0)[:n], maskT
 
 
+@pytest.mark.parametrize("presplit", [True, False])
 @pytest.mark.parametrize("n,cap_n,K,D", [(1000, 1500, 104, 256), (64943, 66000, 104, 256), (130, 256, 15, 128),
-                                         (5000, 5000, 605, 256), (1, 128, 100, 256), (777, 900, 1436, 384)])
-def test_l1_fwd_tc_matches_fp64(cuda_device, n, cap_n, K, D):
+                                         (5000, 5000, 605, 256), (1, 128, 100, 256), (777, 900, 1436, 384),
+                                         (3000, 3000, 131, 256)])
+def test_l1_fwd_tc_matches_fp64(cuda_device, n, cap_n, K, D, presplit):
     g = torch.Generator().manual_seed(n + K)
     ldy = (K + 3) // 4 * 4
     Y = torch.zeros(cap_n, ldy)
@@ -38,7 +51,8 @@ def test_l1_fwd_tc_matches_fp64(cuda_device, n, cap_n, K, D):
     b1 = torch.randn(D, generator=g) * 0.1
     w2 = torch.randn(D, generator=g) * 0.1
     ref = (torch.relu(Y[:n, :K].double() @ W1.double().t() + b1.double()) * w2.double()).sum(1)
-    got, _ = _run_tc(Y.to(cuda_device), W1.to(cuda_device), b1.to(cuda_device), w2.to(cuda_device), n, cuda_device)
+    got, _ = _run_tc(Y.to(cuda_device), W1.to(cuda_device), b1.to(cuda_device), w2.to(cuda_device), n, cuda_device,
+                     presplit=presplit)
     err = (got.double().cpu() - ref).abs().max() / ref.abs().max()
     assert err < 1e-5, f"relative error {err:.3e}"
 
@@ -62,9 +76,10 @@ def test_l1_fwd_tc_relu_mask_bits(cuda_device):
     assert (bits.bool() != want).float().mean() < 1e-4
 
 
+@pytest.mark.parametrize("presplit", [True, False])
 @pytest.mark.parametrize("n,cap_n,K,D,extra", [(3000, 3072, 104, 256, 0), (64943, 66000, 104, 256, 0), (100, 128, 15, 128, 0),
                                                (2000, 2048, 100, 256, 4), (5000, 5100, 131, 256, 0)])
-def test_l1_bwd_tc_matches_fp64_autograd(cuda_device, n, cap_n, K, D, extra):
+def test_l1_bwd_tc_matches_fp64_autograd(cuda_device, n, cap_n, K, D, extra, presplit):
     """d(sum_r dz[r] z[r]) / d(W1, b1, w2) from the relu-mask bits: S = mask^T (dz * [Y | 1]).
     `extra` indicator-like columns sit between K and the ones column (the gcn_z case, K = F < F')."""
     from grapes_b200._lib import lib, ptr
@@ -86,17 +101,16 @@ def test_l1_bwd_tc_matches_fp64_autograd(cuda_device, n, cap_n, K, D, extra):
     pre64 = Y[:n, :K].double() @ W1.double().t() + b1.double()
     Yd, W1d, b1d, w2d, dzd = (t.to(dev) for t in (Y, W1, b1, w2, dz))
     ldw = (K + 3) // 4 * 4
-    Yh, Yl = torch.empty_like(Yd), torch.empty_like(Yd)
     Wh, Wl = torch.empty((D, ldw), device=dev), torch.empty((D, ldw), device=dev)
-    L.grapes_split_tf32(ctx, ptr(Yd), ldy, cap_n, ldy, ptr(Yh), ptr(Yl), ldy, st)
     L.grapes_split_tf32(ctx, ptr(W1d), K, D, K, ptr(Wh), ptr(Wl), ldw, st)
     zpart = torch.zeros((D // 128, cap_n), device=dev)
     cnt = torch.tensor([n], dtype=torch.int32, device=dev)
     maskT = torch.zeros(((cap_n + 127) // 128 * 4, D), dtype=torch.int32, device=dev)
-    L.grapes_sampler_l1_fwd_tc(ctx, ptr(Yh), ptr(Yl), ldy, ptr(cnt), cap_n, K, ptr(Wh), ptr(Wl), ldw, D, ptr(b1d),
+    Ya, Yb = _split(Yd, presplit, dev)
+    L.grapes_sampler_l1_fwd_tc(ctx, ptr(Ya), ptr(Yb), ldy, ptr(cnt), cap_n, K, ptr(Wh), ptr(Wl), ldw, D, ptr(b1d),
                                ptr(w2d), ptr(zpart), ptr(maskT), st)
     gW1, gb1, gw2 = torch.zeros(D, K, device=dev), torch.zeros(D, device=dev), torch.zeros(D, device=dev)
-    L.grapes_sampler_l1_bwd_tc(ctx, ptr(Yh), ptr(Yl), ldy, ncols, ptr(cnt), cap_n, K, ones_col, ptr(maskT), ptr(W1d), K,
+    L.grapes_sampler_l1_bwd_tc(ctx, ptr(Ya), ptr(Yb), ldy, ncols, ptr(cnt), cap_n, K, ones_col, ptr(maskT), ptr(W1d), K,
                                D, ptr(b1d), ptr(w2d), ptr(dzd), 1.0, ptr(gW1), ptr(gb1), ptr(gw2), st)
     torch.cuda.synchronize()
     # the relu mask the forward emitted: identical to float64's away from the kink; AT the kink (|pre| within fp32
