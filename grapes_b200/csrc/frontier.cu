@@ -74,6 +74,67 @@ __global__ void __launch_bounds__(256) k_expand(const int64_t* __restrict__ indp
 }
 
 // ---------------------------------------------------------------------------------------
+// k_expand_fused: k_row_offsets + k_expand in one launch for row lists that fit shared memory (P <= EXF_MAX_P).
+// Every CTA recomputes the exclusive scan of the P CSR degrees into shared memory (P is ~1k: a few L2 hits per
+// thread), CTA 0 also publishes row_off / m and marks the row bitmaps; then the CTAs split the m edge slots and
+// locate each slot's row by binary search in SHARED memory.  Same outputs as the two kernels.
+// ---------------------------------------------------------------------------------------
+#define EXF_THREADS 512
+#define EXF_MAX_P 8192
+__global__ void __launch_bounds__(EXF_THREADS) k_expand_fused(
+    const int64_t* __restrict__ indptr, const int* __restrict__ indices, const int* __restrict__ rows,
+    const int* __restrict__ P_dev, int cap_P, int* __restrict__ row_off, int* __restrict__ m_out, int cap_m,
+    int* __restrict__ e_row, int* __restrict__ e_col, uint32_t* bm_rows, uint32_t* bm_batch, int* overflow) {
+    extern __shared__ int s_off[];                       // [P + 1]
+    __shared__ long long s_scan[EXF_THREADS / 32 + 2];
+    __shared__ long long s_carry;
+    int P = *P_dev;
+    if (P > cap_P) { P = cap_P; if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(overflow, GRAPES_OVF_ROWS); }
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < P; base += EXF_THREADS) {
+        const int i = base + threadIdx.x;
+        long long deg = 0;
+        if (i < P) {
+            const int r = rows[i];
+            deg = indptr[r + 1] - indptr[r];
+            if (blockIdx.x == 0) {
+                if (bm_rows) bitmap_set(bm_rows, r);
+                if (bm_batch && deg > 0) bitmap_set(bm_batch, r);
+            }
+        }
+        long long total;
+        const long long excl = block_scan_excl<long long>(deg, s_scan, &total);
+        const long long carry = s_carry;
+        if (i < P) s_off[i] = (int)min(carry + excl, (long long)cap_m);
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + total;
+        __syncthreads();
+    }
+    long long mm = s_carry;
+    if (mm > cap_m) { mm = cap_m; if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(overflow, GRAPES_OVF_EDGES); }
+    const int m = (int)mm;
+    if (threadIdx.x == 0) s_off[P] = m;
+    __syncthreads();
+    if (blockIdx.x == 0) {
+        for (int i = threadIdx.x; i <= P; i += EXF_THREADS) row_off[i] = s_off[i];
+        if (threadIdx.x == 0) *m_out = m;
+    }
+    for (int e = blockIdx.x * EXF_THREADS + threadIdx.x; e < m; e += gridDim.x * EXF_THREADS) {
+        int lo = 0, hi = P;                              // largest i with s_off[i] <= e
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_off[mid] <= e) lo = mid; else hi = mid;
+        }
+        const int r = rows[lo];
+        const int v = indices[indptr[r] + (e - s_off[lo])];
+        e_row[e] = lo;
+        e_col[e] = v;
+        if (bm_batch) bitmap_set(bm_batch, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // k_rank_scan: single-pass scan over the node bitmap.  For every word: exclusive popcount
 // prefix (pref_batch; pref_nb for batch & ~prev).  Enumerates the set bits in ascending id
 // order, which IS the reference's local numbering (mask -> nonzero, main.py:189-195):
@@ -108,6 +169,19 @@ __global__ void __launch_bounds__(RANK_THREADS) k_rank_scan(
         p[i] = (w < W && bm_prev) ? bm_prev[w] : 0u;
         mine += ((unsigned long long)__popc(b[i]) << 31) | (unsigned long long)__popc(b[i] & ~p[i]);
     }
+    // indicator rows of the words that hold batch nodes: loaded now, consumed after the scan (latency hidden)
+    uint32_t iw[RANK_WPT][8];
+    if (ind_bits) {
+#pragma unroll
+        for (int i = 0; i < RANK_WPT; ++i) {
+            const int w = w0 + i;
+#pragma unroll
+            for (int h = 0; h < 8; ++h) {
+                iw[i][h] = 0u;
+                if (b[i] && ((h < ind_rows - 1 && h < hop) || h == ind_rows - 1)) iw[i][h] = bm_ind[(size_t)h * W + w];
+            }
+        }
+    }
     unsigned long long total;
     const unsigned long long excl_in_tile = block_scan_excl<unsigned long long>(mine, s_scan, &total);
     const bool nonempty = tile * RANK_TILE < W;
@@ -133,10 +207,8 @@ __global__ void __launch_bounds__(RANK_THREADS) k_rank_scan(
             if (ind_bits && bits) {
 #pragma unroll
                 for (int h = 0; h < 8; ++h) {
-                    ind_w[h] = 0u;
-                    if (h < ind_rows - 1 && h < hop) ind_w[h] = bm_ind[(size_t)h * W + w];
+                    ind_w[h] = iw[i][h];
                     if (h == hop && h < ind_rows - 1) ind_w[h] = nbits;
-                    if (h == ind_rows - 1) ind_w[h] = bm_ind[(size_t)h * W + w];
                 }
             }
             while (bits) {
@@ -596,6 +668,27 @@ int grapes_expand_rows(grapes_ctx* ctx, const int64_t* indptr, const int* indice
     GRAPES_REQUIRE(ctx && indptr && indices && rows && P_dev && row_off && m_dev && e_row && e_col, "null argument");
     k_expand<<<grid_for(ctx, cap_m, 256), 256, 0, (cudaStream_t)stream>>>(indptr, indices, rows, P_dev, cap_P,
                                                                           row_off, m_dev, e_row, e_col, bm_batch);
+    grapes_count_launches(1);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+/* grapes_row_offsets + grapes_expand_rows in one launch (row lists of <= 8192 rows; larger lists take the two calls) */
+int grapes_expand_frontier(grapes_ctx* ctx, const int64_t* indptr, const int* indices, const int* rows,
+                           const int* P_dev, int cap_P, int* row_off, int* m_dev, int cap_m, int* e_row, int* e_col,
+                           uint32_t* bm_rows, uint32_t* bm_batch, int* overflow, void* stream) {
+    GRAPES_REQUIRE(ctx && indptr && indices && rows && P_dev && row_off && m_dev && e_row && e_col && overflow, "null argument");
+    if (cap_P > EXF_MAX_P) {
+        int rc = grapes_row_offsets(ctx, indptr, rows, P_dev, cap_P, row_off, m_dev, cap_m, bm_rows, bm_batch, overflow, stream);
+        if (rc != GRAPES_OK) return rc;
+        return grapes_expand_rows(ctx, indptr, indices, rows, P_dev, cap_P, row_off, m_dev, cap_m, e_row, e_col, bm_batch, stream);
+    }
+    const int smem = (cap_P + 1) * (int)sizeof(int);
+    int blocks = grapes_div_up(cap_m, EXF_THREADS * 2);
+    if (blocks > ctx->sm_count * 2) blocks = ctx->sm_count * 2;
+    if (blocks < 1) blocks = 1;
+    k_expand_fused<<<blocks, EXF_THREADS, smem, (cudaStream_t)stream>>>(indptr, indices, rows, P_dev, cap_P, row_off, m_dev,
+                                                                        cap_m, e_row, e_col, bm_rows, bm_batch, overflow);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;

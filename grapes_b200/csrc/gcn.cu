@@ -114,6 +114,157 @@ __global__ void __launch_bounds__(256) k_agg(const float* __restrict__ X, int F,
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// k_agg_rows: the same aggregation with R destination rows per warp, their dependent load chains interleaved
+// (row offsets -> source ids -> source node ids / weights -> feature rows): the chain is 4 memory latencies deep and
+// one-row-per-warp pays it once per row and wave; R rows in flight per warp cut the number of waves R-fold.  Same
+// summation order as k_agg (self term, then sources ascending) -> bitwise identical results.
+// float4 path only (F, ldx, ldo multiples of 4, 16-byte aligned bases); virtual columns (indicators | ones | pad)
+// must fit one warp (ldo - F <= 32).
+// ---------------------------------------------------------------------------------------
+template <int R, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_agg_rows(const float* __restrict__ X, int F, int ldx,
+                                                     const int* __restrict__ nodes, const int* __restrict__ n_dev,
+                                                     int cap_n, const int* __restrict__ in_off,
+                                                     const int* __restrict__ in_src, const float* __restrict__ dinv,
+                                                     const uint32_t* __restrict__ ind_bits, int num_ind,
+                                                     const float* __restrict__ bias, int relu, float* __restrict__ out,
+                                                     int ldo, float* __restrict__ out_hi, float* __restrict__ out_lo,
+                                                     int ones_col) {
+    const int n = min(*n_dev, cap_n);
+    const int lane = lane_id();
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const bool has_ind = ind_bits != nullptr && num_ind > 0;
+    for (int j0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * R; j0 < n; j0 += warps * R) {
+        // ---- level 1: per-row metadata (warp-uniform values, R independent loads each) ----
+        int beg[R], cnt[R];
+        float dj[R];
+        size_t gj[R];
+        uint32_t ibj[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int j = min(j0 + r, n - 1);
+            beg[r] = in_off[j];
+            cnt[r] = (j0 + r < n) ? in_off[j + 1] - beg[r] : 0;
+            dj[r] = dinv[j];
+            gj[r] = nodes ? (size_t)nodes[j] : (size_t)j;
+            ibj[r] = has_ind ? ind_bits[j] : 0u;
+        }
+        // ---- levels 2-3: lane t of row r preloads source t (first 32 sources; longer rows finish in the hub loop) ----
+        float w[R];
+        unsigned long long sg[R];
+        uint32_t sb[R];
+        int sl[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) sl[r] = (lane < cnt[r]) ? in_src[beg[r] + lane] : -1;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            w[r] = 0.f; sg[r] = gj[r]; sb[r] = 0u;                 // inactive lanes point at the (cached) self row
+            if (sl[r] >= 0) {
+                w[r] = dinv[sl[r]] * dj[r];
+                sg[r] = nodes ? (unsigned long long)nodes[sl[r]] : (unsigned long long)sl[r];
+                sb[r] = has_ind ? ind_bits[sl[r]] : 0u;
+            }
+        }
+        int maxc = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) maxc = max(maxc, min(cnt[r], 32));
+        // ---- level 4: feature rows, 128 columns per pass ----
+        for (int cb = 0; cb < F; cb += 128) {
+            const int c0 = cb + lane * 4;
+            const bool act = c0 < F;
+            float4 acc[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (act) v = *reinterpret_cast<const float4*>(X + gj[r] * ldx + c0);
+                const float ws = dj[r] * dj[r];
+                acc[r].x = fmaf(ws, v.x, 0.f); acc[r].y = fmaf(ws, v.y, 0.f);
+                acc[r].z = fmaf(ws, v.z, 0.f); acc[r].w = fmaf(ws, v.w, 0.f);
+            }
+            for (int t = 0; t < maxc; ++t) {
+                float wt[R];
+                float4 v[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {                      // R independent row loads before any use
+                    wt[r] = __shfl_sync(GRAPES_FULL_MASK, w[r], t);
+                    const unsigned long long st = __shfl_sync(GRAPES_FULL_MASK, sg[r], t);
+                    v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (act && t < cnt[r]) v[r] = *reinterpret_cast<const float4*>(X + (size_t)st * ldx + c0);
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (t < cnt[r]) {                               // warp-uniform: keeps the fma chain identical to k_agg
+                        acc[r].x = fmaf(wt[r], v[r].x, acc[r].x); acc[r].y = fmaf(wt[r], v[r].y, acc[r].y);
+                        acc[r].z = fmaf(wt[r], v[r].z, acc[r].z); acc[r].w = fmaf(wt[r], v[r].w, acc[r].w);
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                for (int pb = beg[r] + 32; pb < beg[r] + cnt[r]; pb += 32) {      // hub rows: sources beyond the first 32
+                    const int p = pb + lane;
+                    float hw = 0.f; unsigned long long hg = 0ull;
+                    if (p < beg[r] + cnt[r]) {
+                        const int s2 = in_src[p];
+                        hw = dinv[s2] * dj[r];
+                        hg = nodes ? (unsigned long long)nodes[s2] : (unsigned long long)s2;
+                    }
+                    const int c2 = min(32, beg[r] + cnt[r] - pb);
+                    for (int t = 0; t < c2; ++t) {
+                        const float wt2 = __shfl_sync(GRAPES_FULL_MASK, hw, t);
+                        const unsigned long long st2 = __shfl_sync(GRAPES_FULL_MASK, hg, t);
+                        if (act) {
+                            const float4 v2 = *reinterpret_cast<const float4*>(X + (size_t)st2 * ldx + c0);
+                            acc[r].x = fmaf(wt2, v2.x, acc[r].x); acc[r].y = fmaf(wt2, v2.y, acc[r].y);
+                            acc[r].z = fmaf(wt2, v2.z, acc[r].z); acc[r].w = fmaf(wt2, v2.w, acc[r].w);
+                        }
+                    }
+                }
+                if (act && j0 + r < n) {
+                    float4 a = acc[r];
+                    if (bias) { a.x += bias[c0]; a.y += bias[c0 + 1]; a.z += bias[c0 + 2]; a.w += bias[c0 + 3]; }
+                    if (relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+                    const size_t o = (size_t)(j0 + r) * ldo + c0;
+                    if (out) *reinterpret_cast<float4*>(out + o) = a;
+                    if (out_hi) {                                   // 3xTF32 operand split for the tcgen05 GEMM
+                        float4 h, l;
+                        h.x = f32_to_tf32(a.x); h.y = f32_to_tf32(a.y); h.z = f32_to_tf32(a.z); h.w = f32_to_tf32(a.w);
+                        l.x = f32_to_tf32(a.x - h.x); l.y = f32_to_tf32(a.y - h.y);
+                        l.z = f32_to_tf32(a.z - h.z); l.w = f32_to_tf32(a.w - h.w);
+                        *reinterpret_cast<float4*>(out_hi + o) = h;
+                        *reinterpret_cast<float4*>(out_lo + o) = l;
+                    }
+                }
+            }
+        }
+        // ---- virtual columns [F, ldo): indicator bits aggregated like features, the ones column, zero padding ----
+        if (ldo > F) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (j0 + r >= n) continue;                          // warp-uniform
+                float a = dj[r] * dj[r] * (float)((ibj[r] >> lane) & 1u);
+                for (int t = 0; t < min(cnt[r], 32); ++t) {
+                    const float wt = __shfl_sync(GRAPES_FULL_MASK, w[r], t);
+                    const uint32_t bt = __shfl_sync(GRAPES_FULL_MASK, sb[r], t);
+                    a = fmaf(wt, (float)((bt >> lane) & 1u), a);
+                }
+                for (int p = beg[r] + 32; p < beg[r] + cnt[r]; ++p) {      // hub rows
+                    const int s2 = in_src[p];
+                    a = fmaf(dinv[s2] * dj[r], has_ind ? (float)((ind_bits[s2] >> lane) & 1u) : 0.f, a);
+                }
+                const int c = F + lane;
+                if (c < ldo) {
+                    const float v = (lane < num_ind) ? a : (c == ones_col ? 1.f : 0.f);
+                    const size_t o = (size_t)(j0 + r) * ldo + c;
+                    if (out) out[o] = v;
+                    if (out_hi) { const float h = f32_to_tf32(v); out_hi[o] = h; out_lo[o] = f32_to_tf32(v - h); }
+                }
+            }
+        }
+    }
+}
+
 // scalar (width-1) aggregation, one thread per row:  out[j] = dinv[j]^2 z[j] + sum w z[src] + bias
 // optional `zero_out[j] = 0` clears a companion vector in the same pass.
 __global__ void __launch_bounds__(256) k_agg_scalar(const float* __restrict__ z, int nparts, int part_stride,
@@ -700,7 +851,11 @@ static inline int grid_for(const grapes_ctx* ctx, long long work, int threads, i
     return (int)(b < cap ? b : cap);
 }
 
+static int g_agg_variant = 0;
+
 extern "C" {
+
+int grapes_agg_variant(int v) { g_agg_variant = v; return 0; }
 
 int grapes_aggregate(grapes_ctx* ctx, const float* X, int F, int ldx, const int* nodes, const int* n_dev, int cap_n,
                      const int* in_off, const int* in_src, const float* dinv, const uint32_t* ind_bits, int num_ind,
@@ -717,7 +872,23 @@ int grapes_aggregate(grapes_ctx* ctx, const float* X, int F, int ldx, const int*
     const size_t al = ((size_t)X) | ((size_t)out) | ((size_t)out_hi) | ((size_t)out_lo);
     const bool a16 = (al & 15) == 0;
     const bool a8 = (al & 7) == 0;
-    if (a16 && (F % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0))
+    if (a16 && (F % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && (ldo - F <= 32) && cap_n >= 4096) {
+        // frontier-sized: R rows per warp with interleaved load chains (variant chosen by grapes_agg_variant, default 0)
+#define AGG_LAUNCH(RR, MB)                                                                                              \
+    k_agg_rows<RR, MB><<<grid_for(ctx, (long long)grapes_div_up(cap_n, RR) * 32, 256, MB), 256, 0, s>>>(                 \
+        X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias, relu, out, ldo, out_hi, out_lo,  \
+        ones_col)
+        switch (g_agg_variant) {
+            case 1: k_agg<4><<<blocks, 256, 0, s>>>(X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind,
+                                                    bias, relu, out, ldo, out_hi, out_lo, ones_col); break;
+            case 2: AGG_LAUNCH(2, 6); break;
+            case 3: AGG_LAUNCH(2, 4); break;
+            case 4: AGG_LAUNCH(4, 3); break;
+            case 5: AGG_LAUNCH(4, 2); break;
+            case 6: AGG_LAUNCH(4, 4); break;
+            default: AGG_LAUNCH(2, 4); break;      // measured best on B200 (products-shaped hop, 65k rows): 2 rows per warp
+        }
+    } else if (a16 && (F % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0))
         k_agg<4><<<blocks, 256, 0, s>>>(X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias,
                                         relu, out, ldo, out_hi, out_lo, ones_col);
     else if (a8 && (F % 2 == 0) && (ldx % 2 == 0) && (ldo % 2 == 0))

@@ -265,6 +265,8 @@ class GrapesEngine:
         self.record: Optional[dict] = None
         # timing experiments only (scripts/ablate.py): leave out parts of the step to see what the rest costs
         self.ablate = set(filter(None, os.environ.get("GRAPES_ABLATE", "").split(",")))
+        if os.environ.get("GRAPES_AGG_VARIANT"):
+            self.L.cdll.grapes_agg_variant(int(os.environ["GRAPES_AGG_VARIANT"]))
         if os.environ.get("GRAPES_TC_DEBUG"):
             self.L.cdll.grapes_tc_debug(int(os.environ["GRAPES_TC_DEBUG"]))
 
@@ -351,10 +353,8 @@ class GrapesEngine:
             rows, P_dev = ptr(self.prev[h]), self._hc(h, "P")
             m_dev, n_dev, c_dev = self._hc(h, "m"), self._hc(h, "n"), self._hc(h, "c")
             # get_neighborhoods + mask dedup (main.py:180-190)
-            L.grapes_row_offsets(ctx, indptr, rows, P_dev, cap_P, ptr(hw.row_off), m_dev, cap_m,
-                                 ptr(self.bm_prev[h]), ptr(self.bm_batch[h]), ovf, st)
-            L.grapes_expand_rows(ctx, indptr, indices, rows, P_dev, cap_P, ptr(hw.row_off), m_dev, cap_m,
-                                 ptr(hw.e_row), ptr(hw.e_col), ptr(self.bm_batch[h]), st)
+            L.grapes_expand_frontier(ctx, indptr, indices, rows, P_dev, cap_P, ptr(hw.row_off), m_dev, cap_m,
+                                     ptr(hw.e_row), ptr(hw.e_col), ptr(self.bm_prev[h]), ptr(self.bm_batch[h]), ovf, st)
             if h > 0:
                 # slice_adjacency(rows = T u S_{h-1}, cols = prev_{h-1}) (main.py:241-244): same row expansion; side B
                 pw = self.hops[h - 1]
@@ -417,9 +417,8 @@ class GrapesEngine:
 
         # ---- last block: slice_adjacency(rows = T u S_{H-1}, cols = prev_{H-1}) ----
         rows, P_dev, m_dev = ptr(self.prev[H]), self._hc(H, "P"), self._hc(H, "m")
-        L.grapes_row_offsets(ctx, indptr, rows, P_dev, cap_P, ptr(self.fin_row_off), m_dev, cap_m, None, None, ovf, st)
-        L.grapes_expand_rows(ctx, indptr, indices, rows, P_dev, cap_P, ptr(self.fin_row_off), m_dev, cap_m,
-                             ptr(self.fin_e_row), ptr(self.fin_e_col), None, st)
+        L.grapes_expand_frontier(ctx, indptr, indices, rows, P_dev, cap_P, ptr(self.fin_row_off), m_dev, cap_m,
+                                 ptr(self.fin_e_row), ptr(self.fin_e_col), None, None, ovf, st)
         lw = self.hops[H - 1]
         join(sB)                                                                  # earlier blocks + frees ctx_b's scratch order
         L.grapes_slice_block(ctx, rows, ptr(self.fin_e_row), ptr(self.fin_e_col), m_dev, cap_m,

@@ -83,6 +83,10 @@ int grapes_row_offsets(grapes_ctx* ctx, const int64_t* indptr, const int* rows, 
 int grapes_expand_rows(grapes_ctx* ctx, const int64_t* indptr, const int* indices, const int* rows,
                        const int* P_dev, int cap_P, const int* row_off, const int* m_dev, int cap_m, int* e_row,
                        int* e_col, uint32_t* bm_batch, void* stream);
+/* grapes_row_offsets + grapes_expand_rows in ONE launch (every CTA rebuilds the row offsets in shared memory)     */
+int grapes_expand_frontier(grapes_ctx* ctx, const int64_t* indptr, const int* indices, const int* rows,
+                           const int* P_dev, int cap_P, int* row_off, int* m_dev, int cap_m, int* e_row, int* e_col,
+                           uint32_t* bm_rows, uint32_t* bm_batch, int* overflow, void* stream);
 /* mask -> ascending id lists + local numbering (main.py:187-195).  pref_* = per-word exclusive
  * popcount prefix (local id of v = pref[v>>5] + popc(bm[v>>5] & ((1<<(v&31))-1)) = TensorMap.map).
  * nb_* describe batch & ~prev (neighbor_nodes; nb_index[j] = position of batch node j in it or -1, optional);
