@@ -122,10 +122,13 @@ class GrapesEngine:
         # chain, side B the induced-block slices.  Each stream has its own library context (scan / split-K scratch).
         self.multi_stream = bool(multi_stream)
         if self.multi_stream:
+            # the critical path (hop chain + classifier) runs at high priority so its kernels are scheduled ahead of the
+            # queued backward / slice kernels of the side streams
+            self.main_hp = torch.cuda.Stream(device=dev, priority=-1) if os.environ.get("GRAPES_HP", "0") == "1" else None
             self.side_a, self.side_b = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
             self.ctx_a, self.ctx_b = graph.new_ctx(), graph.new_ctx(16 << 20)
         else:
-            self.side_a = self.side_b = None
+            self.side_a = self.side_b = self.main_hp = None
             self.ctx_a = self.ctx_b = graph.ctx
 
         # ---- capacities -------------------------------------------------------------------
@@ -312,6 +315,16 @@ class GrapesEngine:
     # ------------------------------------------------------------------ the step
     def _enqueue(self, gumbel_noise: Optional[Sequence[Optional[torch.Tensor]]], apply_optim: bool,
                  noise_mode: int = NOISE_GUMBEL):
+        hp = self.main_hp if (self.multi_stream and self.side_a is not None) else None
+        if hp is None:
+            return self._enqueue_on(gumbel_noise, apply_optim, noise_mode)
+        caller = torch.cuda.current_stream()
+        hp.wait_stream(caller)
+        with torch.cuda.stream(hp):
+            self._enqueue_on(gumbel_noise, apply_optim, noise_mode)
+        caller.wait_stream(hp)
+
+    def _enqueue_on(self, gumbel_noise, apply_optim, noise_mode):
         L, g = self.L, self.g
         main = torch.cuda.current_stream()
         multi = self.multi_stream and self.side_a is not None
