@@ -335,19 +335,27 @@ def main():
             "grapes_sampler_l1_fwd_tc": ("tensor", fwd_flops),
             "grapes_sampler_l1_bwd_tc": ("tensor", fwd_flops),
         }
+        # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full`
+        # capture of this same command (profiles/r01_v3_topkernels.md), averaged over the hop-level launches
+        ncu_traffic = {"grapes_aggregate": 37.1e6, "grapes_sampler_l1_fwd_tc": 49.0e6, "grapes_sampler_l1_bwd_tc": 53.8e6}
         rooflines = {}
         for name, (bound, work) in alg.items():
             if name not in prof:
                 continue
             sec = prof[name][0] / P_STEPS / 1e3
+            calls = prof[name][1] / P_STEPS
             if bound == "hbm":
                 ach = work / sec / 1e9
                 rooflines[name] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                                   "frac": ach / hbm_peak, "traffic": None, "ms_per_step": sec * 1e3}
+                                   "frac": ach / hbm_peak, "traffic": ncu_traffic.get(name), "ms_per_step": sec * 1e3,
+                                   "launches_per_step": calls, "algorithmic_bytes_per_launch": work / calls}
             else:
                 ach = work / sec / 1e12
                 rooflines[name] = {"bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
-                                   "frac": ach / tf_peak, "traffic": None, "ms_per_step": sec * 1e3}
+                                   "frac": ach / tf_peak, "traffic": ncu_traffic.get(name), "ms_per_step": sec * 1e3,
+                                   "launches_per_step": calls, "algorithmic_flops_per_launch": work / calls,
+                                   "ceiling_frac": 1.0 / 6.0,
+                                   "note": "3xTF32 (fp32-accurate): 3 tf32 MMAs per product at half the bf16 rate of the peak"}
         dominant = max(rooflines, key=lambda k: rooflines[k]["ms_per_step"]) if rooflines else None
         roof = dict(rooflines[dominant], kernel=dominant, peak_source=peak_src) if dominant else None
 
