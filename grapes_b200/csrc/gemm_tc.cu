@@ -112,6 +112,19 @@ __device__ __forceinline__ float tf32_rna_f(float x) {
     return __uint_as_float(r);
 }
 
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n"
+        :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+           "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+           "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+           "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 // Shared-memory matrix descriptor, K-major operand tile stored as [rows][32 fp32] with SWIZZLE_128B
 // (what TMA writes): start address >> 4, LBO (unused for swizzled K-major) = 1, SBO = 8 rows * 128 B = 1024 B,
 // descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.   (cute/arch/mma_sm100_desc.hpp SmemDescriptor)
@@ -146,6 +159,7 @@ __device__ __forceinline__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 //   streaming:  W tiles travel with the Y tile in every stage (any K).
 // ------------------------------------------------------------------------------------------------
 #define TCF_THREADS 320
+#define TC_CHUNK_KB 8                 // k-blocks (256 columns) accumulated in the tensor core before promotion to the master
 __global__ void __launch_bounds__(TCF_THREADS, 1) k_l1_fwd_tc(
     const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA_lo,
     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -188,7 +202,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) k_l1_fwd_tc(
         mbar_init(w_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 256);
+    if (warp == 1) tmem_alloc(tmem_slot, 512);        // 2 chunk accumulators (2 x 128 columns) + the fp32 master (128)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -230,32 +244,35 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) k_l1_fwd_tc(
             if (wres && t_first < t_count) { mbar_wait(w_bar, 0); tc_fence_after(); }
             const uint32_t wa = smem_u32(w_smem);
             for (int t = t_first; t < t_count; t += t_step) {
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_BN);
-                for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(presplit ? &raw_bar[stage] : &conv_bar[stage], phase);
+                for (int kc = 0; kc < nkb; kc += TC_CHUNK_KB) {          // the tensor core adds with truncation: keep chains short
+                    mbar_wait(&tempty_bar[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(ring + stage * stage_bytes);
-                    const uint32_t sb = wres ? wa + kb * 2 * TC_TILE_BYTES : sa + 2 * TC_TILE_BYTES;
-                    const uint64_t a_hi = make_kmajor_sw128_desc(sa);
-                    const uint64_t a_lo = make_kmajor_sw128_desc(sa + TC_TILE_BYTES);
-                    const uint64_t b_hi = make_kmajor_sw128_desc(sb);
-                    const uint64_t b_lo = make_kmajor_sw128_desc(sb + TC_TILE_BYTES);
-                    const int nks = min(TC_BK / 8, (K - kb * TC_BK + 7) / 8);     // the last k-block may be partly padding
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_BN);
+                    const int kend = min(nkb, kc + TC_CHUNK_KB);
+                    for (int kb = kc; kb < kend; ++kb) {
+                        mbar_wait(presplit ? &raw_bar[stage] : &conv_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(ring + stage * stage_bytes);
+                        const uint32_t sb = wres ? wa + kb * 2 * TC_TILE_BYTES : sa + 2 * TC_TILE_BYTES;
+                        const uint64_t a_hi = make_kmajor_sw128_desc(sa);
+                        const uint64_t a_lo = make_kmajor_sw128_desc(sa + TC_TILE_BYTES);
+                        const uint64_t b_hi = make_kmajor_sw128_desc(sb);
+                        const uint64_t b_lo = make_kmajor_sw128_desc(sb + TC_TILE_BYTES);
+                        const int nks = min(TC_BK / 8, (K - kb * TC_BK + 7) / 8);     // the last k-block may be partly padding
 #pragma unroll
-                    for (int ks = 0; ks < TC_BK / 8; ++ks) {
-                        if (ks >= nks) break;
-                        const uint64_t adv = (uint64_t)((ks * 32) >> 4);      // +32 bytes per K=8 slice inside the swizzle row
-                        umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | ks) ? 1u : 0u);   // small terms first
-                        umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
-                        umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+                        for (int ks = 0; ks < TC_BK / 8; ++ks) {
+                            if (ks >= nks) break;
+                            const uint64_t adv = (uint64_t)((ks * 32) >> 4);      // +32 bytes per K=8 slice inside the swizzle row
+                            umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, ((kb - kc) | ks) ? 1u : 0u);   // small terms first
+                            umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+                        }
+                        umma_commit(&empty_bar[stage]);                   // smem slot free once these MMAs retire
+                        if (++stage == stages) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(&empty_bar[stage]);                   // smem slot free once these MMAs retire
-                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                    umma_commit(&tfull_bar[acc]);                         // chunk accumulator complete -> epilogue
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
-                umma_commit(&tfull_bar[acc]);                         // accumulator complete -> epilogue
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else if (warp < 6) {
@@ -265,29 +282,44 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) k_l1_fwd_tc(
         for (int t = t_first; t < t_count; t += t_step) {
             const int mt = TILE_MT(t), nh = TILE_NH(t);
             const int row = mt * TC_BM + q * 32 + lane;
-            mbar_wait(&tfull_bar[acc], acc_phase);
-            tc_fence_after();
             float zsum = 0.f;
             uint32_t mbits[4] = {0u, 0u, 0u, 0u};
+            for (int kc = 0; kc < nkb; kc += TC_CHUNK_KB) {
+                const bool first_chunk = (kc == 0), last_chunk = (kc + TC_CHUNK_KB >= nkb);
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
 #pragma unroll
-            for (int ch = 0; ch < TC_BN / 32; ++ch) {
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_BN + ch * 32), v);
+                for (int ch = 0; ch < TC_BN / 32; ++ch) {
+                    uint32_t v[32];
+                    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+                    tmem_ld_32x32(lane_base + (uint32_t)(acc * TC_BN + ch * 32), v);
+                    if (!first_chunk) {                                   // fp32 master += chunk (round to nearest)
+                        uint32_t m[32];
+                        tmem_ld_32x32(lane_base + (uint32_t)(2 * TC_BN + ch * 32), m);
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    // (read-only-cache loads: the shared-memory pipe is what feeds the tensor core, keep it free)
-                    const int col = nh * TC_BN + ch * 32 + c;
-                    const float pre = __uint_as_float(v[c]) + __ldg(&b1[col]);
-                    zsum = fmaf(fmaxf(pre, 0.f), __ldg(&w2[col]), zsum);
-                    if (maskT) {
-                        const uint32_t word = __ballot_sync(GRAPES_FULL_MASK, pre > 0.f && row < n);
-                        if (lane == c) mbits[ch] = word;
+                        for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(m[c]));
+                    }
+                    if (!last_chunk) {
+                        tmem_st_32x32(lane_base + (uint32_t)(2 * TC_BN + ch * 32), v);
+                        continue;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        // (read-only-cache loads: the shared-memory pipe is what feeds the tensor core, keep it free)
+                        const int col = nh * TC_BN + ch * 32 + c;
+                        const float pre = __uint_as_float(v[c]) + __ldg(&b1[col]);
+                        zsum = fmaf(fmaxf(pre, 0.f), __ldg(&w2[col]), zsum);
+                        if (maskT) {
+                            const uint32_t word = __ballot_sync(GRAPES_FULL_MASK, pre > 0.f && row < n);
+                            if (lane == c) mbits[ch] = word;
+                        }
                     }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             if (row < n) zpart[(size_t)nh * cap_n + row] = zsum;
             if (maskT) {
                 // maskT[(row group of 32)][D]: bit r of word (g, d) = relu'(pre[32 g + r, d])
@@ -295,7 +327,6 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) k_l1_fwd_tc(
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch) dst[ch * 32 + lane] = mbits[ch];
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (!presplit) {
         // ===== converters (warps 6..9): Y tile -> (hi, lo) in shared memory =====
@@ -326,7 +357,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) k_l1_fwd_tc(
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 256);
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -365,31 +396,40 @@ __device__ __forceinline__ float tf32_rna(float x) {
     return __uint_as_float(r);
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) k_l1_bwd_tc(
-    const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmY_lo, int presplit,
+// v2 of the contraction: the relu mask is 0/1 -- EXACT in tf32 -- so it is the single A operand, and dz is folded into
+// the other side: B''[r, k] = fl(dz[r] * Y[r, k]) split into (hi, lo) by the expander warps in shared memory.
+//   S = mask^T B''_hi + mask^T B''_lo   ->  with [B''_hi | B''_lo] stored back to back as ONE MN-major operand of
+//   N = 2 * NB * 32 columns this is ONE tcgen05.mma per 8-row slice and 128-unit half (instead of three), reading
+//   12 KB of operands instead of 24 KB (the kernel is fed at the shared-memory read limit).  The two accumulator halves
+//   are added in the epilogue.  Columns [col0, col0 + NB*32) of Y per launch (NB <= 4): wider Y = several launches.
+#define TCB_THREADS 320          // TMA, MMA, 4 mask-expander (+ epilogue) warps, 4 operand-scaling warps
+__global__ void __launch_bounds__(TCB_THREADS, 1) k_l1_bwd_tc(
+    const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmY_lo, int presplit, int col0,
     const int* __restrict__ n_dev, int cap_n, int NH, int NB, int stages, const uint32_t* __restrict__ maskT, int D,
     const float* __restrict__ dz, float* __restrict__ part, int debug) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int a_bytes = NH * TCB_A_TILE;             // one of (hi | lo)
-    const int b_bytes = NB * TCB_B_TILE;
-    const int stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    const int a_bytes = NH * TCB_A_TILE;             // mask tiles of all halves
+    const int b_bytes = NB * TCB_B_TILE;             // one of (hi | lo)
+    const int stage_bytes = a_bytes + 2 * b_bytes;
     uint64_t* bars = (uint64_t*)(smem + stages * stage_bytes);
-    uint64_t* full_bar = bars;                       // [stages] 4 expander warps -> MMA
+    uint64_t* full_bar = bars;                       // [stages] 4 mask-expander + 4 scaling warps -> MMA
     uint64_t* empty_bar = bars + 4;                  // [stages] MMA -> TMA + expanders
-    uint64_t* tma_bar = bars + 8;                    // [stages] TMA (raw Y tile) -> expanders
+    uint64_t* tma_bar = bars + 8;                    // [stages] TMA (Y tile) -> expanders
     uint64_t* done_bar = bars + 12;                  // all MMAs retired -> epilogue
     uint32_t* tmem_slot = (uint32_t*)(bars + 13);
+    float* s_dz = (float*)(bars + 16);               // [stages][32] dz of the group's rows
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = min(*n_dev, cap_n);
     const int groups = (n + TCB_ROWS - 1) / TCB_ROWS;
-    const int N = NB * 32;                           // accumulator columns per half
+    const int N = NB * 32;                           // S columns of this launch; accumulator holds 2N per half
     const int my_groups = (groups > (int)blockIdx.x) ? (groups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmY);
-        for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 4); mbar_init(&empty_bar[s], 1); mbar_init(&tma_bar[s], 1); }
+        if (presplit) tma_prefetch_desc(&tmY_lo);
+        for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 8); mbar_init(&empty_bar[s], 1); mbar_init(&tma_bar[s], 1); }
         mbar_init(done_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -404,19 +444,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_l1_bwd_tc(
             int stage = 0; uint32_t phase = 0;
             for (int g = blockIdx.x; g < groups; g += gridDim.x) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
-                uint8_t* st = smem + stage * stage_bytes + 2 * a_bytes;
+                uint8_t* st = smem + stage * stage_bytes + a_bytes;
                 mbar_arrive_expect_tx(&tma_bar[stage], (uint32_t)((presplit ? 2 : 1) * b_bytes));
                 for (int nb = 0; nb < NB; ++nb) {
-                    tma_load_2d(st + nb * TCB_B_TILE, &tmY, &tma_bar[stage], nb * 32, g * TCB_ROWS);
-                    if (presplit) tma_load_2d(st + b_bytes + nb * TCB_B_TILE, &tmY_lo, &tma_bar[stage], nb * 32, g * TCB_ROWS);
+                    tma_load_2d(st + nb * TCB_B_TILE, &tmY, &tma_bar[stage], col0 + nb * 32, g * TCB_ROWS);
+                    if (presplit) tma_load_2d(st + b_bytes + nb * TCB_B_TILE, &tmY_lo, &tma_bar[stage], col0 + nb * 32, g * TCB_ROWS);
                 }
                 if (++stage == stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         if (elect_one()) {
-            // A: K-major, B: MN-major (bit 16), M = 128, N = NB*32
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
+            // A: K-major, B: MN-major (bit 16), M = 128, N = 2 * NB * 32 (hi block columns, then lo block columns)
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)((2 * N) >> 3) << 17) |
                                    ((uint32_t)(128 >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             bool first = true;
@@ -424,19 +464,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_l1_bwd_tc(
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-                const uint64_t b_hi = make_mnmajor_sw128_32b_desc(sa + 2 * a_bytes, TCB_B_TILE);
-                const uint64_t b_lo = make_mnmajor_sw128_32b_desc(sa + 2 * a_bytes + b_bytes, TCB_B_TILE);
+                const uint64_t bd = make_mnmajor_sw128_32b_desc(sa + a_bytes, TCB_B_TILE);
                 for (int h = 0; h < NH; ++h) {
-                    const uint64_t a_hi = make_kmajor_sw128_desc(sa + h * TCB_A_TILE);
-                    const uint64_t a_lo = make_kmajor_sw128_desc(sa + a_bytes + h * TCB_A_TILE);
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(h * N);
+                    const uint64_t ad = make_kmajor_sw128_desc(sa + h * TCB_A_TILE);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(h * 2 * N);
 #pragma unroll
                     for (int ks = 0; ks < TCB_ROWS / 8; ++ks) {
                         const uint64_t adv_a = (uint64_t)((ks * 32) >> 4);       // 8 r = 32 bytes along the swizzle row
                         const uint64_t adv_b = (uint64_t)((ks * 1024) >> 4);     // 8 rows of 128 bytes
-                        umma_tf32(d_tmem, a_lo + adv_a, b_hi + adv_b, idesc, (first && ks == 0) ? 0u : 1u);
-                        umma_tf32(d_tmem, a_hi + adv_a, b_lo + adv_b, idesc, 1u);
-                        umma_tf32(d_tmem, a_hi + adv_a, b_hi + adv_b, idesc, 1u);
+                        umma_tf32(d_tmem, ad + adv_a, bd + adv_b, idesc, (first && ks == 0) ? 0u : 1u);
                     }
                 }
                 first = false;
@@ -445,69 +481,73 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_l1_bwd_tc(
             }
             umma_commit(done_bar);
         }
+    } else if (warp >= 6) {
+        // ===== scaling warps (6..9): B'' = dz * Y split into (hi, lo), in place on the tile(s) the TMA delivered.
+        //       MN-major tiles: every 128-byte line holds one row r of a 32-column block, so the row of 16-byte chunk
+        //       q is (q / 8) % 32 whatever the swizzle. =====
+        const int e = (warp - 6) * 32 + lane;
+        int stage = 0; uint32_t phase = 0;
+        float dz_nx = 0.f;
+        if ((int)blockIdx.x < groups) { const int r0 = blockIdx.x * TCB_ROWS + lane; dz_nx = (r0 < n) ? dz[r0] : 0.f; }
+        for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+            const float dzr = dz_nx;
+            const int gn = g + gridDim.x;
+            if (gn < groups) { const int rn = gn * TCB_ROWS + lane; dz_nx = (rn < n) ? dz[rn] : 0.f; }
+            uint8_t* bh = smem + stage * stage_bytes + a_bytes;
+            mbar_wait(&tma_bar[stage], phase);
+            const int n16 = b_bytes >> 4;
+            for (int q = e; q < n16; q += 128) {
+                const float sc = __shfl_sync(GRAPES_FULL_MASK, dzr, (q >> 3) & 31);
+                float4 v = *reinterpret_cast<const float4*>(bh + (size_t)q * 16);
+                if (presplit) {
+                    const float4 v2 = *reinterpret_cast<const float4*>(bh + b_bytes + (size_t)q * 16);
+                    v.x += v2.x; v.y += v2.y; v.z += v2.z; v.w += v2.w;
+                }
+                v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+                float4 hh, ll;
+                hh.x = tf32_rna(v.x); hh.y = tf32_rna(v.y); hh.z = tf32_rna(v.z); hh.w = tf32_rna(v.w);
+                ll.x = tf32_rna(v.x - hh.x); ll.y = tf32_rna(v.y - hh.y); ll.z = tf32_rna(v.z - hh.z); ll.w = tf32_rna(v.w - hh.w);
+                *reinterpret_cast<float4*>(bh + (size_t)q * 16) = hh;
+                *reinterpret_cast<float4*>(bh + b_bytes + (size_t)q * 16) = ll;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[stage]);
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
     } else {
-        // ===== expanders (warps 2..5), then epilogue =====
+        // ===== mask expanders (warps 2..5), then epilogue =====
         const int e = (warp - 2) * 32 + lane;            // d index inside a half
         int stage = 0; uint32_t phase = 0;
-        // software pipeline: the dz / mask words of the NEXT group are loaded while this group is expanded, so the
-        // global-load latency is off the expander's critical path
-        float dz_nx = 0.f;
+        // software pipeline: the mask words of the NEXT group are loaded while this group is expanded
         uint32_t words_nx[4] = {0u, 0u, 0u, 0u};
         if ((int)blockIdx.x < groups) {
-            const int r0 = blockIdx.x * TCB_ROWS + lane;
-            dz_nx = (r0 < n) ? dz[r0] : 0.f;
 #pragma unroll
             for (int h = 0; h < 4; ++h) if (h < NH) words_nx[h] = maskT[(size_t)blockIdx.x * D + h * 128 + e];
         }
         for (int g = blockIdx.x; g < groups; g += gridDim.x) {
-            const float dzr = dz_nx;
             uint32_t words[4];
 #pragma unroll
             for (int h = 0; h < 4; ++h) words[h] = words_nx[h];
             const int gn = g + gridDim.x;
             if (gn < groups) {
-                const int rn = gn * TCB_ROWS + lane;
-                dz_nx = (rn < n) ? dz[rn] : 0.f;
 #pragma unroll
                 for (int h = 0; h < 4; ++h) if (h < NH) words_nx[h] = maskT[(size_t)gn * D + h * 128 + e];
             }
-            const float dzh = tf32_rna(dzr), dzl = tf32_rna(dzr - dzh);
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* st = smem + stage * stage_bytes;
+            // A: mask bits of hidden unit e (row) over the group's 32 rows (K), 1.0 / 0.0
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                float vh[4], vl[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    vh[i] = __shfl_sync(GRAPES_FULL_MASK, dzh, c * 4 + i);
-                    vl[i] = __shfl_sync(GRAPES_FULL_MASK, dzl, c * 4 + i);
-                }
                 const int off = e * 128 + ((c ^ (e & 7)) << 4);          // SWIZZLE_128B: 16-byte chunk index ^ (row % 8)
 #pragma unroll
                 for (int h = 0; h < 4; ++h) {
                     if (h >= NH) break;
                     const uint32_t w = words[h] >> (c * 4);
-                    float4 ah, al;
-                    ah.x = (w & 1u) ? vh[0] : 0.f; ah.y = (w & 2u) ? vh[1] : 0.f; ah.z = (w & 4u) ? vh[2] : 0.f; ah.w = (w & 8u) ? vh[3] : 0.f;
-                    al.x = (w & 1u) ? vl[0] : 0.f; al.y = (w & 2u) ? vl[1] : 0.f; al.z = (w & 4u) ? vl[2] : 0.f; al.w = (w & 8u) ? vl[3] : 0.f;
-                    if (debug & 1) { ah = make_float4(1.f, 1.f, 1.f, 1.f); al = make_float4(0.f, 0.f, 0.f, 0.f); }
-                    *reinterpret_cast<float4*>(st + h * TCB_A_TILE + off) = ah;
-                    *reinterpret_cast<float4*>(st + a_bytes + h * TCB_A_TILE + off) = al;
-                }
-            }
-            // B' = the raw Y tile the TMA delivered: 3xTF32 split in place (hi) and beside it (lo); elementwise, so the
-            // 32-byte-atom swizzle the TMA wrote is preserved
-            mbar_wait(&tma_bar[stage], phase);
-            if (!presplit) {
-                uint8_t* braw = st + 2 * a_bytes;
-                const int n16 = b_bytes >> 4;                             // 16-byte chunks
-                for (int q = e; q < n16; q += 128) {
-                    const float4 v = *reinterpret_cast<const float4*>(braw + (size_t)q * 16);
-                    float4 h, l;
-                    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-                    l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
-                    *reinterpret_cast<float4*>(braw + (size_t)q * 16) = h;
-                    *reinterpret_cast<float4*>(braw + b_bytes + (size_t)q * 16) = l;
+                    float4 a;
+                    a.x = (w & 1u) ? 1.f : 0.f; a.y = (w & 2u) ? 1.f : 0.f; a.z = (w & 4u) ? 1.f : 0.f; a.w = (w & 8u) ? 1.f : 0.f;
+                    if (debug & 1) a = make_float4(1.f, 1.f, 1.f, 1.f);
+                    *reinterpret_cast<float4*>(st + h * TCB_A_TILE + off) = a;
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
@@ -515,7 +555,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_l1_bwd_tc(
             if (lane == 0) mbar_arrive(&full_bar[stage]);
             if (++stage == stages) { stage = 0; phase ^= 1; }
         }
-        // epilogue: this CTA's partial S -> part[cta][NH*128][N]
+        // epilogue: this CTA's partial S -> part[cta][NH*128][N]  (hi-part + lo-part accumulators)
         const int q = warp & 3;
         float* dst = part + (size_t)blockIdx.x * NH * 128 * N;
         if (my_groups > 0) {
@@ -524,12 +564,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_l1_bwd_tc(
             for (int h = 0; h < NH; ++h) {
                 float* row = dst + (size_t)(h * 128 + q * 32 + lane) * N;
                 for (int ch = 0; ch < NB; ++ch) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * N + ch * 32), v);
+                    uint32_t v[32], v2[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 2 * N + ch * 32), v);
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 2 * N + N + ch * 32), v2);
 #pragma unroll
                     for (int c = 0; c < 32; c += 4)
                         *reinterpret_cast<float4*>(row + ch * 32 + c) =
-                            make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]), __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
+                            make_float4(__uint_as_float(v[c]) + __uint_as_float(v2[c]),
+                                        __uint_as_float(v[c + 1]) + __uint_as_float(v2[c + 1]),
+                                        __uint_as_float(v[c + 2]) + __uint_as_float(v2[c + 2]),
+                                        __uint_as_float(v[c + 3]) + __uint_as_float(v2[c + 3]));
                 }
             }
         } else {
@@ -550,7 +594,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_l1_bwd_tc(
 // combine through shared memory.
 #define FIN_THREADS 1024
 __global__ void __launch_bounds__(FIN_THREADS) k_l1_bwd_finalize(
-    const float* __restrict__ part, int nparts, int D, int N, int K, const float* __restrict__ W1, int ldw,
+    const float* __restrict__ part, int nparts, int D, int N, int col0, int K, const float* __restrict__ W1, int ldw,
     const float* __restrict__ b1, const float* __restrict__ w2, int ones_col, float scale, float* __restrict__ gW1,
     float* __restrict__ gb1, float* __restrict__ gw2) {
     __shared__ __align__(16) float sums[4 * FIN_THREADS];        // [groups][N], groups * N == 4096
@@ -575,9 +619,9 @@ __global__ void __launch_bounds__(FIN_THREADS) k_l1_bwd_finalize(
     __syncthreads();
     float acc_w2 = 0.f;
     if (threadIdx.x < N) {
-        const int k = threadIdx.x;
+        const int k = col0 + threadIdx.x;                        // column of Y / W1 this launch's column `threadIdx.x` is
         float s = 0.f;
-        for (int g = 0; g < groups; ++g) s += sums[g * N + k];   // fixed order
+        for (int g = 0; g < groups; ++g) s += sums[g * N + threadIdx.x];   // fixed order
         const float w2d = w2[d];
         if (k < K) {
             gW1[(size_t)d * K + k] += scale * w2d * s;
@@ -731,35 +775,39 @@ int grapes_sampler_l1_bwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo,
                              const float* W1, int ldw, int D, const float* b1, const float* w2, const float* dz,
                              float scale, float* gW1, float* gb1, float* gw2, void* stream) {
     GRAPES_REQUIRE(ctx && Y && n_dev && maskT && W1 && b1 && w2 && dz && gW1 && gb1 && gw2, "null argument");
-    GRAPES_REQUIRE(D % 128 == 0 && D >= 128 && D <= 512, "hidden dim must be a multiple of 128 (<= 512)");
+    GRAPES_REQUIRE(D % 128 == 0 && D >= 128 && D <= 256, "hidden dim must be 128 or 256 for the tcgen05 backward");
     GRAPES_REQUIRE(K <= ones_col && ones_col < ncols && ncols <= ldy, "bad column layout");
-    const int NH = D / 128, NB = (ncols + 31) / 32;
-    GRAPES_REQUIRE(NH * NB * 32 <= 512 && NB * 32 <= 256, "accumulator does not fit TMEM (use the SIMT path)");
-    const int stage_bytes = NH * 2 * TCB_A_TILE + NB * 2 * TCB_B_TILE;
-    int stages = (220 * 1024) / stage_bytes;
-    if (stages > 4) stages = 4;
-    GRAPES_REQUIRE(stages >= 2, "stage does not fit shared memory");
-    const int smem_bytes = stages * stage_bytes + 1024 + 256;
-    CUtensorMap my, my_lo;
-    int rc;
-    if ((rc = make_map(&my, Y, cap_n, ncols, ldy, TCB_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != GRAPES_OK) return rc;
-    if ((rc = make_map(&my_lo, Y_lo ? Y_lo : Y, cap_n, ncols, ldy, TCB_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != GRAPES_OK) return rc;
-    static int attr_bytes = 0;
-    if (smem_bytes > attr_bytes) {
-        GRAPES_CUDA_OK(cudaFuncSetAttribute(k_l1_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        attr_bytes = smem_bytes;
-    }
-    const int max_groups = (cap_n + TCB_ROWS - 1) / TCB_ROWS;
-    int blocks = max_groups < ctx->sm_count ? max_groups : ctx->sm_count;
-    if (blocks < 1) blocks = 1;
-    const int N = NB * 32;
-    GRAPES_REQUIRE((size_t)blocks * D * N * sizeof(float) <= ctx->partials_bytes, "split partial buffer too small");
+    const int NH = D / 128;
     cudaStream_t s = (cudaStream_t)stream;
-    k_l1_bwd_tc<<<blocks, TC_THREADS, smem_bytes, s>>>(my, my_lo, Y_lo ? 1 : 0, n_dev, cap_n, NH, NB, stages, maskT, D, dz,
-                                                       ctx->partials, g_tc_debug);
-    grapes_count_launches(1);
-    k_l1_bwd_finalize<<<D, FIN_THREADS, 0, s>>>(ctx->partials, blocks, D, N, K, W1, ldw, b1, w2, ones_col, scale, gW1, gb1, gw2);
-    grapes_count_launches(1);
+    // column chunks of <= 128 columns of Y (accumulator: NH halves x (hi | lo) x 128 columns = all 512 TMEM columns)
+    for (int col0 = 0; col0 < ncols; col0 += 128) {
+        const int NB = (grapes_min_i(ncols - col0, 128) + 31) / 32;
+        const int N = NB * 32;
+        const int stage_bytes = NH * TCB_A_TILE + NB * 2 * TCB_B_TILE;
+        int stages = (224 * 1024) / stage_bytes;
+        if (stages > 4) stages = 4;
+        GRAPES_REQUIRE(stages >= 2, "stage does not fit shared memory");
+        const int smem_bytes = stages * stage_bytes + 1024 + 128 + 4 * 32 * (int)sizeof(float);
+        CUtensorMap my, my_lo;
+        int rc;
+        if ((rc = make_map(&my, Y, cap_n, ncols, ldy, TCB_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != GRAPES_OK) return rc;
+        if ((rc = make_map(&my_lo, Y_lo ? Y_lo : Y, cap_n, ncols, ldy, TCB_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != GRAPES_OK) return rc;
+        static int attr_bytes = 0;
+        if (smem_bytes > attr_bytes) {
+            GRAPES_CUDA_OK(cudaFuncSetAttribute(k_l1_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+            attr_bytes = smem_bytes;
+        }
+        const int max_groups = (cap_n + TCB_ROWS - 1) / TCB_ROWS;
+        int blocks = max_groups < ctx->sm_count ? max_groups : ctx->sm_count;
+        if (blocks < 1) blocks = 1;
+        GRAPES_REQUIRE((size_t)blocks * D * N * sizeof(float) <= ctx->partials_bytes, "split partial buffer too small");
+        k_l1_bwd_tc<<<blocks, TCB_THREADS, smem_bytes, s>>>(my, my_lo, Y_lo ? 1 : 0, col0, n_dev, cap_n, NH, NB, stages,
+                                                           maskT, D, dz, ctx->partials, g_tc_debug);
+        grapes_count_launches(1);
+        k_l1_bwd_finalize<<<D, FIN_THREADS, 0, s>>>(ctx->partials, blocks, D, N, col0, K, W1, ldw, b1, w2, ones_col, scale,
+                                                    gW1, gb1, gw2);
+        grapes_count_launches(1);
+    }
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
 }

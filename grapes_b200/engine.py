@@ -102,12 +102,11 @@ class GrapesEngine:
         self.num_ind = self.H + 1 if self.use_ind else 0
         self.Fp = F + self.num_ind
         self.ldY = _round_up(self.Fp, 4)
-        # tcgen05 path: hidden multiple of 128 and K <= 255.  Longer K (Cora 1433, Reddit 602 features) stays on the
-        # fp32 SIMT kernels: the tensor core accumulates in fp32 with truncation, and > ~100 chained K-slices
-        # drift past the 1e-5 bar (measured 1.0e-5 at K = 1436); chunked promotion is future work.
-        nb = (self.Fp + 1 + 31) // 32                      # 32-column accumulator blocks of the tensor-core backward
-        self.use_tc = bool(use_tensor_cores) and (self.D % 128 == 0) and nb * 32 <= 256
-        self.use_tc_bwd = self.use_tc and (self.D // 128) * nb * 32 <= 512
+        # tcgen05 path: hidden dim a multiple of 128.  Any K: the forward promotes its tensor-core accumulator to an fp32
+        # master every 256 columns (the tensor core adds with truncation; long chains drift past the 1e-5 bar) and the
+        # backward walks Y in chunks of 128 columns.
+        self.use_tc = bool(use_tensor_cores) and (self.D % 128 == 0) and self.D <= 512
+        self.use_tc_bwd = self.use_tc and self.D // 128 <= 2    # backward accumulators: halves x (hi | lo) x 128 columns of TMEM
         if self.use_tc_bwd:
             self.ldY = _round_up(self.Fp + 1, 4)           # room for the column of ones (bias column)
         self.ldW = _round_up(self.Fp, 4)

@@ -132,7 +132,7 @@ def test_step_parity_trajectory_balance(cuda_device, name, seed):
     _check_step(st, eng, train_idx[:B], cuda_device, apply_optim=False)
 
 
-@pytest.mark.parametrize("name,seed", [("tiny", 0), ("small", 1), ("small", 2)])
+@pytest.mark.parametrize("name,seed", [("tiny", 0), ("small", 1), ("small", 2), ("cora", 0)])
 def test_tensor_core_engine_step_parity(cuda_device, name, seed):
     """The same whole-step parity with the tcgen05 3xTF32 kernels in the loop: integer outputs and sampled sets stay
     bit-exact, logits / losses hold the 1e-5 bar, gradients hold it up to relu-kink flips (see _grad_ok)."""

@@ -78,7 +78,8 @@ def test_l1_fwd_tc_relu_mask_bits(cuda_device):
 
 @pytest.mark.parametrize("presplit", [True, False])
 @pytest.mark.parametrize("n,cap_n,K,D,extra", [(3000, 3072, 104, 256, 0), (64943, 66000, 104, 256, 0), (100, 128, 15, 128, 0),
-                                               (2000, 2048, 100, 256, 4), (5000, 5100, 131, 256, 0)])
+                                               (2000, 2048, 100, 256, 4), (5000, 5100, 131, 256, 0),
+                                               (4000, 4096, 605, 256, 0), (1500, 1536, 1433, 256, 3)])
 def test_l1_bwd_tc_matches_fp64_autograd(cuda_device, n, cap_n, K, D, extra, presplit):
     """d(sum_r dz[r] z[r]) / d(W1, b1, w2) from the relu-mask bits: S = mask^T (dz * [Y | 1]).
     `extra` indicator-like columns sit between K and the ones column (the gcn_z case, K = F < F')."""
