@@ -61,6 +61,8 @@ class _Lib:
             fn = getattr(self.cdll, name)
             fn.restype = {"char*": ctypes.c_char_p, "int64": ctypes.c_int64}.get(ret, ctypes.c_int)
             fn.argtypes = [_ctype(t) for t, _ in params]
+        if os.environ.get("GRAPES_PDL", "") != "":
+            self.cdll.grapes_set_pdl(int(os.environ["GRAPES_PDL"], 0))   # bit mask per source file; 0 = plain stream order
         self.launches = 0          # number of C-ABI compute calls issued
         self.profiling = False     # when True every call is bracketed by CUDA events (bench.py breakdown)
         self._events = []

@@ -58,6 +58,42 @@ void grapes_count_launches(int n);   // bookkeeping for bench.py's gpu_launches
         }                                                                                 \
     } while (0)
 
+// ---------------------------------------------------------------------------------------
+// Programmatic dependent launch: every kernel of the library starts with pdl_begin() and is launched through pdl(),
+// so in a stream (or captured graph) the NEXT kernel's launch, block scheduling and prologue overlap this kernel;
+// griddepcontrol.wait then blocks until the previous kernel has completed and flushed its writes.
+// grapes_set_pdl(0) turns the launch attribute off (plain stream order).
+// ---------------------------------------------------------------------------------------
+extern int g_grapes_pdl;          // bit mask over source files (GRAPES_PDL_GROUP), off by default
+#ifndef GRAPES_PDL_GROUP
+#define GRAPES_PDL_GROUP 1
+#endif
+#ifdef __CUDACC__
+#include <utility>
+__device__ __forceinline__ void pdl_begin() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename K>
+struct PdlLaunch {
+    K kernel; dim3 grid, block; size_t smem; cudaStream_t stream;
+    template <typename... Args>
+    void operator()(Args&&... args) const {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = (g_grapes_pdl & GRAPES_PDL_GROUP) ? 1 : 0;
+        cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+    }
+};
+template <typename K>
+static inline PdlLaunch<K> pdl(K kernel, dim3 grid, dim3 block, size_t smem = 0, cudaStream_t stream = 0) {
+    return PdlLaunch<K>{kernel, grid, block, smem, stream};
+}
+#endif
+
 static inline int grapes_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline int grapes_min_i(int a, int b) { return a < b ? a : b; }
 static inline int grapes_max_i(int a, int b) { return a > b ? a : b; }

@@ -5,6 +5,7 @@
 
 static thread_local char g_err[512] = "";
 static long long g_launches = 0;
+int g_grapes_pdl = 0;   // measured on B200: slower or neutral per group and unsafe in combination
 void grapes_count_launches(int n) { g_launches += n; }
 
 void grapes_set_error(const char* fmt, ...) {
@@ -18,6 +19,7 @@ extern "C" {
 
 const char* grapes_last_error(void) { return g_err; }
 int grapes_abi_version(void) { return 1; }
+int grapes_set_pdl(int mask) { g_grapes_pdl = mask; return 0; }
 int64_t grapes_kernel_launches(void) { return (int64_t)g_launches; }
 
 int grapes_ctx_create(int device, int64_t num_nodes, int64_t max_frontier, int64_t partials_bytes, grapes_ctx** out) {

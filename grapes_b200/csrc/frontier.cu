@@ -7,6 +7,7 @@
 //   TensorMap.update / .map     /root/reference/modules/utils.py:98-120
 //   slice_adjacency             /root/reference/modules/utils.py:85-95
 // All outputs are bit-exact with those (ordering contracts in DESIGN.md section 3).
+#define GRAPES_PDL_GROUP 1
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------------------
@@ -20,6 +21,7 @@ __global__ void __launch_bounds__(1024) k_row_offsets(const int64_t* __restrict_
                                                       int* __restrict__ row_off, int* __restrict__ m_out,
                                                       int cap_m, uint32_t* bm_rows, uint32_t* bm_batch,
                                                       int* overflow) {
+    pdl_begin();
     __shared__ long long s_scan[34];
     int P = *P_dev;
     if (P > cap_P) { P = cap_P; if (threadIdx.x == 0) atomicOr(overflow, GRAPES_OVF_ROWS); }
@@ -57,6 +59,7 @@ __global__ void __launch_bounds__(256) k_expand(const int64_t* __restrict__ indp
                                                 const int* __restrict__ m_dev,
                                                 int* __restrict__ e_row, int* __restrict__ e_col,
                                                 uint32_t* bm_batch) {
+    pdl_begin();
     const int P = min(*P_dev, cap_P);
     const int m = *m_dev;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < m; e += gridDim.x * blockDim.x) {
@@ -85,6 +88,7 @@ __global__ void __launch_bounds__(EXF_THREADS) k_expand_fused(
     const int64_t* __restrict__ indptr, const int* __restrict__ indices, const int* __restrict__ rows,
     const int* __restrict__ P_dev, int cap_P, int* __restrict__ row_off, int* __restrict__ m_out, int cap_m,
     int* __restrict__ e_row, int* __restrict__ e_col, uint32_t* bm_rows, uint32_t* bm_batch, int* overflow) {
+    pdl_begin();
     extern __shared__ int s_off[];                       // [P + 1]
     __shared__ long long s_scan[EXF_THREADS / 32 + 2];
     __shared__ long long s_carry;
@@ -152,6 +156,7 @@ __global__ void __launch_bounds__(RANK_THREADS) k_rank_scan(
     int* __restrict__ nb_nodes, int* __restrict__ nb_local, int* __restrict__ nb_index,
     uint32_t* __restrict__ ind_bits, uint32_t* bm_ind, int ind_rows, int hop, int cap_n, int* __restrict__ n_out,
     int* __restrict__ c_out, int* overflow, unsigned long long* status, unsigned int* counters) {
+    pdl_begin();
     __shared__ unsigned long long s_scan[RANK_THREADS / 32 + 2];
     __shared__ int s_tile;
     __shared__ unsigned long long s_excl;
@@ -255,6 +260,7 @@ __global__ void __launch_bounds__(256) k_edge_local(const int* __restrict__ rows
                                                     const uint32_t* __restrict__ bm,
                                                     const int* __restrict__ pref,
                                                     int* __restrict__ e_src, int* __restrict__ e_dst, int* cnt_hist) {
+    pdl_begin();
     const int m = *m_dev;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < m; e += gridDim.x * blockDim.x) {
         const int s = bitmap_rank(bm, pref, rows[e_row[e]]);
@@ -269,6 +275,7 @@ __global__ void __launch_bounds__(256) k_edge_local(const int* __restrict__ rows
 __global__ void __launch_bounds__(256) k_relabel(const int* __restrict__ ids, const int* __restrict__ cnt_dev,
                                                  int cap, const uint32_t* __restrict__ bm,
                                                  const int* __restrict__ pref, int* __restrict__ out) {
+    pdl_begin();
     const int n = min(*cnt_dev, cap);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         out[i] = bitmap_rank(bm, pref, ids[i]);
@@ -283,6 +290,7 @@ __global__ void __launch_bounds__(256) k_relabel(const int* __restrict__ ids, co
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_hist(const int* __restrict__ key, const int* __restrict__ val,
                                               const int* __restrict__ E_dev, int cap_E, int* cnt) {
+    pdl_begin();
     const int E = min(*E_dev, cap_E);
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
         const int k = key[e];
@@ -299,6 +307,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_i32(const int* __restrict
                                                            int* __restrict__ out, float* __restrict__ dinv,
                                                            int* __restrict__ total_out,
                                                            unsigned long long* status, unsigned int* counters) {
+    pdl_begin();
     __shared__ unsigned long long s_scan[SCAN_THREADS / 32 + 2];
     __shared__ int s_tile;
     __shared__ unsigned long long s_excl;
@@ -349,6 +358,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_i32(const int* __restrict
 __global__ void __launch_bounds__(256) k_fill(const int* __restrict__ key, const int* __restrict__ val,
                                               const int* __restrict__ E_dev, int cap_E,
                                               const int* __restrict__ off, int* cnt, int* __restrict__ out_val) {
+    pdl_begin();
     const int E = min(*E_dev, cap_E);
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
         const int k = key[e], v = val[e];
@@ -363,6 +373,7 @@ __global__ void __launch_bounds__(256) k_fill(const int* __restrict__ key, const
 // through `tmp` (O(len^2 / 32) per warp; in-degrees are bounded by the number of expanded rows).
 __global__ void __launch_bounds__(256) k_sort_rows(const int* __restrict__ off, const int* __restrict__ n_dev,
                                                    int cap_n, int* vals, int* tmp) {
+    pdl_begin();
     const int n = min(*n_dev, cap_n);
     const int lane = lane_id();
     const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -482,6 +493,7 @@ __device__ void csr_small_build(const int* key, const int* val, int E, int n, in
 __global__ void __launch_bounds__(1024) k_build_csr_small(const int* key, const int* val, const int* __restrict__ E_dev,
                                                           int cap_E, const int* __restrict__ n_dev, int cap_n, int* off,
                                                           int* out_val, int* tmp, float* dinv, int* nnz_out) {
+    pdl_begin();
     __shared__ CsrSmallSmem sm;
     const int E = min(*E_dev, cap_E);
     const int n = min(min(*n_dev, cap_n), SMALL_N);
@@ -501,6 +513,7 @@ __global__ void __launch_bounds__(1024) k_cls_prep(
     const int* __restrict__ blk1_src, const int* __restrict__ blk1_dst, const int* __restrict__ E1_dev, int cap_blk,
     int* cl_src0, int* cl_dst0, int* cl_src1, int* cl_dst1, int* in_off0, int* in_src0, float* dinv0, int* in_off1,
     int* in_src1, float* dinv1, int* out_off1, int* out_dst1, int* tmp, int* nnz_out3, int* tgt_of_row) {
+    pdl_begin();
     __shared__ CsrSmallSmem sm;
     const int tid = threadIdx.x;
     const int A = min(min(*A_dev, cap_A), SMALL_N);
@@ -545,6 +558,7 @@ __global__ void __launch_bounds__(FC_THREADS) k_filter_compact(
     const int* __restrict__ m_dev, int cap_m, const uint32_t* __restrict__ bm_cols,
     int* __restrict__ out_src, int* __restrict__ out_dst, int cap_out, int* __restrict__ count_out,
     int* overflow, unsigned long long* status, unsigned int* counters) {
+    pdl_begin();
     __shared__ unsigned long long s_scan[FC_THREADS / 32 + 2];
     __shared__ int s_tile;
     __shared__ unsigned long long s_excl;
@@ -598,17 +612,20 @@ __global__ void __launch_bounds__(FC_THREADS) k_filter_compact(
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_bitmap_set_list(const int* __restrict__ ids, const int* __restrict__ cnt_dev,
                                                          int cap, uint32_t* bm) {
+    pdl_begin();
     const int n = min(*cnt_dev, cap);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) bitmap_set(bm, ids[i]);
 }
 __global__ void __launch_bounds__(256) k_bitmap_clear_list(const int* __restrict__ ids, const int* __restrict__ cnt_dev,
                                                            int cap, uint32_t* bm) {
+    pdl_begin();
     const int n = min(*cnt_dev, cap);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) bm[ids[i] >> 5] = 0u;
 }
 // dst[off .. off+n) = src[0..n); *total = off + n   (next-hop assembly, main.py:236-238)
 __global__ void __launch_bounds__(256) k_append_list(const int* __restrict__ src, const int* __restrict__ cnt_dev,
                                                      int cap, int* __restrict__ dst, int off, int* total) {
+    pdl_begin();
     const int n = min(*cnt_dev, cap);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[off + i] = src[i];
     if (blockIdx.x == 0 && threadIdx.x == 0 && total) *total = off + n;
@@ -619,6 +636,7 @@ __global__ void __launch_bounds__(256) k_step_reset(const int* __restrict__ targ
                                                     int cap_B, int* __restrict__ lists, long long list_stride,
                                                     int nlists, int* __restrict__ P0_dev, uint32_t* bm_a,
                                                     uint32_t* bm_b) {
+    pdl_begin();
     const int n = min(*B_dev, cap_B);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int t = targets[i];
@@ -630,11 +648,13 @@ __global__ void __launch_bounds__(256) k_step_reset(const int* __restrict__ targ
 }
 __global__ void __launch_bounds__(256) k_i64_to_i32(const int64_t* __restrict__ in, int* __restrict__ out, int n,
                                                     int* count_out) {
+    pdl_begin();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = (int)in[i];
     if (count_out && blockIdx.x == 0 && threadIdx.x == 0) *count_out = n;
 }
 __global__ void __launch_bounds__(256) k_i32_to_i64(const int* __restrict__ in, const int* __restrict__ cnt_dev,
                                                     int cap, int64_t* __restrict__ out) {
+    pdl_begin();
     const int n = cnt_dev ? min(*cnt_dev, cap) : cap;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = (int64_t)in[i];
 }
@@ -655,7 +675,7 @@ int grapes_row_offsets(grapes_ctx* ctx, const int64_t* indptr, const int* rows, 
                        int* row_off, int* m_dev, int cap_m, uint32_t* bm_rows, uint32_t* bm_batch,
                        int* overflow, void* stream) {
     GRAPES_REQUIRE(ctx && indptr && rows && P_dev && row_off && m_dev && overflow, "null argument");
-    k_row_offsets<<<1, 1024, 0, (cudaStream_t)stream>>>(indptr, rows, P_dev, cap_P, row_off, m_dev, cap_m,
+    pdl((k_row_offsets), 1, 1024, 0, (cudaStream_t)stream)(indptr, rows, P_dev, cap_P, row_off, m_dev, cap_m,
                                                           bm_rows, bm_batch, overflow);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
@@ -666,7 +686,7 @@ int grapes_expand_rows(grapes_ctx* ctx, const int64_t* indptr, const int* indice
                        const int* P_dev, int cap_P, const int* row_off, const int* m_dev, int cap_m,
                        int* e_row, int* e_col, uint32_t* bm_batch, void* stream) {
     GRAPES_REQUIRE(ctx && indptr && indices && rows && P_dev && row_off && m_dev && e_row && e_col, "null argument");
-    k_expand<<<grid_for(ctx, cap_m, 256), 256, 0, (cudaStream_t)stream>>>(indptr, indices, rows, P_dev, cap_P,
+    pdl((k_expand), grid_for(ctx, cap_m, 256), 256, 0, (cudaStream_t)stream)(indptr, indices, rows, P_dev, cap_P,
                                                                           row_off, m_dev, e_row, e_col, bm_batch);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
@@ -687,7 +707,7 @@ int grapes_expand_frontier(grapes_ctx* ctx, const int64_t* indptr, const int* in
     int blocks = grapes_div_up(cap_m, EXF_THREADS * 2);
     if (blocks > ctx->sm_count * 2) blocks = ctx->sm_count * 2;
     if (blocks < 1) blocks = 1;
-    k_expand_fused<<<blocks, EXF_THREADS, smem, (cudaStream_t)stream>>>(indptr, indices, rows, P_dev, cap_P, row_off, m_dev,
+    pdl((k_expand_fused), blocks, EXF_THREADS, smem, (cudaStream_t)stream)(indptr, indices, rows, P_dev, cap_P, row_off, m_dev,
                                                                         cap_m, e_row, e_col, bm_rows, bm_batch, overflow);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
@@ -704,7 +724,7 @@ int grapes_rank_nodes(grapes_ctx* ctx, const uint32_t* bm_batch, const uint32_t*
     GRAPES_REQUIRE(!nb_nodes || (nb_local && pref_nb && c_dev), "nb_nodes needs nb_local, pref_nb, c_dev");
     const int tiles = grapes_div_up(ctx->num_words, RANK_TILE);
     GRAPES_REQUIRE(tiles <= ctx->scan_cap_tiles, "scan scratch too small");
-    k_rank_scan<<<tiles, RANK_THREADS, 0, (cudaStream_t)stream>>>(
+    pdl((k_rank_scan), tiles, RANK_THREADS, 0, (cudaStream_t)stream)(
         bm_batch, bm_prev, ctx->num_words, pref_batch, pref_nb, batch_nodes, nb_nodes, nb_local, nb_index, ind_bits,
         bm_ind, ind_rows, hop, cap_n, n_dev, c_dev, overflow, ctx->scan_status, ctx->scan_counters);
         grapes_count_launches(1);
@@ -716,7 +736,7 @@ int grapes_edges_to_local(grapes_ctx* ctx, const int* rows, const int* e_row, co
                           int cap_m, const uint32_t* bm, const int* pref, int* e_src, int* e_dst, int* cnt_hist,
                           void* stream) {
     GRAPES_REQUIRE(ctx && rows && e_row && e_col && m_dev && bm && pref && e_src && e_dst, "null argument");
-    k_edge_local<<<grid_for(ctx, cap_m, 256), 256, 0, (cudaStream_t)stream>>>(rows, e_row, e_col, m_dev, bm, pref,
+    pdl((k_edge_local), grid_for(ctx, cap_m, 256), 256, 0, (cudaStream_t)stream)(rows, e_row, e_col, m_dev, bm, pref,
                                                                               e_src, e_dst, cnt_hist);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
@@ -726,7 +746,7 @@ int grapes_edges_to_local(grapes_ctx* ctx, const int* rows, const int* e_row, co
 int grapes_relabel(grapes_ctx* ctx, const int* ids, const int* count_dev, int cap, const uint32_t* bm,
                    const int* pref, int* out, void* stream) {
     GRAPES_REQUIRE(ctx && ids && count_dev && bm && pref && out, "null argument");
-    k_relabel<<<grid_for(ctx, cap, 256), 256, 0, (cudaStream_t)stream>>>(ids, count_dev, cap, bm, pref, out);
+    pdl((k_relabel), grid_for(ctx, cap, 256), 256, 0, (cudaStream_t)stream)(ids, count_dev, cap, bm, pref, out);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
@@ -739,7 +759,7 @@ int grapes_build_csr(grapes_ctx* ctx, const int* key, const int* val, const int*
                    "null argument");
     cudaStream_t s = (cudaStream_t)stream;
     if (!hist_done && cap_n <= SMALL_N) {
-        k_build_csr_small<<<1, 1024, 0, s>>>(key, val, E_dev, cap_E, n_dev, cap_n, off, sorted_val, tmp_val, dinv,
+        pdl((k_build_csr_small), 1, 1024, 0, s)(key, val, E_dev, cap_E, n_dev, cap_n, off, sorted_val, tmp_val, dinv,
                                              nnz_dev);
         grapes_count_launches(1);
         GRAPES_LAUNCH_OK();
@@ -749,15 +769,15 @@ int grapes_build_csr(grapes_ctx* ctx, const int* key, const int* val, const int*
     GRAPES_REQUIRE(tiles <= ctx->scan_cap_tiles, "scan scratch too small for cap_n");
     if (!hist_done) {
         // cnt_scratch is all-zero on entry by contract (zero-initialised by the caller; k_fill returns it to zero)
-        k_hist<<<grid_for(ctx, cap_E, 256), 256, 0, s>>>(key, val, E_dev, cap_E, cnt_scratch);
+        pdl((k_hist), grid_for(ctx, cap_E, 256), 256, 0, s)(key, val, E_dev, cap_E, cnt_scratch);
         grapes_count_launches(1);
     }
-    k_scan_i32<<<grapes_max_i(tiles, 1), SCAN_THREADS, 0, s>>>(cnt_scratch, n_dev, cap_n, off, dinv, nnz_dev,
+    pdl((k_scan_i32), grapes_max_i(tiles, 1), SCAN_THREADS, 0, s)(cnt_scratch, n_dev, cap_n, off, dinv, nnz_dev,
                                                               ctx->scan_status, ctx->scan_counters);
     grapes_count_launches(1);
-    k_fill<<<grid_for(ctx, cap_E, 256), 256, 0, s>>>(key, val, E_dev, cap_E, off, cnt_scratch, sorted_val);
+    pdl((k_fill), grid_for(ctx, cap_E, 256), 256, 0, s)(key, val, E_dev, cap_E, off, cnt_scratch, sorted_val);
     grapes_count_launches(1);
-    k_sort_rows<<<grid_for(ctx, cap_n, 256), 256, 0, s>>>(off, n_dev, cap_n, sorted_val, tmp_val);
+    pdl((k_sort_rows), grid_for(ctx, cap_n, 256), 256, 0, s)(off, n_dev, cap_n, sorted_val, tmp_val);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
@@ -774,7 +794,7 @@ int grapes_classifier_prep(grapes_ctx* ctx, const uint32_t* bm_all, const int* p
                        in_src0 && dinv0 && in_off1 && in_src1 && dinv1 && out_off1 && out_dst1 && tmp && nnz_dev3,
                    "null argument");
     GRAPES_REQUIRE(cap_A <= SMALL_N, "sampled subgraph too large for the single-CTA preparation");
-    k_cls_prep<<<1, 1024, 0, (cudaStream_t)stream>>>(bm_all, pref_all, A_dev, cap_A, targets, B_dev, cap_B, target_local,
+    pdl((k_cls_prep), 1, 1024, 0, (cudaStream_t)stream)(bm_all, pref_all, A_dev, cap_A, targets, B_dev, cap_B, target_local,
                                                       blk0_src, blk0_dst, E0_dev, blk1_src, blk1_dst, E1_dev, cap_blk,
                                                       cl_src0, cl_dst0, cl_src1, cl_dst1, in_off0, in_src0, dinv0,
                                                       in_off1, in_src1, dinv1, out_off1, out_dst1, tmp, nnz_dev3,
@@ -791,7 +811,7 @@ int grapes_slice_block(grapes_ctx* ctx, const int* rows, const int* e_row, const
                    "null argument");
     const int tiles = grapes_max_i(grapes_div_up(cap_m, FC_TILE), 1);
     GRAPES_REQUIRE(tiles <= ctx->scan_cap_tiles, "scan scratch too small for cap_m");
-    k_filter_compact<<<tiles, FC_THREADS, 0, (cudaStream_t)stream>>>(rows, e_row, e_col, m_dev, cap_m, bm_cols,
+    pdl((k_filter_compact), tiles, FC_THREADS, 0, (cudaStream_t)stream)(rows, e_row, e_col, m_dev, cap_m, bm_cols,
                                                                      out_src, out_dst, cap_out, count_dev, overflow,
                                                                      ctx->scan_status, ctx->scan_counters);
     grapes_count_launches(1);
@@ -801,7 +821,7 @@ int grapes_slice_block(grapes_ctx* ctx, const int* rows, const int* e_row, const
 
 int grapes_bitmap_set(grapes_ctx* ctx, const int* ids, const int* count_dev, int cap, uint32_t* bm, void* stream) {
     GRAPES_REQUIRE(ctx && ids && count_dev && bm, "null argument");
-    k_bitmap_set_list<<<grid_for(ctx, cap, 256), 256, 0, (cudaStream_t)stream>>>(ids, count_dev, cap, bm);
+    pdl((k_bitmap_set_list), grid_for(ctx, cap, 256), 256, 0, (cudaStream_t)stream)(ids, count_dev, cap, bm);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
@@ -810,7 +830,7 @@ int grapes_bitmap_set(grapes_ctx* ctx, const int* ids, const int* count_dev, int
 int grapes_bitmap_clear_words(grapes_ctx* ctx, const int* ids, const int* count_dev, int cap, uint32_t* bm,
                               void* stream) {
     GRAPES_REQUIRE(ctx && ids && count_dev && bm, "null argument");
-    k_bitmap_clear_list<<<grid_for(ctx, cap, 256), 256, 0, (cudaStream_t)stream>>>(ids, count_dev, cap, bm);
+    pdl((k_bitmap_clear_list), grid_for(ctx, cap, 256), 256, 0, (cudaStream_t)stream)(ids, count_dev, cap, bm);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
@@ -819,7 +839,7 @@ int grapes_bitmap_clear_words(grapes_ctx* ctx, const int* ids, const int* count_
 int grapes_append_list(grapes_ctx* ctx, const int* src, const int* count_dev, int cap, int* dst, int dst_offset,
                        int* total_dev, void* stream) {
     GRAPES_REQUIRE(ctx && src && count_dev && dst, "null argument");
-    k_append_list<<<grid_for(ctx, cap, 256), 256, 0, (cudaStream_t)stream>>>(src, count_dev, cap, dst, dst_offset,
+    pdl((k_append_list), grid_for(ctx, cap, 256), 256, 0, (cudaStream_t)stream)(src, count_dev, cap, dst, dst_offset,
                                                                              total_dev);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
@@ -829,7 +849,7 @@ int grapes_append_list(grapes_ctx* ctx, const int* src, const int* count_dev, in
 int grapes_step_reset(grapes_ctx* ctx, const int* targets, const int* B_dev, int cap_B, int* lists,
                       int64_t list_stride, int nlists, int* P0_dev, uint32_t* bm_a, uint32_t* bm_b, void* stream) {
     GRAPES_REQUIRE(ctx && targets && B_dev && lists && nlists >= 1, "null argument");
-    k_step_reset<<<grid_for(ctx, cap_B, 256), 256, 0, (cudaStream_t)stream>>>(targets, B_dev, cap_B, lists,
+    pdl((k_step_reset), grid_for(ctx, cap_B, 256), 256, 0, (cudaStream_t)stream)(targets, B_dev, cap_B, lists,
                                                                               (long long)list_stride, nlists, P0_dev,
                                                                               bm_a, bm_b);
     grapes_count_launches(1);
@@ -839,7 +859,7 @@ int grapes_step_reset(grapes_ctx* ctx, const int* targets, const int* B_dev, int
 
 int grapes_ids_i64_to_i32(grapes_ctx* ctx, const int64_t* in, int n, int* out, int* count_dev, void* stream) {
     GRAPES_REQUIRE(ctx && out && (in || n == 0), "null argument");
-    k_i64_to_i32<<<grid_for(ctx, n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, n, count_dev);
+    pdl((k_i64_to_i32), grid_for(ctx, n, 256), 256, 0, (cudaStream_t)stream)(in, out, n, count_dev);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
@@ -847,7 +867,7 @@ int grapes_ids_i64_to_i32(grapes_ctx* ctx, const int64_t* in, int n, int* out, i
 
 int grapes_ids_i32_to_i64(grapes_ctx* ctx, const int* in, const int* count_dev, int cap, int64_t* out, void* stream) {
     GRAPES_REQUIRE(ctx && out && (in || cap == 0), "null argument");
-    k_i32_to_i64<<<grid_for(ctx, cap, 256), 256, 0, (cudaStream_t)stream>>>(in, count_dev, cap, out);
+    pdl((k_i32_to_i64), grid_for(ctx, cap, 256), 256, 0, (cudaStream_t)stream)(in, count_dev, cap, out);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;

@@ -5,6 +5,7 @@
 //   out = D^-1/2 (A_noloop + I) D^-1/2 (X W^T) + b,  deg = in-degree incl. the added self-loop.
 // Aggregation commutes with the dense transform, so it is done at the NARROWER width
 // (features for layer 1, the scalar / class logits for layer 2) -- DESIGN.md section 4.
+#define GRAPES_PDL_GROUP 2
 #include "common.cuh"
 
 template <int VEC> struct VecT;
@@ -45,6 +46,7 @@ __global__ void __launch_bounds__(256) k_agg(const float* __restrict__ X, int F,
                                              int num_ind, const float* __restrict__ bias, int relu,
                                              float* __restrict__ out, int ldo, float* __restrict__ out_hi,
                                              float* __restrict__ out_lo, int ones_col) {
+    pdl_begin();
     const int n = min(*n_dev, cap_n);
     const int lane = lane_id();
     const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -131,6 +133,7 @@ __global__ void __launch_bounds__(256, MINB) k_agg_rows(const float* __restrict_
                                                      const float* __restrict__ bias, int relu, float* __restrict__ out,
                                                      int ldo, float* __restrict__ out_hi, float* __restrict__ out_lo,
                                                      int ones_col) {
+    pdl_begin();
     const int n = min(*n_dev, cap_n);
     const int lane = lane_id();
     const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -273,6 +276,7 @@ __global__ void __launch_bounds__(256) k_agg_scalar(const float* __restrict__ z,
                                                     const int* __restrict__ in_src, const float* __restrict__ dinv,
                                                     const float* __restrict__ bias, float* __restrict__ out,
                                                     float* __restrict__ zero_out) {
+    pdl_begin();
     const int n = min(*n_dev, cap_n);
     const float b = bias ? bias[0] : 0.f;
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
@@ -298,6 +302,7 @@ __global__ void __launch_bounds__(256) k_agg_scalar(const float* __restrict__ z,
 //   dz[s] += sum_{e in row i, dst != s} dinv[s] dinv[dst] dl[dst]   s = e_src of row i   (k_dz_rows)
 __global__ void __launch_bounds__(256) k_dz_self(const float* __restrict__ dl, const int* __restrict__ n_dev, int cap_n,
                                                  const float* __restrict__ dinv, float* __restrict__ dz) {
+    pdl_begin();
     const int n = min(*n_dev, cap_n);
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
         dz[j] = dinv[j] * dinv[j] * dl[j];
@@ -306,6 +311,7 @@ __global__ void __launch_bounds__(256) k_dz_rows(const float* __restrict__ dl, c
                                                  const int* __restrict__ row_off, const int* __restrict__ e_src,
                                                  const int* __restrict__ e_dst, const float* __restrict__ dinv,
                                                  float* __restrict__ dz) {
+    pdl_begin();
     const int P = min(*P_dev, cap_P);
     const int lane = lane_id();
     const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -325,6 +331,7 @@ __global__ void __launch_bounds__(256) k_dz_rows(const float* __restrict__ dl, c
 
 // v[j] = 1 / n for j < n  (d mean(logits) / d logits, main.py:228)
 __global__ void __launch_bounds__(256) k_fill_inv_count(float* __restrict__ v, const int* __restrict__ n_dev, int cap_n) {
+    pdl_begin();
     const int n = min(*n_dev, cap_n);
     const float inv = n > 0 ? 1.0f / (float)n : 0.f;
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) v[j] = inv;
@@ -339,6 +346,7 @@ __global__ void __launch_bounds__(256) k_dz_fused(const float* __restrict__ dl, 
                                                   const uint32_t* __restrict__ bm_prev,
                                                   const int* __restrict__ batch_nodes, int nbA,
                                                   float* __restrict__ dz) {
+    pdl_begin();
     if ((int)blockIdx.x < nbA) {
         const int n = min(*n_dev, cap_n);
         for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += nbA * blockDim.x)
@@ -369,6 +377,7 @@ __global__ void __launch_bounds__(256) k_dz_fused(const float* __restrict__ dl, 
 // out[c] (+)= scale * sum_r part[r*ld + c], r < R (R from device or host)
 __global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ part, const int* __restrict__ R_dev, int R_cap,
                                                 int ld, int C, float scale, int accumulate, float* __restrict__ out) {
+    pdl_begin();
     const int R = R_dev ? min(*R_dev, R_cap) : R_cap;
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
         float a = 0.f;
@@ -382,6 +391,7 @@ __global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ part, 
 // column sums of a tall matrix M[R x C] in two deterministic stages: slab partials, then k_colsum
 __global__ void __launch_bounds__(256) k_colsum_slabs(const float* __restrict__ Mx, const int* __restrict__ R_dev,
                                                       int R_cap, int ld, int C, float* __restrict__ part) {
+    pdl_begin();
     const int R = min(*R_dev, R_cap);
     const int slabs = gridDim.y;
     const int rows_per = (R + slabs - 1) / slabs;
@@ -400,6 +410,7 @@ __global__ void __launch_bounds__(256) k_colsum_slabs(const float* __restrict__ 
 #define VS_CHUNK 4096
 __global__ void __launch_bounds__(256) k_vec_sum_part(const float* __restrict__ v, const int* __restrict__ n_dev,
                                                       int cap_n, float* __restrict__ part) {
+    pdl_begin();
     __shared__ float s[8];
     const int n = min(*n_dev, cap_n);
     const int base = blockIdx.x * VS_CHUNK;
@@ -413,6 +424,7 @@ __global__ void __launch_bounds__(256) k_vec_sum_part(const float* __restrict__ 
 __global__ void __launch_bounds__(1024) k_vec_sum_final(const float* __restrict__ part, int nparts,
                                                         const int* __restrict__ n_dev, int cap_n, float scale,
                                                         int divide_by_n, int accumulate, float* out) {
+    pdl_begin();
     __shared__ float s[32];
     const int n = n_dev ? min(*n_dev, cap_n) : cap_n;
     float a = 0.f;
@@ -523,6 +535,7 @@ __global__ void __launch_bounds__(G_THREADS) k_gemm(const float* __restrict__ A,
                                                     const int* __restrict__ M_dev, int M_cap, int N, int K,
                                                     const float* __restrict__ bias, int relu,
                                                     const float* __restrict__ relu_gate, int ldg) {
+    pdl_begin();
     __shared__ __align__(16) float As[GB_K][GB_M + G_PAD];
     __shared__ __align__(16) float Bs[GB_K][GB_N + G_PAD];
     const int M = M_dev ? min(*M_dev, M_cap) : M_cap;
@@ -560,6 +573,7 @@ __global__ void __launch_bounds__(G_THREADS) k_gemm_tn_splitk(const float* __res
                                                               const float* __restrict__ B, int ldb,
                                                               const int* __restrict__ R_dev, int R_cap, int M, int N,
                                                               float* __restrict__ part) {
+    pdl_begin();
     __shared__ __align__(16) float As[GB_K][GB_M + G_PAD];
     __shared__ __align__(16) float Bs[GB_K][GB_N + G_PAD];
     const int R = R_dev ? min(*R_dev, R_cap) : R_cap;
@@ -662,6 +676,7 @@ __global__ void __launch_bounds__(G_THREADS) k_gemm_s(const float* __restrict__ 
                                                       const int* __restrict__ M_dev, int M_cap, int N, int K,
                                                       const float* __restrict__ bias, int relu,
                                                       const float* __restrict__ relu_gate, int ldg) {
+    pdl_begin();
     __shared__ __align__(16) float As[GB_K][GS_M + GS_PAD];
     __shared__ __align__(16) float Bs[GB_K][GS_N + GS_PAD];
     const int M = M_dev ? min(*M_dev, M_cap) : M_cap;
@@ -696,6 +711,7 @@ __global__ void __launch_bounds__(G_THREADS) k_gemm_tn_splitk_s(const float* __r
                                                                 const float* __restrict__ B, int ldb,
                                                                 const int* __restrict__ R_dev, int R_cap, int M, int N,
                                                                 float* __restrict__ part) {
+    pdl_begin();
     __shared__ __align__(16) float As[GB_K][GS_M + GS_PAD];
     __shared__ __align__(16) float Bs[GB_K][GS_N + GS_PAD];
     const int R = R_dev ? min(*R_dev, R_cap) : R_cap;
@@ -727,6 +743,7 @@ __global__ void __launch_bounds__(G_THREADS) k_gemm_tn_splitk_s(const float* __r
 // out[i] (+)= scale * sum_s part[s*size + i]
 __global__ void __launch_bounds__(256) k_reduce_slabs(const float* __restrict__ part, int slabs, int size, float scale,
                                                       int accumulate, float* __restrict__ out) {
+    pdl_begin();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < size; i += gridDim.x * blockDim.x) {
         float a = 0.f;
 #pragma unroll 8
@@ -747,6 +764,7 @@ __global__ void __launch_bounds__(G_THREADS) k_l1_fwd(const float* __restrict__ 
                                                       int cap_n, int K, const float* __restrict__ W1, int ldw, int D,
                                                       const float* __restrict__ b1, const float* __restrict__ w2,
                                                       float* __restrict__ z) {
+    pdl_begin();
     __shared__ __align__(16) float As[GB_K][GB_M + G_PAD];
     __shared__ __align__(16) float Bs[GB_K][GB_N + G_PAD];
     const int n = min(*n_dev, cap_n);
@@ -790,6 +808,7 @@ __global__ void __launch_bounds__(G_THREADS) k_l1_bwd(const float* __restrict__ 
                                                       const float* __restrict__ b1, const float* __restrict__ w2,
                                                       const float* __restrict__ dz, float* __restrict__ dpre, int ldd,
                                                       float* __restrict__ dw2_part, float* __restrict__ db1_part) {
+    pdl_begin();
     __shared__ __align__(16) float As[GB_K][GB_M + G_PAD];
     __shared__ __align__(16) float Bs[GB_K][GB_N + G_PAD];
     __shared__ float red[16][GB_N];
@@ -875,11 +894,11 @@ int grapes_aggregate(grapes_ctx* ctx, const float* X, int F, int ldx, const int*
     if (a16 && (F % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && (ldo - F <= 32) && cap_n >= 4096) {
         // frontier-sized: R rows per warp with interleaved load chains (variant chosen by grapes_agg_variant, default 0)
 #define AGG_LAUNCH(RR, MB)                                                                                              \
-    k_agg_rows<RR, MB><<<grid_for(ctx, (long long)grapes_div_up(cap_n, RR) * 32, 256, MB), 256, 0, s>>>(                 \
+    pdl((k_agg_rows<RR, MB>), grid_for(ctx, (long long)grapes_div_up(cap_n, RR) * 32, 256, MB), 256, 0, s)(                 \
         X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias, relu, out, ldo, out_hi, out_lo,  \
         ones_col)
         switch (g_agg_variant) {
-            case 1: k_agg<4><<<blocks, 256, 0, s>>>(X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind,
+            case 1: pdl((k_agg<4>), blocks, 256, 0, s)(X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind,
                                                     bias, relu, out, ldo, out_hi, out_lo, ones_col); break;
             case 2: AGG_LAUNCH(2, 6); break;
             case 3: AGG_LAUNCH(2, 4); break;
@@ -889,13 +908,13 @@ int grapes_aggregate(grapes_ctx* ctx, const float* X, int F, int ldx, const int*
             default: AGG_LAUNCH(2, 4); break;      // measured best on B200 (products-shaped hop, 65k rows): 2 rows per warp
         }
     } else if (a16 && (F % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0))
-        k_agg<4><<<blocks, 256, 0, s>>>(X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias,
+        pdl((k_agg<4>), blocks, 256, 0, s)(X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias,
                                         relu, out, ldo, out_hi, out_lo, ones_col);
     else if (a8 && (F % 2 == 0) && (ldx % 2 == 0) && (ldo % 2 == 0))
-        k_agg<2><<<blocks, 256, 0, s>>>(X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias,
+        pdl((k_agg<2>), blocks, 256, 0, s)(X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias,
                                         relu, out, ldo, out_hi, out_lo, ones_col);
     else
-        k_agg<1><<<blocks, 256, 0, s>>>(X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias,
+        pdl((k_agg<1>), blocks, 256, 0, s)(X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias,
                                         relu, out, ldo, out_hi, out_lo, ones_col);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
@@ -907,7 +926,7 @@ int grapes_aggregate_scalar(grapes_ctx* ctx, const float* z, int nparts, int par
                             void* stream) {
     GRAPES_REQUIRE(ctx && z && n_dev && in_off && in_src && dinv && out, "null argument");
     GRAPES_REQUIRE(nparts >= 1, "nparts >= 1");
-    k_agg_scalar<<<grid_for(ctx, cap_n, 256), 256, 0, (cudaStream_t)stream>>>(z, nparts, part_stride, n_dev, cap_n, in_off, in_src, dinv,
+    pdl((k_agg_scalar), grid_for(ctx, cap_n, 256), 256, 0, (cudaStream_t)stream)(z, nparts, part_stride, n_dev, cap_n, in_off, in_src, dinv,
                                                                               bias, out, zero_out);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
@@ -921,15 +940,15 @@ int grapes_aggregate_scalar_T(grapes_ctx* ctx, const float* dl, const int* n_dev
     cudaStream_t s = (cudaStream_t)stream;
     if (bm_prev && batch_nodes) {
         const int nbA = grid_for(ctx, cap_n, 256), nbB = grid_for(ctx, (long long)cap_P * 32, 256);
-        k_dz_fused<<<nbA + nbB, 256, 0, s>>>(dl, n_dev, cap_n, P_dev, cap_P, row_off, e_src, e_dst, dinv, bm_prev,
+        pdl((k_dz_fused), nbA + nbB, 256, 0, s)(dl, n_dev, cap_n, P_dev, cap_P, row_off, e_src, e_dst, dinv, bm_prev,
                                              batch_nodes, nbA, dz);
         grapes_count_launches(1);
         GRAPES_LAUNCH_OK();
         return GRAPES_OK;
     }
-    k_dz_self<<<grid_for(ctx, cap_n, 256), 256, 0, s>>>(dl, n_dev, cap_n, dinv, dz);
+    pdl((k_dz_self), grid_for(ctx, cap_n, 256), 256, 0, s)(dl, n_dev, cap_n, dinv, dz);
     grapes_count_launches(1);
-    k_dz_rows<<<grid_for(ctx, (long long)cap_P * 32, 256), 256, 0, s>>>(dl, P_dev, cap_P, row_off, e_src, e_dst, dinv,
+    pdl((k_dz_rows), grid_for(ctx, (long long)cap_P * 32, 256), 256, 0, s)(dl, P_dev, cap_P, row_off, e_src, e_dst, dinv,
                                                                          dz);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
@@ -938,7 +957,7 @@ int grapes_aggregate_scalar_T(grapes_ctx* ctx, const float* dl, const int* n_dev
 
 int grapes_fill_inv_count(grapes_ctx* ctx, float* v, const int* n_dev, int cap_n, void* stream) {
     GRAPES_REQUIRE(ctx && v && n_dev, "null argument");
-    k_fill_inv_count<<<grid_for(ctx, cap_n, 256), 256, 0, (cudaStream_t)stream>>>(v, n_dev, cap_n);
+    pdl((k_fill_inv_count), grid_for(ctx, cap_n, 256), 256, 0, (cudaStream_t)stream)(v, n_dev, cap_n);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
@@ -949,9 +968,9 @@ int grapes_vec_sum(grapes_ctx* ctx, const float* v, const int* n_dev, int cap_n,
     GRAPES_REQUIRE(ctx && v && n_dev && out, "null argument");
     const int nparts = grapes_max_i(1, grapes_div_up(cap_n, VS_CHUNK));
     GRAPES_REQUIRE((size_t)nparts * sizeof(float) <= ctx->partials_bytes, "partial buffer too small");
-    k_vec_sum_part<<<nparts, 256, 0, (cudaStream_t)stream>>>(v, n_dev, cap_n, ctx->partials);
+    pdl((k_vec_sum_part), nparts, 256, 0, (cudaStream_t)stream)(v, n_dev, cap_n, ctx->partials);
     grapes_count_launches(1);
-    k_vec_sum_final<<<1, 1024, 0, (cudaStream_t)stream>>>(ctx->partials, nparts, n_dev, cap_n, scale, divide_by_n,
+    pdl((k_vec_sum_final), 1, 1024, 0, (cudaStream_t)stream)(ctx->partials, nparts, n_dev, cap_n, scale, divide_by_n,
                                                           accumulate, out);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
@@ -971,10 +990,10 @@ int grapes_gemm(grapes_ctx* ctx, int layout, const float* A, int lda, const floa
         // classifier-sized product: 64x64 tiles so the grid covers the GPU
         dim3 grid(grapes_div_up(N, GS_N), grapes_min_i(grapes_div_up(M_cap, GS_M), 65535));
         switch (layout & 3) {
-            case 3: k_gemm_s<true, true><<<grid, G_THREADS, 0, s>>>(A, lda, B, ldb, C, ldc, M_dev, M_cap, N, K, bias, relu, relu_gate, ldg); break;
-            case 1: k_gemm_s<true, false><<<grid, G_THREADS, 0, s>>>(A, lda, B, ldb, C, ldc, M_dev, M_cap, N, K, bias, relu, relu_gate, ldg); break;
-            case 2: k_gemm_s<false, true><<<grid, G_THREADS, 0, s>>>(A, lda, B, ldb, C, ldc, M_dev, M_cap, N, K, bias, relu, relu_gate, ldg); break;
-            default: k_gemm_s<false, false><<<grid, G_THREADS, 0, s>>>(A, lda, B, ldb, C, ldc, M_dev, M_cap, N, K, bias, relu, relu_gate, ldg); break;
+            case 3: pdl((k_gemm_s<true, true>), grid, G_THREADS, 0, s)(A, lda, B, ldb, C, ldc, M_dev, M_cap, N, K, bias, relu, relu_gate, ldg); break;
+            case 1: pdl((k_gemm_s<true, false>), grid, G_THREADS, 0, s)(A, lda, B, ldb, C, ldc, M_dev, M_cap, N, K, bias, relu, relu_gate, ldg); break;
+            case 2: pdl((k_gemm_s<false, true>), grid, G_THREADS, 0, s)(A, lda, B, ldb, C, ldc, M_dev, M_cap, N, K, bias, relu, relu_gate, ldg); break;
+            default: pdl((k_gemm_s<false, false>), grid, G_THREADS, 0, s)(A, lda, B, ldb, C, ldc, M_dev, M_cap, N, K, bias, relu, relu_gate, ldg); break;
         }
         GRAPES_LAUNCH_OK();
         return GRAPES_OK;
@@ -985,10 +1004,10 @@ int grapes_gemm(grapes_ctx* ctx, int layout, const float* A, int lda, const floa
     tiles_m = grapes_min_i(tiles_m, max_y);
     dim3 grid(tiles_n, tiles_m);
     switch (layout & 3) {
-        case 3: k_gemm<true, true><<<grid, G_THREADS, 0, s>>>(A, lda, B, ldb, C, ldc, M_dev, M_cap, N, K, bias, relu, relu_gate, ldg); break;
-        case 1: k_gemm<true, false><<<grid, G_THREADS, 0, s>>>(A, lda, B, ldb, C, ldc, M_dev, M_cap, N, K, bias, relu, relu_gate, ldg); break;
-        case 2: k_gemm<false, true><<<grid, G_THREADS, 0, s>>>(A, lda, B, ldb, C, ldc, M_dev, M_cap, N, K, bias, relu, relu_gate, ldg); break;
-        default: k_gemm<false, false><<<grid, G_THREADS, 0, s>>>(A, lda, B, ldb, C, ldc, M_dev, M_cap, N, K, bias, relu, relu_gate, ldg); break;
+        case 3: pdl((k_gemm<true, true>), grid, G_THREADS, 0, s)(A, lda, B, ldb, C, ldc, M_dev, M_cap, N, K, bias, relu, relu_gate, ldg); break;
+        case 1: pdl((k_gemm<true, false>), grid, G_THREADS, 0, s)(A, lda, B, ldb, C, ldc, M_dev, M_cap, N, K, bias, relu, relu_gate, ldg); break;
+        case 2: pdl((k_gemm<false, true>), grid, G_THREADS, 0, s)(A, lda, B, ldb, C, ldc, M_dev, M_cap, N, K, bias, relu, relu_gate, ldg); break;
+        default: pdl((k_gemm<false, false>), grid, G_THREADS, 0, s)(A, lda, B, ldb, C, ldc, M_dev, M_cap, N, K, bias, relu, relu_gate, ldg); break;
     }
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
@@ -1006,10 +1025,10 @@ int grapes_gemm_tn(grapes_ctx* ctx, const float* A, int lda, const float* B, int
     const size_t need = (size_t)slabs * M * N * sizeof(float);
     GRAPES_REQUIRE(need <= ctx->partials_bytes, "split-K partial buffer too small");
     dim3 grid(tiles_n, tiles_m, slabs);
-    if (small) k_gemm_tn_splitk_s<<<grid, G_THREADS, 0, s>>>(A, lda, B, ldb, R_dev, R_cap, M, N, ctx->partials);
-    else k_gemm_tn_splitk<<<grid, G_THREADS, 0, s>>>(A, lda, B, ldb, R_dev, R_cap, M, N, ctx->partials);
+    if (small) pdl((k_gemm_tn_splitk_s), grid, G_THREADS, 0, s)(A, lda, B, ldb, R_dev, R_cap, M, N, ctx->partials);
+    else pdl((k_gemm_tn_splitk), grid, G_THREADS, 0, s)(A, lda, B, ldb, R_dev, R_cap, M, N, ctx->partials);
     grapes_count_launches(1);
-    k_reduce_slabs<<<grid_for(ctx, (long long)M * N, 256), 256, 0, s>>>(ctx->partials, slabs, M * N, scale, accumulate,
+    pdl((k_reduce_slabs), grid_for(ctx, (long long)M * N, 256), 256, 0, s)(ctx->partials, slabs, M * N, scale, accumulate,
                                                                        out);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
@@ -1025,9 +1044,9 @@ int grapes_colsum(grapes_ctx* ctx, const float* Mx, const int* R_dev, int R_cap,
     const int slabs = grapes_max_i(1, grapes_min_i(ctx->sm_count, grapes_div_up(R_cap, 64)));
     GRAPES_REQUIRE((size_t)slabs * C * sizeof(float) <= ctx->partials_bytes, "partial buffer too small");
     dim3 grid(grapes_div_up(C, 256), slabs);
-    k_colsum_slabs<<<grid, 256, 0, s>>>(Mx, R_dev, R_cap, ld, C, ctx->partials);
+    pdl((k_colsum_slabs), grid, 256, 0, s)(Mx, R_dev, R_cap, ld, C, ctx->partials);
     grapes_count_launches(1);
-    k_colsum<<<grapes_div_up(C, 256), 256, 0, s>>>(ctx->partials, nullptr, slabs, C, C, scale, accumulate, out);
+    pdl((k_colsum), grapes_div_up(C, 256), 256, 0, s)(ctx->partials, nullptr, slabs, C, C, scale, accumulate, out);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
@@ -1037,7 +1056,7 @@ int grapes_sampler_l1_fwd(grapes_ctx* ctx, const float* Y, int ldy, const int* n
                           const float* W1, int ldw, int D, const float* b1, const float* w2, float* z, void* stream) {
     GRAPES_REQUIRE(ctx && Y && n_dev && W1 && b1 && w2 && z, "null argument");
     const int blocks = grapes_max_i(1, grapes_min_i(grapes_div_up(cap_n, GB_M), ctx->sm_count * 2));
-    k_l1_fwd<<<blocks, G_THREADS, 0, (cudaStream_t)stream>>>(Y, ldy, n_dev, cap_n, K, W1, ldw, D, b1, w2, z);
+    pdl((k_l1_fwd), blocks, G_THREADS, 0, (cudaStream_t)stream)(Y, ldy, n_dev, cap_n, K, W1, ldw, D, b1, w2, z);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
@@ -1055,13 +1074,13 @@ int grapes_sampler_l1_bwd(grapes_ctx* ctx, const float* Y, int ldy, const int* n
     GRAPES_REQUIRE((size_t)2 * blocks * D * sizeof(float) <= ctx->partials_bytes, "partial buffer too small");
     float* dw2_part = ctx->partials;
     float* db1_part = ctx->partials + (size_t)blocks * D;
-    k_l1_bwd<<<blocks, G_THREADS, 0, s>>>(Y, ldy, n_dev, cap_n, K, W1, ldw, D, b1, w2, dz, dpre_scratch, D, dw2_part,
+    pdl((k_l1_bwd), blocks, G_THREADS, 0, s)(Y, ldy, n_dev, cap_n, K, W1, ldw, D, b1, w2, dz, dpre_scratch, D, dw2_part,
                                           db1_part);
     grapes_count_launches(1);
     // a CTA whose first tile is past n writes zeros (its loops do not run), so all `blocks` rows are valid
-    k_colsum<<<grapes_div_up(D, 256), 256, 0, s>>>(dw2_part, nullptr, blocks, D, D, scale, accumulate, gw2);
+    pdl((k_colsum), grapes_div_up(D, 256), 256, 0, s)(dw2_part, nullptr, blocks, D, D, scale, accumulate, gw2);
     grapes_count_launches(1);
-    k_colsum<<<grapes_div_up(D, 256), 256, 0, s>>>(db1_part, nullptr, blocks, D, D, scale, accumulate, gb1);
+    pdl((k_colsum), grapes_div_up(D, 256), 256, 0, s)(db1_part, nullptr, blocks, D, D, scale, accumulate, gb1);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     // gW1[D x K] += scale * dpre^T Y   (uses ctx->partials again, stream-ordered after the colsums)

@@ -14,6 +14,7 @@
 //               relu mask emitted as bits (warp ballot) for the backward
 #include <cuda.h>
 
+#define GRAPES_PDL_GROUP 4
 #include "common.cuh"
 
 #define TC_BM 128
@@ -166,6 +167,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) k_l1_fwd_tc(
     const int* __restrict__ n_dev, int cap_n, int K, int D, int stages, int wres, int presplit,
     const float* __restrict__ b1, const float* __restrict__ w2, float* __restrict__ zpart,
     uint32_t* __restrict__ maskT) {
+    pdl_begin();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // SWIZZLE_128B tiles: 1024 B aligned
     const int nkb = (K + TC_BK - 1) / TC_BK;
@@ -407,6 +409,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) k_l1_bwd_tc(
     const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmY_lo, int presplit, int col0,
     const int* __restrict__ n_dev, int cap_n, int NH, int NB, int stages, const uint32_t* __restrict__ maskT, int D,
     const float* __restrict__ dz, float* __restrict__ part, int debug) {
+    pdl_begin();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int a_bytes = NH * TCB_A_TILE;             // mask tiles of all halves
@@ -597,6 +600,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_l1_bwd_finalize(
     const float* __restrict__ part, int nparts, int D, int N, int col0, int K, const float* __restrict__ W1, int ldw,
     const float* __restrict__ b1, const float* __restrict__ w2, int ones_col, float scale, float* __restrict__ gW1,
     float* __restrict__ gb1, float* __restrict__ gw2) {
+    pdl_begin();
     __shared__ __align__(16) float sums[4 * FIN_THREADS];        // [groups][N], groups * N == 4096
     __shared__ float red[8];
     const int d = blockIdx.x;
@@ -650,6 +654,7 @@ __device__ __forceinline__ float to_tf32(float x) {
 }
 __global__ void __launch_bounds__(256) k_split_tf32(const float* __restrict__ src, int ld_src, int R, int K,
                                                     float* __restrict__ hi, float* __restrict__ lo, int ld_dst) {
+    pdl_begin();
     const long long total = (long long)R * ld_dst;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int r = (int)(i / ld_dst), c = (int)(i % ld_dst);
@@ -709,7 +714,7 @@ int grapes_split_tf32(grapes_ctx* ctx, const float* src, int ld_src, int R, int 
     int blocks = (int)((total + 255) / 256);
     if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
     if (blocks < 1) blocks = 1;
-    k_split_tf32<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, ld_src, R, K, hi, lo, ld_dst);
+    pdl((k_split_tf32), blocks, 256, 0, (cudaStream_t)stream)(src, ld_src, R, K, hi, lo, ld_dst);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
@@ -760,7 +765,7 @@ int grapes_sampler_l1_fwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo,
         GRAPES_CUDA_OK(cudaFuncSetAttribute(k_l1_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         attr = smem_bytes;
     }
-    k_l1_fwd_tc<<<blocks, TCF_THREADS, smem_bytes, (cudaStream_t)stream>>>(ma, ma_lo, mb_hi, mb_lo, n_dev, cap_n, K, D,
+    pdl((k_l1_fwd_tc), blocks, TCF_THREADS, smem_bytes, (cudaStream_t)stream)(ma, ma_lo, mb_hi, mb_lo, n_dev, cap_n, K, D,
                                                                            stages, wres, presplit, b1, w2, zpart, maskT);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
@@ -801,10 +806,10 @@ int grapes_sampler_l1_bwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo,
         int blocks = max_groups < ctx->sm_count ? max_groups : ctx->sm_count;
         if (blocks < 1) blocks = 1;
         GRAPES_REQUIRE((size_t)blocks * D * N * sizeof(float) <= ctx->partials_bytes, "split partial buffer too small");
-        k_l1_bwd_tc<<<blocks, TCB_THREADS, smem_bytes, s>>>(my, my_lo, Y_lo ? 1 : 0, col0, n_dev, cap_n, NH, NB, stages,
+        pdl((k_l1_bwd_tc), blocks, TCB_THREADS, smem_bytes, s)(my, my_lo, Y_lo ? 1 : 0, col0, n_dev, cap_n, NH, NB, stages,
                                                            maskT, D, dz, ctx->partials, g_tc_debug);
         grapes_count_launches(1);
-        k_l1_bwd_finalize<<<D, FIN_THREADS, 0, s>>>(ctx->partials, blocks, D, N, col0, K, W1, ldw, b1, w2, ones_col, scale,
+        pdl((k_l1_bwd_finalize), D, FIN_THREADS, 0, s)(ctx->partials, blocks, D, N, col0, K, W1, ldw, b1, w2, ones_col, scale,
                                                     gW1, gb1, gw2);
         grapes_count_launches(1);
     }

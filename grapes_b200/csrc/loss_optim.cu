@@ -3,6 +3,7 @@
 //   CrossEntropyLoss / BCEWithLogitsLoss + reg_param * sum(var(logits, dim=1))   main.py:120-123,260-261
 //   trajectory-balance / REINFORCE loss                                          main.py:271-282
 //   torch.optim.Adam (defaults betas=(0.9,0.999), eps=1e-8, no weight decay)     main.py:117-118
+#define GRAPES_PDL_GROUP 8
 #include "common.cuh"
 
 #define LOSS_THREADS 1024
@@ -29,6 +30,7 @@ __global__ void __launch_bounds__(256) k_loss_rows(const float* __restrict__ log
                                                    int B, const int64_t* __restrict__ labels_i64,
                                                    const float* __restrict__ labels_f32, float* __restrict__ dlogits,
                                                    float* __restrict__ row_loss) {
+    pdl_begin();
     const int lane = lane_id();
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (r >= B) return;
@@ -67,6 +69,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) k_loss_final(const float* __rest
                                                              const int* __restrict__ A_dev, int A_cap, int B,
                                                              const float* __restrict__ row_loss, float reg_param,
                                                              float* __restrict__ dlogits, float* loss_out) {
+    pdl_begin();
     __shared__ float s[32];
     const int A = min(*A_dev, A_cap);
     const int lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -108,6 +111,7 @@ __global__ void __launch_bounds__(LR2_WARPS * 32) k_loss_rows2(
     const int* __restrict__ tgt_of_row, const int* __restrict__ targets, int B,
     const int64_t* __restrict__ labels_i64, const float* __restrict__ labels_f32, float reg_param,
     float* __restrict__ dlogits, float* __restrict__ row_loss, float* __restrict__ colpart) {
+    pdl_begin();
     extern __shared__ float s_cols[];                    // [LR2_WARPS][C]
     const int A = min(*A_dev, A_cap);
     const int lane = lane_id(), warp = threadIdx.x >> 5;
@@ -172,6 +176,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) k_loss_final2(const int* __restr
                                                               const float* __restrict__ row_loss,
                                                               const float* __restrict__ colpart, int nblocks,
                                                               float* loss_out, float* __restrict__ colsum_out) {
+    pdl_begin();
     __shared__ float s[32];
     __shared__ float s_col[LOSS_THREADS];
     const int A = min(*A_dev, A_cap);
@@ -206,6 +211,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) k_loss_final2(const int* __restr
 //   TB       : loss_gfn = (log_z + tot + coef*loss_c)^2 ; d/dtheta = 2(...) * (dlog_z + dtot)      main.py:282
 //   REINFORCE: loss_gfn = -tot * loss_c                 ; d/dtheta = -loss_c * dtot               main.py:279
 __global__ void k_gfn_finalize(float* scal, float loss_coef, float log_z_init, int reinforce, int have_log_z) {
+    pdl_begin();
     const float loss_c = scal[GRAPES_SCAL_LOSS_C];
     const float tot = scal[GRAPES_SCAL_TOT_LOG_PROB];
     const float log_z = have_log_z ? scal[GRAPES_SCAL_LOG_Z_MEAN] - log_z_init : 0.f;
@@ -225,6 +231,7 @@ __global__ void k_gfn_finalize(float* scal, float loss_coef, float log_z_init, i
 // grad[i] = (*g) * dir[i]
 __global__ void __launch_bounds__(256) k_scale_by_dev(const float* __restrict__ dir, const float* __restrict__ g, int n,
                                                       float* __restrict__ grad) {
+    pdl_begin();
     const float gg = *g;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) grad[i] = gg * dir[i];
 }
@@ -233,6 +240,7 @@ __global__ void __launch_bounds__(256) k_scale_by_dev(const float* __restrict__ 
 __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                               float* __restrict__ v, int n, float lr, float beta1, float beta2,
                                               float eps, const float* __restrict__ step) {
+    pdl_begin();
     __shared__ float s_step_size, s_bc2_sqrt;
     if (threadIdx.x == 0) {
         const double t = (double)(*step) + 1.0;
@@ -251,7 +259,8 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float
         p[i] = p[i] - step_size * (mi / denom);
     }
 }
-__global__ void k_step_inc(float* step) { *step += 1.0f; }
+__global__ void k_step_inc(float* step) {
+    pdl_begin(); *step += 1.0f; }
 // finalize + scale in one launch: every block recomputes the scalar from the (read-only) inputs of `scal`, block 0
 // publishes the derived scalars; grad = g * direction for the gcn_gf and gcn_z parameter ranges.
 __global__ void __launch_bounds__(256) k_gfn_finalize_scale(float* scal, float loss_coef, float log_z_init, int reinforce,
@@ -259,6 +268,7 @@ __global__ void __launch_bounds__(256) k_gfn_finalize_scale(float* scal, float l
                                                             float* __restrict__ grad_gf,
                                                             const float* __restrict__ dir_z, int n_z,
                                                             float* __restrict__ grad_z) {
+    pdl_begin();
     const float loss_c = scal[GRAPES_SCAL_LOSS_C];
     const float tot = scal[GRAPES_SCAL_TOT_LOG_PROB];
     const float log_z = have_log_z ? scal[GRAPES_SCAL_LOG_Z_MEAN] - log_z_init : 0.f;
@@ -285,6 +295,7 @@ __global__ void __launch_bounds__(256) k_adam2(float* __restrict__ p, const floa
                                                float* __restrict__ v, int off0, int n0, float lr0, int off1, int n1,
                                                float lr1, float beta1, float beta2, float eps, float* steps,
                                                unsigned int* ticket) {
+    pdl_begin();
     __shared__ float s_step_size[2], s_bc2_sqrt[2];
     __shared__ int s_last;
     if (threadIdx.x < 2) {
@@ -318,6 +329,7 @@ __global__ void __launch_bounds__(256) k_adam2(float* __restrict__ p, const floa
 }
 
 __global__ void __launch_bounds__(256) k_fill_f32(float* p, float v, int n) {
+    pdl_begin();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
 }
 
@@ -343,21 +355,21 @@ int grapes_classifier_loss(grapes_ctx* ctx, const float* logits, int ldl, int C,
         GRAPES_REQUIRE(((size_t)A_cap + (size_t)nblocks * C) * sizeof(float) <= ctx->partials_bytes, "partial buffer too small");
         float* row_loss = ctx->partials;
         float* colpart = ctx->partials + A_cap;
-        k_loss_rows2<<<nblocks, LR2_WARPS * 32, LR2_WARPS * C * sizeof(float), s>>>(
+        pdl((k_loss_rows2), nblocks, LR2_WARPS * 32, LR2_WARPS * C * sizeof(float), s)(
             logits, ldl, C, A_dev, A_cap, tgt_of_row, targets, B, labels_i64, labels_f32, reg_param, dlogits, row_loss,
             colpart);
         grapes_count_launches(1);
-        k_loss_final2<<<1, LOSS_THREADS, 0, s>>>(A_dev, A_cap, C, row_loss, colpart, nblocks, loss_out, colsum_out);
+        pdl((k_loss_final2), 1, LOSS_THREADS, 0, s)(A_dev, A_cap, C, row_loss, colpart, nblocks, loss_out, colsum_out);
         grapes_count_launches(1);
         GRAPES_LAUNCH_OK();
         return GRAPES_OK;
     }
     GRAPES_CUDA_OK(cudaMemsetAsync(dlogits, 0, sizeof(float) * (size_t)A_cap * ldl, s));
     GRAPES_REQUIRE((size_t)B * sizeof(float) <= ctx->partials_bytes, "partial buffer too small");
-    k_loss_rows<<<grapes_div_up((long long)B * 32, 256), 256, 0, s>>>(logits, ldl, C, row_ids, targets, B, labels_i64,
+    pdl((k_loss_rows), grapes_div_up((long long)B * 32, 256), 256, 0, s)(logits, ldl, C, row_ids, targets, B, labels_i64,
                                                                       labels_f32, dlogits, ctx->partials);
     grapes_count_launches(1);
-    k_loss_final<<<1, LOSS_THREADS, 0, s>>>(logits, ldl, C, A_dev, A_cap, B, ctx->partials, reg_param, dlogits,
+    pdl((k_loss_final), 1, LOSS_THREADS, 0, s)(logits, ldl, C, A_dev, A_cap, B, ctx->partials, reg_param, dlogits,
                                             loss_out);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
@@ -368,7 +380,7 @@ int grapes_classifier_loss(grapes_ctx* ctx, const float* logits, int ldl, int C,
 int grapes_gfn_finalize(grapes_ctx* ctx, float* scal, float loss_coef, float log_z_init, int reinforce, int have_log_z,
                         void* stream) {
     GRAPES_REQUIRE(ctx && scal, "null argument");
-    k_gfn_finalize<<<1, 1, 0, (cudaStream_t)stream>>>(scal, loss_coef, log_z_init, reinforce, have_log_z);
+    pdl((k_gfn_finalize), 1, 1, 0, (cudaStream_t)stream)(scal, loss_coef, log_z_init, reinforce, have_log_z);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
@@ -377,7 +389,7 @@ int grapes_gfn_finalize(grapes_ctx* ctx, float* scal, float loss_coef, float log
 int grapes_scale_by_device_scalar(grapes_ctx* ctx, const float* dir, const float* g_dev, int n, float* grad,
                                   void* stream) {
     GRAPES_REQUIRE(ctx && dir && g_dev && grad, "null argument");
-    k_scale_by_dev<<<grid_for(ctx, n, 256), 256, 0, (cudaStream_t)stream>>>(dir, g_dev, n, grad);
+    pdl((k_scale_by_dev), grid_for(ctx, n, 256), 256, 0, (cudaStream_t)stream)(dir, g_dev, n, grad);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
@@ -388,10 +400,10 @@ int grapes_adam_step(grapes_ctx* ctx, float* params, const float* grads, float* 
                      void* stream) {
     GRAPES_REQUIRE(ctx && params && grads && exp_avg && exp_avg_sq && step_dev, "null argument");
     cudaStream_t s = (cudaStream_t)stream;
-    k_adam<<<grid_for(ctx, n, 256), 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+    pdl((k_adam), grid_for(ctx, n, 256), 256, 0, s)(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                  step_dev);
     grapes_count_launches(1);
-    if (increment_step) k_step_inc<<<1, 1, 0, s>>>(step_dev);
+    if (increment_step) pdl((k_step_inc), 1, 1, 0, s)(step_dev);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
@@ -401,7 +413,7 @@ int grapes_gfn_finalize_scale(grapes_ctx* ctx, float* scal, float loss_coef, flo
                               int have_log_z, const float* dir_gf, int n_gf, float* grad_gf, const float* dir_z,
                               int n_z, float* grad_z, void* stream) {
     GRAPES_REQUIRE(ctx && scal && dir_gf && grad_gf && (n_z == 0 || (dir_z && grad_z)), "null argument");
-    k_gfn_finalize_scale<<<grid_for(ctx, n_gf + n_z, 256), 256, 0, (cudaStream_t)stream>>>(
+    pdl((k_gfn_finalize_scale), grid_for(ctx, n_gf + n_z, 256), 256, 0, (cudaStream_t)stream)(
         scal, loss_coef, log_z_init, reinforce, have_log_z, dir_gf, n_gf, grad_gf, dir_z, n_z, grad_z);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
@@ -413,7 +425,7 @@ int grapes_adam_step2(grapes_ctx* ctx, float* params, const float* grads, float*
                       float* steps_dev, void* stream) {
     GRAPES_REQUIRE(ctx && params && grads && exp_avg && exp_avg_sq && steps_dev, "null argument");
     GRAPES_REQUIRE(n0 >= 0 && n1 >= 0 && n0 + n1 > 0, "empty parameter groups");
-    k_adam2<<<grid_for(ctx, n0 + n1, 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, off0, n0,
+    pdl((k_adam2), grid_for(ctx, n0 + n1, 256), 256, 0, (cudaStream_t)stream)(params, grads, exp_avg, exp_avg_sq, off0, n0,
                                                                            lr0, off1, n1, lr1, beta1, beta2, eps,
                                                                            steps_dev, ctx->scan_counters + 2);
     grapes_count_launches(1);
@@ -423,7 +435,7 @@ int grapes_adam_step2(grapes_ctx* ctx, float* params, const float* grads, float*
 
 int grapes_fill_f32(grapes_ctx* ctx, float* p, float value, int n, void* stream) {
     GRAPES_REQUIRE(ctx && p, "null argument");
-    k_fill_f32<<<grid_for(ctx, n, 256), 256, 0, (cudaStream_t)stream>>>(p, value, n);
+    pdl((k_fill_f32), grid_for(ctx, n, 256), 256, 0, (cudaStream_t)stream)(p, value, n);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;

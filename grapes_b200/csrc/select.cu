@@ -18,6 +18,7 @@
 // the same rule).  Integer counting only -> the selected set does not depend on scheduling.
 #include <cooperative_groups.h>
 
+#define GRAPES_PDL_GROUP 16
 #include "common.cuh"
 namespace cg = cooperative_groups;
 
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(KEYS_THREADS) k_logits_keys(
     float* __restrict__ logits_all, float* __restrict__ lg_c, uint32_t* __restrict__ ukeys,
     float* __restrict__ keys_out, float* __restrict__ log_prob, float* __restrict__ dl_all,
     uint8_t* __restrict__ mask_out, float* __restrict__ stat_part) {
+    pdl_begin();
     __shared__ float s_red[KEYS_THREADS / 32];
     const int n = min(*n_dev, cap_n);
     const bool take_all = (k >= min(*c_dev, cap_n));          // utils.py:31-33: no noise is drawn
@@ -224,6 +226,7 @@ __global__ void __cluster_dims__(SEL_CTAS, 1, 1) __launch_bounds__(SEL_THREADS, 
     int* __restrict__ sampled_out, int sampled_offset, int* __restrict__ s_dev, int* __restrict__ total_dev,
     uint8_t* __restrict__ mask_out, float* __restrict__ log_prob, float* tot_log_prob, float* __restrict__ stats,
     float* __restrict__ dl_all, float* sum_dl, uint32_t* bm_mark) {
+    pdl_begin();
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     __shared__ SelShared sh;
@@ -533,7 +536,7 @@ int grapes_select_hop(grapes_ctx* ctx, const float* z, int nparts, int part_stri
     const int nblk = keys_grid(ctx, cap_n);
     float* stat_part = work;
     float* lg_c = stat_part + (size_t)SEL_STAT_FLOATS * nblk;
-    k_logits_keys<<<nblk, KEYS_THREADS, 0, s>>>(z, nparts, part_stride, n_dev, cap_n, in_off, in_src, dinv, bias,
+    pdl((k_logits_keys), nblk, KEYS_THREADS, 0, s)(z, nparts, part_stride, n_dev, cap_n, in_off, in_src, dinv, bias,
                                                 nb_index, c_dev, k, noise_mode, noise, rng_state, logits_all, lg_c,
                                                 ukeys_scratch, keys_out, log_prob, dl_all, mask_out, stat_part);
     grapes_count_launches(1);
@@ -546,7 +549,7 @@ int grapes_select_hop(grapes_ctx* ctx, const float* z, int nparts, int part_stri
         GRAPES_CUDA_OK(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr = smem;
     }
-    k_select<<<SEL_CTAS, SEL_THREADS, smem, s>>>(ukeys_scratch, lg_c, nb_local, nb_nodes, c_dev, cap_n, k, noise_mode,
+    pdl((k_select), SEL_CTAS, SEL_THREADS, smem, s)(ukeys_scratch, lg_c, nb_local, nb_nodes, c_dev, cap_n, k, noise_mode,
                                                  rng_state, stat_part, nblk, staged, sampled_out, sampled_offset,
                                                  s_dev, total_dev, mask_out, log_prob, tot_log_prob, stats, dl_all,
                                                  sum_dl, bm_mark);

@@ -68,6 +68,10 @@ int grapes_ctx_create(int device, int64_t num_nodes, int64_t max_frontier, int64
 int grapes_ctx_destroy(grapes_ctx* ctx);
 const char* grapes_last_error(void);
 int grapes_abi_version(void);
+/* programmatic dependent launch between consecutive kernels of a stream: bit mask over the library's source files
+ * (1 frontier, 2 gcn, 4 gemm_tc, 8 loss_optim, 16 select) whose kernels may start before their predecessor ends;
+ * 0 = plain stream order */
+int grapes_set_pdl(int mask);
 /* number of kernels this library has launched (or recorded into a capturing stream) so far      */
 int64_t grapes_kernel_launches(void);
 int grapes_zero(grapes_ctx* ctx, void* ptr, int64_t bytes, void* stream);
