@@ -897,6 +897,18 @@ int grapes_aggregate(grapes_ctx* ctx, const float* X, int F, int ldx, const int*
     pdl((k_agg_rows<RR, MB>), grid_for(ctx, (long long)grapes_div_up(cap_n, RR) * 32, 256, MB), 256, 0, s)(                 \
         X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias, relu, out, ldo, out_hi, out_lo,  \
         ones_col)
+        // default: rows staged by TMA bulk copies (spmm_tma.cu).  Measured on B200 (scripts/bench_spmm.py): frontier-sized
+        // launches are best with 16-entry chunks and 2 CTAs/SM, whole-graph launches with 32-entry chunks and 1 CTA/SM.
+        // grapes_agg_variant: 100 + ec / 200 + ec force a shape, 1..6 select the register-staged kernels.
+        if (g_agg_variant == 0 || g_agg_variant >= 100) {
+            const int v = g_agg_variant ? g_agg_variant : (cap_n > (1 << 19) ? 132 : 216);
+            if (grapes_launch_agg_tma(ctx, X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias,
+                                      relu, out, ldo, out_hi, out_lo, ones_col, v % 100, v / 100, s) == 0) {
+                grapes_count_launches(1);
+                GRAPES_LAUNCH_OK();
+                return GRAPES_OK;
+            }
+        }
         switch (g_agg_variant) {
             case 1: pdl((k_agg<4>), blocks, 256, 0, s)(X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind,
                                                     bias, relu, out, ldo, out_hi, out_lo, ones_col); break;
@@ -905,7 +917,7 @@ int grapes_aggregate(grapes_ctx* ctx, const float* X, int F, int ldx, const int*
             case 4: AGG_LAUNCH(4, 3); break;
             case 5: AGG_LAUNCH(4, 2); break;
             case 6: AGG_LAUNCH(4, 4); break;
-            default: AGG_LAUNCH(2, 4); break;      // measured best on B200 (products-shaped hop, 65k rows): 2 rows per warp
+            default: AGG_LAUNCH(2, 4); break;      // best register-staged form (products-shaped hop, 65k rows): 2 rows per warp
         }
     } else if (a16 && (F % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0))
         pdl((k_agg<4>), blocks, 256, 0, s)(X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias,

@@ -61,11 +61,59 @@ class NormAdj:
         return out
 
 
-def _gemm(layout, A, lda, B, ldb, M, N, K, bias=None, relu=0):
+class GraphNorm(NormAdj):
+    """gcn_norm structure of the WHOLE graph, built once from a :class:`DeviceGraph` (full-batch evaluation,
+    /root/reference/eval.py:47-56: ``gcn_c(x, edge_index)`` over every edge).  PyG semantics:
+    stored self-loops are dropped, one self-loop per node is added, deg = in-degree + 1; the in-neighbour lists are
+    the CSR of the transposed adjacency (edge_index[0] = source row, edge_index[1] = destination column),
+    ascending source inside a row.  One-off device sort; the aggregation itself is ``grapes_aggregate``
+    (TMA-staged SpMM) straight on these arrays -- nnz must fit int32 offsets (papers100M-shape needs sharding)."""
+
+    def __init__(self, graph, edge_index=None):
+        """``edge_index`` given: the structure of THAT edge list (duplicates kept and counted, exactly what
+        ``gcn_c(x, data.edge_index)`` sees in eval.py:50); otherwise the graph's canonical CSR (duplicates collapsed
+        by main.py:134)."""
+        dev = graph.device
+        N = graph.num_nodes
+        self.holder = graph
+        if edge_index is not None:
+            ei = edge_index.to(device=dev, dtype=torch.int64)
+            src, dst = ei[0], ei[1]
+        else:
+            counts = graph.indptr[1:] - graph.indptr[:-1]
+            src = torch.repeat_interleave(torch.arange(N, device=dev, dtype=torch.int64), counts)
+            dst = graph.indices.to(torch.int64)
+        if src.numel() >= (1 << 31) - 1:
+            raise GrapesError("full-graph aggregation needs nnz < 2^31 per device")
+        keep = src != dst
+        key = dst[keep] * N + src[keep]
+        del src, dst, keep
+        self.n, self.E = N, int(key.numel())
+        key = torch.sort(key).values
+        d = torch.div(key, N, rounding_mode="floor")
+        self.in_src = (key - d * N).to(torch.int32)
+        del key
+        indeg = torch.bincount(d, minlength=N)
+        del d
+        self.in_off = torch.zeros(N + 1, dtype=torch.int32, device=dev)
+        self.in_off[1:] = torch.cumsum(indeg, 0).to(torch.int32)
+        self.dinv = (1.0 / torch.sqrt((indeg + 1).to(torch.float32))).contiguous()
+        self.cnt = torch.tensor([int(self.in_src.numel()), N, 0, 0, 0, 0], dtype=torch.int32, device=dev)
+        self.out_off = self.out_dst = None
+
+    def aggregate(self, x, transpose=False, bias=None):
+        if transpose:
+            raise GrapesError("GraphNorm is forward-only (evaluation); training uses the sampled blocks")
+        return super().aggregate(x, False, bias)
+
+
+def _gemm(layout, A, lda, B, ldb, M, N, K, bias=None, relu=0, ldc=None):
     holder = _any_ctx(A.device)
-    C = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    ldc = N if ldc is None else ldc
+    C = torch.empty((M, N), dtype=torch.float32, device=A.device) if ldc == N else \
+        torch.zeros((M, ldc), dtype=torch.float32, device=A.device)
     if M > 0:
-        lib().grapes_gemm(holder.ctx, layout, ptr(A), lda, ptr(B), ldb, ptr(C), N, None, M, N, K, ptr(bias), relu,
+        lib().grapes_gemm(holder.ctx, layout, ptr(A), lda, ptr(B), ldb, ptr(C), ldc, None, M, N, K, ptr(bias), relu,
                           None, 0, _stream())
     return C
 
@@ -93,8 +141,14 @@ class _GCNConvFn(torch.autograd.Function):
             out = _gemm(3, y, I, w, I, n, O, I, bias=bias)
             ctx_.save_for_backward(y, w)
         else:
-            h = _gemm(3, x, I, w, I, n, O, I)
-            out = adj.aggregate(h, bias=bias)
+            O4 = (O + 3) // 4 * 4
+            if O4 != O and n >= 4096:                                 # float4 / TMA aggregation path: pad the width
+                h = _gemm(3, x, I, w, I, n, O, I, ldc=O4)
+                b4 = None if bias is None else F.pad(bias.detach().float(), (0, O4 - O))
+                out = adj.aggregate(h, bias=b4)[:, :O]
+            else:
+                h = _gemm(3, x, I, w, I, n, O, I)
+                out = adj.aggregate(h, bias=bias)
             ctx_.save_for_backward(x, w)
         return out
 

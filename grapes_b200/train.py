@@ -19,32 +19,25 @@ from .graph import DeviceGraph
 from .utils import get_logger
 
 
-@torch.inference_mode()
-def evaluate(engine: GrapesEngine, data, mask: torch.Tensor, full_batch: bool = True):
-    """Full-batch evaluation (/root/reference/eval.py:47-70) on the device: one full-graph forward of the
-    classifier through the same CUDA GCNConv kernels, accuracy and micro-F1 (multi-label: TP/FP/FN F1)."""
-    if not full_batch:
-        raise NotImplementedError("mini-batch evaluation (eval.py:71-163) is a 'next' row (DESIGN.md section 7)")
+def evaluate(engine: GrapesEngine, data, mask: torch.Tensor, full_batch: bool = True, args=None, graph=None):
+    """The reference's two evaluation modes (/root/reference/eval.py:47-70 full-batch, :71-163 mini-batch) on the
+    device, with the engine's current weights loaded into drop-in ``GCN`` modules (grapes_b200/eval.py)."""
+    from .eval import evaluate as _evaluate
     dev = engine.device
+    sd = engine.state_dicts()
     gcn_c = GCN(engine.F, [engine.D, engine.C]).to(dev)
-    gcn_c.load_state_dict(engine.state_dicts()["gcn_c"])
-    gcn_c.eval()
-    logits, _ = gcn_c(engine.x, data.edge_index.to(dev))
-    mask = mask.to(dev)
-    y = engine.y
-    if y.dim() == 1:
-        pred = torch.argmax(logits, dim=1)[mask]
-        acc = (pred == y[mask]).float().mean().item()
-        return acc, acc                                   # micro-F1 == accuracy for single-label multi-class
-    y_pred = logits[mask] > 0
-    y_true = y[mask] > 0.5
-    tp = int((y_true & y_pred).sum()); fp = int((~y_true & y_pred).sum()); fn = int((y_true & ~y_pred).sum())
-    try:
-        precision, recall = tp / (tp + fp), tp / (tp + fn)
-        f1 = 2 * precision * recall / (precision + recall)
-    except ZeroDivisionError:
-        f1 = 0.
-    return f1, f1
+    gcn_c.load_state_dict(sd["gcn_c"])
+    gcn_gf = GCN(engine.Fp, [engine.D, 1]).to(dev)
+    gcn_gf.load_state_dict(sd["gcn_gf"])
+    graph = graph or engine.g
+    loader = None
+    if not full_batch:
+        idx = mask.nonzero().squeeze(1)
+        loader = [(b,) for b in torch.split(idx, engine.bsz)]       # DataLoader(TensorDataset(idx), batch_size) main.py:127-132
+    ns = args if args is not None else type("A", (), dict(sampling_hops=engine.H, num_samples=engine.k,
+                                                          use_indicators=engine.use_ind))()
+    return _evaluate(gcn_c, gcn_gf, data, ns, graph, None, engine.num_ind, dev, mask=mask, eval_on_cpu=False,
+                     loader=loader, full_batch=full_batch)
 
 
 def train(args: Arguments, data=None, device: Optional[torch.device] = None, use_cuda_graph: bool = True,

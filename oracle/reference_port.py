@@ -376,3 +376,98 @@ def reference_step(st: OracleState, target_nodes: torch.Tensor,
     rec.update(loss_gfn=loss_gfn.detach().clone(), log_z=log_z.detach().clone().reshape(()),
                tot_log_prob=tot_log_prob.detach().clone())
     return rec
+
+
+# =============================================================================================
+# evaluation (eval.py:11-165)
+# =============================================================================================
+@torch.inference_mode()
+def reference_evaluate(st: OracleState, mask: torch.Tensor, full_batch: bool = True,
+                       batch_size: int = 256, stable_ties: bool = True) -> dict:
+    """Restatement of ``evaluate`` (eval.py:12-165) on the oracle's models.
+
+    full_batch (eval.py:47-70): one whole-graph forward ``gcn_c(x, edge_index)``; accuracy / micro-F1
+    (single label: both are the fraction of correct predictions) or the TP/FP/FN F1 for multi-label.
+    mini-batch (eval.py:71-163): the hop loop with deterministic ``topk(Bernoulli(logits).probs)`` (:126-127)
+    and ``slice_adjacency(rows=previous_nodes, cols=batch_nodes)`` (:140-142); batches are consecutive slices of
+    ``mask.nonzero()`` like the un-shuffled DataLoader of main.py:127-132.  ``stable_ties`` breaks ties of equal
+    probabilities towards the lower candidate index (torch.topk leaves ties unspecified)."""
+    data, adjacency, node_map = st.data, st.adjacency, st.node_map
+    out: dict = {}
+    if full_batch:
+        logits_total, _ = st.gcn_c(st.x, data.edge_index)                       # eval.py:50
+        out["logits"] = logits_total
+        if data.y[mask].dim() == 1:
+            predictions = torch.argmax(logits_total, dim=1)[mask]
+            out["predictions"] = predictions
+            out["accuracy"] = out["f1"] = float((predictions == data.y[mask]).double().mean())
+        else:
+            y_pred = logits_total[mask] > 0
+            y_true = data.y[mask] > 0.5
+            tp = int((y_true & y_pred).sum()); fp = int((~y_true & y_pred).sum()); fn = int((y_true & ~y_pred).sum())
+            try:
+                precision, recall = tp / (tp + fp), tp / (tp + fn)
+                out["accuracy"] = out["f1"] = 2 * (precision * recall) / (precision + recall)
+            except ZeroDivisionError:
+                out["accuracy"] = out["f1"] = 0.
+        return out
+
+    idx = mask.nonzero().squeeze(1)
+    prev_nodes_mask = torch.zeros(data.num_nodes, dtype=torch.bool)
+    batch_nodes_mask = torch.zeros(data.num_nodes, dtype=torch.bool)
+    indicator_features = torch.zeros((data.num_nodes, st.num_indicators), dtype=st.dtype)
+    all_predictions, per_batch = [], []
+    for target_nodes in torch.split(idx, batch_size):
+        previous_nodes = target_nodes.clone()
+        all_nodes_mask = torch.zeros_like(prev_nodes_mask)
+        all_nodes_mask[target_nodes] = True
+        indicator_features.zero_()
+        if st.use_indicators:
+            indicator_features[target_nodes, -1] = 1.0
+        global_edge_indices, hops = [], []
+        for hop in range(st.hops):
+            neighborhoods = get_neighborhoods(previous_nodes, adjacency)        # eval.py:94
+            prev_nodes_mask.zero_(); batch_nodes_mask.zero_()
+            prev_nodes_mask[previous_nodes] = True
+            batch_nodes_mask[neighborhoods.view(-1)] = True
+            neighbor_nodes_mask = batch_nodes_mask & ~prev_nodes_mask
+            batch_nodes = node_map.values[batch_nodes_mask]
+            neighbor_nodes = node_map.values[neighbor_nodes_mask]
+            if st.use_indicators:
+                indicator_features[neighbor_nodes, hop] = 1.0
+            node_map.update(batch_nodes)
+            local_neighborhoods = node_map.map(neighborhoods)
+            if st.use_indicators:
+                x = torch.cat([st.x[batch_nodes], indicator_features[batch_nodes]], dim=1)
+            else:
+                x = st.x[batch_nodes]
+            if neighbor_nodes.numel() > 0:
+                node_logits, _ = st.gcn_gf(x, local_neighborhoods)              # eval.py:121
+                node_logits = node_logits[node_map.map(neighbor_nodes)]
+                probs = torch.sigmoid(node_logits.squeeze(-1))                  # Bernoulli(logits).probs
+                k = min(neighbor_nodes.size(0), st.k)
+                samples = stable_topk_indices(probs, k) if stable_ties else torch.topk(probs, k, sorted=False)[1]
+                sample_mask = torch.zeros_like(probs)
+                sample_mask[samples] = 1
+                sampled = neighbor_nodes[sample_mask.bool()]
+            else:
+                sampled = neighbor_nodes
+            all_nodes_mask[sampled] = True
+            batch_nodes = torch.cat([target_nodes, sampled], dim=0)
+            k_hop_edges = slice_adjacency(adjacency, rows=previous_nodes, cols=batch_nodes)   # eval.py:140-142
+            global_edge_indices.append(k_hop_edges)
+            hops.append({"neighbor_nodes": neighbor_nodes.clone(), "sampled": sampled.clone(),
+                         "block_edges": k_hop_edges.clone()})
+            previous_nodes = batch_nodes.clone()
+        all_nodes = node_map.values[all_nodes_mask]
+        node_map.update(all_nodes)
+        edge_indices = [node_map.map(e) for e in global_edge_indices]
+        logits_total, _ = st.gcn_c(st.x[all_nodes], edge_indices)
+        predictions = torch.argmax(logits_total, dim=1)[node_map.map(target_nodes)]
+        all_predictions.append(predictions)
+        per_batch.append({"hops": hops, "all_nodes": all_nodes.clone(), "logits": logits_total.clone()})
+    all_predictions = torch.cat(all_predictions)
+    out["predictions"] = all_predictions
+    out["batches"] = per_batch
+    out["accuracy"] = out["f1"] = float((all_predictions == data.y[mask]).double().mean())
+    return out
