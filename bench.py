@@ -38,6 +38,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-spmm", action="store_true", help="skip the whole-graph SpMM leg")
+    ap.add_argument("--no-prefetch", action="store_true", help="no cross-step prefetch of the next batch's hop-0 front end")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)
     return ap.parse_args()
 
@@ -249,20 +250,21 @@ def main():
     nb = train_idx.numel() // B
     from grapes_b200.dist import allreduce_mean_, shard_batches
     mine = shard_batches(nb, rank, world)                             # batch i -> rank i mod W
-    order = [mine[j % len(mine)] for j in range(W + K)]
+    order = [mine[j % len(mine)] for j in range(W + K + 1)]
     batches = torch.stack([train_idx[b * B:(b + 1) * B] for b in order]).to(torch.int32)
-    eng.counts[eng._CNT["B"]] = B
-    eng.bsz = B
     use_graph = not args.no_graph
+    prefetch = not args.no_prefetch
 
     def one_step(j):
-        eng.targets.copy_(batches[j])
+        # the ids of batch j+1 are handed over with batch j: its reset + weight-independent hop-0 front end are enqueued
+        # next to this step's classifier tail (the reference's DataLoader order is known in advance, main.py:125-126)
+        nxt = batches[j + 1] if prefetch else None
         if world > 1:
-            eng.step(None, apply_optim=False, use_graph=use_graph)
+            eng.step(batches[j], apply_optim=False, use_graph=use_graph, next_targets=nxt)
             allreduce_mean_(eng.grads)                              # the only collective: gradient allreduce
             eng._enqueue_optim()
         else:
-            eng.step(None, apply_optim=True, use_graph=use_graph)
+            eng.step(batches[j], apply_optim=True, use_graph=use_graph, next_targets=nxt)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -304,19 +306,34 @@ def main():
     host_targets = torch.stack([train_idx[b * B:(b + 1) * B] for b in order]).to(torch.int64).cpu().pin_memory()
     host_scal = torch.zeros(16, dtype=torch.float32).pin_memory()
     dev_t64 = torch.zeros(B, dtype=torch.int64, device=dev)
+    ids32 = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(2)]
+    cnt_scratch = torch.zeros(1, dtype=torch.int32, device=dev)
     st = torch.cuda.current_stream().cuda_stream
 
-    def e2e_step(j):
+    def h2d_ids(j):
+        """pinned host int64 ids of batch j -> device int32 list (slot j % 2)"""
         dev_t64.copy_(host_targets[j], non_blocking=True)                                # H2D: B int64 ids
-        L.grapes_ids_i64_to_i32(graph.ctx, dev_t64.data_ptr(), B, eng.targets.data_ptr(), eng._cnt("B"), st)
+        L.grapes_ids_i64_to_i32(graph.ctx, dev_t64.data_ptr(), B, ids32[j % 2].data_ptr(), cnt_scratch.data_ptr(), st)
+        return ids32[j % 2]
+
+    e2e_state = {"have": -1}
+
+    def e2e_step(j):
+        # every step copies ONE batch of ids host -> device (the next batch's when prefetching: its front end runs next to
+        # this step's classifier tail) and reads the losses back, synchronising like loss.item() (main.py:269,291)
+        cur = ids32[j % 2] if e2e_state["have"] == j else h2d_ids(j)
+        nxt = None
+        if prefetch:
+            nxt = h2d_ids(j + 1)
+            e2e_state["have"] = j + 1
         if world > 1:
-            eng.step(None, apply_optim=False, use_graph=use_graph)
+            eng.step(cur, apply_optim=False, use_graph=use_graph, next_targets=nxt)
             allreduce_mean_(eng.grads)
             eng._enqueue_optim()
         else:
-            eng.step(None, apply_optim=True, use_graph=use_graph)
+            eng.step(cur, apply_optim=True, use_graph=use_graph, next_targets=nxt)
         host_scal.copy_(eng.scal, non_blocking=True)                                     # D2H: losses
-        torch.cuda.current_stream().synchronize()                                        # loss_c.item() (main.py:269,291)
+        torch.cuda.current_stream().synchronize()
         return float(host_scal[0])
 
     for j in range(3):
@@ -343,7 +360,7 @@ def main():
         eng.multi_stream = False             # one stream: each kernel is timed alone, not against its co-runners
         per_hop_acc = None
         for j in range(P_STEPS):
-            eng.targets.copy_(batches[j])
+            eng.set_targets(batches[j])
             # park the GPU for ~2 ms so the whole step is queued before it starts: the per-call CUDA events then
             # bracket device time only (no CPU launch gaps inside the brackets)
             torch.cuda._sleep(4_000_000)
@@ -438,7 +455,7 @@ def main():
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(cfgname, cfg, world),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": int(per_step),
                 "roofline": roof, "rooflines": rooflines, "spmm": spmm, "cpu_baseline": cpu, "breakdown_ms_per_step": breakdown,
-                "frontier": per_hop, "cuda_graph": use_graph}
+                "frontier": per_hop, "cuda_graph": use_graph, "cross_step_prefetch": prefetch}
         emit(line)
     if world > 1:
         dist.barrier()

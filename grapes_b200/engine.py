@@ -125,10 +125,11 @@ class GrapesEngine:
             # queued backward / slice kernels of the side streams
             self.main_hp = torch.cuda.Stream(device=dev, priority=-1) if os.environ.get("GRAPES_HP", "0") == "1" else None
             self.side_a, self.side_b = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-            self.ctx_a, self.ctx_b = graph.new_ctx(), graph.new_ctx(16 << 20)
+            self.side_p = torch.cuda.Stream(device=dev)          # front end of the NEXT batch (cross-step prefetch)
+            self.ctx_a, self.ctx_b, self.ctx_p = graph.new_ctx(), graph.new_ctx(16 << 20), graph.new_ctx(16 << 20)
         else:
-            self.side_a = self.side_b = self.main_hp = None
-            self.ctx_a = self.ctx_b = graph.ctx
+            self.side_a = self.side_b = self.side_p = self.main_hp = None
+            self.ctx_a = self.ctx_b = self.ctx_p = graph.ctx
 
         # ---- capacities -------------------------------------------------------------------
         self.cap_P = self.B + self.k
@@ -161,63 +162,23 @@ class GrapesEngine:
         n_par = self.net_z.end
         self.n_par = n_par
 
-        # ---- ONE pool that is cleared by ONE memset at the start of every step:
-        #   bitmaps (int32 words): all_nodes | indicator rows | prev rows of hop 0..H-1 | batch rows of hop 0..H-1
-        #   floats: scalars | per-hop stats | gradient direction of the sampler nets
-        n_bm = 1 + max(self.num_ind, 1) + 2 * H
-        n_fl = 16 + 4 * H + n_par
-        self.step_pool = z(n_bm * W + n_fl, **i32)
-        bm = self.step_pool[:n_bm * W].view(n_bm, W)
-        self.bm_all = bm[0]
-        self.bm_ind = bm[1:1 + max(self.num_ind, 1)]
-        self.bm_prev = [bm[1 + max(self.num_ind, 1) + h] for h in range(H)]
-        self.bm_batch = [bm[1 + max(self.num_ind, 1) + H + h] for h in range(H)]
-        fl = self.step_pool[n_bm * W:].view(torch.float32)
-        self.zero_pool = fl
-        self.scal = fl[:16]
-        self.stats = fl[16:16 + 4 * H].view(H, 4)
-        self.gdir = fl[16 + 4 * H:]          # gradient DIRECTION of (log_z, sum log_prob) w.r.t. gf / z params
-        self.pref_batch, self.pref_nb, self.pref_all = z(W + 1, **i32), z(W + 1, **i32), z(W + 1, **i32)
-
-        # ---- id lists and device-side sizes ------------------------------------------------
-        self.targets = z(self.B, **i32)
-        self.prev_pool = z((H + 1, cap_P), **i32)            # prev[h] = rows expanded at hop h; prev[H] = last block's rows
-        self.prev = [self.prev_pool[h] for h in range(H + 1)]
-        self.counts = z(16 * (H + 2), **i32)                 # [0:16] globals, then one 16-int block per hop (+ final)
-        self.cnt_scratch = z(max(cap_n, self.cap_A), **i32)
-        self.tmp_val = e(cap_m, **i32)
+        self.pref_all = z(W + 1, **i32)
         self.ukeys = e(cap_n, **i32)
         self.sel_work = z(int(self.L.cdll.grapes_select_work_floats(graph.ctx, cap_n)), **f32)   # zero once: the library keeps its histogram clean
-        self.log_prob = z((H, cap_n), **f32)
         self.overflow = z(1, **i32)
         self.rng_state = torch.tensor([seed & 0x7fffffffffffffff, 0], dtype=torch.int64, device=dev)
-
-        # ---- per-hop workspaces ------------------------------------------------------------
+        # ---- two step states (see _alloc_step_state); self.<buffer> always refers to the ACTIVE one ----
+        base_names = set(self.__dict__)
+        self._states = []
+        for _ in range(2):
+            self._alloc_step_state()
+            self._states.append({k: v for k, v in self.__dict__.items() if k not in base_names and k != "_states"})
+        self.par = 0
+        self._activate(0)
+        self._front_ready = [False, False]       # hop-0 front end of the state already enqueued (prefetched)
+        self._pref_key = None                    # (data_ptr, numel) of the targets the prefetched front end was built from
+        self._prefetch_next = False              # this step enqueues the other state's front end next to its classifier tail
         need_Y = not self.random_sampling
-        self.hops: List[_Hop] = []
-        for h in range(H):
-            hw = _Hop()
-            hw.row_off = z(cap_P + 1, **i32)
-            hw.e_row, hw.e_col = e(cap_m, **i32), e(cap_m, **i32)
-            hw.e_src, hw.e_dst = e(cap_m, **i32), e(cap_m, **i32)
-            hw.batch_nodes, hw.nb_nodes, hw.nb_local = e(cap_n, **i32), e(cap_n, **i32), e(cap_n, **i32)
-            hw.nb_index = e(cap_n, **i32)
-            hw.ind_bits = z(cap_n, **i32)
-            hw.in_off, hw.in_src, hw.dinv = z(cap_n + 1, **i32), e(cap_m, **i32), e(cap_n, **f32)
-            hw.logits_all, hw.dl_all, hw.dz = z(cap_n, **f32), z(cap_n, **f32), e(cap_n, **f32)
-            hw.Y = hw.Y_lo = hw.mask_gf = None
-            if need_Y:
-                # tensor-core path: (Y, Y_lo) is the 3xTF32 (hi, lo) pair written by the aggregation; else plain fp32 Y
-                hw.Y = z((cap_n, self.ldY), **f32)
-                if self.use_tc:
-                    hw.Y_lo = z((cap_n, self.ldY), **f32)
-                if self.use_tc_bwd:
-                    hw.mask_gf = z(((cap_n + 127) // 128 * 4, D), **i32)
-            hw.blk_src, hw.blk_dst = e(self.cap_blk, **i32), e(self.cap_blk, **i32)
-            self.hops.append(hw)
-        # expansion of the last block's rows (T u S_{H-1})
-        self.fin_row_off = z(cap_P + 1, **i32)
-        self.fin_e_row, self.fin_e_col = e(cap_m, **i32), e(cap_m, **i32)
         # sampler-net scratch
         if need_Y:
             if self.use_tc:
@@ -261,8 +222,8 @@ class GrapesEngine:
             v = net.views(self.params)
             glorot_(v["gcn_layers.0.lin.weight"], gen)
             glorot_(v["gcn_layers.1.lin.weight"], gen)
-        self.bsz = self.B                   # current batch size (<= capacity B); the last batch of an epoch is partial
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        self._graph_launches: Dict[tuple, int] = {}
         self.launches_per_graph = 0
         self.record: Optional[dict] = None
         # timing experiments only (scripts/ablate.py): leave out parts of the step to see what the rest costs
@@ -271,6 +232,79 @@ class GrapesEngine:
             self.L.cdll.grapes_agg_variant(int(os.environ["GRAPES_AGG_VARIANT"]))
         if os.environ.get("GRAPES_TC_DEBUG"):
             self.L.cdll.grapes_tc_debug(int(os.environ["GRAPES_TC_DEBUG"]))
+
+    def _alloc_step_state(self):
+        """Every buffer that belongs to ONE step in flight (bitmap / scalar pool, id lists, device-side sizes, per-hop
+        workspaces).  Allocated twice: the engine keeps two step states so the weight-independent front end of the NEXT
+        batch (expand .. aggregate of hop 0) can be enqueued next to the classifier tail of the current one."""
+        dev, H, W, N, F, D = self.device, self.H, self.W, self.N, self.F, self.D
+        n_par = self.n_par
+        cap_m, cap_n, cap_P = self.cap_m, self.cap_n, self.cap_P
+        i32 = dict(dtype=torch.int32, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        z = torch.zeros
+        e = torch.empty
+        need_Y = not self.random_sampling
+        # ---- ONE pool that is cleared by ONE memset at the start of every step:
+        #   bitmaps (int32 words): all_nodes | indicator rows | prev rows of hop 0..H-1 | batch rows of hop 0..H-1
+        #   floats: scalars | per-hop stats | gradient direction of the sampler nets
+        n_bm = 1 + max(self.num_ind, 1) + 2 * H
+        n_fl = 16 + 4 * H + n_par
+        self.step_pool = z(n_bm * W + n_fl, **i32)
+        bm = self.step_pool[:n_bm * W].view(n_bm, W)
+        self.bm_all = bm[0]
+        self.bm_ind = bm[1:1 + max(self.num_ind, 1)]
+        self.bm_prev = [bm[1 + max(self.num_ind, 1) + h] for h in range(H)]
+        self.bm_batch = [bm[1 + max(self.num_ind, 1) + H + h] for h in range(H)]
+        fl = self.step_pool[n_bm * W:].view(torch.float32)
+        self.zero_pool = fl
+        self.scal = fl[:16]
+        self.stats = fl[16:16 + 4 * H].view(H, 4)
+        self.gdir = fl[16 + 4 * H:]          # gradient DIRECTION of (log_z, sum log_prob) w.r.t. gf / z params
+        self.pref_batch, self.pref_nb = z(W + 1, **i32), z(W + 1, **i32)
+
+        # ---- id lists and device-side sizes ------------------------------------------------
+        self.targets = z(self.B, **i32)
+        self.prev_pool = z((H + 1, cap_P), **i32)            # prev[h] = rows expanded at hop h; prev[H] = last block's rows
+        self.prev = [self.prev_pool[h] for h in range(H + 1)]
+        self.counts = z(16 * (H + 2), **i32)                 # [0:16] globals, then one 16-int block per hop (+ final)
+        self.cnt_scratch = z(max(cap_n, self.cap_A), **i32)
+        self.tmp_val = e(cap_m, **i32)
+        self.log_prob = z((H, cap_n), **f32)
+
+        # ---- per-hop workspaces ------------------------------------------------------------
+        self.hops: List[_Hop] = []
+        for h in range(H):
+            hw = _Hop()
+            hw.row_off = z(cap_P + 1, **i32)
+            hw.e_row, hw.e_col = e(cap_m, **i32), e(cap_m, **i32)
+            hw.e_src, hw.e_dst = e(cap_m, **i32), e(cap_m, **i32)
+            hw.batch_nodes, hw.nb_nodes, hw.nb_local = e(cap_n, **i32), e(cap_n, **i32), e(cap_n, **i32)
+            hw.nb_index = e(cap_n, **i32)
+            hw.ind_bits = z(cap_n, **i32)
+            hw.in_off, hw.in_src, hw.dinv = z(cap_n + 1, **i32), e(cap_m, **i32), e(cap_n, **f32)
+            hw.logits_all, hw.dl_all, hw.dz = z(cap_n, **f32), z(cap_n, **f32), e(cap_n, **f32)
+            hw.Y = hw.Y_lo = hw.mask_gf = None
+            if need_Y:
+                # tensor-core path: (Y, Y_lo) is the 3xTF32 (hi, lo) pair written by the aggregation; else plain fp32 Y
+                hw.Y = z((cap_n, self.ldY), **f32)
+                if self.use_tc:
+                    hw.Y_lo = z((cap_n, self.ldY), **f32)
+                if self.use_tc_bwd:
+                    hw.mask_gf = z(((cap_n + 127) // 128 * 4, D), **i32)
+            hw.blk_src, hw.blk_dst = e(self.cap_blk, **i32), e(self.cap_blk, **i32)
+            self.hops.append(hw)
+        # expansion of the last block's rows (T u S_{H-1})
+        self.fin_row_off = z(cap_P + 1, **i32)
+        self.fin_e_row, self.fin_e_col = e(cap_m, **i32), e(cap_m, **i32)
+        self.bsz = self.B                   # current batch size (<= capacity B); the last batch of an epoch is partial
+
+    def _activate(self, p: int):
+        self.__dict__.update(self._states[p])
+        self.par = p
+
+    def _save_state_scalars(self):
+        self._states[self.par]["bsz"] = self.bsz
 
     # ------------------------------------------------------------------ helpers
     _CNT = dict(B=0, A=1, cl_nnz=2)
@@ -329,8 +363,8 @@ class GrapesEngine:
         multi = self.multi_stream and self.side_a is not None
         ctx, st = g.ctx, main.cuda_stream
         ctx_a, ctx_b = self.ctx_a, self.ctx_b
-        sA, sB = (self.side_a, self.side_b) if multi else (main, main)
-        stA, stB = sA.cuda_stream, sB.cuda_stream
+        sA, sB, sP = (self.side_a, self.side_b, self.side_p) if multi else (main, main, main)
+        stA, stB, stP = sA.cuda_stream, sB.cuda_stream, sP.cuda_stream
         on = (lambda s: torch.cuda.stream(s)) if multi else (lambda s: contextlib.nullcontext())
 
         forked = set()
@@ -354,20 +388,24 @@ class GrapesEngine:
         tc = self.use_tc
         gf, nz = self.net_gf, self.net_z
 
-        # ---- per-batch reset (main.py:161-176): one memset + one kernel ----
-        L.grapes_zero(ctx, ptr(self.step_pool), 4 * self.step_pool.numel(), st)
-        L.grapes_step_reset(ctx, ptr(self.targets), self._cnt("B"), B, ptr(self.prev_pool), cap_P, H + 1,
-                            self._hc(0, "P"), ptr(self.bm_all),
-                            self.bm_ind.data_ptr() + 4 * W * (self.num_ind - 1) if self.use_ind else None, st)
+        # ---- per-batch reset + hop-0 front end: already enqueued next to the previous step's classifier tail when this
+        # state was prefetched (step(..., next_targets=...)), else inline ----
+        if self._front_ready[self.par]:
+            self._front_ready[self.par] = False
+        else:
+            self._enqueue_front0(ctx, st)
+
+        if os.environ.get("GRAPES_PREFETCH_AT", "start") == "start":
+            self._enqueue_prefetch(fork, on, sP, stP)
 
         for h in range(H):
             hw = self.hops[h]
             rows, P_dev = ptr(self.prev[h]), self._hc(h, "P")
             m_dev, n_dev, c_dev = self._hc(h, "m"), self._hc(h, "n"), self._hc(h, "c")
-            # get_neighborhoods + mask dedup (main.py:180-190)
-            L.grapes_expand_frontier(ctx, indptr, indices, rows, P_dev, cap_P, ptr(hw.row_off), m_dev, cap_m,
-                                     ptr(hw.e_row), ptr(hw.e_col), ptr(self.bm_prev[h]), ptr(self.bm_batch[h]), ovf, st)
             if h > 0:
+                # get_neighborhoods + mask dedup (main.py:180-190)
+                L.grapes_expand_frontier(ctx, indptr, indices, rows, P_dev, cap_P, ptr(hw.row_off), m_dev, cap_m,
+                                         ptr(hw.e_row), ptr(hw.e_col), ptr(self.bm_prev[h]), ptr(self.bm_batch[h]), ovf, st)
                 # slice_adjacency(rows = T u S_{h-1}, cols = prev_{h-1}) (main.py:241-244): same row expansion; side B
                 pw = self.hops[h - 1]
                 fork(sB)
@@ -375,23 +413,8 @@ class GrapesEngine:
                     L.grapes_slice_block(ctx_b, rows, ptr(hw.e_row), ptr(hw.e_col), m_dev, cap_m,
                                          ptr(self.bm_prev[h - 1]), ptr(pw.blk_src), ptr(pw.blk_dst), self.cap_blk,
                                          self._hc(h - 1, "blk"), ovf, stB)
-            L.grapes_rank_nodes(ctx, ptr(self.bm_batch[h]), ptr(self.bm_prev[h]), ptr(self.pref_batch),
-                                ptr(self.pref_nb), ptr(hw.batch_nodes), ptr(hw.nb_nodes), ptr(hw.nb_local),
-                                ptr(hw.nb_index), ptr(hw.ind_bits) if self.use_ind else None,
-                                ptr(self.bm_ind) if self.use_ind else None, self.num_ind, h, cap_n,
-                                n_dev, c_dev, ovf, st)
-            L.grapes_edges_to_local(ctx, rows, ptr(hw.e_row), ptr(hw.e_col), m_dev, cap_m, ptr(self.bm_batch[h]),
-                                    ptr(self.pref_batch), ptr(hw.e_src), ptr(hw.e_dst), ptr(self.cnt_scratch), st)
-            # gcn_norm structure of the hop graph (dst-sorted CSR, deg^-1/2)
-            L.grapes_build_csr(ctx, ptr(hw.e_dst), ptr(hw.e_src), m_dev, cap_m, n_dev, cap_n, ptr(self.cnt_scratch),
-                               1, ptr(hw.in_off), ptr(hw.in_src), ptr(self.tmp_val), ptr(hw.dinv),
-                               self._hc(h, "nnz"), ovf, st)
+                self._enqueue_hop_structure(h, ctx, st)
             if need_Y:
-                # Y = A_hat [x | indicators]   (feature gather fused, main.py:198-204 + GCNConv aggregation)
-                L.grapes_aggregate(ctx, X, F, F, ptr(hw.batch_nodes), n_dev, cap_n, ptr(hw.in_off), ptr(hw.in_src),
-                                   ptr(hw.dinv), ptr(hw.ind_bits) if self.use_ind else None, self.num_ind, None, 0,
-                                   None if tc else ptr(hw.Y), self.ldY, ptr(hw.Y) if tc else None, ptr(hw.Y_lo),
-                                   Fp if self.use_tc_bwd else -1, st)
                 if tc:
                     if h == 0:
                         self._split_weights(ctx, st)
@@ -427,6 +450,9 @@ class GrapesEngine:
                 with on(sA):
                     self._enqueue_hop_backward(h, ctx_a, stA)
 
+        if os.environ.get("GRAPES_PREFETCH_AT", "start") == "tail":
+            self._enqueue_prefetch(fork, on, sP, stP)
+
         # ---- last block: slice_adjacency(rows = T u S_{H-1}, cols = prev_{H-1}) ----
         rows, P_dev, m_dev = ptr(self.prev[H]), self._hc(H, "P"), self._hc(H, "m")
         L.grapes_expand_frontier(ctx, indptr, indices, rows, P_dev, cap_P, ptr(self.fin_row_off), m_dev, cap_m,
@@ -439,6 +465,7 @@ class GrapesEngine:
 
         if "nocls" in self.ablate:
             join(sA)
+            join(sP)
             return
         # ---- classifier on the sampled subgraph (main.py:252-269) ----
         L.tag = "[cls]"
@@ -507,6 +534,7 @@ class GrapesEngine:
         # ---- GFlowNet / REINFORCE loss (main.py:271-291): loss, gradient scale, scaled directions in one launch ----
         join(sB)
         join(sA)
+        join(sP)
         if not self.random_sampling:
             n_z = 0 if self.reinforce else nz.size
             L.grapes_gfn_finalize_scale(ctx, ptr(self.scal), self.loss_coef, self.log_z_init, int(self.reinforce), 1,
@@ -514,6 +542,63 @@ class GrapesEngine:
                                         self._dir(nz.base), n_z, self._grd(nz.base), st)
         if apply_optim:
             self._enqueue_optim()
+
+    def _enqueue_prefetch(self, fork, on, sP, stP):
+        # ---- cross-step prefetch: the hop chain and the classifier tail of THIS batch are chains of small, latency-bound
+        # kernels -> the reset and the weight-independent hop-0 front end of the NEXT batch run next to them on the other
+        # step state (own stream, own scan scratch; joined before the optimiser step) ----
+        if not self._prefetch_next:
+            return
+        cur = self.par
+        fork(sP)
+        self._activate(1 - cur)
+        try:
+            with on(sP):
+                self._enqueue_front0(self.ctx_p, stP)
+        finally:
+            self._activate(cur)
+        self._front_ready[1 - cur] = True
+
+    def _enqueue_hop_structure(self, h: int, ctx, st):
+        """After the row expansion of hop h: mask dedup + id lists + indicator bits (main.py:183-195), local relabel,
+        gcn_norm structure of the hop graph (dst-sorted CSR, deg^-1/2) and Y = A_hat [x | indicators] (feature gather
+        fused, main.py:198-204 + GCNConv aggregation).  None of it depends on the weights."""
+        L = self.L
+        hw = self.hops[h]
+        cap_m, cap_n = self.cap_m, self.cap_n
+        rows = ptr(self.prev[h])
+        m_dev, n_dev, c_dev = self._hc(h, "m"), self._hc(h, "n"), self._hc(h, "c")
+        ovf = ptr(self.overflow)
+        L.grapes_rank_nodes(ctx, ptr(self.bm_batch[h]), ptr(self.bm_prev[h]), ptr(self.pref_batch),
+                            ptr(self.pref_nb), ptr(hw.batch_nodes), ptr(hw.nb_nodes), ptr(hw.nb_local),
+                            ptr(hw.nb_index), ptr(hw.ind_bits) if self.use_ind else None,
+                            ptr(self.bm_ind) if self.use_ind else None, self.num_ind, h, cap_n,
+                            n_dev, c_dev, ovf, st)
+        L.grapes_edges_to_local(ctx, rows, ptr(hw.e_row), ptr(hw.e_col), m_dev, cap_m, ptr(self.bm_batch[h]),
+                                ptr(self.pref_batch), ptr(hw.e_src), ptr(hw.e_dst), ptr(self.cnt_scratch), st)
+        L.grapes_build_csr(ctx, ptr(hw.e_dst), ptr(hw.e_src), m_dev, cap_m, n_dev, cap_n, ptr(self.cnt_scratch),
+                           1, ptr(hw.in_off), ptr(hw.in_src), ptr(self.tmp_val), ptr(hw.dinv),
+                           self._hc(h, "nnz"), ovf, st)
+        if not self.random_sampling:
+            tc = self.use_tc
+            L.grapes_aggregate(ctx, ptr(self.x), self.F, self.F, ptr(hw.batch_nodes), n_dev, cap_n, ptr(hw.in_off),
+                               ptr(hw.in_src), ptr(hw.dinv), ptr(hw.ind_bits) if self.use_ind else None, self.num_ind,
+                               None, 0, None if tc else ptr(hw.Y), self.ldY, ptr(hw.Y) if tc else None, ptr(hw.Y_lo),
+                               self.Fp if self.use_tc_bwd else -1, st)
+
+    def _enqueue_front0(self, ctx, st):
+        """Per-batch reset (main.py:161-176: one memset + one kernel) and the whole hop-0 front end of the ACTIVE step
+        state on stream `st`: everything of a batch that can be computed before the previous batch's optimiser step."""
+        L, g = self.L, self.g
+        hw = self.hops[0]
+        L.grapes_zero(ctx, ptr(self.step_pool), 4 * self.step_pool.numel(), st)
+        L.grapes_step_reset(ctx, ptr(self.targets), self._cnt("B"), self.bsz, ptr(self.prev_pool), self.cap_P, self.H + 1,
+                            self._hc(0, "P"), ptr(self.bm_all),
+                            self.bm_ind.data_ptr() + 4 * self.W * (self.num_ind - 1) if self.use_ind else None, st)
+        L.grapes_expand_frontier(ctx, ptr(g.indptr), ptr(g.indices), ptr(self.prev[0]), self._hc(0, "P"), self.cap_P,
+                                 ptr(hw.row_off), self._hc(0, "m"), self.cap_m, ptr(hw.e_row), ptr(hw.e_col),
+                                 ptr(self.bm_prev[0]), ptr(self.bm_batch[0]), ptr(self.overflow), st)
+        self._enqueue_hop_structure(0, ctx, st)
 
     def _enqueue_hop_backward(self, h: int, ctx, st):
         """Side stream A.  Gradient direction of sum(log_prob_h) w.r.t. gcn_gf (main.py:271-287 via
@@ -589,33 +674,72 @@ class GrapesEngine:
                             ptr(self.adam_steps), st)
 
     # ------------------------------------------------------------------ public API
-    def set_targets(self, target_nodes: torch.Tensor):
+    def set_targets(self, target_nodes: torch.Tensor, state: Optional[int] = None):
+        """Writes the batch's target ids into a step state (default: the active one)."""
         t = target_nodes
         b = int(t.numel())
         if b > self.B or b < 1:
             raise GrapesError(f"engine built for batch_size<={self.B}, got {b} targets")
-        self.bsz = b
-        self.targets[:b].copy_(t.to(torch.int32), non_blocking=True)
-        self.counts[self._CNT["B"]] = b
+        p = self.par if state is None else state
+        stt = self._states[p]
+        if stt["bsz"] != b or not stt.get("_b_written", False):
+            stt["counts"][self._CNT["B"]] = b
+            stt["bsz"] = b
+            stt["_b_written"] = True
+            if p == self.par:
+                self.bsz = b
+        stt["targets"][:b].copy_(t if t.dtype == torch.int32 else t.to(torch.int32), non_blocking=True)
 
     def step(self, target_nodes: Optional[torch.Tensor] = None, gumbel_noise=None, apply_optim: bool = True,
-             use_graph: bool = False, record: bool = False, noise_mode: int = NOISE_GUMBEL):
+             use_graph: bool = False, record: bool = False, noise_mode: int = NOISE_GUMBEL,
+             next_targets: Optional[torch.Tensor] = None):
+        """One batch of main.py:161-291.  ``next_targets`` (optional) names the batch of the NEXT call: its reset and
+        hop-0 front end (weight independent) are enqueued next to this step's classifier tail on the second step state,
+        and the next call -- which must pass the same tensor as ``target_nodes`` -- starts at the sampler GEMM of hop 0.
+        Results are bit-identical with and without it (tests/test_gpu_engine.py::test_prefetch_matches_plain_steps)."""
         if target_nodes is not None:
-            self.set_targets(target_nodes)
+            key = (target_nodes.data_ptr(), int(target_nodes.numel()))
+            if self._front_ready[1 - self.par] and self._pref_key == key:
+                self._activate(1 - self.par)                 # front end already there
+            else:
+                self._front_ready = [False, False]           # a prefetched front end for other targets is dropped
+                self.set_targets(target_nodes)
+        self._pref_key = None
+        self._prefetch_next = False
+        if next_targets is not None and not record and gumbel_noise is None:
+            self.set_targets(next_targets, state=1 - self.par)
+            self._pref_key = (next_targets.data_ptr(), int(next_targets.numel()))
+            self._prefetch_next = True
         if use_graph:
             assert gumbel_noise is None and not record
-            key = (apply_optim, self.bsz)
+            ready = self._front_ready[self.par]
+            key = (apply_optim, self.bsz, self.par, ready, self._prefetch_next,
+                   self._states[1 - self.par]["bsz"] if self._prefetch_next else 0)
             gr = self._graphs.get(key)
             if gr is None:
-                self.step(None, apply_optim=False)        # warm the allocator / lazy init outside capture
-                torch.cuda.synchronize()
+                if not ready:
+                    # warm the allocator / lazy init outside capture (a state whose front end is prefetched cannot be
+                    # re-run: its reset already happened; every kernel has been launched by an earlier variant then)
+                    flags, pf = list(self._front_ready), self._prefetch_next
+                    rng = self.rng_state.clone()             # the warm-up must not consume the Philox stream
+                    self._prefetch_next = False
+                    self._enqueue(None, False)
+                    torch.cuda.synchronize()
+                    self.rng_state.copy_(rng)
+                    self._front_ready, self._prefetch_next = flags, pf
                 gr = torch.cuda.CUDAGraph()
                 n0 = self.L.grapes_kernel_launches()
+                flags = list(self._front_ready)
                 with torch.cuda.graph(gr):
                     self._enqueue(None, apply_optim)
-                self.launches_per_graph = int(self.L.grapes_kernel_launches() - n0)
+                self._front_ready = flags
+                self._graph_launches[key] = int(self.L.grapes_kernel_launches() - n0)
                 self._graphs[key] = gr
+            self.launches_per_graph = self._graph_launches[key]
             gr.replay()
+            self._front_ready[self.par] = False
+            if self._prefetch_next:
+                self._front_ready[1 - self.par] = True
             return None
         if record:
             self.record = {"keys": [torch.zeros(self.cap_n, dtype=torch.float32, device=self.device)

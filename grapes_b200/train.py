@@ -69,7 +69,7 @@ def train(args: Arguments, data=None, device: Optional[torch.device] = None, use
                           reg_param=args.reg_param, random_sampling=args.random_sampling,
                           reinforce_baseline=args.reinforce_baseline, seed=0 if args.seed is None else args.seed)
     train_idx = data.train_mask.nonzero().squeeze(1).to(device)
-    batches = list(torch.split(train_idx, args.batch_size))      # DataLoader(TensorDataset(train_idx), batch_size)
+    batches = [b.to(torch.int32).contiguous() for b in torch.split(train_idx, args.batch_size)]   # DataLoader(TensorDataset(train_idx), batch_size)
     if max_batches is not None:
         batches = batches[:max_batches]
 
@@ -79,8 +79,9 @@ def train(args: Arguments, data=None, device: Optional[torch.device] = None, use
     for epoch in range(1, args.max_epochs + 1):
         acc_c = torch.zeros((), device=device)
         acc_gfn = torch.zeros((), device=device)
-        for batch in batches:
-            engine.step(batch, use_graph=use_cuda_graph)
+        for bi, batch in enumerate(batches):
+            # the next batch's reset + hop-0 front end is enqueued next to this step's classifier tail
+            engine.step(batch, use_graph=use_cuda_graph, next_targets=batches[bi + 1] if bi + 1 < len(batches) else None)
             acc_c += engine.scal[0] / len(batches)               # deferred: no .item() inside the loop
             acc_gfn += engine.scal[4] / len(batches)
             mb = torch.cuda.memory_allocated() / (1024 * 1024)

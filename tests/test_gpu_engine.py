@@ -267,3 +267,40 @@ def test_determinism_run_to_run(cuda_device):
     torch.cuda.synchronize()
     assert torch.equal(eng.params, eng2.params)
     assert torch.equal(eng.grads, eng2.grads)
+
+
+def test_prefetch_matches_plain_steps(cuda_device):
+    """Cross-step prefetch (step(..., next_targets=...): reset + hop-0 front end of the next batch enqueued next to the
+    classifier tail on the second step state) must not change a single bit: same batches, same Philox stream, Adam on;
+    eager and CUDA-graph replay, with a partial last batch."""
+    from grapes_b200.engine import GrapesEngine
+    from grapes_b200.graph import DeviceGraph
+    from grapes_b200.synth import SHAPES
+    dev = cuda_device
+    cfg = SHAPES["small"]
+    d = make_synth("small", seed=4)
+    g = DeviceGraph.from_edge_index(d.edge_index, d.num_nodes, device=dev)
+    idx = d.train_mask.nonzero().squeeze(1).to(dev)
+    B = cfg["batch_size"]
+    batches = [idx[i * B:(i + 1) * B].to(torch.int32).contiguous() for i in range(6)]
+    batches.append(idx[6 * B:6 * B + B // 2].to(torch.int32).contiguous())          # a partial last batch
+    outs = {}
+    for mode in ("plain", "prefetch"):
+        for use_graph in (False, True):
+            eng = GrapesEngine(g, d.x.to(dev), d.y.to(dev), num_classes=d.num_classes, batch_size=B,
+                               num_samples=cfg["num_samples"], sampling_hops=cfg["sampling_hops"], seed=11)
+            scal, nodes = [], []
+            for j, b in enumerate(batches):
+                nxt = batches[j + 1] if (mode == "prefetch" and j + 1 < len(batches)) else None
+                eng.step(b, use_graph=use_graph, next_targets=nxt)
+                scal.append(eng.scal.clone())
+                nodes.append(eng.all_nodes.clone())
+            eng.check_overflow()
+            torch.cuda.synchronize()
+            outs[(mode, use_graph)] = (eng.params.clone(), torch.stack(scal), torch.stack(nodes))
+    ref = outs[("plain", False)]
+    assert torch.isfinite(ref[1]).all()
+    for key, val in outs.items():
+        assert torch.equal(val[2], ref[2]), f"{key}: sampled subgraphs differ"
+        assert torch.equal(val[1], ref[1]), f"{key}: losses differ"
+        assert torch.equal(val[0], ref[0]), f"{key}: parameters differ"
