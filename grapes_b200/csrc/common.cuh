@@ -96,7 +96,7 @@ static inline PdlLaunch<K> pdl(K kernel, dim3 grid, dim3 block, size_t smem = 0,
 
 #ifdef __CUDACC__
 // spmm_tma.cu: 0 = launched, 1 = shape not covered (the caller falls back to the register-staged kernels)
-int grapes_launch_agg_tma(grapes_ctx* ctx, const float* X, int F, int ldx, const int* nodes, const int* n_dev, int cap_n,
+int grapes_launch_agg_tma(grapes_ctx* ctx, const void* X, int x_bf16, int F, int ldx, const int* nodes, const int* n_dev, int cap_n,
                           const int* in_off, const int* in_src, const float* dinv, const uint32_t* ind_bits, int num_ind,
                           const float* bias, int relu, float* out, int ldo, float* out_hi, float* out_lo, int ones_col,
                           int ec_req, int ctas_per_sm, cudaStream_t s);

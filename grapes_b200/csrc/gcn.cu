@@ -27,6 +27,29 @@ __device__ __forceinline__ void vec_fma(float (&acc)[VEC], float w, const float*
     for (int i = 0; i < VEC; ++i) acc[i] = fmaf(w, f[i], acc[i]);
 }
 
+// the same for a feature table stored as fp32 (XB16 = false) or bf16 (true; widened to fp32, arithmetic stays fp32)
+template <int VEC, bool XB16>
+__device__ __forceinline__ void vec_fma_x(float (&acc)[VEC], float w, const void* X, size_t elem) {
+    if (!XB16) {
+        vec_fma<VEC>(acc, w, reinterpret_cast<const float*>(X) + elem);
+    } else {
+        const unsigned short* p = reinterpret_cast<const unsigned short*>(X) + elem;
+        float f[VEC];
+        if (VEC == 4) {
+            const uint2 r = *reinterpret_cast<const uint2*>(p);
+            f[0] = __uint_as_float(r.x << 16); f[1] = __uint_as_float(r.x & 0xffff0000u);
+            f[2 % VEC] = __uint_as_float(r.y << 16); f[3 % VEC] = __uint_as_float(r.y & 0xffff0000u);
+        } else if (VEC == 2) {
+            const uint32_t r = *reinterpret_cast<const uint32_t*>(p);
+            f[0] = __uint_as_float(r << 16); f[1 % VEC] = __uint_as_float(r & 0xffff0000u);
+        } else {
+            f[0] = __uint_as_float(((uint32_t)p[0]) << 16);
+        }
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = fmaf(w, f[i], acc[i]);
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // k_agg: one warp per destination row j (local id).
 //   out[j, :F] = dinv[j]^2 * X[g(j), :F] + sum_{s in in(j)} dinv[s] dinv[j] * X[g(s), :F]   (+bias)(relu)
@@ -38,8 +61,8 @@ __device__ __forceinline__ void vec_fma(float (&acc)[VEC], float w, const float*
 // Sources are preloaded 32 at a time and broadcast by shuffle so the dependent chain
 // in_src -> nodes -> X is paid once per 32 sources.
 // ---------------------------------------------------------------------------------------
-template <int VEC>
-__global__ void __launch_bounds__(256) k_agg(const float* __restrict__ X, int F, int ldx,
+template <int VEC, bool XB16 = false>
+__global__ void __launch_bounds__(256) k_agg(const void* __restrict__ X, int F, int ldx,
                                              const int* __restrict__ nodes, const int* __restrict__ n_dev, int cap_n,
                                              const int* __restrict__ in_off, const int* __restrict__ in_src,
                                              const float* __restrict__ dinv, const uint32_t* __restrict__ ind_bits,
@@ -54,7 +77,6 @@ __global__ void __launch_bounds__(256) k_agg(const float* __restrict__ X, int F,
         const float dj = dinv[j];
         const int beg = in_off[j], end = in_off[j + 1];
         const size_t gj = nodes ? (size_t)nodes[j] : (size_t)j;
-        const float* xj = X + gj * ldx;
         float* oj = out ? out + (size_t)j * ldo : nullptr;
         float* ohj = out_hi ? out_hi + (size_t)j * ldo : nullptr;
         float* olj = out_hi ? out_lo + (size_t)j * ldo : nullptr;
@@ -64,7 +86,7 @@ __global__ void __launch_bounds__(256) k_agg(const float* __restrict__ X, int F,
             float acc[VEC];
 #pragma unroll
             for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
-            if (act) vec_fma<VEC>(acc, dj * dj, xj + c0);
+            if (act) vec_fma_x<VEC, XB16>(acc, dj * dj, X, gj * ldx + c0);
             for (int pb = beg; pb < end; pb += 32) {
                 const int p = pb + lane;
                 float w = 0.f; unsigned long long sg = 0ull;
@@ -77,7 +99,7 @@ __global__ void __launch_bounds__(256) k_agg(const float* __restrict__ X, int F,
                 for (int t = 0; t < cnt; ++t) {
                     const float wt = __shfl_sync(GRAPES_FULL_MASK, w, t);
                     const unsigned long long st = __shfl_sync(GRAPES_FULL_MASK, sg, t);
-                    if (act) vec_fma<VEC>(acc, wt, X + (size_t)st * ldx + c0);
+                    if (act) vec_fma_x<VEC, XB16>(acc, wt, X, (size_t)st * ldx + c0);
                 }
             }
             if (act) {
@@ -876,10 +898,11 @@ extern "C" {
 
 int grapes_agg_variant(int v) { g_agg_variant = v; return 0; }
 
-int grapes_aggregate(grapes_ctx* ctx, const float* X, int F, int ldx, const int* nodes, const int* n_dev, int cap_n,
-                     const int* in_off, const int* in_src, const float* dinv, const uint32_t* ind_bits, int num_ind,
-                     const float* bias, int relu, float* out, int ldo, float* out_hi, float* out_lo, int ones_col,
-                     void* stream) {
+static int aggregate_impl(grapes_ctx* ctx, const void* Xv, int x_bf16, int F, int ldx, const int* nodes, const int* n_dev,
+                          int cap_n, const int* in_off, const int* in_src, const float* dinv, const uint32_t* ind_bits,
+                          int num_ind, const float* bias, int relu, float* out, int ldo, float* out_hi, float* out_lo,
+                          int ones_col, void* stream) {
+    const float* X = reinterpret_cast<const float*>(Xv);
     GRAPES_REQUIRE(ctx && X && n_dev && in_off && in_src && dinv && (out || out_hi), "null argument");
     GRAPES_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), "out_hi and out_lo go together");
     GRAPES_REQUIRE(ones_col < 0 || (ones_col >= F + num_ind && ones_col < ldo), "ones_col must lie in the pad columns");
@@ -891,6 +914,29 @@ int grapes_aggregate(grapes_ctx* ctx, const float* X, int F, int ldx, const int*
     const size_t al = ((size_t)X) | ((size_t)out) | ((size_t)out_hi) | ((size_t)out_lo);
     const bool a16 = (al & 15) == 0;
     const bool a8 = (al & 7) == 0;
+    if (x_bf16) {
+        // bf16 feature table (papers100M-shaped config): TMA-staged form when the shape allows, else one warp per row
+        if (a16 && cap_n >= 4096 &&
+            grapes_launch_agg_tma(ctx, Xv, 1, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias, relu,
+                                  out, ldo, out_hi, out_lo, ones_col, cap_n > (1 << 19) ? 32 : 16,
+                                  cap_n > (1 << 19) ? 1 : 2, s) == 0) {
+            grapes_count_launches(1);
+            GRAPES_LAUNCH_OK();
+            return GRAPES_OK;
+        }
+        if (a16 && (F % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0))
+            pdl((k_agg<4, true>), blocks, 256, 0, s)(Xv, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind,
+                                                     bias, relu, out, ldo, out_hi, out_lo, ones_col);
+        else if ((F % 2 == 0) && (ldx % 2 == 0) && (ldo % 2 == 0) && a8)
+            pdl((k_agg<2, true>), blocks, 256, 0, s)(Xv, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind,
+                                                     bias, relu, out, ldo, out_hi, out_lo, ones_col);
+        else
+            pdl((k_agg<1, true>), blocks, 256, 0, s)(Xv, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind,
+                                                     bias, relu, out, ldo, out_hi, out_lo, ones_col);
+        grapes_count_launches(1);
+        GRAPES_LAUNCH_OK();
+        return GRAPES_OK;
+    }
     if (a16 && (F % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && (ldo - F <= 32) && cap_n >= 4096) {
         // frontier-sized: R rows per warp with interleaved load chains (variant chosen by grapes_agg_variant, default 0)
 #define AGG_LAUNCH(RR, MB)                                                                                              \
@@ -902,7 +948,7 @@ int grapes_aggregate(grapes_ctx* ctx, const float* X, int F, int ldx, const int*
         // grapes_agg_variant: 100 + ec / 200 + ec force a shape, 1..6 select the register-staged kernels.
         if (g_agg_variant == 0 || g_agg_variant >= 100) {
             const int v = g_agg_variant ? g_agg_variant : (cap_n > (1 << 19) ? 132 : 216);
-            if (grapes_launch_agg_tma(ctx, X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias,
+            if (grapes_launch_agg_tma(ctx, X, 0, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias,
                                       relu, out, ldo, out_hi, out_lo, ones_col, v % 100, v / 100, s) == 0) {
                 grapes_count_launches(1);
                 GRAPES_LAUNCH_OK();
@@ -931,6 +977,22 @@ int grapes_aggregate(grapes_ctx* ctx, const float* X, int F, int ldx, const int*
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
+}
+
+int grapes_aggregate(grapes_ctx* ctx, const float* X, int F, int ldx, const int* nodes, const int* n_dev, int cap_n,
+                     const int* in_off, const int* in_src, const float* dinv, const uint32_t* ind_bits, int num_ind,
+                     const float* bias, int relu, float* out, int ldo, float* out_hi, float* out_lo, int ones_col,
+                     void* stream) {
+    return aggregate_impl(ctx, X, 0, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias, relu, out,
+                          ldo, out_hi, out_lo, ones_col, stream);
+}
+
+int grapes_aggregate_bf16(grapes_ctx* ctx, const void* X_bf16, int F, int ldx, const int* nodes, const int* n_dev,
+                          int cap_n, const int* in_off, const int* in_src, const float* dinv, const uint32_t* ind_bits,
+                          int num_ind, const float* bias, int relu, float* out, int ldo, float* out_hi, float* out_lo,
+                          int ones_col, void* stream) {
+    return aggregate_impl(ctx, X_bf16, 1, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias, relu,
+                          out, ldo, out_hi, out_lo, ones_col, stream);
 }
 
 int grapes_aggregate_scalar(grapes_ctx* ctx, const float* z, int nparts, int part_stride, const int* n_dev, int cap_n, const int* in_off,

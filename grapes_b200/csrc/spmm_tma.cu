@@ -61,9 +61,11 @@ struct AtB { int g; float dsl, dj; uint32_t sb; int rk; };        // node id, de
 // OUTMODE: 1 = out, 2 = (out_hi, out_lo), 3 = all three.  The kernel is bound by instruction issue, not by memory
 // (ncu: issue slots 60 % busy at 25 % DRAM), so the per-entry loop is kept to: one broadcast LDS.128 of the entry's
 // metadata, one LDS.128 of the row per 128 columns, 4 FFMA, one branch.
-template <int NPASS, bool HAS_IND, int OUTMODE>
+// XB16: the feature table holds bf16 (papers100M-shaped config: 128 bf16 features); rows are staged as stored (2F bytes)
+// and widened to fp32 when they are read from shared memory; all arithmetic and the output stay fp32.
+template <int NPASS, bool HAS_IND, int OUTMODE, bool XB16>
 __global__ void __launch_bounds__(AT_THREADS) k_agg_tma(
-    const float* __restrict__ X, int F, int ldx, const int* __restrict__ nodes, const int* __restrict__ n_dev, int cap_n,
+    const void* __restrict__ X, int F, int ldx, const int* __restrict__ nodes, const int* __restrict__ n_dev, int cap_n,
     const int* __restrict__ in_off, const int* __restrict__ in_src, const float* __restrict__ dinv,
     const uint32_t* __restrict__ ind_bits, int num_ind, const float* __restrict__ bias, int relu, float* __restrict__ out,
     int ldo, float* __restrict__ out_hi, float* __restrict__ out_lo, int ones_col, int ec, int rb_min) {
@@ -72,7 +74,7 @@ __global__ void __launch_bounds__(AT_THREADS) k_agg_tma(
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
     const int n = min(*n_dev, cap_n);
-    const uint32_t rowbytes = (uint32_t)F * 4u;
+    const uint32_t rowbytes = (uint32_t)F * (XB16 ? 2u : 4u);
     const uint32_t slot_bytes = (uint32_t)ec * rowbytes;
     unsigned char* wslots = at_smem + (size_t)warp * 2u * slot_bytes;
     unsigned char* tail = at_smem + (size_t)AT_WARPS * 2u * slot_bytes;
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(AT_THREADS) k_agg_tma(
                 __syncwarp();
                 if (b.rk & AT_VALID)
                     at_bulk_row(slot0 + (uint32_t)(c & 1) * slot_bytes + (uint32_t)lane * rowbytes,
-                                X + (size_t)b.g * ldx, rowbytes, bar);
+                                reinterpret_cast<const unsigned char*>(X) + (size_t)b.g * ldx * (XB16 ? 2u : 4u), rowbytes, bar);
             }
         };
 
@@ -172,15 +174,23 @@ __global__ void __launch_bounds__(AT_THREADS) k_agg_tma(
             const int cnt = min(ec, T - c * ec);
             at_mbar_wait((c & 1) ? bar1 : bar0, (ph >> (c & 1)) & 1u);
             ph ^= 1u << (c & 1);
-            const float4* rp = reinterpret_cast<const float4*>(wslots + (size_t)(c & 1) * slot_bytes) + lane;
+            // lane l owns columns 4l .. 4l+3 of every 128-column pass: a float4 (fp32 table) or a uint2 (bf16 table)
+            const unsigned char* rp = wslots + (size_t)(c & 1) * slot_bytes + (size_t)lane * (XB16 ? 8u : 16u);
             const int4* mp = s_meta + (c & 1) * 32;
-            for (int t = 0; t < cnt; ++t, rp += (rowbytes >> 4)) {
+            for (int t = 0; t < cnt; ++t, rp += rowbytes) {
                 const int4 m = mp[t];                                      // broadcast: weight | row + flags | indicator bits
                 const float wt = __int_as_float(m.x);
 #pragma unroll
                 for (int p = 0; p < NPASS; ++p) {
                     if (act[p]) {
-                        const float4 v = rp[p * 32];
+                        float4 v;
+                        if (XB16) {
+                            const uint2 r = reinterpret_cast<const uint2*>(rp)[p * 32];
+                            v.x = __uint_as_float(r.x << 16); v.y = __uint_as_float(r.x & 0xffff0000u);
+                            v.z = __uint_as_float(r.y << 16); v.w = __uint_as_float(r.y & 0xffff0000u);
+                        } else {
+                            v = reinterpret_cast<const float4*>(rp)[p * 32];
+                        }
                         acc[p].x = fmaf(wt, v.x, acc[p].x); acc[p].y = fmaf(wt, v.y, acc[p].y);
                         acc[p].z = fmaf(wt, v.z, acc[p].z); acc[p].w = fmaf(wt, v.w, acc[p].w);
                     }
@@ -222,22 +232,24 @@ __global__ void __launch_bounds__(AT_THREADS) k_agg_tma(
     }
 }
 
-size_t grapes_agg_tma_smem(int F, int ec) {
-    return (size_t)AT_WARPS * 2u * (size_t)ec * (size_t)F * 4u + (size_t)AT_WARPS * 64u * 16u +
+size_t grapes_agg_tma_smem(int F, int ec, int es = 4) {
+    return (size_t)AT_WARPS * 2u * (size_t)ec * (size_t)F * (size_t)es + (size_t)AT_WARPS * 64u * 16u +
            (size_t)AT_WARPS * AT_POS_STRIDE * 4u + AT_WARPS * 16u;
 }
 
 // Returns 0 when the kernel was launched, 1 when the shape is not covered (caller falls back to k_agg_rows / k_agg).
-int grapes_launch_agg_tma(grapes_ctx* ctx, const float* X, int F, int ldx, const int* nodes, const int* n_dev, int cap_n,
+int grapes_launch_agg_tma(grapes_ctx* ctx, const void* X, int x_bf16, int F, int ldx, const int* nodes, const int* n_dev, int cap_n,
                           const int* in_off, const int* in_src, const float* dinv, const uint32_t* ind_bits, int num_ind,
                           const float* bias, int relu, float* out, int ldo, float* out_hi, float* out_lo, int ones_col,
                           int ec_req, int ctas_per_sm, cudaStream_t s) {
     if (F % 4 != 0 || ldx % 4 != 0 || ldo % 4 != 0 || ldo - F > 32 || F > 128 * 12 || F < 4) return 1;
+    if (x_bf16 && (F % 8 != 0 || ldx % 8 != 0 || F > 256)) return 1;         // 16-byte rows; bf16 forms built for F <= 256
+    const int es = x_bf16 ? 2 : 4;
     const size_t budget = (ctas_per_sm >= 2 ? 113u : 226u) * 1024u;
     int ec = ec_req > 0 ? ec_req : 32;
     if (ec > 32) ec = 32;
-    while (ec > 1 && grapes_agg_tma_smem(F, ec) > budget) ec >>= 1;
-    const size_t smem = grapes_agg_tma_smem(F, ec);
+    while (ec > 1 && grapes_agg_tma_smem(F, ec, es) > budget) ec >>= 1;
+    const size_t smem = grapes_agg_tma_smem(F, ec, es);
     if (smem > 226u * 1024u) return 1;
     const int npass = (F + 127) / 128;
     const int rb_min = 8;
@@ -245,34 +257,42 @@ int grapes_launch_agg_tma(grapes_ctx* ctx, const float* X, int F, int ldx, const
     const long long cap = (long long)ctx->sm_count * (smem > 113u * 1024u ? 1 : 2);
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-#define AT_LAUNCH3(NP, IND, OM)                                                                                         \
+#define AT_LAUNCH4(NP, IND, OM, XB)                                                                                       \
     do {                                                                                                                \
         static bool configured = false;                                                                                 \
         if (!configured) {                                                                                              \
-            if (cudaFuncSetAttribute(k_agg_tma<NP, IND, OM>, cudaFuncAttributeMaxDynamicSharedMemorySize,               \
+            if (cudaFuncSetAttribute(k_agg_tma<NP, IND, OM, XB>, cudaFuncAttributeMaxDynamicSharedMemorySize,               \
                                      (int)(226u * 1024u)) != cudaSuccess) return 1;                                     \
             configured = true;                                                                                          \
         }                                                                                                               \
-        pdl((k_agg_tma<NP, IND, OM>), (int)blocks, AT_THREADS, smem, s)(X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, \
+        pdl((k_agg_tma<NP, IND, OM, XB>), (int)blocks, AT_THREADS, smem, s)(X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, \
                                                                           dinv, ind_bits, num_ind, bias, relu, out, ldo,  \
                                                                           out_hi, out_lo, ones_col, ec, rb_min);          \
     } while (0)
-#define AT_LAUNCH2(NP, IND)                                                                                             \
+#define AT_LAUNCH2(NP, IND, XB)                                                                                         \
     do {                                                                                                                \
-        if (om == 1) AT_LAUNCH3(NP, IND, 1); else if (om == 2) AT_LAUNCH3(NP, IND, 2); else AT_LAUNCH3(NP, IND, 3);     \
+        if (om == 1) AT_LAUNCH4(NP, IND, 1, XB); else if (om == 2) AT_LAUNCH4(NP, IND, 2, XB);                          \
+        else AT_LAUNCH4(NP, IND, 3, XB);                                                                                \
     } while (0)
 #define AT_LAUNCH(NP)                                                                                                   \
     do {                                                                                                                \
-        if (has_ind) AT_LAUNCH2(NP, true); else AT_LAUNCH2(NP, false);                                                  \
+        if (has_ind) AT_LAUNCH2(NP, true, false); else AT_LAUNCH2(NP, false, false);                                    \
+    } while (0)
+#define AT_LAUNCH_B16(NP)                                                                                               \
+    do {                                                                                                                \
+        if (has_ind) AT_LAUNCH2(NP, true, true); else AT_LAUNCH2(NP, false, true);                                      \
     } while (0)
     const bool has_ind = ind_bits != nullptr && num_ind > 0;
     const int om = (out ? 1 : 0) | (out_hi ? 2 : 0);
-    if (npass == 1) AT_LAUNCH(1);
+    if (x_bf16) {
+        if (npass == 1) AT_LAUNCH_B16(1); else AT_LAUNCH_B16(2);
+    } else if (npass == 1) AT_LAUNCH(1);
     else if (npass == 2) AT_LAUNCH(2);
     else if (npass <= 5) AT_LAUNCH(5);
     else AT_LAUNCH(12);
+#undef AT_LAUNCH_B16
 #undef AT_LAUNCH2
-#undef AT_LAUNCH3
+#undef AT_LAUNCH4
 #undef AT_LAUNCH
     return 0;
 }

@@ -87,7 +87,9 @@ class GrapesEngine:
         self.L = lib()
         dev = graph.device
         self.device = dev
-        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        assert x.is_cuda and x.dtype in (torch.float32, torch.bfloat16) and x.is_contiguous()
+        # bf16 feature table (papers100M-shaped config): rows are gathered as stored and widened to fp32 in the aggregation
+        self.x_bf16 = x.dtype == torch.bfloat16
         assert sampling_hops <= 7, "indicator bits are packed in 8 columns"
         self.x, self.y = x, y.contiguous()
         self.multilabel = (y.dim() == 2)
@@ -502,7 +504,8 @@ class GrapesEngine:
         nc = self.net_c
         ldYc = self.Yc.shape[1]
         A_dev, cap_A = self._cnt("A"), self.cap_A
-        L.grapes_aggregate(ctx, X, F, F, ptr(self.all_nodes), A_dev, cap_A, ptr(self.cl_in_off[0]),
+        (L.grapes_aggregate_bf16 if self.x_bf16 else L.grapes_aggregate)(
+                           ctx, X, F, F, ptr(self.all_nodes), A_dev, cap_A, ptr(self.cl_in_off[0]),
                            ptr(self.cl_in_src[0]), ptr(self.cl_dinv[0]), None, 0, None, 0, ptr(self.Yc), ldYc, None, None, -1, st)
         L.grapes_gemm(ctx, 3, ptr(self.Yc), ldYc, self._par(nc.W1), F, ptr(self.out1), D, A_dev, cap_A, D, F,
                       self._par(nc.b1), 1, None, 0, st)
@@ -581,7 +584,8 @@ class GrapesEngine:
                            self._hc(h, "nnz"), ovf, st)
         if not self.random_sampling:
             tc = self.use_tc
-            L.grapes_aggregate(ctx, ptr(self.x), self.F, self.F, ptr(hw.batch_nodes), n_dev, cap_n, ptr(hw.in_off),
+            agg_x = L.grapes_aggregate_bf16 if self.x_bf16 else L.grapes_aggregate
+            agg_x(ctx, ptr(self.x), self.F, self.F, ptr(hw.batch_nodes), n_dev, cap_n, ptr(hw.in_off),
                                ptr(hw.in_src), ptr(hw.dinv), ptr(hw.ind_bits) if self.use_ind else None, self.num_ind,
                                None, 0, None if tc else ptr(hw.Y), self.ldY, ptr(hw.Y) if tc else None, ptr(hw.Y_lo),
                                self.Fp if self.use_tc_bwd else -1, st)

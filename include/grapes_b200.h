@@ -152,6 +152,12 @@ int grapes_aggregate(grapes_ctx* ctx, const float* X, int F, int ldx, const int*
                      const int* in_off, const int* in_src, const float* dinv, const uint32_t* ind_bits, int num_ind,
                      const float* bias, int relu, float* out, int ldo, float* out_hi, float* out_lo, int ones_col,
                      void* stream);
+/* the same with the feature table stored as bf16 (papers100M-shaped config: 128 bf16 features, BASELINE.json configs[4]);
+ * rows are widened to fp32 as they are read, arithmetic and outputs stay fp32.  ldx in elements.                */
+int grapes_aggregate_bf16(grapes_ctx* ctx, const void* X_bf16, int F, int ldx, const int* nodes, const int* n_dev,
+                          int cap_n, const int* in_off, const int* in_src, const float* dinv, const uint32_t* ind_bits,
+                          int num_ind, const float* bias, int relu, float* out, int ldo, float* out_hi, float* out_lo,
+                          int ones_col, void* stream);
 /* z may be given as `nparts` partial vectors `part_stride` floats apart (summed on the fly)           */
 int grapes_aggregate_scalar(grapes_ctx* ctx, const float* z, int nparts, int part_stride, const int* n_dev, int cap_n, const int* in_off,
                             const int* in_src, const float* dinv, const float* bias, float* out, float* zero_out,

@@ -30,6 +30,9 @@ def _setup(name, seed, dev, use_tensor_cores=False, **kw):
     cfg = dict(SHAPES[name])
     torch.manual_seed(1000 + seed)     # the oracle draws its Gumbel noise from the global CPU generator
     d = make_synth(name, seed=seed, multilabel=kw.pop("multilabel", False))
+    feature_bf16 = kw.pop("feature_bf16", False)
+    if feature_bf16:                     # the table is STORED in bf16; the oracle computes on exactly those values
+        d.x = d.x.bfloat16().float()
     hp = dict(sampling_hops=cfg["sampling_hops"], num_samples=cfg["num_samples"])
     hp.update(kw)
     hidden = hp.pop("hidden_dim", 256)
@@ -37,7 +40,8 @@ def _setup(name, seed, dev, use_tensor_cores=False, **kw):
     # the same reference path in its own precision (fp32): measures how far fp32 itself sits from fp64
     st.fp32 = rp.OracleState(d, seed=seed + 100, dtype=torch.float32, hidden_dim=hidden, **hp)
     g = DeviceGraph.from_edge_index(d.edge_index, d.num_nodes, device=dev)
-    eng = GrapesEngine(g, d.x.to(dev), d.y.to(dev), num_classes=d.num_classes, batch_size=cfg["batch_size"],
+    eng = GrapesEngine(g, d.x.to(dev).bfloat16() if feature_bf16 else d.x.to(dev), d.y.to(dev),
+                       num_classes=d.num_classes, batch_size=cfg["batch_size"],
                        hidden_dim=st.gcn_c.gcn_layers[0].lin.weight.shape[0],
                        lr_gc=1e-3, lr_gf=1e-4, seed=seed, use_tensor_cores=use_tensor_cores, **hp)
     eng.load_state_dicts(gcn_c=st.gcn_c.state_dict(), gcn_gf=st.gcn_gf.state_dict(), gcn_z=st.gcn_z.state_dict())
@@ -304,3 +308,21 @@ def test_prefetch_matches_plain_steps(cuda_device):
         assert torch.equal(val[2], ref[2]), f"{key}: sampled subgraphs differ"
         assert torch.equal(val[1], ref[1]), f"{key}: losses differ"
         assert torch.equal(val[0], ref[0]), f"{key}: parameters differ"
+
+
+@pytest.mark.parametrize("name,seed,tc", [("tiny", 0, False), ("small", 1, True), ("mid16", 2, True)])
+def test_step_parity_bf16_feature_table(cuda_device, name, seed, tc):
+    """papers100M-shaped config (BASELINE.json configs[4]): the feature table is stored as bf16.  Rows are gathered as
+    stored and widened in the aggregation, arithmetic stays fp32, so against the oracle fed the same bf16-rounded values
+    the fp32 bars hold (far inside the 2e-2 bf16 tolerance of the north star); integer contracts bit-exact.
+    'mid16' (F = 128, frontier >= 4096 rows) takes the TMA-staged bf16 kernel, the others the warp-per-row form."""
+    from grapes_b200.synth import SHAPES
+    if name == "mid16":
+        SHAPES["mid16"] = dict(N=30_000, E_dir=600_000, F=128, C=9, n_train=8_000, batch_size=256, num_samples=64,
+                               sampling_hops=2)
+    try:
+        d, st, eng, train_idx, B = _setup(name, seed, cuda_device, use_tensor_cores=tc, feature_bf16=True)
+    finally:
+        SHAPES.pop("mid16", None)
+    assert eng.x_bf16
+    _check_step(st, eng, train_idx[:B], cuda_device, apply_optim=False, relaxed=tc)
