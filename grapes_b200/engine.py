@@ -305,9 +305,6 @@ class GrapesEngine:
         self.__dict__.update(self._states[p])
         self.par = p
 
-    def _save_state_scalars(self):
-        self._states[self.par]["bsz"] = self.bsz
-
     # ------------------------------------------------------------------ helpers
     _CNT = dict(B=0, A=1, cl_nnz=2)
 
