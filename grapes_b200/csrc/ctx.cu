@@ -22,6 +22,14 @@ int grapes_abi_version(void) { return 1; }
 int grapes_set_pdl(int mask) { g_grapes_pdl = mask; return 0; }
 int64_t grapes_kernel_launches(void) { return (int64_t)g_launches; }
 
+int grapes_ctx_set_sm_limit(grapes_ctx* ctx, int sms) {
+    GRAPES_REQUIRE(ctx != nullptr, "null ctx");
+    cudaDeviceProp prop;
+    GRAPES_CUDA_OK(cudaGetDeviceProperties(&prop, ctx->device));
+    ctx->sm_count = (sms > 0 && sms < prop.multiProcessorCount) ? sms : prop.multiProcessorCount;
+    return GRAPES_OK;
+}
+
 int grapes_ctx_create(int device, int64_t num_nodes, int64_t max_frontier, int64_t partials_bytes, grapes_ctx** out) {
     GRAPES_REQUIRE(out != nullptr, "null out");
     GRAPES_REQUIRE(num_nodes > 0 && num_nodes < (1ll << 31), "num_nodes must fit int32");

@@ -129,6 +129,13 @@ class GrapesEngine:
             self.side_a, self.side_b = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
             self.side_p = torch.cuda.Stream(device=dev)          # front end of the NEXT batch (cross-step prefetch)
             self.ctx_a, self.ctx_b, self.ctx_p = graph.new_ctx(), graph.new_ctx(16 << 20), graph.new_ctx(16 << 20)
+            # the backward / gcn_z branch is off the critical path: its persistent tcgen05 kernels get a share of the SMs
+            # so the hop chain's small kernels are not queued behind them (measured)
+            # products / arxiv shape (K ~ 100): 96 of 148 SMs -> 0.549 -> 0.533 / 0.251 -> 0.236 ms/step; with long K
+            # (Reddit 602, Cora 1433 columns) the backward is heavy enough to become the critical path when limited
+            side_sms = int(os.environ.get("GRAPES_SIDE_SMS", "96" if (F + self.H + 1) <= 256 else "0"))
+            if side_sms > 0:
+                self.L.grapes_ctx_set_sm_limit(self.ctx_a, side_sms)
         else:
             self.side_a = self.side_b = self.side_p = self.main_hp = None
             self.ctx_a = self.ctx_b = self.ctx_p = graph.ctx

@@ -65,6 +65,10 @@ typedef struct grapes_ctx grapes_ctx;
  * number of frontier nodes/edges any later call is given (sizes the scan scratch);
  * `partials_bytes` sizes the split-K partial buffer of the weight-gradient GEMMs.                 */
 int grapes_ctx_create(int device, int64_t num_nodes, int64_t max_frontier, int64_t partials_bytes, grapes_ctx** out);
+/* Grid-size budget of this context: every launch through `ctx` sizes its grid for `sms` SMs instead of the whole GPU
+ * (<= 0 restores the device's count).  Used for the contexts of side streams whose kernels are off the critical path
+ * (the sampler backward): persistent tcgen05 kernels that take every SM would stall the critical path's small kernels. */
+int grapes_ctx_set_sm_limit(grapes_ctx* ctx, int sms);
 int grapes_ctx_destroy(grapes_ctx* ctx);
 const char* grapes_last_error(void);
 int grapes_abi_version(void);
