@@ -237,6 +237,9 @@ class GrapesEngine:
         self.record: Optional[dict] = None
         # timing experiments only (scripts/ablate.py): leave out parts of the step to see what the rest costs
         self.ablate = set(filter(None, os.environ.get("GRAPES_ABLATE", "").split(",")))
+        # where the gcn_z chain sits on the backward branch: behind the LAST hop's backward it overlaps the classifier tail
+        # (small kernels) instead of hop 1's aggregation + GEMM: products 0.533 -> 0.511 ms/step; neutral with long K
+        self.z_at = os.environ.get("GRAPES_Z_AT", "last" if (F + self.H + 1) <= 256 else "hop0")
         if os.environ.get("GRAPES_AGG_VARIANT"):
             self.L.cdll.grapes_agg_variant(int(os.environ["GRAPES_AGG_VARIANT"]))
         if os.environ.get("GRAPES_TC_DEBUG"):
@@ -455,6 +458,8 @@ class GrapesEngine:
                 fork(sA)
                 with on(sA):
                     self._enqueue_hop_backward(h, ctx_a, stA)
+                    if h == H - 1 and self.z_at != "hop0":
+                        self._enqueue_gcn_z(ctx_a, stA)
 
         if os.environ.get("GRAPES_PREFETCH_AT", "start") == "tail":
             self._enqueue_prefetch(fork, on, sP, stP)
@@ -628,8 +633,19 @@ class GrapesEngine:
             L.grapes_sampler_l1_bwd(ctx, ptr(hw.Y), self.ldY, n_dev, cap_n, Fp, self._par(gf.W1), Fp, D,
                                     self._par(gf.b1), self._par(gf.W2), ptr(hw.dz), ptr(self.dpre), 1.0, 1,
                                     self._dir(gf.W1), Fp, self._dir(gf.b1), self._dir(gf.W2), st)
-        if h != 0:
-            return
+        if h == 0 and self.z_at == "hop0":
+            self._enqueue_gcn_z(ctx, st)
+
+    def _enqueue_gcn_z(self, ctx, st):
+        """Side stream A.  gcn_z on the hop-0 frontier: log_z (main.py:223-228) and its gradient direction.  Needs only
+        the hop-0 workspace, so it can sit anywhere on the branch; `z_at` = "last" puts it behind the last hop's backward,
+        where it overlaps the classifier tail (small kernels) instead of hop 1's aggregation and GEMM."""
+        L = self.L
+        h = 0
+        hw = self.hops[0]
+        F, Fp, D, cap_n, cap_P = self.F, self.Fp, self.D, self.cap_n, self.cap_P
+        nz = self.net_z
+        n_dev, P_dev = self._hc(0, "n"), self._hc(0, "P")
         # log_z = mean(gcn_z(x[batch_nodes], edges)) - log_z_init   (main.py:223-228)
         if self.use_tc:
             L.grapes_sampler_l1_fwd_tc(ctx, ptr(hw.Y), ptr(hw.Y_lo), self.ldY, n_dev, cap_n, F, ptr(self.Wz_hi),
