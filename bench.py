@@ -397,6 +397,8 @@ def main():
         P_STEPS = 5
         L.profiling = True
         eng.multi_stream = False             # one stream: each kernel is timed alone, not against its co-runners
+        if eng.ctx_a is not graph.ctx:
+            L.grapes_ctx_set_sm_limit(eng.ctx_a, 0)    # ... and with the whole GPU (in the step the backward branch is given 96 SMs)
         per_hop_acc = None
         for j in range(P_STEPS):
             eng.set_targets(batches[j])
