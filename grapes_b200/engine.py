@@ -237,6 +237,10 @@ class GrapesEngine:
         self.record: Optional[dict] = None
         # timing experiments only (scripts/ablate.py): leave out parts of the step to see what the rest costs
         self.ablate = set(filter(None, os.environ.get("GRAPES_ABLATE", "").split(",")))
+        # rank + relabel + CSR build of a hop as ONE cooperative launch (grapes_hop_structure): bit-identical, 73 -> 61
+        # launches per step, but NOT faster (34 us per hop either way: the phases are memory-latency chains, and a
+        # cooperative grid has to wait for SMs held by the side branches) -> opt-in
+        self.fused_struct = os.environ.get("GRAPES_FUSED_STRUCT", "0") == "1"
         # where the gcn_z chain sits on the backward branch: behind the LAST hop's backward it overlaps the classifier tail
         # (small kernels) instead of hop 1's aggregation + GEMM: products 0.533 -> 0.511 ms/step; neutral with long K
         self.z_at = os.environ.get("GRAPES_Z_AT", "last" if (F + self.H + 1) <= 256 else "hop0")
@@ -581,16 +585,26 @@ class GrapesEngine:
         rows = ptr(self.prev[h])
         m_dev, n_dev, c_dev = self._hc(h, "m"), self._hc(h, "n"), self._hc(h, "c")
         ovf = ptr(self.overflow)
-        L.grapes_rank_nodes(ctx, ptr(self.bm_batch[h]), ptr(self.bm_prev[h]), ptr(self.pref_batch),
-                            ptr(self.pref_nb), ptr(hw.batch_nodes), ptr(hw.nb_nodes), ptr(hw.nb_local),
-                            ptr(hw.nb_index), ptr(hw.ind_bits) if self.use_ind else None,
-                            ptr(self.bm_ind) if self.use_ind else None, self.num_ind, h, cap_n,
-                            n_dev, c_dev, ovf, st)
-        L.grapes_edges_to_local(ctx, rows, ptr(hw.e_row), ptr(hw.e_col), m_dev, cap_m, ptr(self.bm_batch[h]),
-                                ptr(self.pref_batch), ptr(hw.e_src), ptr(hw.e_dst), ptr(self.cnt_scratch), st)
-        L.grapes_build_csr(ctx, ptr(hw.e_dst), ptr(hw.e_src), m_dev, cap_m, n_dev, cap_n, ptr(self.cnt_scratch),
-                           1, ptr(hw.in_off), ptr(hw.in_src), ptr(self.tmp_val), ptr(hw.dinv),
-                           self._hc(h, "nnz"), ovf, st)
+        if self.fused_struct:
+            # rank -> relabel + histogram -> scan -> fill -> per-row sort in ONE cooperative launch (grid barriers)
+            L.grapes_hop_structure(ctx, ptr(self.bm_batch[h]), ptr(self.bm_prev[h]), ptr(self.pref_batch),
+                                   ptr(self.pref_nb), ptr(hw.batch_nodes), ptr(hw.nb_nodes), ptr(hw.nb_local),
+                                   ptr(hw.nb_index), ptr(hw.ind_bits) if self.use_ind else None,
+                                   ptr(self.bm_ind) if self.use_ind else None, self.num_ind, h, cap_n, n_dev, c_dev,
+                                   rows, ptr(hw.e_row), ptr(hw.e_col), m_dev, cap_m, ptr(hw.e_src), ptr(hw.e_dst),
+                                   ptr(self.cnt_scratch), ptr(hw.in_off), ptr(hw.in_src), ptr(self.tmp_val),
+                                   ptr(hw.dinv), self._hc(h, "nnz"), ovf, st)
+        else:
+            L.grapes_rank_nodes(ctx, ptr(self.bm_batch[h]), ptr(self.bm_prev[h]), ptr(self.pref_batch),
+                                ptr(self.pref_nb), ptr(hw.batch_nodes), ptr(hw.nb_nodes), ptr(hw.nb_local),
+                                ptr(hw.nb_index), ptr(hw.ind_bits) if self.use_ind else None,
+                                ptr(self.bm_ind) if self.use_ind else None, self.num_ind, h, cap_n,
+                                n_dev, c_dev, ovf, st)
+            L.grapes_edges_to_local(ctx, rows, ptr(hw.e_row), ptr(hw.e_col), m_dev, cap_m, ptr(self.bm_batch[h]),
+                                    ptr(self.pref_batch), ptr(hw.e_src), ptr(hw.e_dst), ptr(self.cnt_scratch), st)
+            L.grapes_build_csr(ctx, ptr(hw.e_dst), ptr(hw.e_src), m_dev, cap_m, n_dev, cap_n, ptr(self.cnt_scratch),
+                               1, ptr(hw.in_off), ptr(hw.in_src), ptr(self.tmp_val), ptr(hw.dinv),
+                               self._hc(h, "nnz"), ovf, st)
         if not self.random_sampling:
             tc = self.use_tc
             agg_x = L.grapes_aggregate_bf16 if self.x_bf16 else L.grapes_aggregate

@@ -104,6 +104,15 @@ int grapes_rank_nodes(grapes_ctx* ctx, const uint32_t* bm_batch, const uint32_t*
                       int* pref_nb, int* batch_nodes, int* nb_nodes, int* nb_local, int* nb_index, uint32_t* ind_bits,
                       uint32_t* bm_ind, int ind_rows, int hop, int cap_n, int* n_dev, int* c_dev, int* overflow,
                       void* stream);
+/* grapes_rank_nodes + grapes_edges_to_local + grapes_build_csr (frontier-sized form) in ONE cooperative launch with
+ * grid barriers between the five phases: same outputs bit for bit (main.py:183-195 + gcn_norm structure of the hop
+ * graph); cnt_scratch all-zero on entry and on exit.                                                              */
+int grapes_hop_structure(grapes_ctx* ctx, const uint32_t* bm_batch, const uint32_t* bm_prev, int* pref_batch, int* pref_nb,
+                         int* batch_nodes, int* nb_nodes, int* nb_local, int* nb_index, uint32_t* ind_bits,
+                         uint32_t* bm_ind, int ind_rows, int hop, int cap_n, int* n_dev, int* c_dev, const int* rows,
+                         const int* e_row, const int* e_col, const int* m_dev, int cap_m, int* e_src, int* e_dst,
+                         int* cnt_scratch, int* in_off, int* in_src, int* tmp_val, float* dinv, int* nnz_dev,
+                         int* overflow, void* stream);
 /* node_map.map(neighborhoods) (main.py:195): local (src, dst) of every expanded edge.  cnt_hist
  * (optional, all-zero on entry) receives the in-degree histogram grapes_build_csr(hist_done=1) needs. */
 int grapes_edges_to_local(grapes_ctx* ctx, const int* rows, const int* e_row, const int* e_col, const int* m_dev,
