@@ -34,3 +34,28 @@ def allreduce_mean_(flat: torch.Tensor) -> torch.Tensor:
 
 def flatten_grads(named_grads) -> torch.Tensor:
     return torch.cat([g.reshape(-1) for _, g in sorted(named_grads.items())])
+
+
+class PeerGradExchange:
+    """Symmetric (peer-mapped) gradient buffers for ``grapes_allreduce_adam_peer``: every rank allocates the same buffer
+    with ``torch.distributed._symmetric_memory`` and receives the peers' device pointers, so the mean all-reduce and both
+    Adam updates run as two kernels over NVLink inside the step's CUDA graph (no host-side collective call)."""
+
+    def __init__(self, n_floats: int, device: torch.device, group=None):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm_mem
+        from ._lib import lib
+        group = group or dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 8:
+            raise RuntimeError("peer exchange is built for one NVSwitch box (<= 8 ranks)")
+        total = int(lib().cdll.grapes_peer_buffer_floats(int(n_floats)))
+        self.buf = symm_mem.empty(total, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, group.group_name if hasattr(group, "group_name") else group)
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        assert ptrs[self.rank] == self.buf.data_ptr()
+        self.peer_ptrs = (ctypes.c_void_p * self.world)(*ptrs)              # HOST array handed to the C ABI
+        self.state = torch.zeros(4, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                                                   # every buffer is zeroed before anyone publishes

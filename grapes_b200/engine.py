@@ -28,7 +28,8 @@ from .graph import DeviceGraph
 
 SCAL = dict(loss_c=0, tot_log_prob=1, log_z_mean=2, log_z=3, loss_gfn=4, g_gf=5, g_z=6, sum_dl=7)
 NOISE_PHILOX, NOISE_GUMBEL, NOISE_UNIFORM, NOISE_KEYS, NOISE_TOPK_PROBS = 0, 1, 2, 3, 4
-OVF_NAMES = {1: "rows>cap_P", 2: "edges>cap_m", 4: "nodes>cap_n", 8: "block>cap_blk", 16: "hub worklist"}
+OVF_NAMES = {1: "rows>cap_P", 2: "edges>cap_m", 4: "nodes>cap_n", 8: "block>cap_blk", 16: "hub worklist",
+             32: "a peer rank never published its gradients"}
 
 
 def _round_up(a: int, b: int) -> int:
@@ -232,6 +233,7 @@ class GrapesEngine:
             glorot_(v["gcn_layers.0.lin.weight"], gen)
             glorot_(v["gcn_layers.1.lin.weight"], gen)
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        self.peer = None                         # PeerGradExchange when data-parallel over NVLink peer memory
         self._graph_launches: Dict[tuple, int] = {}
         self.launches_per_graph = 0
         self.record: Optional[dict] = None
@@ -698,8 +700,16 @@ class GrapesEngine:
         L.grapes_split_tf32(ctx, self._par(nz.W1), self.F, self.D, self.F, ptr(self.Wz_hi), ptr(self.Wz_lo),
                             self.ldW, st)
 
+    def enable_peer_exchange(self, group=None):
+        """Data-parallel mode: from now on the optimiser launch of every step is the peer-memory mean all-reduce + Adam
+        (``grapes_allreduce_adam_peer``), captured with the rest of the step."""
+        from .dist import PeerGradExchange
+        self.peer = PeerGradExchange(self.n_par, self.device, group)
+        self._graphs.clear()
+
     def _enqueue_optim(self):
-        """optimizer_c.step() and optimizer_gf.step() (main.py:268,289) as one launch over the flat buffers."""
+        """optimizer_c.step() and optimizer_gf.step() (main.py:268,289) as one launch over the flat buffers; with a
+        peer exchange enabled: on the mean of the per-rank gradients, all-reduced over NVLink peer memory."""
         L, ctx = self.L, self.g.ctx
         st = torch.cuda.current_stream().cuda_stream
         nc, gf, nz = self.net_c, self.net_gf, self.net_z
@@ -707,6 +717,13 @@ class GrapesEngine:
             n1 = 0
         else:
             n1 = (nz.end - gf.base) if not self.reinforce else gf.size   # gcn_z has no grad under REINFORCE (main.py:279)
+        if self.peer is not None:
+            pe = self.peer
+            L.grapes_allreduce_adam_peer(ctx, pe.peer_ptrs, pe.rank, pe.world, ptr(self.grads), self.n_par,
+                                         ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                                         nc.base, nc.size, self.lr_gc, gf.base, n1, self.lr_gf, 0.9, 0.999, 1e-8,
+                                         ptr(self.adam_steps), ptr(pe.state), ptr(self.overflow), st)
+            return
         L.grapes_adam_step2(ctx, ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq),
                             nc.base, nc.size, self.lr_gc, gf.base, n1, self.lr_gf, 0.9, 0.999, 1e-8,
                             ptr(self.adam_steps), st)

@@ -39,6 +39,7 @@ extern "C" {
 #define GRAPES_OVF_NODES 4  /* frontier nodes exceed cap_n     */
 #define GRAPES_OVF_BLOCK 8  /* induced block exceeds cap_out   */
 #define GRAPES_OVF_HUB 16   /* hub-row worklist exceeded       */
+#define GRAPES_OVF_PEER_TIMEOUT 32 /* a peer rank never published its gradients (grapes_allreduce_adam_peer) */
 
 /* noise modes of grapes_select_topk */
 #define GRAPES_NOISE_PHILOX 0          /* draw u on the device (Philox4x32-10), g = -log(-log u)          */
@@ -268,6 +269,20 @@ int grapes_adam_step2(grapes_ctx* ctx, float* params, const float* grads, float*
                       int off0, int n0, float lr0, int off1, int n1, float lr1, float beta1, float beta2, float eps,
                       float* steps_dev, void* stream);
 int grapes_fill_f32(grapes_ctx* ctx, float* p, float value, int n, void* stream);
+
+/* ---- data-parallel exchange: gradient all-reduce (mean) + both Adam groups over NVLink peer memory ------------ */
+/* floats of symmetric buffer each rank must provide for an n-float gradient (two slots + flag words)              */
+int64_t grapes_peer_buffer_floats(int n);
+/* Publishes `grads` into this rank's symmetric buffer, waits (bounded) for every peer, sums the `world` slots in rank
+ * order over NVLink, divides by `world`, applies grapes_adam_step2's arithmetic and writes the mean gradient to
+ * grads_mean_out.  peer_bufs: HOST array of `world` peer-mapped device pointers (own buffer at index `rank`), zeroed
+ * once; state: 4 device uint32, zeroed once; err_flag receives GRAPES_OVF_PEER_TIMEOUT instead of a hang.  Two launches,
+ * no per-step host argument: capturable into the step's CUDA graph (main.py:268,289 on the mean of the per-rank
+ * gradients; the reference itself is single-process).                                                              */
+int grapes_allreduce_adam_peer(grapes_ctx* ctx, void* const* peer_bufs, int rank, int world, const float* grads, int n,
+                               float* params, float* grads_mean_out, float* exp_avg, float* exp_avg_sq, int off0,
+                               int n0, float lr0, int off1, int n1, float lr1, float beta1, float beta2, float eps,
+                               float* steps_dev, unsigned int* state, int* err_flag, void* stream);
 
 #ifdef __cplusplus
 }
