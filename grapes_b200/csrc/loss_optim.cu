@@ -288,6 +288,52 @@ __global__ void __launch_bounds__(256) k_gfn_finalize_scale(float* scal, float l
     }
 }
 
+// Learned node features (main.py:89-100,116: an nn.Parameter table [N, F] inside optimizer_c).  torch.optim.Adam is DENSE:
+// every row's moments decay and every row whose moments are non-zero keeps moving, not only the rows of this batch.  The
+// gradient is sparse -- d loss_c / d x is non-zero only on the batch's all_nodes rows -- so it is read through the
+// all_nodes bitmap (local row = rank of the bit) instead of being scattered into a dense [N, F] buffer first.  Rows that
+// were never touched (m = v = 0, no gradient) are left alone: their update is exactly 0.  `step` = optimizer_c's count
+// BEFORE this update (grapes_adam_step2, launched afterwards, increments it).
+__global__ void __launch_bounds__(256) k_adam_embed(float* __restrict__ x, float* __restrict__ m, float* __restrict__ v,
+                                                    int64_t N, int F4, const uint32_t* __restrict__ bm,
+                                                    const int* __restrict__ pref, const float* __restrict__ grows,
+                                                    int ldg4, float lr, float beta1, float beta2, float eps,
+                                                    const float* __restrict__ step) {
+    pdl_begin();
+    __shared__ float s_step_size, s_bc2_sqrt;
+    if (threadIdx.x == 0) {
+        const double t = (double)(*step) + 1.0;
+        const double bc1 = 1.0 - pow((double)beta1, t), bc2 = 1.0 - pow((double)beta2, t);
+        s_step_size = (float)((double)lr / bc1);
+        s_bc2_sqrt = (float)sqrt(bc2);
+    }
+    __syncthreads();
+    const float step_size = s_step_size, bc2s = s_bc2_sqrt;
+    const int64_t total = N * (int64_t)F4;
+    float4* x4 = reinterpret_cast<float4*>(x);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    const float4* g4 = reinterpret_cast<const float4*>(grows);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int node = (int)(i / F4), c = (int)(i - (int64_t)node * F4);
+        const bool hit = bitmap_test(bm, node);
+        float4 mi = m4[i], vi = v4[i];
+        if (!hit && mi.x == 0.f && mi.y == 0.f && mi.z == 0.f && mi.w == 0.f && vi.x == 0.f && vi.y == 0.f &&
+            vi.z == 0.f && vi.w == 0.f)
+            continue;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (hit) g = g4[(size_t)bitmap_rank(bm, pref, node) * ldg4 + c];
+        float4 p = x4[i];
+#define GRAPES_ADAM1(f)                                                                       \
+        mi.f = mi.f + (g.f - mi.f) * (1.0f - beta1);                                          \
+        vi.f = vi.f * beta2 + (1.0f - beta2) * g.f * g.f;                                     \
+        p.f = p.f - step_size * (mi.f / (sqrtf(vi.f) / bc2s + eps));
+        GRAPES_ADAM1(x) GRAPES_ADAM1(y) GRAPES_ADAM1(z) GRAPES_ADAM1(w)
+#undef GRAPES_ADAM1
+        m4[i] = mi; v4[i] = vi; x4[i] = p;
+    }
+}
+
 // Two Adam parameter groups (optimizer_c, optimizer_gf: main.py:117-118) in one launch.  Every block reads the step
 // counts before anyone changes them; the last block to finish increments both (threadfence + ticket), so no
 // separate increment launch is needed.
@@ -428,6 +474,24 @@ int grapes_adam_step2(grapes_ctx* ctx, float* params, const float* grads, float*
     pdl((k_adam2), grid_for(ctx, n0 + n1, 256), 256, 0, (cudaStream_t)stream)(params, grads, exp_avg, exp_avg_sq, off0, n0,
                                                                            lr0, off1, n1, lr1, beta1, beta2, eps,
                                                                            steps_dev, ctx->scan_counters + 2);
+    grapes_count_launches(1);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+int grapes_adam_embed(grapes_ctx* ctx, float* table, float* exp_avg, float* exp_avg_sq, int64_t num_nodes, int F,
+                      const uint32_t* bm_rows, const int* pref_rows, const float* grad_rows, int ldg, float lr,
+                      float beta1, float beta2, float eps, const float* step_dev, void* stream) {
+    GRAPES_REQUIRE(ctx && table && exp_avg && exp_avg_sq && bm_rows && pref_rows && grad_rows && step_dev, "null argument");
+    GRAPES_REQUIRE(F > 0 && F % 4 == 0 && ldg % 4 == 0 && ldg >= F, "embedding width and gradient pitch must be multiples of 4");
+    GRAPES_REQUIRE(num_nodes == ctx->num_nodes, "table rows != graph nodes");
+    const long long total = (long long)num_nodes * (F / 4);
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)ctx->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    pdl((k_adam_embed), (int)blocks, 256, 0, (cudaStream_t)stream)(table, exp_avg, exp_avg_sq, num_nodes, F / 4, bm_rows,
+                                                                  pref_rows, grad_rows, ldg / 4, lr, beta1, beta2, eps,
+                                                                  step_dev);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;

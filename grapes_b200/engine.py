@@ -83,7 +83,7 @@ class GrapesEngine:
                  log_z_init: float = 0., reg_param: float = 0., random_sampling: bool = False,
                  reinforce_baseline: bool = False, seed: int = 0, cap_edges: Optional[int] = None,
                  cap_nodes: Optional[int] = None, cap_block: Optional[int] = None,
-                 use_tensor_cores: bool = True, multi_stream: bool = True):
+                 use_tensor_cores: bool = True, multi_stream: bool = True, embed_nodes: bool = False):
         self.g = graph
         self.L = lib()
         dev = graph.device
@@ -93,6 +93,11 @@ class GrapesEngine:
         self.x_bf16 = x.dtype == torch.bfloat16
         assert sampling_hops <= 7, "indicator bits are packed in 8 columns"
         self.x, self.y = x, y.contiguous()
+        # main.py:89-100,116: `x` is a learned table (nn.Parameter inside optimizer_c); it is updated IN PLACE by every
+        # optimiser step (dense Adam from the sparse classifier gradient, grapes_adam_embed)
+        self.embed_nodes = bool(embed_nodes)
+        if self.embed_nodes:
+            assert x.dtype == torch.float32 and x.shape[1] % 4 == 0, "learned node features: fp32, width a multiple of 4"
         self.multilabel = (y.dim() == 2)
         if self.multilabel:
             self.y = self.y.to(torch.float32)
@@ -222,6 +227,13 @@ class GrapesEngine:
         self.dlogits = z((A, C), **f32)
         self.dZ = e((A, C), **f32)
         self.dpre1 = e((A, D), **f32)
+        if self.embed_nodes:
+            # d loss_c / d x[all_nodes] = A_hat_1^T (dpre1 W1): needs the layer-1 block keyed by SOURCE as well
+            self.cl_out_off0 = z(A + 1, **i32)
+            self.cl_out_dst0 = e(self.cap_blk, **i32)
+            self.dYc = z((A, _round_up(F, 4)), **f32)
+            self.dXc = z((A, _round_up(F, 4)), **f32)
+            self.emb_exp_avg, self.emb_exp_avg_sq = torch.zeros_like(x), torch.zeros_like(x)
 
         self.params = z(n_par, **f32)
         self.grads = z(n_par, **f32)
@@ -519,6 +531,10 @@ class GrapesEngine:
         nc = self.net_c
         ldYc = self.Yc.shape[1]
         A_dev, cap_A = self._cnt("A"), self.cap_A
+        if self.embed_nodes:
+            L.grapes_build_csr(ctx, ptr(self.cl_src[0]), ptr(self.cl_dst[0]), self._hc(H - 1, "blk"), self.cap_blk,
+                               A_dev, cap_A, ptr(self.cnt_scratch), 0, ptr(self.cl_out_off0), ptr(self.cl_out_dst0),
+                               ptr(self.cl_tmp), None, self._cnt("cl_nnz", 3), ovf, st)
         (L.grapes_aggregate_bf16 if self.x_bf16 else L.grapes_aggregate)(
                            ctx, X, F, F, ptr(self.all_nodes), A_dev, cap_A, ptr(self.cl_in_off[0]),
                            ptr(self.cl_in_src[0]), ptr(self.cl_dinv[0]), None, 0, None, 0, ptr(self.Yc), ldYc, None, None, -1, st)
@@ -548,6 +564,13 @@ class GrapesEngine:
             L.grapes_colsum(ctx_b, ptr(self.dpre1), A_dev, cap_A, D, D, 1.0, 0, self._grd(nc.b1), stB)
         L.grapes_gemm_tn(ctx, ptr(self.dpre1), D, ptr(self.Yc), ldYc, A_dev, cap_A, D, F, 1.0, 0, self._grd(nc.W1),
                          st)
+        if self.embed_nodes:
+            # d loss_c / d x[all_nodes] (main.py:267 with embeddings in optimizer_c): dYc = dpre1 W1, dX = A_hat_1^T dYc
+            L.grapes_gemm(ctx, 1, ptr(self.dpre1), D, self._par(nc.W1), F, ptr(self.dYc), ldYc, A_dev, cap_A, F, D,
+                          None, 0, None, 0, st)
+            L.grapes_aggregate(ctx, ptr(self.dYc), F, ldYc, None, A_dev, cap_A, ptr(self.cl_out_off0),
+                               ptr(self.cl_out_dst0), ptr(self.cl_dinv[0]), None, 0, None, 0, ptr(self.dXc), ldYc,
+                               None, None, -1, st)
         L.tag = ""
         # ---- GFlowNet / REINFORCE loss (main.py:271-291): loss, gradient scale, scaled directions in one launch ----
         join(sB)
@@ -717,6 +740,12 @@ class GrapesEngine:
             n1 = 0
         else:
             n1 = (nz.end - gf.base) if not self.reinforce else gf.size   # gcn_z has no grad under REINFORCE (main.py:279)
+        if self.embed_nodes:
+            if self.peer is not None:
+                raise GrapesError("embed_nodes is single-GPU (SURVEY.md section 8e): the table gradient is not exchanged")
+            L.grapes_adam_embed(ctx, ptr(self.x), ptr(self.emb_exp_avg), ptr(self.emb_exp_avg_sq), self.N, self.F,
+                                ptr(self.bm_all), ptr(self.pref_all), ptr(self.dXc), self.dXc.shape[1], self.lr_gc,
+                                0.9, 0.999, 1e-8, ptr(self.adam_steps), st)
         if self.peer is not None:
             pe = self.peer
             L.grapes_allreduce_adam_peer(ctx, pe.peer_ptrs, pe.rank, pe.world, ptr(self.grads), self.n_par,
@@ -761,6 +790,8 @@ class GrapesEngine:
                 self.set_targets(target_nodes)
         self._pref_key = None
         self._prefetch_next = False
+        if self.embed_nodes:
+            next_targets = None          # the hop-0 front end reads x, which this step's optimiser updates: no prefetch
         if next_targets is not None and not record and gumbel_noise is None:
             self.set_targets(next_targets, state=1 - self.par)
             self._pref_key = (next_targets.data_ptr(), int(next_targets.numel()))
@@ -853,6 +884,8 @@ class GrapesEngine:
         out["logits_c"] = self.logits_c[:A].clone()
         out["scalars"] = self.scalars()
         out["grads"] = {k: {n: t.clone() for n, t in v.items()} for k, v in self.grad_dicts().items()}
+        if self.embed_nodes:
+            out["grad_x_rows"] = self.dXc[:A, :self.F].clone()       # d loss_c / d x[all_nodes]
         out["cl_edges"] = []
         for slot, hop in ((0, H - 1), (1, 0)):
             e = sizes[hop]["blk"]

@@ -21,6 +21,32 @@ def _require_cuda(device) -> torch.device:
     return device
 
 
+def csr_from_edge_index(edge_index: torch.Tensor, num_nodes: int, device) -> "tuple[torch.Tensor, torch.Tensor]":
+    """``edge_index`` int64 [2, E] (host or device) -> (indptr int64 [N+1], indices int32 [nnz]) in HBM: scipy's
+    canonical CSR of main.py:134-136, through the C ABI (``grapes_csr_from_edges``)."""
+    device = _require_cuda(device)
+    N = int(num_nodes)
+    ei = edge_index.to(device=device, dtype=torch.int64)
+    if ei.dim() != 2 or ei.shape[0] != 2:
+        raise ValueError("edge_index must have shape [2, E]")
+    src, dst = ei[0].contiguous(), ei[1].contiguous()
+    E = int(src.numel())
+    L = lib()
+    with torch.cuda.device(device):
+        ws_bytes = int(L.cdll.grapes_csr_workspace_bytes(N, E))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+        indptr = torch.empty(N + 1, dtype=torch.int64, device=device)
+        cap = torch.empty(max(E, 1), dtype=torch.int32, device=device)
+        meta = torch.zeros(2, dtype=torch.int64, device=device)          # [0] nnz, [1] error flag (low int32)
+        L.grapes_csr_from_edges(ptr(src), ptr(dst), E, N, ptr(indptr), ptr(cap), meta.data_ptr(), meta.data_ptr() + 8,
+                                ptr(ws), ws_bytes, torch.cuda.current_stream(device).cuda_stream)
+        nnz, err = (int(v) for v in meta.cpu().tolist())
+    if err & 0xffffffff:
+        raise ValueError("edge_index holds node ids outside [0, num_nodes)")    # scipy: index exceeds matrix dimensions
+    del ws
+    return indptr, (cap if nnz == cap.numel() else cap[:nnz].clone())
+
+
 class DeviceGraph:
     """CSR adjacency + the per-device library context.
 
@@ -84,20 +110,11 @@ class DeviceGraph:
     # ------------------------------------------------------------------ construction
     @classmethod
     def from_edge_index(cls, edge_index: torch.Tensor, num_nodes: int, device="cuda", **kw) -> "DeviceGraph":
-        """main.py:134-136: ``csr_matrix((ones bool, edge_index), (N, N))`` -- duplicates collapse,
-        columns sorted.  Done with sort/unique on the device (one-off, outside the step)."""
+        """main.py:134-136: ``csr_matrix((ones bool, edge_index), (N, N))`` -- duplicates collapse, columns sorted,
+        self-loops kept.  Built on the device by ``grapes_csr_from_edges`` (counting sort by row + per-row sort/unique,
+        csrc/csr_build.cu); one-off, outside the step.  Ids outside [0, N) raise ValueError like scipy."""
         device = _require_cuda(device)
-        ei = edge_index.to(device=device, dtype=torch.int64)
-        key = ei[0] * int(num_nodes) + ei[1]
-        del ei
-        key = torch.unique(key, sorted=True)
-        rows = torch.div(key, int(num_nodes), rounding_mode="floor")
-        indices = (key - rows * int(num_nodes)).to(torch.int32)
-        del key
-        counts = torch.bincount(rows, minlength=int(num_nodes))
-        del rows
-        indptr = torch.zeros(int(num_nodes) + 1, dtype=torch.int64, device=device)
-        torch.cumsum(counts, 0, out=indptr[1:])
+        indptr, indices = csr_from_edge_index(edge_index, num_nodes, device)
         return cls(indptr, indices, num_nodes, **kw)
 
     @classmethod

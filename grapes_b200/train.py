@@ -55,14 +55,22 @@ def train(args: Arguments, data=None, device: Optional[torch.device] = None, use
         if not args.embed_nodes:
             raise ValueError('Dataset does not contain node features, and embed_nodes is False. '
                              'Did you mean to run with --embed_nodes=True?')          # main.py:91-94
-        raise NotImplementedError("embed_nodes (learned node features) is a 'next' row (DESIGN.md section 7)")
+        # main.py:95-100: embeddings = nn.Parameter(FloatTensor(N, node_emb_dim).normal_()), appended to optimizer_c.
+        # Here the table lives in HBM and the engine's optimiser launch updates it in place (grapes_adam_embed).
+        logger.info('Using learned node embeddings for features')
+        gen = torch.Generator().manual_seed(0 if args.seed is None else args.seed)
+        data.x = torch.empty(data.num_nodes, args.node_emb_dim).normal_(generator=gen).to(device)
+        data.num_features = num_features = args.node_emb_dim
     if args.model_type != 'gcn':
         raise ValueError("only model_type='gcn' is wired in the reference's train() (main.py:109)")
     if args.dropout != 0.:
         raise NotImplementedError("dropout > 0 is not used by any reference config; use grapes_b200.gcn.GCN directly")
 
     graph = DeviceGraph.from_edge_index(data.edge_index, data.num_nodes, device=device)
-    engine = GrapesEngine(graph, data.x.to(device).contiguous(), data.y.to(device), num_classes=num_classes,
+    x_dev = data.x.to(device).contiguous()
+    if args.embed_nodes:
+        data.x = x_dev                       # evaluation reads the table the optimiser updates
+    engine = GrapesEngine(graph, x_dev, data.y.to(device), num_classes=num_classes, embed_nodes=args.embed_nodes,
                           batch_size=args.batch_size, num_samples=args.num_samples, sampling_hops=args.sampling_hops,
                           use_indicators=args.use_indicators, hidden_dim=args.hidden_dim, lr_gc=args.lr_gc,
                           lr_gf=args.lr_gf, loss_coef=args.loss_coef, log_z_init=args.log_z_init,

@@ -81,6 +81,18 @@ int grapes_set_pdl(int mask);
 int64_t grapes_kernel_launches(void);
 int grapes_zero(grapes_ctx* ctx, void* ptr, int64_t bytes, void* stream);
 
+/* ---- CSR construction (main.py:134-136: sp.csr_matrix((ones bool, edge_index), shape=(N, N))) ---------------- */
+/* bytes of caller-owned device scratch grapes_csr_from_edges needs for this (N, E)                               */
+int64_t grapes_csr_workspace_bytes(int64_t num_nodes, int64_t num_edges);
+/* edge list (src[e], dst[e]), int64 like the reference's edge_index rows -> scipy's canonical CSR of the bool
+ * matrix: indptr int64 [N+1], indices int32 (capacity E; rows ascending, duplicate edges collapsed, self-loops
+ * kept), *nnz_dev = stored entries.  *err_dev = 1 when an id is outside [0, N) (scipy raises ValueError; such edges
+ * are skipped here and the caller raises).  No ctx: the graph's context is created from the result.  Counting sort by
+ * row + per-row sort/unique in registers / shared memory; enqueued on `stream`, no host synchronisation.           */
+int grapes_csr_from_edges(const int64_t* src, const int64_t* dst, int64_t num_edges, int64_t num_nodes, int64_t* indptr,
+                          int* indices, int64_t* nnz_dev, int* err_dev, void* workspace, int64_t workspace_bytes,
+                          void* stream);
+
 /* ---- frontier expansion / dedup / relabel  (utils.py:74-82, main.py:183-195, utils.py:98-120) */
 /* rows[P] -> row_off[P+1] = exclusive scan of CSR degrees, *m_dev = total.  Sets the bit of every
  * row in bm_rows (prev_nodes_mask, main.py:185) and of rows with degree > 0 in bm_batch.          */
@@ -268,6 +280,14 @@ int grapes_adam_step(grapes_ctx* ctx, float* params, const float* grads, float* 
 int grapes_adam_step2(grapes_ctx* ctx, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                       int off0, int n0, float lr0, int off1, int n1, float lr1, float beta1, float beta2, float eps,
                       float* steps_dev, void* stream);
+/* Learned node features (main.py:89-100,116: embeddings = nn.Parameter [N, node_emb_dim] inside optimizer_c): dense
+ * torch.optim.Adam update of the whole table from a SPARSE gradient -- grad_rows[r, :F] (pitch ldg) is the gradient of
+ * the node whose bit has rank r in bm_rows / pref_rows (the batch's all_nodes bitmap), every other row has gradient 0
+ * (its moments still decay and it still moves, as in the reference).  step_dev = optimizer_c's step count BEFORE this
+ * update; call it before grapes_adam_step2, which increments the count.                                           */
+int grapes_adam_embed(grapes_ctx* ctx, float* table, float* exp_avg, float* exp_avg_sq, int64_t num_nodes, int F,
+                      const uint32_t* bm_rows, const int* pref_rows, const float* grad_rows, int ldg, float lr,
+                      float beta1, float beta2, float eps, const float* step_dev, void* stream);
 int grapes_fill_f32(grapes_ctx* ctx, float* p, float value, int n, void* stream);
 
 /* ---- data-parallel exchange: gradient all-reduce (mean) + both Adam groups over NVLink peer memory ------------ */

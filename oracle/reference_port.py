@@ -249,7 +249,8 @@ class OracleState:
     def __init__(self, data, *, sampling_hops=2, num_samples=16, use_indicators=True,
                  hidden_dim=256, lr_gc=1e-3, lr_gf=1e-4, loss_coef=1e4, log_z_init=0.,
                  reg_param=0., dropout=0., random_sampling=False, reinforce_baseline=False,
-                 seed: int = 0, dtype=torch.float32, adjacency: Optional[sp.csr_matrix] = None):
+                 seed: int = 0, dtype=torch.float32, adjacency: Optional[sp.csr_matrix] = None,
+                 embed_nodes: bool = False):
         self.data = data
         self.hops, self.k = sampling_hops, num_samples
         self.use_indicators = use_indicators
@@ -262,7 +263,15 @@ class OracleState:
         self.gcn_c = OracleGCN(Fdim, [hidden_dim, C], dropout, g).to(dtype)
         self.gcn_gf = OracleGCN(Fdim + self.num_indicators, [hidden_dim, 1], generator=g).to(dtype)
         self.gcn_z = OracleGCN(Fdim, [hidden_dim, 1], generator=g).to(dtype)
-        self.opt_c = torch.optim.Adam(self.gcn_c.parameters(), lr=lr_gc)
+        # main.py:89-100,116: learned node features are an nn.Parameter table inside optimizer_c (the caller passes the
+        # nn.init.normal_ draw as data.x so the oracle and the device engine start from the same table)
+        self.embed_nodes = bool(embed_nodes)
+        self.x = data.x.to(dtype)
+        embedding_params = []
+        if self.embed_nodes:
+            self.x = nn.Parameter(self.x.clone(), requires_grad=True)
+            embedding_params.append(self.x)
+        self.opt_c = torch.optim.Adam(list(self.gcn_c.parameters()) + embedding_params, lr=lr_gc)
         self.opt_gf = torch.optim.Adam(list(self.gcn_gf.parameters()) + list(self.gcn_z.parameters()), lr=lr_gf)
         self.loss_fn = nn.CrossEntropyLoss() if data.y.dim() == 1 else nn.BCEWithLogitsLoss()
         self.adjacency = adjacency if adjacency is not None else build_adjacency(data.edge_index, N)
@@ -270,7 +279,6 @@ class OracleState:
         self.prev_nodes_mask = torch.zeros(N, dtype=torch.bool)
         self.batch_nodes_mask = torch.zeros(N, dtype=torch.bool)
         self.indicator_features = torch.zeros((N, self.num_indicators), dtype=dtype)
-        self.x = data.x.to(dtype)
         self.dtype = dtype
 
 
@@ -351,6 +359,8 @@ def reference_step(st: OracleState, target_nodes: torch.Tensor,
     st.opt_c.zero_grad()
     loss_c.backward()
     grads_c = {n: p.grad.detach().clone() for n, p in st.gcn_c.named_parameters()}
+    if getattr(st, "embed_nodes", False):
+        rec["grad_x"] = st.x.grad.detach().clone()          # dense [N, F]; rows outside all_nodes are zero
     if apply_optim:
         st.opt_c.step()
     rec.update(all_nodes=all_nodes.clone(), edge_indices=[e.clone() for e in edge_indices],

@@ -146,3 +146,29 @@ def test_reference_step_runs_and_is_deterministic_given_noise():
     # trajectory-balance closed form used by the CUDA path: d loss / d logit_i = 2 r (mask_i - p_i)
     r = rec["log_z"] + rec["tot_log_prob"] + st.loss_coef * rec["loss_c"]
     assert torch.allclose(rec["loss_gfn"], r * r, rtol=1e-6)
+
+
+def test_oracle_embed_nodes_table_is_in_optimizer_c():
+    """main.py:89-100,116: the learned table sits in optimizer_c; its gradient after loss_c.backward() is non-zero only on
+    all_nodes rows, and torch's dense Adam keeps moving rows of EARLIER batches (what grapes_adam_embed reproduces)."""
+    from grapes_b200.synth import make_synth, SHAPES
+    cfg = SHAPES["tiny"]
+    d = make_synth("tiny", seed=0)
+    torch.manual_seed(7)
+    st = rp.OracleState(d, sampling_hops=cfg["sampling_hops"], num_samples=cfg["num_samples"], seed=1, embed_nodes=True)
+    assert any(p is st.x for g in st.opt_c.param_groups for p in g["params"])
+    idx = d.train_mask.nonzero().squeeze(1)
+    B = cfg["batch_size"]
+    x0 = st.x.detach().clone()
+    r1 = rp.reference_step(st, idx[:B])
+    outside = torch.ones(d.num_nodes, dtype=torch.bool)
+    outside[r1["all_nodes"]] = False
+    assert float(r1["grad_x"][outside].abs().max()) == 0.0 and float(r1["grad_x"].abs().max()) > 0.0
+    x1 = st.x.detach().clone()
+    assert torch.equal(x1[outside], x0[outside]) and not torch.equal(x1, x0)
+    r2 = rp.reference_step(st, idx[B:2 * B])
+    only_first = torch.zeros(d.num_nodes, dtype=torch.bool)
+    only_first[r1["all_nodes"]] = True
+    only_first[r2["all_nodes"]] = False
+    moved = (st.x.detach()[only_first] != x1[only_first]).any(dim=1)
+    assert only_first.any() and bool(moved.any())                  # zero gradient this step, Adam momentum still moves them
