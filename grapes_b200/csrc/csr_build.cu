@@ -4,7 +4,7 @@
 //
 // HBM-bound integer work, one pass per phase, no global sort: a counting sort by row (degree histogram -> 64-bit scan ->
 // scatter) groups the edges, then every row segment is sorted and deduplicated where it lies -- a warp in registers for
-// rows of <= 32 entries, a CTA in shared memory for rows up to 32768 entries, a CTA in global memory for longer hub rows
+// rows of <= 32 entries, a warp in shared memory up to 256, a CTA in shared memory for rows up to 32768 entries, a CTA in global memory for longer hub rows
 // (all three use the same ascending-only bitonic network, so tails never need padding) -- and a second scan + copy
 // closes the gaps the duplicates left.  The scatter order inside a row depends on atomics, the result does not.
 //
@@ -22,7 +22,8 @@
 #define CB_SCAN_THREADS 1024
 #define CB_SCAN_ITEMS 8
 #define CB_SCAN_TILE (CB_SCAN_THREADS * CB_SCAN_ITEMS)
-#define CB_MED_MAX 2048              // rows of 33 .. 2048 entries: 256-thread CTA, 8 KB of shared memory
+#define CB_WARP_MAX 256              // rows of 33 .. 256 entries: one warp, a 1 KB strip of shared memory
+#define CB_MED_MAX 2048              // rows of 257 .. 2048 entries: 256-thread CTA, 8 KB of shared memory
 #define CB_LONG_SMEM 32768           // rows up to 32768 entries are sorted in shared memory (128 KB), longer ones in HBM
 #define CB_MED_THREADS 256
 #define CB_LONG_THREADS 1024
@@ -121,12 +122,14 @@ __global__ void __launch_bounds__(CB_THREADS) k_csr_scatter(const int64_t* __res
 __global__ void __launch_bounds__(CB_THREADS) k_csr_sort_short(int64_t N, const long long* __restrict__ raw_off,
                                                                 int* __restrict__ tmp, int* __restrict__ ucount,
                                                                 int* __restrict__ worklist, int* __restrict__ wl_count) {
+    __shared__ int s_rows[CB_THREADS / 32][CB_WARP_MAX];
     const int lane = lane_id();
+    int* a = s_rows[threadIdx.x >> 5];
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < N; r += warps) {
         const long long o = raw_off[r];
         const int d = (int)(raw_off[r + 1] - o);
-        if (d > 32) {                                   // medium rows are listed from the front, long rows from the back
+        if (d > CB_WARP_MAX) {                          // medium rows are listed from the front, long rows from the back
             if (lane == 0) {
                 if (d <= CB_MED_MAX) worklist[atomicAdd(&wl_count[0], 1)] = (int)r;
                 else worklist[N - 1 - atomicAdd(&wl_count[1], 1)] = (int)r;
@@ -134,6 +137,42 @@ __global__ void __launch_bounds__(CB_THREADS) k_csr_sort_short(int64_t N, const 
             continue;
         }
         if (d == 0) { if (lane == 0) ucount[r] = 0; continue; }
+        if (d > 32) {
+            // 33 .. CB_WARP_MAX entries: the warp sorts the row in its own shared-memory strip (same ascending-only
+            // network as cb_bitonic, __syncwarp between stages), then writes the unique values back in order
+            for (int i = lane; i < d; i += 32) a[i] = tmp[o + i];
+            __syncwarp();
+            int P = 64;
+            while (P < d) P <<= 1;
+            for (int size = 2; size <= P; size <<= 1) {
+                const int half = size >> 1;
+                for (int p = lane; p < (P >> 1); p += 32) {
+                    const int blk = p / half, off = p - blk * half;
+                    const int i = blk * size + off, j = blk * size + size - 1 - off;
+                    if (j < d) { const int x = a[i], y = a[j]; if (x > y) { a[i] = y; a[j] = x; } }
+                }
+                __syncwarp();
+                for (int st = size >> 2; st > 0; st >>= 1) {
+                    for (int p = lane; p < (P >> 1); p += 32) {
+                        const int i = 2 * st * (p / st) + (p % st), j = i + st;
+                        if (j < d) { const int x = a[i], y = a[j]; if (x > y) { a[i] = y; a[j] = x; } }
+                    }
+                    __syncwarp();
+                }
+            }
+            int base = 0;
+            for (int i0 = 0; i0 < d; i0 += 32) {
+                const int i = i0 + lane;
+                const int v = i < d ? a[i] : 0;
+                const bool keep = i < d && (i == 0 || v != a[i - 1]);
+                const unsigned m = __ballot_sync(GRAPES_FULL_MASK, keep);
+                if (keep) tmp[o + base + __popc(m & ((1u << lane) - 1u))] = v;
+                base += __popc(m);
+            }
+            if (lane == 0) ucount[r] = base;
+            __syncwarp();
+            continue;
+        }
         int v = lane < d ? tmp[o + lane] : 0x7fffffff;
 #pragma unroll
         for (int size = 2; size <= 32; size <<= 1) {
