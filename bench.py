@@ -45,8 +45,10 @@ def parse_args():
 
 
 # --------------------------------------------------------------------------------------------
-def build_workload(name: str, seed: int, device):
-    """SURVEY.md section 8(d) generator, run with torch ops on `device` (one-off, untimed)."""
+def build_workload(name: str, seed: int, device, native_csr: bool = False):
+    """SURVEY.md section 8(d) generator on `device` (one-off, untimed).  native_csr=True (this repo's arm): the CSR is built
+    by grapes_csr_from_edges (csrc/csr_build.cu, the replacement of main.py:134-136) and its event-timed duration is
+    returned in cfg["csr_build"]; False (reference arm, may be a CPU-only process): torch sort/unique, same result."""
     cfg = dict(SHAPES[name])
     N, E_dir, F, C, n_train = cfg["N"], cfg["E_dir"], cfg["F"], cfg["C"], cfg["n_train"]
     g = torch.Generator(device=device).manual_seed(seed)
@@ -55,16 +57,36 @@ def build_workload(name: str, seed: int, device):
     half = E_dir // 2
     src = torch.randint(0, N, (half,), generator=g, device=device, dtype=torch.int64)
     dst = torch.randint(0, N, (half,), generator=g, device=device, dtype=torch.int64)
-    key = torch.cat([src * N + dst, dst * N + src])
-    del src, dst
-    key = torch.unique(key, sorted=True)                 # csr_matrix(bool) collapses duplicates (main.py:134)
-    rows = torch.div(key, N, rounding_mode="floor")
-    indices = (key - rows * N).to(torch.int32)
-    del key
-    counts = torch.bincount(rows, minlength=N)
-    del rows
-    indptr = torch.zeros(N + 1, dtype=torch.int64, device=device)
-    torch.cumsum(counts, 0, out=indptr[1:])
+    if native_csr:
+        from grapes_b200.graph import csr_from_edge_index
+        ei = torch.stack([torch.cat([src, dst]), torch.cat([dst, src])])
+        del src, dst
+        csr_from_edge_index(ei[:, :1024], N, device)            # load the library, warm the allocator
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        indptr, indices = csr_from_edge_index(ei, N, device)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        E, nnz = int(ei.shape[1]), int(indices.numel())
+        alg = 16 * E + 4 * E + 16 * E + 4 * E + 8 * E + 2 * 12 * N + 8 * nnz      # phases listed in csrc/csr_build.cu
+        cfg["csr_build"] = {"entry": "grapes_csr_from_edges", "edges_in": E, "nnz": nnz, "ms": ms,
+                            "algorithmic_GBps": alg / ms / 1e6,
+                            "note": "one-off (main.py:134-136; scipy on the host in the reference), includes workspace "
+                                    "allocation and the nnz read-back; random-scatter bound"}
+        del ei
+    else:
+        key = torch.cat([src * N + dst, dst * N + src])
+        del src, dst
+        key = torch.unique(key, sorted=True)                 # csr_matrix(bool) collapses duplicates (main.py:134)
+        rows = torch.div(key, N, rounding_mode="floor")
+        indices = (key - rows * N).to(torch.int32)
+        del key
+        counts = torch.bincount(rows, minlength=N)
+        del rows
+        indptr = torch.zeros(N + 1, dtype=torch.int64, device=device)
+        torch.cumsum(counts, 0, out=indptr[1:])
     x = torch.randn(N, F, generator=g, device=device, dtype=torch.float32)
     y = torch.randint(0, C, (N,), generator=g, device=device, dtype=torch.int64)
     train_idx = torch.sort(torch.randperm(N, generator=g, device=device)[:n_train]).values
@@ -280,7 +302,8 @@ def main():
     from grapes_b200.engine import GrapesEngine
     from grapes_b200.graph import DeviceGraph
 
-    cfg, indptr, indices, x, y, train_idx = build_workload(cfgname, args.seed, dev)
+    cfg, indptr, indices, x, y, train_idx = build_workload(cfgname, args.seed, dev, native_csr=True)
+    csr_build = cfg.pop("csr_build", None)
     N, F, C, B = cfg["N"], cfg["F"], cfg["C"], cfg["batch_size"]
     graph = DeviceGraph(indptr, indices, N)
     eng = GrapesEngine(graph, x, y, num_classes=C, batch_size=B, num_samples=cfg["num_samples"],
@@ -503,7 +526,7 @@ def main():
                 "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(cfgname, cfg, world),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": int(per_step),
-                "roofline": roof, "rooflines": rooflines, "spmm": spmm, "cpu_baseline": cpu, "breakdown_ms_per_step": breakdown,
+                "roofline": roof, "rooflines": rooflines, "spmm": spmm, "csr_build": csr_build, "cpu_baseline": cpu, "breakdown_ms_per_step": breakdown,
                 "frontier": per_hop, "cuda_graph": use_graph, "cross_step_prefetch": prefetch,
                 "gradient_exchange": ("peer-memory all-reduce + Adam in the step graph" if peer else ("nccl all_reduce + adam launch" if world > 1 else "none"))}
         emit(line)

@@ -29,7 +29,7 @@ def _setup(name, seed, dev, use_tensor_cores=False, **kw):
     from grapes_b200.synth import SHAPES
     cfg = dict(SHAPES[name])
     torch.manual_seed(1000 + seed)     # the oracle draws its Gumbel noise from the global CPU generator
-    d = make_synth(name, seed=seed, multilabel=kw.pop("multilabel", False))
+    d = make_synth(name, seed=seed, multilabel=kw.pop("multilabel", False), power_law=kw.pop("power_law", 0.0))
     feature_bf16 = kw.pop("feature_bf16", False)
     if feature_bf16:                     # the table is STORED in bf16; the oracle computes on exactly those values
         d.x = d.x.bfloat16().float()
@@ -134,6 +134,16 @@ def _check_step(st, eng, targets, dev, apply_optim=True, relaxed=False, post_opt
 def test_step_parity_trajectory_balance(cuda_device, name, seed):
     d, st, eng, train_idx, B = _setup(name, seed, cuda_device)
     _check_step(st, eng, train_idx[:B], cuda_device, apply_optim=False)
+
+
+@pytest.mark.parametrize("use_tc", [False, True])
+def test_step_parity_power_law_hub_rows(cuda_device, use_tc):
+    """SURVEY.md section 8(d) stress variant: Zipf-like endpoints -> a few hub rows with thousands of entries next to
+    isolated nodes (hub worklist of the per-row sort, long rows in the expansion, skewed in-degrees in gcn_norm)."""
+    d, st, eng, train_idx, B = _setup("small", 5, cuda_device, use_tensor_cores=use_tc, power_law=1.5)
+    deg = torch.bincount(d.edge_index[0], minlength=d.num_nodes)
+    assert int(deg.max()) > 1000 and int((deg == 0).sum()) > 0
+    _check_step(st, eng, train_idx[:B], cuda_device, apply_optim=False, relaxed=use_tc)
 
 
 @pytest.mark.parametrize("name,seed", [("tiny", 0), ("small", 1), ("small", 2), ("cora", 0)])
