@@ -70,11 +70,11 @@ def build_workload(name: str, seed: int, device, native_csr: bool = False):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         E, nnz = int(ei.shape[1]), int(indices.numel())
-        alg = 16 * E + 4 * E + 16 * E + 4 * E + 8 * E + 2 * 12 * N + 8 * nnz      # phases listed in csrc/csr_build.cu
+        alg = 16 * E + 4 * E + 16 * E + 8 * E + 8 * E + 4 * E + 8 * E + 2 * 12 * N + 8 * nnz   # phases listed in csrc/csr_build.cu
         cfg["csr_build"] = {"entry": "grapes_csr_from_edges", "edges_in": E, "nnz": nnz, "ms": ms,
                             "algorithmic_GBps": alg / ms / 1e6,
                             "note": "one-off (main.py:134-136; scipy on the host in the reference), includes workspace "
-                                    "allocation and the nnz read-back; random-scatter bound"}
+                                    "allocation and the nnz read-back"}
         del ei
     else:
         key = torch.cat([src * N + dst, dst * N + src])

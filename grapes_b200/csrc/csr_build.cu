@@ -4,14 +4,16 @@
 //
 // HBM-bound integer work, one pass per phase, no global sort: a counting sort by row (degree histogram -> 64-bit scan ->
 // scatter) groups the edges, then every row segment is sorted and deduplicated where it lies -- a warp in registers for
-// rows of <= 32 entries, a warp in shared memory up to 256, a CTA in shared memory for rows up to 32768 entries, a CTA in global memory for longer hub rows
-// (all three use the same ascending-only bitonic network, so tails never need padding) -- and a second scan + copy
+// rows of <= 128 entries (1, 2 or 4 per lane), a warp in shared memory up to 256, a CTA in shared memory up to 32768,
+// a CTA in global memory for longer hub rows (all use the same ascending-only bitonic network, so tails never need
+// padding) -- and a second scan + copy
 // closes the gaps the duplicates left.  The scatter order inside a row depends on atomics, the result does not.
 //
 // Phases (E = edges in, N = nodes):                                algorithmic bytes
 //   k_csr_degree     histogram of src                              16 E read (+ 4 E atomic)
 //   scan64           deg -> raw_off                                 4 N read, 8 N write
-//   k_csr_scatter    tmp[raw_off[src] + cursor++] = dst             16 E read, 4 E write
+//   k_csr_partition  (row, col) pairs grouped by row bucket         16 E read, 8 E write
+//   k_csr_scatter_part  tmp[raw_off[row] + cursor++] = col, bucket by bucket (L2-sized windows)   8 E read, 4 E write
 //   k_csr_sort_*     sort + unique per row, in place                4 E read, <= 4 E write
 //   scan64           ucount -> indptr                               4 N read, 8 N write
 //   k_csr_compact    indices[indptr[r] ..] = tmp[raw_off[r] ..]     4 nnz read + write
@@ -22,8 +24,8 @@
 #define CB_SCAN_THREADS 1024
 #define CB_SCAN_ITEMS 8
 #define CB_SCAN_TILE (CB_SCAN_THREADS * CB_SCAN_ITEMS)
-#define CB_WARP_MAX 256              // rows of 33 .. 256 entries: one warp, a 1 KB strip of shared memory
-#define CB_MED_MAX 2048              // rows of 257 .. 2048 entries: 256-thread CTA, 8 KB of shared memory
+#define CB_WARP_MAX 1024             // rows of 129 .. 1024 entries: one warp, a 4 KB strip of shared memory
+#define CB_MED_MAX 2048              // rows of 1025 .. 2048 entries: 256-thread CTA, 8 KB of shared memory
 #define CB_LONG_SMEM 32768           // rows up to 32768 entries are sorted in shared memory (128 KB), longer ones in HBM
 #define CB_MED_THREADS 256
 #define CB_LONG_THREADS 1024
@@ -116,9 +118,148 @@ __global__ void __launch_bounds__(CB_THREADS) k_csr_scatter(const int64_t* __res
     }
 }
 
+// The direct scatter above writes 4 bytes at a random place of a table far larger than L2: every store costs a 32-byte
+// sector read + write in DRAM (ncu, products-shape: 6.8 GB read + 3.7 GB written for 2.5 GB of algorithmic traffic).
+// Two passes with locality instead: (A) a tile of edges is split by row BUCKET (<= 1024 buckets of 2^shift rows) with a
+// shared-memory histogram, each (tile, bucket) run is reserved with one global atomic and written as 8-byte (row, col)
+// pairs next to each other -- whole sectors; (B) the CTAs walk the buckets in order, a group of CTAs per bucket, so the
+// random 4-byte stores of a bucket fall into a window of a few MB that L2 holds until its sectors are complete.
+#define CB_PART_THREADS 512
+#define CB_PART_ITEMS 8
+#define CB_PART_TILE (CB_PART_THREADS * CB_PART_ITEMS)
+#define CB_PART_MAXB 1024
+
+__global__ void __launch_bounds__(CB_PART_THREADS, 2) k_csr_partition(
+    const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t E, int64_t N,
+    const long long* __restrict__ raw_off, int shift, int B, unsigned long long* __restrict__ bucket_fill,
+    unsigned long long* __restrict__ pairs) {
+    __shared__ int hist[CB_PART_MAXB];
+    __shared__ long long base[CB_PART_MAXB];
+    const int64_t tiles = (E + CB_PART_TILE - 1) / CB_PART_TILE;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int t = threadIdx.x; t < B; t += CB_PART_THREADS) hist[t] = 0;
+        __syncthreads();
+        int rr[CB_PART_ITEMS], cc[CB_PART_ITEMS], rk[CB_PART_ITEMS];
+        int64_t r64[CB_PART_ITEMS], c64[CB_PART_ITEMS];
+#pragma unroll
+        for (int i = 0; i < CB_PART_ITEMS; ++i) {                   // every load of the tile in flight before the first use
+            const int64_t e = tile * CB_PART_TILE + (int64_t)i * CB_PART_THREADS + threadIdx.x;
+            r64[i] = e < E ? src[e] : -1;
+            c64[i] = e < E ? dst[e] : -1;
+        }
+#pragma unroll
+        for (int i = 0; i < CB_PART_ITEMS; ++i) {
+            const int64_t r = r64[i], c = c64[i];
+            rr[i] = -1;
+            if (r >= 0 && r < N && c >= 0 && c < N) {
+                rr[i] = (int)r; cc[i] = (int)c;
+                rk[i] = atomicAdd(&hist[(int)(r >> shift)], 1);
+            }
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < B; t += CB_PART_THREADS) {
+            const int n = hist[t];
+            if (n > 0) {
+                const int64_t first = (int64_t)t << shift;
+                base[t] = raw_off[first] + (long long)atomicAdd(&bucket_fill[t], (unsigned long long)n);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < CB_PART_ITEMS; ++i)
+            if (rr[i] >= 0)
+                pairs[base[rr[i] >> shift] + rk[i]] = ((unsigned long long)(unsigned)rr[i] << 32) | (unsigned)cc[i];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(CB_THREADS) k_csr_scatter_part(const unsigned long long* __restrict__ pairs,
+                                                                  const long long* __restrict__ raw_off, int64_t N,
+                                                                  int shift, int G, int* __restrict__ cursor,
+                                                                  int* __restrict__ tmp) {
+    const int b = blockIdx.x / G, g = blockIdx.x - b * G;
+    const int64_t r0 = (int64_t)b << shift, r1 = min(N, ((int64_t)b + 1) << shift);
+    const long long lo = raw_off[r0], hi = raw_off[r1];
+    const long long per = (hi - lo + G - 1) / G;
+    const long long s = lo + (long long)g * per, e = min(hi, s + per);
+    for (long long p = s + threadIdx.x; p < e; p += CB_THREADS) {
+        const unsigned long long pr = pairs[p];
+        const int r = (int)(pr >> 32);
+        const int k = atomicAdd(&cursor[r], 1);
+        tmp[raw_off[r] + k] = (int)(unsigned)pr;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // per-row sort + unique.  Short rows: one warp per row, the row in one register per lane.
 // ---------------------------------------------------------------------------------------------------------------------
+// Sort + unique of a row of d <= 32 K entries held K per lane (entry i in register i / 32 of lane i % 32): the ascending-only
+// bitonic network with shuffles for strides < 32 and register-to-register exchanges above; +inf pads the tail.
+template <int K>
+__device__ __forceinline__ int cb_warp_sort_unique(int* __restrict__ row, int d, int lane) {
+    int v[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) v[j] = (j * 32 + lane < d) ? row[j * 32 + lane] : 0x7fffffff;
+#pragma unroll
+    for (int size = 2; size <= 32 * K; size <<= 1) {
+        if (size <= 32) {                                   // flip step inside a register: partner = lane ^ (size - 1)
+            const bool lower = (lane & (size - 1)) < (size >> 1);
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const int p = __shfl_xor_sync(GRAPES_FULL_MASK, v[j], size - 1);
+                v[j] = lower ? min(v[j], p) : max(v[j], p);
+            }
+        } else {                                            // flip step across registers: (a, lane) <-> (c, lane ^ 31)
+            const int S = size >> 5;
+#pragma unroll
+            for (int b0 = 0; b0 < K; b0 += S) {
+#pragma unroll
+                for (int j = 0; j < S / 2; ++j) {
+                    const int a = b0 + j, c = b0 + S - 1 - j;
+                    const int pa = __shfl_xor_sync(GRAPES_FULL_MASK, v[c], 31);
+                    const int pc = __shfl_xor_sync(GRAPES_FULL_MASK, v[a], 31);
+                    v[a] = min(v[a], pa);
+                    v[c] = max(v[c], pc);
+                }
+            }
+        }
+#pragma unroll
+        for (int st = size >> 2; st > 0; st >>= 1) {
+            if (st >= 32) {
+                const int sj = st >> 5;
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    if (!(j & sj)) {
+                        const int lo = min(v[j], v[j + sj]), hi = max(v[j], v[j + sj]);
+                        v[j] = lo; v[j + sj] = hi;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    const int p = __shfl_xor_sync(GRAPES_FULL_MASK, v[j], st);
+                    v[j] = (lane & st) ? max(v[j], p) : min(v[j], p);
+                }
+            }
+        }
+    }
+    int base = 0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        int prev = __shfl_up_sync(GRAPES_FULL_MASK, v[j], 1);
+        if (j > 0) {
+            const int last = __shfl_sync(GRAPES_FULL_MASK, v[j - 1], 31);
+            if (lane == 0) prev = last;
+        }
+        const int i = j * 32 + lane;
+        const bool keep = i < d && (i == 0 || v[j] != prev);
+        const unsigned m = __ballot_sync(GRAPES_FULL_MASK, keep);
+        if (keep) row[base + __popc(m & ((1u << lane) - 1u))] = v[j];
+        base += __popc(m);
+    }
+    return base;
+}
+
 __global__ void __launch_bounds__(CB_THREADS) k_csr_sort_short(int64_t N, const long long* __restrict__ raw_off,
                                                                 int* __restrict__ tmp, int* __restrict__ ucount,
                                                                 int* __restrict__ worklist, int* __restrict__ wl_count) {
@@ -137,8 +278,8 @@ __global__ void __launch_bounds__(CB_THREADS) k_csr_sort_short(int64_t N, const 
             continue;
         }
         if (d == 0) { if (lane == 0) ucount[r] = 0; continue; }
-        if (d > 32) {
-            // 33 .. CB_WARP_MAX entries: the warp sorts the row in its own shared-memory strip (same ascending-only
+        if (d > 128) {
+            // 129 .. CB_WARP_MAX entries: the warp sorts the row in its own shared-memory strip (same ascending-only
             // network as cb_bitonic, __syncwarp between stages), then writes the unique values back in order
             for (int i = lane; i < d; i += 32) a[i] = tmp[o + i];
             __syncwarp();
@@ -173,25 +314,11 @@ __global__ void __launch_bounds__(CB_THREADS) k_csr_sort_short(int64_t N, const 
             __syncwarp();
             continue;
         }
-        int v = lane < d ? tmp[o + lane] : 0x7fffffff;
-#pragma unroll
-        for (int size = 2; size <= 32; size <<= 1) {
-            {   // flip step: partner = lane ^ (size - 1)
-                const int p = __shfl_xor_sync(GRAPES_FULL_MASK, v, size - 1);
-                const bool lower = (lane & (size - 1)) < (size >> 1);
-                v = lower ? min(v, p) : max(v, p);
-            }
-#pragma unroll
-            for (int st = size >> 2; st > 0; st >>= 1) {
-                const int p = __shfl_xor_sync(GRAPES_FULL_MASK, v, st);
-                v = (lane & st) ? max(v, p) : min(v, p);
-            }
-        }
-        const int prev = __shfl_up_sync(GRAPES_FULL_MASK, v, 1);
-        const bool keep = lane < d && (lane == 0 || v != prev);
-        const unsigned m = __ballot_sync(GRAPES_FULL_MASK, keep);
-        if (keep) tmp[o + __popc(m & ((1u << lane) - 1u))] = v;
-        if (lane == 0) ucount[r] = __popc(m);
+        int u;
+        if (d <= 32) u = cb_warp_sort_unique<1>(tmp + o, d, lane);
+        else if (d <= 64) u = cb_warp_sort_unique<2>(tmp + o, d, lane);
+        else u = cb_warp_sort_unique<4>(tmp + o, d, lane);
+        if (lane == 0) ucount[r] = u;
     }
 }
 
@@ -285,10 +412,12 @@ __global__ void __launch_bounds__(CB_THREADS) k_csr_compact(int64_t N, const lon
     }
 }
 
+int g_csr_direct_scatter = 0;      // 0 = by shape, 1 = single-pass random scatter, 2 = partition + windowed scatter (A/B)
+
 static inline size_t cb_align(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct CbLayout {
-    size_t deg, ucount, raw_off, tile_sum, worklist, flags, tmp, total;
+    size_t deg, ucount, raw_off, tile_sum, worklist, flags, bucket_fill, tmp, pairs, total;
 };
 static CbLayout cb_layout(int64_t N, int64_t E) {
     CbLayout L;
@@ -300,12 +429,16 @@ static CbLayout cb_layout(int64_t N, int64_t E) {
     L.tile_sum = o; o += cb_align(sizeof(long long) * tiles);
     L.worklist = o; o += cb_align(sizeof(int) * (size_t)N);
     L.flags = o; o += cb_align(sizeof(int) * 4);
+    L.bucket_fill = o; o += cb_align(sizeof(unsigned long long) * CB_PART_MAXB);
     L.tmp = o; o += cb_align(sizeof(int) * (size_t)(E > 0 ? E : 1));
+    L.pairs = o; o += cb_align(sizeof(unsigned long long) * (size_t)(E > 0 ? E : 1));
     L.total = o;
     return L;
 }
 
 extern "C" {
+
+int grapes_csr_set_direct_scatter(int mode) { g_csr_direct_scatter = (mode == 1 || mode == 2) ? mode : 0; return GRAPES_OK; }
 
 int64_t grapes_csr_workspace_bytes(int64_t num_nodes, int64_t num_edges) {
     if (num_nodes <= 0 || num_edges < 0) return 0;
@@ -348,9 +481,32 @@ int grapes_csr_from_edges(const int64_t* src, const int64_t* dst, int64_t num_ed
     }
     cb_scan64(deg, N, tile_sum, raw_off, nullptr, s);
     GRAPES_CUDA_OK(cudaMemsetAsync(deg, 0, sizeof(int) * (size_t)N, s));          // deg becomes the scatter cursor
-    if (E > 0) {
+    // short rows scattered over a table larger than L2 pay a DRAM read-modify-write per store: partition first.  Long rows
+    // (Reddit-shape, ~500 entries) and tables that fit L2 do better with the single pass (measured).
+    const bool direct = g_csr_direct_scatter == 1 || (g_csr_direct_scatter == 0 && (E < (8ll << 20) || E / N >= 128));
+    if (E > 0 && direct) {
         pdl(k_csr_scatter, edge_grid, CB_THREADS, 0, s)(src, dst, E, N, raw_off, deg, tmp);
         grapes_count_launches(1);
+    } else if (E > 0) {
+        unsigned long long* bucket_fill = (unsigned long long*)(ws + L.bucket_fill);
+        unsigned long long* pairs = (unsigned long long*)(ws + L.pairs);
+        const int max_b = E <= (1ll << 28) ? 256 : CB_PART_MAXB;
+        int shift = 0;
+        while (((N + (1ll << shift) - 1) >> shift) > max_b) ++shift;
+        const int B = (int)((N + (1ll << shift) - 1) >> shift);
+        // CTAs per bucket: as many buckets in flight as keep their windows of `tmp` (4 E / B bytes each) inside 32 MB of L2
+        const double window = 4.0 * (double)E / B;
+        long long conc = (long long)(32.0 * 1024 * 1024 / (window > 1.0 ? window : 1.0));
+        if (conc < 1) conc = 1;
+        long long G = ((long long)sms * 8 + conc - 1) / conc;
+        if (G < 1) G = 1;
+        if (G > 4096) G = 4096;
+        GRAPES_CUDA_OK(cudaMemsetAsync(bucket_fill, 0, sizeof(unsigned long long) * CB_PART_MAXB, s));
+        const int64_t tiles = (E + CB_PART_TILE - 1) / CB_PART_TILE;
+        const int part_grid = (int)(tiles < (int64_t)sms * 4 ? tiles : (int64_t)sms * 4);
+        pdl(k_csr_partition, part_grid, CB_PART_THREADS, 0, s)(src, dst, E, N, raw_off, shift, B, bucket_fill, pairs);
+        pdl(k_csr_scatter_part, (int)(B * G), CB_THREADS, 0, s)(pairs, raw_off, N, shift, (int)G, deg, tmp);
+        grapes_count_launches(2);
     }
     pdl(k_csr_sort_short, row_grid, CB_THREADS, 0, s)(N, raw_off, tmp, ucount, worklist, flags);
     {

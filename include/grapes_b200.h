@@ -89,6 +89,9 @@ int64_t grapes_csr_workspace_bytes(int64_t num_nodes, int64_t num_edges);
  * kept), *nnz_dev = stored entries.  *err_dev = 1 when an id is outside [0, N) (scipy raises ValueError; such edges
  * are skipped here and the caller raises).  No ctx: the graph's context is created from the result.  Counting sort by
  * row + per-row sort/unique in registers / shared memory; enqueued on `stream`, no host synchronisation.           */
+/* how the edges are grouped by row: 0 (default) = chosen by shape, 1 = ONE random scatter (4x the algorithmic DRAM
+ * traffic when short rows spread over a table larger than L2), 2 = bucket partition + L2-windowed scatter            */
+int grapes_csr_set_direct_scatter(int mode);
 int grapes_csr_from_edges(const int64_t* src, const int64_t* dst, int64_t num_edges, int64_t num_nodes, int64_t* indptr,
                           int* indices, int64_t* nnz_dev, int* err_dev, void* workspace, int64_t workspace_bytes,
                           void* stream);

@@ -36,7 +36,7 @@ def test_empty_and_isolated(cuda_device):
     _check(torch.tensor([[0, 8, 8, 0], [8, 0, 0, 8]]), 9, cuda_device)
 
 
-@pytest.mark.parametrize("hub_deg", [33, 64, 65, 256, 257, 2048, 2049, 32768, 40000])
+@pytest.mark.parametrize("hub_deg", [33, 64, 65, 128, 129, 256, 257, 512, 513, 1024, 1025, 2048, 2049, 32768, 40000])
 def test_hub_rows_every_sort_tier(cuda_device, hub_deg):
     """row 5 gets `hub_deg` entries before dedup (shuffled, with repeats): 33..256 -> warp shared-memory tier, 257..2048 -> medium CTA tier,
     2049..32768 -> shared-memory long tier, beyond -> in-HBM bitonic."""
