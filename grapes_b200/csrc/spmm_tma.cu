@@ -63,7 +63,15 @@ struct AtB { int g; float dsl, dj; uint32_t sb; int rk; };        // node id, de
 // metadata, one LDS.128 of the row per 128 columns, 4 FFMA, one branch.
 // XB16: the feature table holds bf16 (papers100M-shaped config: 128 bf16 features); rows are staged as stored (2F bytes)
 // and widened to fp32 when they are read from shared memory; all arithmetic and the output stay fp32.
-template <int NPASS, bool HAS_IND, int OUTMODE, bool XB16>
+// VS ("virtual columns in the slot", fp32 tables): the columns [F, ldo) -- indicators | ones | zero pad -- are handled by the
+// SAME float4 lanes as the feature columns instead of one scalar lane each: the copy stage writes the entry's indicator
+// floats right behind its TMA-staged row, so the lane that owns columns F .. F+3 accumulates them with the ordinary
+// LDS.128 + 4 FFMA (same order, same values as the scalar form -> bitwise identical), and the row is written with float4
+// stores only.  Per output row this removes the shift/and/convert/fma chain of every entry and the scalar
+// convert + 2 stores per virtual column (15 % of the kernel's instructions at frontier size, ncu source view).  Measured
+// on B200: 2 us SLOWER per frontier-sized launch than the scalar form (the kernel waits on fixed-latency dependencies at
+// 23 % occupancy, it is not short of issue slots), so the launcher only uses it on request (grapes_agg_tma_virtual_slot).
+template <int NPASS, bool HAS_IND, int OUTMODE, bool XB16, bool VS>
 __global__ void __launch_bounds__(AT_THREADS) k_agg_tma(
     const void* __restrict__ X, int F, int ldx, const int* __restrict__ nodes, const int* __restrict__ n_dev, int cap_n,
     const int* __restrict__ in_off, const int* __restrict__ in_src, const float* __restrict__ dinv,
@@ -75,7 +83,9 @@ __global__ void __launch_bounds__(AT_THREADS) k_agg_tma(
     const int warp = threadIdx.x >> 5;
     const int n = min(*n_dev, cap_n);
     const uint32_t rowbytes = (uint32_t)F * (XB16 ? 2u : 4u);
-    const uint32_t slot_bytes = (uint32_t)ec * rowbytes;
+    const int ni4 = (VS && HAS_IND) ? (num_ind + 3) >> 2 : 0;      // float4 groups of indicator columns behind each staged row
+    const uint32_t rowstride = rowbytes + 16u * (uint32_t)ni4;
+    const uint32_t slot_bytes = (uint32_t)ec * rowstride;
     unsigned char* wslots = at_smem + (size_t)warp * 2u * slot_bytes;
     unsigned char* tail = at_smem + (size_t)AT_WARPS * 2u * slot_bytes;
     int4* s_meta = reinterpret_cast<int4*>(tail) + warp * 64;                         // [2 slots][32 entries]
@@ -88,9 +98,13 @@ __global__ void __launch_bounds__(AT_THREADS) k_agg_tma(
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
     uint32_t ph = 0;                                              // phase parity of the two barriers (bits 0, 1)
-    bool act[NPASS];
+    bool act[NPASS];                                              // this lane accumulates columns p*128 + 4*lane .. +3
+    bool acto[NPASS];                                             // ... and stores them
 #pragma unroll
-    for (int p = 0; p < NPASS; ++p) act[p] = p * 128 + lane * 4 < F;
+    for (int p = 0; p < NPASS; ++p) {
+        act[p] = p * 128 + lane * 4 < F + 4 * ni4;
+        acto[p] = p * 128 + lane * 4 < (VS ? ldo : F);
+    }
     const int cv = F + lane;                                      // this lane's virtual column
     const float vconst = (cv == ones_col) ? 1.f : 0.f;
 
@@ -142,9 +156,15 @@ __global__ void __launch_bounds__(AT_THREADS) k_agg_tma(
                 const uint32_t bar = (c & 1) ? bar1 : bar0;
                 if (lane == 0) at_mbar_expect_tx(bar, (uint32_t)cnt * rowbytes);
                 s_meta[(c & 1) * 32 + lane] = make_int4(__float_as_int(b.dsl * b.dj), b.rk, (int)b.sb, 0);  // self: dj * dj
+                if (VS && HAS_IND && (b.rk & AT_VALID)) {           // indicator floats of the entry's source behind its row
+                    float4* ip = reinterpret_cast<float4*>(wslots + (size_t)(c & 1) * slot_bytes + (size_t)lane * rowstride + rowbytes);
+                    for (int q = 0; q < ni4; ++q)
+                        ip[q] = make_float4((float)((b.sb >> (4 * q)) & 1u), (float)((b.sb >> (4 * q + 1)) & 1u),
+                                            (float)((b.sb >> (4 * q + 2)) & 1u), (float)((b.sb >> (4 * q + 3)) & 1u));
+                }
                 __syncwarp();
                 if (b.rk & AT_VALID)
-                    at_bulk_row(slot0 + (uint32_t)(c & 1) * slot_bytes + (uint32_t)lane * rowbytes,
+                    at_bulk_row(slot0 + (uint32_t)(c & 1) * slot_bytes + (uint32_t)lane * rowstride,
                                 reinterpret_cast<const unsigned char*>(X) + (size_t)b.g * ldx * (XB16 ? 2u : 4u), rowbytes, bar);
             }
         };
@@ -177,7 +197,7 @@ __global__ void __launch_bounds__(AT_THREADS) k_agg_tma(
             // lane l owns columns 4l .. 4l+3 of every 128-column pass: a float4 (fp32 table) or a uint2 (bf16 table)
             const unsigned char* rp = wslots + (size_t)(c & 1) * slot_bytes + (size_t)lane * (XB16 ? 8u : 16u);
             const int4* mp = s_meta + (c & 1) * 32;
-            for (int t = 0; t < cnt; ++t, rp += rowbytes) {
+            for (int t = 0; t < cnt; ++t, rp += rowstride) {
                 const int4 m = mp[t];                                      // broadcast: weight | row + flags | indicator bits
                 const float wt = __int_as_float(m.x);
 #pragma unroll
@@ -195,16 +215,21 @@ __global__ void __launch_bounds__(AT_THREADS) k_agg_tma(
                         acc[p].z = fmaf(wt, v.z, acc[p].z); acc[p].w = fmaf(wt, v.w, acc[p].w);
                     }
                 }
-                if (HAS_IND) aind = fmaf(wt, (float)(((uint32_t)m.z >> lane) & 1u), aind);
+                if (HAS_IND && !VS) aind = fmaf(wt, (float)(((uint32_t)m.z >> lane) & 1u), aind);
                 if (m.y & AT_LAST) {                               // warp-uniform: the row is complete
                     const size_t orow = (size_t)(j0 + (m.y & 0x1ff)) * ldo;
 #pragma unroll
                     for (int p = 0; p < NPASS; ++p) {
-                        if (act[p]) {
+                        if (acto[p]) {
                             const int c0 = p * 128 + lane * 4;
-                            float4 a = acc[p];
-                            if (bias) { a.x += bias[c0]; a.y += bias[c0 + 1]; a.z += bias[c0 + 2]; a.w += bias[c0 + 3]; }
-                            if (relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+                            float4 a = act[p] ? acc[p] : make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (!VS || c0 < F) {
+                                if (bias) { a.x += bias[c0]; a.y += bias[c0 + 1]; a.z += bias[c0 + 2]; a.w += bias[c0 + 3]; }
+                                if (relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+                            } else {                               // virtual lane: indicators (accumulated) | ones | zero pad
+                                const int oc = ones_col - c0;
+                                if (oc == 0) a.x = 1.f; else if (oc == 1) a.y = 1.f; else if (oc == 2) a.z = 1.f; else if (oc == 3) a.w = 1.f;
+                            }
                             if (OUTMODE & 1) *reinterpret_cast<float4*>(out + orow + c0) = a;
                             if (OUTMODE & 2) {                     // 3xTF32 operand split for the tcgen05 GEMM
                                 float4 h, l;
@@ -217,7 +242,7 @@ __global__ void __launch_bounds__(AT_THREADS) k_agg_tma(
                         }
                         acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);    // next row starts from fma(w_self, x, 0)
                     }
-                    if (cv < ldo) {                                // virtual columns: indicators | ones | zero pad
+                    if (!VS && cv < ldo) {                         // virtual columns, one scalar lane each
                         const float v = (HAS_IND && lane < num_ind) ? aind : vconst;
                         if (OUTMODE & 1) out[orow + cv] = v;
                         if (OUTMODE & 2) { const float h = at_tf32(v); out_hi[orow + cv] = h; out_lo[orow + cv] = at_tf32(v - h); }
@@ -232,8 +257,12 @@ __global__ void __launch_bounds__(AT_THREADS) k_agg_tma(
     }
 }
 
-size_t grapes_agg_tma_smem(int F, int ec, int es = 4) {
-    return (size_t)AT_WARPS * 2u * (size_t)ec * (size_t)F * (size_t)es + (size_t)AT_WARPS * 64u * 16u +
+int g_agg_tma_vs = 0;          // grapes_agg_tma_virtual_slot(1): pad columns through the float4 lanes -- bit-identical, fewer
+                               // instructions, and measured ~2 us SLOWER per frontier-sized launch on B200 -> opt-in
+extern "C" int grapes_agg_tma_virtual_slot(int on) { g_agg_tma_vs = on ? 1 : 0; return 0; }
+
+size_t grapes_agg_tma_smem(int F, int ec, int es = 4, int extra = 0) {
+    return (size_t)AT_WARPS * 2u * (size_t)ec * ((size_t)F * (size_t)es + (size_t)extra) + (size_t)AT_WARPS * 64u * 16u +
            (size_t)AT_WARPS * AT_POS_STRIDE * 4u + AT_WARPS * 16u;
 }
 
@@ -245,29 +274,39 @@ int grapes_launch_agg_tma(grapes_ctx* ctx, const void* X, int x_bf16, int F, int
     if (F % 4 != 0 || ldx % 4 != 0 || ldo % 4 != 0 || ldo - F > 32 || F > 128 * 12 || F < 4) return 1;
     if (x_bf16 && (F % 8 != 0 || ldx % 8 != 0 || F > 256)) return 1;         // 16-byte rows; bf16 forms built for F <= 256
     const int es = x_bf16 ? 2 : 4;
-    const size_t budget = (ctas_per_sm >= 2 ? 113u : 226u) * 1024u;
+    const int cps = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 6 ? 6 : ctas_per_sm);       // resident CTAs per SM the shape is sized for
+    const size_t budget = cps == 1 ? 226u * 1024u : (cps == 2 ? 113u * 1024u : (size_t)(227u * 1024u / cps - 1024u));
+    const int npass = (F + 127) / 128;
+    const bool has_ind = ind_bits != nullptr && num_ind > 0;
+    // virtual columns through the float4 lanes (VS): fp32 table, pad columns present and inside the last 128-column pass
+    const bool vs = !x_bf16 && ldo > F && ldo <= npass * 128 && g_agg_tma_vs;
+    const int extra = (vs && has_ind) ? 16 * ((num_ind + 3) / 4) : 0;
     int ec = ec_req > 0 ? ec_req : 32;
     if (ec > 32) ec = 32;
-    while (ec > 1 && grapes_agg_tma_smem(F, ec, es) > budget) ec >>= 1;
-    const size_t smem = grapes_agg_tma_smem(F, ec, es);
+    while (ec > 1 && grapes_agg_tma_smem(F, ec, es, extra) > budget) ec >>= 1;
+    const size_t smem = grapes_agg_tma_smem(F, ec, es, extra);
     if (smem > 226u * 1024u) return 1;
-    const int npass = (F + 127) / 128;
     const int rb_min = 8;
     long long blocks = ((long long)cap_n + AT_WARPS * rb_min - 1) / (AT_WARPS * rb_min);
-    const long long cap = (long long)ctx->sm_count * (smem > 113u * 1024u ? 1 : 2);
+    const long long cap = (long long)ctx->sm_count * (smem > 113u * 1024u ? 1 : (cps >= 2 ? cps : 2));
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-#define AT_LAUNCH4(NP, IND, OM, XB)                                                                                       \
+#define AT_LAUNCH5(NP, IND, OM, XB, VSF)                                                                                 \
     do {                                                                                                                \
         static bool configured = false;                                                                                 \
         if (!configured) {                                                                                              \
-            if (cudaFuncSetAttribute(k_agg_tma<NP, IND, OM, XB>, cudaFuncAttributeMaxDynamicSharedMemorySize,               \
+            if (cudaFuncSetAttribute(k_agg_tma<NP, IND, OM, XB, VSF>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                                      (int)(226u * 1024u)) != cudaSuccess) return 1;                                     \
             configured = true;                                                                                          \
         }                                                                                                               \
-        pdl((k_agg_tma<NP, IND, OM, XB>), (int)blocks, AT_THREADS, smem, s)(X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, \
-                                                                          dinv, ind_bits, num_ind, bias, relu, out, ldo,  \
-                                                                          out_hi, out_lo, ones_col, ec, rb_min);          \
+        pdl((k_agg_tma<NP, IND, OM, XB, VSF>), (int)blocks, AT_THREADS, smem, s)(X, F, ldx, nodes, n_dev, cap_n, in_off,   \
+                                                                               in_src, dinv, ind_bits, num_ind, bias, relu, \
+                                                                               out, ldo, out_hi, out_lo, ones_col, ec,     \
+                                                                               rb_min);                                    \
+    } while (0)
+#define AT_LAUNCH4(NP, IND, OM, XB)                                                                                     \
+    do {                                                                                                                \
+        if (!XB && vs) AT_LAUNCH5(NP, IND, OM, false, true); else AT_LAUNCH5(NP, IND, OM, XB, false);                   \
     } while (0)
 #define AT_LAUNCH2(NP, IND, XB)                                                                                         \
     do {                                                                                                                \
@@ -282,7 +321,6 @@ int grapes_launch_agg_tma(grapes_ctx* ctx, const void* X, int x_bf16, int F, int
     do {                                                                                                                \
         if (has_ind) AT_LAUNCH2(NP, true, true); else AT_LAUNCH2(NP, false, true);                                      \
     } while (0)
-    const bool has_ind = ind_bits != nullptr && num_ind > 0;
     const int om = (out ? 1 : 0) | (out_hi ? 2 : 0);
     if (x_bf16) {
         if (npass == 1) AT_LAUNCH_B16(1); else AT_LAUNCH_B16(2);
@@ -292,6 +330,7 @@ int grapes_launch_agg_tma(grapes_ctx* ctx, const void* X, int x_bf16, int F, int
     else AT_LAUNCH(12);
 #undef AT_LAUNCH_B16
 #undef AT_LAUNCH2
+#undef AT_LAUNCH5
 #undef AT_LAUNCH4
 #undef AT_LAUNCH
     return 0;

@@ -22,11 +22,12 @@ def run(L, ctx, X, F, nodes, n, in_off, in_src, dinv, variant, reps=5, hi_lo=Fal
         L.grapes_aggregate(ctx, ptr(X), F, F, ptr(nodes), cnt.data_ptr(), n, ptr(in_off), ptr(in_src), ptr(dinv), None, 0,
                            None, 0, None if hi_lo else ptr(out), ldo, ptr(out) if hi_lo else None, ptr(out_lo), -1, st)
     call(); torch.cuda.synchronize()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush = torch.zeros(256 << 20, dtype=torch.uint8, device=dev)
     ts = []
     for _ in range(reps):
         if do_flush:
-            flush.zero_()                               # L2 flush between timed launches
+            flush.sum()                                 # L2 flush between timed launches: READ 256 MB (clean lines; a memset
+                                                        # leaves 126 MB of dirty lines whose write-back lands in the timed kernel)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); call(); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
@@ -81,6 +82,39 @@ def main():
         _, ms2 = run(L, g.ctx, x, F, nodes, n, off, src, dv, v, reps=9, hi_lo=False, ldo=ldo)
         _, ms3 = run(L, g.ctx, x, F, nodes, n, off, src, dv, v, reps=9, hi_lo=True, ldo=ldo, do_flush=False)
         print(f"hop-shaped v{v}: {ms*1e3:.2f} us  equal={same}  algorithmic {alg/ms/1e6:.0f} GB/s; single fp32 output {ms2*1e3:.2f} us; hi/lo warm L2 {ms3*1e3:.2f} us", flush=True)
+    # ---- the engine's hop aggregation itself: indicator columns + ones column, (hi, lo) output; pad columns through the
+    # float4 lanes (virtual slot, opt-in) against one scalar lane per pad column (default) ----
+    bits = torch.randint(0, 16, (n,), generator=gen, device=dev, dtype=torch.int32)
+    ldo2 = ((F + 4 + 1 + 3) // 4) * 4
+    cnt = torch.tensor([n], dtype=torch.int32, device=dev)
+    hi, lo = torch.zeros(n, ldo2, device=dev), torch.zeros(n, ldo2, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    L.cdll.grapes_agg_variant(0)
+    flush = torch.zeros(256 << 20, dtype=torch.uint8, device=dev)
+    keep = {}
+    vlist = [int(v) for v in os.environ.get("HOP_VARIANTS", "0").split(",")]
+    for vs in [(a, b) for b in vlist for a in (1, 0)]:
+        L.cdll.grapes_agg_variant(vs[1])
+        vs, vtag = vs[0], f"{vs[0]}_v{vs[1]}"
+        L.cdll.grapes_agg_tma_virtual_slot(vs)
+        ts = []
+        for it in range(12):
+            flush.sum()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            L.grapes_aggregate(g.ctx, ptr(x), F, F, ptr(nodes), cnt.data_ptr(), n, ptr(off), ptr(src), ptr(dv), ptr(bits), 4,
+                               None, 0, None, ldo2, ptr(hi), ptr(lo), F + 4, st)
+            e1.record(); torch.cuda.synchronize()
+            if it: ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        keep[vs] = (hi.clone(), lo.clone())
+        vs = vtag
+        alg = 4.0 * n * (F + ldo2) + 12.0 * n + 4.0 * n
+        res[f"hop_ind_virtual_slot_{vs}"] = {"us": round(ts[len(ts) // 2] * 1e3, 2), "alg_GBps": round(alg / ts[len(ts) // 2] / 1e6, 1)}
+        print(f"hop aggregation with indicators, virtual_slot={vs}: {ts[len(ts)//2]*1e3:.2f} us", flush=True)
+    L.cdll.grapes_agg_tma_virtual_slot(0)
+    L.cdll.grapes_agg_variant(0)
+    res["hop_ind_bitwise_equal"] = bool(torch.equal(keep[0][0], keep[1][0]) and torch.equal(keep[0][1], keep[1][1]))
     print(json.dumps(res))
 
 

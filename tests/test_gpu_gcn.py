@@ -77,3 +77,65 @@ def test_gcn_input_gradient(cuda_device):
     xg = x.to(cuda_device).requires_grad_(True)
     net(xg, ei.to(cuda_device))[0].square().sum().backward()
     _close(xg.grad, xr.grad)
+
+
+@pytest.mark.parametrize("F,num_ind,ones", [(100, 4, True), (36, 4, True), (100, 3, False), (64, 8, True), (256, 3, True)])
+@pytest.mark.parametrize("hi_lo", [False, True])
+def test_agg_tma_virtual_columns_bit_identical(cuda_device, F, num_ind, ones, hi_lo):
+    """The TMA-staged aggregation with the pad columns (indicators | ones | zeros) carried by the float4 lanes
+    (grapes_agg_tma_virtual_slot 1, opt-in) == one scalar lane per pad column (0, default) == the register-staged kernel
+    (grapes_agg_variant 1), bit for bit; the indicator columns equal the weighted sums of the source bits."""
+    from grapes_b200._lib import lib, ptr
+    from grapes_b200.graph import DeviceGraph
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(F + num_ind)
+    N, n = 30000, 9000
+    g = DeviceGraph.from_edge_index(torch.randint(0, N, (2, 1000), generator=gen), N, device=dev)
+    x = torch.randn(N, F, generator=gen).to(dev)
+    nodes = torch.sort(torch.randperm(N, generator=gen)[:n]).values.to(torch.int32).to(dev)
+    cnt_e = torch.randint(0, 6, (n,), generator=gen)
+    cnt_e[5] = 300                                                     # one long row: several 16-entry chunks
+    in_off = torch.zeros(n + 1, dtype=torch.int32)
+    in_off[1:] = torch.cumsum(cnt_e, 0)
+    in_src = torch.randint(0, n, (int(in_off[-1]),), generator=gen, dtype=torch.int32)
+    dinv = (torch.rand(n, generator=gen) * 0.5 + 0.1).to(dev)
+    bits = torch.randint(0, 1 << num_ind, (n,), generator=gen, dtype=torch.int32).to(dev)
+    ldo = (F + num_ind + (1 if ones else 0) + 3) // 4 * 4
+    ones_col = F + num_ind if ones else -1
+    n_dev = torch.tensor([n], dtype=torch.int32, device=dev)
+    in_off, in_src = in_off.to(dev), in_src.to(dev)
+    L = lib()
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run():
+        a = torch.full((n, ldo), float("nan"), device=dev)
+        b = torch.full((n, ldo), float("nan"), device=dev)
+        L.grapes_aggregate(g.ctx, ptr(x), F, F, ptr(nodes), ptr(n_dev), n, ptr(in_off), ptr(in_src), ptr(dinv), ptr(bits),
+                           num_ind, None, 0, None if hi_lo else ptr(a), ldo, ptr(a) if hi_lo else None,
+                           ptr(b) if hi_lo else None, ones_col, st)
+        torch.cuda.synchronize()
+        return (a, b) if hi_lo else (a,)
+    try:
+        L.cdll.grapes_agg_tma_virtual_slot(1)
+        y_vs = run()
+        L.cdll.grapes_agg_tma_virtual_slot(0)
+        y_scalar = run()
+        L.cdll.grapes_agg_variant(1)
+        y_reg = run()
+    finally:
+        L.cdll.grapes_agg_variant(0)
+        L.cdll.grapes_agg_tma_virtual_slot(0)
+    for a, b, c in zip(y_vs, y_scalar, y_reg):
+        assert not torch.isnan(a).any()
+        assert torch.equal(a, b) and torch.equal(a, c)
+    y = y_vs[0] + y_vs[1] if hi_lo else y_vs[0]
+    # reference of the pad columns in float64
+    w_self = dinv.double() ** 2
+    bitf = torch.stack([((bits >> i) & 1).double() for i in range(num_ind)], 1)
+    ind = w_self[:, None] * bitf
+    rows = torch.repeat_interleave(torch.arange(n, device=dev), cnt_e.to(dev))
+    ind.index_add_(0, rows, (dinv.double()[in_src.long()] * dinv.double()[rows])[:, None] * bitf[in_src.long()])
+    assert (y[:, F:F + num_ind].double() - ind).abs().max() < 1e-5 * ind.abs().max()
+    if ones:
+        assert bool((y[:, ones_col] == 1).all())
+    assert bool((y[:, F + num_ind + (1 if ones else 0):] == 0).all())
