@@ -944,10 +944,11 @@ static int aggregate_impl(grapes_ctx* ctx, const void* Xv, int x_bf16, int F, in
         X, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias, relu, out, ldo, out_hi, out_lo,  \
         ones_col)
         // default: rows staged by TMA bulk copies (spmm_tma.cu).  Measured on B200 (scripts/bench_spmm.py): frontier-sized
-        // launches are best with 16-entry chunks and 2 CTAs/SM, whole-graph launches with 32-entry chunks and 1 CTA/SM.
+        // launches are best with 8-entry chunks and 3 CTAs/SM (ncu: 21.8 us against 23.3 at 2 CTAs/SM, 24.6 at 4), whole-graph launches
+        // with 32-entry chunks and 1 CTA/SM.
         // grapes_agg_variant: 100 + ec / 200 + ec force a shape, 1..6 select the register-staged kernels.
         if (g_agg_variant == 0 || g_agg_variant >= 100) {
-            const int v = g_agg_variant ? g_agg_variant : (cap_n > (1 << 19) ? 132 : 216);
+            const int v = g_agg_variant ? g_agg_variant : (cap_n > (1 << 19) ? 132 : 308);
             if (grapes_launch_agg_tma(ctx, X, 0, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias,
                                       relu, out, ldo, out_hi, out_lo, ones_col, v % 100, v / 100, s) == 0) {
                 grapes_count_launches(1);

@@ -115,6 +115,10 @@ class GrapesEngine:
         # backward walks Y in chunks of 128 columns.
         self.use_tc = bool(use_tensor_cores) and (self.D % 128 == 0) and self.D <= 512
         self.use_tc_bwd = self.use_tc and self.D // 128 <= 2    # backward accumulators: halves x (hi | lo) x 128 columns of TMEM
+        # default (GRAPES_Y_SINGLE=0 restores the pre-split pair): the aggregation writes Y once as fp32 and the tcgen05 kernels split it into (hi, lo) themselves
+        # (half the Y bytes written and read, one more pipeline step per k-block in the GEMMs; products-shape: aggregation 73.8 -> 60.8,
+        # forward 120 -> 136, backward 155 -> 149 us per step, step 0.512 -> 0.508 ms)
+        self.y_single = self.use_tc and os.environ.get("GRAPES_Y_SINGLE", "1" if self.Fp <= 1024 else "0") == "1"   # Cora-shape (K = 1436): the pair is 2 % faster
         if self.use_tc_bwd:
             self.ldY = _round_up(self.Fp + 1, 4)           # room for the column of ones (bias column)
         self.ldW = _round_up(self.Fp, 4)
@@ -318,7 +322,7 @@ class GrapesEngine:
             if need_Y:
                 # tensor-core path: (Y, Y_lo) is the 3xTF32 (hi, lo) pair written by the aggregation; else plain fp32 Y
                 hw.Y = z((cap_n, self.ldY), **f32)
-                if self.use_tc:
+                if self.use_tc and not self.y_single:
                     hw.Y_lo = z((cap_n, self.ldY), **f32)
                 if self.use_tc_bwd:
                     hw.mask_gf = z(((cap_n + 127) // 128 * 4, D), **i32)
@@ -635,7 +639,8 @@ class GrapesEngine:
             agg_x = L.grapes_aggregate_bf16 if self.x_bf16 else L.grapes_aggregate
             agg_x(ctx, ptr(self.x), self.F, self.F, ptr(hw.batch_nodes), n_dev, cap_n, ptr(hw.in_off),
                                ptr(hw.in_src), ptr(hw.dinv), ptr(hw.ind_bits) if self.use_ind else None, self.num_ind,
-                               None, 0, None if tc else ptr(hw.Y), self.ldY, ptr(hw.Y) if tc else None, ptr(hw.Y_lo),
+                               None, 0, None if (tc and not self.y_single) else ptr(hw.Y), self.ldY,
+                               ptr(hw.Y) if (tc and not self.y_single) else None, ptr(hw.Y_lo),
                                self.Fp if self.use_tc_bwd else -1, st)
 
     def _enqueue_front0(self, ctx, st):
@@ -865,7 +870,7 @@ class GrapesEngine:
         for h in range(H):
             hw, sz = self.hops[h], sizes[h]
             P, m, n, c, s, e = sz["P"], sz["m"], sz["n"], sz["c"], sz["s"], sz["blk"]
-            Y = None if self.random_sampling else (hw.Y[:n] + hw.Y_lo[:n] if self.use_tc else hw.Y[:n].clone())
+            Y = None if self.random_sampling else (hw.Y[:n] + hw.Y_lo[:n] if hw.Y_lo is not None else hw.Y[:n].clone())
             r = dict(P=P, m=m, n=n, c=c, s=s,
                      prev=self.prev[h][:P].clone(), e_row=hw.e_row[:m].clone(), e_col=hw.e_col[:m].clone(),
                      e_src=hw.e_src[:m].clone(), e_dst=hw.e_dst[:m].clone(),
