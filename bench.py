@@ -483,8 +483,9 @@ def main():
             "grapes_sampler_l1_bwd_tc": ("tensor", fwd_flops),
         }
         # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full`
-        # capture of this same command (profiles/r01_v4_topkernels.md), averaged over the hop-level launches
-        ncu_traffic = {"grapes_aggregate": 36.5e6, "grapes_sampler_l1_fwd_tc": 49.0e6, "grapes_sampler_l1_bwd_tc": 53.8e6}
+        # capture of this same command (profiles/r01_v6_topkernels.md), averaged over the hop-level launches.  Y is
+        # written once and consumed while it is still in L2, so the GEMMs read about half of what the (hi, lo) pair cost.
+        ncu_traffic = {"grapes_aggregate": 32.7e6, "grapes_sampler_l1_fwd_tc": 26.5e6, "grapes_sampler_l1_bwd_tc": 28.4e6}
         rooflines = {}
         for name, (bound, work) in alg.items():
             if name not in prof:
