@@ -764,7 +764,8 @@ class GrapesEngine:
 
     # ------------------------------------------------------------------ public API
     def set_targets(self, target_nodes: torch.Tensor, state: Optional[int] = None):
-        """Writes the batch's target ids into a step state (default: the active one)."""
+        """Writes the batch's target ids into a step state (default: the active one).  ``target_nodes`` may live on the
+        device or in pinned host memory (int32: one cudaMemcpyAsync straight into the state's list, no staging)."""
         t = target_nodes
         b = int(t.numel())
         if b > self.B or b < 1:
