@@ -633,24 +633,26 @@ __global__ void __launch_bounds__(G_THREADS) k_gemm_tn_splitk(const float* __res
 #define GS_N 64
 #define GS_PAD 4
 
+// One 16 x 64 operand tile = one float4 per thread.  fetch_tile_s reads it from global memory into registers (zeros outside
+// the matrix), store_tile_s puts it into shared memory: the main loop fetches tile k+1 before it computes on tile k, so the
+// global-load latency of these classifier-sized products (a handful of k-steps per CTA) overlaps the FMAs instead of
+// being exposed once per k-step.  Same summation order as the unpipelined loop -> bitwise identical results.
 template <bool KC>
-__device__ __forceinline__ void load_tile_s(const float* __restrict__ T, int ld, int mn0, int MN, int k0, int k1,
-                                            float (*S)[GS_M + GS_PAD]) {
+__device__ __forceinline__ float4 fetch_tile_s(const float* __restrict__ T, int ld, int mn0, int MN, int k0, int k1) {
     const int tid = threadIdx.x;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
     if (KC) {
         const int mm = tid >> 2, kk0 = (tid & 3) * 4;
         const int mrow = mn0 + mm;
         const float* src = T + (size_t)mrow * ld + k0 + kk0;
         const bool vec = ((ld & 3) == 0) && ((((size_t)T) & 15) == 0) && ((k0 & 3) == 0);
         if (mrow < MN && vec && k0 + kk0 + 4 <= k1) {
-            const float4 a = *reinterpret_cast<const float4*>(src);
-            S[kk0 + 0][mm] = a.x; S[kk0 + 1][mm] = a.y; S[kk0 + 2][mm] = a.z; S[kk0 + 3][mm] = a.w;
-        } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int k = k0 + kk0 + i;
-                S[kk0 + i][mm] = (mrow < MN && k < k1) ? src[i] : 0.f;
-            }
+            a = *reinterpret_cast<const float4*>(src);
+        } else if (mrow < MN) {
+            if (k0 + kk0 + 0 < k1) a.x = src[0];
+            if (k0 + kk0 + 1 < k1) a.y = src[1];
+            if (k0 + kk0 + 2 < k1) a.z = src[2];
+            if (k0 + kk0 + 3 < k1) a.w = src[3];
         }
     } else {
         const int mm = (tid & 15) * 4, kk = tid >> 4;
@@ -658,12 +660,25 @@ __device__ __forceinline__ void load_tile_s(const float* __restrict__ T, int ld,
         const float* src = T + (size_t)k * ld + mn0 + mm;
         const bool vec = ((ld & 3) == 0) && ((((size_t)T) & 15) == 0) && ((mn0 & 3) == 0);
         if (k < k1 && vec && mn0 + mm + 4 <= MN) {
-            const float4 a = *reinterpret_cast<const float4*>(src);
-            S[kk][mm] = a.x; S[kk][mm + 1] = a.y; S[kk][mm + 2] = a.z; S[kk][mm + 3] = a.w;
-        } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) S[kk][mm + i] = (k < k1 && mn0 + mm + i < MN) ? src[i] : 0.f;
+            a = *reinterpret_cast<const float4*>(src);
+        } else if (k < k1) {
+            if (mn0 + mm + 0 < MN) a.x = src[0];
+            if (mn0 + mm + 1 < MN) a.y = src[1];
+            if (mn0 + mm + 2 < MN) a.z = src[2];
+            if (mn0 + mm + 3 < MN) a.w = src[3];
         }
+    }
+    return a;
+}
+template <bool KC>
+__device__ __forceinline__ void store_tile_s(const float4 a, float (*S)[GS_M + GS_PAD]) {
+    const int tid = threadIdx.x;
+    if (KC) {
+        const int mm = tid >> 2, kk0 = (tid & 3) * 4;
+        S[kk0 + 0][mm] = a.x; S[kk0 + 1][mm] = a.y; S[kk0 + 2][mm] = a.z; S[kk0 + 3][mm] = a.w;
+    } else {
+        const int mm = (tid & 15) * 4, kk = tid >> 4;
+        S[kk][mm] = a.x; S[kk][mm + 1] = a.y; S[kk][mm + 2] = a.z; S[kk][mm + 3] = a.w;
     }
 }
 
@@ -673,10 +688,17 @@ __device__ __forceinline__ void gemm_mainloop_s(const float* __restrict__ A, int
                                                 float (*As)[GS_M + GS_PAD], float (*Bs)[GS_N + GS_PAD],
                                                 float (&acc)[4][4]) {
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    if (k0 >= k1) return;
+    float4 ra = fetch_tile_s<A_KC>(A, lda, m0, M, k0, k1);
+    float4 rb = fetch_tile_s<B_KC>(B, ldb, n0, N, k0, k1);
     for (int k = k0; k < k1; k += GB_K) {
-        load_tile_s<A_KC>(A, lda, m0, M, k, k1, As);
-        load_tile_s<B_KC>(B, ldb, n0, N, k, k1, Bs);
+        store_tile_s<A_KC>(ra, As);
+        store_tile_s<B_KC>(rb, Bs);
         __syncthreads();
+        if (k + GB_K < k1) {                                       // next tile in flight while this one is multiplied
+            ra = fetch_tile_s<A_KC>(A, lda, m0, M, k + GB_K, k1);   // (two tiles ahead measured no better: 0.498 vs 0.494 ms/step)
+            rb = fetch_tile_s<B_KC>(B, ldb, n0, N, k + GB_K, k1);
+        }
 #pragma unroll
         for (int kk = 0; kk < GB_K; ++kk) {
             const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
