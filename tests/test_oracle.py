@@ -172,3 +172,35 @@ def test_oracle_embed_nodes_table_is_in_optimizer_c():
     only_first[r2["all_nodes"]] = False
     moved = (st.x.detach()[only_first] != x1[only_first]).any(dim=1)
     assert only_first.any() and bool(moved.any())                  # zero gradient this step, Adam momentum still moves them
+
+
+def test_csr_oracle_is_the_reference_statement():
+    """main.py:134-136 verbatim (``sp.csr_matrix((np.ones(E, dtype=bool), edge_index), shape=(N, N))``) against the
+    oracle's ``build_adjacency`` and against a sort/unique restatement in numpy: the three agree on indptr / indices, so
+    the GPU tests of grapes_csr_from_edges (tests/test_gpu_csr_build.py) are pinned to what the reference itself builds.
+    Row slicing of the reference's (non-canonicalised) matrix gives the same neighbour lists (utils.py:78)."""
+    import numpy as np
+    import scipy.sparse as sp
+    g = torch.Generator().manual_seed(11)
+    N, E = 200, 3000
+    ei = torch.randint(0, N, (2, E), generator=g)
+    ei = torch.cat([ei, ei[:, :500], torch.arange(N).repeat(2, 1)], dim=1)          # duplicates + self-loops
+    ref = sp.csr_matrix((np.ones(ei.shape[1], dtype=bool), ei.numpy()), shape=(N, N))   # the reference's statement
+    adj = rp.build_adjacency(ei, N)
+    key = np.unique(ei[0].numpy() * N + ei[1].numpy())
+    rows, cols = key // N, key % N
+    indptr = np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=N))])
+    assert np.array_equal(adj.indptr, indptr) and np.array_equal(adj.indices, cols)
+    canon = ref.copy(); canon.sum_duplicates(); canon.sort_indices()
+    assert np.array_equal(canon.indptr, adj.indptr) and np.array_equal(canon.indices, adj.indices)
+    nodes = torch.tensor([3, 77, 3, 199])
+    a = rp.get_neighborhoods(nodes, ref)
+    b = rp.get_neighborhoods(nodes, adj)
+    assert torch.equal(a, b)
+
+
+def test_csr_from_edge_index_has_no_cpu_path():
+    from grapes_b200._lib import GrapesError
+    from grapes_b200.graph import csr_from_edge_index
+    with pytest.raises(GrapesError):
+        csr_from_edge_index(torch.zeros(2, 3, dtype=torch.long), 4, "cpu")
