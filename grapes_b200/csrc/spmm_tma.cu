@@ -82,7 +82,9 @@ __global__ void __launch_bounds__(AT_THREADS) k_agg_tma(
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
     const int n = min(*n_dev, cap_n);
-    const uint32_t rowbytes = (uint32_t)F * (XB16 ? 2u : 4u);
+    // bytes staged per row: the row rounded up to a whole float4 (F % 4 != 0: the table's rows are padded, ldx >= round_up(F, 4);
+    // the pad values are accumulated into the unused components of the last feature lane and never stored)
+    const uint32_t rowbytes = XB16 ? (uint32_t)F * 2u : (uint32_t)((F + 3) & ~3) * 4u;
     const int ni4 = (VS && HAS_IND) ? (num_ind + 3) >> 2 : 0;      // float4 groups of indicator columns behind each staged row
     const uint32_t rowstride = rowbytes + 16u * (uint32_t)ni4;
     const uint32_t slot_bytes = (uint32_t)ec * rowstride;
@@ -224,20 +226,37 @@ __global__ void __launch_bounds__(AT_THREADS) k_agg_tma(
                             const int c0 = p * 128 + lane * 4;
                             float4 a = act[p] ? acc[p] : make_float4(0.f, 0.f, 0.f, 0.f);
                             if (!VS || c0 < F) {
-                                if (bias) { a.x += bias[c0]; a.y += bias[c0 + 1]; a.z += bias[c0 + 2]; a.w += bias[c0 + 3]; }
+                                if (bias) {
+                                    if (c0 + 4 <= F) { a.x += bias[c0]; a.y += bias[c0 + 1]; a.z += bias[c0 + 2]; a.w += bias[c0 + 3]; }
+                                    else { a.x += bias[c0]; if (c0 + 1 < F) a.y += bias[c0 + 1]; if (c0 + 2 < F) a.z += bias[c0 + 2]; }
+                                }
                                 if (relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
                             } else {                               // virtual lane: indicators (accumulated) | ones | zero pad
                                 const int oc = ones_col - c0;
                                 if (oc == 0) a.x = 1.f; else if (oc == 1) a.y = 1.f; else if (oc == 2) a.z = 1.f; else if (oc == 3) a.w = 1.f;
                             }
-                            if (OUTMODE & 1) *reinterpret_cast<float4*>(out + orow + c0) = a;
-                            if (OUTMODE & 2) {                     // 3xTF32 operand split for the tcgen05 GEMM
-                                float4 h, l;
-                                h.x = at_tf32(a.x); h.y = at_tf32(a.y); h.z = at_tf32(a.z); h.w = at_tf32(a.w);
-                                l.x = at_tf32(a.x - h.x); l.y = at_tf32(a.y - h.y);
-                                l.z = at_tf32(a.z - h.z); l.w = at_tf32(a.w - h.w);
-                                *reinterpret_cast<float4*>(out_hi + orow + c0) = h;
-                                *reinterpret_cast<float4*>(out_lo + orow + c0) = l;
+                            if (!VS && c0 + 4 > F) {               // last feature lane of a row with F % 4 != 0: 1..3 valid columns
+                                const int nvv = F - c0;
+                                auto put = [&](int i, float val) {
+                                    if (OUTMODE & 1) out[orow + c0 + i] = val;
+                                    if (OUTMODE & 2) {
+                                        const float h = at_tf32(val);
+                                        out_hi[orow + c0 + i] = h; out_lo[orow + c0 + i] = at_tf32(val - h);
+                                    }
+                                };
+                                put(0, a.x);
+                                if (nvv > 1) put(1, a.y);
+                                if (nvv > 2) put(2, a.z);
+                            } else {
+                                if (OUTMODE & 1) *reinterpret_cast<float4*>(out + orow + c0) = a;
+                                if (OUTMODE & 2) {                 // 3xTF32 operand split for the tcgen05 GEMM
+                                    float4 h, l;
+                                    h.x = at_tf32(a.x); h.y = at_tf32(a.y); h.z = at_tf32(a.z); h.w = at_tf32(a.w);
+                                    l.x = at_tf32(a.x - h.x); l.y = at_tf32(a.y - h.y);
+                                    l.z = at_tf32(a.z - h.z); l.w = at_tf32(a.w - h.w);
+                                    *reinterpret_cast<float4*>(out_hi + orow + c0) = h;
+                                    *reinterpret_cast<float4*>(out_lo + orow + c0) = l;
+                                }
                             }
                         }
                         acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);    // next row starts from fma(w_self, x, 0)
@@ -271,7 +290,10 @@ int grapes_launch_agg_tma(grapes_ctx* ctx, const void* X, int x_bf16, int F, int
                           const int* in_off, const int* in_src, const float* dinv, const uint32_t* ind_bits, int num_ind,
                           const float* bias, int relu, float* out, int ldo, float* out_hi, float* out_lo, int ones_col,
                           int ec_req, int ctas_per_sm, cudaStream_t s) {
-    if (F % 4 != 0 || ldx % 4 != 0 || ldo % 4 != 0 || ldo - F > 32 || F > 128 * 12 || F < 4) return 1;
+    // fp32 rows must start 16-byte aligned and be readable up to a whole float4: ldx % 4 == 0 and ldx >= round_up(F, 4)
+    // (F itself may be any width: Reddit 602, Cora 1433 -- the caller pads the table's row pitch, engine.py)
+    if (ldx % 4 != 0 || ldx < ((F + 3) & ~3) || ldo % 4 != 0 || ldo - F > 32 || F > 128 * 12 || F < 4) return 1;
+    if (x_bf16 && F % 4 != 0) return 1;
     if (x_bf16 && (F % 8 != 0 || ldx % 8 != 0 || F > 256)) return 1;         // 16-byte rows; bf16 forms built for F <= 256
     const int es = x_bf16 ? 2 : 4;
     const int cps = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 6 ? 6 : ctas_per_sm);       // resident CTAs per SM the shape is sized for
@@ -279,12 +301,13 @@ int grapes_launch_agg_tma(grapes_ctx* ctx, const void* X, int x_bf16, int F, int
     const int npass = (F + 127) / 128;
     const bool has_ind = ind_bits != nullptr && num_ind > 0;
     // virtual columns through the float4 lanes (VS): fp32 table, pad columns present and inside the last 128-column pass
-    const bool vs = !x_bf16 && ldo > F && ldo <= npass * 128 && g_agg_tma_vs;
+    const bool vs = !x_bf16 && F % 4 == 0 && ldo > F && ldo <= npass * 128 && g_agg_tma_vs;
     const int extra = (vs && has_ind) ? 16 * ((num_ind + 3) / 4) : 0;
+    const int Fs = x_bf16 ? F : ((F + 3) & ~3);                                       // staged row width
     int ec = ec_req > 0 ? ec_req : 32;
     if (ec > 32) ec = 32;
-    while (ec > 1 && grapes_agg_tma_smem(F, ec, es, extra) > budget) ec >>= 1;
-    const size_t smem = grapes_agg_tma_smem(F, ec, es, extra);
+    while (ec > 1 && grapes_agg_tma_smem(Fs, ec, es, extra) > budget) ec >>= 1;
+    const size_t smem = grapes_agg_tma_smem(Fs, ec, es, extra);
     if (smem > 226u * 1024u) return 1;
     const int rb_min = 8;
     long long blocks = ((long long)cap_n + AT_WARPS * rb_min - 1) / (AT_WARPS * rb_min);

@@ -104,6 +104,14 @@ class GrapesEngine:
         else:
             self.y = self.y.to(torch.int64)
         N, F = graph.num_nodes, x.shape[1]
+        # TMA row copies need 16-byte rows: a table whose width is not a multiple of 4 floats (Reddit 602, Cora 1433) is
+        # re-pitched once to ldx = round_up(F, 4); self.x stays the [N, F] view, the kernels get (F, ldx)
+        self.ldx = F
+        if x.dtype == torch.float32 and F % 4 != 0 and not embed_nodes:
+            self.ldx = _round_up(F, 4)
+            xp = torch.zeros((N, self.ldx), dtype=torch.float32, device=x.device)
+            xp[:, :F].copy_(x)
+            self.x = xp[:, :F]
         self.N, self.F, self.C, self.D = N, F, int(num_classes), int(hidden_dim)
         self.B, self.k, self.H = int(batch_size), int(num_samples), int(sampling_hops)
         self.use_ind = bool(use_indicators)
@@ -540,7 +548,7 @@ class GrapesEngine:
                                A_dev, cap_A, ptr(self.cnt_scratch), 0, ptr(self.cl_out_off0), ptr(self.cl_out_dst0),
                                ptr(self.cl_tmp), None, self._cnt("cl_nnz", 3), ovf, st)
         (L.grapes_aggregate_bf16 if self.x_bf16 else L.grapes_aggregate)(
-                           ctx, X, F, F, ptr(self.all_nodes), A_dev, cap_A, ptr(self.cl_in_off[0]),
+                           ctx, X, F, self.ldx, ptr(self.all_nodes), A_dev, cap_A, ptr(self.cl_in_off[0]),
                            ptr(self.cl_in_src[0]), ptr(self.cl_dinv[0]), None, 0, None, 0, ptr(self.Yc), ldYc, None, None, -1, st)
         L.grapes_gemm(ctx, 3, ptr(self.Yc), ldYc, self._par(nc.W1), F, ptr(self.out1), D, A_dev, cap_A, D, F,
                       self._par(nc.b1), 1, None, 0, st)
@@ -637,7 +645,7 @@ class GrapesEngine:
         if not self.random_sampling:
             tc = self.use_tc
             agg_x = L.grapes_aggregate_bf16 if self.x_bf16 else L.grapes_aggregate
-            agg_x(ctx, ptr(self.x), self.F, self.F, ptr(hw.batch_nodes), n_dev, cap_n, ptr(hw.in_off),
+            agg_x(ctx, ptr(self.x), self.F, self.ldx, ptr(hw.batch_nodes), n_dev, cap_n, ptr(hw.in_off),
                                ptr(hw.in_src), ptr(hw.dinv), ptr(hw.ind_bits) if self.use_ind else None, self.num_ind,
                                None, 0, None if (tc and not self.y_single) else ptr(hw.Y), self.ldY,
                                ptr(hw.Y) if (tc and not self.y_single) else None, ptr(hw.Y_lo),

@@ -29,7 +29,8 @@ def _setup(name, seed, dev, use_tensor_cores=False, **kw):
     from grapes_b200.synth import SHAPES
     cfg = dict(SHAPES[name])
     torch.manual_seed(1000 + seed)     # the oracle draws its Gumbel noise from the global CPU generator
-    d = make_synth(name, seed=seed, multilabel=kw.pop("multilabel", False), power_law=kw.pop("power_law", 0.0))
+    over = {"F": kw.pop("F")} if "F" in kw else {}
+    d = make_synth(name, seed=seed, multilabel=kw.pop("multilabel", False), power_law=kw.pop("power_law", 0.0), **over)
     feature_bf16 = kw.pop("feature_bf16", False)
     if feature_bf16:                     # the table is STORED in bf16; the oracle computes on exactly those values
         d.x = d.x.bfloat16().float()
@@ -134,6 +135,15 @@ def _check_step(st, eng, targets, dev, apply_optim=True, relaxed=False, post_opt
 def test_step_parity_trajectory_balance(cuda_device, name, seed):
     d, st, eng, train_idx, B = _setup(name, seed, cuda_device)
     _check_step(st, eng, train_idx[:B], cuda_device, apply_optim=False)
+
+
+@pytest.mark.parametrize("F,use_tc", [(38, False), (41, True), (602, True)])
+def test_step_parity_feature_width_not_multiple_of_4(cuda_device, F, use_tc):
+    """Reddit has 602 features, Cora 1433: the engine re-pitches the table to ldx = round_up(F, 4) and the TMA-staged
+    aggregation (frontier >= 4096 rows here) carries a partial last feature lane.  Same bars as every other step test."""
+    d, st, eng, train_idx, B = _setup("small", 1, cuda_device, use_tensor_cores=use_tc, F=F)
+    assert eng.ldx == (F + 3) // 4 * 4 and eng.cap_n >= 4096 and tuple(eng.x.shape) == (d.num_nodes, F)
+    _check_step(st, eng, train_idx[:B], cuda_device, apply_optim=False, relaxed=use_tc)
 
 
 @pytest.mark.parametrize("use_tc", [False, True])

@@ -139,3 +139,61 @@ def test_agg_tma_virtual_columns_bit_identical(cuda_device, F, num_ind, ones, hi
     if ones:
         assert bool((y[:, ones_col] == 1).all())
     assert bool((y[:, F + num_ind + (1 if ones else 0):] == 0).all())
+
+
+@pytest.mark.parametrize("F,num_ind", [(602, 3), (1433, 3), (38, 4), (41, 0), (103, 4)])
+@pytest.mark.parametrize("hi_lo", [False, True])
+def test_agg_tma_width_not_multiple_of_4_bit_identical(cuda_device, F, num_ind, hi_lo):
+    """Feature widths that are not a multiple of 4 floats (Reddit 602, Cora 1433) on a table with a padded row pitch: the
+    TMA-staged aggregation (partial last feature lane) == the register-staged kernel, bit for bit; pad columns of the
+    TABLE hold NaN canaries (they are staged and accumulated, never stored), every output column is written."""
+    from grapes_b200._lib import lib, ptr
+    from grapes_b200.graph import DeviceGraph
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(F)
+    N, n = 12000, 5000
+    ldx = (F + 3) // 4 * 4
+    g = DeviceGraph.from_edge_index(torch.randint(0, N, (2, 1000), generator=gen), N, device=dev)
+    xp = torch.full((N, ldx), float("nan"))
+    xp[:, :F] = torch.randn(N, F, generator=gen)
+    xp = xp.to(dev)
+    nodes = torch.sort(torch.randperm(N, generator=gen)[:n]).values.to(torch.int32).to(dev)
+    cnt_e = torch.randint(0, 5, (n,), generator=gen)
+    cnt_e[7] = 70
+    in_off = torch.zeros(n + 1, dtype=torch.int32)
+    in_off[1:] = torch.cumsum(cnt_e, 0)
+    in_src = torch.randint(0, n, (int(in_off[-1]),), generator=gen, dtype=torch.int32).to(dev)
+    in_off = in_off.to(dev)
+    dinv = (torch.rand(n, generator=gen) * 0.5 + 0.1).to(dev)
+    bits = torch.randint(0, 1 << max(num_ind, 1), (n,), generator=gen, dtype=torch.int32).to(dev)
+    ones_col = F + num_ind
+    ldo = (F + num_ind + 1 + 3) // 4 * 4
+    n_dev = torch.tensor([n], dtype=torch.int32, device=dev)
+    L = lib()
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run():
+        a = torch.full((n, ldo), float("nan"), device=dev)
+        b = torch.full((n, ldo), float("nan"), device=dev)
+        L.grapes_aggregate(g.ctx, ptr(xp), F, ldx, ptr(nodes), ptr(n_dev), n, ptr(in_off), ptr(in_src), ptr(dinv),
+                           ptr(bits) if num_ind else None, num_ind, None, 0, None if hi_lo else ptr(a), ldo,
+                           ptr(a) if hi_lo else None, ptr(b) if hi_lo else None, ones_col, st)
+        torch.cuda.synchronize()
+        return (a, b) if hi_lo else (a,)
+    try:
+        n0 = L.grapes_kernel_launches()
+        y_tma = run()
+        L.cdll.grapes_agg_variant(1)
+        y_reg = run()
+    finally:
+        L.cdll.grapes_agg_variant(0)
+    for a, b in zip(y_tma, y_reg):
+        assert not torch.isnan(a).any() and torch.equal(a, b)
+    y = (y_tma[0] + y_tma[1]) if hi_lo else y_tma[0]
+    x = xp[:, :F].double()
+    ref = (dinv.double() ** 2)[:, None] * x[nodes.long()]
+    rows = torch.repeat_interleave(torch.arange(n, device=dev), cnt_e.to(dev))
+    w = dinv.double()[in_src.long()] * dinv.double()[rows]
+    ref.index_add_(0, rows, w[:, None] * x[nodes.long()[in_src.long()]])
+    assert (y[:, :F].double() - ref).abs().max() < 1e-5 * ref.abs().max()
+    assert bool((y[:, ones_col] == 1).all())
