@@ -962,8 +962,8 @@ static int aggregate_impl(grapes_ctx* ctx, const void* Xv, int x_bf16, int F, in
     if (a16 && (F % 4 != 0) && (ldx % 4 == 0) && ldx >= ((F + 3) & ~3) && (ldo % 4 == 0) && (ldo - F <= 32) && cap_n >= 4096 &&
         (g_agg_variant == 0 || g_agg_variant >= 100)) {
         // rows whose width is not a multiple of 4 (Reddit 602, Cora 1433) on a table with a padded row pitch: TMA-staged
-        // form with a partial last feature lane; wide rows -> 1 CTA per SM, as many entries per chunk as fit
-        const int v = g_agg_variant ? g_agg_variant : 132;
+        // form with a partial last feature lane
+        const int v = g_agg_variant ? g_agg_variant : (cap_n > (1 << 19) ? 132 : 216);   // Reddit-shape hop: 2 CTAs/SM 0.236, 1 CTA/SM 0.272 ms/step
         if (grapes_launch_agg_tma(ctx, X, 0, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias, relu,
                                   out, ldo, out_hi, out_lo, ones_col, v % 100, v / 100, s) == 0) {
             grapes_count_launches(1);
@@ -982,7 +982,7 @@ static int aggregate_impl(grapes_ctx* ctx, const void* Xv, int x_bf16, int F, in
         // with 32-entry chunks and 1 CTA/SM.
         // grapes_agg_variant: 100 + ec / 200 + ec force a shape, 1..6 select the register-staged kernels.
         if (g_agg_variant == 0 || g_agg_variant >= 100) {
-            const int v = g_agg_variant ? g_agg_variant : ((cap_n > (1 << 19) || F > 256) ? 132 : 308);   // wide rows: 1 CTA per SM
+            const int v = g_agg_variant ? g_agg_variant : (cap_n > (1 << 19) ? 132 : (F > 256 ? 216 : 308));   // wide rows: 2 CTAs per SM
             if (grapes_launch_agg_tma(ctx, X, 0, F, ldx, nodes, n_dev, cap_n, in_off, in_src, dinv, ind_bits, num_ind, bias,
                                       relu, out, ldo, out_hi, out_lo, ones_col, v % 100, v / 100, s) == 0) {
                 grapes_count_launches(1);
