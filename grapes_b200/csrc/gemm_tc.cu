@@ -403,13 +403,18 @@ __device__ __forceinline__ float tf32_rna(float x) {
 //   S = mask^T B''_hi + mask^T B''_lo   ->  with [B''_hi | B''_lo] stored back to back as ONE MN-major operand of
 //   N = 2 * NB * 32 columns this is ONE tcgen05.mma per 8-row slice and 128-unit half (instead of three), reading
 //   12 KB of operands instead of 24 KB (the kernel is fed at the shared-memory read limit).  The two accumulator halves
-//   are added in the epilogue.  Columns [col0, col0 + NB*32) of Y per launch (NB <= 4): wider Y = several launches.
+//   are added in the epilogue.  Columns [col0, col0 + NB*32) of Y per CTA (NB <= 4): wider Y = several column chunks (blockIdx.y).
 #define TCB_THREADS 320          // TMA, MMA, 4 mask-expander (+ epilogue) warps, 4 operand-scaling warps
 __global__ void __launch_bounds__(TCB_THREADS, 1) k_l1_bwd_tc(
     const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmY_lo, int presplit, int col0,
     const int* __restrict__ n_dev, int cap_n, int NH, int NB, int stages, const uint32_t* __restrict__ maskT, int D,
-    const float* __restrict__ dz, float* __restrict__ part, int debug) {
+    const float* __restrict__ dz, float* __restrict__ part, int debug, int ncols, long long chunk_stride) {
     pdl_begin();
+    // blockIdx.y = column chunk of Y (128 columns each): all chunks of a wide Y (Cora 1437, Reddit 606 columns) run in ONE
+    // launch next to each other instead of one launch per chunk; every chunk has its own slab of the partial buffer
+    col0 += (int)blockIdx.y * 128;
+    NB = min(NB, (ncols - col0 + 31) / 32);
+    part += (size_t)blockIdx.y * (size_t)chunk_stride;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int a_bytes = NH * TCB_A_TILE;             // mask tiles of all halves
@@ -597,51 +602,60 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) k_l1_bwd_tc(
 // combine through shared memory.
 #define FIN_THREADS 1024
 __global__ void __launch_bounds__(FIN_THREADS) k_l1_bwd_finalize(
-    const float* __restrict__ part, int nparts, int D, int N, int col0, int K, const float* __restrict__ W1, int ldw,
-    const float* __restrict__ b1, const float* __restrict__ w2, int ones_col, float scale, float* __restrict__ gW1,
-    float* __restrict__ gb1, float* __restrict__ gw2) {
+    const float* __restrict__ part_all, int nparts, int D, int ncols, int nchunks, long long chunk_stride, int K,
+    const float* __restrict__ W1, int ldw, const float* __restrict__ b1, const float* __restrict__ w2, int ones_col,
+    float scale, float* __restrict__ gW1, float* __restrict__ gb1, float* __restrict__ gw2) {
     pdl_begin();
     __shared__ __align__(16) float sums[4 * FIN_THREADS];        // [groups][N], groups * N == 4096
     __shared__ float red[8];
     const int d = blockIdx.x;
-    const int nq = N >> 2;                                       // threads per partial row (N is a multiple of 32, <= 256)
-    const int groups = FIN_THREADS / nq;
-    const int pg = threadIdx.x / nq, kq = threadIdx.x % nq;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p = pg; p < nparts; p += 5 * groups) {
-        float4 v[5];
+    // the column chunks of Y one after the other (fixed order: gw2[d] accumulates chunk by chunk, as separate launches did)
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+        const int col0 = chunk * 128;
+        const int N = min(4, (ncols - col0 + 31) / 32) * 32;
+        const float* part = part_all + (size_t)chunk * (size_t)chunk_stride;
+        const int nq = N >> 2;                                   // threads per partial row (N is a multiple of 32, <= 128)
+        const int groups = FIN_THREADS / nq;
+        const int pg = threadIdx.x / nq, kq = threadIdx.x % nq;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pg < groups) {
+            for (int p = pg; p < nparts; p += 5 * groups) {
+                float4 v[5];
 #pragma unroll
-        for (int u = 0; u < 5; ++u) {
-            const int pp = p + u * groups;
-            v[u] = (pp < nparts) ? __ldg(reinterpret_cast<const float4*>(part + ((size_t)pp * D + d) * N) + kq)
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+                for (int u = 0; u < 5; ++u) {
+                    const int pp = p + u * groups;
+                    v[u] = (pp < nparts) ? __ldg(reinterpret_cast<const float4*>(part + ((size_t)pp * D + d) * N) + kq)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
 #pragma unroll
-        for (int u = 0; u < 5; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
-    }
-    reinterpret_cast<float4*>(sums)[pg * nq + kq] = acc;
-    __syncthreads();
-    float acc_w2 = 0.f;
-    if (threadIdx.x < N) {
-        const int k = col0 + threadIdx.x;                        // column of Y / W1 this launch's column `threadIdx.x` is
-        float s = 0.f;
-        for (int g = 0; g < groups; ++g) s += sums[g * N + threadIdx.x];   // fixed order
-        const float w2d = w2[d];
-        if (k < K) {
-            gW1[(size_t)d * K + k] += scale * w2d * s;
-            acc_w2 = W1[(size_t)d * ldw + k] * s;
-        } else if (k == ones_col) {
-            gb1[d] += scale * w2d * s;
-            acc_w2 = b1[d] * s;
+                for (int u = 0; u < 5; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+            }
+            reinterpret_cast<float4*>(sums)[pg * nq + kq] = acc;
         }
+        __syncthreads();
+        float acc_w2 = 0.f;
+        if (threadIdx.x < N) {
+            const int k = col0 + threadIdx.x;                    // column of Y / W1 this chunk's column `threadIdx.x` is
+            float s = 0.f;
+            for (int g = 0; g < groups; ++g) s += sums[g * N + threadIdx.x];   // fixed order
+            const float w2d = w2[d];
+            if (k < K) {
+                gW1[(size_t)d * K + k] += scale * w2d * s;
+                acc_w2 = W1[(size_t)d * ldw + k] * s;
+            } else if (k == ones_col) {
+                gb1[d] += scale * w2d * s;
+                acc_w2 = b1[d] * s;
+            }
+        }
+        if (threadIdx.x < 256) {
+            acc_w2 = warp_sum(acc_w2);
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc_w2;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            gw2[d] += scale * (((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7])));
+        __syncthreads();                                         // sums / red are reused by the next chunk
     }
-    if (threadIdx.x < 256) {
-        acc_w2 = warp_sum(acc_w2);
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc_w2;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0)
-        gw2[d] += scale * (((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7])));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -784,35 +798,36 @@ int grapes_sampler_l1_bwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo,
     GRAPES_REQUIRE(K <= ones_col && ones_col < ncols && ncols <= ldy, "bad column layout");
     const int NH = D / 128;
     cudaStream_t s = (cudaStream_t)stream;
-    // column chunks of <= 128 columns of Y (accumulator: NH halves x (hi | lo) x 128 columns = all 512 TMEM columns)
-    for (int col0 = 0; col0 < ncols; col0 += 128) {
-        const int NB = (grapes_min_i(ncols - col0, 128) + 31) / 32;
-        const int N = NB * 32;
-        const int stage_bytes = NH * TCB_A_TILE + NB * 2 * TCB_B_TILE;
-        int stages = (224 * 1024) / stage_bytes;
-        if (stages > 4) stages = 4;
-        GRAPES_REQUIRE(stages >= 2, "stage does not fit shared memory");
-        const int smem_bytes = stages * stage_bytes + 1024 + 128 + 4 * 32 * (int)sizeof(float);
-        CUtensorMap my, my_lo;
-        int rc;
-        if ((rc = make_map(&my, Y, cap_n, ncols, ldy, TCB_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != GRAPES_OK) return rc;
-        if ((rc = make_map(&my_lo, Y_lo ? Y_lo : Y, cap_n, ncols, ldy, TCB_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != GRAPES_OK) return rc;
-        static int attr_bytes = 0;
-        if (smem_bytes > attr_bytes) {
-            GRAPES_CUDA_OK(cudaFuncSetAttribute(k_l1_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-            attr_bytes = smem_bytes;
-        }
-        const int max_groups = (cap_n + TCB_ROWS - 1) / TCB_ROWS;
-        int blocks = max_groups < ctx->sm_count ? max_groups : ctx->sm_count;
-        if (blocks < 1) blocks = 1;
-        GRAPES_REQUIRE((size_t)blocks * D * N * sizeof(float) <= ctx->partials_bytes, "split partial buffer too small");
-        pdl((k_l1_bwd_tc), blocks, TCB_THREADS, smem_bytes, s)(my, my_lo, Y_lo ? 1 : 0, col0, n_dev, cap_n, NH, NB, stages,
-                                                           maskT, D, dz, ctx->partials, g_tc_debug);
-        grapes_count_launches(1);
-        pdl((k_l1_bwd_finalize), D, FIN_THREADS, 0, s)(ctx->partials, blocks, D, N, col0, K, W1, ldw, b1, w2, ones_col, scale,
-                                                    gW1, gb1, gw2);
-        grapes_count_launches(1);
+    // column chunks of <= 128 columns of Y (accumulator: NH halves x (hi | lo) x 128 columns = all 512 TMEM columns): ONE
+    // launch, blockIdx.y = chunk, the SMs divided among the chunks; then ONE finalize that walks the chunks in order
+    const int nchunks = (ncols + 127) / 128;
+    const int NB = (grapes_min_i(ncols, 128) + 31) / 32;              // blocks of 32 columns in a full chunk
+    const int stage_bytes = NH * TCB_A_TILE + NB * 2 * TCB_B_TILE;
+    int stages = (224 * 1024) / stage_bytes;
+    if (stages > 4) stages = 4;
+    GRAPES_REQUIRE(stages >= 2, "stage does not fit shared memory");
+    const int smem_bytes = stages * stage_bytes + 1024 + 128 + 4 * 32 * (int)sizeof(float);
+    CUtensorMap my, my_lo;
+    int rc;
+    if ((rc = make_map(&my, Y, cap_n, ncols, ldy, TCB_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != GRAPES_OK) return rc;
+    if ((rc = make_map(&my_lo, Y_lo ? Y_lo : Y, cap_n, ncols, ldy, TCB_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != GRAPES_OK) return rc;
+    static int attr_bytes = 0;
+    if (smem_bytes > attr_bytes) {
+        GRAPES_CUDA_OK(cudaFuncSetAttribute(k_l1_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        attr_bytes = smem_bytes;
     }
+    const int max_groups = (cap_n + TCB_ROWS - 1) / TCB_ROWS;
+    int blocks = grapes_max_i(1, ctx->sm_count / nchunks);           // CTAs per chunk
+    if (blocks > max_groups) blocks = max_groups;
+    while (blocks > 1 && (size_t)nchunks * blocks * D * 128 * sizeof(float) > ctx->partials_bytes) --blocks;
+    GRAPES_REQUIRE((size_t)nchunks * blocks * D * 128 * sizeof(float) <= ctx->partials_bytes, "split partial buffer too small");
+    const long long chunk_stride = (long long)blocks * D * 128;
+    pdl((k_l1_bwd_tc), dim3(blocks, nchunks), TCB_THREADS, smem_bytes, s)(my, my_lo, Y_lo ? 1 : 0, 0, n_dev, cap_n, NH, NB, stages,
+                                                                      maskT, D, dz, ctx->partials, g_tc_debug, ncols, chunk_stride);
+    grapes_count_launches(1);
+    pdl((k_l1_bwd_finalize), D, FIN_THREADS, 0, s)(ctx->partials, blocks, D, ncols, nchunks, chunk_stride, K, W1, ldw, b1, w2,
+                                                ones_col, scale, gW1, gb1, gw2);
+    grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;
 }
