@@ -959,7 +959,7 @@ static int aggregate_impl(grapes_ctx* ctx, const void* Xv, int x_bf16, int F, in
         GRAPES_LAUNCH_OK();
         return GRAPES_OK;
     }
-    if (a16 && (F % 4 != 0) && (ldx % 4 == 0) && ldx >= ((F + 3) & ~3) && (ldo % 4 == 0) && (ldo - F <= 32) && cap_n >= 4096 &&
+    if (a16 && (F % 4 != 0) && (ldx % 4 == 0) && ldx >= ((F + 3) & ~3) && (ldo % 4 == 0) && (ldo - F <= 32) && cap_n >= 256 &&
         (g_agg_variant == 0 || g_agg_variant >= 100)) {
         // rows whose width is not a multiple of 4 (Reddit 602, Cora 1433) on a table with a padded row pitch: TMA-staged
         // form with a partial last feature lane

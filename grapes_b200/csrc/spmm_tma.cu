@@ -309,7 +309,7 @@ int grapes_launch_agg_tma(grapes_ctx* ctx, const void* X, int x_bf16, int F, int
     while (ec > 1 && grapes_agg_tma_smem(Fs, ec, es, extra) > budget) ec >>= 1;
     const size_t smem = grapes_agg_tma_smem(Fs, ec, es, extra);
     if (smem > 226u * 1024u) return 1;
-    const int rb_min = 8;
+    const int rb_min = (size_t)Fs * es >= 2048 ? 2 : 8;      // wide rows (Reddit 2.4 KB, Cora 5.7 KB): spread a small frontier over every warp
     long long blocks = ((long long)cap_n + AT_WARPS * rb_min - 1) / (AT_WARPS * rb_min);
     const long long cap = (long long)ctx->sm_count * (smem > 113u * 1024u ? 1 : (cps >= 2 ? cps : 2));
     if (blocks > cap) blocks = cap;
