@@ -176,7 +176,9 @@ int grapes_build_csr(grapes_ctx* ctx, const int* key, const int* val, const int*
 /* out[j,:F] = dinv[j]^2 X[g(j)] + sum_s dinv[s] dinv[j] X[g(s)] (+bias)(relu); g = nodes[] or identity.
  * Indicator columns [F, F+num_ind) from ind_bits; [F+num_ind, ldo) zero-filled.  out_hi/out_lo
  * (optional, same ldo) receive the 3xTF32 operand split tf32(v), tf32(v - tf32(v)) for the tcgen05 GEMM;
- * ones_col >= 0 puts a column of ones there (bias column of the tensor-core backward), -1 = none.       */
+ * ones_col >= 0 puts a column of ones there (bias column of the tensor-core backward), -1 = none.        * TMA-staged form (feature rows copied by cp.async.bulk into shared memory): 16-byte aligned X / outputs, ldx % 4 == 0 and
+ * ldx >= round_up(F, 4) -- F itself may be any width (Reddit 602, Cora 1433: pad the row PITCH, the pad values are never
+ * stored); other layouts take the register-staged kernels.  Bitwise identical results either way.                       */
 int grapes_aggregate(grapes_ctx* ctx, const float* X, int F, int ldx, const int* nodes, const int* n_dev, int cap_n,
                      const int* in_off, const int* in_src, const float* dinv, const uint32_t* ind_bits, int num_ind,
                      const float* bias, int relu, float* out, int ldo, float* out_hi, float* out_lo, int ones_col,
