@@ -915,10 +915,12 @@ static inline int grid_for(const grapes_ctx* ctx, long long work, int threads, i
 }
 
 static int g_agg_variant = 0;
+static int g_agg_min_rows = 4096;       // smallest row capacity that takes the multi-row / TMA-staged forms (aligned widths)
 
 extern "C" {
 
 int grapes_agg_variant(int v) { g_agg_variant = v; return 0; }
+int grapes_agg_tma_min_rows(int rows) { g_agg_min_rows = rows > 0 ? rows : 4096; return 0; }
 
 static int aggregate_impl(grapes_ctx* ctx, const void* Xv, int x_bf16, int F, int ldx, const int* nodes, const int* n_dev,
                           int cap_n, const int* in_off, const int* in_src, const float* dinv, const uint32_t* ind_bits,
@@ -971,7 +973,7 @@ static int aggregate_impl(grapes_ctx* ctx, const void* Xv, int x_bf16, int F, in
             return GRAPES_OK;
         }
     }
-    if (a16 && (F % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && (ldo - F <= 32) && cap_n >= 4096) {
+    if (a16 && (F % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && (ldo - F <= 32) && cap_n >= g_agg_min_rows) {
         // frontier-sized: R rows per warp with interleaved load chains (variant chosen by grapes_agg_variant, default 0)
 #define AGG_LAUNCH(RR, MB)                                                                                              \
     pdl((k_agg_rows<RR, MB>), grid_for(ctx, (long long)grapes_div_up(cap_n, RR) * 32, 256, MB), 256, 0, s)(                 \

@@ -272,6 +272,8 @@ class GrapesEngine:
         self.z_at = os.environ.get("GRAPES_Z_AT", "last" if (F + self.H + 1) <= 256 else "hop0")
         if os.environ.get("GRAPES_AGG_VARIANT"):
             self.L.cdll.grapes_agg_variant(int(os.environ["GRAPES_AGG_VARIANT"]))
+        if os.environ.get("GRAPES_AGG_MIN_ROWS"):
+            self.L.cdll.grapes_agg_tma_min_rows(int(os.environ["GRAPES_AGG_MIN_ROWS"]))
         if os.environ.get("GRAPES_TC_DEBUG"):
             self.L.cdll.grapes_tc_debug(int(os.environ["GRAPES_TC_DEBUG"]))
 

@@ -189,6 +189,9 @@ int grapes_aggregate(grapes_ctx* ctx, const float* X, int F, int ldx, const int*
  * row in shared memory), 0 (default) = one scalar lane per pad column.  Bitwise identical results; the float4 form
  * executes 15 % fewer instructions and measured slower on B200, so it is opt-in.                                  */
 int grapes_agg_tma_virtual_slot(int on);
+/* smallest row capacity (cap_n) whose aligned-width aggregation takes the TMA-staged form (default 4096; smaller launches
+ * use one warp per row)                                                                                              */
+int grapes_agg_tma_min_rows(int rows);
 int grapes_aggregate_bf16(grapes_ctx* ctx, const void* X_bf16, int F, int ldx, const int* nodes, const int* n_dev,
                           int cap_n, const int* in_off, const int* in_src, const float* dinv, const uint32_t* ind_bits,
                           int num_ind, const float* bias, int relu, float* out, int ldo, float* out_hi, float* out_lo,
