@@ -38,7 +38,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-spmm", action="store_true", help="skip the whole-graph SpMM leg")
-    ap.add_argument("--peer-exchange", action="store_true", help="N > 1: gradient all-reduce + Adam over NVLink peer memory inside the step graph instead of NCCL + Adam launch")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: 'peer' = gradient scale + push all-reduce + Adam as ONE kernel over NVLink peer memory inside "
+                         "the step graph (default); 'nccl' = ncclAllReduce(AVG) of the flat gradient captured into the step graph")
+    ap.add_argument("--prime", type=int, default=40, help="untimed steps before the W warm-up steps (clocks, allocator, graph variants, communicator)")
     ap.add_argument("--no-prefetch", action="store_true", help="no cross-step prefetch of the next batch's hop-0 front end")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)
     return ap.parse_args()
@@ -131,7 +134,7 @@ def build_workload_blocked(cfg, g, device, blocks: int = 64):
 
 
 class ClockSampler:
-    """Samples SM clocks / throttle reasons DURING the timed region: NVML polled every 2 ms from a thread
+    """Samples SM clocks / throttle reasons DURING the timed region: NVML polled every 1 ms from a thread
     (B200_PROFILING.md clocks line; nvidia-smi -lms is too coarse for a 20 ms region and is only the fallback)."""
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
@@ -171,7 +174,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.001)
 
     def start(self):
         if self.nvml is None:
@@ -186,7 +189,7 @@ class ClockSampler:
         self.thread.join(timeout=1.0)
         sm = sorted(self.samples)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "samples": len(sm),
-                "reasons": sorted(self.reasons), "source": "nvml, 2 ms polling during the timed region"}
+                "reasons": sorted(self.reasons), "source": "nvml, 1 ms polling during the timed region"}
 
     def _smi_once(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -273,7 +276,7 @@ def main():
             return 0
         dev = torch.device("cuda", local_rank) if have_cuda else torch.device("cpu")
         cfg, indptr, indices, x, y, train_idx = build_workload(cfgname, args.seed, dev)
-        warm = min(args.warmup, 2)
+        warm = args.warmup
         done, t_total, threads = cpu_reference_run(cfg, indptr, indices, x, y, train_idx, args.steps, warm,
                                                    budget_s=150.0)
         B = cfg["batch_size"]
@@ -310,30 +313,26 @@ def main():
                        sampling_hops=cfg["sampling_hops"], hidden_dim=256, seed=args.seed)
     L = lib()
     K, W = args.steps, max(args.warmup, 3)
+    PRIME = max(args.prime, 0)
     nb = train_idx.numel() // B
-    from grapes_b200.dist import allreduce_mean_, shard_batches
+    from grapes_b200.dist import shard_batches
     mine = shard_batches(nb, rank, world)                             # batch i -> rank i mod W
     order = [mine[j % len(mine)] for j in range(W + K + 1)]
     batches = torch.stack([train_idx[b * B:(b + 1) * B] for b in order]).to(torch.int32)
     use_graph = not args.no_graph
     prefetch = not args.no_prefetch
-    # N > 1: ONE collective per step, the mean all-reduce of the flat gradient (NCCL, 91 k floats), then the Adam launch.
-    # --peer-exchange runs all-reduce + Adam as two kernels over NVLink peer memory inside the step graph instead
-    # (grapes_allreduce_adam_peer: bit-identical parameters on every rank; measured 0.542 vs 0.522 ms/step at N = 2)
-    peer = world > 1 and args.peer_exchange
-    if peer:
-        eng.enable_peer_exchange()
+    # N > 1: the engine owns the exchange (GrapesEngine.enable_data_parallel): ONE collective per step, the mean of the
+    # flat gradient (91 k floats on products-shape), fused with the gradient scale and both Adam updates into the step's
+    # last launch over NVLink peer memory ('peer'), or ncclAllReduce captured into the step graph ('nccl').  Either way a
+    # step is one graph launch and every rank ends it with bit-identical parameters.
+    if world > 1:
+        eng.enable_data_parallel(exchange=args.exchange)
 
     def one_step(j):
         # the ids of batch j+1 are handed over with batch j: its reset + weight-independent hop-0 front end are enqueued
         # next to this step's classifier tail (the reference's DataLoader order is known in advance, main.py:125-126)
         nxt = batches[j + 1] if prefetch else None
-        if world > 1 and not peer:
-            eng.step(batches[j], apply_optim=False, use_graph=use_graph, next_targets=nxt)
-            allreduce_mean_(eng.grads)                              # the only collective: gradient allreduce
-            eng._enqueue_optim()
-        else:
-            eng.step(batches[j], apply_optim=True, use_graph=use_graph, next_targets=nxt)
+        eng.step(batches[j], apply_optim=True, use_graph=use_graph, next_targets=nxt)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -341,6 +340,9 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    for j in range(PRIME):                                            # untimed: clocks up, every graph variant captured,
+        one_step(j % W)                                               # communicator channels set up
+    sync_all()
     for j in range(W):
         one_step(j)
     sync_all()
@@ -349,26 +351,33 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     sync_all()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    ev[0].record()
     for j in range(W, W + K):
         one_step(j)
-    e1.record()
+        ev[j - W + 1].record()
     sync_all()
     clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
+    ms = ev[0].elapsed_time(ev[K])
     eng.check_overflow()
     if use_graph:
-        # kernels recorded into the graph once, replayed K times
-        per_step = eng.launches_per_graph + (0 if (world == 1 or peer) else 4)
+        # kernels recorded into the graph once, replayed K times (the NCCL exchange adds its own all-reduce kernel)
+        per_step = eng.launches_per_graph + (1 if (world > 1 and args.exchange == "nccl") else 0)
         launches = per_step * K
     else:
         launches = L.grapes_kernel_launches() - launches0
         per_step = launches // K
-    t = torch.tensor([ms], device=dev)
+    # per-step device times of this rank (event to event), gathered from every rank
+    per = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(K))
+    mine_t = torch.tensor([ms, per[len(per) // 2], per[min(len(per) - 1, int(0.99 * len(per)))], per[-1], per[0]], device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+        allt = [torch.zeros_like(mine_t) for _ in range(world)]
+        dist.all_gather(allt, mine_t)
+    else:
+        allt = [mine_t]
+    step_times = [{"rank": r, "total_ms": float(t_[0]), "p50_ms": float(t_[1]), "p99_ms": float(t_[2]),
+                   "max_ms": float(t_[3]), "min_ms": float(t_[4])} for r, t_ in enumerate(allt)]
+    ms = max(st_["total_ms"] for st_ in step_times)                   # max over ranks
     value = world * B * K / (ms / 1e3)
 
     # ------------------------------------------------------------------ e2e: host buffers in, loss out, every step
@@ -395,6 +404,7 @@ def main():
             scal_ready[j % 2].synchronize()
             e2e_state["losses"] += 1
             e2e_state["last_loss"] = float(host_scal[j % 2][0])
+            eng.raise_on_flags(int(host_scal[j % 2][15]))                                # frontier overflow / peer failure of THAT step
             e2e_state["pending"] = None
 
     def e2e_step(j):
@@ -406,13 +416,8 @@ def main():
         if prefetch:
             nxt = h2d_ids(j + 1)
             e2e_state["have"] = j + 1
-        if world > 1 and not peer:
-            eng.step(cur, apply_optim=False, use_graph=use_graph, next_targets=nxt)
-            allreduce_mean_(eng.grads)
-            eng._enqueue_optim()
-        else:
-            eng.step(cur, apply_optim=True, use_graph=use_graph, next_targets=nxt)
-        host_scal[j % 2].copy_(eng.scal, non_blocking=True)                              # D2H: losses of step j
+        eng.step(cur, apply_optim=True, use_graph=use_graph, next_targets=nxt)
+        host_scal[j % 2].copy_(eng.scal, non_blocking=True)                              # D2H: losses (+ overflow bits) of step j
         scal_ready[j % 2].record()
         e2e_collect()                                                                    # losses of step j - 1
         e2e_state["pending"] = j
@@ -422,6 +427,7 @@ def main():
     e2e_collect()
     sync_all()
     e2e_state["losses"] = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for j in range(W, W + K):
         e2e_step(j)
@@ -443,11 +449,11 @@ def main():
     if rank == 0:
         hbm_peak, tf_peak, peak_src = load_peaks()
         P_STEPS = 5
-        L.profiling = True
         eng.multi_stream = False             # one stream: each kernel is timed alone, not against its co-runners
-        eng.peer = None                      # rank 0 alone from here on: local Adam, no exchange
+        eng.peer = eng.dp_group = None       # rank 0 alone from here on: local Adam, no exchange
         if eng.ctx_a is not graph.ctx:
             L.grapes_ctx_set_sm_limit(eng.ctx_a, 0)    # ... and with the whole GPU (in the step the backward branch is given 96 SMs)
+        L.profiling = True                   # (after the host-only call above: it is not a kernel)
         per_hop_acc = None
         for j in range(P_STEPS):
             eng.set_targets(batches[j])
@@ -481,10 +487,16 @@ def main():
             "grapes_sampler_l1_fwd_tc": ("tensor", fwd_flops),
             "grapes_sampler_l1_bwd_tc": ("tensor", fwd_flops),
         }
-        # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full`
-        # capture of this same command (profiles/r01_v6_topkernels.md), averaged over the hop-level launches.  Y is
-        # written once and consumed while it is still in L2, so the GEMMs read about half of what the (hi, lo) pair cost.
-        ncu_traffic = {"grapes_aggregate": 32.7e6, "grapes_sampler_l1_fwd_tc": 26.5e6, "grapes_sampler_l1_bwd_tc": 28.4e6}
+        # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the hop-level launches, from the
+        # committed summary of the latest `ncu --set full` capture of this same command (profiles/ncu_traffic.json names
+        # the commit and the report it was read from); null when the workload has no capture
+        ncu_traffic, traffic_src = {}, None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.isfile(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("workload") == cfgname:
+                ncu_traffic = tj.get("bytes_per_launch", {})
+                traffic_src = {k: tj.get(k) for k in ("commit", "report", "command")}
         rooflines = {}
         for name, (bound, work) in alg.items():
             if name not in prof:
@@ -504,7 +516,7 @@ def main():
                                    "ceiling_frac": 1.0 / 6.0,
                                    "note": "3xTF32 (fp32-accurate): 3 tf32 MMAs per product at half the bf16 rate of the peak"}
         dominant = max(rooflines, key=lambda k: rooflines[k]["ms_per_step"]) if rooflines else None
-        roof = dict(rooflines[dominant], kernel=dominant, peak_source=peak_src) if dominant else None
+        roof = dict(rooflines[dominant], kernel=dominant, peak_source=peak_src, traffic_source=traffic_src) if dominant else None
 
         # ---- whole-graph SpMM (the metric's "SpMM HBM GB/s"): Y = A_hat X over every edge of the workload graph, the
         # aggregation of the full-batch evaluation forward (eval.py:47-56); one launch of the TMA-staged kernel ----
@@ -547,7 +559,10 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": int(per_step),
                 "roofline": roof, "rooflines": rooflines, "spmm": spmm, "csr_build": csr_build, "cpu_baseline": cpu, "breakdown_ms_per_step": breakdown,
                 "frontier": per_hop, "cuda_graph": use_graph, "cross_step_prefetch": prefetch,
-                "gradient_exchange": ("peer-memory all-reduce + Adam in the step graph" if peer else ("nccl all_reduce + adam launch" if world > 1 else "none"))}
+                "step_times": step_times, "prime_steps": PRIME,
+                "gradient_exchange": ("none" if world == 1 else
+                                      ("gradient scale + push all-reduce over NVLink peer memory + Adam: one kernel inside the step graph"
+                                       if args.exchange == "peer" else "ncclAllReduce(AVG) captured into the step graph + Adam launch"))}
         emit(line)
     if world > 1:
         dist.barrier()

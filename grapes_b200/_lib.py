@@ -52,10 +52,15 @@ class GrapesError(RuntimeError):
 
 class _Lib:
     def __init__(self):
-        if not os.path.isfile(LIB_PATH):
-            from .build import build_library
-            build_library()
+        # no-op when the binary carries the id of this source tree; rebuilds (one process at a time) when it does not, and
+        # raises without nvcc: prototypes parsed from a header the binary was not built from would corrupt arguments
+        from .build import build_library, built_id, tree_id
+        build_library()
         self.cdll = ctypes.CDLL(LIB_PATH)
+        self.cdll.grapes_build_id.restype = ctypes.c_char_p
+        if self.cdll.grapes_build_id().decode() != tree_id():
+            raise GrapesError("libgrapes_b200.so loaded in this process does not match the source tree "
+                              f"(library {built_id()[:12]}, tree {tree_id()[:12]}): restart after the rebuild")
         self.protos = parse_header()
         for name, (ret, params) in self.protos.items():
             fn = getattr(self.cdll, name)

@@ -19,6 +19,12 @@ extern "C" {
 
 const char* grapes_last_error(void) { return g_err; }
 int grapes_abi_version(void) { return 1; }
+#ifndef GRAPES_BUILD_ID
+#define GRAPES_BUILD_ID "unknown"
+#endif
+// the marker prefix lets the host read the id out of the file without loading it
+static const char g_build_id[] = "GRAPES_BUILD_ID=" GRAPES_BUILD_ID;
+const char* grapes_build_id(void) { return g_build_id + 16; }
 int grapes_set_pdl(int mask) { g_grapes_pdl = mask; return 0; }
 int64_t grapes_kernel_launches(void) { return (int64_t)g_launches; }
 
@@ -37,6 +43,9 @@ int grapes_ctx_create(int device, int64_t num_nodes, int64_t max_frontier, int64
     int ndev = 0;
     GRAPES_CUDA_OK(cudaGetDeviceCount(&ndev));
     GRAPES_REQUIRE(device >= 0 && device < ndev, "no such CUDA device (there is no CPU fallback)");
+    int prev_device = device;
+    GRAPES_CUDA_OK(cudaGetDevice(&prev_device));
+    struct Restore { int d; ~Restore() { cudaSetDevice(d); } } restore{prev_device};   // the caller's current device is left as found
     GRAPES_CUDA_OK(cudaSetDevice(device));
     cudaDeviceProp prop;
     GRAPES_CUDA_OK(cudaGetDeviceProperties(&prop, device));

@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(RANK_THREADS) k_rank_scan(
                 }
                 if ((nbits >> t) & 1u) {
                     const int q = rn++;
-                    if (q < cap_n && nb_nodes) { nb_nodes[q] = v; nb_local[q] = j; }
+                    if (q < cap_n && nb_nodes) { nb_nodes[q] = v; nb_local[q] = min(j, cap_n - 1); }   // (clamped only when GRAPES_OVF_NODES is raised)
                     if (nb_index && j < cap_n) nb_index[j] = q < cap_n ? q : -1;
                 } else if (nb_index && j < cap_n) nb_index[j] = -1;
             }
@@ -261,13 +261,16 @@ __global__ void __launch_bounds__(256) k_edge_local(const int* __restrict__ rows
                                                     const int* __restrict__ e_col,
                                                     const int* __restrict__ m_dev,
                                                     const uint32_t* __restrict__ bm,
-                                                    const int* __restrict__ pref,
+                                                    const int* __restrict__ pref, int cap_n,
                                                     int* __restrict__ e_src, int* __restrict__ e_dst, int* cnt_hist) {
     pdl_begin();
     const int m = *m_dev;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < m; e += gridDim.x * blockDim.x) {
-        const int s = bitmap_rank(bm, pref, rows[e_row[e]]);
-        const int d = bitmap_rank(bm, pref, e_col[e]);
+        int s = bitmap_rank(bm, pref, rows[e_row[e]]);
+        int d = bitmap_rank(bm, pref, e_col[e]);
+        // frontier larger than the caller's node capacity (GRAPES_OVF_NODES is already raised by the rank pass): an edge
+        // that touches a node past the capacity becomes a dropped self-edge, so every later index stays inside cap_n
+        if (s >= cap_n || d >= cap_n) s = d = 0;
         e_src[e] = s;
         e_dst[e] = d;
         if (cnt_hist && s != d) atomicAdd(&cnt_hist[d], 1);       // in-degree histogram of the CSR build, fused
@@ -511,7 +514,7 @@ __global__ void __launch_bounds__(HS_THREADS, 2) k_hop_structure(const HopStruct
                 }
                 if ((nbits >> t) & 1u) {
                     const int q = rn++;
-                    if (q < cap_n && a.nb_nodes) { a.nb_nodes[q] = v; a.nb_local[q] = j; }
+                    if (q < cap_n && a.nb_nodes) { a.nb_nodes[q] = v; a.nb_local[q] = min(j, cap_n - 1); }
                     if (a.nb_index && j < cap_n) a.nb_index[j] = q < cap_n ? q : -1;
                 } else if (a.nb_index && j < cap_n) a.nb_index[j] = -1;
             }
@@ -532,8 +535,9 @@ __global__ void __launch_bounds__(HS_THREADS, 2) k_hop_structure(const HopStruct
     const int n = min(*(volatile int*)a.n_out, cap_n);
     for (int e = gtid; e < m; e += gthreads) {
         const int sg = a.rows[a.e_row[e]], dg = a.e_col[e];
-        const int sl = a.pref_batch[sg >> 5] + __popc(a.bm_batch[sg >> 5] & ((1u << (sg & 31)) - 1u));
-        const int dl = a.pref_batch[dg >> 5] + __popc(a.bm_batch[dg >> 5] & ((1u << (dg & 31)) - 1u));
+        int sl = a.pref_batch[sg >> 5] + __popc(a.bm_batch[sg >> 5] & ((1u << (sg & 31)) - 1u));
+        int dl = a.pref_batch[dg >> 5] + __popc(a.bm_batch[dg >> 5] & ((1u << (dg & 31)) - 1u));
+        if (sl >= cap_n || dl >= cap_n) sl = dl = 0;        // node capacity exceeded: dropped self-edge (see k_edge_local)
         a.e_src[e] = sl;
         a.e_dst[e] = dl;
         if (sl != dl) atomicAdd(&a.cnt[dl], 1);
@@ -994,11 +998,12 @@ int grapes_hop_structure(grapes_ctx* ctx, const uint32_t* bm_batch, const uint32
 }
 
 int grapes_edges_to_local(grapes_ctx* ctx, const int* rows, const int* e_row, const int* e_col, const int* m_dev,
-                          int cap_m, const uint32_t* bm, const int* pref, int* e_src, int* e_dst, int* cnt_hist,
-                          void* stream) {
+                          int cap_m, const uint32_t* bm, const int* pref, int cap_n, int* e_src, int* e_dst,
+                          int* cnt_hist, void* stream) {
     GRAPES_REQUIRE(ctx && rows && e_row && e_col && m_dev && bm && pref && e_src && e_dst, "null argument");
+    GRAPES_REQUIRE(cap_n > 0, "cap_n: capacity of the node-indexed buffers (cnt_hist, in_off, dinv, ...)");
     pdl((k_edge_local), grid_for(ctx, cap_m, 256), 256, 0, (cudaStream_t)stream)(rows, e_row, e_col, m_dev, bm, pref,
-                                                                              e_src, e_dst, cnt_hist);
+                                                                              cap_n, e_src, e_dst, cnt_hist);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;

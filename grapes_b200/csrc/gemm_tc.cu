@@ -718,7 +718,6 @@ static int make_map(CUtensorMap* m, const float* base, int rows, int cols, int l
 extern "C" {
 
 int grapes_tc_debug(int flags) { g_tc_debug = flags; return 0; }
-const float* grapes_ctx_partials(grapes_ctx* ctx) { return ctx->partials; }
 
 int grapes_split_tf32(grapes_ctx* ctx, const float* src, int ld_src, int R, int K, float* hi, float* lo, int ld_dst,
                       void* stream) {

@@ -374,6 +374,32 @@ __global__ void __launch_bounds__(256) k_adam2(float* __restrict__ p, const floa
     }
 }
 
+// predictions = argmax(logits, dim=1)[row_ids]  (eval.py:152-153); ties go to the lowest class index, NaN never wins
+__global__ void __launch_bounds__(256) k_argmax_rows(const float* __restrict__ logits, int ldl, int C,
+                                                     const int* __restrict__ row_ids, const int* __restrict__ B_dev,
+                                                     int cap_B, int* __restrict__ out) {
+    pdl_begin();
+    const int B = min(*B_dev, cap_B);
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < B; i += warps) {
+        const float* row = logits + (size_t)row_ids[i] * ldl;
+        float best = -INFINITY;
+        int arg = 0x7fffffff;
+        for (int c = lane; c < C; c += 32) {
+            const float v = row[c];
+            if (v > best || (v == best && c < arg)) { best = v; arg = c; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(GRAPES_FULL_MASK, best, o);
+            const int oa = __shfl_xor_sync(GRAPES_FULL_MASK, arg, o);
+            if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+        }
+        if (lane == 0) out[i] = (arg == 0x7fffffff) ? 0 : arg;
+    }
+}
+
 __global__ void __launch_bounds__(256) k_fill_f32(float* p, float v, int n) {
     pdl_begin();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
@@ -492,6 +518,17 @@ int grapes_adam_embed(grapes_ctx* ctx, float* table, float* exp_avg, float* exp_
     pdl((k_adam_embed), (int)blocks, 256, 0, (cudaStream_t)stream)(table, exp_avg, exp_avg_sq, num_nodes, F / 4, bm_rows,
                                                                   pref_rows, grad_rows, ldg / 4, lr, beta1, beta2, eps,
                                                                   step_dev);
+    grapes_count_launches(1);
+    GRAPES_LAUNCH_OK();
+    return GRAPES_OK;
+}
+
+int grapes_argmax_rows(grapes_ctx* ctx, const float* logits, int ldl, int C, const int* row_ids, const int* B_dev,
+                       int cap_B, int* out, void* stream) {
+    GRAPES_REQUIRE(ctx && logits && row_ids && B_dev && out, "null argument");
+    GRAPES_REQUIRE(C > 0 && ldl >= C && cap_B > 0, "bad shape");
+    pdl((k_argmax_rows), grid_for(ctx, (long long)cap_B * 32, 256), 256, 0, (cudaStream_t)stream)(logits, ldl, C, row_ids,
+                                                                                                B_dev, cap_B, out);
     grapes_count_launches(1);
     GRAPES_LAUNCH_OK();
     return GRAPES_OK;

@@ -544,10 +544,11 @@ int grapes_select_hop(grapes_ctx* ctx, const float* z, int nparts, int part_stri
     const size_t chunk_bytes = ((size_t)(cap_n + SEL_CTAS - 1) / SEL_CTAS) * sizeof(uint32_t);
     const int staged = chunk_bytes <= 160 * 1024 ? 1 : 0;
     const int smem = staged ? (int)chunk_bytes : 0;
-    static int attr = 0;
-    if (smem > attr) {
+    static int attr[64] = {0};                       // per device: the attribute belongs to the device's copy of the function
+    int& have = attr[ctx->device & 63];
+    if (smem > have) {
         GRAPES_CUDA_OK(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr = smem;
+        have = smem;
     }
     pdl((k_select), SEL_CTAS, SEL_THREADS, smem, s)(ukeys_scratch, lg_c, nb_local, nb_nodes, c_dev, cap_n, k, noise_mode,
                                                  rng_state, stat_part, nblk, staged, sampled_out, sampled_offset,

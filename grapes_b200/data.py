@@ -35,5 +35,10 @@ def get_data(root: str, name: str, seed: int = None, split_id: int = 0):
     shape = _ALIASES.get(key)
     if shape is None or shape not in SHAPES:
         raise ValueError(f"Dataset {name} is not available offline (no {path}); synthetic shapes: {sorted(SHAPES)}")
+    if not name.lower().startswith("synth:"):
+        from .utils import get_logger
+        get_logger().warning(f"dataset '{name}' is not available offline (no {path}): substituting a SYNTHETIC graph of the "
+                             f"same shape ('{shape}') with random features and labels -- scores are not the dataset's")
     data = make_synth(shape, seed=0 if seed is None else seed)
+    data.synthetic = True
     return data, data.num_features, data.num_classes

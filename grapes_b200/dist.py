@@ -37,9 +37,10 @@ def flatten_grads(named_grads) -> torch.Tensor:
 
 
 class PeerGradExchange:
-    """Symmetric (peer-mapped) gradient buffers for ``grapes_allreduce_adam_peer``: every rank allocates the same buffer
-    with ``torch.distributed._symmetric_memory`` and receives the peers' device pointers, so the mean all-reduce and both
-    Adam updates run as two kernels over NVLink inside the step's CUDA graph (no host-side collective call)."""
+    """Symmetric (peer-mapped) gradient buffers for ``grapes_step_tail`` / ``grapes_allreduce_adam_peer``: every rank
+    allocates the same buffer with ``torch.distributed._symmetric_memory`` and receives the peers' device pointers, so the
+    mean all-reduce and both Adam updates run as ONE kernel over NVLink inside the step's CUDA graph (no host-side
+    collective call)."""
 
     def __init__(self, n_floats: int, device: torch.device, group=None):
         import ctypes
@@ -49,13 +50,13 @@ class PeerGradExchange:
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         if self.world > 8:
             raise RuntimeError("peer exchange is built for one NVSwitch box (<= 8 ranks)")
-        total = int(lib().cdll.grapes_peer_buffer_floats(int(n_floats)))
+        total = int(lib().cdll.grapes_peer_buffer_floats(int(n_floats), self.world))
         self.buf = symm_mem.empty(total, dtype=torch.float32, device=device)
         self.buf.zero_()
         self.hdl = symm_mem.rendezvous(self.buf, group.group_name if hasattr(group, "group_name") else group)
         ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         assert ptrs[self.rank] == self.buf.data_ptr()
         self.peer_ptrs = (ctypes.c_void_p * self.world)(*ptrs)              # HOST array handed to the C ABI
-        self.state = torch.zeros(4, dtype=torch.int32, device=device)
+        self.state = torch.zeros(int(lib().cdll.grapes_peer_state_words()), dtype=torch.int32, device=device)
         torch.cuda.synchronize(device)
         dist.barrier(group)                                                   # every buffer is zeroed before anyone publishes

@@ -26,7 +26,8 @@ import torch
 from ._lib import lib, ptr, GrapesError
 from .graph import DeviceGraph
 
-SCAL = dict(loss_c=0, tot_log_prob=1, log_z_mean=2, log_z=3, loss_gfn=4, g_gf=5, g_z=6, sum_dl=7)
+SCAL = dict(loss_c=0, tot_log_prob=1, log_z_mean=2, log_z=3, loss_gfn=4, g_gf=5, g_z=6, sum_dl=7, flags=15)
+STAT_NAMES = ("min_prob", "max_prob", "mean_entropy", "std_entropy")          # utils.py:62-69, per hop
 NOISE_PHILOX, NOISE_GUMBEL, NOISE_UNIFORM, NOISE_KEYS, NOISE_TOPK_PROBS = 0, 1, 2, 3, 4
 OVF_NAMES = {1: "rows>cap_P", 2: "edges>cap_m", 4: "nodes>cap_n", 8: "block>cap_blk", 16: "hub worklist",
              32: "a peer rank never published its gradients"}
@@ -257,7 +258,11 @@ class GrapesEngine:
             glorot_(v["gcn_layers.0.lin.weight"], gen)
             glorot_(v["gcn_layers.1.lin.weight"], gen)
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
-        self.peer = None                         # PeerGradExchange when data-parallel over NVLink peer memory
+        # data parallelism (enable_data_parallel): the step owns the gradient exchange and the optimiser launch
+        self.peer = None                         # PeerGradExchange when the exchange runs over NVLink peer memory
+        self.dp_group = None                     # process group of the NCCL exchange
+        self.dp_world, self.dp_rank = 1, 0
+        self.tail_state = torch.zeros(int(self.L.cdll.grapes_peer_state_words()), dtype=torch.int32, device=dev)
         self._graph_launches: Dict[tuple, int] = {}
         self.launches_per_graph = 0
         self.record: Optional[dict] = None
@@ -290,20 +295,21 @@ class GrapesEngine:
         e = torch.empty
         need_Y = not self.random_sampling
         # ---- ONE pool that is cleared by ONE memset at the start of every step:
-        #   bitmaps (int32 words): all_nodes | indicator rows | prev rows of hop 0..H-1 | batch rows of hop 0..H-1
+        #   bitmaps (int32 words): all_nodes | indicator rows | prev rows of hop 0..H-1 | batch rows of hop 0..H-1 | prev rows H
         #   floats: scalars | per-hop stats | gradient direction of the sampler nets
-        n_bm = 1 + max(self.num_ind, 1) + 2 * H
+        n_bm = 1 + max(self.num_ind, 1) + 2 * H + 1
         n_fl = 16 + 4 * H + n_par
         self.step_pool = z(n_bm * W + n_fl, **i32)
         bm = self.step_pool[:n_bm * W].view(n_bm, W)
         self.bm_all = bm[0]
         self.bm_ind = bm[1:1 + max(self.num_ind, 1)]
-        self.bm_prev = [bm[1 + max(self.num_ind, 1) + h] for h in range(H)]
+        self.bm_prev = [bm[1 + max(self.num_ind, 1) + h] for h in range(H)] + [bm[n_bm - 1]]   # [H]: rows of the last block (evaluation)
         self.bm_batch = [bm[1 + max(self.num_ind, 1) + H + h] for h in range(H)]
         fl = self.step_pool[n_bm * W:].view(torch.float32)
         self.zero_pool = fl
         self.scal = fl[:16]
         self.stats = fl[16:16 + 4 * H].view(H, 4)
+        self.scal_stats = fl[:16 + 4 * H]    # one contiguous read-back: losses, overflow bits, per-hop sampler statistics
         self.gdir = fl[16 + 4 * H:]          # gradient DIRECTION of (log_z, sum log_prob) w.r.t. gf / z params
         self.pref_batch, self.pref_nb = z(W + 1, **i32), z(W + 1, **i32)
 
@@ -510,6 +516,57 @@ class GrapesEngine:
             join(sA)
             join(sP)
             return
+        self._enqueue_classifier_forward(ctx, st)
+        L.tag = "[cls]"
+        nc = self.net_c
+        ldYc = self.Yc.shape[1]
+        A_dev, cap_A = self._cnt("A"), self.cap_A
+        # loss + d loss / d logits + d loss / d b2 (column sums) in one launch (main.py:260-261)
+        L.grapes_classifier_loss(ctx, ptr(self.logits_c), C, C, A_dev, cap_A, ptr(self.target_local),
+                                 ptr(self.tgt_of_row) if self.cap_A <= 4096 else None, ptr(self.targets), B, None if self.multilabel else ptr(self.y),
+                                 ptr(self.y) if self.multilabel else None, self.reg_param, ptr(self.dlogits),
+                                 self._scal("loss_c"), self._grd(nc.b2), st)
+        # backward of the classifier (loss_c.backward(), main.py:267); the two weight-gradient products that nothing
+        # else waits for run on side B next to the chain dZ -> dpre1 -> dW1
+        L.grapes_aggregate(ctx, ptr(self.dlogits), C, C, None, A_dev, cap_A, ptr(self.cl_out_off),
+                           ptr(self.cl_out_dst), ptr(self.cl_dinv[1]), None, 0, None, 0, ptr(self.dZ), C, None, None, -1, st)
+        fork(sB)
+        with on(sB):
+            L.grapes_gemm_tn(ctx_b, ptr(self.dZ), C, ptr(self.out1), D, A_dev, cap_A, C, D, 1.0, 0, self._grd(nc.W2), stB)
+        L.grapes_gemm(ctx, 1, ptr(self.dZ), C, self._par(nc.W2), D, ptr(self.dpre1), D, A_dev, cap_A, D, C, None, 0,
+                      ptr(self.out1), D, st)
+        fork(sB)
+        with on(sB):
+            L.grapes_colsum(ctx_b, ptr(self.dpre1), A_dev, cap_A, D, D, 1.0, 0, self._grd(nc.b1), stB)
+        L.grapes_gemm_tn(ctx, ptr(self.dpre1), D, ptr(self.Yc), ldYc, A_dev, cap_A, D, F, 1.0, 0, self._grd(nc.W1),
+                         st)
+        if self.embed_nodes:
+            # d loss_c / d x[all_nodes] (main.py:267 with embeddings in optimizer_c): dYc = dpre1 W1, dX = A_hat_1^T dYc
+            L.grapes_gemm(ctx, 1, ptr(self.dpre1), D, self._par(nc.W1), F, ptr(self.dYc), ldYc, A_dev, cap_A, F, D,
+                          None, 0, None, 0, st)
+            L.grapes_aggregate(ctx, ptr(self.dYc), F, ldYc, None, A_dev, cap_A, ptr(self.cl_out_off0),
+                               ptr(self.cl_out_dst0), ptr(self.cl_dinv[0]), None, 0, None, 0, ptr(self.dXc), ldYc,
+                               None, None, -1, st)
+        L.tag = ""
+        # ---- GFlowNet / REINFORCE loss (main.py:271-291): loss, gradient scale, scaled directions in one launch ----
+        join(sB)
+        join(sA)
+        join(sP)
+        if apply_optim:
+            self._enqueue_tail(st)
+        elif not self.random_sampling:
+            n_z = 0 if self.reinforce else nz.size
+            L.grapes_gfn_finalize_scale(ctx, ptr(self.scal), self.loss_coef, self.log_z_init, int(self.reinforce), 1,
+                                        self._dir(gf.base), gf.size, self._grd(gf.base),
+                                        self._dir(nz.base), n_z, self._grd(nz.base), st)
+
+    def _enqueue_classifier_forward(self, ctx, st):
+        """all_nodes + relabel of the per-hop blocks + gcn_norm structure of the classifier's two layers, then
+        logits = gcn_c(x[all_nodes], [block_0 .. block_{H-1}]) (main.py:252-257, eval.py:147-151)."""
+        L = self.L
+        H, F, D, C, B = self.H, self.F, self.D, self.C, self.bsz
+        ovf = ptr(self.overflow)
+        X = ptr(self.x)
         # ---- classifier on the sampled subgraph (main.py:252-269) ----
         L.tag = "[cls]"
         L.grapes_rank_nodes(ctx, ptr(self.bm_all), None, ptr(self.pref_all), None, ptr(self.all_nodes), None, None,
@@ -559,44 +616,81 @@ class GrapesEngine:
         L.grapes_aggregate(ctx, ptr(self.Zc), C, C, None, A_dev, cap_A, ptr(self.cl_in_off[1]),
                            ptr(self.cl_in_src[1]), ptr(self.cl_dinv[1]), None, 0, self._par(nc.b2), 0,
                            ptr(self.logits_c), C, None, None, -1, st)
-        # loss + d loss / d logits + d loss / d b2 (column sums) in one launch (main.py:260-261)
-        L.grapes_classifier_loss(ctx, ptr(self.logits_c), C, C, A_dev, cap_A, ptr(self.target_local),
-                                 ptr(self.tgt_of_row) if self.cap_A <= 4096 else None, ptr(self.targets), B, None if self.multilabel else ptr(self.y),
-                                 ptr(self.y) if self.multilabel else None, self.reg_param, ptr(self.dlogits),
-                                 self._scal("loss_c"), self._grd(nc.b2), st)
-        # backward of the classifier (loss_c.backward(), main.py:267); the two weight-gradient products that nothing
-        # else waits for run on side B next to the chain dZ -> dpre1 -> dW1
-        L.grapes_aggregate(ctx, ptr(self.dlogits), C, C, None, A_dev, cap_A, ptr(self.cl_out_off),
-                           ptr(self.cl_out_dst), ptr(self.cl_dinv[1]), None, 0, None, 0, ptr(self.dZ), C, None, None, -1, st)
-        fork(sB)
-        with on(sB):
-            L.grapes_gemm_tn(ctx_b, ptr(self.dZ), C, ptr(self.out1), D, A_dev, cap_A, C, D, 1.0, 0, self._grd(nc.W2), stB)
-        L.grapes_gemm(ctx, 1, ptr(self.dZ), C, self._par(nc.W2), D, ptr(self.dpre1), D, A_dev, cap_A, D, C, None, 0,
-                      ptr(self.out1), D, st)
-        fork(sB)
-        with on(sB):
-            L.grapes_colsum(ctx_b, ptr(self.dpre1), A_dev, cap_A, D, D, 1.0, 0, self._grd(nc.b1), stB)
-        L.grapes_gemm_tn(ctx, ptr(self.dpre1), D, ptr(self.Yc), ldYc, A_dev, cap_A, D, F, 1.0, 0, self._grd(nc.W1),
-                         st)
-        if self.embed_nodes:
-            # d loss_c / d x[all_nodes] (main.py:267 with embeddings in optimizer_c): dYc = dpre1 W1, dX = A_hat_1^T dYc
-            L.grapes_gemm(ctx, 1, ptr(self.dpre1), D, self._par(nc.W1), F, ptr(self.dYc), ldYc, A_dev, cap_A, F, D,
-                          None, 0, None, 0, st)
-            L.grapes_aggregate(ctx, ptr(self.dYc), F, ldYc, None, A_dev, cap_A, ptr(self.cl_out_off0),
-                               ptr(self.cl_out_dst0), ptr(self.cl_dinv[0]), None, 0, None, 0, ptr(self.dXc), ldYc,
-                               None, None, -1, st)
         L.tag = ""
-        # ---- GFlowNet / REINFORCE loss (main.py:271-291): loss, gradient scale, scaled directions in one launch ----
-        join(sB)
-        join(sA)
-        join(sP)
-        if not self.random_sampling:
-            n_z = 0 if self.reinforce else nz.size
-            L.grapes_gfn_finalize_scale(ctx, ptr(self.scal), self.loss_coef, self.log_z_init, int(self.reinforce), 1,
-                                        self._dir(gf.base), gf.size, self._grd(gf.base),
-                                        self._dir(nz.base), n_z, self._grd(nz.base), st)
-        if apply_optim:
-            self._enqueue_optim()
+
+    def _enqueue_eval(self, pred_ptr):
+        """The mini-batch evaluator's batch body (/root/reference/eval.py:84-153) on the training step's kernels, forward
+        only: per hop the sampler GCN's logits, DETERMINISTIC top-k on the probabilities (eval.py:126-130,
+        GRAPES_NOISE_NONE_TOPK_PROBS) and -- unlike training -- the block ``A[rows = previous_nodes][:, cols = T u sampled]``
+        (eval.py:140-142), which is a filter of the hop's OWN row expansion; then the classifier forward and the argmax of
+        the target rows.  One stream, no host synchronisation, graph-capturable."""
+        L, g = self.L, self.g
+        ctx, st = g.ctx, torch.cuda.current_stream().cuda_stream
+        if self.random_sampling:
+            raise GrapesError("mini-batch evaluation runs the sampler net (eval.py:121): build the engine with random_sampling=False")
+        B, k, H, Fp, D = self.bsz, self.k, self.H, self.Fp, self.D
+        cap_P, cap_m, cap_n = self.cap_P, self.cap_m, self.cap_n
+        ovf = ptr(self.overflow)
+        gf = self.net_gf
+        self._front_ready = [False, False]
+        self._enqueue_front0(ctx, st)
+        for h in range(H):
+            hw = self.hops[h]
+            rows, P_dev = ptr(self.prev[h]), self._hc(h, "P")
+            m_dev, n_dev, c_dev = self._hc(h, "m"), self._hc(h, "n"), self._hc(h, "c")
+            if h > 0:
+                L.grapes_expand_frontier(ctx, ptr(g.indptr), ptr(g.indices), rows, P_dev, cap_P, ptr(hw.row_off), m_dev,
+                                         cap_m, ptr(hw.e_row), ptr(hw.e_col), ptr(self.bm_prev[h]), ptr(self.bm_batch[h]),
+                                         ovf, st)
+                self._enqueue_hop_structure(h, ctx, st)
+            if self.use_tc:
+                if h == 0:
+                    self._split_weights(ctx, st)
+                L.grapes_sampler_l1_fwd_tc(ctx, ptr(hw.Y), ptr(hw.Y_lo), self.ldY, n_dev, cap_n, Fp, ptr(self.Wgf_hi),
+                                           ptr(self.Wgf_lo), self.ldW, D, self._par(gf.b1), self._par(gf.W2),
+                                           ptr(self.zpart), ptr(hw.mask_gf), st)
+                z_ptr, z_parts, z_stride = ptr(self.zpart), D // 128, cap_n
+            else:
+                L.grapes_sampler_l1_fwd(ctx, ptr(hw.Y), self.ldY, n_dev, cap_n, Fp, self._par(gf.W1), Fp, D,
+                                        self._par(gf.b1), self._par(gf.W2), ptr(self.z_gf), st)
+                z_ptr, z_parts, z_stride = ptr(self.z_gf), 1, 0
+            L.grapes_select_hop(ctx, z_ptr, z_parts, z_stride, n_dev, cap_n, ptr(hw.in_off), ptr(hw.in_src), ptr(hw.dinv),
+                                self._par(gf.b2), ptr(hw.nb_index), ptr(hw.nb_local), ptr(hw.nb_nodes), c_dev, k,
+                                NOISE_TOPK_PROBS, None, ptr(self.rng_state), ptr(self.sel_work), ptr(self.ukeys),
+                                ptr(hw.logits_all), None, ptr(self.prev[h + 1]), B, self._hc(h, "s"), self._hc(h + 1, "P"),
+                                None, None, None, None, None, None, ptr(self.bm_all), st)
+            # eval.py:140-142: rows = previous_nodes (the hop's expansion), cols = cat(targets, sampled)
+            L.grapes_bitmap_set(ctx, ptr(self.prev[h + 1]), self._hc(h + 1, "P"), cap_P, ptr(self.bm_prev[h + 1]), st)
+            L.grapes_slice_block(ctx, rows, ptr(hw.e_row), ptr(hw.e_col), m_dev, cap_m, ptr(self.bm_prev[h + 1]),
+                                 ptr(hw.blk_src), ptr(hw.blk_dst), self.cap_blk, self._hc(h, "blk"), ovf, st)
+        self._enqueue_classifier_forward(ctx, st)
+        # predictions = argmax(logits)[node_map.map(target_nodes)]   (eval.py:152-153)
+        L.grapes_argmax_rows(ctx, ptr(self.logits_c), self.C, self.C, ptr(self.target_local), self._cnt("B"), self.B,
+                             pred_ptr, st)
+
+    def predict(self, target_nodes: torch.Tensor, out: torch.Tensor, use_graph: bool = True):
+        """Class predictions of one evaluation batch (eval.py:84-153) written to ``out[:len(target_nodes)]`` (int32, device).
+        Enqueues only; the caller synchronises once after the last batch."""
+        assert out.dtype == torch.int32 and out.is_cuda and out.is_contiguous()
+        self.set_targets(target_nodes)
+        self._pref_key = None
+        if not use_graph:
+            self._enqueue_eval(out.data_ptr())
+            return
+        # the output address is baked into the captured launch: predictions land in a fixed buffer, then one copy
+        if not hasattr(self, "_pred_buf"):
+            self._pred_buf = torch.zeros(self.B, dtype=torch.int32, device=self.device)
+        key = ("eval", self.bsz, self.par)
+        gr = self._graphs.get(key)
+        if gr is None:
+            self._enqueue_eval(self._pred_buf.data_ptr())            # warm-up outside capture (deterministic: no RNG)
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                self._enqueue_eval(self._pred_buf.data_ptr())
+            self._graphs[key] = gr
+        gr.replay()
+        out[:self.bsz].copy_(self._pred_buf[:self.bsz])
 
     def _enqueue_prefetch(self, fork, on, sP, stP):
         # ---- cross-step prefetch: the hop chain and the classifier tail of THIS batch are chains of small, latency-bound
@@ -640,7 +734,7 @@ class GrapesEngine:
                                 ptr(self.bm_ind) if self.use_ind else None, self.num_ind, h, cap_n,
                                 n_dev, c_dev, ovf, st)
             L.grapes_edges_to_local(ctx, rows, ptr(hw.e_row), ptr(hw.e_col), m_dev, cap_m, ptr(self.bm_batch[h]),
-                                    ptr(self.pref_batch), ptr(hw.e_src), ptr(hw.e_dst), ptr(self.cnt_scratch), st)
+                                    ptr(self.pref_batch), cap_n, ptr(hw.e_src), ptr(hw.e_dst), ptr(self.cnt_scratch), st)
             L.grapes_build_csr(ctx, ptr(hw.e_dst), ptr(hw.e_src), m_dev, cap_m, n_dev, cap_n, ptr(self.cnt_scratch),
                                1, ptr(hw.in_off), ptr(hw.in_src), ptr(self.tmp_val), ptr(hw.dinv),
                                self._hc(h, "nnz"), ovf, st)
@@ -738,39 +832,70 @@ class GrapesEngine:
         L.grapes_split_tf32(ctx, self._par(nz.W1), self.F, self.D, self.F, ptr(self.Wz_hi), ptr(self.Wz_lo),
                             self.ldW, st)
 
-    def enable_peer_exchange(self, group=None):
-        """Data-parallel mode: from now on the optimiser launch of every step is the peer-memory mean all-reduce + Adam
-        (``grapes_allreduce_adam_peer``), captured with the rest of the step."""
-        from .dist import PeerGradExchange
-        self.peer = PeerGradExchange(self.n_par, self.device, group)
+    def enable_data_parallel(self, group=None, exchange: str = "peer"):
+        """Data-parallel mode (BASELINE.json north_star; the reference is single-process): this rank's ``step`` runs its
+        own batch, exchanges the flat gradient (mean over the ranks of ``group``) and applies both Adam updates, so every
+        rank holds bit-identical parameters after every step.  ``exchange``:
+          "peer"  one launch over NVLink peer memory (``grapes_step_tail``: gradient scale + push all-reduce + Adam),
+                  captured with the rest of the step -- the N-rank step is ONE graph launch;
+          "nccl"  ``ncclAllReduce(AVG)`` on the flat buffer between the scale and the Adam launch (captured into the step
+                  graph as well when the step is replayed from a graph)."""
+        import torch.distributed as dist
+        if self.embed_nodes:
+            raise GrapesError("embed_nodes is single-GPU (SURVEY.md section 8e): the table gradient is not exchanged")
+        if exchange not in ("peer", "nccl"):
+            raise ValueError("exchange must be 'peer' or 'nccl'")
+        group = group or dist.group.WORLD
+        self.dp_world, self.dp_rank = dist.get_world_size(group), dist.get_rank(group)
+        self.peer, self.dp_group = None, None
+        if self.dp_world > 1:
+            if exchange == "peer":
+                from .dist import PeerGradExchange
+                self.peer = PeerGradExchange(self.n_par, self.device, group)
+            else:
+                self.dp_group = group
+                # the first collectives of a communicator set up its channels: not inside a captured or timed step
+                warm = torch.zeros_like(self.grads)
+                for _ in range(24):
+                    dist.all_reduce(warm, op=dist.ReduceOp.AVG, group=group)
+                torch.cuda.synchronize(self.device)
         self._graphs.clear()
 
-    def _enqueue_optim(self):
-        """optimizer_c.step() and optimizer_gf.step() (main.py:268,289) as one launch over the flat buffers; with a
-        peer exchange enabled: on the mean of the per-rank gradients, all-reduced over NVLink peer memory."""
+    def enable_peer_exchange(self, group=None):
+        self.enable_data_parallel(group, "peer")
+
+    def _enqueue_tail(self, st):
+        """The tail of the step (main.py:271-291 after both backward passes): loss_gfn and the scale of the sampler nets'
+        gradient directions, the data-parallel gradient exchange, optimizer_c.step() and optimizer_gf.step() -- one
+        launch (``grapes_step_tail``); with the NCCL exchange: scale, all-reduce, Adam."""
         L, ctx = self.L, self.g.ctx
-        st = torch.cuda.current_stream().cuda_stream
         nc, gf, nz = self.net_c, self.net_gf, self.net_z
-        if self.random_sampling:
-            n1 = 0
-        else:
-            n1 = (nz.end - gf.base) if not self.reinforce else gf.size   # gcn_z has no grad under REINFORCE (main.py:279)
+        scale = not self.random_sampling
+        n_z = 0 if self.reinforce else nz.size                       # gcn_z has no grad under REINFORCE (main.py:279)
+        n1 = (gf.size + n_z) if scale else 0
         if self.embed_nodes:
-            if self.peer is not None:
-                raise GrapesError("embed_nodes is single-GPU (SURVEY.md section 8e): the table gradient is not exchanged")
             L.grapes_adam_embed(ctx, ptr(self.x), ptr(self.emb_exp_avg), ptr(self.emb_exp_avg_sq), self.N, self.F,
                                 ptr(self.bm_all), ptr(self.pref_all), ptr(self.dXc), self.dXc.shape[1], self.lr_gc,
                                 0.9, 0.999, 1e-8, ptr(self.adam_steps), st)
-        if self.peer is not None:
-            pe = self.peer
-            L.grapes_allreduce_adam_peer(ctx, pe.peer_ptrs, pe.rank, pe.world, ptr(self.grads), self.n_par,
-                                         ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq),
-                                         nc.base, nc.size, self.lr_gc, gf.base, n1, self.lr_gf, 0.9, 0.999, 1e-8,
-                                         ptr(self.adam_steps), ptr(pe.state), ptr(self.overflow), st)
+        if self.dp_group is not None:
+            import torch.distributed as dist
+            if scale:
+                L.grapes_gfn_finalize_scale(ctx, ptr(self.scal), self.loss_coef, self.log_z_init, int(self.reinforce), 1,
+                                            self._dir(gf.base), gf.size, self._grd(gf.base),
+                                            self._dir(nz.base), n_z, self._grd(nz.base), st)
+            dist.all_reduce(self.grads, op=dist.ReduceOp.AVG, group=self.dp_group)
+            L.grapes_adam_step2(ctx, ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                                nc.base, nc.size, self.lr_gc, gf.base, n1, self.lr_gf, 0.9, 0.999, 1e-8,
+                                ptr(self.adam_steps), st)
             return
-        L.grapes_adam_step2(ctx, ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq),
-                            nc.base, nc.size, self.lr_gc, gf.base, n1, self.lr_gf, 0.9, 0.999, 1e-8,
-                            ptr(self.adam_steps), st)
+        pe = self.peer
+        L.grapes_step_tail(ctx, ptr(self.scal), int(scale), self.loss_coef, self.log_z_init, int(self.reinforce), 1,
+                           ptr(self.gdir), gf.base, gf.size if scale else 0, nz.base, n_z if scale else 0,
+                           pe.peer_ptrs if pe is not None else None, pe.rank if pe is not None else 0,
+                           pe.world if pe is not None else 1, self.n_par, ptr(self.params), ptr(self.grads),
+                           ptr(self.exp_avg), ptr(self.exp_avg_sq), nc.base, nc.size, self.lr_gc, gf.base, n1, self.lr_gf,
+                           0.9, 0.999, 1e-8, ptr(self.adam_steps), ptr(pe.state if pe is not None else self.tail_state),
+                           ptr(self.overflow), st)
 
     # ------------------------------------------------------------------ public API
     def set_targets(self, target_nodes: torch.Tensor, state: Optional[int] = None):
@@ -854,11 +979,23 @@ class GrapesEngine:
             return self._record_all(rec)
         return None
 
-    def check_overflow(self):
-        v = int(self.overflow.item())
+    @staticmethod
+    def raise_on_flags(v: int):
+        """GRAPES_OVF_* bits of a step (``scalars()['flags']`` / the ``overflow`` word) -> GrapesError"""
+        v = int(v)
         if v:
             names = [n for b, n in OVF_NAMES.items() if v & b]
+            if v & 32:
+                raise GrapesError("data-parallel exchange failed (" + ", ".join(names) + "): the step was not applied")
             raise GrapesError("frontier capacity exceeded (" + ", ".join(names) + "): raise cap_edges / cap_nodes")
+
+    def check_overflow(self):
+        self.raise_on_flags(int(self.overflow.item()))
+
+    def sampler_stats(self) -> List[Dict[str, float]]:
+        """per-hop statistics of the last step's sampler (utils.py:62-69; what main.py:304-308 logs); syncs"""
+        s = self.stats.cpu()
+        return [{k: float(s[h, i]) for i, k in enumerate(STAT_NAMES)} for h in range(self.H)]
 
     def scalars(self) -> Dict[str, float]:
         s = self.scal.cpu()

@@ -5,10 +5,12 @@ same two modes, same return ``(accuracy, f1)``.
   whole graph.  The reference moves the model to the CPU for this (``eval_on_cpu=True``, main.py:43); here it stays
   on the B200 -- the whole-graph aggregation is ``grapes_aggregate`` (TMA-staged SpMM, csrc/spmm_tma.cu) on the
   gcn_norm structure of the full CSR (:class:`grapes_b200.gcn.GraphNorm`, built once and cached on the graph).
-* ``full_batch=False`` (eval.py:71-163): the hop loop with DETERMINISTIC top-k on the probabilities
-  (eval.py:126-130) and -- differently from training -- ``slice_adjacency(rows=previous_nodes, cols=batch_nodes)``
-  (eval.py:140-142).  Built from the same drop-in pieces as the training path (``get_neighborhoods``,
-  ``slice_adjacency``, ``TensorMap``, ``GCN``, the selection kernel in ``GRAPES_NOISE_NONE_TOPK_PROBS`` mode).
+* ``full_batch=False`` (eval.py:71-163): every batch runs on the training engine's kernels, forward only
+  (``GrapesEngine.predict``): frontier expansion, bitmap dedup / relabel, fused gather + aggregation, the sampler GCN's
+  tcgen05 forward, DETERMINISTIC top-k on the probabilities (eval.py:126-130, ``GRAPES_NOISE_NONE_TOPK_PROBS``), the
+  evaluation's block direction ``slice_adjacency(rows=previous_nodes, cols=batch_nodes)`` (eval.py:140-142, a filter of
+  the hop's own row expansion), classifier forward, argmax of the target rows.  Batches are enqueued back to back
+  (CUDA-graph replays); the host synchronises once, after the last batch.
 
 ``eval_on_cpu`` is accepted for signature compatibility and ignored: there is no CPU fallback (north_star).
 sklearn's accuracy / micro-F1 on single-label predictions are both the fraction of correct predictions, computed
@@ -23,8 +25,7 @@ import torch
 from ._lib import GrapesError
 from .gcn import GCN, GraphNorm
 from .graph import DeviceGraph
-from .utils import (NOISE_TOPK_PROBS, TensorMap, get_logger, get_neighborhoods, sample_neighborhoods_from_probs,
-                    slice_adjacency)
+from .utils import TensorMap, get_logger
 
 
 def _graph_norm(adjacency: DeviceGraph, data) -> GraphNorm:
@@ -67,6 +68,7 @@ def evaluate(gcn_c: GCN,
              loader=None,
              full_batch: bool = False,
              return_predictions: bool = False,
+             engine=None,
              ):
     get_logger().info('Evaluating')
     device = torch.device(device)
@@ -82,65 +84,41 @@ def evaluate(gcn_c: GCN,
         res = _scores(logits_total[mask_d], y[mask_d])
         return (res + (logits_total,)) if return_predictions else res
 
-    # ---- mini-batch message passing (eval.py:71-163) ----
+    # ---- mini-batch message passing (eval.py:71-163) on the engine's device path ----
     assert loader is not None, 'loader must be provided if full_batch is False'
-    gcn_gf = gcn_gf.to(device).eval()
-    N = data.num_nodes
-    if node_map is None:
-        node_map = TensorMap(size=N, device=device)
-    prev_nodes_mask = torch.zeros(N, dtype=torch.bool, device=device)
-    batch_nodes_mask = torch.zeros(N, dtype=torch.bool, device=device)
-    indicator_features = torch.zeros((N, num_indicators), device=device)
-    values = torch.arange(N, device=device)
-    all_predictions = []
-    for batch_id, batch in enumerate(loader):
-        target_nodes = batch[0].to(device)
-        previous_nodes = target_nodes.clone()
-        all_nodes_mask = torch.zeros_like(prev_nodes_mask)
-        all_nodes_mask[target_nodes] = True
-        indicator_features.zero_()
-        if num_indicators:
-            indicator_features[target_nodes, -1] = 1.0
-        global_edge_indices = []
-        for hop in range(args.sampling_hops):
-            neighborhoods = get_neighborhoods(previous_nodes, adjacency)                 # eval.py:94
-            prev_nodes_mask.zero_()
-            batch_nodes_mask.zero_()
-            prev_nodes_mask[previous_nodes] = True
-            batch_nodes_mask[neighborhoods.view(-1)] = True
-            neighbor_nodes_mask = batch_nodes_mask & ~prev_nodes_mask
-            batch_nodes = values[batch_nodes_mask]
-            neighbor_nodes = values[neighbor_nodes_mask]
-            if num_indicators:
-                indicator_features[neighbor_nodes, hop] = 1.0
-            node_map.update(batch_nodes)
-            local_neighborhoods = node_map.map(neighborhoods)
-            if args.use_indicators:
-                xb = torch.cat([x[batch_nodes], indicator_features[batch_nodes]], dim=1)
-            else:
-                xb = x[batch_nodes]
-            if neighbor_nodes.numel() > 0:
-                node_logits, _ = gcn_gf(xb, local_neighborhoods)                         # eval.py:121
-                node_logits = node_logits[node_map.map(neighbor_nodes)]
-                # torch.topk(Bernoulli(logits).probs, k=min(c, num_samples)) -> ids ascending (eval.py:126-130)
-                k = min(int(neighbor_nodes.size(0)), int(args.num_samples))
-                sampled_neighboring_nodes, _, _ = sample_neighborhoods_from_probs(
-                    node_logits, neighbor_nodes, k, noise_mode=NOISE_TOPK_PROBS)
-            else:
-                sampled_neighboring_nodes = neighbor_nodes
-            all_nodes_mask[sampled_neighboring_nodes] = True
-            batch_nodes = torch.cat([target_nodes, sampled_neighboring_nodes], dim=0)
-            k_hop_edges = slice_adjacency(adjacency, rows=previous_nodes, cols=batch_nodes)   # eval.py:140-142
-            global_edge_indices.append(k_hop_edges)
-            previous_nodes = batch_nodes.clone()
-        all_nodes = values[all_nodes_mask]
-        node_map.update(all_nodes)
-        edge_indices = [node_map.map(e) for e in global_edge_indices]
-        logits_total, _ = gcn_c(x[all_nodes], edge_indices)
-        predictions = torch.argmax(logits_total, dim=1)
-        predictions = predictions[node_map.map(target_nodes)]
-        all_predictions.append(predictions)
-    all_predictions = torch.cat(all_predictions) if all_predictions else torch.zeros(0, dtype=torch.long, device=device)
+    batches = [b[0] if isinstance(b, (tuple, list)) else b for b in loader]
+    eng = engine if engine is not None else _eval_engine(adjacency, data, args, gcn_c, gcn_gf, num_indicators, device,
+                                                         max([int(b.numel()) for b in batches] + [1]))
+    total = sum(int(b.numel()) for b in batches)
+    preds = torch.zeros(max(total, 1), dtype=torch.int32, device=device)
+    off = 0
+    for b in batches:                                                  # every batch is enqueued; nothing is read back
+        n = int(b.numel())
+        eng.predict(b.to(device), preds[off:off + n])
+        off += n
+    eng.check_overflow()                                               # the one synchronisation of the evaluation
+    all_predictions = preds[:total].to(torch.int64)
     targets = y[mask_d]
     acc = (all_predictions == targets).float().mean().item()          # accuracy_score == micro f1_score here
     return (acc, acc, all_predictions) if return_predictions else (acc, acc)
+
+
+def _eval_engine(adjacency: DeviceGraph, data, args, gcn_c: GCN, gcn_gf: GCN, num_indicators: int, device, batch_size: int):
+    """Engine for a stand-alone ``evaluate(..., full_batch=False)`` call (the training loop passes its own): built once
+    per (graph, features, shape) and cached on the graph object; the modules' weights are loaded on every call."""
+    from .engine import GrapesEngine
+    D = int(gcn_c.gcn_layers[0].lin.weight.shape[0])
+    C = int(gcn_c.gcn_layers[-1].lin.weight.shape[0])
+    x = data.x.to(device).contiguous()
+    key = (x.data_ptr(), tuple(x.shape), D, C, int(batch_size), int(args.num_samples), int(args.sampling_hops),
+           bool(num_indicators))
+    cached = getattr(adjacency, "_eval_engine", None)
+    if cached is None or cached[0] != key:
+        eng = GrapesEngine(adjacency, x, data.y.to(device), num_classes=C, batch_size=int(batch_size),
+                           num_samples=int(args.num_samples), sampling_hops=int(args.sampling_hops),
+                           use_indicators=bool(num_indicators), hidden_dim=D)
+        cached = (key, eng)
+        adjacency._eval_engine = cached
+    eng = cached[1]
+    eng.load_state_dicts(gcn_c=gcn_c.state_dict(), gcn_gf=gcn_gf.state_dict())
+    return eng

@@ -18,6 +18,8 @@ def _require_cuda(device) -> torch.device:
     device = torch.device(device)
     if device.type != "cuda" or not torch.cuda.is_available():
         raise GrapesError("grapes_b200 has no CPU fallback: a CUDA (sm_100a) device is required")
+    if device.index is None:                         # torch.device('cuda') means the CURRENT device, not device 0
+        device = torch.device("cuda", torch.cuda.current_device())
     return device
 
 
@@ -71,7 +73,7 @@ class DeviceGraph:
         self._ctx = ctypes.c_void_p()
         self._extra = []
         L = lib()
-        rc = L.cdll.grapes_ctx_create(device.index or 0, self.num_nodes, self.max_frontier, partials_bytes,
+        rc = L.cdll.grapes_ctx_create(device.index, self.num_nodes, self.max_frontier, partials_bytes,
                                       ctypes.byref(self._ctx))
         if rc != 0:
             raise GrapesError(f"grapes_ctx_create failed ({rc}): {L.last_error()}")
@@ -85,7 +87,7 @@ class DeviceGraph:
         (a ctx owns the scan / split-K scratch and is not re-entrant)."""
         c = ctypes.c_void_p()
         L = lib()
-        rc = L.cdll.grapes_ctx_create(self.device.index or 0, self.num_nodes, self.max_frontier, partials_bytes,
+        rc = L.cdll.grapes_ctx_create(self.device.index, self.num_nodes, self.max_frontier, partials_bytes,
                                       ctypes.byref(c))
         if rc != 0:
             raise GrapesError(f"grapes_ctx_create failed ({rc}): {L.last_error()}")

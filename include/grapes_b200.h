@@ -57,6 +57,7 @@ extern "C" {
 #define GRAPES_SCAL_G_GF 5
 #define GRAPES_SCAL_G_Z 6
 #define GRAPES_SCAL_SUM_DL 7
+#define GRAPES_SCAL_FLAGS 15   /* GRAPES_OVF_* bits seen by the step's tail launch, as an integer-valued float */
 #define GRAPES_SCAL_COUNT 16
 
 typedef struct grapes_ctx grapes_ctx;
@@ -73,6 +74,9 @@ int grapes_ctx_set_sm_limit(grapes_ctx* ctx, int sms);
 int grapes_ctx_destroy(grapes_ctx* ctx);
 const char* grapes_last_error(void);
 int grapes_abi_version(void);
+/* sha1 over the library's sources + this header at build time: the host loader compares it with the tree it parses its
+ * prototypes from and refuses (or rebuilds) a binary that does not match                                                */
+const char* grapes_build_id(void);
 /* programmatic dependent launch between consecutive kernels of a stream: bit mask over the library's source files
  * (1 frontier, 2 gcn, 4 gemm_tc, 8 loss_optim, 16 select) whose kernels may start before their predecessor ends;
  * 0 = plain stream order */
@@ -130,10 +134,13 @@ int grapes_hop_structure(grapes_ctx* ctx, const uint32_t* bm_batch, const uint32
                          int* cnt_scratch, int* in_off, int* in_src, int* tmp_val, float* dinv, int* nnz_dev,
                          int* overflow, void* stream);
 /* node_map.map(neighborhoods) (main.py:195): local (src, dst) of every expanded edge.  cnt_hist
- * (optional, all-zero on entry) receives the in-degree histogram grapes_build_csr(hist_done=1) needs. */
+ * (optional, all-zero on entry) receives the in-degree histogram grapes_build_csr(hist_done=1) needs.
+ * cap_n = capacity of every node-indexed buffer downstream (cnt_hist, in_off, dinv, Y ...): when the frontier holds
+ * more nodes than that (GRAPES_OVF_NODES, raised by grapes_rank_nodes) an edge touching a node past the capacity is
+ * written as the dropped self-edge (0, 0), so an overflowing step is flagged AND memory-safe.                       */
 int grapes_edges_to_local(grapes_ctx* ctx, const int* rows, const int* e_row, const int* e_col, const int* m_dev,
-                          int cap_m, const uint32_t* bm, const int* pref, int* e_src, int* e_dst, int* cnt_hist,
-                          void* stream);
+                          int cap_m, const uint32_t* bm, const int* pref, int cap_n, int* e_src, int* e_dst,
+                          int* cnt_hist, void* stream);
 /* TensorMap.map on an id list (main.py:213,253-254,259).                                          */
 int grapes_relabel(grapes_ctx* ctx, const int* ids, const int* count_dev, int cap, const uint32_t* bm,
                    const int* pref, int* out, void* stream);
@@ -192,6 +199,9 @@ int grapes_agg_tma_virtual_slot(int on);
 /* smallest row capacity (cap_n) whose aligned-width aggregation takes the TMA-staged form (default 4096; smaller launches
  * use one warp per row)                                                                                              */
 int grapes_agg_tma_min_rows(int rows);
+/* A/B knob of the measurement scripts: 0 (default) = shape chosen by the launcher; 1..6 = a register-staged kernel,
+ * 100 + ec / 200 + ec = a forced TMA-staged shape (csrc/gcn.cu aggregate_impl).  Every variant is bitwise identical.   */
+int grapes_agg_variant(int v);
 int grapes_aggregate_bf16(grapes_ctx* ctx, const void* X_bf16, int F, int ldx, const int* nodes, const int* n_dev,
                           int cap_n, const int* in_off, const int* in_src, const float* dinv, const uint32_t* ind_bits,
                           int num_ind, const float* bias, int relu, float* out, int ldo, float* out_hi, float* out_lo,
@@ -234,6 +244,8 @@ int grapes_sampler_l1_bwd(grapes_ctx* ctx, const float* Y, int ldy, const int* n
  * zpart[D/128][cap_n] partial row dots; maskT[(rows/32)][D] relu mask bits (optional).                            */
 int grapes_split_tf32(grapes_ctx* ctx, const float* src, int ld_src, int R, int K, float* hi, float* lo, int ld_dst,
                       void* stream);
+/* measurement knob of the tcgen05 kernels (bit 1: stream the weight tiles instead of keeping them resident)           */
+int grapes_tc_debug(int flags);
 int grapes_sampler_l1_fwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo, int ldy, const int* n_dev, int cap_n,
                              int K, const float* W_hi, const float* W_lo, int ldw, int D, const float* b1,
                              const float* w2, float* zpart, uint32_t* maskT, void* stream);
@@ -277,6 +289,9 @@ int grapes_classifier_loss(grapes_ctx* ctx, const float* logits, int ldl, int C,
                            const float* labels_f32, float reg_param, float* dlogits, float* loss_out,
                            float* colsum_out /* optional: column sums of dlogits = d loss / d last bias */,
                            void* stream);
+/* out[i] = argmax_c logits[row_ids[i], c], i < *B_dev: predictions of the target rows (eval.py:152-153); ties -> lowest c */
+int grapes_argmax_rows(grapes_ctx* ctx, const float* logits, int ldl, int C, const int* row_ids, const int* B_dev,
+                       int cap_B, int* out, void* stream);
 int grapes_gfn_finalize(grapes_ctx* ctx, float* scal, float loss_coef, float log_z_init, int reinforce,
                         int have_log_z, void* stream);
 /* grapes_gfn_finalize + both grapes_scale_by_device_scalar calls (gcn_gf, gcn_z ranges) in one launch            */
@@ -302,19 +317,34 @@ int grapes_adam_embed(grapes_ctx* ctx, float* table, float* exp_avg, float* exp_
                       float beta1, float beta2, float eps, const float* step_dev, void* stream);
 int grapes_fill_f32(grapes_ctx* ctx, float* p, float value, int n, void* stream);
 
-/* ---- data-parallel exchange: gradient all-reduce (mean) + both Adam groups over NVLink peer memory ------------ */
-/* floats of symmetric buffer each rank must provide for an n-float gradient (two slots + flag words)              */
-int64_t grapes_peer_buffer_floats(int n);
-/* Publishes `grads` into this rank's symmetric buffer, waits (bounded) for every peer, sums the `world` slots in rank
- * order over NVLink, divides by `world`, applies grapes_adam_step2's arithmetic and writes the mean gradient to
- * grads_mean_out.  peer_bufs: HOST array of `world` peer-mapped device pointers (own buffer at index `rank`), zeroed
- * once; state: 4 device uint32, zeroed once; err_flag receives GRAPES_OVF_PEER_TIMEOUT instead of a hang.  Two launches,
- * no per-step host argument: capturable into the step's CUDA graph (main.py:268,289 on the mean of the per-rank
- * gradients; the reference itself is single-process).                                                              */
+/* ---- step tail: gradient scale + data-parallel exchange + both Adam groups in ONE launch -------------------------- */
+/* floats of symmetric buffer each rank must provide for an n-float gradient exchanged among `world` ranks
+ * (2 parities x world slots + flag words), and the uint32 words of device state of one exchange endpoint        */
+int64_t grapes_peer_buffer_floats(int n, int world);
+int grapes_peer_state_words(void);
+/* Mean all-reduce over NVLink peer memory + grapes_adam_step2's arithmetic, one launch, no per-step host argument
+ * (capturable into the step's CUDA graph; main.py:268,289 on the mean of the per-rank gradients -- the reference itself
+ * is single-process).  Every rank WRITES its gradient into its slot of every rank's buffer, signals, waits (bounded) for
+ * all peers' signals, then sums its own buffer's slots in rank order: identical bits on every rank.  peer_bufs: HOST array
+ * of `world` peer-mapped device pointers (own buffer at index `rank`), zeroed once; state: grapes_peer_state_words()
+ * device uint32, zeroed once.  grads_mean_out must be `grads` (the mean replaces it in place).  A peer that never arrives
+ * raises GRAPES_OVF_PEER_TIMEOUT in *err_flag and the step is a NO-OP on this rank (parameters, moments, step counts
+ * untouched); the failure is sticky: every later call is a no-op too.                                                  */
 int grapes_allreduce_adam_peer(grapes_ctx* ctx, void* const* peer_bufs, int rank, int world, const float* grads, int n,
                                float* params, float* grads_mean_out, float* exp_avg, float* exp_avg_sq, int off0,
                                int n0, float lr0, int off1, int n1, float lr1, float beta1, float beta2, float eps,
                                float* steps_dev, unsigned int* state, int* err_flag, void* stream);
+/* The whole tail of a training step (main.py:271-291) in one launch: grapes_gfn_finalize_scale's arithmetic when
+ * do_scale != 0 (`dir` is indexed like the flat parameter buffer; ranges [gf_off, gf_off + n_gf), [z_off, z_off + n_z)),
+ * the exchange above when peer_bufs != NULL and world > 1, then both Adam groups.  `grads` [n] holds the classifier
+ * gradient on entry and the step's (mean) gradient of every parameter on exit.  scal[GRAPES_SCAL_FLAGS] receives the
+ * bits of *err_flag (GRAPES_OVF_*) as an integer-valued float, so the 64-byte loss read-back of a step also carries its
+ * overflow / peer-failure verdict.  state: grapes_peer_state_words() device uint32 (needed with or without peers).      */
+int grapes_step_tail(grapes_ctx* ctx, float* scal, int do_scale, float loss_coef, float log_z_init, int reinforce,
+                     int have_log_z, const float* dir, int gf_off, int n_gf, int z_off, int n_z, void* const* peer_bufs,
+                     int rank, int world, int n, float* params, float* grads, float* exp_avg, float* exp_avg_sq, int off0,
+                     int n0, float lr0, int off1, int n1, float lr1, float beta1, float beta2, float eps, float* steps_dev,
+                     unsigned int* state, int* err_flag, void* stream);
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,7 @@ Pinning status:
   * integer path (get_neighborhoods, slice_adjacency, TensorMap, mask dedup) and
     sample_neighborhoods_from_probs: PINNED against the reference's own
     ``modules/utils.py`` imported from /root/reference (oracle/ref_import.py,
-    oracle/validate_against_reference.py) and against the committed fixtures in
+    tests/test_oracle.py::test_oracle_matches_live_reference) and against the committed fixtures in
     tests/golden/ produced by tests/golden/make_golden.py from that import, and
     against the only known-answer vector the reference holds (TensorMap
     docstring, utils.py:104-108).

@@ -10,15 +10,9 @@ import torch
 
 from grapes_b200.synth import make_synth
 from oracle import reference_port as rp
+from parity_utils import TOL, _rel, check_step as _check_step
 
 pytestmark = pytest.mark.gpu
-TOL = 1e-5
-
-
-def _rel(got, ref):
-    ref = torch.as_tensor(ref).double()
-    got = torch.as_tensor(got).double().cpu()
-    return ((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30)).item()
 
 
 def _setup(name, seed, dev, use_tensor_cores=False, **kw):
@@ -34,6 +28,7 @@ def _setup(name, seed, dev, use_tensor_cores=False, **kw):
     feature_bf16 = kw.pop("feature_bf16", False)
     if feature_bf16:                     # the table is STORED in bf16; the oracle computes on exactly those values
         d.x = d.x.bfloat16().float()
+    eng_kw = {k: kw.pop(k) for k in ("cap_nodes", "cap_edges", "cap_block", "multi_stream") if k in kw}   # engine only
     hp = dict(sampling_hops=cfg["sampling_hops"], num_samples=cfg["num_samples"])
     hp.update(kw)
     hidden = hp.pop("hidden_dim", 256)
@@ -44,91 +39,10 @@ def _setup(name, seed, dev, use_tensor_cores=False, **kw):
     eng = GrapesEngine(g, d.x.to(dev).bfloat16() if feature_bf16 else d.x.to(dev), d.y.to(dev),
                        num_classes=d.num_classes, batch_size=cfg["batch_size"],
                        hidden_dim=st.gcn_c.gcn_layers[0].lin.weight.shape[0],
-                       lr_gc=1e-3, lr_gf=1e-4, seed=seed, use_tensor_cores=use_tensor_cores, **hp)
+                       lr_gc=1e-3, lr_gf=1e-4, seed=seed, use_tensor_cores=use_tensor_cores, **eng_kw, **hp)
     eng.load_state_dicts(gcn_c=st.gcn_c.state_dict(), gcn_gf=st.gcn_gf.state_dict(), gcn_z=st.gcn_z.state_dict())
     train_idx = d.train_mask.nonzero().squeeze(1)
     return d, st, eng, train_idx, cfg["batch_size"]
-
-
-def _grad_tol(got32, ref64, floor=TOL):
-    """Gradients are sums of O(frontier) signed terms; their fp32 conditioning is a property of the
-    problem, not of the kernel.  Bar: 1e-5 relative, or -- when the reference's own fp32 evaluation
-    (same path, CPU torch) is already further than that from float64 -- no worse than 2x the reference."""
-    return max(floor, 2.0 * _rel(got32, ref64))
-
-
-def _grad_ok(got, ref64, ref32, relaxed, floor=TOL):
-    """strict: elementwise bar.  relaxed (tensor-core path): a hidden unit whose pre-activation sits within fp32
-    noise of the relu kink may take the other branch than float64 did (so can the reference's own fp32 run); such
-    a flip moves ONE row of the weight gradient.  Allow <= 3 outlier rows, bounded, and hold all others to the bar."""
-    tol = _grad_tol(ref32, ref64, floor)
-    ref = torch.as_tensor(ref64).double()
-    err = (torch.as_tensor(got).double().cpu() - ref).abs() / ref.abs().max().clamp_min(1e-30)
-    if not relaxed:
-        return bool(err.max() < tol)
-    rows = err.reshape(err.shape[0], -1).max(1).values if err.dim() > 1 else err
-    bad = rows > 3 * tol
-    return bool(bad.sum() <= 3 and err.max() < 2e-2)
-
-
-def _check_step(st, eng, targets, dev, apply_optim=True, relaxed=False, post_optim=False):
-    # first step: the 1e-5 bar.  After an Adam step the weights carry fp32 history (Adam divides by sqrt(v), which
-    # amplifies the rounding noise of small gradient entries): floats are then held to the 1e-4 bar that
-    # test_three_steps_with_adam holds the weights themselves to; integer contracts stay bit-exact.
-    FT = 1e-4 if post_optim else TOL
-    ref = rp.reference_step(st, targets, apply_optim=apply_optim)
-    ref32 = rp.reference_step(st.fp32, targets, gumbel_noise=[h["noise"] for h in ref["hops"]], apply_optim=apply_optim)
-    for a, b in zip(ref32["hops"], ref["hops"]):
-        assert torch.equal(a["sampled"], b["sampled"]), "fp32 / fp64 oracle disagree on the sampled set: pick another seed"
-    for h in ref["hops"]:                     # the selection must be well separated for a bit-exact set claim
-        if h["keys"] is not None:
-            srt = torch.sort(h["keys"], descending=True).values
-            k = h["sampled"].numel()
-            assert (srt[k - 1] - srt[k]) > 1e-4 * srt[:k + 1].abs().max(), "pick another seed: top-k boundary too tight"
-    noise = [None if h["noise"] is None else h["noise"].float().to(dev) for h in ref["hops"]]
-    rec = eng.step(targets.to(dev), gumbel_noise=noise, apply_optim=apply_optim, record=True)
-    eng.check_overflow()
-    for h, (a, b) in enumerate(zip(rec["hops"], ref["hops"])):
-        # ---- integer contracts: bit-exact ----
-        assert torch.equal(a["prev"].cpu().long(), b["prev"]), f"hop {h} prev"
-        assert torch.equal(a["batch_nodes"].cpu().long(), b["batch_nodes"]), f"hop {h} batch_nodes"
-        assert torch.equal(a["neighbor_nodes"].cpu().long(), b["neighbor_nodes"]), f"hop {h} neighbor_nodes"
-        assert torch.equal(a["nb_local"].cpu().long(), b["nb_local"]), f"hop {h} nb_local"
-        loc = torch.stack([a["e_src"], a["e_dst"]]).cpu().long()
-        assert torch.equal(loc, b["local_neighborhoods"]), f"hop {h} local edges"
-        glob = torch.stack([a["prev"].long()[a["e_row"].long()], a["e_col"].long()]).cpu()
-        assert torch.equal(glob, b["neighborhoods"]), f"hop {h} neighborhoods"
-        assert torch.equal(a["block_edges"].cpu().long(), b["block_edges"]), f"hop {h} block edges"
-        assert torch.equal(a["sampled"].cpu().long(), b["sampled"]), f"hop {h} sampled set"
-        # ---- floating point: 1e-5 relative ----
-        if not st.random_sampling:
-            ei, w = rp.gcn_norm(b["local_neighborhoods"], b["x"].shape[0], dtype=torch.float64)
-            y_ref = torch.zeros_like(b["x"]).index_add(0, ei[1], b["x"][ei[0]] * w.unsqueeze(1))
-            assert _rel(a["Y"][:, :y_ref.shape[1]], y_ref) < FT, f"hop {h} aggregated features"
-            assert _rel(a["logits_all"], b["logits_all"]) < FT, f"hop {h} logits"
-        assert _rel(a["log_prob"], b["log_prob"]) < FT, f"hop {h} log_prob"
-        if b["stats"]:
-            for i, key in enumerate(("min_prob", "max_prob", "mean_entropy", "std_entropy")):
-                assert abs(a["stats"][i].item() - b["stats"][key].item()) < 1e-4 * max(1.0, abs(b["stats"][key].item()))
-    assert torch.equal(rec["all_nodes"].cpu().long(), ref["all_nodes"])
-    assert torch.equal(rec["target_local"].cpu().long(), ref["local_target_ids"])
-    assert torch.equal(rec["cl_edges"][0].cpu().long(), ref["edge_indices"][-1])
-    assert torch.equal(rec["cl_edges"][1].cpu().long(), ref["edge_indices"][0])
-    assert _rel(rec["logits_c"], ref["logits_c"]) < FT
-    s = rec["scalars"]
-    assert abs(s["loss_c"] - ref["loss_c"].item()) < FT * abs(ref["loss_c"].item())
-    assert abs(s["tot_log_prob"] - ref["tot_log_prob"].item()) < FT * abs(ref["tot_log_prob"].item())
-    for name, gref in ref["grads_c"].items():
-        assert _grad_ok(rec["grads"]["gcn_c"][name], gref, ref32["grads_c"][name], False, FT), f"grad gcn_c {name}"
-    if not st.random_sampling:
-        assert abs(s["log_z"] - ref["log_z"].item()) < FT * max(1.0, abs(ref["log_z"].item()))
-        assert abs(s["loss_gfn"] - ref["loss_gfn"].item()) < 4 * FT * abs(ref["loss_gfn"].item())
-        for name, gref in ref["grads_gf"].items():
-            assert _grad_ok(rec["grads"]["gcn_gf"][name], gref, ref32["grads_gf"][name], relaxed, FT), f"grad gcn_gf {name}"
-        for name, gref in ref["grads_z"].items():
-            if gref is not None:
-                assert _grad_ok(rec["grads"]["gcn_z"][name], gref, ref32["grads_z"][name], relaxed, FT), f"grad gcn_z {name}"
-    return rec, ref
 
 
 @pytest.mark.parametrize("name,seed", [("tiny", 0), ("cora", 0), ("small", 1)])
@@ -143,7 +57,7 @@ def test_step_parity_feature_width_not_multiple_of_4(cuda_device, F, use_tc):
     aggregation (frontier >= 4096 rows here) carries a partial last feature lane.  Same bars as every other step test."""
     d, st, eng, train_idx, B = _setup("small", 1, cuda_device, use_tensor_cores=use_tc, F=F)
     assert eng.ldx == (F + 3) // 4 * 4 and eng.cap_n >= 4096 and tuple(eng.x.shape) == (d.num_nodes, F)
-    _check_step(st, eng, train_idx[:B], cuda_device, apply_optim=False, relaxed=use_tc)
+    _check_step(st, eng, train_idx[:B], cuda_device, apply_optim=False)
 
 
 @pytest.mark.parametrize("use_tc", [False, True])
@@ -153,7 +67,7 @@ def test_step_parity_power_law_hub_rows(cuda_device, use_tc):
     d, st, eng, train_idx, B = _setup("small", 5, cuda_device, use_tensor_cores=use_tc, power_law=1.5)
     deg = torch.bincount(d.edge_index[0], minlength=d.num_nodes)
     assert int(deg.max()) > 1000 and int((deg == 0).sum()) > 0
-    _check_step(st, eng, train_idx[:B], cuda_device, apply_optim=False, relaxed=use_tc)
+    _check_step(st, eng, train_idx[:B], cuda_device, apply_optim=False)
 
 
 @pytest.mark.parametrize("name,seed", [("tiny", 0), ("small", 1), ("small", 2), ("cora", 0)])
@@ -162,7 +76,7 @@ def test_tensor_core_engine_step_parity(cuda_device, name, seed):
     bit-exact, logits / losses hold the 1e-5 bar, gradients hold it up to relu-kink flips (see _grad_ok)."""
     d, st, eng, train_idx, B = _setup(name, seed, cuda_device, use_tensor_cores=True)
     assert eng.use_tc and eng.use_tc_bwd
-    _check_step(st, eng, train_idx[:B], cuda_device, apply_optim=False, relaxed=True)
+    _check_step(st, eng, train_idx[:B], cuda_device, apply_optim=False)
 
 
 def test_tensor_core_engine_matches_simt_engine(cuda_device):
@@ -268,18 +182,22 @@ def test_take_all_branch_in_step(cuda_device):
 
 
 def test_graph_replay_matches_eager(cuda_device):
-    """The captured CUDA graph replays the same kernels: bitwise-identical weights."""
-    from grapes_b200.engine import GrapesEngine
+    """The captured CUDA graph replays the same kernels: bitwise-identical weights, gradients and losses.  The eager
+    warm-up before the first capture restores the Philox state, so both engines draw the same noise."""
     d, st, eng, train_idx, B = _setup("cora", 0, cuda_device)
     d2, st2, eng2, _, _ = _setup("cora", 0, cuda_device)
     for i in range(2):
         t = train_idx[i * B:(i + 1) * B].to(cuda_device)
         eng.step(t, use_graph=False)
         eng2.step(t, use_graph=True)
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        assert torch.equal(eng.scal, eng2.scal), f"step {i}: losses differ between eager and graph replay"
+        assert torch.equal(eng.all_nodes, eng2.all_nodes)
     eng.check_overflow(); eng2.check_overflow()
-    # the eager warm-up before capture consumed one Philox offset; compare a noise-free quantity
-    assert eng.scalars().keys() == eng2.scalars().keys()
+    assert torch.equal(eng.rng_state, eng2.rng_state)
+    assert torch.equal(eng.grads, eng2.grads)
+    assert torch.equal(eng.params, eng2.params)
+    assert torch.equal(eng.exp_avg_sq, eng2.exp_avg_sq)
     assert eng2.count("A") > B
 
 
@@ -345,7 +263,7 @@ def test_step_parity_bf16_feature_table(cuda_device, name, seed, tc):
     finally:
         SHAPES.pop("mid16", None)
     assert eng.x_bf16
-    _check_step(st, eng, train_idx[:B], cuda_device, apply_optim=False, relaxed=tc)
+    _check_step(st, eng, train_idx[:B], cuda_device, apply_optim=False)
 
 
 def test_fused_hop_structure_kernel_is_bit_identical(cuda_device):
@@ -367,3 +285,33 @@ def test_fused_hop_structure_kernel_is_bit_identical(cuda_device):
     for net in r0["grads"]:
         for name in r0["grads"][net]:
             assert torch.equal(r0["grads"][net][name], r1["grads"][net][name]), (net, name)
+
+
+def test_node_capacity_overflow_is_flagged_and_memory_safe(cuda_device):
+    """A caller-chosen cap_nodes smaller than the frontier: the step must raise GRAPES_OVF_NODES (in the overflow word and
+    in the step's flag scalar) and stay inside every buffer -- checked under compute-sanitizer when the tool is on the box."""
+    import os
+    import shutil
+    import subprocess
+    import sys
+    from grapes_b200._lib import GrapesError
+    d, st, eng, train_idx, B = _setup("small", 1, cuda_device, use_tensor_cores=True, cap_nodes=700)
+    assert eng.cap_n == 700
+    eng.step(train_idx[:B].to(cuda_device), apply_optim=True)
+    torch.cuda.synchronize()
+    assert int(eng.overflow.item()) & 4
+    assert int(eng.scalars()["flags"]) & 4                      # the tail launch copies the bits next to the losses
+    with pytest.raises(GrapesError, match="nodes>cap_n"):
+        eng.check_overflow()
+    tool = shutil.which("compute-sanitizer") or "/usr/local/cuda/bin/compute-sanitizer"
+    if not os.path.isfile(tool):
+        pytest.skip("compute-sanitizer not on this box (flag + no crash checked above)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, torch; sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests');"
+            "import test_gpu_engine as E; dev = torch.device('cuda:0');"
+            "d, st, eng, tr, B = E._setup('small', 1, dev, use_tensor_cores=False, cap_nodes=700, multi_stream=False);"
+            "eng.step(tr[:B].to(dev), apply_optim=True); torch.cuda.synchronize();"
+            "assert int(eng.overflow.item()) & 4; print('SANITIZED')") % (root, root)
+    res = subprocess.run([tool, "--error-exitcode", "9", "--launch-timeout", "0", sys.executable, "-c", code],
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0 and "SANITIZED" in res.stdout, res.stdout[-3000:] + res.stderr[-2000:]

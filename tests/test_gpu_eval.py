@@ -104,3 +104,62 @@ def test_mini_batch_eval_matches_oracle(cuda_device, name, seed, bs):
                              loader=loader, full_batch=False, return_predictions=True)
     assert torch.equal(pred.cpu(), ref["predictions"])
     assert abs(acc - ref["accuracy"]) < 1e-6 and acc == f1
+
+
+@pytest.mark.parametrize("name,seed,bs,tc", [("tiny", 0, 32, False), ("small", 1, 128, True), ("small", 2, 100, True)])
+def test_mini_batch_eval_engine_path_bit_exact_per_hop(cuda_device, name, seed, bs, tc):
+    """The evaluator's batch body on the engine (GrapesEngine.predict, eval.py:84-153): per hop the candidate list, the
+    deterministic top-k set and the block in the EVALUATION direction (rows = previous_nodes, cols = targets u sampled,
+    eval.py:140-142) bit-exact against the oracle; classifier logits at 1e-5; eager launches == graph replay."""
+    from grapes_b200.engine import GrapesEngine
+    cfg, d, st, g, gcn_c, gcn_gf, args = _setup(name, seed, cuda_device)
+    dev = cuda_device
+    mask = d.val_mask
+    ref = rp.reference_evaluate(st, mask, full_batch=False, batch_size=bs)
+    eng = GrapesEngine(g, d.x.to(dev), d.y.to(dev), num_classes=d.num_classes, batch_size=bs,
+                       num_samples=cfg["num_samples"], sampling_hops=cfg["sampling_hops"], use_tensor_cores=tc)
+    eng.load_state_dicts(gcn_c=st.gcn_c.state_dict(), gcn_gf=st.gcn_gf.state_dict())
+    idx = mask.nonzero().squeeze(1)
+    out = torch.zeros(bs, dtype=torch.int32, device=dev)
+    out_g = torch.zeros(bs, dtype=torch.int32, device=dev)
+    for bi, t in enumerate(torch.split(idx, bs)):
+        b = int(t.numel())
+        eng.predict(t.to(dev), out, use_graph=False)
+        torch.cuda.synchronize()
+        eng.check_overflow()
+        rb = ref["batches"][bi]
+        sizes = eng.hop_sizes()
+        for h, (sz, rh) in enumerate(zip(sizes, rb["hops"])):
+            hw = eng.hops[h]
+            assert torch.equal(hw.nb_nodes[:sz["c"]].cpu().long(), rh["neighbor_nodes"]), f"batch {bi} hop {h}: candidates"
+            assert torch.equal(eng.prev[h + 1][b:b + sz["s"]].cpu().long(), rh["sampled"]), f"batch {bi} hop {h}: top-k set"
+            blk = torch.stack([hw.blk_src[:sz["blk"]], hw.blk_dst[:sz["blk"]]]).cpu().long()
+            assert torch.equal(blk, rh["block_edges"]), f"batch {bi} hop {h}: block (rows = previous_nodes)"
+        A = eng.count("A")
+        assert torch.equal(eng.all_nodes[:A].cpu().long(), rb["all_nodes"])
+        _close(eng.logits_c[:A], rb["logits"])
+        eng.predict(t.to(dev), out_g, use_graph=True)
+        torch.cuda.synchronize()
+        assert torch.equal(out[:b], out_g[:b]), "graph replay differs from eager launches"
+
+
+def test_train_mini_batch_eval_uses_configured_batch_size(cuda_device):
+    """main.py:127-132 builds val_loader / test_loader with args.batch_size -- NOT the size of the last (partial) training
+    batch.  After training on a split that is not a multiple of batch_size, the mini-batch evaluation of train() must
+    equal the oracle's evaluation of the SAME weights with batch_size = args.batch_size."""
+    from grapes_b200.args import Arguments
+    from grapes_b200.synth import make_synth
+    from grapes_b200 import train as T
+    d = make_synth("tiny", seed=5)
+    assert int(d.train_mask.sum()) % 32 != 0
+    args = Arguments.parse_args(["--dataset", "tiny", "--batch_size", "32", "--num_samples", "8", "--sampling_hops", "2",
+                                   "--max_epochs", "1", "--eval_frequency", "5", "--eval_full_batch", "False",
+                                   "--eval_on_cpu", "False"])
+    f1, *_ = T.train(args, data=d, device=cuda_device)
+    eng = T.train.last_engine
+    assert eng.bsz != 32 and eng.B == 32                      # the last training batch was partial
+    st = rp.OracleState(d, sampling_hops=2, num_samples=8, seed=0, dtype=torch.float64)
+    sd = {k: {n: t.detach().cpu().double() for n, t in v.items()} for k, v in eng.state_dicts().items()}
+    st.gcn_c.load_state_dict(sd["gcn_c"]); st.gcn_gf.load_state_dict(sd["gcn_gf"])
+    ref = rp.reference_evaluate(st, d.test_mask, full_batch=False, batch_size=32)
+    assert abs(f1 - ref["f1"]) < 1e-6

@@ -20,3 +20,16 @@ def test_peer_allreduce_adam_matches_nccl_and_is_identical_across_ranks(cuda_dev
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert "peer exchange ok" in res.stdout
+
+
+def test_engine_data_parallel_step_equals_mean_of_oracle_gradients(cuda_device):
+    """scripts/check_dp_engine.py under torchrun: the engine's own exchange (peer-memory kernel and NCCL) against the
+    mean of the per-rank float64 oracle gradients, bit-identical parameters across ranks (eager and graph replay), and
+    the flagged / no-op / sticky behaviour when a peer never arrives."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29543", os.path.join(ROOT, "scripts", "check_dp_engine.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert "dp engine ok" in res.stdout
