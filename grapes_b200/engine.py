@@ -279,6 +279,8 @@ class GrapesEngine:
             self.L.cdll.grapes_agg_variant(int(os.environ["GRAPES_AGG_VARIANT"]))
         if os.environ.get("GRAPES_AGG_MIN_ROWS"):
             self.L.cdll.grapes_agg_tma_min_rows(int(os.environ["GRAPES_AGG_MIN_ROWS"]))
+        if os.environ.get("GRAPES_SELECT_VARIANT"):
+            self.L.cdll.grapes_select_variant(int(os.environ["GRAPES_SELECT_VARIANT"]))
         if os.environ.get("GRAPES_TC_DEBUG"):
             self.L.cdll.grapes_tc_debug(int(os.environ["GRAPES_TC_DEBUG"]))
 

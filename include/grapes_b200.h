@@ -260,8 +260,13 @@ int grapes_sampler_l1_bwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo,
 /* ---- selection (utils.py:13-71; eval.py:126-130) --------------------------------------------- */
 /* debugging aid: phase time stamps (globaltimer ns) of the last on-chip selection launch, HOST array of 16 */
 int grapes_debug_select_stamps(int64_t* out16);
-/* floats of scratch (`work`, 16-byte aligned) the two calls below need for cap_c candidates              */
+/* floats of scratch (`work`, 16-byte aligned, ZEROED ONCE by the caller: every launch leaves its counters clean) the
+ * two calls below need for cap_c candidates                                                              */
 int64_t grapes_select_work_floats(grapes_ctx* ctx, int cap_c);
+/* 0 (default): the whole head of a hop as ONE launch on every SM (k_select_fused: layer-2 aggregation, keys, global
+ * bucket histogram, two software grid barriers, exact threshold, ordered output); 1: GPU-wide key pass + selection on
+ * one 8-CTA cluster (the earlier form; kept for A/B measurements).  Same results bit for bit.                 */
+int grapes_select_variant(int v);
 /* One hop of the sampler head: layer-2 aggregation of the sampler GCN at width 1 -> logits (main.py:210-213;
  * arguments as grapes_aggregate_scalar, in_off == NULL: z already holds the logits), then
  * sample_neighborhoods_from_probs (utils.py:13-71) on the candidate rows: Gumbel-top-k, Bernoulli log-prob of the

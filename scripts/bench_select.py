@@ -1,5 +1,6 @@
-"""Micro-benchmark of the selection head on a products-sized candidate set (c ~ 64k, k = 256): CUDA-event time of
-grapes_select_topk (k_logits_keys + k_select) and the in-kernel phase stamps of k_select."""
+"""Micro-benchmark of the selection head on products- / Reddit-sized candidate sets (k = 256): CUDA-event time of
+grapes_select_topk for the fused one-launch kernel (variant 0, default) and the earlier k_logits_keys + one-cluster
+k_select pair (variant 1, with its in-kernel phase stamps)."""
 import ctypes, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,7 +10,8 @@ from grapes_b200.utils import _any_ctx
 def main():
     dev = torch.device("cuda", 0)
     L = lib(); ctx = _any_ctx(dev).ctx
-    for c in (8192, 65536, 150000):
+    for variant, c in ((v, c) for c in (8192, 65536, 150000) for v in (0, 1)):
+        L.cdll.grapes_select_variant(variant)
         k = 256
         logits = torch.randn(c, device=dev) * 2
         nb = torch.arange(c, device=dev, dtype=torch.int32)
@@ -37,7 +39,12 @@ def main():
         t = list(out)
         names = {0: "start", 1: "bucket found", 2: "members gathered", 3: "threshold", 4: "counts exchanged", 5: "outputs", 6: "end"}
         rel = {names[i]: round((t[i] - t[0]) / 1e3, 2) for i in sorted(names) if t[i]}
-        print(f"c={c}: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per select (both kernels); stamps us: {rel}")
+        torch.manual_seed(0)
+        ref = torch.sort(sampled[:k]).values.clone()
+        tag = "fused (one launch, every SM)" if variant == 0 else "k_logits_keys + one-cluster k_select"
+        print(f"c={c} variant {variant} [{tag}]: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per select"
+              + (f"; stamps us: {rel}" if variant == 1 else ""))
+    L.cdll.grapes_select_variant(0)
 
 if __name__ == "__main__":
     main()

@@ -87,3 +87,55 @@ def test_philox_sampler_is_uniform_when_logits_constant(cuda_device):
     freq = hits / trials
     assert abs(freq.mean().item() - k / n) < 1e-6
     assert freq.min() > 0.04 and freq.max() < 0.25          # k/n = 0.125, sd ~ 0.0165
+
+
+@pytest.mark.parametrize("n,k,levels", [(40000, 1000, 1), (70001, 256, 3), (9000, 8999, 2), (150000, 256, 100000)])
+def test_crowded_threshold_bucket_and_both_kernel_forms_agree(cuda_device, n, k, levels):
+    """Massive ties (few distinct keys, so the threshold bucket holds far more members than the on-chip list): the
+    radix-select fallback finds the same threshold; ties go to the LOWEST candidate index.  The fused one-launch form
+    (default) and the earlier key pass + one-cluster selection must return the same set, log-probs and statistics."""
+    from grapes_b200._lib import lib
+    from grapes_b200.utils import NOISE_KEYS
+    g = torch.Generator().manual_seed(n + k)
+    keys = torch.randint(0, levels, (n,), generator=g).float() * 0.25 - 3.0
+    logits = torch.randn(n, 1, generator=g)
+    nb = torch.arange(n) * 2 + 1
+    want = nb[torch.sort(rp.stable_topk_indices(keys, k)).values]
+    outs = []
+    try:
+        for variant in (0, 1):
+            lib().cdll.grapes_select_variant(variant)
+            nodes, lp, stats = _run(logits, nb, k, cuda_device, gumbel_noise=keys, noise_mode=NOISE_KEYS)
+            assert torch.equal(nodes.cpu(), want), f"variant {variant}"
+            outs.append((nodes, lp, stats))
+    finally:
+        lib().cdll.grapes_select_variant(0)
+    assert torch.equal(outs[0][1], outs[1][1])                       # log-probs bit for bit
+    for key in outs[0][2]:
+        torch.testing.assert_close(outs[0][2][key], outs[1][2][key], rtol=1e-6, atol=1e-7)
+
+
+def test_fused_selection_matches_cluster_selection_on_gumbel_keys(cuda_device):
+    """Same Gumbel noise in -> the same sampled set, log-probs and gradient from both kernel forms, at the frontier
+    sizes of the BASELINE shapes (products ~65 k, Reddit ~150 k candidates) and at sizes around the block boundaries."""
+    from grapes_b200._lib import lib
+    for n, k in ((65000, 256), (150000, 256), (511, 16), (513, 16), (75777, 256), (1, 1), (2, 1)):
+        g = torch.Generator().manual_seed(n)
+        logits = torch.randn(n, 1, generator=g) * 2
+        nb = torch.sort(torch.randperm(3 * n, generator=g)[:n]).values
+        noise = rp.draw_gumbel_like_reference(n, g)
+        res = []
+        try:
+            for variant in (0, 1):
+                lib().cdll.grapes_select_variant(variant)
+                res.append(_run(logits, nb, k, cuda_device, gumbel_noise=noise))
+        finally:
+            lib().cdll.grapes_select_variant(0)
+        assert torch.equal(res[0][0], res[1][0]), (n, k)
+        assert torch.equal(res[0][1], res[1][1]), (n, k)
+        if k < n:
+            ref_nodes, _, _ = rp.sample_neighborhoods_from_probs(logits, nb, k, gumbel_noise=noise)
+            keys = rp.perturbed_keys(logits.squeeze(-1), noise)
+            srt = torch.sort(keys, descending=True).values
+            if (srt[k - 1] - srt[k]) > 2e-6 * srt.abs().max():
+                assert torch.equal(res[0][0].cpu(), ref_nodes), (n, k)
