@@ -26,7 +26,8 @@
 #define TC_THREADS 192
 #define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/)
 
-static int g_tc_debug = 0;      // bit 0: backward operand debug fill; bit 1: force the streaming (non W-resident) forward
+static int g_tc_debug = 0;      // bit 0: backward operand debug fill; bit 1: force the streaming (non W-resident) forward;
+                                // bit 2: forward with the A operand in tensor memory (k_l1_fwd_ts)
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -354,6 +355,264 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) k_l1_fwd_tc(
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&conv_bar[stage]);
                 if (++stage == stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward kernel, A operand in TENSOR MEMORY (tcgen05.mma ... [d_tmem], [a_tmem], b_desc: "TS" form).
+//
+// Why: a 128x128x8 tf32 MMA whose two operands both come from shared memory reads 8 KB per 32 tensor-core cycles --
+// twice what the shared-memory pipe delivers (128 B/clk) -- and splitting the Y tile in shared memory adds another 48 KB
+// of shared-memory traffic per k-block: k_l1_fwd_tc sits at the shared-memory read limit with the tensor pipe 35 % busy.
+// Here the Y tile never touches shared memory: 8 converter warps read it from global memory (L2) straight into
+// registers (each thread: its own row, 64 contiguous bytes per k-block, the next k-block's loads in flight), split it
+// into the 3xTF32 (hi, lo) pair and store both into a ring of TMEM slots (tcgen05.st; TMEM lane == tile row, which is
+// exactly how an M = 128 A operand lives in tensor memory).  The MMA then reads only W from shared memory: 4 KB per
+// 32 cycles, exactly the pipe's rate.  Same arithmetic, same summation order, same outputs as k_l1_fwd_tc.
+//   warp 0       TMA: the CTA's half of W (hi | lo) once (resident, K <= 192), or W tiles through a ring (any K)
+//   warp 1       MMA issuer; accumulators in TMEM (2 x 128 columns, double buffered), fp32 master for long K
+//   warps 2..5   epilogue (bias + relu + dot(w2), relu mask bits)
+//   warps 6..13  converters: global -> registers -> (hi, lo) -> TMEM slot; lane quarter = warp % 4, column half = (warp-6)/4
+// TMEM columns: [0,256) accumulators, [256,384) master when nkb > 8, then the A ring: slots of 64 columns (hi | lo).
+// ------------------------------------------------------------------------------------------------
+#define TCS_THREADS 448
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32_x16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+        :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+           "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
+    const float* __restrict__ Y, int ldy, const __grid_constant__ CUtensorMap tmB_hi,
+    const __grid_constant__ CUtensorMap tmB_lo, const int* __restrict__ n_dev, int cap_n, int K, int D, int wres,
+    int bstages, const float* __restrict__ b1, const float* __restrict__ w2, float* __restrict__ zpart,
+    uint32_t* __restrict__ maskT) {
+    pdl_begin();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // SWIZZLE_128B tiles: 1024 B aligned
+    const int nkb = (K + TC_BK - 1) / TC_BK;
+    const int nbt = wres ? nkb : bstages;                                            // W tiles (hi | lo) held in shared memory
+    uint8_t* w_smem = smem;
+    uint64_t* bars = (uint64_t*)(smem + (size_t)nbt * 2 * TC_TILE_BYTES);
+    uint64_t* conv_bar = bars;                       // [4]  converters -> MMA   (A slot filled)
+    uint64_t* aempty_bar = bars + 4;                 // [4]  MMA -> converters   (A slot free)
+    uint64_t* bfull_bar = bars + 8;                  // [8]  TMA -> MMA          (W tile landed; streaming mode)
+    uint64_t* bempty_bar = bars + 16;                // [8]  MMA -> TMA
+    uint64_t* tfull_bar = bars + 24;                 // [2]  MMA -> epilogue
+    uint64_t* tempty_bar = bars + 26;                // [2]  epilogue -> MMA
+    uint64_t* w_bar = bars + 28;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 29);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = min(*n_dev, cap_n);
+    const int NH = D / TC_BN;
+    const int m_tiles = (n + TC_BM - 1) / TC_BM;
+    // fixed column half per CTA, row tiles strided over the CTAs of that half
+    const int t_first = (int)blockIdx.x / NH, t_step = (int)gridDim.x / NH;
+    const int nh = (int)blockIdx.x % NH;
+    const bool long_k = nkb > TC_CHUNK_KB;
+    const uint32_t a_col0 = long_k ? 384u : 256u;
+    const int aslots = long_k ? 2 : 4;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
+        for (int s = 0; s < 4; ++s) { mbar_init(&conv_bar[s], 8); mbar_init(&aempty_bar[s], 1); }
+        for (int s = 0; s < 8; ++s) { mbar_init(&bfull_bar[s], 1); mbar_init(&bempty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        mbar_init(w_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA: W =====
+        if (elect_one() && t_first < m_tiles) {
+            if (wres) {
+                mbar_arrive_expect_tx(w_bar, (uint32_t)(nkb * 2 * TC_TILE_BYTES));
+                for (int kb = 0; kb < nkb; ++kb) {
+                    tma_load_2d(w_smem + kb * 2 * TC_TILE_BYTES, &tmB_hi, w_bar, kb * TC_BK, nh * TC_BN);
+                    tma_load_2d(w_smem + kb * 2 * TC_TILE_BYTES + TC_TILE_BYTES, &tmB_lo, w_bar, kb * TC_BK, nh * TC_BN);
+                }
+            } else {
+                int stage = 0; uint32_t phase = 0;
+                for (int t = t_first; t < m_tiles; t += t_step) {
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        mbar_wait(&bempty_bar[stage], phase ^ 1);
+                        uint8_t* st = w_smem + stage * 2 * TC_TILE_BYTES;
+                        mbar_arrive_expect_tx(&bfull_bar[stage], (uint32_t)(2 * TC_TILE_BYTES));
+                        tma_load_2d(st, &tmB_hi, &bfull_bar[stage], kb * TC_BK, nh * TC_BN);
+                        tma_load_2d(st + TC_TILE_BYTES, &tmB_lo, &bfull_bar[stage], kb * TC_BK, nh * TC_BN);
+                        if (++stage == bstages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_tf32(TC_BM, TC_BN);
+            int slot = 0; uint32_t sphase = 0;
+            int bst = 0; uint32_t bphase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            if (wres && t_first < m_tiles) { mbar_wait(w_bar, 0); tc_fence_after(); }
+            const uint32_t wa = smem_u32(w_smem);
+            for (int t = t_first; t < m_tiles; t += t_step) {
+                for (int kc = 0; kc < nkb; kc += TC_CHUNK_KB) {          // the tensor core adds with truncation: keep chains short
+                    mbar_wait(&tempty_bar[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_BN);
+                    const int kend = min(nkb, kc + TC_CHUNK_KB);
+                    for (int kb = kc; kb < kend; ++kb) {
+                        mbar_wait(&conv_bar[slot], sphase);               // (hi, lo) of this k-block are in the TMEM slot
+                        if (!wres) mbar_wait(&bfull_bar[bst], bphase);
+                        tc_fence_after();
+                        const uint32_t a_hi = tmem_base + a_col0 + (uint32_t)(slot * 64);
+                        const uint32_t a_lo = a_hi + 32u;
+                        const uint32_t sb = wa + (uint32_t)((wres ? kb : bst) * 2 * TC_TILE_BYTES);
+                        const uint64_t b_hi = make_kmajor_sw128_desc(sb);
+                        const uint64_t b_lo = make_kmajor_sw128_desc(sb + TC_TILE_BYTES);
+                        const int nks = min(TC_BK / 8, (K - kb * TC_BK + 7) / 8);     // the last k-block may be partly padding
+#pragma unroll
+                        for (int ks = 0; ks < TC_BK / 8; ++ks) {
+                            if (ks >= nks) break;
+                            const uint64_t adv = (uint64_t)((ks * 32) >> 4);      // +32 bytes per K=8 slice inside the swizzle row
+                            const uint32_t ac = (uint32_t)(ks * 8);               // +8 TMEM columns per K=8 slice
+                            umma_tf32_ts(d_tmem, a_lo + ac, b_hi + adv, idesc, ((kb - kc) | ks) ? 1u : 0u);   // small terms first
+                            umma_tf32_ts(d_tmem, a_hi + ac, b_lo + adv, idesc, 1u);
+                            umma_tf32_ts(d_tmem, a_hi + ac, b_hi + adv, idesc, 1u);
+                        }
+                        umma_commit(&aempty_bar[slot]);                   // TMEM slot free once these MMAs retire
+                        if (++slot == aslots) { slot = 0; sphase ^= 1; }
+                        if (!wres) {
+                            umma_commit(&bempty_bar[bst]);
+                            if (++bst == bstages) { bst = 0; bphase ^= 1; }
+                        }
+                    }
+                    umma_commit(&tfull_bar[acc]);                         // chunk accumulator complete -> epilogue
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp < 6) {
+        // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4 =====
+        const int q = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int t = t_first; t < m_tiles; t += t_step) {
+            const int mt = t;
+            const int row = mt * TC_BM + q * 32 + lane;
+            float zsum = 0.f;
+            uint32_t mbits[4] = {0u, 0u, 0u, 0u};
+            for (int kc = 0; kc < nkb; kc += TC_CHUNK_KB) {
+                const bool first_chunk = (kc == 0), last_chunk = (kc + TC_CHUNK_KB >= nkb);
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+#pragma unroll
+                for (int ch = 0; ch < TC_BN / 32; ++ch) {
+                    uint32_t v[32];
+                    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+                    tmem_ld_32x32(lane_base + (uint32_t)(acc * TC_BN + ch * 32), v);
+                    if (!first_chunk) {                                   // fp32 master += chunk (round to nearest)
+                        uint32_t m[32];
+                        tmem_ld_32x32(lane_base + (uint32_t)(2 * TC_BN + ch * 32), m);
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(m[c]));
+                    }
+                    if (!last_chunk) {
+                        tmem_st_32x32(lane_base + (uint32_t)(2 * TC_BN + ch * 32), v);
+                        continue;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const int col = nh * TC_BN + ch * 32 + c;
+                        const float pre = __uint_as_float(v[c]) + __ldg(&b1[col]);
+                        zsum = fmaf(fmaxf(pre, 0.f), __ldg(&w2[col]), zsum);
+                        if (maskT) {
+                            const uint32_t word = __ballot_sync(GRAPES_FULL_MASK, pre > 0.f && row < n);
+                            if (lane == c) mbits[ch] = word;
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+            if (row < n) zpart[(size_t)nh * cap_n + row] = zsum;
+            if (maskT) {
+                // maskT[(row group of 32)][D]: bit r of word (g, d) = relu'(pre[32 g + r, d])
+                uint32_t* dst = maskT + (size_t)(mt * 4 + q) * D + nh * TC_BN;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) dst[ch * 32 + lane] = mbits[ch];
+            }
+        }
+    } else {
+        // ===== converters (warps 6..13): Y rows from global memory -> (hi, lo) in the TMEM slot =====
+        const int q = warp & 3;                                       // TMEM lane quarter this warp may touch
+        const int half = (warp - 6) >> 2;                             // columns [16 half, 16 half + 16) of the k-block
+        const int r_in = q * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + a_col0 + (uint32_t)(half * 16);
+        int slot = 0; uint32_t sphase = 0;
+        float4 nx[4];
+        // the loads of one k-block: 4 x 16 bytes of this thread's row; rows >= n and columns >= ldy read as zero
+        auto issue = [&](int t, int kb) {
+            const int row = t * TC_BM + r_in;
+            const int c0 = kb * TC_BK + half * 16;
+            const float* src = Y + (size_t)row * ldy + c0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                nx[i] = (row < n && c0 + 4 * i + 3 < ldy) ? __ldg(reinterpret_cast<const float4*>(src) + i)
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        if (t_first < m_tiles) issue(t_first, 0);
+        for (int t = t_first; t < m_tiles; t += t_step) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                float4 cur[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) cur[i] = nx[i];
+                // next k-block (or the first one of the CTA's next tile) while this one is converted
+                if (kb + 1 < nkb) issue(t, kb + 1);
+                else if (t + t_step < m_tiles) issue(t + t_step, 0);
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float x[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float h = tf32_rna_f(x[c]);
+                        hi[4 * i + c] = __float_as_uint(h);
+                        lo[4 * i + c] = __float_as_uint(tf32_rna_f(x[c] - h));
+                    }
+                }
+                mbar_wait(&aempty_bar[slot], sphase ^ 1);             // the MMAs that read this slot have retired
+                tc_fence_after();
+                tmem_st_32x32_x16(lane_addr + (uint32_t)(slot * 64), hi);
+                tmem_st_32x32_x16(lane_addr + (uint32_t)(slot * 64 + 32), lo);
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&conv_bar[slot]);
+                if (++slot == aslots) { slot = 0; sphase ^= 1; }
             }
         }
     }
@@ -745,6 +1004,31 @@ int grapes_sampler_l1_fwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo,
     const int presplit = Y_lo ? 1 : 0;
     CUtensorMap ma, ma_lo, mb_hi, mb_lo;
     int rc;
+    if (!presplit && (g_tc_debug & 4) && ldy % 4 == 0 && (((uintptr_t)Y) & 15) == 0) {
+        // A operand in tensor memory (k_l1_fwd_ts): Y goes global -> registers -> TMEM, only W is staged in shared memory
+        if ((rc = make_map(&mb_hi, W_hi, D, K, ldw)) != GRAPES_OK) return rc;
+        if ((rc = make_map(&mb_lo, W_lo, D, K, ldw)) != GRAPES_OK) return rc;
+        const int nkb = (K + TC_BK - 1) / TC_BK, NH = D / TC_BN;
+        const int m_tiles_cap = (cap_n + TC_BM - 1) / TC_BM;
+        const int tail_b = 1024 /*align slack*/ + 512 /*barriers*/;
+        const int wres = (nkb * 2 * TC_TILE_BYTES + tail_b <= 227 * 1024 && ctx->sm_count >= NH) ? 1 : 0;
+        const int bstages = 6;
+        const int smem_bytes = (wres ? nkb : bstages) * 2 * TC_TILE_BYTES + tail_b;
+        int per_half = ctx->sm_count / NH;
+        if (per_half > m_tiles_cap) per_half = m_tiles_cap;
+        if (per_half < 1) per_half = 1;
+        static int attr_ts[64] = {0};
+        int& have = attr_ts[ctx->device & 63];
+        if (smem_bytes > have) {
+            GRAPES_CUDA_OK(cudaFuncSetAttribute(k_l1_fwd_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+            have = smem_bytes;
+        }
+        pdl((k_l1_fwd_ts), per_half * NH, TCS_THREADS, smem_bytes, (cudaStream_t)stream)(Y, ldy, mb_hi, mb_lo, n_dev, cap_n, K, D,
+                                                                                        wres, bstages, b1, w2, zpart, maskT);
+        grapes_count_launches(1);
+        GRAPES_LAUNCH_OK();
+        return GRAPES_OK;
+    }
     if ((rc = make_map(&ma, Y, cap_n, K, ldy)) != GRAPES_OK) return rc;
     if ((rc = make_map(&ma_lo, presplit ? Y_lo : Y, cap_n, K, ldy)) != GRAPES_OK) return rc;
     if ((rc = make_map(&mb_hi, W_hi, D, K, ldw)) != GRAPES_OK) return rc;

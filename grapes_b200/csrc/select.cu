@@ -526,7 +526,8 @@ __global__ void __cluster_dims__(SEL_CTAS, 1, 1) __launch_bounds__(SEL_THREADS, 
 #define SF_MAX_BLOCKS 256
 #define SF_I_FIRST (SF_I_DEF + SF_MAX_BLOCKS)         // [max blocks]: first candidate index per block
 #define SF_I_MEMBER (SF_I_FIRST + SF_MAX_BLOCKS)      // [2 * SF_MEMBER_CAP]: member composites (64-bit)
-#define SF_I_TOTAL (SF_I_MEMBER + 2 * SF_MEMBER_CAP)
+#define SF_I_STAMP (SF_I_MEMBER + 2 * SF_MEMBER_CAP)   // [16] 64-bit phase time stamps of block 0 (globaltimer ns)
+#define SF_I_TOTAL (SF_I_STAMP + 32)
 #define SF_DELTA_FLOATS 2                             // per block: lp_delta, dl_delta
 
 __device__ __forceinline__ int key_bucket_m(uint32_t ukey, int mode) {
@@ -537,6 +538,13 @@ __device__ __forceinline__ int key_bucket_m(uint32_t ukey, int mode) {
     return (int)fminf(fmaxf(x, 0.f), (float)(SEL_BUCKETS - 1));
 }
 
+__device__ __forceinline__ void sf_stamp(int* iw, int slot) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        reinterpret_cast<unsigned long long*>(iw + SF_I_STAMP)[slot] = t;
+    }
+}
 __device__ __forceinline__ int ld_acquire_gpu_i32(const int* p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -593,6 +601,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_select_fused(
     int* hist_g = iw + SF_I_HIST;
 
     // ---------------- phase A ----------------
+    sf_stamp(iw, 0);
     for (int q = tid; q < SEL_BUCKETS; q += SF_THREADS) s_hist[q] = 0;
     if (tid == 0) s_first = 0x7fffffff;
     __syncthreads();
@@ -671,12 +680,15 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_select_fused(
     }
     bool alive = true;
     float lp_delta = 0.f, dl_delta = 0.f;
+    sf_stamp(iw, 1);
     if (!take_all) {
         for (int q = tid; q < SEL_BUCKETS; q += SF_THREADS) {
             const int h = s_hist[q];
             if (h) atomicAdd(&hist_g[q], h);
         }
+        sf_stamp(iw, 2);
         alive = sf_grid_barrier(iw + SF_I_BAR1, nb, iw + SF_I_ERR);
+        sf_stamp(iw, 3);
         // ---------------- phase B: threshold bucket (coarse level of 64 x 32 buckets, then inside the coarse bin) ----
         for (int q = tid; q < SEL_BUCKETS; q += SF_THREADS) s_hist[q] = __ldcg(&hist_g[q]);
         __syncthreads();
@@ -718,7 +730,9 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_select_fused(
         long long tot_def;
         block_scan_excl<long long>((long long)my_def, s_scan, &tot_def);
         if (tid == 0) { iw[SF_I_DEF + b] = (int)tot_def; iw[SF_I_FIRST + b] = s_first; }
+        sf_stamp(iw, 4);
         alive = sf_grid_barrier(iw + SF_I_BAR2, nb, iw + SF_I_ERR) && alive;
+        sf_stamp(iw, 5);
         // ---------------- phase C: exact threshold, positions, fix-ups ----------------
         unsigned long long thr_comp;
         if (!crowded) {
@@ -835,6 +849,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_select_fused(
         if (tid == 0) { delta_part[b * SF_DELTA_FLOATS] = lp_delta; delta_part[b * SF_DELTA_FLOATS + 1] = dl_delta; }
     }
     (void)alive;
+    sf_stamp(iw, 6);
     // ---------------- ticket: the last block combines the partials in block order and cleans the scratch ----------------
     __syncthreads();
     if (tid == 0) {
@@ -880,6 +895,9 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_select_fused(
             }
             if (mode == GRAPES_NOISE_PHILOX && !take_all) rng_state[1] += 1ull;
             iw[SF_I_BAR1] = 0; iw[SF_I_BAR2] = 0; iw[SF_I_TICKET] = 0; iw[SF_I_MCOUNT] = 0; iw[SF_I_THR_READY] = 0;
+            unsigned long long tend;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tend));
+            reinterpret_cast<unsigned long long*>(iw + SF_I_STAMP)[7] = tend;
         }
     }
 }
@@ -901,6 +919,9 @@ int grapes_debug_select_stamps(int64_t* out16) {
     return GRAPES_OK;
 }
 
+// debugging aid: phase time stamps (ns) of the last fused selection launch that used `work` (synchronises)
+int grapes_debug_select_fused_stamps(grapes_ctx* ctx, const float* work, int cap_c, int64_t* out8);
+
 // floats of scratch grapes_select_* needs in `work` (zeroed ONCE by the caller; every launch leaves the integer part clean):
 // per-block statistics | per-block deltas | candidate logits | integer words of the fused kernel (barrier counters,
 // global histogram, per-block counts, member list)
@@ -917,6 +938,13 @@ static inline int64_t sel_int_offset(const grapes_ctx* ctx, int cap_c) {
 int64_t grapes_select_work_floats(grapes_ctx* ctx, int cap_c) {
     if (!ctx) return 0;
     return sel_int_offset(ctx, cap_c) + SF_I_TOTAL + 16;
+}
+
+int grapes_debug_select_fused_stamps(grapes_ctx* ctx, const float* work, int cap_c, int64_t* out8) {
+    if (!ctx || !work || !out8) return GRAPES_ERR_ARG;
+    const int* iw = reinterpret_cast<const int*>(work + sel_int_offset(ctx, cap_c));
+    if (cudaMemcpy(out8, iw + SF_I_STAMP, 8 * sizeof(int64_t), cudaMemcpyDeviceToHost) != cudaSuccess) return GRAPES_ERR_CUDA;
+    return GRAPES_OK;
 }
 
 static int g_select_variant = 0;

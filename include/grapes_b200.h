@@ -244,7 +244,8 @@ int grapes_sampler_l1_bwd(grapes_ctx* ctx, const float* Y, int ldy, const int* n
  * zpart[D/128][cap_n] partial row dots; maskT[(rows/32)][D] relu mask bits (optional).                            */
 int grapes_split_tf32(grapes_ctx* ctx, const float* src, int ld_src, int R, int K, float* hi, float* lo, int ld_dst,
                       void* stream);
-/* measurement knob of the tcgen05 kernels (bit 1: stream the weight tiles instead of keeping them resident)           */
+/* measurement knob of the tcgen05 kernels (bit 1: stream the weight tiles instead of keeping them resident; bit 2: the
+ * forward with its A operand in tensor memory, k_l1_fwd_ts)                                                         */
 int grapes_tc_debug(int flags);
 int grapes_sampler_l1_fwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo, int ldy, const int* n_dev, int cap_n,
                              int K, const float* W_hi, const float* W_lo, int ldw, int D, const float* b1,
@@ -267,6 +268,10 @@ int64_t grapes_select_work_floats(grapes_ctx* ctx, int cap_c);
  * bucket histogram, two software grid barriers, exact threshold, ordered output); 1: GPU-wide key pass + selection on
  * one 8-CTA cluster (the earlier form; kept for A/B measurements).  Same results bit for bit.                 */
 int grapes_select_variant(int v);
+/* debugging aid: globaltimer stamps (ns) of block 0 at the phase boundaries of the last fused selection launch that used
+ * `work` (start, keys done, histogram merged, barrier 1, members listed, barrier 2, outputs done, last block done);
+ * HOST array of 8, synchronises                                                                                      */
+int grapes_debug_select_fused_stamps(grapes_ctx* ctx, const float* work, int cap_c, int64_t* out8);
 /* One hop of the sampler head: layer-2 aggregation of the sampler GCN at width 1 -> logits (main.py:210-213;
  * arguments as grapes_aggregate_scalar, in_off == NULL: z already holds the logits), then
  * sample_neighborhoods_from_probs (utils.py:13-71) on the candidate rows: Gumbel-top-k, Bernoulli log-prob of the

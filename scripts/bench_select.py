@@ -41,9 +41,15 @@ def main():
         rel = {names[i]: round((t[i] - t[0]) / 1e3, 2) for i in sorted(names) if t[i]}
         torch.manual_seed(0)
         ref = torch.sort(sampled[:k]).values.clone()
+        if variant == 0:
+            o8 = (ctypes.c_int64 * 8)()
+            L.cdll.grapes_debug_select_fused_stamps(ctx, ctypes.c_void_p(work.data_ptr()), c, o8)
+            t8 = list(o8)
+            n8 = ["start", "keys done", "hist merged", "barrier 1", "members listed", "barrier 2", "outputs done", "last block done"]
+            rel = {n8[i]: round((t8[i] - t8[0]) / 1e3, 2) for i in range(8)}
         tag = "fused (one launch, every SM)" if variant == 0 else "k_logits_keys + one-cluster k_select"
         print(f"c={c} variant {variant} [{tag}]: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per select"
-              + (f"; stamps us: {rel}" if variant == 1 else ""))
+              + f"; stamps us: {rel}")
     L.cdll.grapes_select_variant(0)
 
 if __name__ == "__main__":

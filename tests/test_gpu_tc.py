@@ -128,3 +128,31 @@ def test_l1_bwd_tc_matches_fp64_autograd(cuda_device, n, cap_n, K, D, extra, pre
     for got, ref, name in refs:
         err = (got.double().cpu() - ref).abs().max() / ref.abs().max()
         assert err < 1e-5, f"{name}: relative error {err:.3e}"
+
+
+@pytest.mark.parametrize("n,cap_n,K,D", [(1000, 1500, 104, 256), (64943, 66000, 104, 256), (130, 256, 15, 128),
+                                         (5000, 5000, 605, 256), (1, 128, 100, 256), (777, 900, 1436, 384),
+                                         (3000, 3000, 131, 256), (40000, 40001, 100, 256)])
+def test_l1_fwd_ts_tensor_memory_operand(cuda_device, n, cap_n, K, D):
+    """k_l1_fwd_ts (the Y tile goes global -> registers -> tensor memory, the MMA takes its A operand from TMEM) against
+    float64 at 1e-5, and against k_l1_fwd_tc: same operand split, same MMA order, same epilogue -> the same bits, z and
+    relu mask.  Stale rows behind n and columns behind K (indicator-like values) must not leak."""
+    from grapes_b200._lib import lib
+    g = torch.Generator().manual_seed(n + K)
+    ldy = (K + 1 + 3) // 4 * 4
+    Y = torch.randn(cap_n, ldy, generator=g)                      # pad columns hold finite junk, like the ones column
+    W1 = (torch.rand(D, K, generator=g) * 2 - 1) * (6.0 / (D + K)) ** 0.5
+    b1 = torch.randn(D, generator=g) * 0.1
+    w2 = torch.randn(D, generator=g) * 0.1
+    ref = (torch.relu(Y[:n, :K].double() @ W1.double().t() + b1.double()) * w2.double()).sum(1)
+    args = (Y.to(cuda_device), W1.to(cuda_device), b1.to(cuda_device), w2.to(cuda_device), n, cuda_device)
+    z_tc, m_tc = _run_tc(*args, with_mask=True, presplit=False)
+    try:
+        lib().cdll.grapes_tc_debug(4)
+        z_ts, m_ts = _run_tc(*args, with_mask=True, presplit=False)
+    finally:
+        lib().cdll.grapes_tc_debug(0)
+    err = (z_ts.double().cpu() - ref).abs().max() / ref.abs().max()
+    assert err < 1e-5, f"relative error {err:.3e}"
+    assert torch.equal(z_ts, z_tc)
+    assert torch.equal(m_ts[: (n + 31) // 32], m_tc[: (n + 31) // 32])
