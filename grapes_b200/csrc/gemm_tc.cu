@@ -27,7 +27,7 @@
 #define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/)
 
 static int g_tc_debug = 0;      // bit 0: backward operand debug fill; bit 1: force the streaming (non W-resident) forward;
-                                // bit 2: forward with the A operand in tensor memory (k_l1_fwd_ts)
+                                // bit 2: forward with the A operand in tensor memory (k_l1_fwd_ts); bit 3: backward likewise (k_l1_bwd_ts)
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -369,15 +369,18 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) k_l1_fwd_tc(
 // Why: a 128x128x8 tf32 MMA whose two operands both come from shared memory reads 8 KB per 32 tensor-core cycles --
 // twice what the shared-memory pipe delivers (128 B/clk) -- and splitting the Y tile in shared memory adds another 48 KB
 // of shared-memory traffic per k-block: k_l1_fwd_tc sits at the shared-memory read limit with the tensor pipe 35 % busy.
-// Here the Y tile never touches shared memory: 8 converter warps read it from global memory (L2) straight into
-// registers (each thread: its own row, 64 contiguous bytes per k-block, the next k-block's loads in flight), split it
-// into the 3xTF32 (hi, lo) pair and store both into a ring of TMEM slots (tcgen05.st; TMEM lane == tile row, which is
-// exactly how an M = 128 A operand lives in tensor memory).  The MMA then reads only W from shared memory: 4 KB per
-// 32 cycles, exactly the pipe's rate.  Same arithmetic, same summation order, same outputs as k_l1_fwd_tc.
-//   warp 0       TMA: the CTA's half of W (hi | lo) once (resident, K <= 192), or W tiles through a ring (any K)
+// Here the raw fp32 Y tile is TMA-loaded into a shared-memory ring and read ONCE by 8 converter warps (thread = tile row:
+// with SWIZZLE_128B the 32 rows of a warp hit all 32 banks, 4 wavefronts per 512 bytes, the minimum), which split it into
+// the 3xTF32 (hi, lo) pair and store both into a ring of TMEM slots (tcgen05.st; TMEM lane == tile row, which is exactly
+// how an M = 128 A operand lives in tensor memory).  The MMA then reads only W from shared memory: 4 KB per 32 cycles,
+// exactly the pipe's rate; per k-block 80 KB go through shared memory instead of 160 KB.  Same arithmetic, same
+// summation order, same outputs as k_l1_fwd_tc.  (First form of this kernel: the converters read Y from global memory
+// directly -- 28 k-blocks per CTA, each waiting ~0.7 us of L2 latency with one k-block of loads in flight: 31.5 vs 35 us.)
+//   warp 0       TMA: raw Y tiles through a ring; the CTA's half of W (hi | lo) once (resident, K <= 128 or so), or
+//                W tiles through a second ring (any K)
 //   warp 1       MMA issuer; accumulators in TMEM (2 x 128 columns, double buffered), fp32 master for long K
 //   warps 2..5   epilogue (bias + relu + dot(w2), relu mask bits)
-//   warps 6..13  converters: global -> registers -> (hi, lo) -> TMEM slot; lane quarter = warp % 4, column half = (warp-6)/4
+//   warps 6..13  converters: shared memory -> registers -> (hi, lo) -> TMEM slot; lane quarter = warp % 4, column half = (warp-6)/4
 // TMEM columns: [0,256) accumulators, [256,384) master when nkb > 8, then the A ring: slots of 64 columns (hi | lo).
 // ------------------------------------------------------------------------------------------------
 #define TCS_THREADS 448
@@ -400,9 +403,9 @@ __device__ __forceinline__ void tmem_st_32x32_x16(uint32_t taddr, const uint32_t
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
-    const float* __restrict__ Y, int ldy, const __grid_constant__ CUtensorMap tmB_hi,
+    const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB_hi,
     const __grid_constant__ CUtensorMap tmB_lo, const int* __restrict__ n_dev, int cap_n, int K, int D, int wres,
-    int bstages, const float* __restrict__ b1, const float* __restrict__ w2, float* __restrict__ zpart,
+    int bstages, int ystages, const float* __restrict__ b1, const float* __restrict__ w2, float* __restrict__ zpart,
     uint32_t* __restrict__ maskT) {
     pdl_begin();
     extern __shared__ uint8_t smem_raw[];
@@ -410,7 +413,8 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
     const int nkb = (K + TC_BK - 1) / TC_BK;
     const int nbt = wres ? nkb : bstages;                                            // W tiles (hi | lo) held in shared memory
     uint8_t* w_smem = smem;
-    uint64_t* bars = (uint64_t*)(smem + (size_t)nbt * 2 * TC_TILE_BYTES);
+    uint8_t* y_ring = smem + (size_t)nbt * 2 * TC_TILE_BYTES;                        // [ystages] raw fp32 Y tiles
+    uint64_t* bars = (uint64_t*)(y_ring + (size_t)ystages * TC_TILE_BYTES);
     uint64_t* conv_bar = bars;                       // [4]  converters -> MMA   (A slot filled)
     uint64_t* aempty_bar = bars + 4;                 // [4]  MMA -> converters   (A slot free)
     uint64_t* bfull_bar = bars + 8;                  // [8]  TMA -> MMA          (W tile landed; streaming mode)
@@ -418,6 +422,8 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
     uint64_t* tfull_bar = bars + 24;                 // [2]  MMA -> epilogue
     uint64_t* tempty_bar = bars + 26;                // [2]  epilogue -> MMA
     uint64_t* w_bar = bars + 28;
+    uint64_t* yfull_bar = bars + 32;                 // [8]  TMA -> converters   (raw Y tile landed)
+    uint64_t* yempty_bar = bars + 40;                // [8]  converters -> TMA   (tile read into registers)
     uint32_t* tmem_slot = (uint32_t*)(bars + 29);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -432,8 +438,9 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
     const int aslots = long_k ? 2 : 4;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
+        tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
         for (int s = 0; s < 4; ++s) { mbar_init(&conv_bar[s], 8); mbar_init(&aempty_bar[s], 1); }
+        for (int s = 0; s < 8; ++s) { mbar_init(&yfull_bar[s], 1); mbar_init(&yempty_bar[s], 8); }
         for (int s = 0; s < 8; ++s) { mbar_init(&bfull_bar[s], 1); mbar_init(&bempty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
         mbar_init(w_bar, 1);
@@ -446,7 +453,7 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===== TMA: W =====
+        // ===== TMA: W (once, or through its ring) and the raw Y tiles =====
         if (elect_one() && t_first < m_tiles) {
             if (wres) {
                 mbar_arrive_expect_tx(w_bar, (uint32_t)(nkb * 2 * TC_TILE_BYTES));
@@ -454,10 +461,16 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
                     tma_load_2d(w_smem + kb * 2 * TC_TILE_BYTES, &tmB_hi, w_bar, kb * TC_BK, nh * TC_BN);
                     tma_load_2d(w_smem + kb * 2 * TC_TILE_BYTES + TC_TILE_BYTES, &tmB_lo, w_bar, kb * TC_BK, nh * TC_BN);
                 }
-            } else {
-                int stage = 0; uint32_t phase = 0;
-                for (int t = t_first; t < m_tiles; t += t_step) {
-                    for (int kb = 0; kb < nkb; ++kb) {
+            }
+            int ys = 0; uint32_t yphase = 0;
+            int stage = 0; uint32_t phase = 0;
+            for (int t = t_first; t < m_tiles; t += t_step) {
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&yempty_bar[ys], yphase ^ 1);
+                    mbar_arrive_expect_tx(&yfull_bar[ys], (uint32_t)TC_TILE_BYTES);
+                    tma_load_2d(y_ring + ys * TC_TILE_BYTES, &tmA, &yfull_bar[ys], kb * TC_BK, t * TC_BM);
+                    if (++ys == ystages) { ys = 0; yphase ^= 1; }
+                    if (!wres) {
                         mbar_wait(&bempty_bar[stage], phase ^ 1);
                         uint8_t* st = w_smem + stage * 2 * TC_TILE_BYTES;
                         mbar_arrive_expect_tx(&bfull_bar[stage], (uint32_t)(2 * TC_TILE_BYTES));
@@ -567,32 +580,24 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
             }
         }
     } else {
-        // ===== converters (warps 6..13): Y rows from global memory -> (hi, lo) in the TMEM slot =====
+        // ===== converters (warps 6..13): raw Y tile in shared memory -> registers -> (hi, lo) in the TMEM slot =====
         const int q = warp & 3;                                       // TMEM lane quarter this warp may touch
         const int half = (warp - 6) >> 2;                             // columns [16 half, 16 half + 16) of the k-block
-        const int r_in = q * 32 + lane;
+        const int r_in = q * 32 + lane;                               // tile row == TMEM lane
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + a_col0 + (uint32_t)(half * 16);
         int slot = 0; uint32_t sphase = 0;
-        float4 nx[4];
-        // the loads of one k-block: 4 x 16 bytes of this thread's row; rows >= n and columns >= ldy read as zero
-        auto issue = [&](int t, int kb) {
-            const int row = t * TC_BM + r_in;
-            const int c0 = kb * TC_BK + half * 16;
-            const float* src = Y + (size_t)row * ldy + c0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                nx[i] = (row < n && c0 + 4 * i + 3 < ldy) ? __ldg(reinterpret_cast<const float4*>(src) + i)
-                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-        };
-        if (t_first < m_tiles) issue(t_first, 0);
+        int ys = 0; uint32_t yphase = 0;
         for (int t = t_first; t < m_tiles; t += t_step) {
             for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&yfull_bar[ys], yphase);
+                const uint8_t* tile = y_ring + ys * TC_TILE_BYTES + r_in * 128;
                 float4 cur[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) cur[i] = nx[i];
-                // next k-block (or the first one of the CTA's next tile) while this one is converted
-                if (kb + 1 < nkb) issue(t, kb + 1);
-                else if (t + t_step < m_tiles) issue(t + t_step, 0);
+                for (int i = 0; i < 4; ++i)                            // SWIZZLE_128B: 16-byte chunk index ^ (row % 8)
+                    cur[i] = *reinterpret_cast<const float4*>(tile + ((((half * 4 + i) ^ (r_in & 7))) << 4));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&yempty_bar[ys]);          // the tile is in registers: the slot may be refilled
+                if (++ys == ystages) { ys = 0; yphase ^= 1; }
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -855,6 +860,189 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) k_l1_bwd_tc(
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward kernel, scaled-feature operand in TENSOR MEMORY ("TS" form of the contraction, transposed):
+//
+//     S^T[k, d] = sum_r B''[r, k] * mask[r, d],      B''[r, k] = fl(dz[r] * Y[r, k])  split into (hi, lo)
+//
+// k_l1_bwd_tc stages both operands in shared memory: per 32-row group the TMA writes the Y tile (16 KB), four warps read
+// it, scale, split and write it back twice (48 KB), four warps write the mask tiles (32 KB) and the MMAs read 96 KB --
+// 192 KB through a 128 B/clk pipe for 512 tensor-core cycles of work.  Here the Y tile is read from shared memory once:
+//   warp 0       TMA: Y tiles (32 rows x 32-column blocks, no swizzle -- no MMA reads them) through a ring
+//   warps 6..9   read the tile TRANSPOSED (thread = column k of Y = TMEM lane; for a fixed row the 32 lanes of a warp
+//                read one 128-byte line: conflict free), scale by dz, split, and store (hi | lo) into a ring of TMEM
+//                slots: the A operand [M = k, K = r] of the MMA lives in tensor memory.
+//   warps 2..5   expand the relu-mask bits of the CTA's 128 hidden units into the B operand [N = d, K = r] (1.0 / 0.0,
+//                exact in tf32) in shared memory; afterwards they are the epilogue.
+//   warp 1       MMA issuer: per 8-row slice one M128 N128 K8 MMA for the hi part and one for the lo part, into two
+//                accumulators (added in the epilogue, as in k_l1_bwd_tc).
+// Shared-memory traffic per group: 80 KB (Y 16 + 16, mask 16 + 32) instead of 192 KB.  A CTA owns ONE 128-unit half of the hidden layer
+// (blockIdx.x % NH) and a strided share of the row groups; blockIdx.y = 128-column chunk of Y.
+// Partials: part[chunk][cta / NH][D][N] -- the layout k_l1_bwd_finalize already reads.
+// TMEM columns: [0,128) hi accumulator, [128,256) lo accumulator, [256,512) A ring: 4 slots of (hi 32 | lo 32).
+// ------------------------------------------------------------------------------------------------
+#define TCBS_THREADS 320
+#define TCBS_STAGES 4
+__global__ void __launch_bounds__(TCBS_THREADS, 1) k_l1_bwd_ts(
+    const __grid_constant__ CUtensorMap tmY, int ncols, const int* __restrict__ n_dev, int cap_n, int NH,
+    const uint32_t* __restrict__ maskT, int D, const float* __restrict__ dz, float* __restrict__ part,
+    long long chunk_stride, int ystages) {
+    pdl_begin();
+    const int col0 = (int)blockIdx.y * 128;
+    const int N = min(4, (ncols - col0 + 31) / 32) * 32;            // S columns of this chunk (a multiple of 32)
+    part += (size_t)blockIdx.y * (size_t)chunk_stride;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* y_ring = smem + TCBS_STAGES * TCB_A_TILE;                // [ystages][4 blocks][32 rows][32 floats]
+    uint64_t* bars = (uint64_t*)(y_ring + (size_t)ystages * 4 * TCB_B_TILE);
+    uint64_t* full_bar = bars;                       // [4] 4 mask-expander + 4 converter warps -> MMA
+    uint64_t* empty_bar = bars + 4;                  // [4] MMA -> producers
+    uint64_t* done_bar = bars + 8;                   // all MMAs retired -> epilogue
+    uint32_t* tmem_slot = (uint32_t*)(bars + 9);
+    uint64_t* yfull_bar = bars + 10;                 // [8] TMA -> converters
+    uint64_t* yempty_bar = bars + 18;                // [8] converters -> TMA
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = min(*n_dev, cap_n);
+    const int groups = (n + TCB_ROWS - 1) / TCB_ROWS;
+    const int h = (int)blockIdx.x % NH;              // hidden half of this CTA
+    const int g_first = (int)blockIdx.x / NH, g_step = (int)gridDim.x / NH;
+    const bool have_work = g_first < groups;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmY);
+        for (int s = 0; s < TCBS_STAGES; ++s) { mbar_init(&full_bar[s], 8); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 8; ++s) { mbar_init(&yfull_bar[s], 1); mbar_init(&yempty_bar[s], 4); }
+        mbar_init(done_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int NBk = N / 32;                                           // 32-column blocks of this chunk
+    if (warp == 0) {
+        if (elect_one()) {
+            int ys = 0; uint32_t yphase = 0;
+            for (int g = g_first; g < groups; g += g_step) {
+                mbar_wait(&yempty_bar[ys], yphase ^ 1);
+                mbar_arrive_expect_tx(&yfull_bar[ys], (uint32_t)(NBk * TCB_B_TILE));
+                for (int nb = 0; nb < NBk; ++nb)
+                    tma_load_2d(y_ring + (size_t)ys * 4 * TCB_B_TILE + nb * TCB_B_TILE, &tmY, &yfull_bar[ys], col0 + nb * 32,
+                                g * TCB_ROWS);
+                if (++ys == ystages) { ys = 0; yphase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_tf32(128, 128);
+            int stage = 0; uint32_t phase = 0;
+            bool first = true;
+            for (int g = g_first; g < groups; g += g_step) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint64_t bd = make_kmajor_sw128_desc(smem_u32(smem + stage * TCB_A_TILE));
+                const uint32_t a_hi = tmem_base + 256u + (uint32_t)(stage * 64);
+#pragma unroll
+                for (int ks = 0; ks < TCB_ROWS / 8; ++ks) {
+                    const uint64_t adv = (uint64_t)((ks * 32) >> 4);          // 8 r = 32 bytes along the swizzle row
+                    const uint32_t acc = (first && ks == 0) ? 0u : 1u;
+                    umma_tf32_ts(tmem_base, a_hi + (uint32_t)(ks * 8), bd + adv, idesc, acc);
+                    umma_tf32_ts(tmem_base + 128u, a_hi + 32u + (uint32_t)(ks * 8), bd + adv, idesc, acc);
+                }
+                first = false;
+                umma_commit(&empty_bar[stage]);
+                if (++stage == TCBS_STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(done_bar);
+        }
+    } else if (warp >= 6) {
+        // ===== converters (warps 6..9): B''^T = (dz * Y)^T split into (hi, lo), shared memory -> registers -> TMEM =====
+        const int q = warp & 3;                                       // TMEM lane quarter of this warp == 32-column block
+        const bool blk_valid = q < NBk;                               // blocks behind the chunk's columns hold nothing: zeros
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + 256u;
+        int stage = 0; uint32_t phase = 0;
+        int ys = 0; uint32_t yphase = 0;
+        float dz_nx = 0.f;                                            // dz of the NEXT group's rows: loaded one group ahead
+        if (have_work) { const int r = g_first * TCB_ROWS + lane; dz_nx = (r < n) ? __ldg(&dz[r]) : 0.f; }
+        for (int g = g_first; g < groups; g += g_step) {
+            const float dzr = dz_nx;
+            if (g + g_step < groups) { const int r = (g + g_step) * TCB_ROWS + lane; dz_nx = (r < n) ? __ldg(&dz[r]) : 0.f; }
+            mbar_wait(&yfull_bar[ys], yphase);
+            const float* tile = reinterpret_cast<const float*>(y_ring + (size_t)ys * 4 * TCB_B_TILE + q * TCB_B_TILE) + lane;
+            uint32_t hi[32], lo[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                // rows >= n of the last group are stale in Y: their dz is 0, and 0 * finite = 0 (Y holds finite values only)
+                const float y = blk_valid ? tile[i * 32] : 0.f;
+                const float v = y * __shfl_sync(GRAPES_FULL_MASK, dzr, i);
+                const float hh = tf32_rna(v);
+                hi[i] = __float_as_uint(hh);
+                lo[i] = __float_as_uint(tf32_rna(v - hh));
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&yempty_bar[ys]);              // tile consumed: the TMA may refill the slot
+            if (++ys == ystages) { ys = 0; yphase ^= 1; }
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            tc_fence_after();
+            tmem_st_32x32(lane_addr + (uint32_t)(stage * 64), hi);
+            tmem_st_32x32(lane_addr + (uint32_t)(stage * 64 + 32), lo);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[stage]);
+            if (++stage == TCBS_STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp >= 2) {
+        // ===== mask expanders (warps 2..5), then epilogue =====
+        const int e = (warp - 2) * 32 + lane;            // hidden unit inside the half: row of the B operand tile
+        int stage = 0; uint32_t phase = 0;
+        uint32_t word_nx = have_work ? maskT[(size_t)g_first * D + h * 128 + e] : 0u;
+        for (int g = g_first; g < groups; g += g_step) {
+            const uint32_t word = word_nx;
+            if (g + g_step < groups) word_nx = maskT[(size_t)(g + g_step) * D + h * 128 + e];
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* st = smem + stage * TCB_A_TILE;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int off = e * 128 + ((c ^ (e & 7)) << 4);          // SWIZZLE_128B: 16-byte chunk index ^ (row % 8)
+                const uint32_t w = word >> (c * 4);
+                float4 a;
+                a.x = (w & 1u) ? 1.f : 0.f; a.y = (w & 2u) ? 1.f : 0.f; a.z = (w & 4u) ? 1.f : 0.f; a.w = (w & 8u) ? 1.f : 0.f;
+                *reinterpret_cast<float4*>(st + off) = a;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[stage]);
+            if (++stage == TCBS_STAGES) { stage = 0; phase ^= 1; }
+        }
+        // epilogue: TMEM lane = column k of Y, TMEM column = hidden unit; stored transposed -> part[cta/NH][h*128 + d][k]
+        const int q = warp & 3;
+        const int kk = q * 32 + lane;
+        float* dst = part + ((size_t)((int)blockIdx.x / NH) * D + (size_t)h * 128) * N;
+        if (have_work) {
+            mbar_wait(done_bar, 0);
+            tc_fence_after();
+            for (int ch = 0; ch < 4; ++ch) {
+                uint32_t v[32], v2[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(128 + ch * 32), v2);
+                if (kk < N) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)
+                        dst[(size_t)(ch * 32 + c) * N + kk] = __uint_as_float(v[c]) + __uint_as_float(v2[c]);
+                }
+            }
+        } else if (kk < N) {
+            for (int d = 0; d < 128; ++d) dst[(size_t)d * N + kk] = 0.f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 // Sum the per-CTA partials (fixed order) and turn S into the three gradients, accumulated (+=, times scale).
 // One 1024-thread block per hidden unit d.  N/4 threads cover one partial row with float4 loads; the 1024/(N/4)
 // thread groups split the partials, each thread keeping 5 independent 16-byte loads in flight, then a fixed-order
@@ -1004,16 +1192,21 @@ int grapes_sampler_l1_fwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo,
     const int presplit = Y_lo ? 1 : 0;
     CUtensorMap ma, ma_lo, mb_hi, mb_lo;
     int rc;
-    if (!presplit && (g_tc_debug & 4) && ldy % 4 == 0 && (((uintptr_t)Y) & 15) == 0) {
+    if (!presplit && (g_tc_debug & 4)) {
         // A operand in tensor memory (k_l1_fwd_ts): Y goes global -> registers -> TMEM, only W is staged in shared memory
         if ((rc = make_map(&mb_hi, W_hi, D, K, ldw)) != GRAPES_OK) return rc;
         if ((rc = make_map(&mb_lo, W_lo, D, K, ldw)) != GRAPES_OK) return rc;
         const int nkb = (K + TC_BK - 1) / TC_BK, NH = D / TC_BN;
         const int m_tiles_cap = (cap_n + TC_BM - 1) / TC_BM;
+        if ((rc = make_map(&ma, Y, cap_n, K, ldy)) != GRAPES_OK) return rc;
         const int tail_b = 1024 /*align slack*/ + 512 /*barriers*/;
-        const int wres = (nkb * 2 * TC_TILE_BYTES + tail_b <= 227 * 1024 && ctx->sm_count >= NH) ? 1 : 0;
-        const int bstages = 6;
-        const int smem_bytes = (wres ? nkb : bstages) * 2 * TC_TILE_BYTES + tail_b;
+        // W half resident when it leaves room for >= 4 raw Y tiles; otherwise W streams through a 4-stage ring
+        const int wres = (nkb * 2 * TC_TILE_BYTES + 4 * TC_TILE_BYTES + tail_b <= 227 * 1024 && ctx->sm_count >= NH) ? 1 : 0;
+        const int bstages = 4;
+        const int nbt = wres ? nkb : bstages;
+        int ystages = (227 * 1024 - tail_b - nbt * 2 * TC_TILE_BYTES) / TC_TILE_BYTES;
+        if (ystages > 8) ystages = 8;
+        const int smem_bytes = nbt * 2 * TC_TILE_BYTES + ystages * TC_TILE_BYTES + tail_b;
         int per_half = ctx->sm_count / NH;
         if (per_half > m_tiles_cap) per_half = m_tiles_cap;
         if (per_half < 1) per_half = 1;
@@ -1023,8 +1216,8 @@ int grapes_sampler_l1_fwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo,
             GRAPES_CUDA_OK(cudaFuncSetAttribute(k_l1_fwd_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
             have = smem_bytes;
         }
-        pdl((k_l1_fwd_ts), per_half * NH, TCS_THREADS, smem_bytes, (cudaStream_t)stream)(Y, ldy, mb_hi, mb_lo, n_dev, cap_n, K, D,
-                                                                                        wres, bstages, b1, w2, zpart, maskT);
+        pdl((k_l1_fwd_ts), per_half * NH, TCS_THREADS, smem_bytes, (cudaStream_t)stream)(ma, mb_hi, mb_lo, n_dev, cap_n, K, D, wres,
+                                                                                        bstages, ystages, b1, w2, zpart, maskT);
         grapes_count_launches(1);
         GRAPES_LAUNCH_OK();
         return GRAPES_OK;
@@ -1084,6 +1277,34 @@ int grapes_sampler_l1_bwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo,
     // column chunks of <= 128 columns of Y (accumulator: NH halves x (hi | lo) x 128 columns = all 512 TMEM columns): ONE
     // launch, blockIdx.y = chunk, the SMs divided among the chunks; then ONE finalize that walks the chunks in order
     const int nchunks = (ncols + 127) / 128;
+    if ((g_tc_debug & 8) && !Y_lo) {
+        // scaled-feature operand in tensor memory (k_l1_bwd_ts): every CTA owns one 128-unit half of the hidden layer
+        const int ystages = 6;
+        const int smem_ts = TCBS_STAGES * TCB_A_TILE + ystages * 4 * TCB_B_TILE + 1024 + 512;
+        CUtensorMap my;
+        int rc;
+        if ((rc = make_map(&my, Y, cap_n, ncols, ldy, TCB_ROWS, CU_TENSOR_MAP_SWIZZLE_NONE)) != GRAPES_OK) return rc;
+        static int attr_ts[64] = {0};
+        int& have = attr_ts[ctx->device & 63];
+        if (smem_ts > have) {
+            GRAPES_CUDA_OK(cudaFuncSetAttribute(k_l1_bwd_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ts));
+            have = smem_ts;
+        }
+        const int max_groups = (cap_n + TCB_ROWS - 1) / TCB_ROWS;
+        int per_half = grapes_max_i(1, ctx->sm_count / nchunks / NH);  // CTAs per chunk and half
+        if (per_half > max_groups) per_half = max_groups;
+        while (per_half > 1 && (size_t)nchunks * per_half * D * 128 * sizeof(float) > ctx->partials_bytes) --per_half;
+        GRAPES_REQUIRE((size_t)nchunks * per_half * D * 128 * sizeof(float) <= ctx->partials_bytes, "split partial buffer too small");
+        const long long chunk_stride = (long long)per_half * D * 128;
+        pdl((k_l1_bwd_ts), dim3(per_half * NH, nchunks), TCBS_THREADS, smem_ts, s)(my, ncols, n_dev, cap_n, NH, maskT, D, dz,
+                                                                                  ctx->partials, chunk_stride, ystages);
+        grapes_count_launches(1);
+        pdl((k_l1_bwd_finalize), D, FIN_THREADS, 0, s)(ctx->partials, per_half, D, ncols, nchunks, chunk_stride, K, W1, ldw, b1, w2,
+                                                    ones_col, scale, gW1, gb1, gw2);
+        grapes_count_launches(1);
+        GRAPES_LAUNCH_OK();
+        return GRAPES_OK;
+    }
     const int NB = (grapes_min_i(ncols, 128) + 31) / 32;              // blocks of 32 columns in a full chunk
     const int stage_bytes = NH * TCB_A_TILE + NB * 2 * TCB_B_TILE;
     int stages = (224 * 1024) / stage_bytes;

@@ -606,7 +606,13 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_select_fused(
     if (tid == 0) s_first = 0x7fffffff;
     __syncthreads();
     float pmin = INFINITY, pmax = -INFINITY, esum = 0.f, esq = 0.f, lpsum = 0.f, dlsum = 0.f;
+    // candidate index, ordered key and logit of this thread's rows of the first two rounds stay in registers for the
+    // phases behind the barriers (<= 1024 rows per block: frontiers up to ~150 k rows); later rounds re-read them
+    int ci0 = -1, ci1 = -1;
+    uint32_t cu0 = 0u, cu1 = 0u;
+    float cl0 = 0.f, cl1 = 0.f;
     for (int j = r0 + tid; j < r1; j += SF_THREADS) {
+        const int rd = (j - r0) / SF_THREADS;
         float logit;
         if (in_off) {
             const float dj = dinv[j];
@@ -661,6 +667,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_select_fused(
         }
         const uint32_t uk = float_to_ordered(key);
         ukeys[i] = uk;
+        if (rd == 0) { ci0 = i; cu0 = uk; cl0 = logit; } else if (rd == 1) { ci1 = i; cu1 = uk; cl1 = logit; }
         if (keys_out) keys_out[i] = key;
         atomicAdd(&s_hist[key_bucket_m(uk, mode)], 1);
         pmin = fminf(pmin, p); pmax = fmaxf(pmax, p);
@@ -717,9 +724,10 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_select_fused(
         // definite items of this block + members into the global list
         int my_def = 0;
         for (int j = r0 + tid; j < r1; j += SF_THREADS) {
-            const int i = nb_index ? nb_index[j] : j;
+            const int rd = (j - r0) / SF_THREADS;
+            const int i = rd == 0 ? ci0 : rd == 1 ? ci1 : (nb_index ? nb_index[j] : j);
             if (i < 0) continue;
-            const uint32_t u = ukeys[i];
+            const uint32_t u = rd == 0 ? cu0 : rd == 1 ? cu1 : ukeys[i];
             const int bk = key_bucket_m(u, mode);
             if (bk > bucket) ++my_def;
             else if (bk == bucket && !crowded) {
@@ -818,10 +826,11 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_select_fused(
         }
         for (int base = r0; base < r1; base += SF_THREADS) {
             const int j = base + tid;
+            const int rd = (base - r0) / SF_THREADS;
             int i = -1;
-            if (j < r1) i = nb_index ? nb_index[j] : j;
+            if (j < r1) i = rd == 0 ? ci0 : rd == 1 ? ci1 : (nb_index ? nb_index[j] : j);
             bool sel = false;
-            if (i >= 0) sel = composite(ukeys[i], i) >= thr_comp;
+            if (i >= 0) sel = composite(rd == 0 ? cu0 : rd == 1 ? cu1 : ukeys[i], i) >= thr_comp;
             const uint32_t bal = __ballot_sync(GRAPES_FULL_MASK, sel);
             if (lane == 0) s_wcnt[warp] = __popc(bal);
             __syncthreads();
@@ -833,7 +842,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_select_fused(
                 const int g = nb_nodes ? nb_nodes[i] : i;
                 if (sampled_out) sampled_out[sampled_offset + pos] = g;
                 if (bm_mark && nb_nodes) bitmap_set(bm_mark, g);
-                const float l = lg_c[i];
+                const float l = rd == 0 ? cl0 : rd == 1 ? cl1 : lg_c[i];
                 const float lp1 = bern_log_prob(l, 1.f), lp0 = bern_log_prob(l, 0.f);
                 if (log_prob) log_prob[i] = lp1;
                 if (dl_all) dl_all[j] = 1.f - sigmoidf_(l);      // j == nb_local[i]
@@ -860,15 +869,26 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_select_fused(
     if (!s_last) return;
     __threadfence();
     for (int q = tid; q < SEL_BUCKETS; q += SF_THREADS) hist_g[q] = 0;
+    // every block's partials in ONE round of parallel loads (s_hist is free now: 8 floats per block), then a fixed-order
+    // combine by warp 0
+    float* s_part = reinterpret_cast<float*>(s_hist);
+    for (int q = tid; q < nb * SEL_STAT_FLOATS; q += SF_THREADS) {
+        float v = __ldcg(stat_part + q);
+        const int bq = q / SEL_STAT_FLOATS, f = q % SEL_STAT_FLOATS;
+        if (f == 6) v = __ldcg(delta_part + bq * SF_DELTA_FLOATS);
+        if (f == 7) v = __ldcg(delta_part + bq * SF_DELTA_FLOATS + 1);
+        s_part[q] = v;
+    }
+    __syncthreads();
     if (tid < 32) {
         float mn = INFINITY, mx = -INFINITY;
         double es = 0.0, eq = 0.0, lp = 0.0, dl = 0.0;
         for (int bq = tid; bq < nb; bq += 32) {
-            const float* p = stat_part + (size_t)bq * SEL_STAT_FLOATS;
-            mn = fminf(mn, __ldcg(p + 0)); mx = fmaxf(mx, __ldcg(p + 1));
-            es += (double)__ldcg(p + 2); eq += (double)__ldcg(p + 3);
-            lp += (double)__ldcg(p + 4) + (double)__ldcg(delta_part + bq * SF_DELTA_FLOATS);
-            dl += (double)__ldcg(p + 5) + (double)__ldcg(delta_part + bq * SF_DELTA_FLOATS + 1);
+            const float* p = s_part + bq * SEL_STAT_FLOATS;
+            mn = fminf(mn, p[0]); mx = fmaxf(mx, p[1]);
+            es += (double)p[2]; eq += (double)p[3];
+            lp += (double)p[4] + (double)p[6];
+            dl += (double)p[5] + (double)p[7];
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {

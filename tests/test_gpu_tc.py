@@ -156,3 +156,58 @@ def test_l1_fwd_ts_tensor_memory_operand(cuda_device, n, cap_n, K, D):
     assert err < 1e-5, f"relative error {err:.3e}"
     assert torch.equal(z_ts, z_tc)
     assert torch.equal(m_ts[: (n + 31) // 32], m_tc[: (n + 31) // 32])
+
+
+@pytest.mark.parametrize("n,cap_n,K,D,extra", [(3000, 3072, 104, 256, 0), (64943, 66000, 104, 256, 0), (100, 128, 15, 128, 0),
+                                               (2000, 2048, 100, 256, 4), (5000, 5100, 131, 256, 0),
+                                               (4000, 4096, 605, 256, 0), (1500, 1536, 1433, 256, 3)])
+def test_l1_bwd_ts_tensor_memory_operand(cuda_device, n, cap_n, K, D, extra):
+    """k_l1_bwd_ts (S^T = (dz * Y)^T mask with the scaled, split features in tensor memory, one hidden half per CTA) against
+    float64 autograd at 1e-5 (evaluated with the kernel's own relu mask, as in test_l1_bwd_tc_matches_fp64_autograd) and
+    against k_l1_bwd_tc to fp32 rounding (the row groups are dealt to the CTAs differently, so not bit for bit)."""
+    from grapes_b200._lib import lib, ptr
+    from grapes_b200.utils import _any_ctx
+    dev = cuda_device
+    L, ctx = lib(), _any_ctx(dev).ctx
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(n + K + extra)
+    ones_col = K + extra
+    ncols = ones_col + 1
+    ldy = (ncols + 3) // 4 * 4
+    Y = torch.zeros(cap_n, ldy)
+    Y[:, :ones_col] = torch.randn(cap_n, ones_col, generator=g)
+    Y[:, ones_col] = 1.0
+    W1 = (torch.rand(D, K, generator=g) * 2 - 1) * (6.0 / (D + K)) ** 0.5
+    b1 = torch.randn(D, generator=g) * 0.1
+    w2 = torch.randn(D, generator=g) * 0.1
+    dz = torch.randn(cap_n, generator=g)
+    pre64 = Y[:n, :K].double() @ W1.double().t() + b1.double()
+    Yd, W1d, b1d, w2d, dzd = (t.to(dev) for t in (Y, W1, b1, w2, dz))
+    ldw = (K + 3) // 4 * 4
+    Wh, Wl = torch.empty((D, ldw), device=dev), torch.empty((D, ldw), device=dev)
+    L.grapes_split_tf32(ctx, ptr(W1d), K, D, K, ptr(Wh), ptr(Wl), ldw, st)
+    zpart = torch.zeros((D // 128, cap_n), device=dev)
+    cnt = torch.tensor([n], dtype=torch.int32, device=dev)
+    maskT = torch.zeros(((cap_n + 127) // 128 * 4, D), dtype=torch.int32, device=dev)
+    L.grapes_sampler_l1_fwd_tc(ctx, ptr(Yd), None, ldy, ptr(cnt), cap_n, K, ptr(Wh), ptr(Wl), ldw, D, ptr(b1d),
+                               ptr(w2d), ptr(zpart), ptr(maskT), st)
+    outs = []
+    try:
+        for flag in (8, 0):
+            L.cdll.grapes_tc_debug(flag)
+            gW1, gb1, gw2 = torch.zeros(D, K, device=dev), torch.zeros(D, device=dev), torch.zeros(D, device=dev)
+            L.grapes_sampler_l1_bwd_tc(ctx, ptr(Yd), None, ldy, ncols, ptr(cnt), cap_n, K, ones_col, ptr(maskT), ptr(W1d), K,
+                                       D, ptr(b1d), ptr(w2d), ptr(dzd), 1.0, ptr(gW1), ptr(gb1), ptr(gw2), st)
+            torch.cuda.synchronize()
+            outs.append((gW1, gb1, gw2))
+    finally:
+        L.cdll.grapes_tc_debug(0)
+    rows = torch.arange(n)
+    m = ((maskT.cpu()[rows // 32] >> (rows % 32).unsqueeze(1)) & 1).double()
+    gg = dz[:n].double().unsqueeze(1) * m * w2.double()
+    refs = (gg.t() @ Y[:n, :K].double(), gg.sum(0), (dz[:n].double().unsqueeze(1) * m * pre64).sum(0))
+    for got, old, ref, name in zip(outs[0], outs[1], refs, ("W1", "b1", "w2")):
+        err = (got.double().cpu() - ref).abs().max() / ref.abs().max()
+        assert err < 1e-5, f"{name}: relative error {err:.3e} against float64"
+        dif = (got.double() - old.double()).abs().max().item() / ref.abs().max().item()
+        assert dif < 2e-6, f"{name}: {dif:.3e} away from k_l1_bwd_tc"
