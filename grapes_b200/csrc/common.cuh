@@ -111,6 +111,14 @@ static inline int grapes_max_i(int a, int b) { return a > b ? a : b; }
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// fp32 -> tf32 (10-bit mantissa), round to nearest, ties away from zero: the value cvt.rna.tf32.f32 returns for every
+// finite input, in TWO integer instructions (add half an ulp to the magnitude bits, clear the 13 low bits).  ptxas expands
+// the cvt into ~6 instructions with NaN / Inf handling; the 3xTF32 operand split calls this twice per element and was
+// the largest instruction stream of the tcgen05 kernels (ncu: profiles/r02_topkernels.md).
+__device__ __forceinline__ float grapes_tf32_rna(float x) {
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+
 // local id of global node v: rank of bit v in the bitmap (pref = exclusive popcount prefix per word)
 __device__ __forceinline__ int bitmap_rank(const uint32_t* __restrict__ bm, const int* __restrict__ pref, int v) {
     const int w = v >> 5;

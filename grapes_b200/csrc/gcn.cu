@@ -13,11 +13,7 @@ template <> struct VecT<1> { typedef float T; };
 template <> struct VecT<2> { typedef float2 T; };
 template <> struct VecT<4> { typedef float4 T; };
 
-__device__ __forceinline__ float f32_to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
+__device__ __forceinline__ float f32_to_tf32(float x) { return grapes_tf32_rna(x); }
 
 template <int VEC>
 __device__ __forceinline__ void vec_fma(float (&acc)[VEC], float w, const float* p) {

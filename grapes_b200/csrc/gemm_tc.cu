@@ -108,11 +108,7 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ float tf32_rna_f(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
+__device__ __forceinline__ float tf32_rna_f(float x) { return grapes_tf32_rna(x); }
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
     asm volatile(
@@ -656,11 +652,7 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_32b_desc(uint32_t smem_ad
     d |= (uint64_t)1u << 61;
     return d;
 }
-__device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
+__device__ __forceinline__ float tf32_rna(float x) { return grapes_tf32_rna(x); }
 
 // v2 of the contraction: the relu mask is 0/1 -- EXACT in tf32 -- so it is the single A operand, and dz is folded into
 // the other side: B''[r, k] = fl(dz[r] * Y[r, k]) split into (hi, lo) by the expander warps in shared memory.
@@ -1108,11 +1100,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_l1_bwd_finalize(
 // ------------------------------------------------------------------------------------------------
 // operand split: hi = tf32(x), lo = tf32(x - hi); zero padded to ld_dst columns
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
+__device__ __forceinline__ float to_tf32(float x) { return grapes_tf32_rna(x); }
 __global__ void __launch_bounds__(256) k_split_tf32(const float* __restrict__ src, int ld_src, int R, int K,
                                                     float* __restrict__ hi, float* __restrict__ lo, int ld_dst) {
     pdl_begin();
