@@ -27,7 +27,9 @@
 #define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/)
 
 static int g_tc_debug = 0;      // bit 0: backward operand debug fill; bit 1: force the streaming (non W-resident) forward;
-                                // bit 2: forward with the A operand in tensor memory (k_l1_fwd_ts); bit 3: backward likewise (k_l1_bwd_ts)
+                                // bit 2: forward with BOTH operands in shared memory (k_l1_fwd_tc) instead of the default
+                                // A-operand-in-tensor-memory form (k_l1_fwd_ts); bit 3: backward with its scaled operand in
+                                // tensor memory (k_l1_bwd_ts)
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -420,6 +422,7 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
     uint64_t* w_bar = bars + 28;
     uint64_t* yfull_bar = bars + 32;                 // [8]  TMA -> converters   (raw Y tile landed)
     uint64_t* yempty_bar = bars + 40;                // [8]  converters -> TMA   (tile read into registers)
+    uint32_t* s_mask = (uint32_t*)(bars + 48);       // [4 epilogue warps][32]: ballot words of one 32-column chunk
     uint32_t* tmem_slot = (uint32_t*)(bars + 29);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -551,15 +554,25 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
                         tmem_st_32x32(lane_base + (uint32_t)(2 * TC_BN + ch * 32), v);
                         continue;
                     }
+                    // relu mask: the ballot IS the transpose (bit r of column c's word = row r); the warp-uniform word is
+                    // parked in shared memory by one lane and picked up by lane c after the chunk -- two instructions per
+                    // column instead of the compare + select per column that routing it through registers costs.  Rows behind
+                    // n give junk bits: the backward multiplies them by dz = 0.
+                    uint32_t* sm = s_mask + (warp - 2) * 32;
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
                         const int col = nh * TC_BN + ch * 32 + c;
                         const float pre = __uint_as_float(v[c]) + __ldg(&b1[col]);
                         zsum = fmaf(fmaxf(pre, 0.f), __ldg(&w2[col]), zsum);
                         if (maskT) {
-                            const uint32_t word = __ballot_sync(GRAPES_FULL_MASK, pre > 0.f && row < n);
-                            if (lane == c) mbits[ch] = word;
+                            const uint32_t word = __ballot_sync(GRAPES_FULL_MASK, pre > 0.f);
+                            if (lane == 0) sm[c] = word;
                         }
+                    }
+                    if (maskT) {
+                        __syncwarp();
+                        mbits[ch] = sm[lane];
+                        __syncwarp();
                     }
                 }
                 tc_fence_before();
@@ -602,7 +615,7 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
                     for (int c = 0; c < 4; ++c) {
                         const float h = tf32_rna_f(x[c]);
                         hi[4 * i + c] = __float_as_uint(h);
-                        lo[4 * i + c] = __float_as_uint(tf32_rna_f(x[c] - h));
+                        lo[4 * i + c] = __float_as_uint(x[c] - h);    // exact; the tensor core drops its 13 low bits (2^-21 of x)
                     }
                 }
                 mbar_wait(&aempty_bar[slot], sphase ^ 1);             // the MMAs that read this slot have retired
@@ -1180,14 +1193,14 @@ int grapes_sampler_l1_fwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo,
     const int presplit = Y_lo ? 1 : 0;
     CUtensorMap ma, ma_lo, mb_hi, mb_lo;
     int rc;
-    if (!presplit && (g_tc_debug & 4)) {
+    if (!presplit && !(g_tc_debug & 4)) {
         // A operand in tensor memory (k_l1_fwd_ts): Y goes global -> registers -> TMEM, only W is staged in shared memory
         if ((rc = make_map(&mb_hi, W_hi, D, K, ldw)) != GRAPES_OK) return rc;
         if ((rc = make_map(&mb_lo, W_lo, D, K, ldw)) != GRAPES_OK) return rc;
         const int nkb = (K + TC_BK - 1) / TC_BK, NH = D / TC_BN;
         const int m_tiles_cap = (cap_n + TC_BM - 1) / TC_BM;
         if ((rc = make_map(&ma, Y, cap_n, K, ldy)) != GRAPES_OK) return rc;
-        const int tail_b = 1024 /*align slack*/ + 512 /*barriers*/;
+        const int tail_b = 1024 /*align slack*/ + 1024 /*barriers + mask words*/;
         // W half resident when it leaves room for >= 4 raw Y tiles; otherwise W streams through a 4-stage ring
         const int wres = (nkb * 2 * TC_TILE_BYTES + 4 * TC_TILE_BYTES + tail_b <= 227 * 1024 && ctx->sm_count >= NH) ? 1 : 0;
         const int bstages = 4;

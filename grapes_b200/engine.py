@@ -125,7 +125,8 @@ class GrapesEngine:
         self.use_tc = bool(use_tensor_cores) and (self.D % 128 == 0) and self.D <= 512
         self.use_tc_bwd = self.use_tc and self.D // 128 <= 2    # backward accumulators: halves x (hi | lo) x 128 columns of TMEM
         # default (GRAPES_Y_SINGLE=0 restores the pre-split pair): the aggregation writes Y once as fp32 and the tcgen05 kernels split it into (hi, lo) themselves
-        # (half the Y bytes written and read, one more pipeline step per k-block in the GEMMs; products-shape: aggregation 73.8 -> 60.8,
+        # (half the Y bytes written and read; the default forward k_l1_fwd_ts needs the raw fp32 Y: it splits it on the way into
+        # tensor memory; products-shape: aggregation 73.8 -> 60.8,
         # forward 120 -> 136, backward 155 -> 149 us per step, step 0.512 -> 0.508 ms)
         self.y_single = self.use_tc and os.environ.get("GRAPES_Y_SINGLE", "1" if self.Fp <= 1024 else "0") == "1"   # Cora-shape (K = 1436): the pair is 2 % faster
         if self.use_tc_bwd:

@@ -245,7 +245,8 @@ int grapes_sampler_l1_bwd(grapes_ctx* ctx, const float* Y, int ldy, const int* n
 int grapes_split_tf32(grapes_ctx* ctx, const float* src, int ld_src, int R, int K, float* hi, float* lo, int ld_dst,
                       void* stream);
 /* measurement knob of the tcgen05 kernels (bit 1: stream the weight tiles instead of keeping them resident; bit 2: the
- * forward with its A operand in tensor memory, k_l1_fwd_ts)                                                         */
+ * forward with both operands in shared memory, k_l1_fwd_tc, instead of the default k_l1_fwd_ts whose A operand lives in
+ * tensor memory; bit 3: the backward with its scaled-feature operand in tensor memory, k_l1_bwd_ts)                     */
 int grapes_tc_debug(int flags);
 int grapes_sampler_l1_fwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo, int ldy, const int* n_dev, int cap_n,
                              int K, const float* W_hi, const float* W_lo, int ldw, int D, const float* b1,

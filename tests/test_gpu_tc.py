@@ -134,9 +134,11 @@ def test_l1_bwd_tc_matches_fp64_autograd(cuda_device, n, cap_n, K, D, extra, pre
                                          (5000, 5000, 605, 256), (1, 128, 100, 256), (777, 900, 1436, 384),
                                          (3000, 3000, 131, 256), (40000, 40001, 100, 256)])
 def test_l1_fwd_ts_tensor_memory_operand(cuda_device, n, cap_n, K, D):
-    """k_l1_fwd_ts (the Y tile goes global -> registers -> tensor memory, the MMA takes its A operand from TMEM) against
-    float64 at 1e-5, and against k_l1_fwd_tc: same operand split, same MMA order, same epilogue -> the same bits, z and
-    relu mask.  Stale rows behind n and columns behind K (indicator-like values) must not leak."""
+    """k_l1_fwd_ts (default forward: raw Y tile -> TMA ring -> registers -> tensor memory, the MMA takes its A operand
+    from TMEM) against float64 at 1e-5, and against k_l1_fwd_tc (both operands in shared memory, grapes_tc_debug bit 2):
+    same MMA order and epilogue; the lo part of the split is left unrounded here (the tensor core drops its low bits), so
+    z agrees to fp32 rounding and the relu mask away from the kink.  Stale rows behind n and columns behind K
+    (indicator-like values) must not leak."""
     from grapes_b200._lib import lib
     g = torch.Generator().manual_seed(n + K)
     ldy = (K + 1 + 3) // 4 * 4
@@ -146,16 +148,21 @@ def test_l1_fwd_ts_tensor_memory_operand(cuda_device, n, cap_n, K, D):
     w2 = torch.randn(D, generator=g) * 0.1
     ref = (torch.relu(Y[:n, :K].double() @ W1.double().t() + b1.double()) * w2.double()).sum(1)
     args = (Y.to(cuda_device), W1.to(cuda_device), b1.to(cuda_device), w2.to(cuda_device), n, cuda_device)
-    z_tc, m_tc = _run_tc(*args, with_mask=True, presplit=False)
+    z_ts, m_ts = _run_tc(*args, with_mask=True, presplit=False)
     try:
         lib().cdll.grapes_tc_debug(4)
-        z_ts, m_ts = _run_tc(*args, with_mask=True, presplit=False)
+        z_tc, m_tc = _run_tc(*args, with_mask=True, presplit=False)
     finally:
         lib().cdll.grapes_tc_debug(0)
     err = (z_ts.double().cpu() - ref).abs().max() / ref.abs().max()
     assert err < 1e-5, f"relative error {err:.3e}"
-    assert torch.equal(z_ts, z_tc)
-    assert torch.equal(m_ts[: (n + 31) // 32], m_tc[: (n + 31) // 32])
+    assert ((z_ts - z_tc).abs().max() / z_tc.abs().max()).item() < 2e-6
+    rows = torch.arange(n)
+    bits = [((m.cpu()[rows // 32] >> (rows % 32).unsqueeze(1)) & 1).bool() for m in (m_ts, m_tc)]
+    pre = Y[:n, :K].double() @ W1.double().t() + b1.double()
+    clear = pre.abs() > 1e-4 * pre.abs().max()
+    assert torch.equal(bits[0][clear], bits[1][clear]) and torch.equal(bits[0][clear], (pre > 0)[clear])
+    assert (bits[0] != bits[1]).sum() <= 4
 
 
 @pytest.mark.parametrize("n,cap_n,K,D,extra", [(3000, 3072, 104, 256, 0), (64943, 66000, 104, 256, 0), (100, 128, 15, 128, 0),
