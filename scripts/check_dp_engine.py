@@ -96,8 +96,12 @@ def main():
         finals[exchange] = eng.params.clone()
         if exchange == "peer":
             keep = (st, eng)
-    rel = ((finals["peer"] - finals["nccl"]).abs().max() / finals["nccl"].abs().max()).item()
-    assert rel < 1e-4, f"peer vs nccl parameters after 7 steps: {rel:.2e}"
+    # the two exchanges add the ranks' gradients in different orders: a last-bit difference, which Adam's first updates
+    # (~ lr * sign(g)) turn into a 2*lr flip on entries whose gradient is zero up to rounding -- bounded, and rare
+    diff = (finals["peer"] - finals["nccl"]).abs()
+    assert diff.max().item() <= 2.0 * 1e-3 * 7 * 1.01, f"peer vs nccl parameters: {diff.max().item():.3e} beyond the sign-flip bound"
+    rel = (diff > 1e-4 * finals["nccl"].abs().max()).double().mean().item()
+    assert rel < 0.02, f"{rel:.4f} of the parameters differ by > 1e-4 between the peer and the NCCL exchange"
 
     # ---- a peer that never arrives: flagged, no-op, sticky (rank 0 steps alone) ----
     st, eng = keep
@@ -105,7 +109,7 @@ def main():
     if rank == 0:
         before = (eng.params.clone(), eng.exp_avg.clone(), eng.exp_avg_sq.clone(), eng.adam_steps.clone())
         for _ in range(2):
-            eng.step(tr[mine[7] * B:(mine[7] + 1) * B].to(dev), apply_optim=True)
+            eng.step(tr[mine[0] * B:(mine[0] + 1) * B].to(dev), apply_optim=True)
             torch.cuda.synchronize()
             assert int(eng.scalars()["flags"]) & 32, "timeout not reported in the step's flag word"
             for a_, b_ in zip(before, (eng.params, eng.exp_avg, eng.exp_avg_sq, eng.adam_steps)):
@@ -117,9 +121,14 @@ def main():
             assert "exchange failed" in str(e)
     dist.barrier()
     if rank == 0:
-        print(f"dp engine ok: world={world} peer-vs-nccl max rel param diff {rel:.2e}", flush=True)
+        print(f"dp engine ok: world={world}; parameters off by > 1e-4 between peer and NCCL exchange: {rel:.4f}", flush=True)
     dist.destroy_process_group()
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException:
+        import traceback
+        print("RANK", os.environ.get("RANK"), "FAILED:\n" + traceback.format_exc(), flush=True)
+        raise

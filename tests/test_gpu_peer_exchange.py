@@ -31,5 +31,5 @@ def test_engine_data_parallel_step_equals_mean_of_oracle_gradients(cuda_device):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29543", os.path.join(ROOT, "scripts", "check_dp_engine.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert res.returncode == 0, res.stdout[-6000:] + res.stderr[-2000:]
     assert "dp engine ok" in res.stdout
