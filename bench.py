@@ -38,9 +38,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-spmm", action="store_true", help="skip the whole-graph SpMM leg")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl", "none"],
                     help="N > 1: 'peer' = gradient scale + push all-reduce + Adam as ONE kernel over NVLink peer memory inside "
-                         "the step graph (default); 'nccl' = ncclAllReduce(AVG) of the flat gradient captured into the step graph")
+                         "the step graph (default); 'nccl' = ncclAllReduce(AVG) of the flat gradient captured into the step graph; "
+                         "'none' = DIAGNOSTIC ONLY: the ranks train independent replicas (no exchange), to price the exchange")
     ap.add_argument("--prime", type=int, default=40, help="untimed steps before the W warm-up steps (clocks, allocator, graph variants, communicator)")
     ap.add_argument("--no-prefetch", action="store_true", help="no cross-step prefetch of the next batch's hop-0 front end")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)
@@ -325,7 +326,7 @@ def main():
     # flat gradient (91 k floats on products-shape), fused with the gradient scale and both Adam updates into the step's
     # last launch over NVLink peer memory ('peer'), or ncclAllReduce captured into the step graph ('nccl').  Either way a
     # step is one graph launch and every rank ends it with bit-identical parameters.
-    if world > 1:
+    if world > 1 and args.exchange != "none":
         eng.enable_data_parallel(exchange=args.exchange)
 
     def one_step(j):
@@ -560,7 +561,7 @@ def main():
                 "roofline": roof, "rooflines": rooflines, "spmm": spmm, "csr_build": csr_build, "cpu_baseline": cpu, "breakdown_ms_per_step": breakdown,
                 "frontier": per_hop, "cuda_graph": use_graph, "cross_step_prefetch": prefetch,
                 "step_times": step_times, "prime_steps": PRIME,
-                "gradient_exchange": ("none" if world == 1 else
+                "gradient_exchange": ("none" if world == 1 else "NONE (diagnostic run: independent replicas, not data parallel)" if args.exchange == "none" else
                                       ("gradient scale + push all-reduce over NVLink peer memory + Adam: one kernel inside the step graph"
                                        if args.exchange == "peer" else "ncclAllReduce(AVG) captured into the step graph + Adam launch"))}
         emit(line)
