@@ -321,7 +321,10 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) k_l1_fwd_tc(
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            if (row < n) zpart[(size_t)nh * cap_n + row] = zsum;
+            if (row < n) {                                        // two partial rows per half (k_l1_fwd_ts fills both)
+                zpart[(size_t)(nh * 2) * cap_n + row] = zsum;
+                zpart[(size_t)(nh * 2 + 1) * cap_n + row] = 0.f;
+            }
             if (maskT) {
                 // maskT[(row group of 32)][D]: bit r of word (g, d) = relu'(pre[32 g + r, d])
                 uint32_t* dst = maskT + (size_t)(mt * 4 + q) * D + nh * TC_BN;
@@ -422,7 +425,6 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
     uint64_t* w_bar = bars + 28;
     uint64_t* yfull_bar = bars + 32;                 // [8]  TMA -> converters   (raw Y tile landed)
     uint64_t* yempty_bar = bars + 40;                // [8]  converters -> TMA   (tile read into registers)
-    uint32_t* s_mask = (uint32_t*)(bars + 48);       // [4 epilogue warps][32]: ballot words of one 32-column chunk
     uint32_t* tmem_slot = (uint32_t*)(bars + 29);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -438,10 +440,10 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
-        for (int s = 0; s < 4; ++s) { mbar_init(&conv_bar[s], 8); mbar_init(&aempty_bar[s], 1); }
-        for (int s = 0; s < 8; ++s) { mbar_init(&yfull_bar[s], 1); mbar_init(&yempty_bar[s], 8); }
+        for (int s = 0; s < 4; ++s) { mbar_init(&conv_bar[s], 4); mbar_init(&aempty_bar[s], 1); }
+        for (int s = 0; s < 8; ++s) { mbar_init(&yfull_bar[s], 1); mbar_init(&yempty_bar[s], 4); }
         for (int s = 0; s < 8; ++s) { mbar_init(&bfull_bar[s], 1); mbar_init(&bempty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 8); }
         mbar_init(w_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -526,21 +528,25 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
                 }
             }
         }
-    } else if (warp < 6) {
-        // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4 =====
+    } else if (warp < 10) {
+        // ===== epilogue (warps 2..9): TMEM lane quarter = warp % 4, column half of the tile = (warp - 2) / 4.  Two warps
+        // per quarter: one warp per quarter needed ~2800 cycles per tile (a dependent fma chain over 128 columns plus a
+        // ballot per column) against 2550 cycles of MMA -- the epilogue, not the tensor pipe, set the pace =====
         const int q = warp & 3;
+        const int eh = (warp - 2) >> 2;
         int acc = 0; uint32_t acc_phase = 0;
         for (int t = t_first; t < m_tiles; t += t_step) {
             const int mt = t;
             const int row = mt * TC_BM + q * 32 + lane;
-            float zsum = 0.f;
-            uint32_t mbits[4] = {0u, 0u, 0u, 0u};
+            float zs0 = 0.f, zs1 = 0.f, zs2 = 0.f, zs3 = 0.f;     // four independent chains, combined in a fixed order
+            uint32_t mbits[2] = {0u, 0u};
             for (int kc = 0; kc < nkb; kc += TC_CHUNK_KB) {
                 const bool first_chunk = (kc == 0), last_chunk = (kc + TC_CHUNK_KB >= nkb);
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
 #pragma unroll
-                for (int ch = 0; ch < TC_BN / 32; ++ch) {
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int ch = eh * 2 + cc;                          // 32-column chunk of the 128-column half
                     uint32_t v[32];
                     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
                     tmem_ld_32x32(lane_base + (uint32_t)(acc * TC_BN + ch * 32), v);
@@ -554,25 +560,29 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
                         tmem_st_32x32(lane_base + (uint32_t)(2 * TC_BN + ch * 32), v);
                         continue;
                     }
-                    // relu mask: the ballot IS the transpose (bit r of column c's word = row r); the warp-uniform word is
-                    // parked in shared memory by one lane and picked up by lane c after the chunk -- two instructions per
-                    // column instead of the compare + select per column that routing it through registers costs.  Rows behind
-                    // n give junk bits: the backward multiplies them by dz = 0.
-                    uint32_t* sm = s_mask + (warp - 2) * 32;
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
+                    for (int c = 0; c < 32; c += 4) {
                         const int col = nh * TC_BN + ch * 32 + c;
-                        const float pre = __uint_as_float(v[c]) + __ldg(&b1[col]);
-                        zsum = fmaf(fmaxf(pre, 0.f), __ldg(&w2[col]), zsum);
+                        const float p0 = __uint_as_float(v[c]) + __ldg(&b1[col]);
+                        const float p1 = __uint_as_float(v[c + 1]) + __ldg(&b1[col + 1]);
+                        const float p2 = __uint_as_float(v[c + 2]) + __ldg(&b1[col + 2]);
+                        const float p3 = __uint_as_float(v[c + 3]) + __ldg(&b1[col + 3]);
+                        zs0 = fmaf(fmaxf(p0, 0.f), __ldg(&w2[col]), zs0);
+                        zs1 = fmaf(fmaxf(p1, 0.f), __ldg(&w2[col + 1]), zs1);
+                        zs2 = fmaf(fmaxf(p2, 0.f), __ldg(&w2[col + 2]), zs2);
+                        zs3 = fmaf(fmaxf(p3, 0.f), __ldg(&w2[col + 3]), zs3);
                         if (maskT) {
-                            const uint32_t word = __ballot_sync(GRAPES_FULL_MASK, pre > 0.f);
-                            if (lane == 0) sm[c] = word;
+                            // the ballot IS the transpose (bit r of column c's word = row r).  Rows behind n give junk
+                            // bits: the backward multiplies them by dz = 0.
+                            const uint32_t w0 = __ballot_sync(GRAPES_FULL_MASK, p0 > 0.f);
+                            const uint32_t w1 = __ballot_sync(GRAPES_FULL_MASK, p1 > 0.f);
+                            const uint32_t w2b = __ballot_sync(GRAPES_FULL_MASK, p2 > 0.f);
+                            const uint32_t w3 = __ballot_sync(GRAPES_FULL_MASK, p3 > 0.f);
+                            if ((lane >> 2) == (c >> 2)) {
+                                const int sub = lane & 3;
+                                mbits[cc] = sub == 0 ? w0 : sub == 1 ? w1 : sub == 2 ? w2b : w3;
+                            }
                         }
-                    }
-                    if (maskT) {
-                        __syncwarp();
-                        mbits[ch] = sm[lane];
-                        __syncwarp();
                     }
                 }
                 tc_fence_before();
@@ -580,36 +590,36 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            if (row < n) zpart[(size_t)nh * cap_n + row] = zsum;
+            // partial row dot of this warp's 64 columns: zpart[2 nh + eh][row]
+            if (row < n) zpart[(size_t)(nh * 2 + eh) * cap_n + row] = (zs0 + zs1) + (zs2 + zs3);
             if (maskT) {
                 // maskT[(row group of 32)][D]: bit r of word (g, d) = relu'(pre[32 g + r, d])
-                uint32_t* dst = maskT + (size_t)(mt * 4 + q) * D + nh * TC_BN;
+                uint32_t* dst = maskT + (size_t)(mt * 4 + q) * D + nh * TC_BN + eh * 64;
 #pragma unroll
-                for (int ch = 0; ch < 4; ++ch) dst[ch * 32 + lane] = mbits[ch];
+                for (int cc = 0; cc < 2; ++cc) dst[cc * 32 + lane] = mbits[cc];
             }
         }
     } else {
-        // ===== converters (warps 6..13): raw Y tile in shared memory -> registers -> (hi, lo) in the TMEM slot =====
+        // ===== converters (warps 10..13): raw Y tile in shared memory -> registers -> (hi, lo) in the TMEM slot =====
         const int q = warp & 3;                                       // TMEM lane quarter this warp may touch
-        const int half = (warp - 6) >> 2;                             // columns [16 half, 16 half + 16) of the k-block
         const int r_in = q * 32 + lane;                               // tile row == TMEM lane
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + a_col0 + (uint32_t)(half * 16);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + a_col0;
         int slot = 0; uint32_t sphase = 0;
         int ys = 0; uint32_t yphase = 0;
         for (int t = t_first; t < m_tiles; t += t_step) {
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(&yfull_bar[ys], yphase);
                 const uint8_t* tile = y_ring + ys * TC_TILE_BYTES + r_in * 128;
-                float4 cur[4];
+                float4 cur[8];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)                            // SWIZZLE_128B: 16-byte chunk index ^ (row % 8)
-                    cur[i] = *reinterpret_cast<const float4*>(tile + ((((half * 4 + i) ^ (r_in & 7))) << 4));
+                for (int i = 0; i < 8; ++i)                            // SWIZZLE_128B: 16-byte chunk index ^ (row % 8)
+                    cur[i] = *reinterpret_cast<const float4*>(tile + ((i ^ (r_in & 7)) << 4));
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&yempty_bar[ys]);          // the tile is in registers: the slot may be refilled
                 if (++ys == ystages) { ys = 0; yphase ^= 1; }
-                uint32_t hi[16], lo[16];
+                uint32_t hi[32], lo[32];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < 8; ++i) {
                     const float x[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
@@ -620,9 +630,8 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
                 }
                 mbar_wait(&aempty_bar[slot], sphase ^ 1);             // the MMAs that read this slot have retired
                 tc_fence_after();
-                tmem_st_32x32_x16(lane_addr + (uint32_t)(slot * 64), hi);
-                tmem_st_32x32_x16(lane_addr + (uint32_t)(slot * 64 + 32), lo);
-                tmem_wait_st();
+                tmem_st_32x32(lane_addr + (uint32_t)(slot * 64), hi);
+                tmem_st_32x32(lane_addr + (uint32_t)(slot * 64 + 32), lo);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&conv_bar[slot]);
@@ -1181,7 +1190,7 @@ int grapes_split_tf32(grapes_ctx* ctx, const float* src, int ld_src, int R, int 
     return GRAPES_OK;
 }
 
-// zpart[D/128][cap_n]: per 128-column half partial row dots (summed by the caller, e.g. grapes_select_hop).
+// zpart[2 * D/128][cap_n]: partial row dots, two per 128-column half (summed by the caller, e.g. grapes_select_hop).
 // Y_lo == NULL: Y is plain fp32 and is split into the 3xTF32 (hi, lo) pair inside the kernel; otherwise (Y, Y_lo) is
 // the pair grapes_aggregate wrote (faster: one pipeline step less per k-block).
 int grapes_sampler_l1_fwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo, int ldy, const int* n_dev, int cap_n,

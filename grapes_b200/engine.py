@@ -213,7 +213,7 @@ class GrapesEngine:
             if self.use_tc:
                 self.Wgf_hi, self.Wgf_lo = z((D, self.ldW), **f32), z((D, self.ldW), **f32)
                 self.Wz_hi, self.Wz_lo = z((D, self.ldW), **f32), z((D, self.ldW), **f32)
-                self.zpart, self.zpart_z = z((D // 128, cap_n), **f32), z((D // 128, cap_n), **f32)
+                self.zpart, self.zpart_z = z((2 * (D // 128), cap_n), **f32), z((2 * (D // 128), cap_n), **f32)   # two partial rows per 128-unit half
                 if self.use_tc_bwd:
                     self.mask_z = z(((cap_n + 127) // 128 * 4, D), **i32)
             else:
@@ -471,7 +471,7 @@ class GrapesEngine:
                     L.grapes_sampler_l1_fwd_tc(ctx, ptr(hw.Y), ptr(hw.Y_lo), self.ldY, n_dev, cap_n, Fp,
                                                ptr(self.Wgf_hi), ptr(self.Wgf_lo), self.ldW, D, self._par(gf.b1),
                                                self._par(gf.W2), ptr(self.zpart), ptr(hw.mask_gf), st)
-                    z_ptr, z_parts, z_stride = ptr(self.zpart), D // 128, cap_n
+                    z_ptr, z_parts, z_stride = ptr(self.zpart), 2 * (D // 128), cap_n
                 else:
                     L.grapes_sampler_l1_fwd(ctx, ptr(hw.Y), self.ldY, n_dev, cap_n, Fp, self._par(gf.W1), Fp, D,
                                             self._par(gf.b1), self._par(gf.W2), ptr(self.z_gf), st)
@@ -652,7 +652,7 @@ class GrapesEngine:
                 L.grapes_sampler_l1_fwd_tc(ctx, ptr(hw.Y), ptr(hw.Y_lo), self.ldY, n_dev, cap_n, Fp, ptr(self.Wgf_hi),
                                            ptr(self.Wgf_lo), self.ldW, D, self._par(gf.b1), self._par(gf.W2),
                                            ptr(self.zpart), ptr(hw.mask_gf), st)
-                z_ptr, z_parts, z_stride = ptr(self.zpart), D // 128, cap_n
+                z_ptr, z_parts, z_stride = ptr(self.zpart), 2 * (D // 128), cap_n
             else:
                 L.grapes_sampler_l1_fwd(ctx, ptr(hw.Y), self.ldY, n_dev, cap_n, Fp, self._par(gf.W1), Fp, D,
                                         self._par(gf.b1), self._par(gf.W2), ptr(self.z_gf), st)
@@ -802,7 +802,7 @@ class GrapesEngine:
             L.grapes_sampler_l1_fwd_tc(ctx, ptr(hw.Y), ptr(hw.Y_lo), self.ldY, n_dev, cap_n, F, ptr(self.Wz_hi),
                                        ptr(self.Wz_lo), self.ldW, D, self._par(nz.b1), self._par(nz.W2),
                                        ptr(self.zpart_z), ptr(self.mask_z) if self.use_tc_bwd else None, st)
-            L.grapes_aggregate_scalar(ctx, ptr(self.zpart_z), D // 128, cap_n, n_dev, cap_n, ptr(hw.in_off),
+            L.grapes_aggregate_scalar(ctx, ptr(self.zpart_z), 2 * (D // 128), cap_n, n_dev, cap_n, ptr(hw.in_off),
                                       ptr(hw.in_src), ptr(hw.dinv), self._par(nz.b2), ptr(self.zlogits), None, st)
         else:
             L.grapes_sampler_l1_fwd(ctx, ptr(hw.Y), self.ldY, n_dev, cap_n, F, self._par(nz.W1), F, D,

@@ -241,7 +241,7 @@ int grapes_sampler_l1_bwd(grapes_ctx* ctx, const float* Y, int ldy, const int* n
 /* tcgen05 path of the same layer (sm_100a tensor cores, 3xTF32 split operands, TMA + TMEM).  (Y, Y_lo) is the
  * (hi, lo) pair grapes_aggregate's out_hi/out_lo wrote; Y_lo == NULL means Y is plain fp32 and is split inside the
  * kernels (no hi/lo copies in HBM, one more pipeline step).  Weights are pre-split with grapes_split_tf32;
- * zpart[D/128][cap_n] partial row dots; maskT[(rows/32)][D] relu mask bits (optional).                            */
+ * zpart[2 * D/128][cap_n] partial row dots (two per 128-column half: sum them); maskT[(rows/32)][D] relu mask bits (optional).                            */
 int grapes_split_tf32(grapes_ctx* ctx, const float* src, int ld_src, int R, int K, float* hi, float* lo, int ld_dst,
                       void* stream);
 /* measurement knob of the tcgen05 kernels (bit 1: stream the weight tiles instead of keeping them resident; bit 2: the

@@ -28,7 +28,7 @@ def _run_tc(Y, W1, b1, w2, n, dev, with_mask=False, presplit=True):
     ldw = (K + 3) // 4 * 4
     Wh = torch.empty((D, ldw), device=dev); Wl = torch.empty((D, ldw), device=dev)
     L.grapes_split_tf32(ctx, ptr(W1), K, D, K, ptr(Wh), ptr(Wl), ldw, st)
-    zpart = torch.zeros((D // 128, cap_n), device=dev)
+    zpart = torch.zeros((2 * (D // 128), cap_n), device=dev)
     cnt = torch.tensor([n], dtype=torch.int32, device=dev)
     maskT = torch.zeros(((cap_n + 127) // 128 * 4, D), dtype=torch.int32, device=dev) if with_mask else None
     Ya, Yb = _split(Y, presplit, dev)
@@ -104,7 +104,7 @@ def test_l1_bwd_tc_matches_fp64_autograd(cuda_device, n, cap_n, K, D, extra, pre
     ldw = (K + 3) // 4 * 4
     Wh, Wl = torch.empty((D, ldw), device=dev), torch.empty((D, ldw), device=dev)
     L.grapes_split_tf32(ctx, ptr(W1d), K, D, K, ptr(Wh), ptr(Wl), ldw, st)
-    zpart = torch.zeros((D // 128, cap_n), device=dev)
+    zpart = torch.zeros((2 * (D // 128), cap_n), device=dev)
     cnt = torch.tensor([n], dtype=torch.int32, device=dev)
     maskT = torch.zeros(((cap_n + 127) // 128 * 4, D), dtype=torch.int32, device=dev)
     Ya, Yb = _split(Yd, presplit, dev)
@@ -193,7 +193,7 @@ def test_l1_bwd_ts_tensor_memory_operand(cuda_device, n, cap_n, K, D, extra):
     ldw = (K + 3) // 4 * 4
     Wh, Wl = torch.empty((D, ldw), device=dev), torch.empty((D, ldw), device=dev)
     L.grapes_split_tf32(ctx, ptr(W1d), K, D, K, ptr(Wh), ptr(Wl), ldw, st)
-    zpart = torch.zeros((D // 128, cap_n), device=dev)
+    zpart = torch.zeros((2 * (D // 128), cap_n), device=dev)
     cnt = torch.tensor([n], dtype=torch.int32, device=dev)
     maskT = torch.zeros(((cap_n + 127) // 128 * 4, D), dtype=torch.int32, device=dev)
     L.grapes_sampler_l1_fwd_tc(ctx, ptr(Yd), None, ldy, ptr(cnt), cap_n, K, ptr(Wh), ptr(Wl), ldw, D, ptr(b1d),
