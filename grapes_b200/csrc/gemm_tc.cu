@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
     const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB_hi,
     const __grid_constant__ CUtensorMap tmB_lo, const int* __restrict__ n_dev, int cap_n, int K, int D, int wres,
     int bstages, int ystages, const float* __restrict__ b1, const float* __restrict__ w2, float* __restrict__ zpart,
-    uint32_t* __restrict__ maskT) {
+    uint32_t* __restrict__ maskT, unsigned long long* dbg) {
     pdl_begin();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // SWIZZLE_128B tiles: 1024 B aligned
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
         for (int s = 0; s < 4; ++s) { mbar_init(&conv_bar[s], 4); mbar_init(&aempty_bar[s], 1); }
         for (int s = 0; s < 8; ++s) { mbar_init(&yfull_bar[s], 1); mbar_init(&yempty_bar[s], 4); }
         for (int s = 0; s < 8; ++s) { mbar_init(&bfull_bar[s], 1); mbar_init(&bempty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 8); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
         mbar_init(w_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -452,6 +452,15 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // grapes_tc_debug bit 4: CTA 0 records globaltimer stamps (MMA issuer: [0] start, [1] W resident, [2 + i] tile i
+    // committed; epilogue warp 2: [32 + i] tile i drained; converter warp 6: [64 + i] its i-th k-block stored)
+    auto stamp = [&](int slot) {
+        if (dbg && blockIdx.x == 0 && slot < 96) {
+            unsigned long long tt;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
+            dbg[slot] = tt;
+        }
+    };
 
     if (warp == 0) {
         // ===== TMA: W (once, or through its ring) and the raw Y tiles =====
@@ -489,7 +498,10 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
             int slot = 0; uint32_t sphase = 0;
             int bst = 0; uint32_t bphase = 0;
             int acc = 0; uint32_t acc_phase = 0;
+            stamp(0);
             if (wres && t_first < m_tiles) { mbar_wait(w_bar, 0); tc_fence_after(); }
+            stamp(1);
+            int tile_no = 0;
             const uint32_t wa = smem_u32(w_smem);
             for (int t = t_first; t < m_tiles; t += t_step) {
                 for (int kc = 0; kc < nkb; kc += TC_CHUNK_KB) {          // the tensor core adds with truncation: keep chains short
@@ -526,27 +538,25 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
                     umma_commit(&tfull_bar[acc]);                         // chunk accumulator complete -> epilogue
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
+                stamp(2 + tile_no++);
             }
         }
-    } else if (warp < 10) {
-        // ===== epilogue (warps 2..9): TMEM lane quarter = warp % 4, column half of the tile = (warp - 2) / 4.  Two warps
-        // per quarter: one warp per quarter needed ~2800 cycles per tile (a dependent fma chain over 128 columns plus a
-        // ballot per column) against 2550 cycles of MMA -- the epilogue, not the tensor pipe, set the pace =====
+    } else if (warp < 6) {
+        // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4 =====
         const int q = warp & 3;
-        const int eh = (warp - 2) >> 2;
         int acc = 0; uint32_t acc_phase = 0;
+        int tile_no = 0;
         for (int t = t_first; t < m_tiles; t += t_step) {
             const int mt = t;
             const int row = mt * TC_BM + q * 32 + lane;
             float zs0 = 0.f, zs1 = 0.f, zs2 = 0.f, zs3 = 0.f;     // four independent chains, combined in a fixed order
-            uint32_t mbits[2] = {0u, 0u};
+            uint32_t mbits[4] = {0u, 0u, 0u, 0u};
             for (int kc = 0; kc < nkb; kc += TC_CHUNK_KB) {
                 const bool first_chunk = (kc == 0), last_chunk = (kc + TC_CHUNK_KB >= nkb);
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
 #pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    const int ch = eh * 2 + cc;                          // 32-column chunk of the 128-column half
+                for (int ch = 0; ch < TC_BN / 32; ++ch) {
                     uint32_t v[32];
                     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
                     tmem_ld_32x32(lane_base + (uint32_t)(acc * TC_BN + ch * 32), v);
@@ -580,7 +590,7 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
                             const uint32_t w3 = __ballot_sync(GRAPES_FULL_MASK, p3 > 0.f);
                             if ((lane >> 2) == (c >> 2)) {
                                 const int sub = lane & 3;
-                                mbits[cc] = sub == 0 ? w0 : sub == 1 ? w1 : sub == 2 ? w2b : w3;
+                                mbits[ch] = sub == 0 ? w0 : sub == 1 ? w1 : sub == 2 ? w2b : w3;
                             }
                         }
                     }
@@ -590,24 +600,34 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            // partial row dot of this warp's 64 columns: zpart[2 nh + eh][row]
-            if (row < n) zpart[(size_t)(nh * 2 + eh) * cap_n + row] = (zs0 + zs1) + (zs2 + zs3);
+            if (row < n) {                                        // two partial rows per half: (chains 0, 1) and (chains 2, 3)
+                zpart[(size_t)(nh * 2) * cap_n + row] = zs0 + zs1;
+                zpart[(size_t)(nh * 2 + 1) * cap_n + row] = zs2 + zs3;
+            }
             if (maskT) {
                 // maskT[(row group of 32)][D]: bit r of word (g, d) = relu'(pre[32 g + r, d])
-                uint32_t* dst = maskT + (size_t)(mt * 4 + q) * D + nh * TC_BN + eh * 64;
+                uint32_t* dst = maskT + (size_t)(mt * 4 + q) * D + nh * TC_BN;
 #pragma unroll
-                for (int cc = 0; cc < 2; ++cc) dst[cc * 32 + lane] = mbits[cc];
+                for (int ch = 0; ch < 4; ++ch) dst[ch * 32 + lane] = mbits[ch];
             }
+            if (warp == 2 && lane == 0) stamp(32 + tile_no);
+            ++tile_no;
         }
     } else {
-        // ===== converters (warps 10..13): raw Y tile in shared memory -> registers -> (hi, lo) in the TMEM slot =====
+        // ===== converters (warps 6..13): raw Y tile in shared memory -> registers -> (hi, lo) in the TMEM slot.
+        // Two groups of four warps (one per TMEM lane quarter) take the k-blocks ALTERNATELY: one k-block costs a warp a
+        // chain of latencies (barrier, shared-memory load, tcgen05.st + wait, fence, arrive: ~900 cycles) that is longer
+        // than the 786 cycles its MMAs take -- with every warp on every k-block the converters set the pace =====
         const int q = warp & 3;                                       // TMEM lane quarter this warp may touch
+        const int grp = (warp - 6) >> 2;                              // k-blocks it == grp (mod 2)
         const int r_in = q * 32 + lane;                               // tile row == TMEM lane
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + a_col0;
-        int slot = 0; uint32_t sphase = 0;
-        int ys = 0; uint32_t yphase = 0;
+        int it = 0;                                                   // running k-block count of this CTA
         for (int t = t_first; t < m_tiles; t += t_step) {
-            for (int kb = 0; kb < nkb; ++kb) {
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                if ((it & 1) != grp) continue;
+                const int ys = it % ystages, slot = it % aslots;
+                const uint32_t yphase = (uint32_t)((it / ystages) & 1), sphase = (uint32_t)((it / aslots) & 1);
                 mbar_wait(&yfull_bar[ys], yphase);
                 const uint8_t* tile = y_ring + ys * TC_TILE_BYTES + r_in * 128;
                 float4 cur[8];
@@ -616,7 +636,6 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
                     cur[i] = *reinterpret_cast<const float4*>(tile + ((i ^ (r_in & 7)) << 4));
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&yempty_bar[ys]);          // the tile is in registers: the slot may be refilled
-                if (++ys == ystages) { ys = 0; yphase ^= 1; }
                 uint32_t hi[32], lo[32];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -635,7 +654,7 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&conv_bar[slot]);
-                if (++slot == aslots) { slot = 0; sphase ^= 1; }
+                if (warp == 6 && lane == 0) stamp(64 + (it >> 1));
             }
         }
     }
@@ -1175,6 +1194,9 @@ static int make_map(CUtensorMap* m, const float* base, int rows, int cols, int l
 extern "C" {
 
 int grapes_tc_debug(int flags) { g_tc_debug = flags; return 0; }
+// debugging aid (scripts/trace_fwd_ts.py): device address of the ctx's split-K partial buffer, where grapes_tc_debug bit 4
+// parks the phase stamps of k_l1_fwd_ts
+int64_t grapes_debug_partials(grapes_ctx* ctx) { return ctx ? (int64_t)(uintptr_t)ctx->partials : 0; }
 
 int grapes_split_tf32(grapes_ctx* ctx, const float* src, int ld_src, int R, int K, float* hi, float* lo, int ld_dst,
                       void* stream) {
@@ -1227,7 +1249,8 @@ int grapes_sampler_l1_fwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo,
             have = smem_bytes;
         }
         pdl((k_l1_fwd_ts), per_half * NH, TCS_THREADS, smem_bytes, (cudaStream_t)stream)(ma, mb_hi, mb_lo, n_dev, cap_n, K, D, wres,
-                                                                                        bstages, ystages, b1, w2, zpart, maskT);
+                                                                                        bstages, ystages, b1, w2, zpart, maskT,
+                                                                                        (g_tc_debug & 16) ? reinterpret_cast<unsigned long long*>(ctx->partials) : nullptr);
         grapes_count_launches(1);
         GRAPES_LAUNCH_OK();
         return GRAPES_OK;

@@ -248,6 +248,9 @@ int grapes_split_tf32(grapes_ctx* ctx, const float* src, int ld_src, int R, int 
  * forward with both operands in shared memory, k_l1_fwd_tc, instead of the default k_l1_fwd_ts whose A operand lives in
  * tensor memory; bit 3: the backward with its scaled-feature operand in tensor memory, k_l1_bwd_ts)                     */
 int grapes_tc_debug(int flags);
+/* debugging aid (scripts/trace_fwd_ts.py): device address of the ctx's split-K partial buffer, where grapes_tc_debug bit 4
+ * makes k_l1_fwd_ts park the globaltimer stamps of CTA 0's MMA issuer / epilogue / converter warps                  */
+int64_t grapes_debug_partials(grapes_ctx* ctx);
 int grapes_sampler_l1_fwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo, int ldy, const int* n_dev, int cap_n,
                              int K, const float* W_hi, const float* W_lo, int ldw, int D, const float* b1,
                              const float* w2, float* zpart, uint32_t* maskT, void* stream);
