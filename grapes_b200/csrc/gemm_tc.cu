@@ -426,6 +426,8 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
     uint64_t* yfull_bar = bars + 32;                 // [8]  TMA -> converters   (raw Y tile landed)
     uint64_t* yempty_bar = bars + 40;                // [8]  converters -> TMA   (tile read into registers)
     uint32_t* tmem_slot = (uint32_t*)(bars + 29);
+    float* s_b1 = (float*)(bars + 48);               // [128] bias of this CTA's hidden half
+    float* s_w2 = s_b1 + TC_BN;                      // [128] output weights of the half
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = min(*n_dev, cap_n);
@@ -448,6 +450,10 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + TC_BN) {
+        s_b1[threadIdx.x - 64] = b1[nh * TC_BN + threadIdx.x - 64];
+        s_w2[threadIdx.x - 64] = w2[nh * TC_BN + threadIdx.x - 64];
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -557,6 +563,20 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
                 tc_fence_after();
 #pragma unroll
                 for (int ch = 0; ch < TC_BN / 32; ++ch) {
+                    // bias and output weight of the chunk's 32 columns: 16 independent 16-byte shared-memory loads into
+                    // registers BEFORE the accumulator load.  (Fetched column by column inside the loop they cost one
+                    // exposed load latency per column: the timeline showed 3.3 us per tile in the epilogue against
+                    // 1.3 us of MMA -- the epilogue, not the tensor pipe, set the pace of the kernel.)
+                    float bb[32], ww[32];
+                    if (last_chunk) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 t = reinterpret_cast<const float4*>(s_b1)[ch * 8 + i];
+                            const float4 u = reinterpret_cast<const float4*>(s_w2)[ch * 8 + i];
+                            bb[4 * i] = t.x; bb[4 * i + 1] = t.y; bb[4 * i + 2] = t.z; bb[4 * i + 3] = t.w;
+                            ww[4 * i] = u.x; ww[4 * i + 1] = u.y; ww[4 * i + 2] = u.z; ww[4 * i + 3] = u.w;
+                        }
+                    }
                     uint32_t v[32];
                     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
                     tmem_ld_32x32(lane_base + (uint32_t)(acc * TC_BN + ch * 32), v);
@@ -571,27 +591,15 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
                         continue;
                     }
 #pragma unroll
-                    for (int c = 0; c < 32; c += 4) {
-                        const int col = nh * TC_BN + ch * 32 + c;
-                        const float p0 = __uint_as_float(v[c]) + __ldg(&b1[col]);
-                        const float p1 = __uint_as_float(v[c + 1]) + __ldg(&b1[col + 1]);
-                        const float p2 = __uint_as_float(v[c + 2]) + __ldg(&b1[col + 2]);
-                        const float p3 = __uint_as_float(v[c + 3]) + __ldg(&b1[col + 3]);
-                        zs0 = fmaf(fmaxf(p0, 0.f), __ldg(&w2[col]), zs0);
-                        zs1 = fmaf(fmaxf(p1, 0.f), __ldg(&w2[col + 1]), zs1);
-                        zs2 = fmaf(fmaxf(p2, 0.f), __ldg(&w2[col + 2]), zs2);
-                        zs3 = fmaf(fmaxf(p3, 0.f), __ldg(&w2[col + 3]), zs3);
+                    for (int c = 0; c < 32; ++c) {
+                        const float pre = __uint_as_float(v[c]) + bb[c];
+                        const float r = fmaxf(pre, 0.f) * ww[c];
+                        if ((c & 3) == 0) zs0 += r; else if ((c & 3) == 1) zs1 += r; else if ((c & 3) == 2) zs2 += r; else zs3 += r;
                         if (maskT) {
                             // the ballot IS the transpose (bit r of column c's word = row r).  Rows behind n give junk
                             // bits: the backward multiplies them by dz = 0.
-                            const uint32_t w0 = __ballot_sync(GRAPES_FULL_MASK, p0 > 0.f);
-                            const uint32_t w1 = __ballot_sync(GRAPES_FULL_MASK, p1 > 0.f);
-                            const uint32_t w2b = __ballot_sync(GRAPES_FULL_MASK, p2 > 0.f);
-                            const uint32_t w3 = __ballot_sync(GRAPES_FULL_MASK, p3 > 0.f);
-                            if ((lane >> 2) == (c >> 2)) {
-                                const int sub = lane & 3;
-                                mbits[ch] = sub == 0 ? w0 : sub == 1 ? w1 : sub == 2 ? w2b : w3;
-                            }
+                            const uint32_t word = __ballot_sync(GRAPES_FULL_MASK, pre > 0.f);
+                            if (lane == c) mbits[ch] = word;
                         }
                     }
                 }
@@ -1231,7 +1239,7 @@ int grapes_sampler_l1_fwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo,
         const int nkb = (K + TC_BK - 1) / TC_BK, NH = D / TC_BN;
         const int m_tiles_cap = (cap_n + TC_BM - 1) / TC_BM;
         if ((rc = make_map(&ma, Y, cap_n, K, ldy)) != GRAPES_OK) return rc;
-        const int tail_b = 1024 /*align slack*/ + 1024 /*barriers + mask words*/;
+        const int tail_b = 1024 /*align slack*/ + 1536 /*barriers, bias + output weights of the half*/;
         // W half resident when it leaves room for >= 4 raw Y tiles; otherwise W streams through a 4-stage ring
         const int wres = (nkb * 2 * TC_TILE_BYTES + 4 * TC_TILE_BYTES + tail_b <= 227 * 1024 && ctx->sm_count >= NH) ? 1 : 0;
         const int bstages = 4;
