@@ -45,17 +45,21 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Waits with a suspend-time hint: a warp whose phase is not complete is SUSPENDED by the hardware (it resumes when the
+// phase completes, or after the hint at the latest) instead of re-issuing try_wait in a tight loop.  With a dozen waiting
+// warps per SM the tight loop starved the warps that had work: the timeline of k_l1_fwd_ts showed its epilogue warp at
+// one instruction per ~10 cycles (profiles/r02_topkernels.md).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra.uni WAIT_DONE;\n\t"
         "bra.uni WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t"
-        "}\n" ::"r"(addr), "r"(parity) : "memory");
+        "}\n" ::"r"(addr), "r"(parity), "r"(20000u) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile(
@@ -559,8 +563,10 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
             uint32_t mbits[4] = {0u, 0u, 0u, 0u};
             for (int kc = 0; kc < nkb; kc += TC_CHUNK_KB) {
                 const bool first_chunk = (kc == 0), last_chunk = (kc + TC_CHUNK_KB >= nkb);
+                if (warp == 2 && lane == 0 && tile_no == 2) stamp(80);           // tile 2: wait for the accumulator starts
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
+                if (warp == 2 && lane == 0 && tile_no == 2) stamp(81);           // accumulator complete
 #pragma unroll
                 for (int ch = 0; ch < TC_BN / 32; ++ch) {
                     // bias and output weight of the chunk's 32 columns: 16 independent 16-byte shared-memory loads into
@@ -580,6 +586,7 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
                     uint32_t v[32];
                     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
                     tmem_ld_32x32(lane_base + (uint32_t)(acc * TC_BN + ch * 32), v);
+                    if (warp == 2 && lane == 0 && tile_no == 2) stamp(82 + 2 * ch);  // chunk loaded from TMEM
                     if (!first_chunk) {                                   // fp32 master += chunk (round to nearest)
                         uint32_t m[32];
                         tmem_ld_32x32(lane_base + (uint32_t)(2 * TC_BN + ch * 32), m);
@@ -602,6 +609,7 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
                             if (lane == c) mbits[ch] = word;
                         }
                     }
+                    if (warp == 2 && lane == 0 && tile_no == 2) stamp(83 + 2 * ch);  // chunk's math done
                 }
                 tc_fence_before();
                 __syncwarp();

@@ -21,8 +21,11 @@ def main():
     mask = torch.zeros(((n + 127) // 128 * 4, D), dtype=torch.int32, device=dev)
     cnt = torch.tensor([n], dtype=torch.int32, device=dev)
     L.cdll.grapes_tc_debug(16)
+    use_mask = "--no-mask" not in sys.argv
     def run():
-        L.grapes_sampler_l1_fwd_tc(ctx, ptr(Y), None, ldy, ptr(cnt), n, K, ptr(Wh), ptr(Wl), 104, D, ptr(b1), ptr(w2), ptr(zpart), ptr(mask), st)
+        L.grapes_sampler_l1_fwd_tc(ctx, ptr(Y), None, ldy, ptr(cnt), n, K, ptr(Wh), ptr(Wl), 104, D, ptr(b1), ptr(w2), ptr(zpart),
+                                   ptr(mask) if use_mask else None, st)
+    print("relu mask output:", use_mask)
     for _ in range(3): run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -42,6 +45,8 @@ def main():
     print("MMA issuer: start 0, W resident", rel(v[1]), "tiles committed", [rel(x) for x in v[2:12] if x])
     print("epilogue warp 2: tiles drained", [rel(x) for x in v[32:42] if x])
     print("converter warp 6: k-blocks stored", [rel(x) for x in v[64:80] if x])
+    print("epilogue warp 2, tile 2: wait starts", rel(v[80]), "accumulator complete", rel(v[81]),
+          "per chunk (loaded, math done):", [(rel(v[82 + 2 * c]), rel(v[83 + 2 * c])) for c in range(4)])
     L.cdll.grapes_tc_debug(0)
 
 if __name__ == "__main__":
