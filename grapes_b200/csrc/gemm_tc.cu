@@ -45,21 +45,19 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Waits with a suspend-time hint: a warp whose phase is not complete is SUSPENDED by the hardware (it resumes when the
-// phase completes, or after the hint at the latest) instead of re-issuing try_wait in a tight loop.  With a dozen waiting
-// warps per SM the tight loop starved the warps that had work: the timeline of k_l1_fwd_ts showed its epilogue warp at
-// one instruction per ~10 cycles (profiles/r02_topkernels.md).
+// (try_wait with a 20 us suspend-time hint measured SLOWER: the wake-up of a suspended warp costs more than the issue
+// slots its spinning takes; k_l1_fwd_ts 31 -> 37 us per launch.)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
         "@p bra.uni WAIT_DONE;\n\t"
         "bra.uni WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t"
-        "}\n" ::"r"(addr), "r"(parity), "r"(20000u) : "memory");
+        "}\n" ::"r"(addr), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile(
@@ -113,6 +111,19 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
         : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+
+__device__ __forceinline__ void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float tf32_rna_f(float x) { return grapes_tf32_rna(x); }
 
@@ -407,6 +418,18 @@ __device__ __forceinline__ void tmem_st_32x32_x16(uint32_t taddr, const uint32_t
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// 32 x 32 bit transpose across a warp: in, lane r holds bit c = M[r][c]; out, lane c holds bit r = M[r][c]
+__device__ __forceinline__ uint32_t warp_bit_transpose(uint32_t x, int lane) {
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+        const uint32_t m = (j == 16) ? 0x0000ffffu : (j == 8) ? 0x00ff00ffu : (j == 4) ? 0x0f0f0f0fu : (j == 2) ? 0x33333333u : 0x55555555u;
+        const uint32_t y = __shfl_xor_sync(GRAPES_FULL_MASK, x, j);
+        x = (lane & j) ? ((x & ~m) | ((y >> j) & m)) : ((x & m) | ((y << j) & ~m));
+    }
+    return x;
+}
+
+template <bool LONGK>
 __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
     const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB_hi,
     const __grid_constant__ CUtensorMap tmB_lo, const int* __restrict__ n_dev, int cap_n, int K, int D, int wres,
@@ -552,10 +575,16 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
             }
         }
     } else if (warp < 6) {
-        // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4 =====
+        // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4.  What the timeline of the first forms showed: the
+        // epilogue, not the tensor pipe, set the pace (3 us per tile against 1.3 us of MMA).  Its costs, in order: the
+        // ballot / compare / select chain of the relu mask through ONE predicate and ONE register (32 dependent steps per
+        // chunk) -> the row's mask word is built locally and the 32 x 32 bits are transposed across the warp with five
+        // shuffles; bias / weight loads exposed per column -> float4 loads from shared memory; one accumulator chunk
+        // loaded from TMEM at a time -> two in flight =====
         const int q = warp & 3;
         int acc = 0; uint32_t acc_phase = 0;
         int tile_no = 0;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         for (int t = t_first; t < m_tiles; t += t_step) {
             const int mt = t;
             const int row = mt * TC_BM + q * 32 + lane;
@@ -563,53 +592,52 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
             uint32_t mbits[4] = {0u, 0u, 0u, 0u};
             for (int kc = 0; kc < nkb; kc += TC_CHUNK_KB) {
                 const bool first_chunk = (kc == 0), last_chunk = (kc + TC_CHUNK_KB >= nkb);
-                if (warp == 2 && lane == 0 && tile_no == 2) stamp(80);           // tile 2: wait for the accumulator starts
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
-                if (warp == 2 && lane == 0 && tile_no == 2) stamp(81);           // accumulator complete
 #pragma unroll
-                for (int ch = 0; ch < TC_BN / 32; ++ch) {
-                    // bias and output weight of the chunk's 32 columns: 16 independent 16-byte shared-memory loads into
-                    // registers BEFORE the accumulator load.  (Fetched column by column inside the loop they cost one
-                    // exposed load latency per column: the timeline showed 3.3 us per tile in the epilogue against
-                    // 1.3 us of MMA -- the epilogue, not the tensor pipe, set the pace of the kernel.)
-                    float bb[32], ww[32];
-                    if (last_chunk) {
+                for (int cp = 0; cp < 2; ++cp) {                          // two 32-column chunks per round
+                    uint32_t v[2][32];
+                    tmem_ld_32x32_nowait(lane_base + (uint32_t)(acc * TC_BN + cp * 64), v[0]);
+                    tmem_ld_32x32_nowait(lane_base + (uint32_t)(acc * TC_BN + cp * 64 + 32), v[1]);
+                    tmem_wait_ld();
+                    if (LONGK) {
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const int ch = cp * 2 + hh;
+                            if (!first_chunk) {                           // fp32 master += chunk (round to nearest)
+                                uint32_t m[32];
+                                tmem_ld_32x32(lane_base + (uint32_t)(2 * TC_BN + ch * 32), m);
+#pragma unroll
+                                for (int c = 0; c < 32; ++c)
+                                    v[hh][c] = __float_as_uint(__uint_as_float(v[hh][c]) + __uint_as_float(m[c]));
+                            }
+                            if (!last_chunk) tmem_st_32x32(lane_base + (uint32_t)(2 * TC_BN + ch * 32), v[hh]);
+                        }
+                        if (!last_chunk) continue;
+                    }
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int ch = cp * 2 + hh;
+                        uint32_t rowbits = 0u;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const float4 t = reinterpret_cast<const float4*>(s_b1)[ch * 8 + i];
-                            const float4 u = reinterpret_cast<const float4*>(s_w2)[ch * 8 + i];
-                            bb[4 * i] = t.x; bb[4 * i + 1] = t.y; bb[4 * i + 2] = t.z; bb[4 * i + 3] = t.w;
-                            ww[4 * i] = u.x; ww[4 * i + 1] = u.y; ww[4 * i + 2] = u.z; ww[4 * i + 3] = u.w;
+                            const float4 bb = reinterpret_cast<const float4*>(s_b1)[ch * 8 + i];
+                            const float4 ww = reinterpret_cast<const float4*>(s_w2)[ch * 8 + i];
+                            const float p0 = __uint_as_float(v[hh][4 * i]) + bb.x;
+                            const float p1 = __uint_as_float(v[hh][4 * i + 1]) + bb.y;
+                            const float p2 = __uint_as_float(v[hh][4 * i + 2]) + bb.z;
+                            const float p3 = __uint_as_float(v[hh][4 * i + 3]) + bb.w;
+                            zs0 = fmaf(fmaxf(p0, 0.f), ww.x, zs0);
+                            zs1 = fmaf(fmaxf(p1, 0.f), ww.y, zs1);
+                            zs2 = fmaf(fmaxf(p2, 0.f), ww.z, zs2);
+                            zs3 = fmaf(fmaxf(p3, 0.f), ww.w, zs3);
+                            rowbits |= (p0 > 0.f ? 1u : 0u) << (4 * i) | (p1 > 0.f ? 1u : 0u) << (4 * i + 1) |
+                                       (p2 > 0.f ? 1u : 0u) << (4 * i + 2) | (p3 > 0.f ? 1u : 0u) << (4 * i + 3);
                         }
+                        // lane r holds its row's 32 relu bits; the backward wants, per column, the word over the 32 rows.
+                        // Rows behind n give junk bits: the backward multiplies them by dz = 0.
+                        if (maskT) mbits[ch] = warp_bit_transpose(rowbits, lane);
                     }
-                    uint32_t v[32];
-                    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-                    tmem_ld_32x32(lane_base + (uint32_t)(acc * TC_BN + ch * 32), v);
-                    if (warp == 2 && lane == 0 && tile_no == 2) stamp(82 + 2 * ch);  // chunk loaded from TMEM
-                    if (!first_chunk) {                                   // fp32 master += chunk (round to nearest)
-                        uint32_t m[32];
-                        tmem_ld_32x32(lane_base + (uint32_t)(2 * TC_BN + ch * 32), m);
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(m[c]));
-                    }
-                    if (!last_chunk) {
-                        tmem_st_32x32(lane_base + (uint32_t)(2 * TC_BN + ch * 32), v);
-                        continue;
-                    }
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const float pre = __uint_as_float(v[c]) + bb[c];
-                        const float r = fmaxf(pre, 0.f) * ww[c];
-                        if ((c & 3) == 0) zs0 += r; else if ((c & 3) == 1) zs1 += r; else if ((c & 3) == 2) zs2 += r; else zs3 += r;
-                        if (maskT) {
-                            // the ballot IS the transpose (bit r of column c's word = row r).  Rows behind n give junk
-                            // bits: the backward multiplies them by dz = 0.
-                            const uint32_t word = __ballot_sync(GRAPES_FULL_MASK, pre > 0.f);
-                            if (lane == c) mbits[ch] = word;
-                        }
-                    }
-                    if (warp == 2 && lane == 0 && tile_no == 2) stamp(83 + 2 * ch);  // chunk's math done
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -1261,12 +1289,17 @@ int grapes_sampler_l1_fwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo,
         static int attr_ts[64] = {0};
         int& have = attr_ts[ctx->device & 63];
         if (smem_bytes > have) {
-            GRAPES_CUDA_OK(cudaFuncSetAttribute(k_l1_fwd_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+            GRAPES_CUDA_OK(cudaFuncSetAttribute(k_l1_fwd_ts<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+            GRAPES_CUDA_OK(cudaFuncSetAttribute(k_l1_fwd_ts<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
             have = smem_bytes;
         }
-        pdl((k_l1_fwd_ts), per_half * NH, TCS_THREADS, smem_bytes, (cudaStream_t)stream)(ma, mb_hi, mb_lo, n_dev, cap_n, K, D, wres,
-                                                                                        bstages, ystages, b1, w2, zpart, maskT,
-                                                                                        (g_tc_debug & 16) ? reinterpret_cast<unsigned long long*>(ctx->partials) : nullptr);
+        unsigned long long* dbg = (g_tc_debug & 16) ? reinterpret_cast<unsigned long long*>(ctx->partials) : nullptr;
+        if (nkb > TC_CHUNK_KB)
+            pdl((k_l1_fwd_ts<true>), per_half * NH, TCS_THREADS, smem_bytes, (cudaStream_t)stream)(
+                ma, mb_hi, mb_lo, n_dev, cap_n, K, D, wres, bstages, ystages, b1, w2, zpart, maskT, dbg);
+        else
+            pdl((k_l1_fwd_ts<false>), per_half * NH, TCS_THREADS, smem_bytes, (cudaStream_t)stream)(
+                ma, mb_hi, mb_lo, n_dev, cap_n, K, D, wres, bstages, ystages, b1, w2, zpart, maskT, dbg);
         grapes_count_launches(1);
         GRAPES_LAUNCH_OK();
         return GRAPES_OK;

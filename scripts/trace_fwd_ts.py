@@ -45,8 +45,6 @@ def main():
     print("MMA issuer: start 0, W resident", rel(v[1]), "tiles committed", [rel(x) for x in v[2:12] if x])
     print("epilogue warp 2: tiles drained", [rel(x) for x in v[32:42] if x])
     print("converter warp 6: k-blocks stored", [rel(x) for x in v[64:80] if x])
-    print("epilogue warp 2, tile 2: wait starts", rel(v[80]), "accumulator complete", rel(v[81]),
-          "per chunk (loaded, math done):", [(rel(v[82 + 2 * c]), rel(v[83 + 2 * c])) for c in range(4)])
     L.cdll.grapes_tc_debug(0)
 
 if __name__ == "__main__":
