@@ -958,12 +958,13 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) k_l1_bwd_tc(
 // Partials: part[chunk][cta / NH][D][N] -- the layout k_l1_bwd_finalize already reads.
 // TMEM columns: [0,128) hi accumulator, [128,256) lo accumulator, [256,512) A ring: 4 slots of (hi 32 | lo 32).
 // ------------------------------------------------------------------------------------------------
-#define TCBS_THREADS 320
+#define TCBS_THREADS 448            // TMA, MMA, 4 mask-expander (+ epilogue) warps, 8 converter warps (two groups)
 #define TCBS_STAGES 4
+#define TCBS_FLUSH 48               // groups (x 4 MMAs per accumulator) between two flushes of the accumulators
 __global__ void __launch_bounds__(TCBS_THREADS, 1) k_l1_bwd_ts(
     const __grid_constant__ CUtensorMap tmY, int ncols, const int* __restrict__ n_dev, int cap_n, int NH,
     const uint32_t* __restrict__ maskT, int D, const float* __restrict__ dz, float* __restrict__ part,
-    long long chunk_stride, int ystages) {
+    long long chunk_stride, int ystages, int nflush, unsigned long long* dbg) {
     pdl_begin();
     const int col0 = (int)blockIdx.y * 128;
     const int N = min(4, (ncols - col0 + 31) / 32) * 32;            // S columns of this chunk (a multiple of 32)
@@ -974,23 +975,27 @@ __global__ void __launch_bounds__(TCBS_THREADS, 1) k_l1_bwd_ts(
     uint64_t* bars = (uint64_t*)(y_ring + (size_t)ystages * 4 * TCB_B_TILE);
     uint64_t* full_bar = bars;                       // [4] 4 mask-expander + 4 converter warps -> MMA
     uint64_t* empty_bar = bars + 4;                  // [4] MMA -> producers
-    uint64_t* done_bar = bars + 8;                   // all MMAs retired -> epilogue
+    uint64_t* done_bar = bars + 8;                   // MMAs of a flush interval retired -> epilogue
     uint32_t* tmem_slot = (uint32_t*)(bars + 9);
     uint64_t* yfull_bar = bars + 10;                 // [8] TMA -> converters
     uint64_t* yempty_bar = bars + 18;                // [8] converters -> TMA
+    uint64_t* drained_bar = bars + 26;               // epilogue -> MMA: accumulators may be overwritten
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = min(*n_dev, cap_n);
     const int groups = (n + TCB_ROWS - 1) / TCB_ROWS;
     const int h = (int)blockIdx.x % NH;              // hidden half of this CTA
-    const int g_first = (int)blockIdx.x / NH, g_step = (int)gridDim.x / NH;
-    const bool have_work = g_first < groups;
+    const int pp = (int)blockIdx.x / NH, per_half = (int)gridDim.x / NH;
+    const int g_first = pp, g_step = per_half;
+    const int my_groups = (groups > g_first) ? (groups - 1 - g_first) / g_step + 1 : 0;
+    const int my_flushes = (my_groups + TCBS_FLUSH - 1) / TCBS_FLUSH;     // <= nflush (sized for cap_n on the host)
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmY);
         for (int s = 0; s < TCBS_STAGES; ++s) { mbar_init(&full_bar[s], 8); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 8; ++s) { mbar_init(&yfull_bar[s], 1); mbar_init(&yempty_bar[s], 4); }
         mbar_init(done_bar, 1);
+        mbar_init(drained_bar, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -998,6 +1003,13 @@ __global__ void __launch_bounds__(TCBS_THREADS, 1) k_l1_bwd_ts(
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    auto stamp = [&](int slot) {
+        if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && slot < 96) {
+            unsigned long long tt;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
+            dbg[slot] = tt;
+        }
+    };
 
     const int NBk = N / 32;                                           // 32-column blocks of this chunk
     if (warp == 0) {
@@ -1016,8 +1028,16 @@ __global__ void __launch_bounds__(TCBS_THREADS, 1) k_l1_bwd_ts(
         if (elect_one()) {
             const uint32_t idesc = make_idesc_tf32(128, 128);
             int stage = 0; uint32_t phase = 0;
-            bool first = true;
-            for (int g = g_first; g < groups; g += g_step) {
+            stamp(0);
+            for (int it = 0; it < my_groups; ++it) {
+                const int in_flush = it % TCBS_FLUSH;
+                if (in_flush == 0 && it > 0) {
+                    // the tensor core adds into its fp32 accumulator with truncation: chains are kept short.  The epilogue
+                    // stores the interval's sums to their own partial slab; the finalize adds the slabs (round to nearest)
+                    umma_commit(done_bar);
+                    mbar_wait(drained_bar, (uint32_t)((it / TCBS_FLUSH - 1) & 1));
+                    tc_fence_after();
+                }
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 const uint64_t bd = make_kmajor_sw128_desc(smem_u32(smem + stage * TCB_A_TILE));
@@ -1025,28 +1045,30 @@ __global__ void __launch_bounds__(TCBS_THREADS, 1) k_l1_bwd_ts(
 #pragma unroll
                 for (int ks = 0; ks < TCB_ROWS / 8; ++ks) {
                     const uint64_t adv = (uint64_t)((ks * 32) >> 4);          // 8 r = 32 bytes along the swizzle row
-                    const uint32_t acc = (first && ks == 0) ? 0u : 1u;
+                    const uint32_t acc = (in_flush == 0 && ks == 0) ? 0u : 1u;
                     umma_tf32_ts(tmem_base, a_hi + (uint32_t)(ks * 8), bd + adv, idesc, acc);
                     umma_tf32_ts(tmem_base + 128u, a_hi + 32u + (uint32_t)(ks * 8), bd + adv, idesc, acc);
                 }
-                first = false;
                 umma_commit(&empty_bar[stage]);
                 if (++stage == TCBS_STAGES) { stage = 0; phase ^= 1; }
+                if (it < 30) stamp(2 + it);
             }
-            umma_commit(done_bar);
+            if (my_groups > 0) umma_commit(done_bar);
         }
     } else if (warp >= 6) {
-        // ===== converters (warps 6..9): B''^T = (dz * Y)^T split into (hi, lo), shared memory -> registers -> TMEM =====
+        // ===== converters (warps 6..13): B''^T = (dz * Y)^T split into (hi, lo), shared memory -> registers -> TMEM.
+        // Two groups of four warps (one per TMEM lane quarter) take the row groups alternately: one iteration is a chain
+        // of latencies (barrier, shared-memory loads, tcgen05.st + wait, fence, arrive) longer than the group's MMAs =====
         const int q = warp & 3;                                       // TMEM lane quarter of this warp == 32-column block
+        const int grp = (warp - 6) >> 2;
         const bool blk_valid = q < NBk;                               // blocks behind the chunk's columns hold nothing: zeros
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + 256u;
-        int stage = 0; uint32_t phase = 0;
-        int ys = 0; uint32_t yphase = 0;
-        float dz_nx = 0.f;                                            // dz of the NEXT group's rows: loaded one group ahead
-        if (have_work) { const int r = g_first * TCB_ROWS + lane; dz_nx = (r < n) ? __ldg(&dz[r]) : 0.f; }
-        for (int g = g_first; g < groups; g += g_step) {
-            const float dzr = dz_nx;
-            if (g + g_step < groups) { const int r = (g + g_step) * TCB_ROWS + lane; dz_nx = (r < n) ? __ldg(&dz[r]) : 0.f; }
+        for (int it = grp; it < my_groups; it += 2) {
+            const int g = g_first + it * g_step;
+            const int r0 = g * TCB_ROWS;
+            const float dzr = (r0 + lane < n) ? __ldg(&dz[r0 + lane]) : 0.f;    // (issued before the wait: latency hidden)
+            const int ys = it % ystages, stage = it % TCBS_STAGES;
+            const uint32_t yphase = (uint32_t)((it / ystages) & 1), phase = (uint32_t)((it / TCBS_STAGES) & 1);
             mbar_wait(&yfull_bar[ys], yphase);
             const float* tile = reinterpret_cast<const float*>(y_ring + (size_t)ys * 4 * TCB_B_TILE + q * TCB_B_TILE) + lane;
             uint32_t hi[32], lo[32];
@@ -1057,11 +1079,10 @@ __global__ void __launch_bounds__(TCBS_THREADS, 1) k_l1_bwd_ts(
                 const float v = y * __shfl_sync(GRAPES_FULL_MASK, dzr, i);
                 const float hh = tf32_rna(v);
                 hi[i] = __float_as_uint(hh);
-                lo[i] = __float_as_uint(tf32_rna(v - hh));
+                lo[i] = __float_as_uint(v - hh);                       // exact; the tensor core drops its 13 low bits
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&yempty_bar[ys]);              // tile consumed: the TMA may refill the slot
-            if (++ys == ystages) { ys = 0; yphase ^= 1; }
             mbar_wait(&empty_bar[stage], phase ^ 1);
             tc_fence_after();
             tmem_st_32x32(lane_addr + (uint32_t)(stage * 64), hi);
@@ -1069,50 +1090,63 @@ __global__ void __launch_bounds__(TCBS_THREADS, 1) k_l1_bwd_ts(
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_bar[stage]);
-            if (++stage == TCBS_STAGES) { stage = 0; phase ^= 1; }
+            if (warp == 6 && lane == 0 && (it >> 1) < 16) stamp(64 + (it >> 1));
         }
     } else if (warp >= 2) {
-        // ===== mask expanders (warps 2..5), then epilogue =====
+        // ===== mask expanders (warps 2..5), and the epilogue of every flush interval =====
         const int e = (warp - 2) * 32 + lane;            // hidden unit inside the half: row of the B operand tile
+        const int q = warp & 3;
+        const int kk = q * 32 + lane;                    // epilogue: TMEM lane = column k of Y
         int stage = 0; uint32_t phase = 0;
-        uint32_t word_nx = have_work ? maskT[(size_t)g_first * D + h * 128 + e] : 0u;
-        for (int g = g_first; g < groups; g += g_step) {
+        uint32_t word_nx = (my_groups > 0) ? maskT[(size_t)g_first * D + h * 128 + e] : 0u;
+        for (int it = 0; it <= my_groups; ++it) {
+            if ((it % TCBS_FLUSH == 0 && it > 0) || (it == my_groups && my_groups > 0)) {
+                // epilogue of the interval that just ended: TMEM lane = column k of Y, TMEM column = hidden unit; stored
+                // transposed -> part[flush][pp][h*128 + d][k]
+                const int fl = (it - 1) / TCBS_FLUSH;
+                float* dst = part + (((size_t)fl * per_half + pp) * D + (size_t)h * 128) * N;
+                mbar_wait(done_bar, (uint32_t)(fl & 1));
+                tc_fence_after();
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t v[32], v2[32];
+                    tmem_ld_32x32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+                    tmem_ld_32x32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(128 + ch * 32), v2);
+                    tmem_wait_ld();
+                    if (kk < N) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c)
+                            dst[(size_t)(ch * 32 + c) * N + kk] = __uint_as_float(v[c]) + __uint_as_float(v2[c]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(drained_bar);
+                if (warp == 2 && lane == 0) stamp(40 + fl);
+            }
+            if (it == my_groups) break;
+            const int g = g_first + it * g_step;
             const uint32_t word = word_nx;
-            if (g + g_step < groups) word_nx = maskT[(size_t)(g + g_step) * D + h * 128 + e];
+            if (it + 1 < my_groups) word_nx = maskT[(size_t)(g + g_step) * D + h * 128 + e];
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* st = smem + stage * TCB_A_TILE;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const int off = e * 128 + ((c ^ (e & 7)) << 4);          // SWIZZLE_128B: 16-byte chunk index ^ (row % 8)
                 const uint32_t w = word >> (c * 4);
-                float4 a;
-                a.x = (w & 1u) ? 1.f : 0.f; a.y = (w & 2u) ? 1.f : 0.f; a.z = (w & 4u) ? 1.f : 0.f; a.w = (w & 8u) ? 1.f : 0.f;
-                *reinterpret_cast<float4*>(st + off) = a;
+                float4 a4;
+                a4.x = (w & 1u) ? 1.f : 0.f; a4.y = (w & 2u) ? 1.f : 0.f; a4.z = (w & 4u) ? 1.f : 0.f; a4.w = (w & 8u) ? 1.f : 0.f;
+                *reinterpret_cast<float4*>(st + off) = a4;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_bar[stage]);
             if (++stage == TCBS_STAGES) { stage = 0; phase ^= 1; }
         }
-        // epilogue: TMEM lane = column k of Y, TMEM column = hidden unit; stored transposed -> part[cta/NH][h*128 + d][k]
-        const int q = warp & 3;
-        const int kk = q * 32 + lane;
-        float* dst = part + ((size_t)((int)blockIdx.x / NH) * D + (size_t)h * 128) * N;
-        if (have_work) {
-            mbar_wait(done_bar, 0);
-            tc_fence_after();
-            for (int ch = 0; ch < 4; ++ch) {
-                uint32_t v[32], v2[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(128 + ch * 32), v2);
-                if (kk < N) {
-#pragma unroll
-                    for (int c = 0; c < 32; ++c)
-                        dst[(size_t)(ch * 32 + c) * N + kk] = __uint_as_float(v[c]) + __uint_as_float(v2[c]);
-                }
-            }
-        } else if (kk < N) {
-            for (int d = 0; d < 128; ++d) dst[(size_t)d * N + kk] = 0.f;
+        // flush slabs this CTA did not reach (fewer rows than the capacity the host sized for): zeros
+        for (int fl = my_flushes; fl < nflush; ++fl) {
+            float* dst = part + (((size_t)fl * per_half + pp) * D + (size_t)h * 128) * N;
+            if (kk < N)
+                for (int d = 0; d < 128; ++d) dst[(size_t)d * N + kk] = 0.f;
         }
     }
     tc_fence_before();
@@ -1241,6 +1275,7 @@ int grapes_tc_debug(int flags) { g_tc_debug = flags; return 0; }
 // debugging aid (scripts/trace_fwd_ts.py): device address of the ctx's split-K partial buffer, where grapes_tc_debug bit 4
 // parks the phase stamps of k_l1_fwd_ts
 int64_t grapes_debug_partials(grapes_ctx* ctx) { return ctx ? (int64_t)(uintptr_t)ctx->partials : 0; }
+int64_t grapes_debug_partials_bytes(grapes_ctx* ctx) { return ctx ? (int64_t)ctx->partials_bytes : 0; }
 
 int grapes_split_tf32(grapes_ctx* ctx, const float* src, int ld_src, int R, int K, float* hi, float* lo, int ld_dst,
                       void* stream) {
@@ -1375,14 +1410,19 @@ int grapes_sampler_l1_bwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo,
         const int max_groups = (cap_n + TCB_ROWS - 1) / TCB_ROWS;
         int per_half = grapes_max_i(1, ctx->sm_count / nchunks / NH);  // CTAs per chunk and half
         if (per_half > max_groups) per_half = max_groups;
-        while (per_half > 1 && (size_t)nchunks * per_half * D * 128 * sizeof(float) > ctx->partials_bytes) --per_half;
-        GRAPES_REQUIRE((size_t)nchunks * per_half * D * 128 * sizeof(float) <= ctx->partials_bytes, "split partial buffer too small");
-        const long long chunk_stride = (long long)per_half * D * 128;
+        // accumulator chains are cut every TCBS_FLUSH groups: one partial slab per CTA and flush interval
+        int nflush = grapes_div_up(grapes_div_up(max_groups, per_half), TCBS_FLUSH);
+        GRAPES_REQUIRE((size_t)nchunks * nflush * per_half * D * 128 * sizeof(float) <= ctx->partials_bytes,
+                       "split partial buffer too small");
+        const long long chunk_stride = (long long)nflush * per_half * D * 128;
+        // (debug stamps: the last KB of the partial buffer, behind every slab)
+        unsigned long long* dbg = (g_tc_debug & 16) ? reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(ctx->partials) + ctx->partials_bytes - 1024) : nullptr;
+        GRAPES_REQUIRE(!dbg || (size_t)nchunks * nflush * per_half * D * 128 * sizeof(float) + 1024 <= ctx->partials_bytes, "no room for the debug stamps");
         pdl((k_l1_bwd_ts), dim3(per_half * NH, nchunks), TCBS_THREADS, smem_ts, s)(my, ncols, n_dev, cap_n, NH, maskT, D, dz,
-                                                                                  ctx->partials, chunk_stride, ystages);
+                                                                                  ctx->partials, chunk_stride, ystages, nflush, dbg);
         grapes_count_launches(1);
-        pdl((k_l1_bwd_finalize), D, FIN_THREADS, 0, s)(ctx->partials, per_half, D, ncols, nchunks, chunk_stride, K, W1, ldw, b1, w2,
-                                                    ones_col, scale, gW1, gb1, gw2);
+        pdl((k_l1_bwd_finalize), D, FIN_THREADS, 0, s)(ctx->partials, per_half * nflush, D, ncols, nchunks, chunk_stride, K, W1, ldw,
+                                                    b1, w2, ones_col, scale, gW1, gb1, gw2);
         grapes_count_launches(1);
         GRAPES_LAUNCH_OK();
         return GRAPES_OK;

@@ -251,6 +251,7 @@ int grapes_tc_debug(int flags);
 /* debugging aid (scripts/trace_fwd_ts.py): device address of the ctx's split-K partial buffer, where grapes_tc_debug bit 4
  * makes k_l1_fwd_ts park the globaltimer stamps of CTA 0's MMA issuer / epilogue / converter warps                  */
 int64_t grapes_debug_partials(grapes_ctx* ctx);
+int64_t grapes_debug_partials_bytes(grapes_ctx* ctx);   /* k_l1_bwd_ts parks its stamps in the last KB */
 int grapes_sampler_l1_fwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo, int ldy, const int* n_dev, int cap_n,
                              int K, const float* W_hi, const float* W_lo, int ldw, int D, const float* b1,
                              const float* w2, float* zpart, uint32_t* maskT, void* stream);
