@@ -416,6 +416,17 @@ __device__ __forceinline__ void tmem_st_32x32_x16(uint32_t taddr, const uint32_t
            "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
         : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x32_nowait(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n"
+        :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+           "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+           "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+           "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // 32 x 32 bit transpose across a warp: in, lane r holds bit c = M[r][c]; out, lane c holds bit r = M[r][c]
@@ -693,8 +704,9 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
                 }
                 mbar_wait(&aempty_bar[slot], sphase ^ 1);             // the MMAs that read this slot have retired
                 tc_fence_after();
-                tmem_st_32x32(lane_addr + (uint32_t)(slot * 64), hi);
-                tmem_st_32x32(lane_addr + (uint32_t)(slot * 64 + 32), lo);
+                tmem_st_32x32_nowait(lane_addr + (uint32_t)(slot * 64), hi);      // both stores in flight, ONE wait
+                tmem_st_32x32_nowait(lane_addr + (uint32_t)(slot * 64 + 32), lo);
+                tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&conv_bar[slot]);
@@ -960,7 +972,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) k_l1_bwd_tc(
 // ------------------------------------------------------------------------------------------------
 #define TCBS_THREADS 448            // TMA, MMA, 4 mask-expander (+ epilogue) warps, 8 converter warps (two groups)
 #define TCBS_STAGES 4
-#define TCBS_FLUSH 48               // groups (x 4 MMAs per accumulator) between two flushes of the accumulators
+#define TCBS_FLUSH 96               // groups (x 4 MMAs per accumulator) between two flushes of the accumulators
 __global__ void __launch_bounds__(TCBS_THREADS, 1) k_l1_bwd_ts(
     const __grid_constant__ CUtensorMap tmY, int ncols, const int* __restrict__ n_dev, int cap_n, int NH,
     const uint32_t* __restrict__ maskT, int D, const float* __restrict__ dz, float* __restrict__ part,
@@ -1085,8 +1097,9 @@ __global__ void __launch_bounds__(TCBS_THREADS, 1) k_l1_bwd_ts(
             if (lane == 0) mbar_arrive(&yempty_bar[ys]);              // tile consumed: the TMA may refill the slot
             mbar_wait(&empty_bar[stage], phase ^ 1);
             tc_fence_after();
-            tmem_st_32x32(lane_addr + (uint32_t)(stage * 64), hi);
-            tmem_st_32x32(lane_addr + (uint32_t)(stage * 64 + 32), lo);
+            tmem_st_32x32_nowait(lane_addr + (uint32_t)(stage * 64), hi);      // both stores in flight, ONE wait
+            tmem_st_32x32_nowait(lane_addr + (uint32_t)(stage * 64 + 32), lo);
+            tmem_wait_st();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_bar[stage]);
