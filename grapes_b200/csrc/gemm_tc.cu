@@ -28,8 +28,8 @@
 
 static int g_tc_debug = 0;      // bit 0: backward operand debug fill; bit 1: force the streaming (non W-resident) forward;
                                 // bit 2: forward with BOTH operands in shared memory (k_l1_fwd_tc) instead of the default
-                                // A-operand-in-tensor-memory form (k_l1_fwd_ts); bit 3: backward with its scaled operand in
-                                // tensor memory (k_l1_bwd_ts)
+                                // A-operand-in-tensor-memory form (k_l1_fwd_ts); bit 3: backward with both operands in shared
+                                // memory (k_l1_bwd_tc) instead of the default k_l1_bwd_ts; bit 4: timeline stamps
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -1407,7 +1407,7 @@ int grapes_sampler_l1_bwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo,
     // column chunks of <= 128 columns of Y (accumulator: NH halves x (hi | lo) x 128 columns = all 512 TMEM columns): ONE
     // launch, blockIdx.y = chunk, the SMs divided among the chunks; then ONE finalize that walks the chunks in order
     const int nchunks = (ncols + 127) / 128;
-    if ((g_tc_debug & 8) && !Y_lo) {
+    if (!(g_tc_debug & 8) && !Y_lo) {
         // scaled-feature operand in tensor memory (k_l1_bwd_ts): every CTA owns one 128-unit half of the hidden layer
         const int ystages = 6;
         const int smem_ts = TCBS_STAGES * TCB_A_TILE + ystages * 4 * TCB_B_TILE + 1024 + 512;

@@ -246,7 +246,8 @@ int grapes_split_tf32(grapes_ctx* ctx, const float* src, int ld_src, int R, int 
                       void* stream);
 /* measurement knob of the tcgen05 kernels (bit 1: stream the weight tiles instead of keeping them resident; bit 2: the
  * forward with both operands in shared memory, k_l1_fwd_tc, instead of the default k_l1_fwd_ts whose A operand lives in
- * tensor memory; bit 3: the backward with its scaled-feature operand in tensor memory, k_l1_bwd_ts)                     */
+ * tensor memory; bit 3: the backward with both operands in shared memory, k_l1_bwd_tc, instead of the default k_l1_bwd_ts;
+ * bit 4: timeline stamps for scripts/trace_*_ts.py)                                                                    */
 int grapes_tc_debug(int flags);
 /* debugging aid (scripts/trace_fwd_ts.py): device address of the ctx's split-K partial buffer, where grapes_tc_debug bit 4
  * makes k_l1_fwd_ts park the globaltimer stamps of CTA 0's MMA issuer / epilogue / converter warps                  */

@@ -18,7 +18,7 @@ def main():
     cnt = torch.tensor([n], dtype=torch.int32, device=dev)
     gW, gb, gw = torch.zeros(D, K, device=dev), torch.zeros(D, device=dev), torch.zeros(D, device=dev)
     st = torch.cuda.current_stream().cuda_stream
-    for flags, tag in ((8 | 16, "k_l1_bwd_ts"), (0, "k_l1_bwd_tc")):
+    for flags, tag in ((16, "k_l1_bwd_ts"), (8, "k_l1_bwd_tc")):
         L.cdll.grapes_tc_debug(flags)
         def run():
             L.grapes_sampler_l1_bwd_tc(ctx, ptr(Y), None, ldy, ncols, ptr(cnt), n, K, 104, ptr(mask), ptr(W), K, D, ptr(b1), ptr(w2),

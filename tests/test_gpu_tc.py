@@ -200,7 +200,7 @@ def test_l1_bwd_ts_tensor_memory_operand(cuda_device, n, cap_n, K, D, extra):
                                ptr(w2d), ptr(zpart), ptr(maskT), st)
     outs = []
     try:
-        for flag in (8, 0):
+        for flag in (0, 8):                      # 0: k_l1_bwd_ts (default), 8: k_l1_bwd_tc
             L.cdll.grapes_tc_debug(flag)
             gW1, gb1, gw2 = torch.zeros(D, K, device=dev), torch.zeros(D, device=dev), torch.zeros(D, device=dev)
             L.grapes_sampler_l1_bwd_tc(ctx, ptr(Yd), None, ldy, ncols, ptr(cnt), cap_n, K, ones_col, ptr(maskT), ptr(W1d), K,
