@@ -521,15 +521,19 @@ def main():
 
         # ---- whole-graph SpMM (the metric's "SpMM HBM GB/s"): Y = A_hat X over every edge of the workload graph, the
         # aggregation of the full-batch evaluation forward (eval.py:47-56); one launch of the TMA-staged kernel ----
-        spmm = None
+        spmm, full_eval = None, None
         if world == 1 and not args.no_spmm and graph.nnz < (1 << 31) - 1:
-            from grapes_b200.gcn import GraphNorm
-            gn = GraphNorm(graph)
+            from grapes_b200.gcn import GCN, GraphNorm, full_graph_forward
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            gn = GraphNorm(graph)                    # one-off: gcn_norm structure of the whole graph (library kernels)
+            s1.record()
+            torch.cuda.synchronize()
+            build_ms = s0.elapsed_time(s1)
             ysp = gn.aggregate(x)
             torch.cuda.synchronize()
             ts = []
             for _ in range(5):
-                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s0.record()
                 ysp = gn.aggregate(x)
                 s1.record()
@@ -545,8 +549,46 @@ def main():
                     "peak_GBps": hbm_peak, "frac_algorithmic": alg_b / sp_ms / 1e6 / hbm_peak,
                     "frac_gathered": gat_b / sp_ms / 1e6 / hbm_peak,
                     "note": "uniform-random graph: every edge gathers a 4F-byte row from a table 8x larger than L2, so the "
-                            "traffic is the gathered bytes, not the algorithmic ones"}
-            del gn, ysp
+                            "traffic is the gathered bytes, not the algorithmic ones (dram__bytes of this launch: profiles/)"}
+            del ysp
+            # ---- full-graph evaluation forward gcn_c(x, edge_index) (eval.py:47-56) with the engine's current weights:
+            # SpMM at width F -> tcgen05 dense layer (+bias, relu) -> [N x 256] x [256 x C] -> SpMM at width C (+bias) ----
+            gcn_c = GCN(F, [eng.D, C]).to(dev)
+            gcn_c.load_state_dict(eng.state_dicts()["gcn_c"])
+            gcn_c.eval()
+            logits = full_graph_forward(gcn_c, x, gn)
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(3):
+                s0.record()
+                logits = full_graph_forward(gcn_c, x, gn)
+                s1.record()
+                torch.cuda.synchronize()
+                ts.append(s0.elapsed_time(s1))
+            ts.sort()
+            full_eval = {"ms": ts[1], "structure_build_ms": build_ms, "nodes": N, "nnz": nnz_g,
+                         "what": "gcn_c(x, edge_index) over the whole graph (eval.py:50), logits for every node; the structure "
+                                 "(in-neighbour CSR + deg^-1/2) is built once per graph by grapes_build_csr",
+                         "cpu_ms": None}
+            if not args.no_cpu_baseline and cfgname != "papers" and N * F <= 3e8:
+                import numpy as np
+                import scipy.sparse as sp
+                from oracle import reference_port as rp          # checker only: the reference's full-graph forward on the host
+                torch.set_num_threads(os.cpu_count() or 1)
+                ip, ix = indptr.cpu().numpy(), indices.cpu().numpy()
+                adj = sp.csr_matrix((np.ones(ix.shape[0], dtype=bool), ix, ip), shape=(N, N))
+                og = rp.OracleGCN(F, [eng.D, C])
+                og.load_state_dict({k: v.detach().cpu() for k, v in eng.state_dicts()["gcn_c"].items()})
+                xc = x.cpu()
+                with torch.no_grad():
+                    t0 = time.perf_counter()
+                    ref_logits = rp.full_graph_logits_cpu(og, xc, adj)
+                    full_eval["cpu_ms"] = 1e3 * (time.perf_counter() - t0)
+                full_eval["cpu_threads"] = torch.get_num_threads()
+                full_eval["cpu_what"] = "oracle.full_graph_logits_cpu: PyG order, sparse-CSR x dense per layer (incl. building A_hat)"
+                full_eval["max_rel_diff_vs_cpu_fp32"] = float((logits.cpu() - ref_logits).abs().max() / ref_logits.abs().max())
+                del ref_logits, xc, adj
+            del gn, logits
 
         cpu = None
         if world == 1 and not args.no_cpu_baseline and cfgname != "papers":      # the papers-shaped graph does not fit the host oracle
@@ -558,7 +600,7 @@ def main():
                 "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(cfgname, cfg, world),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": int(per_step),
-                "roofline": roof, "rooflines": rooflines, "spmm": spmm, "csr_build": csr_build, "cpu_baseline": cpu, "breakdown_ms_per_step": breakdown,
+                "roofline": roof, "rooflines": rooflines, "spmm": spmm, "full_graph_eval": full_eval, "csr_build": csr_build, "cpu_baseline": cpu, "breakdown_ms_per_step": breakdown,
                 "frontier": per_hop, "cuda_graph": use_graph, "cross_step_prefetch": prefetch,
                 "step_times": step_times, "prime_steps": PRIME,
                 "gradient_exchange": ("none" if world == 1 else "NONE (diagnostic run: independent replicas, not data parallel)" if args.exchange == "none" else

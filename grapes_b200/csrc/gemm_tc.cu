@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
     const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB_hi,
     const __grid_constant__ CUtensorMap tmB_lo, const int* __restrict__ n_dev, int cap_n, int K, int D, int wres,
     int bstages, int ystages, const float* __restrict__ b1, const float* __restrict__ w2, float* __restrict__ zpart,
-    uint32_t* __restrict__ maskT, unsigned long long* dbg) {
+    uint32_t* __restrict__ maskT, float* __restrict__ hout, int ldh, unsigned long long* dbg) {
     pdl_begin();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // SWIZZLE_128B tiles: 1024 B aligned
@@ -642,6 +642,11 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
                             zs1 = fmaf(fmaxf(p1, 0.f), ww.y, zs1);
                             zs2 = fmaf(fmaxf(p2, 0.f), ww.z, zs2);
                             zs3 = fmaf(fmaxf(p3, 0.f), ww.w, zs3);
+                            // dense-layer mode (grapes_gemm_bias_relu_tc): the hidden activations themselves, 16 bytes
+                            // of the thread's row at a time (a thread covers whole 128-byte lines of its row)
+                            if (hout && row < n)
+                                *reinterpret_cast<float4*>(hout + (size_t)row * ldh + nh * TC_BN + ch * 32 + 4 * i) =
+                                    make_float4(fmaxf(p0, 0.f), fmaxf(p1, 0.f), fmaxf(p2, 0.f), fmaxf(p3, 0.f));
                             rowbits |= (p0 > 0.f ? 1u : 0u) << (4 * i) | (p1 > 0.f ? 1u : 0u) << (4 * i + 1) |
                                        (p2 > 0.f ? 1u : 0u) << (4 * i + 2) | (p3 > 0.f ? 1u : 0u) << (4 * i + 3);
                         }
@@ -655,7 +660,7 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            if (row < n) {                                        // two partial rows per half: (chains 0, 1) and (chains 2, 3)
+            if (zpart && row < n) {                               // two partial rows per half: (chains 0, 1) and (chains 2, 3)
                 zpart[(size_t)(nh * 2) * cap_n + row] = zs0 + zs1;
                 zpart[(size_t)(nh * 2 + 1) * cap_n + row] = zs2 + zs3;
             }
@@ -1282,6 +1287,48 @@ static int make_map(CUtensorMap* m, const float* base, int rows, int cols, int l
     return GRAPES_OK;
 }
 
+// A operand in tensor memory (k_l1_fwd_ts): raw Y tiles by TMA, split on the way into TMEM, only W staged for the MMA.
+// hout != NULL: the hidden activations relu(Y W^T + b1) are written to hout[n x D] (pitch ldh); zpart / maskT optional.
+static int launch_fwd_ts(grapes_ctx* ctx, const float* Y, int ldy, const int* n_dev, int cap_n, int K, const float* W_hi,
+                         const float* W_lo, int ldw, int D, const float* b1, const float* w2, float* zpart, uint32_t* maskT,
+                         float* hout, int ldh, void* stream) {
+    CUtensorMap ma, mb_hi, mb_lo;
+    int rc;
+        if ((rc = make_map(&mb_hi, W_hi, D, K, ldw)) != GRAPES_OK) return rc;
+        if ((rc = make_map(&mb_lo, W_lo, D, K, ldw)) != GRAPES_OK) return rc;
+        const int nkb = (K + TC_BK - 1) / TC_BK, NH = D / TC_BN;
+        const int m_tiles_cap = (cap_n + TC_BM - 1) / TC_BM;
+        if ((rc = make_map(&ma, Y, cap_n, K, ldy)) != GRAPES_OK) return rc;
+        const int tail_b = 1024 /*align slack*/ + 1536 /*barriers, bias + output weights of the half*/;
+        // W half resident when it leaves room for >= 4 raw Y tiles; otherwise W streams through a 4-stage ring
+        const int wres = (nkb * 2 * TC_TILE_BYTES + 4 * TC_TILE_BYTES + tail_b <= 227 * 1024 && ctx->sm_count >= NH) ? 1 : 0;
+        const int bstages = 4;
+        const int nbt = wres ? nkb : bstages;
+        int ystages = (227 * 1024 - tail_b - nbt * 2 * TC_TILE_BYTES) / TC_TILE_BYTES;
+        if (ystages > 8) ystages = 8;
+        const int smem_bytes = nbt * 2 * TC_TILE_BYTES + ystages * TC_TILE_BYTES + tail_b;
+        int per_half = ctx->sm_count / NH;
+        if (per_half > m_tiles_cap) per_half = m_tiles_cap;
+        if (per_half < 1) per_half = 1;
+        static int attr_ts[64] = {0};
+        int& have = attr_ts[ctx->device & 63];
+        if (smem_bytes > have) {
+            GRAPES_CUDA_OK(cudaFuncSetAttribute(k_l1_fwd_ts<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+            GRAPES_CUDA_OK(cudaFuncSetAttribute(k_l1_fwd_ts<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+            have = smem_bytes;
+        }
+        unsigned long long* dbg = (g_tc_debug & 16) ? reinterpret_cast<unsigned long long*>(ctx->partials) : nullptr;
+        if (nkb > TC_CHUNK_KB)
+            pdl((k_l1_fwd_ts<true>), per_half * NH, TCS_THREADS, smem_bytes, (cudaStream_t)stream)(
+                ma, mb_hi, mb_lo, n_dev, cap_n, K, D, wres, bstages, ystages, b1, w2, zpart, maskT, hout, ldh, dbg);
+        else
+            pdl((k_l1_fwd_ts<false>), per_half * NH, TCS_THREADS, smem_bytes, (cudaStream_t)stream)(
+                ma, mb_hi, mb_lo, n_dev, cap_n, K, D, wres, bstages, ystages, b1, w2, zpart, maskT, hout, ldh, dbg);
+        grapes_count_launches(1);
+        GRAPES_LAUNCH_OK();
+        return GRAPES_OK;
+}
+
 extern "C" {
 
 int grapes_tc_debug(int flags) { g_tc_debug = flags; return 0; }
@@ -1316,42 +1363,8 @@ int grapes_sampler_l1_fwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo,
     const int presplit = Y_lo ? 1 : 0;
     CUtensorMap ma, ma_lo, mb_hi, mb_lo;
     int rc;
-    if (!presplit && !(g_tc_debug & 4)) {
-        // A operand in tensor memory (k_l1_fwd_ts): Y goes global -> registers -> TMEM, only W is staged in shared memory
-        if ((rc = make_map(&mb_hi, W_hi, D, K, ldw)) != GRAPES_OK) return rc;
-        if ((rc = make_map(&mb_lo, W_lo, D, K, ldw)) != GRAPES_OK) return rc;
-        const int nkb = (K + TC_BK - 1) / TC_BK, NH = D / TC_BN;
-        const int m_tiles_cap = (cap_n + TC_BM - 1) / TC_BM;
-        if ((rc = make_map(&ma, Y, cap_n, K, ldy)) != GRAPES_OK) return rc;
-        const int tail_b = 1024 /*align slack*/ + 1536 /*barriers, bias + output weights of the half*/;
-        // W half resident when it leaves room for >= 4 raw Y tiles; otherwise W streams through a 4-stage ring
-        const int wres = (nkb * 2 * TC_TILE_BYTES + 4 * TC_TILE_BYTES + tail_b <= 227 * 1024 && ctx->sm_count >= NH) ? 1 : 0;
-        const int bstages = 4;
-        const int nbt = wres ? nkb : bstages;
-        int ystages = (227 * 1024 - tail_b - nbt * 2 * TC_TILE_BYTES) / TC_TILE_BYTES;
-        if (ystages > 8) ystages = 8;
-        const int smem_bytes = nbt * 2 * TC_TILE_BYTES + ystages * TC_TILE_BYTES + tail_b;
-        int per_half = ctx->sm_count / NH;
-        if (per_half > m_tiles_cap) per_half = m_tiles_cap;
-        if (per_half < 1) per_half = 1;
-        static int attr_ts[64] = {0};
-        int& have = attr_ts[ctx->device & 63];
-        if (smem_bytes > have) {
-            GRAPES_CUDA_OK(cudaFuncSetAttribute(k_l1_fwd_ts<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-            GRAPES_CUDA_OK(cudaFuncSetAttribute(k_l1_fwd_ts<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-            have = smem_bytes;
-        }
-        unsigned long long* dbg = (g_tc_debug & 16) ? reinterpret_cast<unsigned long long*>(ctx->partials) : nullptr;
-        if (nkb > TC_CHUNK_KB)
-            pdl((k_l1_fwd_ts<true>), per_half * NH, TCS_THREADS, smem_bytes, (cudaStream_t)stream)(
-                ma, mb_hi, mb_lo, n_dev, cap_n, K, D, wres, bstages, ystages, b1, w2, zpart, maskT, dbg);
-        else
-            pdl((k_l1_fwd_ts<false>), per_half * NH, TCS_THREADS, smem_bytes, (cudaStream_t)stream)(
-                ma, mb_hi, mb_lo, n_dev, cap_n, K, D, wres, bstages, ystages, b1, w2, zpart, maskT, dbg);
-        grapes_count_launches(1);
-        GRAPES_LAUNCH_OK();
-        return GRAPES_OK;
-    }
+    if (!presplit && !(g_tc_debug & 4))
+        return launch_fwd_ts(ctx, Y, ldy, n_dev, cap_n, K, W_hi, W_lo, ldw, D, b1, w2, zpart, maskT, nullptr, 0, stream);
     if ((rc = make_map(&ma, Y, cap_n, K, ldy)) != GRAPES_OK) return rc;
     if ((rc = make_map(&ma_lo, presplit ? Y_lo : Y, cap_n, K, ldy)) != GRAPES_OK) return rc;
     if ((rc = make_map(&mb_hi, W_hi, D, K, ldw)) != GRAPES_OK) return rc;
@@ -1392,6 +1405,18 @@ int grapes_sampler_l1_fwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo,
     return GRAPES_OK;
 }
 
+
+// Dense GCNConv.lin layer with bias and relu on the tensor cores: H[n x D] = relu(Y[n x K] W^T + b) (3xTF32, fp32-accurate),
+// the hidden layer of the full-graph evaluation forward (eval.py:50: gcn_c(x, edge_index) over every node).  W_hi / W_lo from
+// grapes_split_tf32; Y 16-byte aligned with ldy % 4 == 0; H 16-byte aligned with ldh % 4 == 0.
+int grapes_gemm_bias_relu_tc(grapes_ctx* ctx, const float* Y, int ldy, const int* n_dev, int cap_n, int K, const float* W_hi,
+                             const float* W_lo, int ldw, int D, const float* b, float* H, int ldh, void* stream) {
+    GRAPES_REQUIRE(ctx && Y && n_dev && W_hi && W_lo && b && H, "null argument");
+    GRAPES_REQUIRE(D % TC_BN == 0 && D >= TC_BN && D <= 512, "hidden dim must be a multiple of 128 (<= 512) for the tcgen05 path");
+    GRAPES_REQUIRE(K > 0 && K <= ldy && K <= ldw && ldh >= D && ldh % 4 == 0 && (((uintptr_t)H) & 15) == 0, "bad layout");
+    return launch_fwd_ts(ctx, Y, ldy, n_dev, cap_n, K, W_hi, W_lo, ldw, D, b, b /* unused weights: zpart == NULL */, nullptr,
+                         nullptr, H, ldh, stream);
+}
 
 // Gradient DIRECTION of sum_r dz[r] z[r] w.r.t. (W1, b1, w2), accumulated (+=, times `scale`).
 // Y must carry a column of ones at index `ones_col` (>= K); maskT from grapes_sampler_l1_fwd_tc.  Y_lo as in the forward.

@@ -23,7 +23,7 @@ from typing import Optional, Tuple
 import torch
 
 from ._lib import GrapesError
-from .gcn import GCN, GraphNorm
+from .gcn import GCN, GraphNorm, full_graph_forward
 from .graph import DeviceGraph
 from .utils import TensorMap, get_logger
 
@@ -80,7 +80,7 @@ def evaluate(gcn_c: GCN,
     mask_d = mask.to(device) if mask is not None else torch.ones(data.num_nodes, dtype=torch.bool, device=device)
 
     if full_batch:
-        logits_total, _ = gcn_c(x, _graph_norm(adjacency, data))            # eval.py:50
+        logits_total = full_graph_forward(gcn_c, x, _graph_norm(adjacency, data))   # eval.py:50
         res = _scores(logits_total[mask_d], y[mask_d])
         return (res + (logits_total,)) if return_predictions else res
 

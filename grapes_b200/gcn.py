@@ -66,45 +66,135 @@ class GraphNorm(NormAdj):
     /root/reference/eval.py:47-56: ``gcn_c(x, edge_index)`` over every edge).  PyG semantics:
     stored self-loops are dropped, one self-loop per node is added, deg = in-degree + 1; the in-neighbour lists are
     the CSR of the transposed adjacency (edge_index[0] = source row, edge_index[1] = destination column),
-    ascending source inside a row.  One-off device sort; the aggregation itself is ``grapes_aggregate``
-    (TMA-staged SpMM) straight on these arrays -- nnz must fit int32 offsets (papers100M-shape needs sharding)."""
+    ascending source inside a row.  Built by the library's own kernels -- ``grapes_row_offsets`` + ``grapes_expand_rows``
+    turn the CSR back into its edge list, ``grapes_build_csr`` (counting sort by destination, per-row sort, self-loops
+    dropped, deg^-1/2) is the same routine that builds every hop's structure -- one-off, cached on the graph; the
+    aggregation itself is ``grapes_aggregate`` (TMA-staged SpMM) straight on these arrays.  nnz must fit int32 offsets
+    (papers100M-shape needs sharding)."""
 
     def __init__(self, graph, edge_index=None):
         """``edge_index`` given: the structure of THAT edge list (duplicates kept and counted, exactly what
         ``gcn_c(x, data.edge_index)`` sees in eval.py:50); otherwise the graph's canonical CSR (duplicates collapsed
         by main.py:134)."""
+        import ctypes
         dev = graph.device
         N = graph.num_nodes
-        self.holder = graph
-        if edge_index is not None:
-            ei = edge_index.to(device=dev, dtype=torch.int64)
-            src, dst = ei[0], ei[1]
-        else:
-            counts = graph.indptr[1:] - graph.indptr[:-1]
-            src = torch.repeat_interleave(torch.arange(N, device=dev, dtype=torch.int64), counts)
-            dst = graph.indices.to(torch.int64)
-        if src.numel() >= (1 << 31) - 1:
+        L = lib()
+        st = _stream()
+        E = int(edge_index.shape[1]) if edge_index is not None else graph.nnz
+        if E >= (1 << 31) - 1:
             raise GrapesError("full-graph aggregation needs nnz < 2^31 per device")
-        keep = src != dst
-        key = dst[keep] * N + src[keep]
-        del src, dst, keep
-        self.n, self.E = N, int(key.numel())
-        key = torch.sort(key).values
-        d = torch.div(key, N, rounding_mode="floor")
-        self.in_src = (key - d * N).to(torch.int32)
-        del key
-        indeg = torch.bincount(d, minlength=N)
-        del d
-        self.in_off = torch.zeros(N + 1, dtype=torch.int32, device=dev)
-        self.in_off[1:] = torch.cumsum(indeg, 0).to(torch.int32)
-        self.dinv = (1.0 / torch.sqrt((indeg + 1).to(torch.float32))).contiguous()
-        self.cnt = torch.tensor([int(self.in_src.numel()), N, 0, 0, 0, 0], dtype=torch.int32, device=dev)
+        capE, capn = max(E, 1), max(N, 1)
+        # a context whose scan scratch covers E entries (the graph's own is sized for frontiers)
+        self._own_ctx = ctypes.c_void_p()
+        rc = L.cdll.grapes_ctx_create(dev.index, N, max(capE, capn), 1 << 20, ctypes.byref(self._own_ctx))
+        if rc != 0:
+            raise GrapesError(f"grapes_ctx_create failed ({rc}): {L.last_error()}")
+        ctx = self._own_ctx
+        self.holder = self                       # NormAdj.aggregate reads holder.ctx
+        self.graph = graph
+        self.n, self.E = N, E
+        cnt = torch.tensor([E, N, 0, 0, 0, 0], dtype=torch.int32, device=dev)
+        c = cnt.data_ptr()
+        if edge_index is not None:
+            ei = edge_index.to(device=dev)
+            src = ei[0].to(torch.int32).contiguous()
+            dst = ei[1].to(torch.int32).contiguous()
+        else:
+            # the CSR back as an edge list: position of a row in `rows` == its id, so e_row is the source id
+            rows = torch.arange(N, dtype=torch.int32, device=dev)
+            row_off = torch.empty(N + 1, dtype=torch.int32, device=dev)
+            src = torch.empty(capE, dtype=torch.int32, device=dev)
+            dst = torch.empty(capE, dtype=torch.int32, device=dev)
+            cntP = torch.tensor([N, 0, 0, 0], dtype=torch.int32, device=dev)
+            L.grapes_row_offsets(ctx, ptr(graph.indptr), ptr(rows), cntP.data_ptr(), capn, ptr(row_off), cntP.data_ptr() + 4,
+                                 capE, None, None, cntP.data_ptr() + 8, st)
+            L.grapes_expand_rows(ctx, ptr(graph.indptr), ptr(graph.indices), ptr(rows), cntP.data_ptr(), capn, ptr(row_off),
+                                 cntP.data_ptr() + 4, capE, ptr(src), ptr(dst), None, st)
+            del rows, row_off
+        scratch = torch.zeros(capn, dtype=torch.int32, device=dev)
+        tmp = torch.empty(capE, dtype=torch.int32, device=dev)
+        ovf = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.in_off = torch.zeros(capn + 1, dtype=torch.int32, device=dev)
+        in_src = torch.empty(capE, dtype=torch.int32, device=dev)
+        self.dinv = torch.empty(capn, dtype=torch.float32, device=dev)
+        L.grapes_build_csr(ctx, ptr(dst), ptr(src), c, capE, c + 4, capn, ptr(scratch), 0, ptr(self.in_off), ptr(in_src),
+                           ptr(tmp), ptr(self.dinv), c + 8, ptr(ovf), st)
+        nnz = int(cnt[2].item())                 # stored entries without the dropped self-loops (one-off read-back)
+        self.in_src = in_src[:nnz].clone() if nnz < capE else in_src
+        del src, dst, tmp, scratch, in_src
+        self.cnt = torch.tensor([nnz, N, 0, 0, 0, 0], dtype=torch.int32, device=dev)
         self.out_off = self.out_dst = None
+
+    @property
+    def ctx(self):
+        return self._own_ctx
+
+    def __del__(self):
+        try:
+            if getattr(self, "_own_ctx", None):
+                lib().cdll.grapes_ctx_destroy(self._own_ctx)
+                self._own_ctx = None
+        except Exception:
+            pass
 
     def aggregate(self, x, transpose=False, bias=None):
         if transpose:
             raise GrapesError("GraphNorm is forward-only (evaluation); training uses the sampled blocks")
         return super().aggregate(x, False, bias)
+
+
+def dense_bias_relu_tc(Y: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """relu(Y W^T + b) for a tall Y [n, K] on the tcgen05 kernels (3xTF32, fp32-accurate; ``grapes_gemm_bias_relu_tc``): the
+    hidden layer of the whole-graph evaluation forward.  Requires out_features % 128 == 0 (<= 512)."""
+    holder = _any_ctx(Y.device)
+    L, ctx, st = lib(), holder.ctx, _stream()
+    n, K = Y.shape
+    D = weight.shape[0]
+    ldy = Y.stride(0)
+    assert Y.stride(1) == 1 and ldy % 4 == 0 and Y.data_ptr() % 16 == 0
+    ldw = (K + 3) // 4 * 4
+    w = weight.detach().float().contiguous()
+    Wh = torch.empty((D, ldw), dtype=torch.float32, device=Y.device)
+    Wl = torch.empty((D, ldw), dtype=torch.float32, device=Y.device)
+    L.grapes_split_tf32(ctx, ptr(w), K, D, K, ptr(Wh), ptr(Wl), ldw, st)
+    H = torch.empty((n, D), dtype=torch.float32, device=Y.device)
+    cnt = torch.tensor([n], dtype=torch.int32, device=Y.device)
+    b = bias.detach().float().contiguous()
+    L.grapes_gemm_bias_relu_tc(ctx, ptr(Y), ldy, cnt.data_ptr(), n, K, ptr(Wh), ptr(Wl), ldw, D, ptr(b), ptr(H), D, st)
+    return H
+
+
+@torch.no_grad()
+def full_graph_forward(gcn: "GCN", x: torch.Tensor, gn: GraphNorm) -> torch.Tensor:
+    """``gcn_c(x, edge_index)`` over the whole graph (eval.py:50) for the two-layer classifier, forward only, every product on
+    this library's kernels: Y = A_hat X (TMA-staged SpMM at the narrower width), H = relu(Y W1^T + b1) on the tensor cores,
+    Z = H W2^T, logits = A_hat Z + b2.  Falls back to the module's own forward for other depths / hidden widths."""
+    layers = list(gcn.gcn_layers)
+    D = layers[0].lin.weight.shape[0] if layers else 0
+    if len(layers) != 2 or D % 128 != 0 or D > 512 or x.shape[0] < 4096 or gcn.training and gcn.dropout > 0:
+        return gcn(x, gn)[0]
+    n, F = x.shape
+    xp = x.float()
+    if F % 4 != 0:                                    # 16-byte rows for the TMA-staged aggregation and the A tiles
+        xp = torch.zeros((n, (F + 3) // 4 * 4), dtype=torch.float32, device=x.device)
+        xp[:, :F].copy_(x)
+        Y = gn.aggregate(xp)
+    else:
+        Y = gn.aggregate(xp.contiguous())
+    H = dense_bias_relu_tc(Y[:, :F] if Y.shape[1] != F else Y, layers[0].lin.weight, layers[0].bias)
+    w2 = layers[1].lin.weight.detach().float().contiguous()
+    C = w2.shape[0]
+    C4 = (C + 3) // 4 * 4
+    Z = _gemm(3, H, D, w2, D, n, C, D, ldc=C4) if C4 != C else _gemm(3, H, D, w2, D, n, C, D)
+    b2 = layers[1].bias.detach().float()
+    if C4 != C:
+        b2 = F_pad(b2, C4 - C)
+    return gn.aggregate(Z, bias=b2.contiguous())[:, :C]
+
+
+def F_pad(t: torch.Tensor, k: int) -> torch.Tensor:
+    return F.pad(t, (0, k))
 
 
 def _gemm(layout, A, lda, B, ldb, M, N, K, bias=None, relu=0, ldc=None):

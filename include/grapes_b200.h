@@ -257,6 +257,11 @@ int grapes_sampler_l1_fwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo,
                              int K, const float* W_hi, const float* W_lo, int ldw, int D, const float* b1,
                              const float* w2, float* zpart, uint32_t* maskT, void* stream);
 
+/* dense layer with bias + relu on the tensor cores (same kernel, hidden activations written out): H[n x D] = relu(Y W^T + b),
+ * the hidden layer of the full-graph evaluation forward gcn_c(x, edge_index) (eval.py:50).  ldh % 4 == 0, H 16-byte aligned.  */
+int grapes_gemm_bias_relu_tc(grapes_ctx* ctx, const float* Y, int ldy, const int* n_dev, int cap_n, int K, const float* W_hi,
+                             const float* W_lo, int ldw, int D, const float* b, float* H, int ldh, void* stream);
+
 /* backward on tensor cores: S = mask^T (dz * Y) from the relu mask bits; Y must hold a column of ones at
  * `ones_col` (K <= ones_col < ncols <= ldy).  Accumulates scale * d(sum dz.z)/d(W1,b1,w2).               */
 int grapes_sampler_l1_bwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo, int ldy, int ncols, const int* n_dev,

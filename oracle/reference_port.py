@@ -481,3 +481,29 @@ def reference_evaluate(st: OracleState, mask: torch.Tensor, full_batch: bool = T
     out["batches"] = per_batch
     out["accuracy"] = out["f1"] = float((all_predictions == data.y[mask]).double().mean())
     return out
+
+
+def full_graph_logits_cpu(gcn: "OracleGCN", x: torch.Tensor, adjacency: sp.csr_matrix) -> torch.Tensor:
+    """eval.py:50 on the host at BASELINE sizes: ``gcn_c(x, edge_index)`` over every stored entry of ``adjacency`` in PyG's
+    order (lin, then propagate), with the propagate written as ONE sparse-CSR x dense
+    product per layer (torch / MKL threads) instead of :func:`gcn_conv`'s ``h[src]`` gather, which would materialise an
+    [E, 256] array (127 GB on the products-shaped graph).  Same arithmetic: out[dst] = sum_e w_e h[src_e] + b with
+    w_e = deg^-1/2[src] deg^-1/2[dst] over the stored edges minus self-loops plus one loop per node."""
+    n = adjacency.shape[0]
+    A = adjacency.astype(np.float32).tocsr(copy=True)
+    A.setdiag(0)
+    A.eliminate_zeros()
+    AT = (A.T + sp.identity(n, dtype=np.float32, format="csr")).tocsr()      # rows = destinations, cols = sources
+    deg = np.asarray(AT.sum(axis=1)).reshape(-1)                              # in-degree + 1
+    dis = (1.0 / np.sqrt(deg)).astype(np.float32)
+    AT = sp.diags(dis) @ AT @ sp.diags(dis)
+    AT = AT.tocsr()
+    a_hat = torch.sparse_csr_tensor(torch.from_numpy(AT.indptr.astype(np.int64)), torch.from_numpy(AT.indices.astype(np.int64)),
+                                    torch.from_numpy(AT.data.astype(np.float32)).to(x.dtype), size=(n, n))
+    h = x
+    layers = list(gcn.gcn_layers)
+    for i, layer in enumerate(layers):
+        h = a_hat @ (h @ layer.lin.weight.t()) + layer.bias
+        if i + 1 < len(layers):
+            h = torch.relu(h)
+    return h

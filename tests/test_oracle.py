@@ -204,3 +204,18 @@ def test_csr_from_edge_index_has_no_cpu_path():
     from grapes_b200.graph import csr_from_edge_index
     with pytest.raises(GrapesError):
         csr_from_edge_index(torch.zeros(2, 3, dtype=torch.long), 4, "cpu")
+
+
+def test_full_graph_logits_cpu_equals_gcn_conv_path():
+    """bench.py's full-graph CPU leg (one sparse-CSR x dense product per layer) is the same arithmetic as the oracle's
+    GCN.forward on the deduplicated edge list (eval.py:50)."""
+    import numpy as np
+    from grapes_b200.synth import make_synth
+    d = make_synth("small", seed=1)
+    st = rp.OracleState(d, sampling_hops=2, num_samples=8, seed=3, dtype=torch.float64)
+    coo = st.adjacency.tocoo()
+    ei = torch.stack([torch.from_numpy(coo.row.astype(np.int64)), torch.from_numpy(coo.col.astype(np.int64))])
+    with torch.no_grad():
+        a = st.gcn_c(st.x, ei)[0]
+        b = rp.full_graph_logits_cpu(st.gcn_c, st.x, st.adjacency)
+    assert float((a - b).abs().max() / a.abs().max()) < 1e-6
