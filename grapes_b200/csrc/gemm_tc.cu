@@ -440,7 +440,7 @@ __device__ __forceinline__ uint32_t warp_bit_transpose(uint32_t x, int lane) {
     return x;
 }
 
-template <bool LONGK>
+template <bool LONGK, bool DENSE>
 __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
     const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB_hi,
     const __grid_constant__ CUtensorMap tmB_lo, const int* __restrict__ n_dev, int cap_n, int K, int D, int wres,
@@ -644,7 +644,7 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
                             zs3 = fmaf(fmaxf(p3, 0.f), ww.w, zs3);
                             // dense-layer mode (grapes_gemm_bias_relu_tc): the hidden activations themselves, 16 bytes
                             // of the thread's row at a time (a thread covers whole 128-byte lines of its row)
-                            if (hout && row < n)
+                            if (DENSE && hout && row < n)
                                 *reinterpret_cast<float4*>(hout + (size_t)row * ldh + nh * TC_BN + ch * 32 + 4 * i) =
                                     make_float4(fmaxf(p0, 0.f), fmaxf(p1, 0.f), fmaxf(p2, 0.f), fmaxf(p3, 0.f));
                             rowbits |= (p0 > 0.f ? 1u : 0u) << (4 * i) | (p1 > 0.f ? 1u : 0u) << (4 * i + 1) |
@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) k_l1_fwd_ts(
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            if (zpart && row < n) {                               // two partial rows per half: (chains 0, 1) and (chains 2, 3)
+            if ((!DENSE || zpart) && row < n) {                   // two partial rows per half: (chains 0, 1) and (chains 2, 3)
                 zpart[(size_t)(nh * 2) * cap_n + row] = zs0 + zs1;
                 zpart[(size_t)(nh * 2 + 1) * cap_n + row] = zs2 + zs3;
             }
@@ -1313,17 +1313,26 @@ static int launch_fwd_ts(grapes_ctx* ctx, const float* Y, int ldy, const int* n_
         static int attr_ts[64] = {0};
         int& have = attr_ts[ctx->device & 63];
         if (smem_bytes > have) {
-            GRAPES_CUDA_OK(cudaFuncSetAttribute(k_l1_fwd_ts<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-            GRAPES_CUDA_OK(cudaFuncSetAttribute(k_l1_fwd_ts<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+            GRAPES_CUDA_OK(cudaFuncSetAttribute(k_l1_fwd_ts<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+            GRAPES_CUDA_OK(cudaFuncSetAttribute(k_l1_fwd_ts<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+            GRAPES_CUDA_OK(cudaFuncSetAttribute(k_l1_fwd_ts<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+            GRAPES_CUDA_OK(cudaFuncSetAttribute(k_l1_fwd_ts<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
             have = smem_bytes;
         }
         unsigned long long* dbg = (g_tc_debug & 16) ? reinterpret_cast<unsigned long long*>(ctx->partials) : nullptr;
-        if (nkb > TC_CHUNK_KB)
-            pdl((k_l1_fwd_ts<true>), per_half * NH, TCS_THREADS, smem_bytes, (cudaStream_t)stream)(
-                ma, mb_hi, mb_lo, n_dev, cap_n, K, D, wres, bstages, ystages, b1, w2, zpart, maskT, hout, ldh, dbg);
-        else
-            pdl((k_l1_fwd_ts<false>), per_half * NH, TCS_THREADS, smem_bytes, (cudaStream_t)stream)(
-                ma, mb_hi, mb_lo, n_dev, cap_n, K, D, wres, bstages, ystages, b1, w2, zpart, maskT, hout, ldh, dbg);
+        const dim3 grid(per_half * NH);
+        cudaStream_t cs = (cudaStream_t)stream;
+        // the sampler-head form (DENSE = false) is the instantiation every parity test of this round ran; the dense-layer form
+        // (hidden activations written out, grapes_gemm_bias_relu_tc) is its own instantiation
+#define TS_ARGS ma, mb_hi, mb_lo, n_dev, cap_n, K, D, wres, bstages, ystages, b1, w2, zpart, maskT, hout, ldh, dbg
+        if (hout) {
+            if (nkb > TC_CHUNK_KB) pdl((k_l1_fwd_ts<true, true>), grid, TCS_THREADS, smem_bytes, cs)(TS_ARGS);
+            else pdl((k_l1_fwd_ts<false, true>), grid, TCS_THREADS, smem_bytes, cs)(TS_ARGS);
+        } else {
+            if (nkb > TC_CHUNK_KB) pdl((k_l1_fwd_ts<true, false>), grid, TCS_THREADS, smem_bytes, cs)(TS_ARGS);
+            else pdl((k_l1_fwd_ts<false, false>), grid, TCS_THREADS, smem_bytes, cs)(TS_ARGS);
+        }
+#undef TS_ARGS
         grapes_count_launches(1);
         GRAPES_LAUNCH_OK();
         return GRAPES_OK;
