@@ -44,7 +44,7 @@ def parse_args():
                          "'none' = DIAGNOSTIC ONLY: the ranks train independent replicas (no exchange), to price the exchange")
     ap.add_argument("--prime", type=int, default=40, help="untimed steps before the W warm-up steps (clocks, allocator, graph variants, communicator)")
     ap.add_argument("--no-prefetch", action="store_true", help="no cross-step prefetch of the next batch's hop-0 front end")
-    ap.add_argument("--cpu-budget-s", type=float, default=20.0)
+    ap.add_argument("--cpu-budget-s", type=float, default=12.0)
     return ap.parse_args()
 
 
@@ -561,7 +561,7 @@ def main():
             try:
                 cmd = [sys.executable, os.path.join(ROOT, "scripts", "bench_full_eval.py"), "--workload", cfgname,
                        "--seed", str(args.seed)] + (["--no-cpu"] if args.no_cpu_baseline else [])
-                res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+                res = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
                 lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
                 full_eval = json.loads(lines[-1]) if (res.returncode == 0 and lines) else \
                     {"error": f"rc={res.returncode}: " + (res.stderr or res.stdout)[-300:]}
