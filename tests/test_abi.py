@@ -64,3 +64,26 @@ def test_product_path_has_no_cpu_fallback():
         from grapes_b200.graph import DeviceGraph
         with pytest.raises(GrapesError):
             DeviceGraph.from_edge_index(torch.zeros(2, 3, dtype=torch.long), 4, device="cpu")
+
+
+def test_built_library_carries_the_id_of_this_source_tree():
+    """The loader refuses (or rebuilds) a binary whose build id is not the sha1 of the sources + header it parses its
+    prototypes from: a stale library would mean silently corrupted arguments."""
+    from grapes_b200 import build
+    from grapes_b200._lib import lib
+    L = lib()
+    assert not build.is_stale()
+    L.cdll.grapes_build_id.restype = __import__("ctypes").c_char_p
+    assert L.cdll.grapes_build_id().decode() == build.tree_id() == build.built_id()
+
+
+def test_flag_word_raises_with_the_reason():
+    """GRAPES_OVF_* bits of a step (scal[15] / the overflow word) -> GrapesError naming the cause; 0 is silent."""
+    import pytest
+    from grapes_b200._lib import GrapesError
+    from grapes_b200.engine import GrapesEngine
+    GrapesEngine.raise_on_flags(0)
+    with pytest.raises(GrapesError, match="nodes>cap_n"):
+        GrapesEngine.raise_on_flags(4)
+    with pytest.raises(GrapesError, match="exchange failed"):
+        GrapesEngine.raise_on_flags(32 | 2)
