@@ -140,7 +140,8 @@ class ClockSampler:
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
-        self.index, self.samples, self.reasons, self.stop_flag, self.thread = index, [], set(), False, None
+        self.index, self.trace, self.stop_flag, self.thread = index, [], False, None
+        self.t0 = self.t1 = None
         self.max_mhz, self.nvml, self.handle = None, None, None
         try:
             import pynvml
@@ -165,32 +166,46 @@ class ClockSampler:
                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
         while not self.stop_flag:
             try:
-                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                t = time.perf_counter()
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
                 except Exception:
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
-                for name, bit in bits.items():
-                    if r & bit:
-                        self.reasons.add(name)
+                self.trace.append((t, mhz, [name for name, bit in bits.items() if r & bit]))
             except Exception:
                 pass
-            time.sleep(0.001)
+            time.sleep(0.0005)
 
     def start(self):
+        """The polling thread starts BEFORE the warm-up (its first NVML calls take milliseconds); only the samples between
+        mark_begin() and mark_end() -- the timed region -- are reported."""
         if self.nvml is None:
             return
+        self.trace, self.t0, self.t1 = [], None, None
         self.thread = threading.Thread(target=self._poll, daemon=True)
         self.thread.start()
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.nvml is None:
             return self._smi_once()
         self.stop_flag = True
         self.thread.join(timeout=1.0)
-        sm = sorted(self.samples)
+        t0 = self.t0 if self.t0 is not None else 0.0
+        t1 = self.t1 if self.t1 is not None else float("inf")
+        inside = [e for e in self.trace if t0 <= e[0] <= t1]
+        if not inside and self.trace:                     # a window shorter than one poll: the samples around it
+            inside = sorted(self.trace, key=lambda e: min(abs(e[0] - t0), abs(e[0] - t1)))[:2]
+        sm = sorted(e[1] for e in inside)
+        reasons = sorted({n for e in inside for n in e[2]})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "samples": len(sm),
-                "reasons": sorted(self.reasons), "source": "nvml, 1 ms polling during the timed region"}
+                "reasons": reasons, "source": "nvml, polled every ~0.5 ms from before the warm-up; samples inside the timed region"}
 
     def _smi_once(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -344,19 +359,22 @@ def main():
     for j in range(PRIME):                                            # untimed: clocks up, every graph variant captured,
         one_step(j % W)                                               # communicator channels set up
     sync_all()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for j in range(W):
         one_step(j)
     sync_all()
     eng.check_overflow()
     launches0 = L.grapes_kernel_launches()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     sync_all()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    sampler.mark_begin()
     ev[0].record()
     for j in range(W, W + K):
         one_step(j)
         ev[j - W + 1].record()
+    torch.cuda.synchronize()
+    sampler.mark_end()
     sync_all()
     clocks = sampler.stop()
     ms = ev[0].elapsed_time(ev[K])
