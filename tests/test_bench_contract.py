@@ -46,3 +46,19 @@ def test_committed_bench_line_carries_the_contract():
     ck = d["clocks"]
     assert ck["sm_mhz"] > 0 and ck["sm_max_mhz"] >= ck["sm_mhz"] and isinstance(ck["reasons"], list)
     assert not set(ck["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_round2_bench_lines_carry_the_round2_keys():
+    """Round-2 additions: per-rank step-time percentiles, the priming steps, where `traffic` was read from, how the gradient is
+    exchanged; the 8-GPU line was taken under the driver's own command (--steps 20 --warmup 5)."""
+    d = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_v3.json")))
+    for k in ("step_times", "prime_steps", "gradient_exchange", "rooflines", "clocks", "e2e", "gpu_launches"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and len(d["step_times"]) == 1 and d["step_times"][0]["p50_ms"] > 0
+    assert d["roofline"]["traffic_source"]["commit"] and d["roofline"]["traffic"] > 0
+    assert d["e2e"]["value"] < d["value"] and d["launches_per_step"] == 69
+    s = json.load(open(os.path.join(ROOT, "profiles", "r02_scale_products_n8_peer_20a.json")))
+    assert s["n_gpus"] == 8 and s["steps"] == 20 and s["warmup"] == 5 and len(s["step_times"]) == 8
+    assert "peer memory" in s["gradient_exchange"] and s["scaling"] == "weak"
+    assert s["value"] > 6.5 * d["value"]                       # the north star's 8-GPU target against this round's 1-GPU line
+    assert max(t["p50_ms"] for t in s["step_times"]) < 1.02 * min(t["p50_ms"] for t in s["step_times"])
