@@ -1402,7 +1402,8 @@ int grapes_sampler_l1_fwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo,
         blocks = max_tiles < ctx->sm_count ? max_tiles : ctx->sm_count;
         if (blocks < 1) blocks = 1;
     }
-    static int attr = 0;
+    static int attr_dev[64] = {0};                   // per device: the attribute belongs to the device's copy of the function
+    int& attr = attr_dev[ctx->device & 63];
     if (smem_bytes > attr) {
         GRAPES_CUDA_OK(cudaFuncSetAttribute(k_l1_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         attr = smem_bytes;
@@ -1484,7 +1485,8 @@ int grapes_sampler_l1_bwd_tc(grapes_ctx* ctx, const float* Y, const float* Y_lo,
     int rc;
     if ((rc = make_map(&my, Y, cap_n, ncols, ldy, TCB_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != GRAPES_OK) return rc;
     if ((rc = make_map(&my_lo, Y_lo ? Y_lo : Y, cap_n, ncols, ldy, TCB_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) != GRAPES_OK) return rc;
-    static int attr_bytes = 0;
+    static int attr_bytes_dev[64] = {0};
+    int& attr_bytes = attr_bytes_dev[ctx->device & 63];
     if (smem_bytes > attr_bytes) {
         GRAPES_CUDA_OK(cudaFuncSetAttribute(k_l1_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         attr_bytes = smem_bytes;
