@@ -305,7 +305,7 @@ def test_node_capacity_overflow_is_flagged_and_memory_safe(cuda_device):
         eng.check_overflow()
     tool = shutil.which("compute-sanitizer") or "/usr/local/cuda/bin/compute-sanitizer"
     # opt-in (GRAPES_SANITIZE=1): B200_PROFILING.md allows one sanitizer OR ncu run per GPU lease, and the round-end
-    # driver profiles with ncu in the lease that runs this suite.  Result of the opt-in run: profiles/r02_sanitizer.md
+    # driver profiles with ncu in the lease that runs this suite.  (Not run in round 2: the GPU budget went elsewhere.)
     if os.environ.get("GRAPES_SANITIZE", "0") != "1" or not os.path.isfile(tool):
         return
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
