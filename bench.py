@@ -341,8 +341,10 @@ def main():
     # flat gradient (91 k floats on products-shape), fused with the gradient scale and both Adam updates into the step's
     # last launch over NVLink peer memory ('peer'), or ncclAllReduce captured into the step graph ('nccl').  Either way a
     # step is one graph launch and every rank ends it with bit-identical parameters.
+    exchange_used = "none"
     if world > 1 and args.exchange != "none":
         eng.enable_data_parallel(exchange=args.exchange)
+        exchange_used = "peer" if eng.peer is not None else "nccl"     # (peer falls back to nccl, on every rank, without P2P)
 
     def one_step(j):
         # the ids of batch j+1 are handed over with batch j: its reset + weight-independent hop-0 front end are enqueued
@@ -381,7 +383,7 @@ def main():
     eng.check_overflow()
     if use_graph:
         # kernels recorded into the graph once, replayed K times (the NCCL exchange adds its own all-reduce kernel)
-        per_step = eng.launches_per_graph + (1 if (world > 1 and args.exchange == "nccl") else 0)
+        per_step = eng.launches_per_graph + (1 if exchange_used == "nccl" else 0)
         launches = per_step * K
     else:
         launches = L.grapes_kernel_launches() - launches0
@@ -594,7 +596,7 @@ def main():
                 "step_times": step_times, "prime_steps": PRIME,
                 "gradient_exchange": ("none" if world == 1 else "NONE (diagnostic run: independent replicas, not data parallel)" if args.exchange == "none" else
                                       ("gradient scale + push all-reduce over NVLink peer memory + Adam: one kernel inside the step graph"
-                                       if args.exchange == "peer" else "ncclAllReduce(AVG) captured into the step graph + Adam launch"))}
+                                       if exchange_used == "peer" else "ncclAllReduce(AVG) captured into the step graph + Adam launch"))}
         emit(line)
     if world > 1:
         dist.barrier()

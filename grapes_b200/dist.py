@@ -59,4 +59,6 @@ class PeerGradExchange:
         self.peer_ptrs = (ctypes.c_void_p * self.world)(*ptrs)              # HOST array handed to the C ABI
         self.state = torch.zeros(int(lib().cdll.grapes_peer_state_words()), dtype=torch.int32, device=device)
         torch.cuda.synchronize(device)
-        dist.barrier(group)                                                   # every buffer is zeroed before anyone publishes
+        # NOTE: no collective here.  The caller must synchronise the ranks once before the first exchange (every buffer is
+        # zeroed before anyone publishes): GrapesEngine.enable_data_parallel does it with the all-reduce that also makes
+        # the ranks agree on whether the peer mapping worked everywhere.

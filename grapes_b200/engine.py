@@ -853,9 +853,24 @@ class GrapesEngine:
         self.peer, self.dp_group = None, None
         if self.dp_world > 1:
             if exchange == "peer":
+                # symmetric (peer-mapped) buffers need P2P access between every pair of GPUs of the group.  Every rank tries,
+                # the ranks agree (MIN over a success flag), and if any of them could not map its peers ALL of them take the
+                # NCCL exchange -- a rank-local decision would deadlock the first step.
                 from .dist import PeerGradExchange
-                self.peer = PeerGradExchange(self.n_par, self.device, group)
-            else:
+                ok, why = 1, ""
+                try:
+                    self.peer = PeerGradExchange(self.n_par, self.device, group)
+                except Exception as exc:                      # noqa: BLE001 -- reported below, never silent
+                    ok, why, self.peer = 0, f"{type(exc).__name__}: {exc}", None
+                flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+                if int(flag.item()) == 0:
+                    import warnings
+                    warnings.warn("grapes_b200: peer-memory gradient exchange unavailable on this box"
+                                  + (f" ({why})" if why else " (another rank could not map its peers)")
+                                  + "; every rank uses the NCCL exchange instead")
+                    self.peer, exchange = None, "nccl"
+            if exchange == "nccl":
                 self.dp_group = group
                 # the first collectives of a communicator set up its channels: not inside a captured or timed step
                 warm = torch.zeros_like(self.grads)

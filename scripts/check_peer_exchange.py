@@ -23,6 +23,7 @@ def main():
     g0 = torch.Generator(device=dev).manual_seed(7)
     params = torch.randn(n, generator=g0, device=dev)
     pe = PeerGradExchange(n, dev)
+    dist.barrier()                                   # every rank's buffer is zeroed before anyone publishes
     st = torch.cuda.current_stream().cuda_stream
     gr = torch.Generator(device=dev).manual_seed(100 + rank)
 
