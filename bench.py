@@ -45,6 +45,9 @@ def parse_args():
     ap.add_argument("--prime", type=int, default=40, help="untimed steps before the W warm-up steps (clocks, allocator, graph variants, communicator)")
     ap.add_argument("--no-prefetch", action="store_true", help="no cross-step prefetch of the next batch's hop-0 front end")
     ap.add_argument("--cpu-budget-s", type=float, default=12.0)
+    ap.add_argument("--full-eval", action="store_true",
+                    help="also run scripts/bench_full_eval.py (full-graph evaluation forward on the opt-in tensor-core path, NOT yet "
+                         "verified on a GPU) in a process of its own and attach its line as `full_graph_eval`")
     return ap.parse_args()
 
 
@@ -575,9 +578,9 @@ def main():
                    "sample": f"{done} steps of batch {B} on the same graph (oracle port of main.py:161-291, torch CPU fp32)",
                    "ms_per_step": 1e3 * t_total / done}
         # ---- full-graph evaluation forward gcn_c(x, edge_index) (eval.py:47-56; next-row f1) beside the oracle's CPU forward.
-        # Written after this round's GPU budget was spent, so it runs in its OWN process (own CUDA context): whatever happens
-        # there costs this entry, never the bench line ----
-        if world == 1 and not args.no_spmm and cfgname != "papers":
+        # Written after this round's GPU budget was spent and never run on a GPU: only on request (--full-eval), and in its OWN
+        # process (own CUDA context) so that whatever happens there costs this entry, never the bench line ----
+        if world == 1 and args.full_eval and cfgname != "papers":
             try:
                 cmd = [sys.executable, os.path.join(ROOT, "scripts", "bench_full_eval.py"), "--workload", cfgname,
                        "--seed", str(args.seed)] + (["--no-cpu"] if args.no_cpu_baseline else [])
