@@ -87,3 +87,23 @@ def test_flag_word_raises_with_the_reason():
         GrapesEngine.raise_on_flags(4)
     with pytest.raises(GrapesError, match="exchange failed"):
         GrapesEngine.raise_on_flags(32 | 2)
+
+
+def test_hot_kernels_are_blackwell_native_in_sass(so_path):
+    """B200_PROFILING.md, "What proves a Blackwell-native kernel": the default sampler-head kernels issue tcgen05.mma with an
+    operand in tensor memory (UTC*MMA + STTM), read their accumulators with tcgen05.ld (LDTM) and stage tiles by TMA (UTMALDG);
+    the aggregation stages rows with cp.async.bulk (UBLKCP); nothing in the library uses the legacy mma.sync path (HMMA)."""
+    import shutil
+    import sys
+    if not (shutil.which("cuobjdump") or os.path.isfile("/usr/local/cuda/bin/cuobjdump")) or not shutil.which("c++filt"):
+        pytest.skip("cuobjdump / c++filt not available")
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from sass_evidence import sass_counts
+    fams, archs = sass_counts(so_path)
+    assert "sm_100a" in archs and archs <= {"sm_100a", "sm_52"}          # sm_52: nvcc's empty device-link stub
+    for k in ("k_l1_fwd_ts", "k_l1_bwd_ts"):
+        r = fams[k]
+        assert r["UTC*MMA"] > 0 and r["LDTM"] > 0 and r["STTM"] > 0 and r["UTMALDG"] > 0 and r["SYNCS"] > 0, (k, dict(r))
+    assert fams["k_agg_tma"]["UBLKCP"] > 0 and fams["k_agg_tma"]["SYNCS"] > 0
+    assert fams["k_step_tail"]["MEMBAR.*SYS"] > 0                         # peer-memory exchange: system-scope fences
+    assert sum(r["HMMA"] for r in fams.values()) == 0
