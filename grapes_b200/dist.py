@@ -32,6 +32,15 @@ def allreduce_mean_(flat: torch.Tensor) -> torch.Tensor:
     return flat
 
 
+def ranks_agree(ok: bool, device, group=None) -> bool:
+    """True iff EVERY rank of ``group`` passed ok=True (all-reduce MIN of a flag; also a synchronisation point of the
+    ranks).  Used where a rank-local decision would deadlock the group: whether the peer-memory exchange could be set up
+    (``GrapesEngine.enable_data_parallel``)."""
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(flag.item()))
+
+
 def flatten_grads(named_grads) -> torch.Tensor:
     return torch.cat([g.reshape(-1) for _, g in sorted(named_grads.items())])
 

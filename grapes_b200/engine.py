@@ -856,15 +856,13 @@ class GrapesEngine:
                 # symmetric (peer-mapped) buffers need P2P access between every pair of GPUs of the group.  Every rank tries,
                 # the ranks agree (MIN over a success flag), and if any of them could not map its peers ALL of them take the
                 # NCCL exchange -- a rank-local decision would deadlock the first step.
-                from .dist import PeerGradExchange
-                ok, why = 1, ""
+                from .dist import PeerGradExchange, ranks_agree
+                ok, why = True, ""
                 try:
                     self.peer = PeerGradExchange(self.n_par, self.device, group)
                 except Exception as exc:                      # noqa: BLE001 -- reported below, never silent
-                    ok, why, self.peer = 0, f"{type(exc).__name__}: {exc}", None
-                flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
-                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-                if int(flag.item()) == 0:
+                    ok, why, self.peer = False, f"{type(exc).__name__}: {exc}", None
+                if not ranks_agree(ok, self.device, group):
                     import warnings
                     warnings.warn("grapes_b200: peer-memory gradient exchange unavailable on this box"
                                   + (f" ({why})" if why else " (another rank could not map its peers)")

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from grapes_b200.dist import allreduce_mean_, flatten_grads, shard_batches
+from grapes_b200.dist import allreduce_mean_, flatten_grads, ranks_agree, shard_batches
 
 
 def _free_port():
@@ -41,7 +41,9 @@ def _worker(rank, world, port, out):
     flat = allreduce_mean_(local.clone())
     # apply the averaged gradient through Adam on every rank
     params = [p for net in (st.gcn_c, st.gcn_gf, st.gcn_z) for _, p in sorted(net.named_parameters())]
-    out[rank] = dict(batches=mine, local=local, reduced=flat,
+    # the agreement the engine uses before it picks the gradient exchange: one failing rank -> every rank sees False
+    agree = (ranks_agree(True, "cpu"), ranks_agree(rank != 1, "cpu"), ranks_agree(False, "cpu"))
+    out[rank] = dict(batches=mine, local=local, reduced=flat, agree=agree,
                      w0=torch.cat([p.detach().reshape(-1) for p in params]).clone())
     dist.barrier()
     dist.destroy_process_group()
@@ -70,3 +72,5 @@ def test_gradient_allreduce_is_mean_of_per_rank_gradients():
         assert torch.allclose(out[r]["reduced"], mean, rtol=1e-6, atol=0)
     assert torch.equal(out[0]["reduced"], out[1]["reduced"])             # identical on every rank -> identical Adam steps
     assert torch.equal(out[0]["w0"], out[1]["w0"])
+    # enable_data_parallel's peer -> NCCL fall-back is a GROUP decision (grapes_b200.dist.ranks_agree)
+    assert out[0]["agree"] == (True, False, False) and out[1]["agree"] == (True, False, False)
