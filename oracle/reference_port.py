@@ -25,6 +25,12 @@ Pinning status:
     tests/golden/ produced by tests/golden/make_golden.py from that import, and
     against the only known-answer vector the reference holds (TensorMap
     docstring, utils.py:104-108).
+  * evaluation (``reference_evaluate``, eval.py:11-165, full-batch and mini-batch): PINNED against the reference's
+    own ``evaluate`` imported live from /root/reference/eval.py (oracle/ref_import.py::load_reference_eval;
+    tests/test_oracle.py::test_oracle_evaluate_matches_live_reference_eval: scores equal, logits of every ``gcn_c`` call
+    equal bit for bit) and against the committed tests/golden/eval_*.npz produced by that function (evaluation blocks
+    bit-exact, logits, scores).  The models inside are this file's GCN restatement, so this pins the evaluation LOOP
+    (deterministic top-k, evaluation-direction slice, relabelling, batching, scores), not GCNConv.
   * GCNConv / gcn_norm, losses, gradients: "parity unpinned" by the reference
     (it has no tests and PyG cannot be installed here); pinned only by the dense
     closed form and a hand-computed 4-node example.

@@ -1,7 +1,8 @@
 """Generates the golden fixtures in this directory FROM THE REFERENCE ITSELF: imports
 /root/reference/modules/utils.py (through the scipy tensor-index shim of oracle/ref_import.py) and runs
 its own get_neighborhoods / slice_adjacency / TensorMap / sample_neighborhoods_from_probs and the mask
-dedup statements of main.py:183-195 on seeded synthetic graphs.  Run in the build container only
+dedup statements of main.py:183-195 on seeded synthetic graphs; and /root/reference/eval.py's own ``evaluate``
+(full-batch and mini-batch) for the eval_*.npz fixtures.  Run in the build container only
 (the GPU box has no /root/reference); the .npz outputs are committed.
 
     python tests/golden/make_golden.py
@@ -86,5 +87,50 @@ def main():
              mapped=tm.map(torch.tensor([52, 42, 32, 22, 22])).numpy())
 
 
+EVAL_CASES = [("tiny", 0, 32, 8, 2), ("tiny", 2, 50, 4, 3), ("small", 1, 256, 64, 2)]
+
+
+def main_eval():
+    """eval_*.npz: the reference's OWN ``evaluate`` (eval.py:11-165, imported live) run full-batch and mini-batch on seeded
+    synthetic graphs with seeded models; what it handed to / got from ``gcn_c`` is recorded per batch (the blocks the
+    evaluation hop loop built, the logits) next to the (accuracy, f1) it returned.  The models are the oracle's GCN restatement
+    (PyG is absent here): the fixture pins the evaluation LOOP -- deterministic top-k selection, evaluation-direction block
+    slice, relabelling, batching, scores -- not GCNConv."""
+    import argparse
+    from oracle import reference_port as rp
+    mod, ru = ref_import.load_reference_eval()
+    for name, seed, B, k, hops in EVAL_CASES:
+        d = make_synth(name, seed=seed)
+        st = rp.OracleState(d, sampling_hops=hops, num_samples=k, seed=seed + 5, dtype=torch.float32)
+        st.gcn_c.eval(); st.gcn_gf.eval()
+        args = argparse.Namespace(sampling_hops=hops, use_indicators=True, num_samples=k)
+        adj = ref_import.reference_adjacency(d.edge_index, d.num_nodes)
+        mask = d.test_mask
+        out = {"name": name, "seed": seed, "B": B, "k": k, "hops": hops, "mask": mask.numpy()}
+        for key, net in (("gcn_c", st.gcn_c), ("gcn_gf", st.gcn_gf)):
+            for n, t in net.state_dict().items():
+                out[f"w_{key}.{n}"] = t.numpy()
+        for full in (True, False):
+            node_map = ru.TensorMap(size=d.num_nodes)
+            loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(mask.nonzero().squeeze(1)), batch_size=B)
+            rc, rg = ref_import.RecordingModule(st.gcn_c), ref_import.RecordingModule(st.gcn_gf)
+            acc, f1 = mod.evaluate(rc, rg, d, args, adj, node_map, hops + 1, torch.device("cpu"), mask=mask,
+                                   eval_on_cpu=True, loader=loader, full_batch=full)
+            tag = "full_" if full else "mini_"
+            out[tag + "accuracy"], out[tag + "f1"] = acc, f1
+            if full:
+                out["full_logits"] = rc.calls[0]["logits"].numpy()
+            else:
+                out["mini_batches"] = len(rc.calls)
+                for b, c in enumerate(rc.calls):
+                    out[f"mini_b{b}_logits"] = c["logits"].numpy()
+                    for h, e in enumerate(c["edge_index"]):
+                        out[f"mini_b{b}_edges{h}"] = e.numpy()            # local ids, evaluation direction (eval.py:140-142,150)
+        path = os.path.join(HERE, f"eval_{name}_s{seed}.npz")
+        np.savez_compressed(path, **out)
+        print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
     main()
+    main_eval()

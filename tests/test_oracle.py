@@ -219,3 +219,68 @@ def test_full_graph_logits_cpu_equals_gcn_conv_path():
         a = st.gcn_c(st.x, ei)[0]
         b = rp.full_graph_logits_cpu(st.gcn_c, st.x, st.adjacency)
     assert float((a - b).abs().max() / a.abs().max()) < 1e-6
+
+
+def _eval_state(name, seed, k, hops, weights=None):
+    d = make_synth(name, seed=seed)
+    st = rp.OracleState(d, sampling_hops=hops, num_samples=k, seed=seed + 5, dtype=torch.float32)
+    if weights is not None:
+        for key, net in (("gcn_c", st.gcn_c), ("gcn_gf", st.gcn_gf)):
+            net.load_state_dict({n: _t(weights[f"w_{key}.{n}"]) for n in net.state_dict()})
+    st.gcn_c.eval(); st.gcn_gf.eval()
+    return d, st
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "eval_*.npz"))))
+def test_oracle_evaluate_matches_reference_golden(path):
+    """eval.py:11-165: the fixtures were produced by the reference's OWN ``evaluate``
+    (tests/golden/make_golden.py::main_eval); the oracle's restatement must rebuild the same evaluation blocks (bit-exact,
+    local ids, evaluation direction), the same logits per batch and the same scores."""
+    z = np.load(path)
+    name, seed, B, k, hops = str(z["name"]), int(z["seed"]), int(z["B"]), int(z["k"]), int(z["hops"])
+    d, st = _eval_state(name, seed, k, hops, weights=z)
+    mask = _t(z["mask"])
+    assert torch.equal(mask, d.test_mask)
+    full = rp.reference_evaluate(st, mask, full_batch=True)
+    assert np.allclose(full["logits"].numpy(), z["full_logits"], rtol=0, atol=1e-5 * np.abs(z["full_logits"]).max())
+    assert full["accuracy"] == pytest.approx(float(z["full_accuracy"]), abs=1e-12)
+    assert full["f1"] == pytest.approx(float(z["full_f1"]), abs=1e-12)
+    mini = rp.reference_evaluate(st, mask, full_batch=False, batch_size=B)
+    assert len(mini["batches"]) == int(z["mini_batches"])
+    for b, rec in enumerate(mini["batches"]):
+        node_map = rp.TensorMap(d.num_nodes)
+        node_map.update(rec["all_nodes"])
+        for h, hop in enumerate(rec["hops"]):
+            assert torch.equal(node_map.map(hop["block_edges"]), _t(z[f"mini_b{b}_edges{h}"])), (b, h)
+        ref = z[f"mini_b{b}_logits"]
+        assert np.allclose(rec["logits"].numpy(), ref, rtol=0, atol=1e-5 * np.abs(ref).max())
+    assert mini["accuracy"] == pytest.approx(float(z["mini_accuracy"]), abs=1e-12)
+    assert mini["f1"] == pytest.approx(float(z["mini_f1"]), abs=1e-12)
+
+
+@pytest.mark.skipif(not ref_import.reference_available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("name,seed,B,k,hops", [("tiny", 3, 32, 8, 2), ("small", 0, 200, 32, 3), ("cora", 1, 512, 16, 2)])
+def test_oracle_evaluate_matches_live_reference_eval(name, seed, B, k, hops):
+    """The reference's own ``evaluate`` imported live (oracle/ref_import.py::load_reference_eval), full-batch and mini-batch,
+    against ``reference_evaluate`` on the same models: scores equal, and every logit the reference's ``gcn_c`` call produced
+    equal bit for bit (same CPU arithmetic on the same blocks in the same order)."""
+    import argparse
+    mod, ru = ref_import.load_reference_eval()
+    d, st = _eval_state(name, seed, k, hops)
+    args = argparse.Namespace(sampling_hops=hops, use_indicators=True, num_samples=k)
+    adj = ref_import.reference_adjacency(d.edge_index, d.num_nodes)
+    for mask in (d.test_mask, d.val_mask):
+        for full in (True, False):
+            loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(mask.nonzero().squeeze(1)), batch_size=B)
+            rc, rg = ref_import.RecordingModule(st.gcn_c), ref_import.RecordingModule(st.gcn_gf)
+            acc, f1 = mod.evaluate(rc, rg, d, args, adj, ru.TensorMap(size=d.num_nodes), hops + 1, torch.device("cpu"),
+                                   mask=mask, eval_on_cpu=True, loader=loader, full_batch=full)
+            o = rp.reference_evaluate(st, mask, full_batch=full, batch_size=B)
+            assert o["accuracy"] == pytest.approx(acc, abs=1e-12) and o["f1"] == pytest.approx(f1, abs=1e-12)
+            if full:
+                assert torch.equal(rc.calls[0]["logits"], o["logits"])
+            else:
+                assert len(rc.calls) == len(o["batches"]) and len(rg.calls) == hops * len(rc.calls)
+                for c, b in zip(rc.calls, o["batches"]):
+                    assert torch.equal(c["logits"], b["logits"])
+                    assert torch.equal(c["x"], st.x[b["all_nodes"]])
