@@ -110,3 +110,116 @@ class RecordingModule(torch.nn.Module):
         ei = [e.clone() for e in edge_index] if isinstance(edge_index, list) else edge_index.clone()
         self.calls.append({"x": x.clone(), "edge_index": ei, "logits": out[0].clone()})
         return out
+
+
+class _SparseShim:
+    """``sp`` as main.py sees it: ``csr_matrix`` returns the CSR wrapped in :class:`TensorIndexCSR` (tensor indices on
+    scipy >= 1.14) and accepts a torch ``edge_index`` as the (row, col) pair like scipy 1.13 did (main.py:134-136)."""
+
+    @staticmethod
+    def csr_matrix(arg1, *a, **k):
+        if isinstance(arg1, tuple) and len(arg1) == 2 and isinstance(arg1[1], torch.Tensor):
+            arg1 = (arg1[0], arg1[1].cpu().numpy())
+        return TensorIndexCSR(sp.csr_matrix(arg1, *a, **k))
+
+
+class WandbStub:
+    """Stands in for ``wandb`` (not installed): ``init`` is a no-op, ``log`` keeps every dict train() logs."""
+
+    def __init__(self):
+        self.logged = []
+
+    def init(self, **kw):
+        return None
+
+    def log(self, d):
+        self.logged.append(dict(d))
+
+
+def load_reference_train(get_data, gcn_factory):
+    """The reference's own ``train(args)`` (main.py:57-340) as a callable.  main.py trains at import time (main.py:342-364),
+    so only its import statements, the ``device`` assignment and the ``train`` FunctionDef are executed, verbatim from the AST
+    of /root/reference/main.py.  Bound while its imports run (none of them installed here or usable offline):
+      wandb -> :class:`WandbStub` (returned);  tap.Tap -> object;  modules.data.get_data -> ``get_data`` (synthetic data);
+      modules.gcn.GCN -> ``gcn_factory`` (the oracle's GCN restatement: PyG is absent);  modules.utils, eval -> the
+      reference's own modules;  sp.csr_matrix -> :class:`_SparseShim` (index-type shim only).
+    Every statement of the batch loop that then runs is the reference's."""
+    import ast
+    import types
+    ev, ru = load_reference_eval()
+    src = open(os.path.join(REFERENCE_ROOT, "main.py")).read()
+    tree = ast.parse(src)
+    keep = []
+    for node in tree.body:
+        if isinstance(node, (ast.Import, ast.ImportFrom)):
+            keep.append(node)
+        elif isinstance(node, ast.Assign) and len(node.targets) == 1 and getattr(node.targets[0], "id", "") == "device":
+            keep.append(node)
+        elif isinstance(node, ast.FunctionDef) and node.name == "train":
+            keep.append(node)
+    assert any(isinstance(n, ast.FunctionDef) for n in keep), "main.py: def train not found"
+    wb = WandbStub()
+    wandb_mod = types.ModuleType("wandb")
+    wandb_mod.init, wandb_mod.log = wb.init, wb.log
+    tap_mod = types.ModuleType("tap")
+    tap_mod.Tap = object
+    pkg = types.ModuleType("modules")
+    data_mod = types.ModuleType("modules.data")
+    data_mod.get_data = get_data
+    gcn_mod = types.ModuleType("modules.gcn")
+    gcn_mod.GCN = gcn_factory
+    pkg.utils, pkg.data, pkg.gcn = ru, data_mod, gcn_mod
+    names = {"wandb": wandb_mod, "tap": tap_mod, "modules": pkg, "modules.utils": ru, "modules.data": data_mod,
+             "modules.gcn": gcn_mod, "eval": ev}
+    saved = {k: sys.modules.get(k) for k in names}
+    sys.modules.update(names)
+    ns = {"__name__": "grapes_reference_main", "Arguments": object}
+    try:
+        exec(compile(ast.Module(body=keep, type_ignores=[]), os.path.join(REFERENCE_ROOT, "main.py"), "exec"), ns)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    ns["sp"] = _SparseShim
+    return ns["train"], wb
+
+
+def run_reference_train(data, *, weight_seed: int, rng_seed: int, batch_size: int, num_samples: int, sampling_hops: int,
+                        max_epochs: int = 1, **over):
+    """Runs the reference's own ``train(args)`` (see :func:`load_reference_train`) on ``data`` with the oracle's GCN modules
+    initialised from ``torch.Generator().manual_seed(weight_seed)`` in the order main.py creates them (gcn_c, gcn_gf, gcn_z,
+    main.py:107-112 -- the order OracleState uses) and the global RNG seeded with ``rng_seed`` right before the call (Gumbel
+    noise, utils.py:40-41).  Returns (test_f1, the per-batch dicts train() logged, [gcn_c, gcn_gf, gcn_z])."""
+    import argparse
+    from . import reference_port as rp
+    gen = torch.Generator().manual_seed(weight_seed)
+    made = []
+
+    def factory(in_features, hidden_dims, dropout=0.):
+        m = rp.OracleGCN(in_features, hidden_dims, dropout, generator=gen)
+        made.append(m)
+        return m
+
+    train, wb = load_reference_train(lambda **kw: (data, data.num_features, data.num_classes), factory)
+
+    class Args(argparse.Namespace):
+        def as_dict(self):
+            return dict(vars(self))
+
+    args = Args(dataset="synthetic", sampling_hops=sampling_hops, num_samples=num_samples, use_indicators=True, lr_gf=1e-4,
+                lr_gc=1e-3, loss_coef=1e4, log_z_init=0., reg_param=0., dropout=0., model_type="gcn", hidden_dim=256,
+                embed_nodes=False, node_emb_dim=64, max_epochs=max_epochs, batch_size=batch_size, eval_frequency=5,
+                eval_on_cpu=True, eval_full_batch=True, random_sampling=False, runs=1, split_id=0, seed=0, notes=None,
+                log_wandb=False, config_file=None, reinforce_baseline=False)
+    for k, v in over.items():
+        assert hasattr(args, k), k
+        setattr(args, k, v)
+    torch.manual_seed(rng_seed)
+    test_f1, *_ = train(args)
+    logs = [l for l in wb.logged if "batch_loss_c" in l]
+    stats = [l for l in wb.logged if "batch_loss_c" not in l and "test_f1" not in l and "epoch" not in l]
+    for l, s in zip(logs, stats):
+        l["stats"] = s
+    return float(test_f1), logs, made

@@ -31,9 +31,17 @@ Pinning status:
     equal bit for bit) and against the committed tests/golden/eval_*.npz produced by that function (evaluation blocks
     bit-exact, logits, scores).  The models inside are this file's GCN restatement, so this pins the evaluation LOOP
     (deterministic top-k, evaluation-direction slice, relabelling, batching, scores), not GCNConv.
-  * GCNConv / gcn_norm, losses, gradients: "parity unpinned" by the reference
-    (it has no tests and PyG cannot be installed here); pinned only by the dense
-    closed form and a hand-computed 4-node example.
+  * the batch loop as a whole (``reference_step``, main.py:161-291: hop loop, both losses, autograd backward, both Adam
+    optimisers): PINNED against the reference's own ``train(args)`` executed live from /root/reference/main.py
+    (oracle/ref_import.py::load_reference_train runs the file's import statements and its ``train`` FunctionDef verbatim;
+    wandb / tap / the dataset loader are stand-ins, the GCN class is this file's restatement) --
+    tests/test_oracle.py::test_oracle_step_matches_live_reference_train: trajectory balance, REINFORCE, random sampling,
+    reg_param / log_z_init / loss_coef, multi-label; every batch's loss_c / loss_gfn / log_z / sum of log-probs and sampler
+    statistics equal bit for bit, the weights after the epoch to 1e-7, the test score equal -- and against the committed
+    tests/golden/train_*.npz produced by that function.
+  * the arithmetic INSIDE GCNConv / gcn_norm: "parity unpinned" by the reference (it has no tests and PyG cannot be
+    installed here); pinned only by the dense closed form and a hand-computed 4-node example.  Every live comparison
+    above runs the reference's loop on THIS restatement of GCNConv.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 reference legs may import this module.

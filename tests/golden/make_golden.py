@@ -2,7 +2,7 @@
 /root/reference/modules/utils.py (through the scipy tensor-index shim of oracle/ref_import.py) and runs
 its own get_neighborhoods / slice_adjacency / TensorMap / sample_neighborhoods_from_probs and the mask
 dedup statements of main.py:183-195 on seeded synthetic graphs; and /root/reference/eval.py's own ``evaluate``
-(full-batch and mini-batch) for the eval_*.npz fixtures.  Run in the build container only
+(full-batch and mini-batch) for the eval_*.npz fixtures and /root/reference/main.py's own ``train`` for train_*.npz.  Run in the build container only
 (the GPU box has no /root/reference); the .npz outputs are committed.
 
     python tests/golden/make_golden.py
@@ -131,6 +131,41 @@ def main_eval():
         print("wrote", path, os.path.getsize(path), "bytes")
 
 
+TRAIN_CASES = {                     # name -> (graph, seed, batch, k, hops, data overrides, argument overrides)
+    "tb":        ("tiny", 0, 32, 8, 2, {}, {}),
+    "reinforce": ("tiny", 1, 50, 4, 3, {}, {"reinforce_baseline": True}),
+    "random":    ("tiny", 2, 32, 8, 2, {}, {"random_sampling": True}),
+    "reg_logz":  ("tiny", 3, 40, 6, 2, {}, {"reg_param": 0.1, "log_z_init": 0.7, "loss_coef": 100.0}),
+    "multilabel": ("tiny", 4, 32, 8, 2, {"multilabel": True}, {}),
+}
+
+
+def main_train():
+    """train_*.npz: the reference's OWN ``train(args)`` (main.py:57-340, executed live through
+    oracle/ref_import.py::load_reference_train) for one epoch on seeded synthetic graphs: every batch's loss_c / loss_gfn /
+    log_z / sum of log-probs as train() logged them, the weights of gcn_c / gcn_gf / gcn_z after the epoch, the test score.
+    GCN modules: the oracle's restatement (PyG is absent); global RNG seeded right before the call; one CPU thread."""
+    import json
+    torch.set_num_threads(1)
+    for case, (name, seed, B, k, hops, dover, over) in TRAIN_CASES.items():
+        d = make_synth(name, seed=seed, **dover)
+        test_f1, logs, nets = ref_import.run_reference_train(d, weight_seed=seed + 100, rng_seed=4242 + seed, batch_size=B,
+                                                             num_samples=k, sampling_hops=hops, **over)
+        out = {"case": case, "name": name, "seed": seed, "B": B, "k": k, "hops": hops,
+               "data_overrides": json.dumps(dover), "arg_overrides": json.dumps(over), "test_f1": test_f1,
+               "loss_c": np.array([l["batch_loss_c"] for l in logs], np.float64),
+               "loss_gfn": np.array([float(l["batch_loss_gfn"]) for l in logs], np.float64),
+               "log_z": np.array([float(l["log_z"].detach()) for l in logs], np.float64),
+               "neg_log_probs": np.array([float(l["-log_probs"].detach()) for l in logs], np.float64)}
+        for key, net in zip(("gcn_c", "gcn_gf", "gcn_z"), nets):
+            for n, p in net.named_parameters():
+                out[f"w_{key}.{n}"] = p.detach().numpy()
+        path = os.path.join(HERE, f"train_{case}.npz")
+        np.savez_compressed(path, **out)
+        print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
     main()
     main_eval()
+    main_train()

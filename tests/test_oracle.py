@@ -19,6 +19,16 @@ def _t(a):
     return torch.from_numpy(np.asarray(a))
 
 
+@pytest.fixture
+def single_thread():
+    """One CPU thread: scatter-adds / reductions run in a fixed order, so two runs of the same arithmetic agree bit for
+    bit and a live-reference comparison can be exact."""
+    threads = torch.get_num_threads()
+    torch.set_num_threads(1)
+    yield
+    torch.set_num_threads(threads)
+
+
 def test_tensormap_docstring_golden():
     """utils.py:104-108 -- the only known-answer vector the reference holds."""
     z = np.load(os.path.join(GOLDEN, "tensormap_docstring.npz"))
@@ -260,7 +270,7 @@ def test_oracle_evaluate_matches_reference_golden(path):
 
 @pytest.mark.skipif(not ref_import.reference_available(), reason="/root/reference not present (GPU box)")
 @pytest.mark.parametrize("name,seed,B,k,hops", [("tiny", 3, 32, 8, 2), ("small", 0, 200, 32, 3), ("cora", 1, 512, 16, 2)])
-def test_oracle_evaluate_matches_live_reference_eval(name, seed, B, k, hops):
+def test_oracle_evaluate_matches_live_reference_eval(single_thread, name, seed, B, k, hops):
     """The reference's own ``evaluate`` imported live (oracle/ref_import.py::load_reference_eval), full-batch and mini-batch,
     against ``reference_evaluate`` on the same models: scores equal, and every logit the reference's ``gcn_c`` call produced
     equal bit for bit (same CPU arithmetic on the same blocks in the same order)."""
@@ -284,3 +294,89 @@ def test_oracle_evaluate_matches_live_reference_eval(name, seed, B, k, hops):
                 for c, b in zip(rc.calls, o["batches"]):
                     assert torch.equal(c["logits"], b["logits"])
                     assert torch.equal(c["x"], st.x[b["all_nodes"]])
+
+
+TRAIN_CASES = {                     # name -> (graph, seed, batch, k, hops, data overrides, argument overrides)
+    "tb":        ("tiny", 0, 32, 8, 2, {}, {}),
+    "reinforce": ("tiny", 1, 50, 4, 3, {}, {"reinforce_baseline": True}),
+    "random":    ("tiny", 2, 32, 8, 2, {}, {"random_sampling": True}),
+    "reg_logz":  ("tiny", 3, 40, 6, 2, {}, {"reg_param": 0.1, "log_z_init": 0.7, "loss_coef": 100.0}),
+    "multilabel": ("tiny", 4, 32, 8, 2, {"multilabel": True}, {}),
+    "small":     ("small", 1, 512, 32, 3, {}, {}),
+}
+
+
+def _oracle_epoch(d, seed, B, k, hops, over, rng_seed, epochs=1):
+    """The oracle's batch loop with the global RNG consumed exactly as main.py consumes it: one DataLoader iterator per
+    epoch (its base seed is drawn from the global generator, main.py:126,157) and the Gumbel draws of utils.py:40-41."""
+    st = rp.OracleState(d, sampling_hops=hops, num_samples=k, seed=seed + 100, dtype=torch.float32, **over)
+    torch.manual_seed(rng_seed)
+    tr = d.train_mask.nonzero().squeeze(1)
+    recs = []
+    for _ in range(epochs):
+        for batch in torch.utils.data.DataLoader(torch.utils.data.TensorDataset(tr), batch_size=B):
+            recs.append(rp.reference_step(st, batch[0], stable_ties=False))
+    return st, recs
+
+
+def _flat_weights(nets):
+    return {f"{key}.{n}": p.detach().clone() for key, net in zip(("gcn_c", "gcn_gf", "gcn_z"), nets)
+            for n, p in net.named_parameters()}
+
+
+@pytest.mark.skipif(not ref_import.reference_available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("case", sorted(TRAIN_CASES))
+def test_oracle_step_matches_live_reference_train(single_thread, case):
+    """The reference's OWN ``train(args)`` (main.py:57-340: batch loop, hop loop, both losses, autograd backward, both Adam
+    optimisers, final evaluation) executed live from /root/reference/main.py (oracle/ref_import.py::load_reference_train)
+    against the oracle's ``reference_step`` on the same data, initial weights and RNG stream: every batch's loss_c / loss_gfn /
+    log_z / sum of log-probs and sampler statistics equal BIT FOR BIT, the weights of all three networks after the epoch equal
+    to 1e-7 (autograd accumulates two of them in another order), the test score equal.  Pins SURVEY.md section 8 rows a2-a13
+    of the oracle to the reference itself -- except the arithmetic inside GCNConv, which is the oracle's restatement in both
+    runs (torch_geometric is absent)."""
+    name, seed, B, k, hops, dover, over = TRAIN_CASES[case]
+    d = make_synth(name, seed=seed, **dover)
+    rng_seed = 4242 + seed
+    test_f1, logs, nets = ref_import.run_reference_train(d, weight_seed=seed + 100, rng_seed=rng_seed, batch_size=B,
+                                                         num_samples=k, sampling_hops=hops, **over)
+    st, recs = _oracle_epoch(d, seed, B, k, hops, over, rng_seed)
+    assert len(recs) == len(logs) and len(recs) >= 2
+    for r, l in zip(recs, logs):
+        assert float(r["loss_c"]) == l["batch_loss_c"]
+        assert float(r["loss_gfn"]) == float(l["batch_loss_gfn"])
+        assert float(r["log_z"]) == float(l["log_z"].detach())
+        assert -float(r["tot_log_prob"]) == float(l["-log_probs"].detach())
+        for h, hop in enumerate(r["hops"]):
+            for key, v in (hop["stats"] or {}).items():
+                assert float(v) == float(l["stats"][f"{key}_{h}"]), (h, key)
+    ref_w, got_w = _flat_weights(nets), _flat_weights((st.gcn_c, st.gcn_gf, st.gcn_z))
+    for key in ref_w:
+        assert torch.allclose(got_w[key], ref_w[key], rtol=0, atol=1e-7 * float(ref_w[key].abs().max())), key
+    multilabel = d.y.dim() == 2
+    o = rp.reference_evaluate(st, d.test_mask, full_batch=True)
+    assert o["f1"] == pytest.approx(test_f1, abs=1e-12) and (multilabel or 0.0 < test_f1 < 1.0)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "train_*.npz"))))
+def test_oracle_step_matches_reference_train_golden(single_thread, path):
+    """The fixtures hold what the reference's OWN ``train(args)`` logged and left behind (tests/golden/make_golden.py::
+    main_train); the oracle's batch loop must reproduce the losses of every batch, the weights after the epoch and the test
+    score from the same seeds (the RNG stream and the initial weights are functions of the seeds)."""
+    import json
+    z = np.load(path)
+    name, seed, B, k, hops = str(z["name"]), int(z["seed"]), int(z["B"]), int(z["k"]), int(z["hops"])
+    dover, over = json.loads(str(z["data_overrides"])), json.loads(str(z["arg_overrides"]))
+    d = make_synth(name, seed=seed, **dover)
+    st, recs = _oracle_epoch(d, seed, B, k, hops, over, 4242 + seed)
+    assert len(recs) == len(z["loss_c"])
+    for key, ref in (("loss_c", z["loss_c"]), ("loss_gfn", z["loss_gfn"]), ("log_z", z["log_z"])):
+        got = np.array([float(r[key]) for r in recs])
+        assert np.allclose(got, ref, rtol=1e-6, atol=1e-7), key
+    got = np.array([-float(r["tot_log_prob"]) for r in recs])
+    assert np.allclose(got, z["neg_log_probs"], rtol=1e-6, atol=1e-7)
+    for key, net in (("gcn_c", st.gcn_c), ("gcn_gf", st.gcn_gf), ("gcn_z", st.gcn_z)):
+        for n, p in net.named_parameters():
+            ref = z[f"w_{key}.{n}"]
+            assert np.abs(p.detach().numpy() - ref).max() <= 1e-6 * max(np.abs(ref).max(), 1e-30), (key, n)
+    o = rp.reference_evaluate(st, d.test_mask, full_batch=True)
+    assert o["f1"] == pytest.approx(float(z["test_f1"]), abs=1e-12)
