@@ -380,3 +380,59 @@ def test_oracle_step_matches_reference_train_golden(single_thread, path):
             assert np.abs(p.detach().numpy() - ref).max() <= 1e-6 * max(np.abs(ref).max(), 1e-30), (key, n)
     o = rp.reference_evaluate(st, d.test_mask, full_batch=True)
     assert o["f1"] == pytest.approx(float(z["test_f1"]), abs=1e-12)
+
+
+@pytest.mark.skipif(not ref_import.reference_available(), reason="/root/reference not present (GPU box)")
+def test_oracle_multi_epoch_and_minibatch_eval_match_live_reference_train(single_thread):
+    """Four epochs of the reference's own ``train`` with its mid-training validation (main.py:313-326: epoch 4 with
+    eval_frequency 5) and the final test evaluation both in MINI-BATCH mode (eval_full_batch=False): the TensorMap and the
+    mask buffers are shared between training and evaluation (main.py:102,138-140), the loaders' base seeds come from the
+    global RNG.  Losses of all 16 batches bit-equal, final score equal to the oracle's mini-batch ``reference_evaluate``."""
+    name, seed, B, k, hops = "tiny", 6, 32, 8, 2
+    d = make_synth(name, seed=seed)
+    test_f1, logs, nets = ref_import.run_reference_train(d, weight_seed=seed + 100, rng_seed=4242 + seed, batch_size=B,
+                                                         num_samples=k, sampling_hops=hops, max_epochs=4,
+                                                         eval_full_batch=False)
+    st, recs = _oracle_epoch(d, seed, B, k, hops, {}, 4242 + seed, epochs=4)
+    assert len(recs) == len(logs) == 16
+    for r, l in zip(recs, logs):
+        assert float(r["loss_c"]) == l["batch_loss_c"] and float(r["loss_gfn"]) == float(l["batch_loss_gfn"])
+    assert logs[-1]["batch_loss_c"] < logs[0]["batch_loss_c"]                         # it trains
+    o = rp.reference_evaluate(st, d.test_mask, full_batch=False, batch_size=B, stable_ties=False)
+    assert o["f1"] == pytest.approx(test_f1, abs=1e-12)
+
+
+@pytest.mark.skipif(not ref_import.reference_available(), reason="/root/reference not present (GPU box)")
+def test_oracle_embed_nodes_matches_live_reference_train(single_thread):
+    """--embed_nodes (main.py:89-100,116): the reference draws the table with nn.init.normal_
+    from the global RNG, makes it an nn.Parameter inside optimizer_c and trains it.  Live ``train`` against the oracle with
+    the same draw: per-batch losses bit-equal, the TABLE after the epoch equal to 1e-7 (dense Adam: rows of earlier batches
+    keep moving), weights equal to 1e-7."""
+    import torch.nn as nn
+    name, seed, B, k, hops, dim = "tiny", 7, 32, 8, 2, 16
+    rng_seed = 4242 + seed
+    d_live = make_synth(name, seed=seed, features=False, F=dim)
+    assert d_live.x is None and d_live.num_features == dim
+    d_live.node_stores = [d_live]                         # main.py:99 `data.node_stores[0].x = embeddings`
+    test_f1, logs, nets = ref_import.run_reference_train(d_live, weight_seed=seed + 100, rng_seed=rng_seed, batch_size=B,
+                                                         num_samples=k, sampling_hops=hops, embed_nodes=True,
+                                                         node_emb_dim=dim)
+    assert isinstance(d_live.x, nn.Parameter) and tuple(d_live.x.shape) == (d_live.num_nodes, dim)
+    # the oracle: same seed, same draw order (the table first, main.py:96-97, then the loader's base seed and the noise)
+    d = make_synth(name, seed=seed, features=False, F=dim)
+    torch.manual_seed(rng_seed)
+    table = torch.FloatTensor(d.num_nodes, dim)
+    nn.init.normal_(table)
+    d.x = table
+    st = rp.OracleState(d, sampling_hops=hops, num_samples=k, seed=seed + 100, dtype=torch.float32, embed_nodes=True)
+    tr = d.train_mask.nonzero().squeeze(1)
+    recs = [rp.reference_step(st, b[0], stable_ties=False)
+            for b in torch.utils.data.DataLoader(torch.utils.data.TensorDataset(tr), batch_size=B)]
+    assert len(recs) == len(logs)
+    for r, l in zip(recs, logs):
+        assert float(r["loss_c"]) == l["batch_loss_c"] and float(r["loss_gfn"]) == float(l["batch_loss_gfn"])
+    assert not torch.equal(st.x.detach(), table)          # the table was trained ...
+    assert torch.allclose(st.x.detach(), d_live.x.detach(), rtol=0, atol=1e-7 * float(table.abs().max()))   # ... identically
+    ref_w, got_w = _flat_weights(nets), _flat_weights((st.gcn_c, st.gcn_gf, st.gcn_z))
+    for key in ref_w:
+        assert torch.allclose(got_w[key], ref_w[key], rtol=0, atol=1e-7 * float(ref_w[key].abs().max())), key
