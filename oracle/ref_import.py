@@ -96,6 +96,34 @@ def load_reference_eval():
     return mod, ru
 
 
+def load_reference_gcn(conv_factory):
+    """Import /root/reference/modules/gcn.py with ``torch_geometric.nn.GCNConv`` bound to ``conv_factory`` (PyG is absent;
+    the other convolutions it imports are never instantiated on this path).  The returned module's ``GCN`` is the
+    reference's own class -- layer list, which edge list feeds which layer, relu / dropout placement, ``(logits,
+    memory_alloc)`` return (gcn.py:9-42) -- over the oracle's restatement of the one GCNConv layer."""
+    import types
+    path = os.path.join(REFERENCE_ROOT, "modules", "gcn.py")
+    tg = types.ModuleType("torch_geometric")
+    tg.nn = types.ModuleType("torch_geometric.nn")
+    tg.nn.GCNConv = conv_factory
+    for other in ("GATConv", "GCN2Conv", "Linear", "PNAConv"):
+        setattr(tg.nn, other, object)
+    names = {"torch_geometric": tg, "torch_geometric.nn": tg.nn}
+    saved = {k: sys.modules.get(k) for k in names}
+    sys.modules.update(names)
+    try:
+        spec = importlib.util.spec_from_file_location("grapes_reference_gcn", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod
+
+
 class RecordingModule(torch.nn.Module):
     """Wraps a model handed to the reference's ``evaluate`` and keeps what it was called with and what it returned (the
     reference returns only (accuracy, f1); the per-batch blocks and logits are read off its ``gcn_c`` calls)."""
@@ -188,17 +216,19 @@ def load_reference_train(get_data, gcn_factory):
 
 def run_reference_train(data, *, weight_seed: int, rng_seed: int, batch_size: int, num_samples: int, sampling_hops: int,
                         max_epochs: int = 1, **over):
-    """Runs the reference's own ``train(args)`` (see :func:`load_reference_train`) on ``data`` with the oracle's GCN modules
-    initialised from ``torch.Generator().manual_seed(weight_seed)`` in the order main.py creates them (gcn_c, gcn_gf, gcn_z,
+    """Runs the reference's own ``train(args)`` (see :func:`load_reference_train`) on ``data`` with the reference's own ``GCN``
+    class over the oracle's GCNConv layer (:func:`load_reference_gcn`), the layers initialised from ``torch.Generator().manual_seed(weight_seed)`` in the order main.py creates them (gcn_c, gcn_gf, gcn_z,
     main.py:107-112 -- the order OracleState uses) and the global RNG seeded with ``rng_seed`` right before the call (Gumbel
     noise, utils.py:40-41).  Returns (test_f1, the per-batch dicts train() logged, [gcn_c, gcn_gf, gcn_z])."""
     import argparse
     from . import reference_port as rp
     gen = torch.Generator().manual_seed(weight_seed)
     made = []
+    # the reference's OWN GCN class (modules/gcn.py:9-42) over the oracle's GCNConv layer
+    ref_gcn = load_reference_gcn(lambda in_channels, out_channels: rp.OracleGCNConv(in_channels, out_channels, gen))
 
     def factory(in_features, hidden_dims, dropout=0.):
-        m = rp.OracleGCN(in_features, hidden_dims, dropout, generator=gen)
+        m = ref_gcn.GCN(in_features, hidden_dims=hidden_dims, dropout=dropout)
         made.append(m)
         return m
 

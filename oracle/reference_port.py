@@ -34,7 +34,8 @@ Pinning status:
   * the batch loop as a whole (``reference_step``, main.py:161-291: hop loop, both losses, autograd backward, both Adam
     optimisers): PINNED against the reference's own ``train(args)`` executed live from /root/reference/main.py
     (oracle/ref_import.py::load_reference_train runs the file's import statements and its ``train`` FunctionDef verbatim;
-    wandb / tap / the dataset loader are stand-ins, the GCN class is this file's restatement) --
+    wandb / tap / the dataset loader are stand-ins; the GCN class is the reference's own modules/gcn.py over this file's
+    one-layer GCNConv restatement) --
     tests/test_oracle.py::test_oracle_step_matches_live_reference_train: trajectory balance, REINFORCE, random sampling,
     reg_param / log_z_init / loss_coef, multi-label; every batch's loss_c / loss_gfn / log_z / sum of log-probs and sampler
     statistics equal bit for bit, the weights after the epoch to 1e-7, the test score equal -- and against the committed

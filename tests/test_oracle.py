@@ -436,3 +436,31 @@ def test_oracle_embed_nodes_matches_live_reference_train(single_thread):
     ref_w, got_w = _flat_weights(nets), _flat_weights((st.gcn_c, st.gcn_gf, st.gcn_z))
     for key in ref_w:
         assert torch.allclose(got_w[key], ref_w[key], rtol=0, atol=1e-7 * float(ref_w[key].abs().max())), key
+
+
+@pytest.mark.skipif(not ref_import.reference_available(), reason="/root/reference not present (GPU box)")
+def test_oracle_gcn_wiring_matches_live_reference_gcn_class(single_thread):
+    """modules/gcn.py:9-42 imported live (oracle/ref_import.py::load_reference_gcn; GCNConv bound to the oracle's layer):
+    the reference's own ``GCN`` -- layer list, ``edge_index[-i]`` for hidden layer i and ``edge_index[0]`` for the output
+    layer when a list is given, relu / dropout placement, tuple return -- against ``OracleGCN`` on the same weights, for a
+    single edge tensor, a per-layer list (2 and 3 layers) and in training mode with dropout (same RNG stream)."""
+    g = torch.Generator().manual_seed(3)
+    n, Fdim = 60, 9
+    x = torch.randn(n, Fdim, generator=g)
+    edges = [torch.randint(0, n, (2, m), generator=g) for m in (150, 90, 200)]
+    for hidden, p in (([16, 4], 0.0), ([16, 8, 4], 0.0), ([16, 4], 0.5)):
+        gen = torch.Generator().manual_seed(11)
+        ref_mod = ref_import.load_reference_gcn(lambda in_channels, out_channels: rp.OracleGCNConv(in_channels, out_channels, gen))
+        ref = ref_mod.GCN(Fdim, hidden_dims=hidden, dropout=p)
+        mine = rp.OracleGCN(Fdim, hidden, dropout=p, generator=torch.Generator().manual_seed(11))
+        assert [k for k, _ in ref.named_parameters()] == [k for k, _ in mine.named_parameters()]
+        for (_, a), (_, b) in zip(ref.named_parameters(), mine.named_parameters()):
+            assert torch.equal(a, b)
+        for ei in (edges[0], edges[:len(hidden)]):
+            for training in ((False, True) if p > 0 else (False,)):
+                ref.train(training); mine.train(training)
+                torch.manual_seed(5)
+                a, mem = ref(x, ei)
+                torch.manual_seed(5)
+                b, _ = mine(x, ei)
+                assert torch.equal(a, b) and isinstance(mem, float)
