@@ -214,8 +214,8 @@ def load_reference_train(get_data, gcn_factory):
     return ns["train"], wb
 
 
-def run_reference_train(data, *, weight_seed: int, rng_seed: int, batch_size: int, num_samples: int, sampling_hops: int,
-                        max_epochs: int = 1, **over):
+def run_reference_train(data, *, weight_seed: int, rng_seed: int, batch_size: int = 0, num_samples: int = 0,
+                        sampling_hops: int = 0, max_epochs: int = 1, args_obj=None, **over):
     """Runs the reference's own ``train(args)`` (see :func:`load_reference_train`) on ``data`` with the reference's own ``GCN``
     class over the oracle's GCNConv layer (:func:`load_reference_gcn`), the layers initialised from ``torch.Generator().manual_seed(weight_seed)`` in the order main.py creates them (gcn_c, gcn_gf, gcn_z,
     main.py:107-112 -- the order OracleState uses) and the global RNG seeded with ``rng_seed`` right before the call (Gumbel
@@ -246,6 +246,8 @@ def run_reference_train(data, *, weight_seed: int, rng_seed: int, batch_size: in
     for k, v in over.items():
         assert hasattr(args, k), k
         setattr(args, k, v)
+    if args_obj is not None:                 # e.g. grapes_b200.args.Arguments: the drop-in for main.py's Tap class
+        args = args_obj
     torch.manual_seed(rng_seed)
     test_f1, *_ = train(args)
     logs = [l for l in wb.logged if "batch_loss_c" in l]

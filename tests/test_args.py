@@ -48,3 +48,29 @@ def test_every_reference_config_file_parses():
     # configs/rl/flickr.txt:15 is malformed in the reference itself ("--runs=1 0")
     assert bad == ["configs/rl/flickr.txt"], bad
     assert len(REF_CONFIGS) == 32
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/main.py"), reason="/root/reference not present (GPU box)")
+def test_fields_and_defaults_match_the_live_reference_class():
+    """main.py:23-54 read from the reference's own source (AST of ``class Arguments(Tap)``): same field names in the same
+    order, same defaults."""
+    import ast
+    import dataclasses
+    tree = ast.parse(open("/root/reference/main.py").read())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "Arguments")
+    ref = [(n.target.id, ast.literal_eval(n.value)) for n in cls.body if isinstance(n, ast.AnnAssign)]
+    mine = [(f.name, f.default) for f in dataclasses.fields(Arguments)]
+    assert mine == ref and len(ref) == 27
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/main.py"), reason="/root/reference not present (GPU box)")
+def test_arguments_object_drives_the_live_reference_train():
+    """The drop-in ``Arguments`` is accepted by the reference's OWN ``train(args)`` (main.py:57-340 executed live, see
+    oracle/ref_import.py::load_reference_train): every attribute the loop reads, and ``as_dict()`` (main.py:61)."""
+    from grapes_b200.synth import make_synth
+    from oracle import ref_import
+    d = make_synth("tiny", seed=0)
+    a = Arguments.parse_args(["--dataset", "tiny", "--batch_size", "32", "--num_samples", "8", "--sampling_hops", "2",
+                              "--max_epochs", "1", "--eval_full_batch", "True"])
+    f1, logs, nets = ref_import.run_reference_train(d, weight_seed=100, rng_seed=4242, args_obj=a)
+    assert len(logs) == 4 and 0.0 < f1 < 1.0 and len(nets) == 3
