@@ -9,8 +9,9 @@ hoploop_*.npz  one batch of the hop loop through the drop-in callables (grapes_b
 eval_*.npz     grapes_b200.eval.evaluate (full-batch and mini-batch on the engine) with the fixture's weights: logits at 1e-5 of
                the reference run's fp32 logits, scores equal up to argmax flips of near-tied rows.
 
-This file sorts last on purpose: it was written after the round's GPU budget was spent (every call below follows the usage of
-an older, GPU-verified test)."""
+This file sorts last on purpose: it was written after the round's GPU budget was spent.  Every device call below follows the
+usage of an older, GPU-verified test, and both test bodies were dry-run on the CPU with the oracle's functions standing in for
+the device calls (fixture keys, shapes, index handling and the assertions themselves are exercised that way)."""
 import glob
 import os
 import types
