@@ -464,3 +464,39 @@ def test_oracle_gcn_wiring_matches_live_reference_gcn_class(single_thread):
                 torch.manual_seed(5)
                 b, _ = mine(x, ei)
                 assert torch.equal(a, b) and isinstance(mem, float)
+
+
+@pytest.mark.skipif(not ref_import.reference_available(), reason="/root/reference not present (GPU box)")
+def test_oracle_edge_cases_match_live_reference_utils():
+    """Edge cases the domain has: empty row lists, rows without neighbours, a self-loop, an empty
+    column set, duplicated ids in the row list, one candidate, k = 1, k >= n -- the reference's own functions against the
+    oracle's, bit for bit."""
+    ru = ref_import.load_reference_utils()
+    ei = torch.tensor([[0, 0, 1, 2, 4, 4, 6], [0, 2, 0, 1, 1, 2, 6]])           # nodes 3 and 5 have no out-edges; 0 and 6 loop
+    N = 7
+    adj_ref, adj = ref_import.reference_adjacency(ei, N), rp.build_adjacency(ei, N)
+    empty = torch.tensor([], dtype=torch.long)
+    for nodes in (empty, torch.tensor([3, 5]), torch.tensor([0, 3, 4]), torch.tensor([4, 0, 1, 2]), torch.tensor([6]),
+                  torch.tensor([4, 4, 0])):
+        a, b = ru.get_neighborhoods(nodes, adj_ref), rp.get_neighborhoods(nodes, adj)
+        assert a.shape == b.shape and torch.equal(a, b), nodes
+        for cols in (empty, torch.tensor([0, 1, 2]), torch.tensor([6, 2]), torch.arange(N)):
+            a, b = ru.slice_adjacency(adj_ref, nodes, cols), rp.slice_adjacency(adj, nodes, cols)
+            assert a.shape == b.shape and torch.equal(a, b), (nodes, cols)
+    g = torch.Generator().manual_seed(0)
+    for n, k in ((1, 1), (1, 4), (5, 1), (9, 9), (9, 8), (300, 299)):
+        logits = torch.randn(n, 1, generator=g)
+        nb = torch.arange(n) * 3 + 1
+        torch.manual_seed(n * 31 + k)
+        a = ru.sample_neighborhoods_from_probs(logits, nb, k)
+        torch.manual_seed(n * 31 + k)
+        b = rp.sample_neighborhoods_from_probs(logits, nb, k, stable_ties=False)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and a[2].keys() == b[2].keys(), (n, k)
+        for key in a[2]:
+            assert torch.equal(a[2][key], b[2][key]) or (torch.isnan(a[2][key]) and torch.isnan(b[2][key])), (n, k, key)
+    # TensorMap: update / map round trip incl. re-update with another key set (stale entries stay, like the reference's)
+    tm_a, tm_b = ru.TensorMap(size=N), rp.TensorMap(N)
+    for keys in (torch.tensor([5, 2, 6]), torch.tensor([0, 6])):
+        tm_a.update(keys); tm_b.update(keys)
+        assert torch.equal(tm_a.map(torch.arange(N)[keys]), tm_b.map(torch.arange(N)[keys]))
+        assert torch.equal(tm_a.values, tm_b.values)
