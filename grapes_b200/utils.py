@@ -2,8 +2,10 @@
 (/root/reference/modules/utils.py:13-134), backed by the C-ABI CUDA library.
 
 Same names, argument meaning, return ordering and error behaviour; ``adjacency`` is a
-:class:`grapes_b200.graph.DeviceGraph` instead of a scipy CSR.  Results live on the GPU (int64
-like the reference).  These wrappers read the data-dependent sizes back (one sync per call) --
+:class:`grapes_b200.graph.DeviceGraph` instead of a scipy CSR.  The work runs on the GPU; id tensors (int64 like the
+reference) are returned on the device of the id tensors passed in -- the reference's loop keeps its masks and id lists
+on the host (main.py:138-140,161-163) and indexes them with these results, so host ids in give host ids out -- and
+log-probs / logits stay on the GPU.  These wrappers read the data-dependent sizes back (one sync per call) --
 they exist for drop-in use and for parity tests; the training loop uses
 :class:`grapes_b200.engine.GrapesEngine`, which never leaves the device.
 """
@@ -59,7 +61,7 @@ def get_neighborhoods(nodes: Tensor, adjacency: DeviceGraph) -> Tensor:
     rows32 = _i32(nodes, adjacency.device)
     e_row, e_col, m, _, _ = _expand(adjacency, rows32)
     src = rows32.to(torch.int64)[e_row.to(torch.int64)]
-    return torch.stack([src, e_col.to(torch.int64)], dim=0)
+    return torch.stack([src, e_col.to(torch.int64)], dim=0).to(nodes.device)
 
 
 def slice_adjacency(adjacency: DeviceGraph, rows: Tensor, cols: Tensor) -> Tensor:
@@ -69,7 +71,7 @@ def slice_adjacency(adjacency: DeviceGraph, rows: Tensor, cols: Tensor) -> Tenso
     rows32, cols32 = _i32(rows, dev), _i32(cols, dev)
     e_row, e_col, m, cnt, _ = _expand(adjacency, rows32)
     if m == 0 or cols32.numel() == 0:
-        return torch.empty((2, 0), dtype=torch.int64, device=dev)
+        return torch.empty((2, 0), dtype=torch.int64, device=rows.device)
     bm = torch.zeros(adjacency.num_words, dtype=torch.int32, device=dev)
     cnt[2] = cols32.numel()
     L.grapes_bitmap_set(ctx, ptr(cols32), cnt.data_ptr() + 8, max(cols32.numel(), 1), ptr(bm), _stream())
@@ -79,7 +81,7 @@ def slice_adjacency(adjacency: DeviceGraph, rows: Tensor, cols: Tensor) -> Tenso
     L.grapes_slice_block(ctx, ptr(rows32), ptr(e_row), ptr(e_col), cnt.data_ptr() + 4, max(m, 1), ptr(bm),
                          ptr(out_src), ptr(out_dst), max(m, 1), cnt.data_ptr() + 12, ptr(ovf), _stream())
     e = int(cnt[3].item())
-    return torch.stack([out_src[:e].to(torch.int64), out_dst[:e].to(torch.int64)], dim=0)
+    return torch.stack([out_src[:e].to(torch.int64), out_dst[:e].to(torch.int64)], dim=0).to(rows.device)
 
 
 class TensorMap:

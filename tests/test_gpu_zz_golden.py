@@ -47,7 +47,9 @@ def test_hop_loop_callables_against_reference_golden(cuda_device, path):
         p = f"hop{hop}_"
         assert torch.equal(prev, _t(z[p + "prev"]))
         nb = get_neighborhoods(prev, g)                                                  # utils.py:74-82
+        assert nb.device == prev.device                                                  # host ids in -> host ids out
         assert torch.equal(nb.cpu(), _t(z[p + "neighborhoods"])), f"hop {hop}: neighborhoods"
+        nb = nb.to(dev)
         pm = torch.zeros(N, dtype=torch.bool, device=dev)
         bm = torch.zeros(N, dtype=torch.bool, device=dev)
         pm[prev.to(dev)] = True                                                          # main.py:183-190
