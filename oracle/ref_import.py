@@ -164,7 +164,7 @@ class WandbStub:
         self.logged.append(dict(d))
 
 
-def load_reference_train(get_data, gcn_factory):
+def load_reference_train(get_data, gcn_factory, utils_overrides=None):
     """The reference's own ``train(args)`` (main.py:57-340) as a callable.  main.py trains at import time (main.py:342-364),
     so only its import statements, the ``device`` assignment and the ``train`` FunctionDef are executed, verbatim from the AST
     of /root/reference/main.py.  Bound while its imports run (none of them installed here or usable offline):
@@ -175,6 +175,11 @@ def load_reference_train(get_data, gcn_factory):
     import ast
     import types
     ev, ru = load_reference_eval()
+    if utils_overrides:                       # e.g. this repo's host-side drop-ins (TensorMap, get_logger) inside the real loop
+        ru2 = types.ModuleType("modules.utils")
+        ru2.__dict__.update({k: v for k, v in ru.__dict__.items() if not k.startswith("__")})
+        ru2.__dict__.update(utils_overrides)
+        ru = ru2
     src = open(os.path.join(REFERENCE_ROOT, "main.py")).read()
     tree = ast.parse(src)
     keep = []
@@ -215,7 +220,7 @@ def load_reference_train(get_data, gcn_factory):
 
 
 def run_reference_train(data, *, weight_seed: int, rng_seed: int, batch_size: int = 0, num_samples: int = 0,
-                        sampling_hops: int = 0, max_epochs: int = 1, args_obj=None, **over):
+                        sampling_hops: int = 0, max_epochs: int = 1, args_obj=None, utils_overrides=None, **over):
     """Runs the reference's own ``train(args)`` (see :func:`load_reference_train`) on ``data`` with the reference's own ``GCN``
     class over the oracle's GCNConv layer (:func:`load_reference_gcn`), the layers initialised from ``torch.Generator().manual_seed(weight_seed)`` in the order main.py creates them (gcn_c, gcn_gf, gcn_z,
     main.py:107-112 -- the order OracleState uses) and the global RNG seeded with ``rng_seed`` right before the call (Gumbel
@@ -232,7 +237,7 @@ def run_reference_train(data, *, weight_seed: int, rng_seed: int, batch_size: in
         made.append(m)
         return m
 
-    train, wb = load_reference_train(lambda **kw: (data, data.num_features, data.num_classes), factory)
+    train, wb = load_reference_train(lambda **kw: (data, data.num_features, data.num_classes), factory, utils_overrides)
 
     class Args(argparse.Namespace):
         def as_dict(self):

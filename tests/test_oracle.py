@@ -500,3 +500,23 @@ def test_oracle_edge_cases_match_live_reference_utils():
         tm_a.update(keys); tm_b.update(keys)
         assert torch.equal(tm_a.map(torch.arange(N)[keys]), tm_b.map(torch.arange(N)[keys]))
         assert torch.equal(tm_a.values, tm_b.values)
+
+
+@pytest.mark.skipif(not ref_import.reference_available(), reason="/root/reference not present (GPU box)")
+def test_host_side_dropins_inside_the_live_reference_loop(single_thread):
+    """INTEGRATION.md section 1 (import-level drop-in), the part that needs no GPU: this repo's ``TensorMap`` and
+    ``get_logger`` (grapes_b200/utils.py, pure torch / logging) bound in place of the reference's inside the reference's OWN
+    ``train`` loop -- same losses on every batch, same weights, same score as the unmodified run."""
+    from grapes_b200.utils import TensorMap, get_logger
+    name, seed, B, k, hops = "tiny", 8, 32, 8, 2
+    d = make_synth(name, seed=seed)
+    kw = dict(weight_seed=seed + 100, rng_seed=4242 + seed, batch_size=B, num_samples=k, sampling_hops=hops, max_epochs=2,
+              eval_full_batch=False)
+    f1_a, logs_a, nets_a = ref_import.run_reference_train(d, **kw)
+    f1_b, logs_b, nets_b = ref_import.run_reference_train(d, utils_overrides={"TensorMap": TensorMap, "get_logger": get_logger},
+                                                          **kw)
+    assert len(logs_a) == len(logs_b) == 8 and f1_a == f1_b
+    for a, b in zip(logs_a, logs_b):
+        assert a["batch_loss_c"] == b["batch_loss_c"] and float(a["batch_loss_gfn"]) == float(b["batch_loss_gfn"])
+    for (ka, pa), (kb, pb) in zip(_flat_weights(nets_a).items(), _flat_weights(nets_b).items()):
+        assert ka == kb and torch.equal(pa, pb)
